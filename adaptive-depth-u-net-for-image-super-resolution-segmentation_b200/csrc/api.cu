@@ -1,0 +1,300 @@
+// extern "C" boundary of libb200unet.so (see include/b200_unet.h).
+#include <string.h>
+
+#include "common.cuh"
+
+namespace b200 {
+
+// ---- error plumbing -------------------------------------------------------------
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+int check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(B200_ERR_LAUNCH, "%s: %s", what, cudaGetErrorString(e));
+  return B200_OK;
+}
+
+// implemented in the kernel translation units
+int conv_simt_fprop(const b200_tensor*, const b200_filter*, const float*, const b200_tensor*, int, int, bool, cudaStream_t);
+int conv_simt_wgrad(const b200_tensor*, const b200_tensor*, int, float*, cudaStream_t);
+int filter_pack(const void*, void*, int, int, int, int, cudaStream_t);
+bool conv_tc_supported(const b200_tensor*, int, int, const b200_tensor*, int);
+int conv_tc_launch(const b200_tensor*, const void*, int, int, int, const float*, const b200_tensor*, int, int, cudaStream_t);
+int umma_probe(const void*, int, const void*, int, int, int, int, float*, cudaStream_t);
+bool wgrad_tc_supported(const b200_tensor*, const b200_tensor*, int);
+size_t wgrad_tc_workspace(const b200_tensor*, const b200_tensor*);
+int wgrad_tc_launch(const b200_tensor*, const b200_tensor*, float*, void*, size_t, cudaStream_t);
+int layernorm_fwd(const b200_tensor*, const float*, const float*, float, int, const b200_tensor*, float*, float*, cudaStream_t);
+int layernorm_bwd(const b200_tensor*, const b200_tensor*, const float*, const float*, const float*, const float*, int,
+                  const b200_tensor*, float*, float*, float*, cudaStream_t);
+int bias_act_bwd(const b200_tensor*, const b200_tensor*, int, const b200_tensor*, float*, cudaStream_t);
+int batchnorm_fwd_train(const b200_tensor*, const float*, const float*, float, float, int, const b200_tensor*, float*,
+                        float*, float*, float*, double*, cudaStream_t);
+int batchnorm_fwd_infer(const b200_tensor*, const float*, const float*, float, int, const float*, const float*,
+                        const b200_tensor*, cudaStream_t);
+int batchnorm_bwd(const b200_tensor*, const b200_tensor*, const float*, const float*, const float*, const float*, int,
+                  const b200_tensor*, float*, float*, float*, double*, cudaStream_t);
+int resize_extent(int, float);
+int resample_taps(int, int, int);
+int resample_plan(int, int, int, int32_t*, float*, int);
+int resample_plan_transpose(int, int, int, const int32_t*, const float*, int32_t*, float*, int);
+int resample2d(const b200_tensor*, const b200_tensor*, const int32_t*, const float*, int, const int32_t*, const float*,
+               int, int, cudaStream_t);
+int maxpool2_fwd(const b200_tensor*, const b200_tensor*, cudaStream_t);
+int maxpool2_bwd(const b200_tensor*, const b200_tensor*, const b200_tensor*, const b200_tensor*, int, cudaStream_t);
+int clipadd_fwd(const b200_tensor*, const b200_tensor*, const b200_tensor*, cudaStream_t);
+int clipadd_bwd(const b200_tensor*, const b200_tensor*, const b200_tensor*, const b200_tensor*, cudaStream_t);
+int sr_loss(const b200_tensor*, const b200_tensor*, int, float, float, float*, const b200_tensor*, float*, cudaStream_t);
+int bce_dice_loss(const b200_tensor*, const b200_tensor*, float, float, float, float*, const b200_tensor*, float*,
+                  cudaStream_t);
+int softmax_fwd(const b200_tensor*, const b200_tensor*, cudaStream_t);
+int softmax_ce_loss(const b200_tensor*, const int32_t*, float, float*, const b200_tensor*, float*, cudaStream_t);
+int adam_advance(int32_t*, cudaStream_t);
+int adam_step(float*, const float*, float*, float*, size_t, const float*, const int32_t*, void*, cudaStream_t);
+int cast(const void*, int, void*, int, size_t, cudaStream_t);
+int copy_tensor(const b200_tensor*, const b200_tensor*, cudaStream_t);
+int scale_inplace(float*, size_t, float, cudaStream_t);
+int convT2_fprop(const b200_tensor*, const void*, const float*, int, const b200_tensor*, cudaStream_t);
+int convT2_dgrad(const b200_tensor*, const void*, int, const b200_tensor*, cudaStream_t);
+int convT2_wgrad(const b200_tensor*, const b200_tensor*, float*, float*, cudaStream_t);
+
+}  // namespace b200
+
+using namespace b200;
+
+#define ST(s) reinterpret_cast<cudaStream_t>(s)
+#define REQ_T(t, name) B200_REQUIRE(valid_tensor(t), B200_ERR_BAD_ARG, "%s: invalid tensor '%s'", __func__, name)
+
+extern "C" {
+
+const char* b200_version(void) { return "b200unet 0.1.0 (sm_100a)"; }
+const char* b200_last_error(void) { return g_err; }
+
+int b200_device_info(int* sms, int* major, int* minor) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return fail(B200_ERR_LAUNCH, "cudaGetDevice: %s", cudaGetErrorString(e));
+  cudaDeviceProp prop;
+  e = cudaGetDeviceProperties(&prop, dev);
+  if (e != cudaSuccess) return fail(B200_ERR_LAUNCH, "cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+  if (sms) *sms = prop.multiProcessorCount;
+  if (major) *major = prop.major;
+  if (minor) *minor = prop.minor;
+  return B200_OK;
+}
+
+int b200_conv2d_fprop(const b200_tensor* x, const b200_filter* f, const float* bias, const b200_tensor* y, int act,
+                      int algo, void* stream) {
+  REQ_T(x, "x"); REQ_T(y, "y");
+  B200_REQUIRE(f && f->hwio, B200_ERR_BAD_ARG, "conv2d_fprop: filter missing");
+  B200_REQUIRE(x->c == f->cin && y->c == f->cout && x->n == y->n && x->h == y->h && x->w == y->w, B200_ERR_BAD_ARG,
+               "conv2d_fprop: shapes x[%d,%d,%d,%d] y[%d,%d,%d,%d] filter cin=%d cout=%d disagree", x->n, x->h, x->w,
+               x->c, y->n, y->h, y->w, y->c, f->cin, f->cout);
+  const bool tc_ok = f->ohwi && f->kh == 3 && f->kw == 3 && f->dtype == B200_BF16 &&
+                     (act == B200_ACT_NONE || act == B200_ACT_RELU) && conv_tc_supported(x, f->cin, f->cout, y, 3);
+  if (algo == B200_ALGO_TCGEN05 || (algo == B200_ALGO_AUTO && tc_ok)) {
+    B200_REQUIRE(tc_ok, B200_ERR_UNSUPPORTED, "conv2d_fprop: tcgen05 path does not support this shape/dtype");
+    return conv_tc_launch(x, f->ohwi, f->cin, f->cout, 0, bias, y, act, 0, ST(stream));
+  }
+  return conv_simt_fprop(x, f, bias, y, act, 0, false, ST(stream));
+}
+
+int b200_conv2d_dgrad(const b200_tensor* dy, const b200_filter* f, const b200_tensor* dx, int accumulate, int algo,
+                      void* stream) {
+  REQ_T(dy, "dy"); REQ_T(dx, "dx");
+  B200_REQUIRE(f && f->hwio, B200_ERR_BAD_ARG, "conv2d_dgrad: filter missing");
+  B200_REQUIRE(dy->c == f->cout && dx->c == f->cin && dx->n == dy->n && dx->h == dy->h && dx->w == dy->w,
+               B200_ERR_BAD_ARG, "conv2d_dgrad: shapes disagree with filter cin=%d cout=%d", f->cin, f->cout);
+  // dgrad is a convolution of dy (K = cout) producing cin channels; its B operand [tap][cin][cout]
+  // is the HWIO kernel itself, read with the tap order reversed.
+  const bool tc_ok = f->kh == 3 && f->kw == 3 && f->dtype == B200_BF16 && conv_tc_supported(dy, f->cout, f->cin, dx, 3);
+  if (algo == B200_ALGO_TCGEN05 || (algo == B200_ALGO_AUTO && tc_ok)) {
+    B200_REQUIRE(tc_ok, B200_ERR_UNSUPPORTED, "conv2d_dgrad: tcgen05 path does not support this shape/dtype");
+    return conv_tc_launch(dy, f->hwio, f->cout, f->cin, 1, nullptr, dx, B200_ACT_NONE, accumulate, ST(stream));
+  }
+  return conv_simt_fprop(dy, f, nullptr, dx, B200_ACT_NONE, accumulate, true, ST(stream));
+}
+
+size_t b200_conv2d_wgrad_workspace(const b200_tensor* x, const b200_tensor* dy, int kh, int kw, int algo) {
+  if (algo == B200_ALGO_SIMT || kh != 3 || kw != 3) return 0;
+  if (!wgrad_tc_supported(x, dy, kh)) return 0;
+  return wgrad_tc_workspace(x, dy);
+}
+
+int b200_conv2d_wgrad(const b200_tensor* x, const b200_tensor* dy, int kh, int kw, float* dw, void* ws, size_t ws_bytes,
+                      int algo, void* stream) {
+  REQ_T(x, "x"); REQ_T(dy, "dy");
+  B200_REQUIRE(dw, B200_ERR_BAD_ARG, "conv2d_wgrad: dw is NULL");
+  B200_REQUIRE(kh == kw && x->n == dy->n && x->h == dy->h && x->w == dy->w, B200_ERR_BAD_ARG,
+               "conv2d_wgrad: shapes disagree");
+  const bool tc_ok = wgrad_tc_supported(x, dy, kh);
+  if (algo == B200_ALGO_TCGEN05 || (algo == B200_ALGO_AUTO && tc_ok)) {
+    B200_REQUIRE(tc_ok, B200_ERR_UNSUPPORTED, "conv2d_wgrad: tcgen05 path does not support this shape/dtype");
+    return wgrad_tc_launch(x, dy, dw, ws, ws_bytes, ST(stream));
+  }
+  return conv_simt_wgrad(x, dy, kh, dw, ST(stream));
+}
+
+int b200_filter_pack(const void* hwio, void* ohwi, int kh, int kw, int cin, int cout, int dtype, void* stream) {
+  B200_REQUIRE(hwio && ohwi && kh > 0 && kw > 0 && cin > 0 && cout > 0, B200_ERR_BAD_ARG, "filter_pack: bad argument");
+  return filter_pack(hwio, ohwi, kh * kw, cin, cout, dtype, ST(stream));
+}
+
+int b200_convT2x2_fprop(const b200_tensor* x, const void* k, const float* bias, int cout, const b200_tensor* y, void* s) {
+  REQ_T(x, "x"); REQ_T(y, "y");
+  return convT2_fprop(x, k, bias, cout, y, ST(s));
+}
+int b200_convT2x2_dgrad(const b200_tensor* dy, const void* k, int cout, const b200_tensor* dx, void* s) {
+  REQ_T(dy, "dy"); REQ_T(dx, "dx");
+  return convT2_dgrad(dy, k, cout, dx, ST(s));
+}
+int b200_convT2x2_wgrad(const b200_tensor* x, const b200_tensor* dy, float* dk, float* db, void* s) {
+  REQ_T(x, "x"); REQ_T(dy, "dy");
+  return convT2_wgrad(x, dy, dk, db, ST(s));
+}
+
+int b200_bias_act_bwd(const b200_tensor* dy, const b200_tensor* y, int act, const b200_tensor* dz, float* dbias, void* s) {
+  REQ_T(dy, "dy"); REQ_T(y, "y"); REQ_T(dz, "dz");
+  return bias_act_bwd(dy, y, act, dz, dbias, ST(s));
+}
+
+int b200_layernorm_fwd(const b200_tensor* z, const float* g, const float* b, float eps, int relu, const b200_tensor* y,
+                       float* mean, float* rstd, void* s) {
+  REQ_T(z, "z"); REQ_T(y, "y");
+  B200_REQUIRE(g && b && mean && rstd, B200_ERR_BAD_ARG, "layernorm_fwd: NULL parameter");
+  return layernorm_fwd(z, g, b, eps, relu, y, mean, rstd, ST(s));
+}
+int b200_layernorm_bwd(const b200_tensor* dy, const b200_tensor* z, const float* mean, const float* rstd, const float* g,
+                       const float* b, int relu, const b200_tensor* dz, float* dg, float* db, float* dbias, void* s) {
+  REQ_T(dy, "dy"); REQ_T(z, "z"); REQ_T(dz, "dz");
+  B200_REQUIRE(g && b && mean && rstd, B200_ERR_BAD_ARG, "layernorm_bwd: NULL parameter");
+  return layernorm_bwd(dy, z, mean, rstd, g, b, relu, dz, dg, db, dbias, ST(s));
+}
+
+int b200_batchnorm_fwd_train(const b200_tensor* z, const float* g, const float* b, float eps, float mom, int relu,
+                             const b200_tensor* y, float* sm, float* sr, float* mm, float* mv, double* ws, void* s) {
+  REQ_T(z, "z"); REQ_T(y, "y");
+  B200_REQUIRE(g && b && sm && sr && ws, B200_ERR_BAD_ARG, "batchnorm_fwd_train: NULL parameter");
+  return batchnorm_fwd_train(z, g, b, eps, mom, relu, y, sm, sr, mm, mv, ws, ST(s));
+}
+int b200_batchnorm_fwd_infer(const b200_tensor* z, const float* g, const float* b, float eps, int relu, const float* mm,
+                             const float* mv, const b200_tensor* y, void* s) {
+  REQ_T(z, "z"); REQ_T(y, "y");
+  B200_REQUIRE(g && b && mm && mv, B200_ERR_BAD_ARG, "batchnorm_fwd_infer: NULL parameter");
+  return batchnorm_fwd_infer(z, g, b, eps, relu, mm, mv, y, ST(s));
+}
+int b200_batchnorm_bwd(const b200_tensor* dy, const b200_tensor* z, const float* sm, const float* sr, const float* g,
+                       const float* b, int relu, const b200_tensor* dz, float* dg, float* db, float* dbias, double* ws,
+                       void* s) {
+  REQ_T(dy, "dy"); REQ_T(z, "z"); REQ_T(dz, "dz");
+  B200_REQUIRE(g && b && sm && sr && ws, B200_ERR_BAD_ARG, "batchnorm_bwd: NULL parameter");
+  return batchnorm_bwd(dy, z, sm, sr, g, b, relu, dz, dg, db, dbias, ws, ST(s));
+}
+
+int b200_resize_extent(int extent, float scale) { return resize_extent(extent, scale); }
+int b200_resample_taps(int in_size, int out_size, int aa) { return resample_taps(in_size, out_size, aa); }
+int b200_resample_plan(int in_size, int out_size, int aa, int32_t* starts, float* weights, int taps) {
+  B200_REQUIRE(starts && weights, B200_ERR_BAD_ARG, "resample_plan: NULL table");
+  return resample_plan(in_size, out_size, aa, starts, weights, taps);
+}
+int b200_resample_plan_transpose(int in_size, int out_size, int taps, const int32_t* starts, const float* weights,
+                                 int32_t* ts, float* tw, int tt) {
+  B200_REQUIRE(starts && weights, B200_ERR_BAD_ARG, "resample_plan_transpose: NULL table");
+  return resample_plan_transpose(in_size, out_size, taps, starts, weights, ts, tw, tt);
+}
+int b200_resample2d(const b200_tensor* x, const b200_tensor* y, const int32_t* hs, const float* hw, int ht,
+                    const int32_t* ws, const float* ww, int wt, int accumulate, void* s) {
+  REQ_T(x, "x"); REQ_T(y, "y");
+  B200_REQUIRE(hs && hw && ws && ww && ht > 0 && wt > 0, B200_ERR_BAD_ARG, "resample2d: NULL table");
+  return resample2d(x, y, hs, hw, ht, ws, ww, wt, accumulate, ST(s));
+}
+
+int b200_maxpool2_fwd(const b200_tensor* x, const b200_tensor* y, void* s) {
+  REQ_T(x, "x"); REQ_T(y, "y");
+  return maxpool2_fwd(x, y, ST(s));
+}
+int b200_maxpool2_bwd(const b200_tensor* x, const b200_tensor* y, const b200_tensor* dy, const b200_tensor* dx, int acc,
+                      void* s) {
+  REQ_T(x, "x"); REQ_T(y, "y"); REQ_T(dy, "dy"); REQ_T(dx, "dx");
+  return maxpool2_bwd(x, y, dy, dx, acc, ST(s));
+}
+
+int b200_clipadd_fwd(const b200_tensor* inp, const b200_tensor* res, const b200_tensor* y, void* s) {
+  REQ_T(inp, "inp"); REQ_T(res, "res"); REQ_T(y, "y");
+  return clipadd_fwd(inp, res, y, ST(s));
+}
+int b200_clipadd_bwd(const b200_tensor* inp, const b200_tensor* res, const b200_tensor* dy, const b200_tensor* dres,
+                     void* s) {
+  REQ_T(inp, "inp"); REQ_T(res, "res"); REQ_T(dy, "dy"); REQ_T(dres, "dres");
+  return clipadd_bwd(inp, res, dy, dres, ST(s));
+}
+
+int b200_sr_loss(const b200_tensor* pred, const b200_tensor* target, int kind, float eps, float gs, float* out,
+                 const b200_tensor* dpred, float* ws, void* s) {
+  REQ_T(pred, "pred"); REQ_T(target, "target");
+  B200_REQUIRE(out && ws, B200_ERR_BAD_ARG, "sr_loss: NULL out/ws");
+  return sr_loss(pred, target, kind, eps, gs, out, dpred, ws, ST(s));
+}
+int b200_bce_dice_loss(const b200_tensor* pred, const b200_tensor* target, float bw, float dw, float gs, float* out,
+                       const b200_tensor* dpred, float* ws, void* s) {
+  REQ_T(pred, "pred"); REQ_T(target, "target");
+  B200_REQUIRE(out && ws, B200_ERR_BAD_ARG, "bce_dice_loss: NULL out/ws");
+  return bce_dice_loss(pred, target, bw, dw, gs, out, dpred, ws, ST(s));
+}
+int b200_softmax_fwd(const b200_tensor* z, const b200_tensor* p, void* s) {
+  REQ_T(z, "z"); REQ_T(p, "p");
+  return softmax_fwd(z, p, ST(s));
+}
+int b200_softmax_ce_loss(const b200_tensor* prob, const int32_t* labels, float gs, float* out, const b200_tensor* dl,
+                         float* ws, void* s) {
+  REQ_T(prob, "prob");
+  B200_REQUIRE(labels && out && ws, B200_ERR_BAD_ARG, "softmax_ce_loss: NULL argument");
+  return softmax_ce_loss(prob, labels, gs, out, dl, ws, ST(s));
+}
+
+int b200_adam_advance(int32_t* step, void* s) {
+  B200_REQUIRE(step, B200_ERR_BAD_ARG, "adam_advance: NULL step");
+  return adam_advance(step, ST(s));
+}
+int b200_adam_step(float* p, const float* g, float* m, float* v, size_t count, const float* hyper, const int32_t* step,
+                   void* shadow, void* s) {
+  B200_REQUIRE(p && g && m && v && hyper && step, B200_ERR_BAD_ARG, "adam_step: NULL argument");
+  if (count == 0) return B200_OK;
+  return adam_step(p, g, m, v, count, hyper, step, shadow, ST(s));
+}
+
+int b200_cast(const void* src, int sdt, void* dst, int ddt, size_t count, void* s) {
+  B200_REQUIRE(src && dst, B200_ERR_BAD_ARG, "cast: NULL argument");
+  if (count == 0) return B200_OK;
+  return cast(src, sdt, dst, ddt, count, ST(s));
+}
+int b200_copy_tensor(const b200_tensor* src, const b200_tensor* dst, void* s) {
+  REQ_T(src, "src"); REQ_T(dst, "dst");
+  return copy_tensor(src, dst, ST(s));
+}
+int b200_scale_inplace(float* p, size_t count, float sc, void* s) {
+  B200_REQUIRE(p, B200_ERR_BAD_ARG, "scale_inplace: NULL argument");
+  if (count == 0) return B200_OK;
+  return scale_inplace(p, count, sc, ST(s));
+}
+
+int b200_debug_umma_probe(const void* a, int a_rows, const void* b, int start_bytes, int sbo_bytes, int lbo_bytes,
+                          int mn_major, float* out, void* s) {
+  B200_REQUIRE(a && b && out, B200_ERR_BAD_ARG, "umma_probe: NULL argument");
+  return umma_probe(a, a_rows, b, start_bytes, sbo_bytes, lbo_bytes, mn_major, out, ST(s));
+}
+
+}  // extern "C"

@@ -1,0 +1,123 @@
+// Shared host/device helpers for the b200 U-Net kernels.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+
+#include "../../include/b200_unet.h"
+
+namespace b200 {
+
+// ---- error plumbing ---------------------------------------------------------
+void set_error(const char* fmt, ...);
+int fail(int code, const char* fmt, ...);
+int check_launch(const char* what);
+
+#define B200_REQUIRE(cond, code, ...)                 \
+  do {                                                \
+    if (!(cond)) return ::b200::fail((code), __VA_ARGS__); \
+  } while (0)
+
+// ---- device view of a b200_tensor --------------------------------------------
+struct TView {
+  void* data;
+  int n, h, w, c;
+  long long sn, sh, sw;
+};
+
+inline TView view_of(const b200_tensor* t) {
+  TView v;
+  v.data = t->data;
+  v.n = t->n; v.h = t->h; v.w = t->w; v.c = t->c;
+  v.sn = t->stride_n; v.sh = t->stride_h; v.sw = t->stride_w;
+  return v;
+}
+
+inline bool same_shape(const b200_tensor* a, const b200_tensor* b) {
+  return a->n == b->n && a->h == b->h && a->w == b->w && a->c == b->c;
+}
+inline bool valid_tensor(const b200_tensor* t) {
+  return t && t->data && t->n > 0 && t->h > 0 && t->w > 0 && t->c > 0 &&
+         (t->dtype == B200_F32 || t->dtype == B200_BF16);
+}
+inline size_t dtype_size(int dt) { return dt == B200_BF16 ? 2 : 4; }
+// channel vectors are 16-byte aligned when base and strides are
+inline bool vec_aligned(const b200_tensor* t, int elems) {
+  size_t es = dtype_size(t->dtype);
+  return (reinterpret_cast<uintptr_t>(t->data) % 16 == 0) && ((t->c * es) % 16 == 0 || true) &&
+         ((t->stride_w * es) % 16 == 0) && ((t->stride_h * es) % 16 == 0) && ((t->stride_n * es) % 16 == 0) &&
+         (t->c % elems == 0);
+}
+
+// ---- element load/store in fp32 ------------------------------------------------
+template <typename T> __device__ __forceinline__ float ldf(const T* p);
+template <> __device__ __forceinline__ float ldf<float>(const float* p) { return *p; }
+template <> __device__ __forceinline__ float ldf<__nv_bfloat16>(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+template <typename T> __device__ __forceinline__ void stf(T* p, float v);
+template <> __device__ __forceinline__ void stf<float>(float* p, float v) { *p = v; }
+template <> __device__ __forceinline__ void stf<__nv_bfloat16>(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
+
+// 8 consecutive channels as fp32 (16 B for bf16, 32 B for fp32)
+template <typename T> struct Vec8;
+template <> struct Vec8<__nv_bfloat16> {
+  static __device__ __forceinline__ void load(const __nv_bfloat16* p, float (&v)[8]) {
+    uint4 r = *reinterpret_cast<const uint4*>(p);
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float2 f = __bfloat1622float2(h[i]);
+      v[2 * i] = f.x; v[2 * i + 1] = f.y;
+    }
+  }
+  static __device__ __forceinline__ void store(__nv_bfloat16* p, const float (&v)[8]) {
+    uint4 r;
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&r);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+    *reinterpret_cast<uint4*>(p) = r;
+  }
+};
+template <> struct Vec8<float> {
+  static __device__ __forceinline__ void load(const float* p, float (&v)[8]) {
+    float4 a = *reinterpret_cast<const float4*>(p);
+    float4 b = *reinterpret_cast<const float4*>(p + 4);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  }
+  static __device__ __forceinline__ void store(float* p, const float (&v)[8]) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+  }
+};
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__device__ __forceinline__ long long pix_offset(const TView& t, int n, int h, int w) {
+  return (long long)n * t.sn + (long long)h * t.sh + (long long)w * t.sw;
+}
+
+inline int sm_count() {
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = 148;
+  }
+  return sms;
+}
+
+// dtype dispatch: DISPATCH_DTYPE(dt, T, { body using T })
+#define B200_DISPATCH_DTYPE(dt, T, ...)                          \
+  do {                                                            \
+    if ((dt) == B200_BF16) { using T = __nv_bfloat16; __VA_ARGS__ } \
+    else { using T = float; __VA_ARGS__ }                         \
+  } while (0)
+
+}  // namespace b200

@@ -1,0 +1,414 @@
+// 3x3 "same" convolution as an implicit GEMM on the 5th-generation tensor cores
+// (tcgen05.mma, fp32 accumulators in TMEM), operands staged by TMA.  One kernel
+// serves fprop and dgrad (dgrad = the same convolution with the tap order reversed
+// and the HWIO kernel read as [tap][cin][cout]).
+//
+// Replaces the cuDNN kernels TF dispatches for keras Conv2D at
+// Super_resolution/code/train_adaptive_unet.py:202,207,259 (reference: /root/reference)
+// and their autodiff (dgrad).
+//
+// Formulation (per CTA work item):
+//   output tile  : 16 rows x 8 columns of one image = 128 GEMM rows (M), BN output channels (N)
+//   A operand    : for each 64-channel block of Cin, ONE TMA box {64ch, 10, 18, 1} -- the tile plus
+//                  its one-pixel halo -- lands in shared memory with the 128-byte swizzle; image
+//                  borders are the TMA's out-of-bounds zero fill.  All nine filter taps read that
+//                  one window through shifted UMMA descriptors: tap (kh,kw) starts (kh*10+kw) pixel
+//                  rows (128 B each) into the window and strides 8-row groups by the window pitch
+//                  (SBO = 10*128 B), so the activations are fetched from L2 once, not nine times.
+//   B operand    : [tap][N][K] K-major weight tiles {64 x BN}; kept resident in shared memory for the
+//                  whole (persistent) CTA when all of them fit, streamed through a ring otherwise.
+//   accumulators : 2 x BN TMEM columns (double buffered: epilogue of item i overlaps MMAs of i+1).
+// Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (one thread) + TMEM owner,
+// warps 2..5 = epilogue (TMEM -> registers -> bias/activation -> bf16 -> global).
+#include <cuda.h>
+
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace b200 {
+
+using namespace ptx;
+
+// ---------------------------------------------------------------------------
+// TMA descriptor helpers (driver entry point fetched through the runtime)
+// ---------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// NHWC bf16 activation view -> 4D map {C, W, H, N}, box {64, bw, bh, 1}, 128B swizzle, zero OOB fill
+int make_act_tmap(CUtensorMap* m, const b200_tensor* t, int box_w, int box_h) {
+  EncodeTiledFn fn = encode_fn();
+  B200_REQUIRE(fn, B200_ERR_LAUNCH, "cuTensorMapEncodeTiled unavailable");
+  cuuint64_t dims[4] = {(cuuint64_t)t->c, (cuuint64_t)t->w, (cuuint64_t)t->h, (cuuint64_t)t->n};
+  cuuint64_t strides[3] = {(cuuint64_t)t->stride_w * 2, (cuuint64_t)t->stride_h * 2, (cuuint64_t)t->stride_n * 2};
+  cuuint32_t box[4] = {64, (cuuint32_t)box_w, (cuuint32_t)box_h, 1};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, t->data, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  B200_REQUIRE(r == CUDA_SUCCESS, B200_ERR_LAUNCH, "cuTensorMapEncodeTiled(activation) failed: %d", (int)r);
+  return B200_OK;
+}
+
+// row-major bf16 matrix [rows][cols] -> 2D map, box {64 cols, box_rows}, 128B swizzle
+int make_mat_tmap(CUtensorMap* m, const void* base, long long rows, long long cols, int box_rows) {
+  EncodeTiledFn fn = encode_fn();
+  B200_REQUIRE(fn, B200_ERR_LAUNCH, "cuTensorMapEncodeTiled unavailable");
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)cols * 2};
+  cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
+  cuuint32_t es[2] = {1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, es,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  B200_REQUIRE(r == CUDA_SUCCESS, B200_ERR_LAUNCH, "cuTensorMapEncodeTiled(matrix) failed: %d", (int)r);
+  return B200_OK;
+}
+
+namespace {
+
+constexpr int TILE_H = 16, TILE_W = 8;            // 128 output pixels
+constexpr int WIN_W = TILE_W + 2, WIN_H = TILE_H + 2;
+constexpr int WIN_BYTES = WIN_W * WIN_H * 128;    // 23040
+constexpr int WIN_STAGE = 23552;                  // padded to a multiple of 1024
+constexpr int WIN_PITCH = WIN_W * 128;            // 1280: byte distance between tile rows = SBO
+constexpr int MAX_WSLOTS = 18;
+constexpr int NTHREADS = 192;
+constexpr int SMEM_LIMIT = 232448;                // 227 KB
+
+struct ConvTcParams {
+  int N, H, W, Cout, KB, BN, n_tiles, tiles_h, tiles_w, total_items;
+  int tap_rev, live_mask, resident, nsw, nsb, act, accumulate;
+  const float* bias;
+  __nv_bfloat16* y;
+  long long ysn, ysh, ysw;
+};
+
+__global__ void __launch_bounds__(NTHREADS, 1)
+conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_b,
+                  const ConvTcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bar_full_w[8], bar_empty_w[8];
+  __shared__ __align__(8) uint64_t bar_full_b[MAX_WSLOTS], bar_empty_b[MAX_WSLOTS];
+  __shared__ __align__(8) uint64_t bar_tmem_full[2], bar_tmem_empty[2];
+  __shared__ uint32_t tmem_base_smem;
+
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t win0 = smem0;
+  const uint32_t wt0 = smem0 + (uint32_t)p.nsw * WIN_STAGE;
+  const uint32_t wt_bytes = (uint32_t)p.BN * 128u;
+  const uint32_t tmem_cols = 2u * (uint32_t)p.BN;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < p.nsw; ++i) { mbar_init(smem_u32(&bar_full_w[i]), 1); mbar_init(smem_u32(&bar_empty_w[i]), 1); }
+    for (int i = 0; i < p.nsb; ++i) { mbar_init(smem_u32(&bar_full_b[i]), 1); mbar_init(smem_u32(&bar_empty_b[i]), 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&bar_tmem_full[i]), 1); mbar_init(smem_u32(&bar_tmem_empty[i]), 4); }
+    fence_barrier_init();
+  }
+  if (warp == 0 && lane == 0) { prefetch_tmap(&tm_x); prefetch_tmap(&tm_b); }
+  if (warp == 1) { tmem_alloc(smem_u32(&tmem_base_smem), tmem_cols); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+
+  if (warp == 0) {
+    // ============================ TMA producer ============================
+    if (lane == 0) {
+      int sw = 0, pw = 0, sb = 0, pb = 0;
+      if (p.resident) {
+        for (int kb = 0; kb < p.KB; ++kb)
+          for (int tap = 0; tap < 9; ++tap) {
+            if (!((p.live_mask >> tap) & 1)) continue;
+            const int slot = kb * 9 + tap;
+            const int trow = (p.tap_rev ? 8 - tap : tap) * p.Cout;
+            mbar_arrive_expect_tx(smem_u32(&bar_full_b[slot]), wt_bytes);
+            tma_load_2d(wt0 + slot * wt_bytes, &tm_b, smem_u32(&bar_full_b[slot]), kb * 64, trow);
+          }
+      }
+      for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
+        const int j = item % p.n_tiles;
+        int t = item / p.n_tiles;
+        const int tw = t % p.tiles_w; t /= p.tiles_w;
+        const int th = t % p.tiles_h;
+        const int n = t / p.tiles_h;
+        for (int kb = 0; kb < p.KB; ++kb) {
+          mbar_wait(smem_u32(&bar_empty_w[sw]), pw ^ 1);
+          mbar_arrive_expect_tx(smem_u32(&bar_full_w[sw]), WIN_BYTES);
+          tma_load_4d(win0 + sw * WIN_STAGE, &tm_x, smem_u32(&bar_full_w[sw]), kb * 64, tw * TILE_W - 1,
+                      th * TILE_H - 1, n);
+          if (++sw == p.nsw) { sw = 0; pw ^= 1; }
+          if (!p.resident) {
+            for (int tap = 0; tap < 9; ++tap) {
+              if (!((p.live_mask >> tap) & 1)) continue;
+              const int trow = (p.tap_rev ? 8 - tap : tap) * p.Cout + j * p.BN;
+              mbar_wait(smem_u32(&bar_empty_b[sb]), pb ^ 1);
+              mbar_arrive_expect_tx(smem_u32(&bar_full_b[sb]), wt_bytes);
+              tma_load_2d(wt0 + sb * wt_bytes, &tm_b, smem_u32(&bar_full_b[sb]), kb * 64, trow);
+              if (++sb == p.nsb) { sb = 0; pb ^= 1; }
+            }
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ============================ MMA issuer ==============================
+    if (lane == 0) {
+      const uint32_t idesc = idesc_bf16(128, p.BN, 0, 0);
+      int sw = 0, pw = 0, sb = 0, pb = 0, as = 0, pa = 0;
+      bool first_item = true;
+      for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
+        mbar_wait(smem_u32(&bar_tmem_empty[as]), pa ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(as * p.BN);
+        uint32_t accumulate = 0;
+        for (int kb = 0; kb < p.KB; ++kb) {
+          mbar_wait(smem_u32(&bar_full_w[sw]), pw);
+          tc_fence_after();
+          const uint32_t win = win0 + sw * WIN_STAGE;
+          for (int tap = 0; tap < 9; ++tap) {
+            if (!((p.live_mask >> tap) & 1)) continue;
+            uint32_t wt;
+            if (p.resident) {
+              const int slot = kb * 9 + tap;
+              if (first_item) { mbar_wait(smem_u32(&bar_full_b[slot]), 0); tc_fence_after(); }
+              wt = wt0 + slot * wt_bytes;
+            } else {
+              mbar_wait(smem_u32(&bar_full_b[sb]), pb);
+              tc_fence_after();
+              wt = wt0 + sb * wt_bytes;
+            }
+            const uint32_t a_addr = win + (uint32_t)((tap / 3) * WIN_W + (tap % 3)) * 128u;
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+              umma_bf16(d_tmem, smem_desc_sw128(a_addr + ks * 32, 0, WIN_PITCH), smem_desc_sw128(wt + ks * 32, 0, 1024),
+                        idesc, accumulate);
+              accumulate = 1;
+            }
+            if (!p.resident) {
+              umma_commit(smem_u32(&bar_empty_b[sb]));
+              if (++sb == p.nsb) { sb = 0; pb ^= 1; }
+            }
+          }
+          umma_commit(smem_u32(&bar_empty_w[sw]));
+          if (++sw == p.nsw) { sw = 0; pw ^= 1; }
+        }
+        umma_commit(smem_u32(&bar_tmem_full[as]));
+        if (++as == 2) { as = 0; pa ^= 1; }
+        first_item = false;
+      }
+    }
+    __syncwarp();
+  } else {
+    // ============================ epilogue ================================
+    const int q = warp % 4;                 // TMEM lane quarter this warp may read
+    const int r = q * 32 + lane;            // GEMM row = pixel of the tile
+    const int ty = r / TILE_W, tx = r % TILE_W;
+    int as = 0, pa = 0;
+    for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
+      const int j = item % p.n_tiles;
+      int t = item / p.n_tiles;
+      const int tw = t % p.tiles_w; t /= p.tiles_w;
+      const int th = t % p.tiles_h;
+      const int n = t / p.tiles_h;
+      const int oh = th * TILE_H + ty, ow = tw * TILE_W + tx;
+      const bool valid = oh < p.H && ow < p.W;
+      __nv_bfloat16* dst = p.y + (long long)n * p.ysn + (long long)oh * p.ysh + (long long)ow * p.ysw + j * p.BN;
+      mbar_wait(smem_u32(&bar_tmem_full[as]), pa);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * p.BN);
+      for (int c0 = 0; c0 < p.BN; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(taddr + c0, v);
+        tmem_ld_wait();
+        if (valid) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            float o[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              float f = __uint_as_float(v[g * 8 + i]);
+              if (p.bias) f += __ldg(p.bias + j * p.BN + c0 + g * 8 + i);
+              if (p.act == B200_ACT_RELU) f = fmaxf(f, 0.f);
+              o[i] = f;
+            }
+            __nv_bfloat16* d8 = dst + c0 + g * 8;
+            if (p.accumulate) {
+              float e[8];
+              Vec8<__nv_bfloat16>::load(d8, e);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) o[i] += e[i];
+            }
+            Vec8<__nv_bfloat16>::store(d8, o);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&bar_tmem_empty[as]));
+      if (++as == 2) { as = 0; pa ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, tmem_cols); }
+}
+
+// ---------------------------------------------------------------------------
+// Descriptor probe: D[128 x 64] = A[rows start.., K=64] * B[64 x 64]^T with a caller-chosen
+// start offset and stride-byte-offset, used by tests to pin the UMMA addressing model.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(128, 1)
+umma_probe_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, int a_rows,
+                  int start_bytes, int sbo_bytes, int lbo_bytes, int mn_major, float* __restrict__ out) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bar_load, bar_mma;
+  __shared__ uint32_t tmem_base_smem;
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t a_smem = smem0, b_smem = smem0 + 65536;
+  if (threadIdx.x == 0) { mbar_init(smem_u32(&bar_load), 1); mbar_init(smem_u32(&bar_mma), 1); fence_barrier_init(); }
+  if (warp == 0) { tmem_alloc(smem_u32(&tmem_base_smem), 64); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+  if (threadIdx.x == 0) {
+    // A: a_rows x 64 (rows of 128 B), loaded in boxes of 64 rows; B: 64 x 64
+    mbar_arrive_expect_tx(smem_u32(&bar_load), (uint32_t)(a_rows * 128 + 64 * 128));
+    for (int r0 = 0; r0 < a_rows; r0 += 64) tma_load_2d(a_smem + r0 * 128, &tm_a, smem_u32(&bar_load), 0, r0);
+    tma_load_2d(b_smem, &tm_b, smem_u32(&bar_load), 0, 0);
+    mbar_wait(smem_u32(&bar_load), 0);
+    tc_fence_after();
+    if (!mn_major) {
+      const uint32_t idesc = idesc_bf16(128, 64, 0, 0);
+      for (int ks = 0; ks < 4; ++ks)
+        umma_bf16(tmem_base, smem_desc_sw128(a_smem + start_bytes + ks * 32, lbo_bytes, sbo_bytes),
+                  smem_desc_sw128(b_smem + ks * 32, 0, 1024), idesc, ks > 0);
+    } else {
+      // wgrad-style: both operands MN-major.  A rows are K (pixels): M = 2 atoms of 64 channels that
+      // are `lbo_bytes` apart (the same window shifted); B = 64 x 64 tile, K rows.
+      const uint32_t idesc = idesc_bf16(128, 64, 1, 1);
+      for (int ks = 0; ks < 4; ++ks)   // K = 64 pixels = 4 steps of 16 rows = 2 groups of 8 rows
+        umma_bf16(tmem_base, smem_desc_sw128(a_smem + start_bytes + ks * 2 * sbo_bytes, lbo_bytes, sbo_bytes),
+                  smem_desc_sw128(b_smem + ks * 2048, 0, 1024), idesc, ks > 0);
+    }
+    umma_commit(smem_u32(&bar_mma));
+  }
+  __syncwarp();
+  mbar_wait(smem_u32(&bar_mma), 0);
+  tc_fence_after();
+  const int row = warp * 32 + lane;
+  for (int c0 = 0; c0 < 64; c0 += 32) {
+    uint32_t v[32];
+    tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + c0, v);
+    tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 32; ++i) out[row * 64 + c0 + i] = __uint_as_float(v[i]);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem_base, 64); }
+}
+
+}  // namespace
+
+bool conv_tc_supported(const b200_tensor* x, int cin, int cout, const b200_tensor* y, int ks) {
+  if (ks != 3) return false;
+  if (x->dtype != B200_BF16 || y->dtype != B200_BF16) return false;
+  if (cin % 64 != 0 || cout % 64 != 0) return false;
+  if (cout > 64 && cout % 128 != 0) return false;
+  auto ok = [](const b200_tensor* t) {
+    return ((uintptr_t)t->data % 16 == 0) && (t->stride_w * 2) % 16 == 0 && (t->stride_h * 2) % 16 == 0 &&
+           (t->stride_n * 2) % 16 == 0;
+  };
+  return ok(x) && ok(y);
+}
+
+// x: input activations (C = K total), wmat: [9][cout][cin] K-major bf16, y: output (C = cout)
+int conv_tc_launch(const b200_tensor* x, const void* wmat, int cin, int cout, int tap_rev, const float* bias,
+                   const b200_tensor* y, int act, int accumulate, cudaStream_t st) {
+  B200_REQUIRE(conv_tc_supported(x, cin, cout, y, 3), B200_ERR_UNSUPPORTED,
+               "conv3x3 tcgen05: unsupported shape cin=%d cout=%d (need bf16, multiples of 64, 16-byte aligned)", cin,
+               cout);
+  B200_REQUIRE(x->n == y->n && x->h == y->h && x->w == y->w && x->c == cin && y->c == cout, B200_ERR_BAD_ARG,
+               "conv3x3 tcgen05: tensor shapes do not match the filter");
+  ConvTcParams p;
+  p.N = y->n; p.H = y->h; p.W = y->w; p.Cout = cout;
+  p.KB = cin / 64;
+  p.BN = cout == 64 ? 64 : 128;
+  p.n_tiles = cout / p.BN;
+  p.tiles_h = (p.H + TILE_H - 1) / TILE_H;
+  p.tiles_w = (p.W + TILE_W - 1) / TILE_W;
+  p.total_items = p.N * p.tiles_h * p.tiles_w * p.n_tiles;
+  p.tap_rev = tap_rev;
+  p.live_mask = 0;
+  for (int t = 0; t < 9; ++t) {
+    const bool dead = (p.H == 1 && t / 3 != 1) || (p.W == 1 && t % 3 != 1);
+    if (!dead) p.live_mask |= 1 << t;
+  }
+  const int wt_bytes = p.BN * 128;
+  const int budget = SMEM_LIMIT - 1024 /*align slack*/ - 1024 /*static*/;
+  const int all_w = 9 * p.KB * wt_bytes;
+  p.resident = (p.n_tiles == 1 && 9 * p.KB <= MAX_WSLOTS && budget - all_w >= 2 * WIN_STAGE) ? 1 : 0;
+  if (p.resident) {
+    p.nsb = 9 * p.KB;
+    p.nsw = (budget - all_w) / WIN_STAGE;
+  } else {
+    p.nsb = 4;
+    p.nsw = (budget - p.nsb * wt_bytes) / WIN_STAGE;
+  }
+  if (p.nsw > 8) p.nsw = 8;
+  B200_REQUIRE(p.nsw >= 2, B200_ERR_UNSUPPORTED, "conv3x3 tcgen05: shared memory budget too small");
+  p.act = act; p.accumulate = accumulate; p.bias = bias;
+  p.y = reinterpret_cast<__nv_bfloat16*>(y->data);
+  p.ysn = y->stride_n; p.ysh = y->stride_h; p.ysw = y->stride_w;
+
+  CUtensorMap tm_x, tm_b;
+  int rc = make_act_tmap(&tm_x, x, WIN_W, WIN_H);
+  if (rc) return rc;
+  rc = make_mat_tmap(&tm_b, wmat, 9LL * cout, cin, p.BN);
+  if (rc) return rc;
+
+  const size_t smem = 1024 + (size_t)p.nsw * WIN_STAGE + (size_t)p.nsb * wt_bytes;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(conv3x3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT - 1024);
+    attr_set = true;
+  }
+  int grid = p.total_items < sm_count() ? p.total_items : sm_count();
+  conv3x3_tc_kernel<<<grid, NTHREADS, smem, st>>>(tm_x, tm_b, p);
+  return check_launch("conv3x3_tc_kernel");
+}
+
+// a: [a_rows][64] bf16 (row-major), b: [64][64] bf16, out: [128][64] fp32
+int umma_probe(const void* a, int a_rows, const void* b, int start_bytes, int sbo_bytes, int lbo_bytes, int mn_major,
+               float* out, cudaStream_t st) {
+  B200_REQUIRE(a_rows % 64 == 0 && a_rows <= 512, B200_ERR_BAD_ARG, "umma_probe: a_rows must be a multiple of 64 <= 512");
+  CUtensorMap tm_a, tm_b;
+  int rc = make_mat_tmap(&tm_a, a, a_rows, 64, 64);
+  if (rc) return rc;
+  rc = make_mat_tmap(&tm_b, b, 64, 64, 64);
+  if (rc) return rc;
+  const size_t smem = 1024 + 65536 + 8192;
+  cudaFuncSetAttribute(umma_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  umma_probe_kernel<<<1, 128, smem, st>>>(tm_a, tm_b, a_rows, start_bytes, sbo_bytes, lbo_bytes, mn_major, out);
+  return check_launch("umma_probe_kernel");
+}
+
+}  // namespace b200

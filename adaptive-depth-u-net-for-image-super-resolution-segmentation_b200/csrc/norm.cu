@@ -1,0 +1,493 @@
+// Channel LayerNorm, BatchNorm and bias/activation backward -- HBM-bound kernels.
+//
+// One thread owns 8 consecutive channels of one pixel (16 B of bf16); the C/8
+// threads of a pixel sit in one warp (C <= 256) or loop (C > 256) and reduce with
+// shuffles.  Replaces keras LayerNormalization(axis=-1)+ReLU
+// (Super_resolution/code/train_adaptive_unet.py:203-204,208-209) and
+// BatchNormalization+ReLU (Segmenation/code/train_adaptive_unet.py:327-331).
+#include "common.cuh"
+
+namespace b200 {
+namespace {
+
+constexpr int NT = 256;
+
+__device__ __forceinline__ void pix_decode(long long p, int H, int W, int& n, int& h, int& w) {
+  w = (int)(p % W); p /= W;
+  h = (int)(p % H);
+  n = (int)(p / H);
+}
+
+__device__ __forceinline__ float group_sum(float v, int tpp) {
+  for (int o = tpp >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// ---------------------------------------------------------------------------
+// LayerNorm forward: TPP threads per pixel (power of two <= 32), CPT chunks/thread
+// ---------------------------------------------------------------------------
+template <typename T, int CPT>
+__global__ void __launch_bounds__(NT)
+ln_fwd_kernel(TView z, const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int relu,
+              TView y, float* __restrict__ mean_out, float* __restrict__ rstd_out, int tpp, long long npix) {
+  const int lane_g = threadIdx.x % tpp;
+  const int ppb = NT / tpp;
+  const int C = z.c, chunks = C / 8;
+  const T* zp = reinterpret_cast<const T*>(z.data);
+  T* yp = reinterpret_cast<T*>(y.data);
+  const float invC = 1.f / (float)C;
+  for (long long base = (long long)blockIdx.x * ppb; base < npix; base += (long long)gridDim.x * ppb) {
+    // warp-uniform trip count: groups past the end recompute the last pixel and skip their stores
+    long long p = base + threadIdx.x / tpp;
+    const bool valid = p < npix;
+    if (!valid) p = npix - 1;
+    int n, h, w;
+    pix_decode(p, z.h, z.w, n, h, w);
+    const T* src = zp + pix_offset(z, n, h, w);
+    float v[CPT][8];
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < CPT; ++k) {
+      int j = lane_g + k * tpp;
+      if (j < chunks) {
+        Vec8<T>::load(src + j * 8, v[k]);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s += v[k][i];
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[k][i] = 0.f;
+      }
+    }
+    const float mu = group_sum(s, tpp) * invC;
+    float q = 0.f;
+#pragma unroll
+    for (int k = 0; k < CPT; ++k) {
+      int j = lane_g + k * tpp;
+      if (j < chunks) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { float d = v[k][i] - mu; q += d * d; }
+      }
+    }
+    const float var = group_sum(q, tpp) * invC;
+    const float rs = rsqrtf(var + eps);
+    T* dst = yp + pix_offset(y, n, h, w);
+#pragma unroll
+    for (int k = 0; k < CPT; ++k) {
+      int j = lane_g + k * tpp;
+      if (j < chunks && valid) {
+        float o[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          float t = (v[k][i] - mu) * rs * gamma[j * 8 + i] + beta[j * 8 + i];
+          o[i] = relu ? fmaxf(t, 0.f) : t;
+        }
+        Vec8<T>::store(dst + j * 8, o);
+      }
+    }
+    if (lane_g == 0 && valid) { mean_out[p] = mu; rstd_out[p] = rs; }
+  }
+}
+
+// LayerNorm backward.  Per-channel partials live in registers across the
+// grid-stride loop, then go through shared memory to one global atomic per block.
+template <typename T, int CPT>
+__global__ void __launch_bounds__(NT)
+ln_bwd_kernel(TView dy, TView z, const float* __restrict__ mean, const float* __restrict__ rstd,
+              const float* __restrict__ gamma, const float* __restrict__ beta, int relu, TView dz,
+              float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dbias, int tpp,
+              long long npix) {
+  extern __shared__ float s_acc[];  // [3][C]
+  const int lane_g = threadIdx.x % tpp;
+  const int ppb = NT / tpp;
+  const int C = z.c, chunks = C / 8;
+  for (int i = threadIdx.x; i < 3 * C; i += NT) s_acc[i] = 0.f;
+  __syncthreads();
+  const T* zp = reinterpret_cast<const T*>(z.data);
+  const T* dyp = reinterpret_cast<const T*>(dy.data);
+  T* dzp = reinterpret_cast<T*>(dz.data);
+  const float invC = 1.f / (float)C;
+  float a_g[CPT][8], a_b[CPT][8], a_z[CPT][8];
+#pragma unroll
+  for (int k = 0; k < CPT; ++k)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { a_g[k][i] = 0.f; a_b[k][i] = 0.f; a_z[k][i] = 0.f; }
+
+  for (long long base = (long long)blockIdx.x * ppb; base < npix; base += (long long)gridDim.x * ppb) {
+    // warp-uniform trip count: groups past the end recompute the last pixel and skip their stores
+    long long p = base + threadIdx.x / tpp;
+    const bool valid = p < npix;
+    if (!valid) p = npix - 1;
+    int n, h, w;
+    pix_decode(p, z.h, z.w, n, h, w);
+    const T* zs = zp + pix_offset(z, n, h, w);
+    const T* ds = dyp + pix_offset(dy, n, h, w);
+    const float mu = mean[p], rs = rstd[p];
+    float xh[CPT][8], g[CPT][8];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int k = 0; k < CPT; ++k) {
+      int j = lane_g + k * tpp;
+      if (j < chunks) {
+        float zv[8], dv[8];
+        Vec8<T>::load(zs + j * 8, zv);
+        Vec8<T>::load(ds + j * 8, dv);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          float x = (zv[i] - mu) * rs;
+          float ga = gamma[j * 8 + i];
+          float t = x * ga + beta[j * 8 + i];
+          float d = (!valid || (relu && !(t > 0.f))) ? 0.f : dv[i];
+          a_g[k][i] += d * x;
+          a_b[k][i] += d;
+          float gg = d * ga;
+          xh[k][i] = x; g[k][i] = gg;
+          s1 += gg; s2 += gg * x;
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { xh[k][i] = 0.f; g[k][i] = 0.f; }
+      }
+    }
+    const float m1 = group_sum(s1, tpp) * invC;
+    const float m2 = group_sum(s2, tpp) * invC;
+    T* dd = dzp + pix_offset(dz, n, h, w);
+#pragma unroll
+    for (int k = 0; k < CPT; ++k) {
+      int j = lane_g + k * tpp;
+      if (j < chunks && valid) {
+        float o[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          o[i] = rs * (g[k][i] - m1 - xh[k][i] * m2);
+          a_z[k][i] += o[i];
+        }
+        Vec8<T>::store(dd + j * 8, o);
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < CPT; ++k) {
+    int j = lane_g + k * tpp;
+    if (j < chunks) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        atomicAdd(&s_acc[j * 8 + i], a_g[k][i]);
+        atomicAdd(&s_acc[C + j * 8 + i], a_b[k][i]);
+        atomicAdd(&s_acc[2 * C + j * 8 + i], a_z[k][i]);
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < C; i += NT) {
+    if (dgamma) atomicAdd(dgamma + i, s_acc[i]);
+    if (dbeta) atomicAdd(dbeta + i, s_acc[C + i]);
+    if (dbias) atomicAdd(dbias + i, s_acc[2 * C + i]);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Generic element-wise backward of bias+activation (scalar path, any C)
+// ---------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(NT)
+bias_act_bwd_kernel(TView dy, TView y, int act, TView dz, float* __restrict__ dbias, long long total) {
+  extern __shared__ float s_acc[];  // [C]
+  const int C = y.c;
+  for (int i = threadIdx.x; i < C; i += NT) s_acc[i] = 0.f;
+  __syncthreads();
+  const T* dyp = reinterpret_cast<const T*>(dy.data);
+  const T* yp = reinterpret_cast<const T*>(y.data);
+  T* dzp = reinterpret_cast<T*>(dz.data);
+  for (long long i = (long long)blockIdx.x * NT + threadIdx.x; i < total; i += (long long)gridDim.x * NT) {
+    int c = (int)(i % C);
+    int n, h, w;
+    pix_decode(i / C, y.h, y.w, n, h, w);
+    float d = ldf(dyp + pix_offset(dy, n, h, w) + c);
+    float yv = ldf(yp + pix_offset(y, n, h, w) + c);
+    if (act == B200_ACT_RELU) d = yv > 0.f ? d : 0.f;
+    else if (act == B200_ACT_SIGMOID) d = d * yv * (1.f - yv);
+    stf(dzp + pix_offset(dz, n, h, w) + c, d);
+    if (dbias) atomicAdd(&s_acc[c], d);
+  }
+  __syncthreads();
+  if (dbias)
+    for (int i = threadIdx.x; i < C; i += NT) atomicAdd(dbias + i, s_acc[i]);
+}
+
+// vectorised variant: C % 8 == 0, C/8 a power of two <= NT
+template <typename T>
+__global__ void __launch_bounds__(NT)
+bias_act_bwd_vec_kernel(TView dy, TView y, int act, TView dz, float* __restrict__ dbias, long long npix) {
+  extern __shared__ float s_acc[];
+  const int C = y.c, chunks = C / 8;
+  for (int i = threadIdx.x; i < C; i += NT) s_acc[i] = 0.f;
+  __syncthreads();
+  const int j = threadIdx.x % chunks;
+  const int ppb = NT / chunks;
+  const T* dyp = reinterpret_cast<const T*>(dy.data);
+  const T* yp = reinterpret_cast<const T*>(y.data);
+  T* dzp = reinterpret_cast<T*>(dz.data);
+  float acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+  for (long long p = (long long)blockIdx.x * ppb + threadIdx.x / chunks; p < npix; p += (long long)gridDim.x * ppb) {
+    int n, h, w;
+    pix_decode(p, y.h, y.w, n, h, w);
+    float d[8], yv[8];
+    Vec8<T>::load(dyp + pix_offset(dy, n, h, w) + j * 8, d);
+    Vec8<T>::load(yp + pix_offset(y, n, h, w) + j * 8, yv);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      if (act == B200_ACT_RELU) d[i] = yv[i] > 0.f ? d[i] : 0.f;
+      else if (act == B200_ACT_SIGMOID) d[i] = d[i] * yv[i] * (1.f - yv[i]);
+      acc[i] += d[i];
+    }
+    Vec8<T>::store(dzp + pix_offset(dz, n, h, w) + j * 8, d);
+  }
+  if (dbias) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) atomicAdd(&s_acc[j * 8 + i], acc[i]);
+    __syncthreads();
+    for (int i = threadIdx.x; i < C; i += NT) atomicAdd(dbias + i, s_acc[i]);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// BatchNorm
+// ---------------------------------------------------------------------------
+// mode 0: sums of z and z^2.  mode 1: sums of g=dy*mask and g*xhat (needs mean/rstd).
+template <typename T, int MODE>
+__global__ void __launch_bounds__(NT)
+bn_stats_kernel(TView z, TView dy, const float* __restrict__ mean, const float* __restrict__ rstd,
+                const float* __restrict__ gamma, const float* __restrict__ beta, int relu,
+                double* __restrict__ stats, long long npix) {
+  extern __shared__ float s_acc[];  // [2][C]
+  const int C = z.c;
+  for (int i = threadIdx.x; i < 2 * C; i += NT) s_acc[i] = 0.f;
+  __syncthreads();
+  const T* zp = reinterpret_cast<const T*>(z.data);
+  const T* dyp = reinterpret_cast<const T*>(dy.data);
+  // thread -> fixed channel set: c = threadIdx.x % C when C <= NT, else loop
+  const int cstep = C < NT ? C : NT;
+  const int ppb = C < NT ? NT / C : 1;
+  const long long chunk = 64;  // pixels per block iteration group
+  for (long long p0 = (long long)blockIdx.x * chunk; p0 < npix; p0 += (long long)gridDim.x * chunk) {
+    for (int c = threadIdx.x % cstep; c < C; c += cstep) {
+      float a = 0.f, b = 0.f;
+      for (long long p = p0 + threadIdx.x / cstep; threadIdx.x / cstep < ppb && p < p0 + chunk && p < npix; p += ppb) {
+        int n, h, w;
+        pix_decode(p, z.h, z.w, n, h, w);
+        float zv = ldf(zp + pix_offset(z, n, h, w) + c);
+        if (MODE == 0) { a += zv; b += zv * zv; }
+        else {
+          float x = (zv - mean[c]) * rstd[c];
+          float t = x * gamma[c] + beta[c];
+          float d = ldf(dyp + pix_offset(dy, n, h, w) + c);
+          if (relu && !(t > 0.f)) d = 0.f;
+          a += d; b += d * x;
+        }
+      }
+      atomicAdd(&s_acc[c], a);
+      atomicAdd(&s_acc[C + c], b);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * C; i += NT) atomicAdd(stats + i, (double)s_acc[i]);
+}
+
+__global__ void bn_finalize_kernel(const double* __restrict__ stats, int C, double count, float eps, float momentum,
+                                   float* save_mean, float* save_rstd, float* moving_mean, float* moving_var) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double m = stats[c] / count;
+  double var = stats[C + c] / count - m * m;
+  if (var < 0) var = 0;
+  save_mean[c] = (float)m;
+  save_rstd[c] = (float)(1.0 / sqrt(var + (double)eps));
+  if (moving_mean) moving_mean[c] = moving_mean[c] * momentum + (float)m * (1.f - momentum);
+  if (moving_var) moving_var[c] = moving_var[c] * momentum + (float)var * (1.f - momentum);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(NT)
+bn_apply_kernel(TView z, const float* __restrict__ mean, const float* __restrict__ rstd,
+                const float* __restrict__ gamma, const float* __restrict__ beta, int relu, TView y,
+                long long total, const float* __restrict__ mmean, const float* __restrict__ mvar, float eps) {
+  const int C = z.c;
+  const T* zp = reinterpret_cast<const T*>(z.data);
+  T* yp = reinterpret_cast<T*>(y.data);
+  for (long long i = (long long)blockIdx.x * NT + threadIdx.x; i < total; i += (long long)gridDim.x * NT) {
+    int c = (int)(i % C);
+    int n, h, w;
+    pix_decode(i / C, z.h, z.w, n, h, w);
+    float mu = mean ? mean[c] : mmean[c];
+    float rs = rstd ? rstd[c] : rsqrtf(mvar[c] + eps);
+    float t = (ldf(zp + pix_offset(z, n, h, w) + c) - mu) * rs * gamma[c] + beta[c];
+    if (relu) t = fmaxf(t, 0.f);
+    stf(yp + pix_offset(y, n, h, w) + c, t);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(NT)
+bn_bwd_apply_kernel(TView dy, TView z, const float* __restrict__ mean, const float* __restrict__ rstd,
+                    const float* __restrict__ gamma, const float* __restrict__ beta, int relu, TView dz,
+                    const double* __restrict__ stats, double count, long long total) {
+  const int C = z.c;
+  const T* zp = reinterpret_cast<const T*>(z.data);
+  const T* dyp = reinterpret_cast<const T*>(dy.data);
+  T* dzp = reinterpret_cast<T*>(dz.data);
+  for (long long i = (long long)blockIdx.x * NT + threadIdx.x; i < total; i += (long long)gridDim.x * NT) {
+    int c = (int)(i % C);
+    int n, h, w;
+    pix_decode(i / C, z.h, z.w, n, h, w);
+    float x = (ldf(zp + pix_offset(z, n, h, w) + c) - mean[c]) * rstd[c];
+    float t = x * gamma[c] + beta[c];
+    float d = ldf(dyp + pix_offset(dy, n, h, w) + c);
+    if (relu && !(t > 0.f)) d = 0.f;
+    float sb = (float)(stats[c] / count), sg = (float)(stats[C + c] / count);
+    stf(dzp + pix_offset(dz, n, h, w) + c, gamma[c] * rstd[c] * (d - sb - x * sg));
+  }
+}
+
+__global__ void bn_bwd_params_kernel(const double* __restrict__ stats, int C, float* dgamma, float* dbeta) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  if (dbeta) dbeta[c] += (float)stats[c];
+  if (dgamma) dgamma[c] += (float)stats[C + c];
+}
+
+inline bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
+inline int grid_for(long long work_items, int per_block) {
+  long long b = (work_items + per_block - 1) / per_block;
+  long long cap = 8LL * sm_count();
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
+}  // namespace
+
+int layernorm_fwd(const b200_tensor* z, const float* gamma, const float* beta, float eps, int relu,
+                  const b200_tensor* y, float* mean, float* rstd, cudaStream_t st) {
+  B200_REQUIRE(same_shape(z, y) && z->dtype == y->dtype, B200_ERR_BAD_ARG, "layernorm_fwd: shape/dtype mismatch");
+  const int C = z->c;
+  B200_REQUIRE(C % 8 == 0 && vec_aligned(z, 8) && vec_aligned(y, 8), B200_ERR_UNSUPPORTED,
+               "layernorm_fwd: C=%d must be a multiple of 8 with 16-byte aligned pixels", C);
+  const int chunks = C / 8;
+  int tpp = 1;
+  while (tpp < chunks && tpp < 32) tpp <<= 1;
+  const int cpt = (chunks + tpp - 1) / tpp;
+  B200_REQUIRE(cpt <= 8, B200_ERR_UNSUPPORTED, "layernorm_fwd: C=%d too wide (max 2048)", C);
+  const long long npix = (long long)z->n * z->h * z->w;
+  const int grid = grid_for(npix, NT / tpp);
+  TView zv = view_of(z), yv = view_of(y);
+  B200_DISPATCH_DTYPE(z->dtype, T, {
+    if (cpt == 1) ln_fwd_kernel<T, 1><<<grid, NT, 0, st>>>(zv, gamma, beta, eps, relu, yv, mean, rstd, tpp, npix);
+    else if (cpt == 2) ln_fwd_kernel<T, 2><<<grid, NT, 0, st>>>(zv, gamma, beta, eps, relu, yv, mean, rstd, tpp, npix);
+    else if (cpt <= 4) ln_fwd_kernel<T, 4><<<grid, NT, 0, st>>>(zv, gamma, beta, eps, relu, yv, mean, rstd, tpp, npix);
+    else ln_fwd_kernel<T, 8><<<grid, NT, 0, st>>>(zv, gamma, beta, eps, relu, yv, mean, rstd, tpp, npix);
+  });
+  return check_launch("ln_fwd_kernel");
+}
+
+int layernorm_bwd(const b200_tensor* dy, const b200_tensor* z, const float* mean, const float* rstd,
+                  const float* gamma, const float* beta, int relu, const b200_tensor* dz, float* dgamma,
+                  float* dbeta, float* dbias, cudaStream_t st) {
+  B200_REQUIRE(same_shape(z, dy) && same_shape(z, dz) && z->dtype == dy->dtype && z->dtype == dz->dtype,
+               B200_ERR_BAD_ARG, "layernorm_bwd: shape/dtype mismatch");
+  const int C = z->c;
+  B200_REQUIRE(C % 8 == 0 && vec_aligned(z, 8) && vec_aligned(dy, 8) && vec_aligned(dz, 8), B200_ERR_UNSUPPORTED,
+               "layernorm_bwd: C=%d must be a multiple of 8 with 16-byte aligned pixels", C);
+  const int chunks = C / 8;
+  int tpp = 1;
+  while (tpp < chunks && tpp < 32) tpp <<= 1;
+  const int cpt = (chunks + tpp - 1) / tpp;
+  B200_REQUIRE(cpt <= 8, B200_ERR_UNSUPPORTED, "layernorm_bwd: C=%d too wide (max 2048)", C);
+  const long long npix = (long long)z->n * z->h * z->w;
+  long long blocks = (npix + (NT / tpp) - 1) / (NT / tpp);
+  long long cap = 2LL * sm_count();
+  const int grid = (int)(blocks < cap ? (blocks < 1 ? 1 : blocks) : cap);
+  const size_t smem = sizeof(float) * 3 * C;
+  TView dyv = view_of(dy), zv = view_of(z), dzv = view_of(dz);
+  B200_DISPATCH_DTYPE(z->dtype, T, {
+    if (cpt == 1) ln_bwd_kernel<T, 1><<<grid, NT, smem, st>>>(dyv, zv, mean, rstd, gamma, beta, relu, dzv, dgamma, dbeta, dbias, tpp, npix);
+    else if (cpt == 2) ln_bwd_kernel<T, 2><<<grid, NT, smem, st>>>(dyv, zv, mean, rstd, gamma, beta, relu, dzv, dgamma, dbeta, dbias, tpp, npix);
+    else if (cpt <= 4) ln_bwd_kernel<T, 4><<<grid, NT, smem, st>>>(dyv, zv, mean, rstd, gamma, beta, relu, dzv, dgamma, dbeta, dbias, tpp, npix);
+    else ln_bwd_kernel<T, 8><<<grid, NT, smem, st>>>(dyv, zv, mean, rstd, gamma, beta, relu, dzv, dgamma, dbeta, dbias, tpp, npix);
+  });
+  return check_launch("ln_bwd_kernel");
+}
+
+int bias_act_bwd(const b200_tensor* dy, const b200_tensor* y, int act, const b200_tensor* dz, float* dbias,
+                 cudaStream_t st) {
+  B200_REQUIRE(same_shape(y, dy) && same_shape(y, dz) && y->dtype == dy->dtype && y->dtype == dz->dtype,
+               B200_ERR_BAD_ARG, "bias_act_bwd: shape/dtype mismatch");
+  const int C = y->c;
+  const long long npix = (long long)y->n * y->h * y->w;
+  TView dyv = view_of(dy), yv = view_of(y), dzv = view_of(dz);
+  const size_t smem = sizeof(float) * C;
+  const bool vec = C % 8 == 0 && is_pow2(C / 8) && C / 8 <= NT && vec_aligned(dy, 8) && vec_aligned(y, 8) &&
+                   vec_aligned(dz, 8);
+  B200_DISPATCH_DTYPE(y->dtype, T, {
+    if (vec) {
+      long long blocks = (npix + (NT / (C / 8)) - 1) / (NT / (C / 8));
+      long long cap = 4LL * sm_count();
+      int grid = (int)(blocks < cap ? (blocks < 1 ? 1 : blocks) : cap);
+      bias_act_bwd_vec_kernel<T><<<grid, NT, smem, st>>>(dyv, yv, act, dzv, dbias, npix);
+    } else {
+      long long total = npix * C;
+      int grid = grid_for(total, NT);
+      bias_act_bwd_kernel<T><<<grid, NT, smem, st>>>(dyv, yv, act, dzv, dbias, total);
+    }
+  });
+  return check_launch("bias_act_bwd_kernel");
+}
+
+int batchnorm_fwd_train(const b200_tensor* z, const float* gamma, const float* beta, float eps, float momentum,
+                        int relu, const b200_tensor* y, float* save_mean, float* save_rstd, float* moving_mean,
+                        float* moving_var, double* stats_ws, cudaStream_t st) {
+  B200_REQUIRE(same_shape(z, y) && z->dtype == y->dtype, B200_ERR_BAD_ARG, "batchnorm_fwd: shape/dtype mismatch");
+  const int C = z->c;
+  const long long npix = (long long)z->n * z->h * z->w;
+  cudaMemsetAsync(stats_ws, 0, sizeof(double) * 2 * C, st);
+  TView zv = view_of(z), yv = view_of(y);
+  const int sgrid = grid_for(npix, 64);
+  B200_DISPATCH_DTYPE(z->dtype, T, {
+    bn_stats_kernel<T, 0><<<sgrid, NT, sizeof(float) * 2 * C, st>>>(zv, zv, nullptr, nullptr, nullptr, nullptr, 0, stats_ws, npix);
+    bn_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(stats_ws, C, (double)npix, eps, momentum, save_mean, save_rstd, moving_mean, moving_var);
+    bn_apply_kernel<T><<<grid_for(npix * C, NT), NT, 0, st>>>(zv, save_mean, save_rstd, gamma, beta, relu, yv, npix * C, nullptr, nullptr, eps);
+  });
+  return check_launch("batchnorm_fwd_train");
+}
+
+int batchnorm_fwd_infer(const b200_tensor* z, const float* gamma, const float* beta, float eps, int relu,
+                        const float* moving_mean, const float* moving_var, const b200_tensor* y, cudaStream_t st) {
+  B200_REQUIRE(same_shape(z, y) && z->dtype == y->dtype, B200_ERR_BAD_ARG, "batchnorm_infer: shape/dtype mismatch");
+  const long long total = (long long)z->n * z->h * z->w * z->c;
+  TView zv = view_of(z), yv = view_of(y);
+  B200_DISPATCH_DTYPE(z->dtype, T, {
+    bn_apply_kernel<T><<<grid_for(total, NT), NT, 0, st>>>(zv, nullptr, nullptr, gamma, beta, relu, yv, total, moving_mean, moving_var, eps);
+  });
+  return check_launch("batchnorm_fwd_infer");
+}
+
+int batchnorm_bwd(const b200_tensor* dy, const b200_tensor* z, const float* save_mean, const float* save_rstd,
+                  const float* gamma, const float* beta, int relu, const b200_tensor* dz, float* dgamma,
+                  float* dbeta, float* dbias, double* stats_ws, cudaStream_t st) {
+  (void)dbias;  // sum(dz) over N,H,W is identically zero after BatchNorm
+  B200_REQUIRE(same_shape(z, dy) && same_shape(z, dz) && z->dtype == dy->dtype && z->dtype == dz->dtype,
+               B200_ERR_BAD_ARG, "batchnorm_bwd: shape/dtype mismatch");
+  const int C = z->c;
+  const long long npix = (long long)z->n * z->h * z->w;
+  cudaMemsetAsync(stats_ws, 0, sizeof(double) * 2 * C, st);
+  TView zv = view_of(z), dyv = view_of(dy), dzv = view_of(dz);
+  B200_DISPATCH_DTYPE(z->dtype, T, {
+    bn_stats_kernel<T, 1><<<grid_for(npix, 64), NT, sizeof(float) * 2 * C, st>>>(zv, dyv, save_mean, save_rstd, gamma, beta, relu, stats_ws, npix);
+    bn_bwd_apply_kernel<T><<<grid_for(npix * C, NT), NT, 0, st>>>(dyv, zv, save_mean, save_rstd, gamma, beta, relu, dzv, stats_ws, (double)npix, npix * C);
+    bn_bwd_params_kernel<<<(C + 127) / 128, 128, 0, st>>>(stats_ws, C, dgamma, dbeta);
+  });
+  return check_launch("batchnorm_bwd");
+}
+
+}  // namespace b200

@@ -1,0 +1,247 @@
+// Adam (keras semantics: eps 1e-7, bias-corrected step size), dtype casts, strided
+// copies and the SIMT Conv2DTranspose(2, strides=2) kernels.
+//
+// Replaces tf.keras.optimizers.Adam at Super_resolution/code/train_adaptive_unet.py:490
+// and keras Conv2DTranspose at Segmenation/code/unet_vinillia.py:67.
+#include "common.cuh"
+
+namespace b200 {
+namespace {
+
+constexpr int NT = 256;
+
+inline int grid_for(long long items, int per_thread = 1) {
+  long long b = (items + (long long)NT * per_thread - 1) / ((long long)NT * per_thread);
+  long long cap = 16LL * sm_count();
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
+__global__ void adam_advance_kernel(int* step) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) *step += 1;
+}
+
+// alpha = lr * sqrt(1 - b2^t) / (1 - b1^t); m += (g-m)(1-b1); v += (g^2-v)(1-b2); p -= alpha*m/(sqrt(v)+eps)
+__global__ void __launch_bounds__(NT)
+adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+            size_t count, const float* __restrict__ hyper, const int* __restrict__ step,
+            __nv_bfloat16* __restrict__ shadow) {
+  const float lr = hyper[0], b1 = hyper[1], b2 = hyper[2], eps = hyper[3];
+  const float t = (float)(*step);
+  const float alpha = lr * sqrtf(1.f - powf(b2, t)) / (1.f - powf(b1, t));
+  const size_t n4 = count / 4;
+  for (size_t i = (size_t)blockIdx.x * NT + threadIdx.x; i < n4; i += (size_t)gridDim.x * NT) {
+    float4 pv = reinterpret_cast<float4*>(p)[i];
+    const float4 gv = reinterpret_cast<const float4*>(g)[i];
+    float4 mv = reinterpret_cast<float4*>(m)[i];
+    float4 vv = reinterpret_cast<float4*>(v)[i];
+    float* pp = &pv.x; const float* gg = &gv.x; float* mm = &mv.x; float* vp = &vv.x;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      mm[k] += (gg[k] - mm[k]) * (1.f - b1);
+      vp[k] += (gg[k] * gg[k] - vp[k]) * (1.f - b2);
+      pp[k] -= alpha * mm[k] / (sqrtf(vp[k]) + eps);
+    }
+    reinterpret_cast<float4*>(p)[i] = pv;
+    reinterpret_cast<float4*>(m)[i] = mv;
+    reinterpret_cast<float4*>(v)[i] = vv;
+    if (shadow) {
+      __nv_bfloat162 a = __floats2bfloat162_rn(pv.x, pv.y), b = __floats2bfloat162_rn(pv.z, pv.w);
+      uint2 u;
+      u.x = *reinterpret_cast<uint32_t*>(&a);
+      u.y = *reinterpret_cast<uint32_t*>(&b);
+      reinterpret_cast<uint2*>(shadow)[i] = u;
+    }
+  }
+  // tail
+  for (size_t i = n4 * 4 + (size_t)blockIdx.x * NT + threadIdx.x; i < count; i += (size_t)gridDim.x * NT) {
+    float mm = m[i] + (g[i] - m[i]) * (1.f - b1);
+    float vv = v[i] + (g[i] * g[i] - v[i]) * (1.f - b2);
+    float pp = p[i] - alpha * mm / (sqrtf(vv) + eps);
+    m[i] = mm; v[i] = vv; p[i] = pp;
+    if (shadow) shadow[i] = __float2bfloat16_rn(pp);
+  }
+}
+
+template <typename TS, typename TD>
+__global__ void __launch_bounds__(NT) cast_kernel(const TS* __restrict__ s, TD* __restrict__ d, size_t count) {
+  for (size_t i = (size_t)blockIdx.x * NT + threadIdx.x; i < count; i += (size_t)gridDim.x * NT) stf(d + i, ldf(s + i));
+}
+
+template <typename TS, typename TD>
+__global__ void __launch_bounds__(NT) copy_tensor_kernel(TView s, TView d, long long total) {
+  const TS* sp = reinterpret_cast<const TS*>(s.data);
+  TD* dp = reinterpret_cast<TD*>(d.data);
+  for (long long i = (long long)blockIdx.x * NT + threadIdx.x; i < total; i += (long long)gridDim.x * NT) {
+    int c = (int)(i % d.c);
+    long long p = i / d.c;
+    int w = (int)(p % d.w); p /= d.w;
+    int h = (int)(p % d.h);
+    int n = (int)(p / d.h);
+    stf(dp + pix_offset(d, n, h, w) + c, ldf(sp + pix_offset(s, n, h, w) + c));
+  }
+}
+
+__global__ void __launch_bounds__(NT) scale_kernel(float* p, size_t count, float s) {
+  for (size_t i = (size_t)blockIdx.x * NT + threadIdx.x; i < count; i += (size_t)gridDim.x * NT) p[i] *= s;
+}
+
+// ---- Conv2DTranspose(k=2, s=2): out[2i+a,2j+b,o] = sum_c in[i,j,c] K[a,b,o,c] + bias[o] -------------
+template <typename T>
+__global__ void __launch_bounds__(NT)
+convT2_fprop_kernel(TView x, const T* __restrict__ k, const float* __restrict__ bias, TView y, long long total) {
+  const T* xp = reinterpret_cast<const T*>(x.data);
+  T* yp = reinterpret_cast<T*>(y.data);
+  const int Cin = x.c, Cout = y.c;
+  for (long long i = (long long)blockIdx.x * NT + threadIdx.x; i < total; i += (long long)gridDim.x * NT) {
+    int o = (int)(i % Cout);
+    long long p = i / Cout;
+    int ow = (int)(p % y.w); p /= y.w;
+    int oh = (int)(p % y.h);
+    int n = (int)(p / y.h);
+    const T* src = xp + pix_offset(x, n, oh / 2, ow / 2);
+    const T* kk = k + (((long long)(oh & 1) * 2 + (ow & 1)) * Cout + o) * Cin;
+    float acc = bias ? bias[o] : 0.f;
+    for (int c = 0; c < Cin; ++c) acc += ldf(src + c) * ldf(kk + c);
+    stf(yp + pix_offset(y, n, oh, ow) + o, acc);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(NT)
+convT2_dgrad_kernel(TView dy, const T* __restrict__ k, TView dx, long long total) {
+  const T* dyp = reinterpret_cast<const T*>(dy.data);
+  T* dxp = reinterpret_cast<T*>(dx.data);
+  const int Cin = dx.c, Cout = dy.c;
+  for (long long i = (long long)blockIdx.x * NT + threadIdx.x; i < total; i += (long long)gridDim.x * NT) {
+    int c = (int)(i % Cin);
+    long long p = i / Cin;
+    int w = (int)(p % dx.w); p /= dx.w;
+    int h = (int)(p % dx.h);
+    int n = (int)(p / dx.h);
+    float acc = 0.f;
+    for (int a = 0; a < 2; ++a)
+      for (int b = 0; b < 2; ++b) {
+        const T* g = dyp + pix_offset(dy, n, 2 * h + a, 2 * w + b);
+        const T* kk = k + ((long long)(a * 2 + b) * Cout) * Cin + c;
+        for (int o = 0; o < Cout; ++o) acc += ldf(g + o) * ldf(kk + (long long)o * Cin);
+      }
+    stf(dxp + pix_offset(dx, n, h, w) + c, acc);
+  }
+}
+
+// dK[a,b,o,c] = sum_{n,i,j} dy[n,2i+a,2j+b,o] * x[n,i,j,c]; one block per (a,b,o), threads over c, atomics-free
+template <typename T>
+__global__ void __launch_bounds__(NT)
+convT2_wgrad_kernel(TView x, TView dy, float* __restrict__ dk, float* __restrict__ dbias) {
+  const T* xp = reinterpret_cast<const T*>(x.data);
+  const T* dyp = reinterpret_cast<const T*>(dy.data);
+  const int Cin = x.c, Cout = dy.c;
+  const int o = blockIdx.x % Cout, ab = blockIdx.x / Cout;
+  const int a = ab / 2, b = ab % 2;
+  const long long npix = (long long)x.n * x.h * x.w;
+  for (int c = threadIdx.x; c < Cin; c += NT) {
+    float acc = 0.f;
+    for (long long p = 0; p < npix; ++p) {
+      int w = (int)(p % x.w);
+      long long q = p / x.w;
+      int h = (int)(q % x.h);
+      int n = (int)(q / x.h);
+      acc += ldf(dyp + pix_offset(dy, n, 2 * h + a, 2 * w + b) + o) * ldf(xp + pix_offset(x, n, h, w) + c);
+    }
+    dk[((long long)ab * Cout + o) * Cin + c] = acc;
+  }
+  if (dbias && ab == 0 && threadIdx.x == 0) {
+    float acc = 0.f;
+    const long long opix = (long long)dy.n * dy.h * dy.w;
+    for (long long p = 0; p < opix; ++p) {
+      int w = (int)(p % dy.w);
+      long long q = p / dy.w;
+      int h = (int)(q % dy.h);
+      int n = (int)(q / dy.h);
+      acc += ldf(dyp + pix_offset(dy, n, h, w) + o);
+    }
+    dbias[o] += acc;
+  }
+}
+
+}  // namespace
+
+int adam_advance(int32_t* step, cudaStream_t st) {
+  adam_advance_kernel<<<1, 32, 0, st>>>(step);
+  return check_launch("adam_advance_kernel");
+}
+
+int adam_step(float* p, const float* g, float* m, float* v, size_t count, const float* hyper, const int32_t* step,
+              void* shadow, cudaStream_t st) {
+  B200_REQUIRE(((uintptr_t)p % 16 == 0) && ((uintptr_t)g % 16 == 0) && ((uintptr_t)m % 16 == 0) &&
+                   ((uintptr_t)v % 16 == 0) && ((uintptr_t)shadow % 8 == 0),
+               B200_ERR_BAD_ARG, "adam_step: buffers must be 16-byte aligned");
+  adam_kernel<<<grid_for((long long)count, 4), NT, 0, st>>>(p, g, m, v, count, hyper, step,
+                                                            reinterpret_cast<__nv_bfloat16*>(shadow));
+  return check_launch("adam_kernel");
+}
+
+int cast(const void* src, int sdt, void* dst, int ddt, size_t count, cudaStream_t st) {
+  const int grid = grid_for((long long)count);
+  if (sdt == B200_F32 && ddt == B200_BF16)
+    cast_kernel<float, __nv_bfloat16><<<grid, NT, 0, st>>>((const float*)src, (__nv_bfloat16*)dst, count);
+  else if (sdt == B200_BF16 && ddt == B200_F32)
+    cast_kernel<__nv_bfloat16, float><<<grid, NT, 0, st>>>((const __nv_bfloat16*)src, (float*)dst, count);
+  else if (sdt == B200_F32 && ddt == B200_F32)
+    cast_kernel<float, float><<<grid, NT, 0, st>>>((const float*)src, (float*)dst, count);
+  else
+    cast_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, NT, 0, st>>>((const __nv_bfloat16*)src, (__nv_bfloat16*)dst, count);
+  return check_launch("cast_kernel");
+}
+
+int copy_tensor(const b200_tensor* s, const b200_tensor* d, cudaStream_t st) {
+  B200_REQUIRE(same_shape(s, d), B200_ERR_BAD_ARG, "copy_tensor: shape mismatch");
+  long long total = (long long)d->n * d->h * d->w * d->c;
+  TView sv = view_of(s), dv = view_of(d);
+  const int grid = grid_for(total);
+  if (s->dtype == B200_F32 && d->dtype == B200_BF16) copy_tensor_kernel<float, __nv_bfloat16><<<grid, NT, 0, st>>>(sv, dv, total);
+  else if (s->dtype == B200_BF16 && d->dtype == B200_F32) copy_tensor_kernel<__nv_bfloat16, float><<<grid, NT, 0, st>>>(sv, dv, total);
+  else if (s->dtype == B200_F32) copy_tensor_kernel<float, float><<<grid, NT, 0, st>>>(sv, dv, total);
+  else copy_tensor_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, NT, 0, st>>>(sv, dv, total);
+  return check_launch("copy_tensor_kernel");
+}
+
+int scale_inplace(float* p, size_t count, float s, cudaStream_t st) {
+  scale_kernel<<<grid_for((long long)count), NT, 0, st>>>(p, count, s);
+  return check_launch("scale_kernel");
+}
+
+int convT2_fprop(const b200_tensor* x, const void* kernel, const float* bias, int cout, const b200_tensor* y,
+                 cudaStream_t st) {
+  B200_REQUIRE(y->h == 2 * x->h && y->w == 2 * x->w && y->n == x->n && y->c == cout && x->dtype == y->dtype,
+               B200_ERR_BAD_ARG, "convT2x2_fprop: shape mismatch");
+  long long total = (long long)y->n * y->h * y->w * y->c;
+  TView xv = view_of(x), yv = view_of(y);
+  B200_DISPATCH_DTYPE(x->dtype, T, {
+    convT2_fprop_kernel<T><<<grid_for(total), NT, 0, st>>>(xv, (const T*)kernel, bias, yv, total);
+  });
+  return check_launch("convT2_fprop_kernel");
+}
+
+int convT2_dgrad(const b200_tensor* dy, const void* kernel, int cout, const b200_tensor* dx, cudaStream_t st) {
+  B200_REQUIRE(dy->h == 2 * dx->h && dy->w == 2 * dx->w && dy->n == dx->n && dy->c == cout && dx->dtype == dy->dtype,
+               B200_ERR_BAD_ARG, "convT2x2_dgrad: shape mismatch");
+  long long total = (long long)dx->n * dx->h * dx->w * dx->c;
+  TView dv = view_of(dy), xv = view_of(dx);
+  B200_DISPATCH_DTYPE(dx->dtype, T, {
+    convT2_dgrad_kernel<T><<<grid_for(total), NT, 0, st>>>(dv, (const T*)kernel, xv, total);
+  });
+  return check_launch("convT2_dgrad_kernel");
+}
+
+int convT2_wgrad(const b200_tensor* x, const b200_tensor* dy, float* dk, float* dbias, cudaStream_t st) {
+  B200_REQUIRE(dy->h == 2 * x->h && dy->w == 2 * x->w && dy->n == x->n && x->dtype == dy->dtype, B200_ERR_BAD_ARG,
+               "convT2x2_wgrad: shape mismatch");
+  TView xv = view_of(x), dv = view_of(dy);
+  B200_DISPATCH_DTYPE(x->dtype, T, { convT2_wgrad_kernel<T><<<4 * dy->c, NT, 0, st>>>(xv, dv, dk, dbias); });
+  return check_launch("convT2_wgrad_kernel");
+}
+
+}  // namespace b200

@@ -1,0 +1,232 @@
+// 3x3 convolution weight gradient on tcgen05 tensor cores.
+//
+//   dW[tap][ci][co] = sum over pixels  x[pixel + tap][ci] * dz[pixel][co]
+//
+// is a GEMM whose reduction (K) dimension is the pixel index.  Both operands are read
+// straight from their NHWC tiles in shared memory as MN-major UMMA operands (channels
+// contiguous, one pixel per 128-byte row), so no transposed copy of the activations is ever
+// made.  One CTA owns a 64(ci) x 64(co) block of all nine taps and walks a contiguous range of
+// 16x8-pixel tiles; per tile it loads ONE halo window of x ({64ch,10,18} TMA box, shared with
+// the fprop kernel's geometry) and one dz tile, and issues, per 16-pixel K step, five M=128
+// MMAs: the 128 rows are TWO taps x 64 input channels -- the second tap is the same window
+// shifted, expressed through the descriptor's leading-byte-offset.  The 9x64x64 fp32 partial
+// sums stay in TMEM (5 x 64 columns) until the CTA has consumed all its tiles, then go to a
+// workspace that a second kernel reduces deterministically over the CTAs.
+//
+// Replaces the autodiff (filter gradient) of keras Conv2D at
+// Super_resolution/code/train_adaptive_unet.py:202,207,259 (reference: /root/reference).
+#include <cuda.h>
+
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace b200 {
+
+using namespace ptx;
+
+int make_act_tmap(CUtensorMap* m, const b200_tensor* t, int box_w, int box_h);
+
+namespace {
+
+constexpr int TILE_H = 16, TILE_W = 8;
+constexpr int WIN_W = TILE_W + 2, WIN_H = TILE_H + 2;
+constexpr int WIN_BYTES = WIN_W * WIN_H * 128;   // 23040
+constexpr int WIN_STAGE = 23552;
+constexpr int DZ_BYTES = TILE_H * TILE_W * 128;  // 16384
+constexpr int STAGE = WIN_STAGE + DZ_BYTES;      // 39936
+constexpr int NSTAGES = 5;
+constexpr int NTHREADS = 192;
+constexpr int NPAIRS = 5;
+
+struct WgradParams {
+  int N, H, W, Cin, Cout;
+  int tiles_h, tiles_w, total_tiles, splits, cblocks, oblocks;
+  float* partial;  // [splits][9][Cin][Cout]
+};
+
+// first tap of each pair, and the distance (in window pixel rows) to the second tap
+__device__ __forceinline__ int pair_first(int pi) { return pi < 4 ? 2 * pi : 7; }
+__device__ __forceinline__ int tap_row(int t) { return (t / 3) * WIN_W + (t % 3); }
+
+__global__ void __launch_bounds__(NTHREADS, 1)
+wgrad3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_dz,
+                   const WgradParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bar_full[NSTAGES], bar_empty[NSTAGES], bar_done;
+  __shared__ uint32_t tmem_base_smem;
+
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
+
+  // work decomposition: blockIdx.x -> (split, ci block, co block)
+  int b = blockIdx.x;
+  const int ob = b % p.oblocks; b /= p.oblocks;
+  const int cb = b % p.cblocks;
+  const int s = b / p.cblocks;
+  const int t_begin = (int)((long long)p.total_tiles * s / p.splits);
+  const int t_end = (int)((long long)p.total_tiles * (s + 1) / p.splits);
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < NSTAGES; ++i) { mbar_init(smem_u32(&bar_full[i]), 1); mbar_init(smem_u32(&bar_empty[i]), 1); }
+    mbar_init(smem_u32(&bar_done), 1);
+    fence_barrier_init();
+  }
+  if (warp == 0 && lane == 0) { prefetch_tmap(&tm_x); prefetch_tmap(&tm_dz); }
+  if (warp == 1) { tmem_alloc(smem_u32(&tmem_base_smem), 512); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int st = 0, ph = 0;
+      for (int t = t_begin; t < t_end; ++t) {
+        int q = t;
+        const int tw = q % p.tiles_w; q /= p.tiles_w;
+        const int th = q % p.tiles_h;
+        const int n = q / p.tiles_h;
+        mbar_wait(smem_u32(&bar_empty[st]), ph ^ 1);
+        const uint32_t base = smem0 + st * STAGE;
+        mbar_arrive_expect_tx(smem_u32(&bar_full[st]), WIN_BYTES + DZ_BYTES);
+        tma_load_4d(base, &tm_x, smem_u32(&bar_full[st]), cb * 64, tw * TILE_W - 1, th * TILE_H - 1, n);
+        tma_load_4d(base + WIN_STAGE, &tm_dz, smem_u32(&bar_full[st]), ob * 64, tw * TILE_W, th * TILE_H, n);
+        if (++st == NSTAGES) { st = 0; ph ^= 1; }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = idesc_bf16(128, 64, 1, 1);
+      int st = 0, ph = 0;
+      for (int t = t_begin; t < t_end; ++t) {
+        mbar_wait(smem_u32(&bar_full[st]), ph);
+        tc_fence_after();
+        const uint32_t win = smem0 + st * STAGE;
+        const uint32_t dz = win + WIN_STAGE;
+#pragma unroll 1
+        for (int ks = 0; ks < 8; ++ks) {
+          const uint64_t bdesc = smem_desc_sw128(dz + ks * 2048, 0, 1024);
+          const uint32_t acc = (t > t_begin || ks > 0) ? 1u : 0u;
+#pragma unroll
+          for (int pi = 0; pi < NPAIRS; ++pi) {
+            const int t0 = pair_first(pi);
+            const uint32_t a_addr = win + (uint32_t)tap_row(t0) * 128u + (uint32_t)ks * 2u * (WIN_W * 128u);
+            const uint32_t lbo = (uint32_t)(tap_row(t0 + 1) - tap_row(t0)) * 128u;
+            umma_bf16(tmem_base + pi * 64, smem_desc_sw128(a_addr, lbo, WIN_W * 128), bdesc, idesc, acc);
+          }
+        }
+        umma_commit(smem_u32(&bar_empty[st]));
+        if (++st == NSTAGES) { st = 0; ph ^= 1; }
+      }
+      umma_commit(smem_u32(&bar_done));
+    }
+    __syncwarp();
+  } else {
+    const int q = warp % 4;
+    const int r = q * 32 + lane;          // TMEM lane = (tap of the pair, ci)
+    const int half = r / 64, ci = r % 64;
+    mbar_wait(smem_u32(&bar_done), 0);
+    tc_fence_after();
+    for (int pi = 0; pi < NPAIRS; ++pi) {
+      const int tap = pair_first(pi) + half;
+      const bool dup = (pi == 4 && half == 0);   // rows 0..63 of the last pair repeat tap 7
+      float* dst = p.partial + (((long long)s * 9 + tap) * p.Cin + cb * 64 + ci) * p.Cout + ob * 64;
+      for (int c0 = 0; c0 < 64; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(pi * 64 + c0), v);
+        tmem_ld_wait();
+        if (!dup) {
+#pragma unroll
+          for (int i = 0; i < 32; i += 4)
+            *reinterpret_cast<float4*>(dst + c0 + i) =
+                make_float4(__uint_as_float(v[i]), __uint_as_float(v[i + 1]), __uint_as_float(v[i + 2]),
+                            __uint_as_float(v[i + 3]));
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+}
+
+__global__ void __launch_bounds__(256)
+wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw, long long count, int splits) {
+  const long long n4 = count / 4;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n4; i += (long long)gridDim.x * 256) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int s = 0; s < splits; ++s) {
+      const float4 v = reinterpret_cast<const float4*>(partial + (long long)s * count)[i];
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    reinterpret_cast<float4*>(dw)[i] = acc;
+  }
+}
+
+inline void plan(const b200_tensor* x, const b200_tensor* dy, WgradParams& p) {
+  p.N = x->n; p.H = x->h; p.W = x->w; p.Cin = x->c; p.Cout = dy->c;
+  p.tiles_h = (p.H + TILE_H - 1) / TILE_H;
+  p.tiles_w = (p.W + TILE_W - 1) / TILE_W;
+  p.total_tiles = p.N * p.tiles_h * p.tiles_w;
+  p.cblocks = p.Cin / 64;
+  p.oblocks = p.Cout / 64;
+  const int pairs = p.cblocks * p.oblocks;
+  int splits = (sm_count() + pairs - 1) / pairs;
+  if (splits > p.total_tiles) splits = p.total_tiles;
+  if (splits < 1) splits = 1;
+  p.splits = splits;
+}
+
+}  // namespace
+
+bool wgrad_tc_supported(const b200_tensor* x, const b200_tensor* dy, int ks) {
+  if (ks != 3) return false;
+  if (x->dtype != B200_BF16 || dy->dtype != B200_BF16) return false;
+  if (x->c % 64 != 0 || dy->c % 64 != 0) return false;
+  auto ok = [](const b200_tensor* t) {
+    return ((uintptr_t)t->data % 16 == 0) && (t->stride_w * 2) % 16 == 0 && (t->stride_h * 2) % 16 == 0 &&
+           (t->stride_n * 2) % 16 == 0;
+  };
+  return ok(x) && ok(dy);
+}
+
+size_t wgrad_tc_workspace(const b200_tensor* x, const b200_tensor* dy) {
+  WgradParams p;
+  plan(x, dy, p);
+  return sizeof(float) * (size_t)p.splits * 9 * p.Cin * p.Cout;
+}
+
+int wgrad_tc_launch(const b200_tensor* x, const b200_tensor* dy, float* dw, void* ws, size_t ws_bytes,
+                    cudaStream_t st) {
+  WgradParams p;
+  plan(x, dy, p);
+  const size_t need = sizeof(float) * (size_t)p.splits * 9 * p.Cin * p.Cout;
+  B200_REQUIRE(ws && ws_bytes >= need, B200_ERR_BAD_ARG, "conv2d_wgrad: workspace too small (%zu < %zu bytes)",
+               ws_bytes, need);
+  B200_REQUIRE((uintptr_t)ws % 16 == 0 && (uintptr_t)dw % 16 == 0, B200_ERR_BAD_ARG,
+               "conv2d_wgrad: workspace/dw must be 16-byte aligned");
+  p.partial = reinterpret_cast<float*>(ws);
+  CUtensorMap tm_x, tm_dz;
+  int rc = make_act_tmap(&tm_x, x, WIN_W, WIN_H);
+  if (rc) return rc;
+  rc = make_act_tmap(&tm_dz, dy, TILE_W, TILE_H);
+  if (rc) return rc;
+  const size_t smem = 1024 + (size_t)NSTAGES * STAGE;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(wgrad3x3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    attr_set = true;
+  }
+  const int grid = p.splits * p.cblocks * p.oblocks;
+  wgrad3x3_tc_kernel<<<grid, NTHREADS, smem, st>>>(tm_x, tm_dz, p);
+  int rc2 = check_launch("wgrad3x3_tc_kernel");
+  if (rc2) return rc2;
+  const long long count = 9LL * p.Cin * p.Cout;
+  long long blocks = (count / 4 + 255) / 256;
+  if (blocks > 4LL * sm_count()) blocks = 4LL * sm_count();
+  wgrad_reduce_kernel<<<(int)blocks, 256, 0, st>>>(p.partial, dw, count, p.splits);
+  return check_launch("wgrad_reduce_kernel");
+}
+
+}  // namespace b200

@@ -1,0 +1,264 @@
+"""Host-side operator wrappers: torch tensors in, C-ABI calls out.
+
+PyTorch is used here only as the owner of device memory and streams; every
+computation is a launch of one of the library's sm_100a kernels on torch's
+current CUDA stream.  Tensors are NHWC (channel stride 1); channel-slice views of
+wider buffers are passed with their real strides (concat written in place).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import _ffi
+from ._ffi import (ACT_NONE, ACT_RELU, ACT_SIGMOID, ALGO_AUTO, ALGO_SIMT, ALGO_TCGEN05, BF16, F32, Filter, Tensor,
+                   check)
+
+_DT = {torch.float32: F32, torch.bfloat16: BF16}
+
+
+def lib():
+    return _ffi.load()
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def tdesc(t: torch.Tensor) -> Tensor:
+    """b200_tensor for an NHWC torch tensor (any strides with channel stride 1)."""
+    if t.dim() != 4:
+        raise ValueError(f"expected NHWC tensor, got shape {tuple(t.shape)}")
+    if t.shape[3] > 1 and t.stride(3) != 1:
+        raise ValueError("channel stride must be 1")
+    if not t.is_cuda:
+        raise _ffi.B200Error("b200 ops need CUDA tensors: there is no CPU fallback")
+    n, h, w, c = t.shape
+    return Tensor(t.data_ptr(), n, h, w, c, t.stride(0), t.stride(1), t.stride(2), _DT[t.dtype], 0)
+
+
+class ConvFilter:
+    """A Conv2D kernel in the layouts the device code consumes (struct b200_filter)."""
+
+    def __init__(self, hwio: torch.Tensor, packed: bool = True):
+        self.hwio = hwio.contiguous()
+        self.kh, self.kw, self.cin, self.cout = self.hwio.shape
+        self.ohwi = None
+        if packed:
+            self.ohwi = torch.empty((self.kh, self.kw, self.cout, self.cin), dtype=hwio.dtype, device=hwio.device)
+            self.repack()
+
+    def repack(self):
+        if self.ohwi is not None:
+            check(lib().b200_filter_pack(_ptr(self.hwio), _ptr(self.ohwi), self.kh, self.kw, self.cin, self.cout,
+                                         _DT[self.hwio.dtype], _stream()), "filter_pack")
+
+    def struct(self) -> Filter:
+        return Filter(self.hwio.data_ptr(), None if self.ohwi is None else self.ohwi.data_ptr(), self.kh, self.kw,
+                      self.cin, self.cout, _DT[self.hwio.dtype], 0)
+
+
+# ---- convolution -------------------------------------------------------------------
+def conv2d_fprop(x, filt: ConvFilter, bias, y, act=ACT_NONE, algo=ALGO_AUTO):
+    check(lib().b200_conv2d_fprop(tdesc(x), filt.struct(), _ptr(bias), tdesc(y), act, algo, _stream()), "conv2d_fprop")
+    return y
+
+
+def conv2d_dgrad(dy, filt: ConvFilter, dx, accumulate=False, algo=ALGO_AUTO):
+    check(lib().b200_conv2d_dgrad(tdesc(dy), filt.struct(), tdesc(dx), int(accumulate), algo, _stream()), "conv2d_dgrad")
+    return dx
+
+
+def conv2d_wgrad_workspace(x, dy, kh, kw, algo=ALGO_AUTO) -> int:
+    return int(lib().b200_conv2d_wgrad_workspace(tdesc(x), tdesc(dy), kh, kw, algo))
+
+
+def conv2d_wgrad(x, dy, kh, kw, dw, workspace=None, algo=ALGO_AUTO):
+    ws_bytes = 0 if workspace is None else workspace.numel() * workspace.element_size()
+    check(lib().b200_conv2d_wgrad(tdesc(x), tdesc(dy), kh, kw, _ptr(dw), _ptr(workspace), ws_bytes, algo, _stream()),
+          "conv2d_wgrad")
+    return dw
+
+
+def convT2x2_fprop(x, kernel, bias, y):
+    check(lib().b200_convT2x2_fprop(tdesc(x), _ptr(kernel), _ptr(bias), kernel.shape[2], tdesc(y), _stream()), "convT2x2_fprop")
+    return y
+
+
+def convT2x2_dgrad(dy, kernel, dx):
+    check(lib().b200_convT2x2_dgrad(tdesc(dy), _ptr(kernel), kernel.shape[2], tdesc(dx), _stream()), "convT2x2_dgrad")
+    return dx
+
+
+def convT2x2_wgrad(x, dy, dkernel, dbias):
+    check(lib().b200_convT2x2_wgrad(tdesc(x), tdesc(dy), _ptr(dkernel), _ptr(dbias), _stream()), "convT2x2_wgrad")
+
+
+# ---- normalisation / activation -------------------------------------------------------
+def bias_act_bwd(dy, y, act, dz, dbias=None):
+    check(lib().b200_bias_act_bwd(tdesc(dy), tdesc(y), act, tdesc(dz), _ptr(dbias), _stream()), "bias_act_bwd")
+    return dz
+
+
+def layernorm_fwd(z, gamma, beta, eps, relu, y, mean, rstd):
+    check(lib().b200_layernorm_fwd(tdesc(z), _ptr(gamma), _ptr(beta), eps, int(relu), tdesc(y), _ptr(mean), _ptr(rstd),
+                                   _stream()), "layernorm_fwd")
+    return y
+
+
+def layernorm_bwd(dy, z, mean, rstd, gamma, beta, relu, dz, dgamma, dbeta, dbias):
+    check(lib().b200_layernorm_bwd(tdesc(dy), tdesc(z), _ptr(mean), _ptr(rstd), _ptr(gamma), _ptr(beta), int(relu),
+                                   tdesc(dz), _ptr(dgamma), _ptr(dbeta), _ptr(dbias), _stream()), "layernorm_bwd")
+    return dz
+
+
+def batchnorm_fwd_train(z, gamma, beta, eps, momentum, relu, y, save_mean, save_rstd, moving_mean, moving_var, stats_ws):
+    check(lib().b200_batchnorm_fwd_train(tdesc(z), _ptr(gamma), _ptr(beta), eps, momentum, int(relu), tdesc(y),
+                                         _ptr(save_mean), _ptr(save_rstd), _ptr(moving_mean), _ptr(moving_var),
+                                         _ptr(stats_ws), _stream()), "batchnorm_fwd_train")
+    return y
+
+
+def batchnorm_fwd_infer(z, gamma, beta, eps, relu, moving_mean, moving_var, y):
+    check(lib().b200_batchnorm_fwd_infer(tdesc(z), _ptr(gamma), _ptr(beta), eps, int(relu), _ptr(moving_mean),
+                                         _ptr(moving_var), tdesc(y), _stream()), "batchnorm_fwd_infer")
+    return y
+
+
+def batchnorm_bwd(dy, z, save_mean, save_rstd, gamma, beta, relu, dz, dgamma, dbeta, stats_ws):
+    check(lib().b200_batchnorm_bwd(tdesc(dy), tdesc(z), _ptr(save_mean), _ptr(save_rstd), _ptr(gamma), _ptr(beta),
+                                   int(relu), tdesc(dz), _ptr(dgamma), _ptr(dbeta), None, _ptr(stats_ws), _stream()),
+          "batchnorm_bwd")
+    return dz
+
+
+# ---- resampling --------------------------------------------------------------------------
+def resize_extent(extent: int, scale: float) -> int:
+    return int(lib().b200_resize_extent(int(extent), float(scale)))
+
+
+class ResamplePlan:
+    """Span tables (forward and transposed) for one axis, uploaded to the device."""
+
+    def __init__(self, in_size: int, out_size: int, antialias: bool, device):
+        L = lib()
+        self.in_size, self.out_size = in_size, out_size
+        taps = int(L.b200_resample_taps(in_size, out_size, int(antialias)))
+        starts = np.zeros(out_size, dtype=np.int32)
+        weights = np.zeros((out_size, taps), dtype=np.float32)
+        check(L.b200_resample_plan(in_size, out_size, int(antialias), starts.ctypes.data, weights.ctypes.data, taps),
+              "resample_plan")
+        t_taps = int(L.b200_resample_plan_transpose(in_size, out_size, taps, starts.ctypes.data, weights.ctypes.data,
+                                                    None, None, 0))
+        t_starts = np.zeros(in_size, dtype=np.int32)
+        t_weights = np.zeros((in_size, t_taps), dtype=np.float32)
+        rc = L.b200_resample_plan_transpose(in_size, out_size, taps, starts.ctypes.data, weights.ctypes.data,
+                                            t_starts.ctypes.data, t_weights.ctypes.data, t_taps)
+        if rc < 0:
+            check(rc, "resample_plan_transpose")
+        self.taps, self.t_taps = taps, t_taps
+        self.host = (starts, weights, t_starts, t_weights)
+        self.starts = torch.from_numpy(starts).to(device)
+        self.weights = torch.from_numpy(weights).to(device)
+        self.t_starts = torch.from_numpy(t_starts).to(device)
+        self.t_weights = torch.from_numpy(t_weights).to(device)
+
+
+def resample2d(x, y, plan_h: ResamplePlan, plan_w: ResamplePlan, accumulate=False):
+    check(lib().b200_resample2d(tdesc(x), tdesc(y), _ptr(plan_h.starts), _ptr(plan_h.weights), plan_h.taps,
+                                _ptr(plan_w.starts), _ptr(plan_w.weights), plan_w.taps, int(accumulate), _stream()),
+          "resample2d")
+    return y
+
+
+def resample2d_bwd(dy, dx, plan_h: ResamplePlan, plan_w: ResamplePlan, accumulate=False):
+    """dx (+)= R^T dy: the same gather kernel over the transposed tables."""
+    check(lib().b200_resample2d(tdesc(dy), tdesc(dx), _ptr(plan_h.t_starts), _ptr(plan_h.t_weights), plan_h.t_taps,
+                                _ptr(plan_w.t_starts), _ptr(plan_w.t_weights), plan_w.t_taps, int(accumulate),
+                                _stream()), "resample2d(bwd)")
+    return dx
+
+
+def maxpool2_fwd(x, y):
+    check(lib().b200_maxpool2_fwd(tdesc(x), tdesc(y), _stream()), "maxpool2_fwd")
+    return y
+
+
+def maxpool2_bwd(x, y, dy, dx, accumulate=False):
+    check(lib().b200_maxpool2_bwd(tdesc(x), tdesc(y), tdesc(dy), tdesc(dx), int(accumulate), _stream()), "maxpool2_bwd")
+    return dx
+
+
+# ---- head / losses ---------------------------------------------------------------------------
+def clipadd_fwd(inp, res, y):
+    check(lib().b200_clipadd_fwd(tdesc(inp), tdesc(res), tdesc(y), _stream()), "clipadd_fwd")
+    return y
+
+
+def clipadd_bwd(inp, res, dy, dres):
+    check(lib().b200_clipadd_bwd(tdesc(inp), tdesc(res), tdesc(dy), tdesc(dres), _stream()), "clipadd_bwd")
+    return dres
+
+
+def _opt_desc(t):
+    return tdesc(t) if t is not None else Tensor(None, 0, 0, 0, 0, 0, 0, 0, 0, 0)
+
+
+def sr_loss(pred, target, kind, eps, grad_scale, out, dpred, ws):
+    check(lib().b200_sr_loss(tdesc(pred), tdesc(target), kind, eps, grad_scale, _ptr(out), _opt_desc(dpred), _ptr(ws),
+                             _stream()), "sr_loss")
+    return out
+
+
+def bce_dice_loss(pred, target, bce_w, dice_w, grad_scale, out, dpred, ws):
+    check(lib().b200_bce_dice_loss(tdesc(pred), tdesc(target), bce_w, dice_w, grad_scale, _ptr(out), _opt_desc(dpred),
+                                   _ptr(ws), _stream()), "bce_dice_loss")
+    return out
+
+
+def softmax_fwd(z, p):
+    check(lib().b200_softmax_fwd(tdesc(z), tdesc(p), _stream()), "softmax_fwd")
+    return p
+
+
+def softmax_ce_loss(prob, labels, grad_scale, out, dlogits, ws):
+    check(lib().b200_softmax_ce_loss(tdesc(prob), _ptr(labels), grad_scale, _ptr(out), _opt_desc(dlogits), _ptr(ws),
+                                     _stream()), "softmax_ce_loss")
+    return out
+
+
+# ---- optimiser / utilities ------------------------------------------------------------------------
+def adam_advance(step):
+    check(lib().b200_adam_advance(_ptr(step), _stream()), "adam_advance")
+
+
+def adam_step(p, g, m, v, hyper, step, shadow=None):
+    check(lib().b200_adam_step(_ptr(p), _ptr(g), _ptr(m), _ptr(v), p.numel(), _ptr(hyper), _ptr(step), _ptr(shadow),
+                               _stream()), "adam_step")
+
+
+def cast(src, dst):
+    check(lib().b200_cast(_ptr(src), _DT[src.dtype], _ptr(dst), _DT[dst.dtype], src.numel(), _stream()), "cast")
+    return dst
+
+
+def copy_tensor(src, dst):
+    check(lib().b200_copy_tensor(tdesc(src), tdesc(dst), _stream()), "copy_tensor")
+    return dst
+
+
+def scale_inplace(p, s):
+    check(lib().b200_scale_inplace(_ptr(p), p.numel(), float(s), _stream()), "scale_inplace")
+
+
+def umma_probe(a, b, start_bytes, sbo_bytes, lbo_bytes, mn_major, out):
+    check(lib().b200_debug_umma_probe(_ptr(a), a.shape[0], _ptr(b), start_bytes, sbo_bytes, lbo_bytes, int(mn_major),
+                                      _ptr(out), _stream()), "umma_probe")
+    return out

@@ -1,0 +1,208 @@
+/*
+ * b200_unet.h -- C ABI of the B200-native adaptive-depth U-Net hot path.
+ *
+ * The reference (KunalNN/Adaptive-Depth-U-Net-...) has no FFI of its own: its
+ * "operator API" for this path is the Keras 3 layer API as used by
+ *   Super_resolution/code/train_adaptive_unet.py:200-287 (conv_block, builder),
+ *   shared/custom_layers.py:85-139 (ResizeByScale, ResizeToMatch, ClippedResidualAdd),
+ *   Segmenation/code/train_adaptive_unet.py:258-362, Segmenation/code/unet_vinillia.py:42-99.
+ * Each entry point below replaces the TF/Keras kernel(s) behind one of those call
+ * sites (cited per function).  INTEGRATION.md shows the ctypes binding.
+ *
+ * Conventions
+ *   - Plain C.  Every pointer inside a b200_tensor / b200_filter and every
+ *     pointer argument not marked "host" is a DEVICE pointer owned by the caller.
+ *     The library never allocates device memory and keeps no per-tensor state.
+ *   - Activations are NHWC with channel stride 1; strides are in ELEMENTS, so a
+ *     channel slice of a wider buffer (concat written in place) is a valid tensor.
+ *   - Every function returns 0 on success or a negative b200_status; a message is
+ *     available from b200_last_error() (thread local).  Unsupported shapes fail
+ *     loudly -- there is no CPU fallback.
+ *   - All launches are asynchronous on `stream` (a cudaStream_t passed as void*).
+ */
+#ifndef B200_UNET_H_
+#define B200_UNET_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum b200_status {
+  B200_OK = 0,
+  B200_ERR_BAD_ARG = -1,
+  B200_ERR_UNSUPPORTED = -2,
+  B200_ERR_LAUNCH = -3
+} b200_status;
+
+typedef enum b200_dtype { B200_F32 = 0, B200_BF16 = 1 } b200_dtype;
+
+/* Epilogue / activation selector. */
+typedef enum b200_act {
+  B200_ACT_NONE = 0,
+  B200_ACT_RELU = 1,
+  B200_ACT_SIGMOID = 2
+} b200_act;
+
+/* Kernel selection for the convolutions. AUTO picks tcgen05 when the shape is
+ * supported and falls back to the SIMT kernel for the rest (Cin = 3, fp32). */
+typedef enum b200_algo { B200_ALGO_AUTO = 0, B200_ALGO_SIMT = 1, B200_ALGO_TCGEN05 = 2 } b200_algo;
+
+typedef enum b200_sr_loss_kind { B200_LOSS_CHARBONNIER = 0, B200_LOSS_L1 = 1, B200_LOSS_MSE = 2 } b200_sr_loss_kind;
+
+typedef struct b200_tensor {
+  void* data;                 /* element (n=0,h=0,w=0,c=0) */
+  int32_t n, h, w, c;
+  int64_t stride_n, stride_h, stride_w; /* elements; channel stride is 1 */
+  int32_t dtype;              /* b200_dtype */
+  int32_t reserved;
+} b200_tensor;
+
+/* A convolution kernel in both layouts the device code consumes.
+ *   hwio : Keras layout [kh][kw][cin][cout]            (SIMT kernels; tcgen05 dgrad B operand)
+ *   ohwi : packed copy  [kh][kw][cout][cin]            (tcgen05 fprop B operand; b200_filter_pack)
+ * `ohwi` may be NULL, in which case only the SIMT kernels are available. */
+typedef struct b200_filter {
+  const void* hwio;
+  const void* ohwi;
+  int32_t kh, kw, cin, cout;
+  int32_t dtype;              /* b200_dtype of both copies */
+  int32_t reserved;
+} b200_filter;
+
+/* ---- library ---------------------------------------------------------- */
+const char* b200_version(void);
+const char* b200_last_error(void);
+/* host out-params: SM count, compute capability. */
+int b200_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ---- convolution (keras Conv2D, stride 1, padding "same") ---------------
+ * Replaces L.Conv2D at train_adaptive_unet.py:202,207,259,267; seg :326,329,361;
+ * unet_vinillia.py:44,49,90.  y = act(conv(x, f) + bias); bias is fp32 [cout] or NULL. */
+int b200_conv2d_fprop(const b200_tensor* x, const b200_filter* f, const float* bias,
+                      const b200_tensor* y, int act, int algo, void* stream);
+/* dx (+)= conv_transpose(dy, f)  -- autodiff of the above w.r.t. its input. */
+int b200_conv2d_dgrad(const b200_tensor* dy, const b200_filter* f, const b200_tensor* dx,
+                      int accumulate, int algo, void* stream);
+/* dw_hwio[kh][kw][cin][cout] (fp32) = sum_pixels x (*) dy.  Overwrites dw.
+ * `workspace` must hold b200_conv2d_wgrad_workspace() bytes (may be 0). */
+size_t b200_conv2d_wgrad_workspace(const b200_tensor* x, const b200_tensor* dy, int kh, int kw, int algo);
+int b200_conv2d_wgrad(const b200_tensor* x, const b200_tensor* dy, int kh, int kw, float* dw_hwio,
+                      void* workspace, size_t workspace_bytes, int algo, void* stream);
+/* hwio -> ohwi repack (same dtype). */
+int b200_filter_pack(const void* hwio, void* ohwi, int kh, int kw, int cin, int cout, int dtype, void* stream);
+
+/* ---- transposed convolution (keras Conv2DTranspose(nf, 2, strides=2)) ----
+ * unet_vinillia.py:67.  kernel layout [2][2][cout][cin] in `dtype`, fp32 bias. */
+int b200_convT2x2_fprop(const b200_tensor* x, const void* kernel, const float* bias, int cout,
+                        const b200_tensor* y, void* stream);
+int b200_convT2x2_dgrad(const b200_tensor* dy, const void* kernel, int cout, const b200_tensor* dx, void* stream);
+int b200_convT2x2_wgrad(const b200_tensor* x, const b200_tensor* dy, float* dkernel, float* dbias, void* stream);
+
+/* ---- bias/activation backward -------------------------------------------
+ * dz = dy * act'(y); dbias[c] += sum dz (fp32 atomics; caller zeroes; may be NULL). */
+int b200_bias_act_bwd(const b200_tensor* dy, const b200_tensor* y, int act, const b200_tensor* dz,
+                      float* dbias, void* stream);
+
+/* ---- keras LayerNormalization(axis=-1) [+ Activation("relu")] ------------
+ * train_adaptive_unet.py:203-204,208-209.  mean/rstd: fp32 [n*h*w] saved for backward. */
+int b200_layernorm_fwd(const b200_tensor* z, const float* gamma, const float* beta, float eps, int relu,
+                       const b200_tensor* y, float* mean, float* rstd, void* stream);
+/* dz from dy; dgamma/dbeta/dbias (fp32 [c]) are accumulated with atomics (caller
+ * zeroes).  dbias is the gradient of the bias of the conv that produced z. */
+int b200_layernorm_bwd(const b200_tensor* dy, const b200_tensor* z, const float* mean, const float* rstd,
+                       const float* gamma, const float* beta, int relu, const b200_tensor* dz,
+                       float* dgamma, float* dbeta, float* dbias, void* stream);
+
+/* ---- keras BatchNormalization() [+ relu], training and inference ---------
+ * Segmenation/code/train_adaptive_unet.py:327-328,330-331.
+ * stats_ws: fp64 [2*c] scratch, zeroed by the call.  save_mean/save_rstd fp32 [c]. */
+int b200_batchnorm_fwd_train(const b200_tensor* z, const float* gamma, const float* beta, float eps,
+                             float momentum, int relu, const b200_tensor* y, float* save_mean,
+                             float* save_rstd, float* moving_mean, float* moving_var, double* stats_ws,
+                             void* stream);
+int b200_batchnorm_fwd_infer(const b200_tensor* z, const float* gamma, const float* beta, float eps, int relu,
+                             const float* moving_mean, const float* moving_var, const b200_tensor* y,
+                             void* stream);
+int b200_batchnorm_bwd(const b200_tensor* dy, const b200_tensor* z, const float* save_mean,
+                       const float* save_rstd, const float* gamma, const float* beta, int relu,
+                       const b200_tensor* dz, float* dgamma, float* dbeta, float* dbias, double* stats_ws,
+                       void* stream);
+
+/* ---- separable linear resampling ----------------------------------------
+ * tf.image.resize(bilinear, antialias) of ResizeByScale / ResizeToMatch
+ * (shared/custom_layers.py:102,124) and UpSampling2D bilinear (seg :357), forward
+ * and exact-transpose backward, as one gather kernel over span tables.
+ * Host helpers fill the tables; the caller uploads them.
+ *   starts [out]        : first source index of each output's span
+ *   weights[out * taps] : span weights, zero padded */
+int b200_resize_extent(int extent, float scale);                    /* max(1, ceil(f32(extent)*scale)) */
+int b200_resample_taps(int in_size, int out_size, int antialias);    /* span width (host) */
+int b200_resample_plan(int in_size, int out_size, int antialias, int32_t* starts /*host*/,
+                       float* weights /*host*/, int taps);
+/* transpose of a plan: tables indexed by SOURCE index; returns taps needed when
+ * t_starts == NULL. */
+int b200_resample_plan_transpose(int in_size, int out_size, int taps, const int32_t* starts /*host*/,
+                                 const float* weights /*host*/, int32_t* t_starts /*host*/,
+                                 float* t_weights /*host*/, int t_taps);
+/* y[n,oh,ow,:] (+)= sum_i sum_j wh[oh][i] * ww[ow][j] * x[n, sh[oh]+i, sw[ow]+j, :] */
+int b200_resample2d(const b200_tensor* x, const b200_tensor* y, const int32_t* h_starts,
+                    const float* h_weights, int h_taps, const int32_t* w_starts, const float* w_weights,
+                    int w_taps, int accumulate, void* stream);
+
+/* ---- keras MaxPooling2D(2) -- seg :351, unet_vinillia.py:62 --------------- */
+int b200_maxpool2_fwd(const b200_tensor* x, const b200_tensor* y, void* stream);
+int b200_maxpool2_bwd(const b200_tensor* x, const b200_tensor* y, const b200_tensor* dy,
+                      const b200_tensor* dx, int accumulate, void* stream);
+
+/* ---- ClippedResidualAdd -- shared/custom_layers.py:136-139 ----------------- */
+int b200_clipadd_fwd(const b200_tensor* inp, const b200_tensor* res, const b200_tensor* y, void* stream);
+int b200_clipadd_bwd(const b200_tensor* inp, const b200_tensor* res, const b200_tensor* dy,
+                     const b200_tensor* dres, void* stream);
+
+/* ---- SR losses + PSNR metric -- train_adaptive_unet.py:308-348 -------------
+ * out[0] = loss, out[1] = psnr metric (fp32, device).  dpred may have data==NULL
+ * (evaluation).  grad_scale multiplies dpred (1/world_size under data parallel).
+ * ws: fp32 [2 + n] scratch, zeroed by the call. */
+int b200_sr_loss(const b200_tensor* pred, const b200_tensor* target, int kind, float eps, float grad_scale,
+                 float* out, const b200_tensor* dpred, float* ws, void* stream);
+
+/* ---- BCE + Dice (+IoU) on probabilities -- seg :258-304 ---------------------
+ * out[0]=loss, out[1]=bce, out[2]=dice, out[3]=iou.  ws: fp32 [1 + 3*n], zeroed by the call. */
+int b200_bce_dice_loss(const b200_tensor* pred, const b200_tensor* target, float bce_weight,
+                       float dice_weight, float grad_scale, float* out, const b200_tensor* dpred, float* ws,
+                       void* stream);
+
+/* ---- softmax head + categorical cross-entropy (config C4; extrapolated) ----
+ * unet_vinillia.py:89-90 softmax head; keras CategoricalCrossentropy semantics. */
+int b200_softmax_fwd(const b200_tensor* z, const b200_tensor* p, void* stream);
+int b200_softmax_ce_loss(const b200_tensor* prob, const int32_t* labels, float grad_scale, float* out,
+                         const b200_tensor* dlogits, float* ws, void* stream);
+
+/* ---- Adam -- train_adaptive_unet.py:490 -----------------------------------
+ * hyper (device fp32[4]) = {lr, beta1, beta2, eps}; step (device int32[1]) is the
+ * 1-based step count, incremented by b200_adam_advance.  Updates p/m/v in place and
+ * writes the compute-dtype shadow copy of p (bf16 or NULL). */
+int b200_adam_advance(int32_t* step, void* stream);
+int b200_adam_step(float* p, const float* g, float* m, float* v, size_t count, const float* hyper,
+                   const int32_t* step, void* shadow_bf16, void* stream);
+
+/* ---- utilities -------------------------------------------------------------- */
+int b200_cast(const void* src, int src_dtype, void* dst, int dst_dtype, size_t count, void* stream);
+int b200_copy_tensor(const b200_tensor* src, const b200_tensor* dst, void* stream); /* strided, converting */
+int b200_scale_inplace(float* p, size_t count, float s, void* stream);
+
+/* ---- debug --------------------------------------------------------------------
+ * Single-CTA tcgen05 descriptor probe used by tests/test_umma_probe.py to pin the UMMA
+ * shared-memory addressing model the convolution kernels rely on (shifted start addresses
+ * and non-1024 stride-byte-offsets under the 128-byte swizzle).
+ * a: [a_rows][64] bf16, b: [64][64] bf16, out: [128][64] fp32. */
+int b200_debug_umma_probe(const void* a, int a_rows, const void* b, int start_bytes, int sbo_bytes,
+                          int lbo_bytes, int mn_major, float* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200_UNET_H_ */

@@ -1,0 +1,399 @@
+"""GPU parity of every kernel against the CPU oracle (bit-for-tolerance).
+
+Tolerances (rel-L2 per tensor): fp32 kernels 2e-5 against the fp32 oracle;
+bf16 kernels 1e-2 against the fp32 oracle fed the same bf16-rounded inputs.
+"""
+import numpy as np
+import pytest
+import torch
+
+from util import TOL, f32, rand, relerr
+
+pytestmark = pytest.mark.gpu
+
+DTYPES = [torch.float32, torch.bfloat16]
+
+
+def _ops():
+    import b200unet.ops as ops
+    return ops
+
+
+def _K():
+    from oracle import keras_ops
+    return keras_ops
+
+
+# ----------------------------------------------------------------------------- conv (SIMT)
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("shape", [(2, 13, 9, 3, 64, 3), (1, 16, 16, 64, 32, 3), (2, 8, 8, 20, 3, 1), (1, 5, 7, 64, 21, 1)])
+def test_conv_simt(dtype, shape):
+    ops, K = _ops(), _K()
+    n, h, w, ci, co, ks = shape
+    x = rand((n, h, w, ci), 1, dtype)
+    wt = rand((ks, ks, ci, co), 2, dtype, 0.2)
+    b = rand((co,), 3, torch.float32, 0.5)
+    dy = rand((n, h, w, co), 4, dtype)
+    filt = ops.ConvFilter(wt, packed=False)
+    y = torch.empty((n, h, w, co), dtype=dtype, device="cuda")
+    ops.conv2d_fprop(x, filt, b, y, ops.ACT_RELU, ops.ALGO_SIMT)
+    dx = torch.empty_like(x)
+    ops.conv2d_dgrad(dy, filt, dx, False, ops.ALGO_SIMT)
+    dw = torch.empty((ks, ks, ci, co), dtype=torch.float32, device="cuda")
+    ops.conv2d_wgrad(x, dy, ks, ks, dw, None, ops.ALGO_SIMT)
+    xr, wr = f32(x).requires_grad_(), f32(wt).requires_grad_()
+    yr = K.conv2d_same(xr, wr, f32(b))
+    (yr * f32(dy)).sum().backward()
+    assert relerr(y, torch.relu(yr)) < TOL[dtype]
+    assert relerr(dx, xr.grad) < TOL[dtype]
+    assert relerr(dw, wr.grad) < TOL[dtype]
+
+
+# ----------------------------------------------------------------------------- UMMA descriptor probe
+def _probe_expected(a, b, start_rows, sbo_rows):
+    rows = [start_rows + (r // 8) * sbo_rows + (r % 8) for r in range(128)]
+    return a[rows].float() @ b.float().t()
+
+
+@pytest.mark.parametrize("start_bytes,sbo_bytes", [(0, 1024), (1024, 1024), (128, 1024), (1408, 1024), (0, 1280), (1408, 1280), (2816, 1280)])
+def test_umma_probe_kmajor(start_bytes, sbo_bytes):
+    """K-major SW128 operand read through a shifted start address / non-1024 SBO.
+    Expected under the absolute-address swizzle model: row r of the operand is the
+    128-byte smem row  start/128 + (r/8)*(SBO/128) + r%8."""
+    ops = _ops()
+    a = rand((320, 64), 5, torch.bfloat16)
+    b = rand((64, 64), 6, torch.bfloat16)
+    out = torch.zeros((128, 64), dtype=torch.float32, device="cuda")
+    ops.umma_probe(a, b, start_bytes, sbo_bytes, 0, False, out)
+    torch.cuda.synchronize()
+    exp = _probe_expected(a.cpu(), b.cpu(), start_bytes // 128, sbo_bytes // 128)
+    err = relerr(out, exp)
+    print(f"probe kmajor start={start_bytes} sbo={sbo_bytes} relerr={err:.3e}")
+    assert err < 1e-5
+
+
+@pytest.mark.parametrize("start_bytes,sbo_bytes,lbo_bytes", [(0, 1024, 1024), (0, 1024, 128), (1408, 1280, 128), (1408, 1280, 1024)])
+def test_umma_probe_mnmajor(start_bytes, sbo_bytes, lbo_bytes):
+    """wgrad-style MN-major operands: D[m][n] = sum_k A[m][k] B[n][k], m = atom*64 + c,
+    A[m][k] = smem row (start + atom*LBO)/128 + (k/8)*(SBO/128) + k%8, channel c; B[n][k] = b[k][n]."""
+    ops = _ops()
+    a = rand((320, 64), 7, torch.bfloat16)
+    b = rand((64, 64), 8, torch.bfloat16)
+    out = torch.zeros((128, 64), dtype=torch.float32, device="cuda")
+    ops.umma_probe(a, b, start_bytes, sbo_bytes, lbo_bytes, True, out)
+    torch.cuda.synchronize()
+    ac, bc = a.cpu().float(), b.cpu().float()
+    exp = torch.zeros(128, 64)
+    for atom in range(2):
+        rows = [start_bytes // 128 + atom * (lbo_bytes // 128) + (k // 8) * (sbo_bytes // 128) + k % 8 for k in range(64)]
+        exp[atom * 64:(atom + 1) * 64] = ac[rows].t() @ bc  # [c][k] @ [k][n]
+    err = relerr(out, exp)
+    print(f"probe mnmajor start={start_bytes} sbo={sbo_bytes} lbo={lbo_bytes} relerr={err:.3e}")
+    assert err < 1e-5
+
+
+# ----------------------------------------------------------------------------- conv (tcgen05)
+TC_SHAPES = [
+    (2, 32, 32, 64, 64), (1, 20, 13, 64, 64), (2, 16, 16, 128, 64), (2, 8, 8, 64, 128),
+    (3, 40, 24, 128, 128), (4, 2, 2, 128, 256), (3, 1, 1, 256, 128), (1, 45, 45, 64, 64),
+]
+
+
+@pytest.mark.parametrize("shape", TC_SHAPES)
+def test_conv_tc_fprop_dgrad(shape):
+    ops, K = _ops(), _K()
+    n, h, w, ci, co = shape
+    dt = torch.bfloat16
+    x = rand((n, h, w, ci), 11, dt)
+    wt = rand((3, 3, ci, co), 12, dt, 0.1)
+    b = rand((co,), 13, torch.float32, 0.5)
+    dy = rand((n, h, w, co), 14, dt)
+    filt = ops.ConvFilter(wt)
+    y = torch.full((n, h, w, co), 7.0, dtype=dt, device="cuda")
+    ops.conv2d_fprop(x, filt, b, y, ops.ACT_RELU, ops.ALGO_TCGEN05)
+    dx = torch.full((n, h, w, ci), 7.0, dtype=dt, device="cuda")
+    ops.conv2d_dgrad(dy, filt, dx, False, ops.ALGO_TCGEN05)
+    torch.cuda.synchronize()
+    xr, wr = f32(x).requires_grad_(), f32(wt).requires_grad_()
+    yr = K.conv2d_same(xr, wr, f32(b))
+    (yr * f32(dy)).sum().backward()
+    e1, e2 = relerr(y, torch.relu(yr)), relerr(dx, xr.grad)
+    print(f"tc conv {shape}: fprop {e1:.3e} dgrad {e2:.3e}")
+    assert e1 < 1e-2 and e2 < 1e-2
+
+
+def test_conv_tc_strided_concat_and_accumulate():
+    """Output written into a channel slice of a wider (concat) buffer; dgrad accumulating."""
+    ops, K = _ops(), _K()
+    dt = torch.bfloat16
+    n, h, w = 2, 24, 16
+    x = rand((n, h, w, 128), 21, dt)
+    wt = rand((3, 3, 128, 64), 22, dt, 0.1)
+    filt = ops.ConvFilter(wt)
+    cat = torch.zeros((n, h, w, 128), dtype=dt, device="cuda")
+    ops.conv2d_fprop(x, filt, None, cat[..., 64:], ops.ACT_NONE, ops.ALGO_TCGEN05)
+    yr = K.conv2d_same(f32(x), f32(wt))
+    assert relerr(cat[..., 64:], yr) < 1e-2
+    assert cat[..., :64].abs().max().item() == 0.0
+    # a conv reading the slice as its input
+    w2 = rand((3, 3, 64, 64), 23, dt, 0.1)
+    f2 = ops.ConvFilter(w2)
+    y2 = torch.empty((n, h, w, 64), dtype=dt, device="cuda")
+    ops.conv2d_fprop(cat[..., 64:], f2, None, y2, ops.ACT_NONE, ops.ALGO_TCGEN05)
+    assert relerr(y2, K.conv2d_same(f32(cat[..., 64:]), f32(w2))) < 1e-2
+    # accumulate
+    dy = rand((n, h, w, 64), 24, dt)
+    base = rand((n, h, w, 128), 25, dt)
+    dx = base.clone()
+    ops.conv2d_dgrad(dy, filt, dx, True, ops.ALGO_TCGEN05)
+    xr = f32(x).requires_grad_()
+    (K.conv2d_same(xr, f32(wt)) * f32(dy)).sum().backward()
+    assert relerr(dx, xr.grad + f32(base)) < 1e-2
+
+
+@pytest.mark.parametrize("shape", TC_SHAPES)
+def test_conv_tc_wgrad(shape):
+    ops, K = _ops(), _K()
+    n, h, w, ci, co = shape
+    dt = torch.bfloat16
+    x = rand((n, h, w, ci), 31, dt)
+    dy = rand((n, h, w, co), 32, dt)
+    dw = torch.full((3, 3, ci, co), 7.0, dtype=torch.float32, device="cuda")
+    nbytes = ops.conv2d_wgrad_workspace(x, dy, 3, 3, ops.ALGO_TCGEN05)
+    ws = torch.empty(max(nbytes, 16) // 4, dtype=torch.float32, device="cuda")
+    ops.conv2d_wgrad(x, dy, 3, 3, dw, ws, ops.ALGO_TCGEN05)
+    torch.cuda.synchronize()
+    wr = torch.zeros(3, 3, ci, co, requires_grad=True)
+    (K.conv2d_same(f32(x), wr) * f32(dy)).sum().backward()
+    e = relerr(dw, wr.grad)
+    print(f"tc wgrad {shape}: {e:.3e}")
+    assert e < 2e-3
+
+
+# ----------------------------------------------------------------------------- layer norm
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("shape", [(2, 7, 5, 64), (1, 3, 3, 8), (2, 4, 4, 256), (1, 2, 3, 1024), (1, 1, 5, 2048)])
+@pytest.mark.parametrize("relu", [True, False])
+def test_layernorm(dtype, shape, relu):
+    ops, K = _ops(), _K()
+    n, h, w, c = shape
+    z = rand(shape, 41, dtype, 2.0)
+    g = (1 + 0.3 * rand((c,), 42)).contiguous()
+    b = rand((c,), 43, scale=0.3)
+    dy = rand(shape, 44, dtype)
+    y = torch.empty_like(z)
+    mean = torch.empty(n * h * w, device="cuda"); rstd = torch.empty_like(mean)
+    ops.layernorm_fwd(z, g, b, 1e-3, relu, y, mean, rstd)
+    dz = torch.empty_like(z)
+    dg = torch.zeros(c, device="cuda"); db = torch.zeros(c, device="cuda"); dbias = torch.zeros(c, device="cuda")
+    ops.layernorm_bwd(dy, z, mean, rstd, g, b, relu, dz, dg, db, dbias)
+    zr, gr, br = f32(z).requires_grad_(), f32(g).requires_grad_(), f32(b).requires_grad_()
+    yr = K.layer_norm(zr, gr, br)
+    yr = torch.relu(yr) if relu else yr
+    (yr * f32(dy)).sum().backward()
+    tol = TOL[dtype]
+    assert relerr(y, yr) < tol
+    assert relerr(dz, zr.grad) < tol * 2
+    assert relerr(dg, gr.grad) < 1e-4 and relerr(db, br.grad) < 1e-4
+    assert relerr(dbias, zr.grad.sum(dim=(0, 1, 2))) < 5e-2 or zr.grad.sum(dim=(0, 1, 2)).abs().max() < 1e-3
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("c,act", [(64, 1), (3, 0), (1, 2), (24, 1)])
+def test_bias_act_bwd(dtype, c, act):
+    ops = _ops()
+    shape = (2, 5, 6, c)
+    y = rand(shape, 51, dtype).abs() * (rand(shape, 52, dtype) > 0)
+    if act == 2:
+        y = torch.sigmoid(rand(shape, 51, torch.float32)).to(dtype)
+    dy = rand(shape, 53, dtype)
+    dz = torch.empty_like(dy)
+    db = torch.zeros(c, device="cuda")
+    ops.bias_act_bwd(dy, y, act, dz, db)
+    yf, df = f32(y), f32(dy)
+    exp = df if act == 0 else (df * (yf > 0) if act == 1 else df * yf * (1 - yf))
+    assert relerr(dz, exp) < TOL[dtype]
+    assert relerr(db, exp.sum(dim=(0, 1, 2))) < 1e-2
+
+
+# ----------------------------------------------------------------------------- batch norm
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("c", [64, 24, 512])
+def test_batchnorm(dtype, c):
+    ops, K = _ops(), _K()
+    shape = (3, 6, 5, c)
+    z = rand(shape, 61, dtype, 2.0) + 0.5
+    g = (1 + 0.3 * rand((c,), 62)).contiguous(); b = rand((c,), 63, scale=0.3)
+    mm = rand((c,), 64, scale=0.1); mv = (1 + 0.2 * rand((c,), 65)).contiguous()
+    dy = rand(shape, 66, dtype)
+    y = torch.empty_like(z)
+    sm = torch.empty(c, device="cuda"); sr = torch.empty(c, device="cuda")
+    ws = torch.empty(2 * c, dtype=torch.float64, device="cuda")
+    mm2, mv2 = mm.clone(), mv.clone()
+    ops.batchnorm_fwd_train(z, g, b, 1e-3, 0.99, True, y, sm, sr, mm2, mv2, ws)
+    dz = torch.empty_like(z); dg = torch.zeros(c, device="cuda"); db = torch.zeros(c, device="cuda")
+    ops.batchnorm_bwd(dy, z, sm, sr, g, b, True, dz, dg, db, ws)
+    yi = torch.empty_like(z)
+    ops.batchnorm_fwd_infer(z, g, b, 1e-3, True, mm, mv, yi)
+    zr, gr, br = f32(z).requires_grad_(), f32(g).requires_grad_(), f32(b).requires_grad_()
+    yr, nm, nv = K.batch_norm_train(zr, gr, br, f32(mm), f32(mv))
+    yr = torch.relu(yr)
+    (yr * f32(dy)).sum().backward()
+    tol = TOL[dtype]
+    assert relerr(y, yr) < tol
+    assert relerr(mm2, nm) < 1e-5 and relerr(mv2, nv) < 1e-5
+    assert relerr(dz, zr.grad) < tol * 3
+    assert relerr(dg, gr.grad) < 1e-3 and relerr(db, br.grad) < 1e-3
+    assert relerr(yi, torch.relu(K.batch_norm_infer(f32(z), f32(g), f32(b), f32(mm), f32(mv)))) < tol
+
+
+# ----------------------------------------------------------------------------- resampling / pooling
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("sizes", [((16, 16), (8, 8)), ((13, 9), (4, 3)), ((8, 8), (32, 32)), ((45, 45), (63, 63)), ((2, 2), (1, 1)), ((1, 1), (2, 2)), ((20, 20), (14, 14))])
+@pytest.mark.parametrize("c", [64, 3])
+def test_resample(dtype, sizes, c):
+    ops, K = _ops(), _K()
+    (h, w), (oh, ow) = sizes
+    x = rand((2, h, w, c), 71, dtype)
+    dy = rand((2, oh, ow, c), 72, dtype)
+    ph = ops.ResamplePlan(h, oh, True, "cuda"); pw = ops.ResamplePlan(w, ow, True, "cuda")
+    y = torch.empty((2, oh, ow, c), dtype=dtype, device="cuda")
+    ops.resample2d(x, y, ph, pw)
+    base = rand((2, h, w, c), 73, dtype)
+    dx = base.clone()
+    ops.resample2d_bwd(dy, dx, ph, pw, accumulate=True)
+    xr = f32(x).requires_grad_()
+    yr = K.resize_bilinear(xr, oh, ow)
+    (yr * f32(dy)).sum().backward()
+    assert relerr(y, yr) < TOL[dtype]
+    assert relerr(dx, xr.grad + f32(base)) < TOL[dtype]
+
+
+def test_resample_tables_match_oracle():
+    ops = _ops()
+    from oracle import resize_np
+    for (a, b) in [(256, 180), (180, 126), (126, 89), (89, 63), (63, 45), (128, 32), (32, 8), (8, 2), (2, 1), (1, 2), (32, 128), (50, 16)]:
+        for aa in (True, False):
+            plan = ops.ResamplePlan(a, b, aa, "cuda")
+            st, wt = resize_np.triangle_spans(a, b, aa)
+            assert np.array_equal(plan.host[0], st)
+            assert np.array_equal(plan.host[1], wt), (a, b, aa)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("hw", [(8, 8), (7, 5)])
+def test_maxpool(dtype, hw):
+    ops, K = _ops(), _K()
+    h, w = hw
+    x = rand((2, h, w, 16), 81, dtype)
+    y = torch.empty((2, h // 2, w // 2, 16), dtype=dtype, device="cuda")
+    ops.maxpool2_fwd(x, y)
+    dy = rand(tuple(y.shape), 82, dtype)
+    dx = torch.empty_like(x)
+    ops.maxpool2_bwd(x, y, dy, dx)
+    xr = f32(x).requires_grad_()
+    yr = K.max_pool2(xr)
+    (yr * f32(dy)).sum().backward()
+    assert relerr(y, yr) < 1e-7
+    assert relerr(dx, xr.grad) < 1e-7
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_conv_transpose(dtype):
+    ops, K = _ops(), _K()
+    x = rand((2, 5, 4, 16), 91, dtype); k = rand((2, 2, 8, 16), 92, dtype, 0.3); b = rand((8,), 93, scale=0.2)
+    y = torch.empty((2, 10, 8, 8), dtype=dtype, device="cuda")
+    ops.convT2x2_fprop(x, k, b, y)
+    dy = rand((2, 10, 8, 8), 94, dtype)
+    dx = torch.empty_like(x); dk = torch.empty((2, 2, 8, 16), device="cuda"); dbias = torch.zeros(8, device="cuda")
+    ops.convT2x2_dgrad(dy, k, dx); ops.convT2x2_wgrad(x, dy, dk, dbias)
+    xr, kr, br = f32(x).requires_grad_(), f32(k).requires_grad_(), f32(b).requires_grad_()
+    yr = K.conv2d_transpose_2x2(xr, kr, br)
+    (yr * f32(dy)).sum().backward()
+    tol = TOL[dtype]
+    assert relerr(y, yr) < tol and relerr(dx, xr.grad) < tol and relerr(dk, kr.grad) < tol and relerr(dbias, br.grad) < tol
+
+
+# ----------------------------------------------------------------------------- head / losses / optimiser
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_clipadd(dtype):
+    ops, K = _ops(), _K()
+    inp = rand((2, 6, 6, 3), 101, torch.float32).abs()
+    res = rand((2, 6, 6, 3), 102, dtype, 0.8)
+    y = torch.empty((2, 6, 6, 3), dtype=dtype, device="cuda")
+    ops.clipadd_fwd(inp, res, y)
+    dy = rand((2, 6, 6, 3), 103, dtype)
+    dres = torch.empty_like(res)
+    ops.clipadd_bwd(inp, res, dy, dres)
+    rr = f32(res).requires_grad_()
+    yr = K.clipped_residual_add(f32(inp), rr)
+    (yr * f32(dy)).sum().backward()
+    assert relerr(y, yr) < TOL[dtype] and relerr(dres, rr.grad) < TOL[dtype]
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("kind", [0, 1, 2])
+def test_sr_loss(dtype, kind):
+    ops, K = _ops(), _K()
+    pred = rand((3, 9, 7, 3), 111, torch.float32).abs().to(dtype)
+    tgt = rand((3, 9, 7, 3), 112, torch.float32).abs()
+    out = torch.zeros(2, device="cuda"); ws = torch.zeros(2 + 3, device="cuda")
+    dp = torch.empty_like(pred)
+    ops.sr_loss(pred, tgt, kind, 1e-3, 0.5, out, dp, ws)
+    pr = f32(pred).requires_grad_()
+    fn = [K.charbonnier_loss, K.l1_loss, K.mse_loss][kind]
+    l = fn(f32(tgt), pr) if kind else K.charbonnier_loss(f32(tgt), pr, 1e-3)
+    l.backward()
+    assert abs(out[0].item() - l.item()) < 1e-5 * max(1, abs(l.item()))
+    assert abs(out[1].item() - K.psnr_metric(f32(tgt), f32(pred)).item()) < 1e-3
+    assert relerr(dp, 0.5 * pr.grad) < TOL[dtype]
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_bce_dice(dtype):
+    ops, K = _ops(), _K()
+    pred = torch.sigmoid(3 * rand((3, 8, 8, 1), 121)).to(dtype)
+    tgt = (rand((3, 8, 8, 1), 122) > 0).float()
+    out = torch.zeros(4, device="cuda"); ws = torch.zeros(1 + 9, device="cuda"); dp = torch.empty_like(pred)
+    ops.bce_dice_loss(pred, tgt, 0.4, 0.6, 1.0, out, dp, ws)
+    pr = f32(pred).requires_grad_()
+    l = K.bce_dice_loss(f32(tgt), pr, 0.4, 0.6)
+    l.backward()
+    assert abs(out[0].item() - l.item()) < 1e-5
+    assert abs(out[2].item() - K.dice_coefficient(f32(tgt), f32(pred)).item()) < 1e-5
+    assert abs(out[3].item() - K.iou_score(f32(tgt), f32(pred)).item()) < 1e-5
+    assert relerr(dp, pr.grad) < TOL[dtype]
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_softmax_ce(dtype):
+    ops, K = _ops(), _K()
+    z = rand((2, 5, 4, 21), 131, dtype, 3.0)
+    labels = torch.randint(0, 21, (2, 5, 4), generator=torch.Generator().manual_seed(5), dtype=torch.int32).cuda()
+    p = torch.empty_like(z)
+    ops.softmax_fwd(z, p)
+    out = torch.zeros(1, device="cuda"); ws = torch.zeros(1, device="cuda"); dz = torch.empty_like(z)
+    ops.softmax_ce_loss(p, labels, 1.0, out, dz, ws)
+    zr = f32(z).requires_grad_()
+    pr = torch.softmax(zr, dim=-1)
+    onehot = torch.nn.functional.one_hot(labels.cpu().long(), 21).float()
+    l = K.categorical_crossentropy(onehot, pr)
+    l.backward()
+    assert relerr(p, pr) < TOL[dtype]
+    assert abs(out[0].item() - l.item()) < (1e-5 if dtype == torch.float32 else 2e-2)
+    assert relerr(dz, zr.grad) < (1e-4 if dtype == torch.float32 else 3e-2)
+
+
+def test_adam():
+    ops, K = _ops(), _K()
+    n = 1003
+    p = rand((n,), 141); g = rand((n,), 142, scale=0.1); m = torch.zeros(n, device="cuda"); v = torch.zeros(n, device="cuda")
+    hyper = torch.tensor([1e-3, 0.9, 0.999, 1e-7], device="cuda"); step = torch.zeros(1, dtype=torch.int32, device="cuda")
+    shadow = torch.empty(n, dtype=torch.bfloat16, device="cuda")
+    pr, mr, vr = f32(p), torch.zeros(n), torch.zeros(n)
+    for t in range(1, 4):
+        ops.adam_advance(step)
+        ops.adam_step(p, g, m, v, hyper, step, shadow)
+        pr, mr, vr = K.adam_step(pr, f32(g), mr, vr, t, 1e-3)
+    assert relerr(p, pr) < 1e-6 and relerr(m, mr) < 1e-6 and relerr(v, vr) < 1e-6
+    assert relerr(shadow, pr) < 4e-3
