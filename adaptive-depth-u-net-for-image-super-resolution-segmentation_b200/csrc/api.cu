@@ -21,7 +21,10 @@ int fail(int code, const char* fmt, ...) {
   va_end(ap);
   return code;
 }
+static long long g_launches = 0;
+void count_launches(int n) { g_launches += n; }
 int check_launch(const char* what) {
+  g_launches += 1;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(B200_ERR_LAUNCH, "%s: %s", what, cudaGetErrorString(e));
   return B200_OK;
@@ -82,6 +85,11 @@ extern "C" {
 
 const char* b200_version(void) { return "b200unet 0.1.0 (sm_100a)"; }
 const char* b200_last_error(void) { return g_err; }
+long long b200_launch_count(int reset) {
+  long long v = g_launches;
+  if (reset) g_launches = 0;
+  return v;
+}
 
 int b200_device_info(int* sms, int* major, int* minor) {
   int dev = 0;

@@ -14,7 +14,8 @@ namespace b200 {
 // ---- error plumbing ---------------------------------------------------------
 void set_error(const char* fmt, ...);
 int fail(int code, const char* fmt, ...);
-int check_launch(const char* what);
+int check_launch(const char* what);   // also counts one kernel launch
+void count_launches(int n);            // extra launches of multi-kernel entry points
 
 #define B200_REQUIRE(cond, code, ...)                 \
   do {                                                \

@@ -301,6 +301,7 @@ int sr_loss(const b200_tensor* pred, const b200_tensor* target, int kind, float 
     sr_loss_kernel<TP, TT><<<grid, NT, 0, st>>>(pv, tv, kind, eps, grad_scale / total, ws, gv, per_img);
   });
   sr_loss_finalize_kernel<<<1, 32, 0, st>>>(ws, pred->n, total, (float)per_img, out);
+  count_launches(1);
   return check_launch("sr_loss_kernel");
 }
 
@@ -322,6 +323,7 @@ int bce_dice_loss(const b200_tensor* pred, const b200_tensor* target, float bw, 
       bce_dice_grad_kernel<TP, TT><<<grid, NT, 0, st>>>(pv, tv, ws, bw, dw, grad_scale, total, gv, per_img);
     }
   });
+  count_launches((dpred && dpred->data) ? 2 : 1);
   return check_launch("bce_dice_loss");
 }
 
@@ -348,6 +350,7 @@ int softmax_ce_loss(const b200_tensor* prob, const int32_t* labels, float grad_s
     softmax_ce_kernel<T><<<grid_for(npix), NT, 0, st>>>(pv, labels, grad_scale, ws, gv, npix);
   });
   mean_finalize_kernel<<<1, 32, 0, st>>>(ws, (float)npix, out);
+  count_launches(1);
   return check_launch("softmax_ce_kernel");
 }
 

@@ -458,6 +458,7 @@ int batchnorm_fwd_train(const b200_tensor* z, const float* gamma, const float* b
     bn_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(stats_ws, C, (double)npix, eps, momentum, save_mean, save_rstd, moving_mean, moving_var);
     bn_apply_kernel<T><<<grid_for(npix * C, NT), NT, 0, st>>>(zv, save_mean, save_rstd, gamma, beta, relu, yv, npix * C, nullptr, nullptr, eps);
   });
+  count_launches(2);
   return check_launch("batchnorm_fwd_train");
 }
 
@@ -487,6 +488,7 @@ int batchnorm_bwd(const b200_tensor* dy, const b200_tensor* z, const float* save
     bn_bwd_apply_kernel<T><<<grid_for(npix * C, NT), NT, 0, st>>>(dyv, zv, save_mean, save_rstd, gamma, beta, relu, dzv, stats_ws, (double)npix, npix * C);
     bn_bwd_params_kernel<<<(C + 127) / 128, 128, 0, st>>>(stats_ws, C, dgamma, dbeta);
   });
+  count_launches(2);
   return check_launch("batchnorm_bwd");
 }
 

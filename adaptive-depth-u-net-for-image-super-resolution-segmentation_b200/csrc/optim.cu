@@ -28,6 +28,7 @@ adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restric
             size_t count, const float* __restrict__ hyper, const int* __restrict__ step,
             __nv_bfloat16* __restrict__ shadow) {
   const float lr = hyper[0], b1 = hyper[1], b2 = hyper[2], eps = hyper[3];
+  const float omb1 = hyper[4], omb2 = hyper[5];  // (1-beta) evaluated in double by the host, as keras does
   const float t = (float)(*step);
   const float alpha = lr * sqrtf(1.f - powf(b2, t)) / (1.f - powf(b1, t));
   const size_t n4 = count / 4;
@@ -39,8 +40,8 @@ adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restric
     float* pp = &pv.x; const float* gg = &gv.x; float* mm = &mv.x; float* vp = &vv.x;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      mm[k] += (gg[k] - mm[k]) * (1.f - b1);
-      vp[k] += (gg[k] * gg[k] - vp[k]) * (1.f - b2);
+      mm[k] += (gg[k] - mm[k]) * omb1;
+      vp[k] += (gg[k] * gg[k] - vp[k]) * omb2;
       pp[k] -= alpha * mm[k] / (sqrtf(vp[k]) + eps);
     }
     reinterpret_cast<float4*>(p)[i] = pv;
@@ -56,8 +57,8 @@ adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restric
   }
   // tail
   for (size_t i = n4 * 4 + (size_t)blockIdx.x * NT + threadIdx.x; i < count; i += (size_t)gridDim.x * NT) {
-    float mm = m[i] + (g[i] - m[i]) * (1.f - b1);
-    float vv = v[i] + (g[i] * g[i] - v[i]) * (1.f - b2);
+    float mm = m[i] + (g[i] - m[i]) * omb1;
+    float vv = v[i] + (g[i] * g[i] - v[i]) * omb2;
     float pp = p[i] - alpha * mm / (sqrtf(vv) + eps);
     m[i] = mm; v[i] = vv; p[i] = pp;
     if (shadow) shadow[i] = __float2bfloat16_rn(pp);

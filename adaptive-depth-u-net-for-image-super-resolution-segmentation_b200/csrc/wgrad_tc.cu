@@ -225,7 +225,7 @@ int wgrad_tc_launch(const b200_tensor* x, const b200_tensor* dy, float* dw, void
   const long long count = 9LL * p.Cin * p.Cout;
   long long blocks = (count / 4 + 255) / 256;
   if (blocks > 4LL * sm_count()) blocks = 4LL * sm_count();
-  wgrad_reduce_kernel<<<(int)blocks, 256, 0, st>>>(p.partial, dw, count, p.splits);
+  wgrad_reduce_kernel<<<(int)blocks, 256, 0, st>>>(p.partial, dw, count, p.splits);  // counted by check_launch
   return check_launch("wgrad_reduce_kernel");
 }
 

@@ -1,0 +1,381 @@
+"""Lowering of a recorded Keras-shaped graph to a static plan of sm_100a kernel launches.
+
+A ``Plan`` is built once per (batch size, training flag): every activation,
+gradient and scratch buffer is allocated up front (device memory is plentiful --
+180 GB -- so nothing is aliased except the deliberate cases below), every launch is
+a C-ABI call with fixed pointers, and the whole step is captured in a CUDA graph.
+
+Deliberate buffer sharing:
+  * Concatenate is never executed: its inputs' buffers (and their gradient buffers)
+    are channel slices of the concat output, so producers store straight into it and
+    the consumer's dgrad splits the gradient for free.
+  * Activation("relu") nodes are folded into the producing conv epilogue or
+    normalisation kernel.
+
+The forward/backward order is the graph's topological order / its reverse, which is
+what keras' ``train_step`` does with a GradientTape
+(/root/reference: Super_resolution/code/train_adaptive_unet.py:489-494, 622-632).
+"""
+from __future__ import annotations
+
+from typing import Callable, Dict, List, Optional
+
+import torch
+
+from .. import ops
+from .._ffi import ACT_NONE, ACT_RELU, ACT_SIGMOID
+from ..shared.custom_layers import ClippedResidualAdd, ResizeByScale, ResizeToMatch
+from . import layers as L
+
+
+class Val:
+    """A concrete activation tensor of the plan (one per KTensor, minus folded nodes)."""
+
+    def __init__(self, name, h, w, c, dtype):
+        self.name, self.h, self.w, self.c, self.dtype = name, h, w, c, dtype
+        self.buf: Optional[torch.Tensor] = None
+        self.grad: Optional[torch.Tensor] = None
+        self.parent: Optional["Val"] = None   # concat output this value is a slice of
+        self.offset = 0
+        self.needs_grad = True
+        self._grad_written = False
+        self.children: List["Val"] = []
+
+    @property
+    def grad_written(self):
+        return self._grad_written or (self.parent is not None and self.parent.grad_written)
+
+    def mark_grad_written(self):
+        self._grad_written = True
+
+
+class Op:
+    def __init__(self, kind, layer=None, inputs=(), output=None, **attrs):
+        self.kind, self.layer, self.inputs, self.output = kind, layer, list(inputs), output
+        self.__dict__.update(attrs)
+
+
+def lower(model) -> (List[Op], Dict[int, Val]):
+    """Graph nodes -> op list (pure structure; no device memory yet)."""
+    nodes = model._nodes
+    consumers: Dict[int, List[L.Node]] = {}
+    for nd in nodes:
+        for t in nd.inputs:
+            consumers.setdefault(id(t), []).append(nd)
+    cdt = model._compute_dtype
+    vals: Dict[int, Val] = {}
+    ops_: List[Op] = []
+    producer: Dict[int, Op] = {}   # id(KTensor) -> op that produced its Val
+
+    def new_val(kt, dtype=None):
+        _, h, w, c = kt.shape
+        v = Val(kt.name, h, w, c, dtype or cdt)
+        vals[id(kt)] = v
+        return v
+
+    for nd in nodes:
+        ly, out = nd.layer, nd.output
+        ins = [vals[id(t)] for t in nd.inputs]
+        if isinstance(ly, L.InputLayer):
+            v = new_val(out, torch.float32)
+            v.needs_grad = False
+            if cdt != torch.float32:
+                vc = Val(out.name + ":cast", v.h, v.w, v.c, cdt)
+                vc.needs_grad = False
+                ops_.append(Op("cast_input", None, [v], vc))
+                v.compute_view = vc
+            else:
+                v.compute_view = v
+            continue
+        # model inputs are consumed in the compute dtype, except by the clip-add (fp32 there, as keras)
+        cin = [getattr(v, "compute_view", v) for v in ins]
+        if isinstance(ly, L.Conv2D):
+            act = {None: ACT_NONE, "relu": ACT_RELU, "sigmoid": ACT_SIGMOID, "softmax": ACT_NONE}[ly.activation]
+            v = new_val(out)
+            if ly.activation == "softmax":
+                z = Val(out.name + ":logits", v.h, v.w, v.c, cdt)
+                op = Op("conv", ly, cin, z, act=ACT_NONE, norm_bias=False)
+                ops_.append(op)
+                ops_.append(Op("softmax", None, [z], v))
+                producer[id(out)] = ops_[-1]
+            else:
+                op = Op("conv", ly, cin, v, act=act, norm_bias=False)
+                ops_.append(op)
+                producer[id(out)] = op
+        elif isinstance(ly, (L.LayerNormalization, L.BatchNormalization)):
+            v = new_val(out)
+            kind = "ln" if isinstance(ly, L.LayerNormalization) else "bn"
+            src = producer.get(id(nd.inputs[0]))
+            conv_src = src if (src is not None and src.kind == "conv" and src.act == ACT_NONE
+                               and len(consumers[id(nd.inputs[0])]) == 1 and src.layer.use_bias) else None
+            if conv_src is not None:
+                conv_src.norm_bias = True   # its bias gradient comes out of the norm backward kernel
+            op = Op(kind, ly, cin, v, relu=False, conv_src=conv_src)
+            ops_.append(op)
+            producer[id(out)] = op
+        elif isinstance(ly, L.Activation):
+            src = producer.get(id(nd.inputs[0]))
+            single = len(consumers[id(nd.inputs[0])]) == 1
+            if src is not None and single and src.kind in ("ln", "bn") and not src.relu:
+                src.relu = True
+            elif src is not None and single and src.kind == "conv" and src.act == ACT_NONE and not src.norm_bias:
+                src.act = ACT_RELU
+            else:
+                raise NotImplementedError(
+                    f"Activation '{ly.name}': a stand-alone ReLU is not on the reference's hot path "
+                    "(it must directly follow a Conv2D / LayerNormalization / BatchNormalization)")
+            vals[id(out)] = ins[0]          # folded: same value
+            producer[id(out)] = src
+        elif isinstance(ly, (ResizeByScale, ResizeToMatch, L.UpSampling2D)):
+            v = new_val(out)
+            aa = getattr(ly, "antialias", False)
+            op = Op("resize", ly, [cin[0]], v, antialias=aa)
+            ops_.append(op)
+            producer[id(out)] = op
+        elif isinstance(ly, L.MaxPooling2D):
+            v = new_val(out)
+            ops_.append(Op("maxpool", ly, cin, v))
+            producer[id(out)] = ops_[-1]
+        elif isinstance(ly, L.Conv2DTranspose):
+            v = new_val(out)
+            ops_.append(Op("convT", ly, cin, v))
+            producer[id(out)] = ops_[-1]
+        elif isinstance(ly, L.Concatenate):
+            v = new_val(out)
+            off = 0
+            copies = []
+            for t, vin in zip(nd.inputs, cin):
+                others_after = any(c.seq > nd.seq for c in consumers[id(t)] if c is not nd)
+                can_alias = vin.parent is None and vin.needs_grad and not others_after and not vin.children
+                if can_alias:
+                    vin.parent, vin.offset = v, off
+                    v.children.append(vin)
+                else:
+                    copies.append((vin, off))
+                off += vin.c
+            ops_.append(Op("concat", ly, cin, v, copies=copies))
+            producer[id(out)] = ops_[-1]
+        elif isinstance(ly, ClippedResidualAdd):
+            v = new_val(out)
+            ops_.append(Op("clipadd", ly, [ins[0], cin[1]], v))   # the raw fp32 input, as keras casts to fp32
+            producer[id(out)] = ops_[-1]
+        else:
+            raise NotImplementedError(f"layer type {type(ly).__name__} is not supported by the b200 engine")
+    return ops_, vals
+
+
+class Plan:
+    def __init__(self, model, batch: int, training: bool):
+        self.model, self.batch, self.training = model, batch, training
+        self.dev = model._device
+        self.ops, self.vals = lower(model)
+        self.cdt = model._compute_dtype
+        self.input_vals = [self.vals[id(t)] for t in model.inputs]
+        self.output_val = self.vals[id(model.outputs[0])]
+        self.steps: List[Callable[[], None]] = []       # forward launches
+        self.bwd_steps: List[Callable[[], None]] = []   # backward launches (training only)
+        self.pre_steps: List[Callable[[], None]] = []   # weight repacks
+        self._resample_cache = {}
+        self._alloc()
+        self._build_forward()
+        if training:
+            self._build_backward()
+
+    # ------------------------------------------------------------------ buffers
+    def _new(self, v: Val, grad=False):
+        return torch.zeros((self.batch, v.h, v.w, v.c), dtype=v.dtype, device=self.dev)
+
+    def _alloc(self):
+        all_vals = []
+        seen = set()
+
+        def add(v):
+            if id(v) not in seen:
+                seen.add(id(v)); all_vals.append(v)
+
+        for v in self.vals.values():
+            add(v)
+        for op in self.ops:
+            for v in op.inputs:
+                add(v)
+            add(op.output)
+        roots = [v for v in all_vals if v.parent is None]
+        for v in roots:
+            v.buf = self._new(v)
+            if self.training and v.needs_grad:
+                v.grad = self._new(v)
+        for v in all_vals:
+            if v.parent is not None:
+                p = v.parent
+                v.buf = p.buf[..., v.offset:v.offset + v.c]
+                if self.training:
+                    v.grad = p.grad[..., v.offset:v.offset + v.c]
+        self.all_vals = all_vals
+
+    def _plans(self, in_hw, out_hw, antialias):
+        key = (in_hw, out_hw, antialias)
+        if key not in self._resample_cache:
+            self._resample_cache[key] = (ops.ResamplePlan(in_hw[0], out_hw[0], antialias, self.dev),
+                                         ops.ResamplePlan(in_hw[1], out_hw[1], antialias, self.dev))
+        return self._resample_cache[key]
+
+    # ------------------------------------------------------------------ forward
+    def _build_forward(self):
+        m, S = self.model, self.steps
+        npix = lambda v: self.batch * v.h * v.w
+        for op in self.ops:
+            k = op.kind
+            if k == "cast_input":
+                S.append(lambda a=op.inputs[0], b=op.output: ops.copy_tensor(a.buf, b.buf))
+            elif k == "conv":
+                filt, bias = m._filter(op.layer), m._param(op.layer, "bias")
+                if filt.ohwi is not None:
+                    self.pre_steps.append(filt.repack)
+                S.append(lambda x=op.inputs[0], f=filt, b=bias, y=op.output, o=op:
+                         ops.conv2d_fprop(x.buf, f, b, y.buf, o.act))
+            elif k == "ln":
+                g, b = m._param(op.layer, "gamma"), m._param(op.layer, "beta")
+                op.mean = torch.empty(npix(op.output), dtype=torch.float32, device=self.dev)
+                op.rstd = torch.empty_like(op.mean)
+                S.append(lambda z=op.inputs[0], y=op.output, o=op, g=g, b=b:
+                         ops.layernorm_fwd(z.buf, g, b, o.layer.epsilon, o.relu, y.buf, o.mean, o.rstd))
+            elif k == "bn":
+                g, b = m._param(op.layer, "gamma"), m._param(op.layer, "beta")
+                mm, mv = m._param(op.layer, "moving_mean"), m._param(op.layer, "moving_variance")
+                c = op.output.c
+                op.save_mean = torch.empty(c, dtype=torch.float32, device=self.dev)
+                op.save_rstd = torch.empty_like(op.save_mean)
+                op.stats_ws = torch.empty(2 * c, dtype=torch.float64, device=self.dev)
+                if self.training:
+                    S.append(lambda z=op.inputs[0], y=op.output, o=op, g=g, b=b, mm=mm, mv=mv:
+                             ops.batchnorm_fwd_train(z.buf, g, b, o.layer.epsilon, o.layer.momentum, o.relu, y.buf,
+                                                     o.save_mean, o.save_rstd, mm, mv, o.stats_ws))
+                else:
+                    S.append(lambda z=op.inputs[0], y=op.output, o=op, g=g, b=b, mm=mm, mv=mv:
+                             ops.batchnorm_fwd_infer(z.buf, g, b, o.layer.epsilon, o.relu, mm, mv, y.buf))
+            elif k == "resize":
+                x, y = op.inputs[0], op.output
+                if (x.h, x.w) == (y.h, y.w):
+                    op.identity = True
+                    S.append(lambda x=x, y=y: ops.copy_tensor(x.buf, y.buf))
+                else:
+                    op.identity = False
+                    op.ph, op.pw = self._plans((x.h, x.w), (y.h, y.w), op.antialias)
+                    S.append(lambda x=x, y=y, o=op: ops.resample2d(x.buf, y.buf, o.ph, o.pw))
+            elif k == "maxpool":
+                S.append(lambda x=op.inputs[0], y=op.output: ops.maxpool2_fwd(x.buf, y.buf))
+            elif k == "convT":
+                kern, bias = m._shadow(op.layer, "kernel"), m._param(op.layer, "bias")
+                S.append(lambda x=op.inputs[0], y=op.output, kk=kern, b=bias: ops.convT2x2_fprop(x.buf, kk, b, y.buf))
+            elif k == "concat":
+                for vin, off in op.copies:
+                    S.append(lambda a=vin, y=op.output, off=off: ops.copy_tensor(a.buf, y.buf[..., off:off + a.c]))
+            elif k == "clipadd":
+                S.append(lambda a=op.inputs[0], r=op.inputs[1], y=op.output: ops.clipadd_fwd(a.buf, r.buf, y.buf))
+            elif k == "softmax":
+                S.append(lambda z=op.inputs[0], p=op.output: ops.softmax_fwd(z.buf, p.buf))
+            else:
+                raise AssertionError(k)
+
+    # ------------------------------------------------------------------ backward
+    def _build_backward(self):
+        m, B = self.model, self.bwd_steps
+        ws_bytes = 0
+        for op in self.ops:
+            if op.kind == "conv" and op.layer.kernel_size == (3, 3):
+                ws_bytes = max(ws_bytes, ops.conv2d_wgrad_workspace(op.inputs[0].buf, op.output.buf, 3, 3))
+        self.wgrad_ws = torch.empty(max(ws_bytes, 16) // 4, dtype=torch.float32, device=self.dev)
+
+        def write_flag(v: Val) -> bool:
+            acc = v.grad_written
+            v.mark_grad_written()
+            return acc
+
+        self.output_val.mark_grad_written()   # the loss kernel writes d(output)
+        for op in reversed(self.ops):
+            k, out = op.kind, op.output
+            if k == "cast_input" or not out.needs_grad:
+                continue
+            if k == "conv":
+                x, ly = op.inputs[0], op.layer
+                filt = m._filter(ly)
+                dbias = m._grad(ly, "bias")
+                kh = ly.kernel_size[0]
+                if op.act != ACT_NONE:
+                    B.append(lambda o=out, a=op.act, db=dbias: ops.bias_act_bwd(o.grad, o.buf, a, o.grad, db))
+                elif not op.norm_bias and dbias is not None:
+                    B.append(lambda o=out, db=dbias: ops.bias_act_bwd(o.grad, o.buf, ACT_NONE, o.grad, db))
+                dw = m._grad(ly, "kernel").view(-1)
+                B.append(lambda x=x, o=out, dw=dw, kh=kh: ops.conv2d_wgrad(x.buf, o.grad, kh, kh, dw, self.wgrad_ws))
+                if x.needs_grad:
+                    acc = write_flag(x)
+                    B.append(lambda x=x, o=out, f=filt, acc=acc: ops.conv2d_dgrad(o.grad, f, x.grad, acc))
+            elif k == "ln":
+                z, ly = op.inputs[0], op.layer
+                assert not z.grad_written, "LayerNormalization input must have a single consumer"
+                z.mark_grad_written()
+                dbias = m._grad(op.conv_src.layer, "bias") if op.conv_src is not None else None
+                B.append(lambda z=z, o=out, op=op, g=m._param(ly, "gamma"), b=m._param(ly, "beta"),
+                         dg=m._grad(ly, "gamma"), db=m._grad(ly, "beta"), dbias=dbias:
+                         ops.layernorm_bwd(o.grad, z.buf, op.mean, op.rstd, g, b, op.relu, z.grad, dg, db, dbias))
+            elif k == "bn":
+                z, ly = op.inputs[0], op.layer
+                assert not z.grad_written, "BatchNormalization input must have a single consumer"
+                z.mark_grad_written()
+                B.append(lambda z=z, o=out, op=op, g=m._param(ly, "gamma"), b=m._param(ly, "beta"),
+                         dg=m._grad(ly, "gamma"), db=m._grad(ly, "beta"):
+                         ops.batchnorm_bwd(o.grad, z.buf, op.save_mean, op.save_rstd, g, b, op.relu, z.grad, dg, db,
+                                           op.stats_ws))
+            elif k == "resize":
+                x = op.inputs[0]
+                if x.needs_grad:
+                    acc = write_flag(x)
+                    if op.identity:
+                        if acc:
+                            raise NotImplementedError("identity resize feeding an accumulated gradient")
+                        B.append(lambda x=x, o=out: ops.copy_tensor(o.grad, x.grad))
+                    else:
+                        B.append(lambda x=x, o=out, op=op, acc=acc: ops.resample2d_bwd(o.grad, x.grad, op.ph, op.pw, acc))
+            elif k == "maxpool":
+                x = op.inputs[0]
+                if x.needs_grad:
+                    acc = write_flag(x)
+                    B.append(lambda x=x, o=out, acc=acc: ops.maxpool2_bwd(x.buf, o.buf, o.grad, x.grad, acc))
+            elif k == "convT":
+                x, ly = op.inputs[0], op.layer
+                B.append(lambda x=x, o=out, dk=m._grad(ly, "kernel"), db=m._grad(ly, "bias"):
+                         ops.convT2x2_wgrad(x.buf, o.grad, dk, db))
+                if x.needs_grad:
+                    if write_flag(x):
+                        raise NotImplementedError("Conv2DTranspose input with several consumers")
+                    B.append(lambda x=x, o=out, kk=m._shadow(ly, "kernel"): ops.convT2x2_dgrad(o.grad, kk, x.grad))
+            elif k == "concat":
+                for vin, off in op.copies:
+                    if vin.needs_grad:
+                        if write_flag(vin):
+                            raise NotImplementedError("copied concat input with several consumers")
+                        B.append(lambda a=vin, o=out, off=off: ops.copy_tensor(o.grad[..., off:off + a.c], a.grad))
+                # aliased inputs: their gradient IS the slice of d(concat), already written by the consumer
+            elif k == "clipadd":
+                inp, res = op.inputs
+                if write_flag(res):
+                    raise NotImplementedError("residual with several consumers")
+                B.append(lambda a=inp, r=res, o=out: ops.clipadd_bwd(a.buf, r.buf, o.grad, r.grad))
+            elif k == "softmax":
+                # softmax + categorical cross-entropy: the loss kernel writes d(logits) directly
+                op.inputs[0].mark_grad_written()
+            else:
+                raise AssertionError(k)
+
+    # ------------------------------------------------------------------ execution
+    def run_pre(self):
+        for f in self.pre_steps:
+            f()
+
+    def run_forward(self):
+        for f in self.steps:
+            f()
+
+    def run_backward(self):
+        for f in self.bwd_steps:
+            f()

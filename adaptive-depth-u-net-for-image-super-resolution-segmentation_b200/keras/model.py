@@ -1,0 +1,497 @@
+"""Keras-shaped ``Model``: compile / fit / evaluate / predict / __call__ / summary / weights IO.
+
+Mirrors the slice of ``keras.Model`` the reference's entry points use
+(/root/reference: Super_resolution/code/train_adaptive_unet.py:489-494 compile,
+:511-516 load_weights, :541-543 summary, :622-632 fit, :676 __call__;
+Segmenation/code/train_adaptive_unet.py:503-546).  All arithmetic runs in the
+library's sm_100a kernels through ``engine.Plan``; one training step
+(zero-grad, forward, loss, backward, gradient all-reduce, Adam) is one CUDA graph.
+"""
+from __future__ import annotations
+
+import io
+import json
+import math
+import os
+import time
+import zipfile
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from .. import ops
+from .._ffi import B200Error
+from . import layers as L
+from .engine import Plan
+
+_POLICY = {"name": "float32"}
+_SEED = {"value": 1234}
+
+
+def set_global_policy(name: str):
+    """keras.mixed_precision.set_global_policy.  "mixed_bfloat16" computes/stores activations in
+    bf16 with fp32 master weights; "mixed_float16" (the reference's policy,
+    train_adaptive_unet.py:471-477) is mapped to the same bf16 path -- the B200 kernels are bf16."""
+    if name not in ("float32", "mixed_bfloat16", "mixed_float16"):
+        raise ValueError(f"unknown policy {name!r}")
+    _POLICY["name"] = name
+
+
+def global_policy() -> str:
+    return _POLICY["name"]
+
+
+def set_random_seed(seed: int):
+    _SEED["value"] = int(seed)
+
+
+def _init_array(kind, shape, rng):
+    if kind in ("glorot_uniform", "glorot_uniform_T"):
+        kh, kw, a, b = shape
+        fan_in, fan_out = (kh * kw * a, kh * kw * b) if kind == "glorot_uniform" else (kh * kw * b, kh * kw * a)
+        lim = math.sqrt(6.0 / (fan_in + fan_out))
+        return rng.uniform(-lim, lim, size=shape).astype(np.float32)
+    if kind == "ones":
+        return np.ones(shape, np.float32)
+    if kind == "zeros":
+        return np.zeros(shape, np.float32)
+    raise NotImplementedError(f"initializer {kind!r}")
+
+
+class History:
+    def __init__(self):
+        self.epoch: List[int] = []
+        self.history: Dict[str, List[float]] = {}
+
+
+class Model:
+    def __init__(self, inputs, outputs, name: Optional[str] = None):
+        self.inputs = list(inputs) if isinstance(inputs, (list, tuple)) else [inputs]
+        self.outputs = list(outputs) if isinstance(outputs, (list, tuple)) else [outputs]
+        if len(self.inputs) != 1 or len(self.outputs) != 1:
+            raise NotImplementedError("single-input single-output models only")
+        self.name = name or "functional"
+        seen, nodes = set(), []
+
+        def visit(t):
+            nd = t.node
+            if id(nd) in seen:
+                return
+            seen.add(id(nd))
+            for i in nd.inputs:
+                visit(i)
+            nodes.append(nd)
+
+        visit(self.outputs[0])
+        self._nodes = sorted(nodes, key=lambda n: n.seq)
+        self.layers: List[L.Layer] = []
+        for nd in self._nodes:
+            if nd.layer not in self.layers:
+                self.layers.append(nd.layer)
+        self.optimizer = None
+        self.loss = None
+        self.metrics_fns = []
+        self.stop_training = False
+        self._built = False
+        self._plans: Dict[tuple, Plan] = {}
+        self._graphs: Dict[tuple, object] = {}
+        self._dist = None
+        self.use_cuda_graph = os.environ.get("B200_NO_CUDA_GRAPH", "0") != "1"
+        self.input_shape = self.inputs[0].shape
+        self.output_shape = self.outputs[0].shape
+
+    # ------------------------------------------------------------------ parameters
+    def _ensure_built(self):
+        if self._built:
+            return
+        if not torch.cuda.is_available():
+            raise B200Error("b200unet needs a CUDA device (sm_100a): there is no CPU fallback for the hot path")
+        ops.lib()
+        self._device = torch.device("cuda", torch.cuda.current_device())
+        self._compute_dtype = torch.float32 if _POLICY["name"] == "float32" else torch.bfloat16
+        rng = np.random.default_rng(_SEED["value"])
+        self._pinfo: Dict[str, tuple] = {}
+        off_t = off_n = 0
+        host_t, host_n = [], []
+        for ly in self.layers:
+            for w in ly.weight_specs:
+                val = w["value"] if w["value"] is not None else _init_array(w["init"], w["shape"], rng)
+                n = int(np.prod(w["shape"]))
+                if w["trainable"]:
+                    self._pinfo[w["name"]] = (True, off_t, w["shape"])
+                    host_t.append((off_t, val)); off_t += (n + 63) // 64 * 64
+                else:
+                    self._pinfo[w["name"]] = (False, off_n, w["shape"])
+                    host_n.append((off_n, val)); off_n += (n + 63) // 64 * 64
+                w["value"] = None
+            ly._model = self
+        self._nparams = off_t
+        flat = np.zeros(max(off_t, 64), np.float32)
+        for o, v in host_t:
+            flat[o:o + v.size] = v.ravel()
+        flat_n = np.zeros(max(off_n, 64), np.float32)
+        for o, v in host_n:
+            flat_n[o:o + v.size] = v.ravel()
+        dev = self._device
+        self.P = torch.from_numpy(flat).to(dev)
+        self.G = torch.zeros_like(self.P)
+        self.NT = torch.from_numpy(flat_n).to(dev)
+        self.S = self.P if self._compute_dtype == torch.float32 else torch.empty_like(self.P, dtype=self._compute_dtype)
+        self._filters: Dict[str, ops.ConvFilter] = {}
+        self._built = True
+        self._refresh_shadow()
+
+    def _refresh_shadow(self):
+        if self.S is not self.P:
+            ops.cast(self.P, self.S)
+        for f in self._filters.values():
+            f.repack()
+
+    def _view(self, flat, ly, name):
+        key = f"{ly.name}/{name}"
+        if key not in self._pinfo:
+            return None
+        trainable, off, shape = self._pinfo[key]
+        n = int(np.prod(shape))
+        return flat[off:off + n].view(shape)
+
+    def _param(self, ly, name):
+        key = f"{ly.name}/{name}"
+        if key not in self._pinfo:
+            return None
+        return self._view(self.P if self._pinfo[key][0] else self.NT, ly, name)
+
+    def _grad(self, ly, name):
+        key = f"{ly.name}/{name}"
+        if key not in self._pinfo or not self._pinfo[key][0]:
+            return None
+        return self._view(self.G, ly, name)
+
+    def _shadow(self, ly, name):
+        return self._view(self.S, ly, name)
+
+    def _filter(self, ly) -> ops.ConvFilter:
+        if ly.name not in self._filters:
+            hwio = self._shadow(ly, "kernel")
+            kh, kw, cin, cout = hwio.shape
+            packed = (hwio.dtype == torch.bfloat16 and (kh, kw) == (3, 3) and cin % 64 == 0 and cout % 64 == 0)
+            f = ops.ConvFilter.__new__(ops.ConvFilter)
+            f.hwio, f.kh, f.kw, f.cin, f.cout = hwio, kh, kw, cin, cout
+            f.ohwi = torch.empty((kh, kw, cout, cin), dtype=hwio.dtype, device=hwio.device) if packed else None
+            f.repack()
+            self._filters[ly.name] = f
+        return self._filters[ly.name]
+
+    # weights API ---------------------------------------------------------------
+    def _layer_weights(self, ly):
+        self._ensure_built()
+        return [self._param(ly, w["name"].split("/", 1)[1]).detach().cpu().numpy().copy() for w in ly.weight_specs]
+
+    def _push_layer_weights(self, ly):
+        self._ensure_built()
+        for w in ly.weight_specs:
+            if w["value"] is not None:
+                self._param(ly, w["name"].split("/", 1)[1]).copy_(torch.from_numpy(w["value"]).to(self._device))
+                w["value"] = None
+        self._refresh_shadow()
+
+    @property
+    def weights(self):
+        return [w for ly in self.layers for w in ly.weight_specs]
+
+    def get_weights(self):
+        return [a for ly in self.layers for a in self._layer_weights(ly)]
+
+    def set_weights(self, values):
+        self._ensure_built()
+        values = list(values)
+        i = 0
+        for ly in self.layers:
+            k = len(ly.weight_specs)
+            if k:
+                for w, v in zip(ly.weight_specs, values[i:i + k]):
+                    v = np.asarray(v, np.float32)
+                    if tuple(v.shape) != w["shape"]:
+                        raise ValueError(f"{w['name']}: shape {v.shape} != {w['shape']}")
+                    self._param(ly, w["name"].split("/", 1)[1]).copy_(torch.from_numpy(v).to(self._device))
+                i += k
+        if i != len(values):
+            raise ValueError(f"expected {i} weight arrays, got {len(values)}")
+        self._refresh_shadow()
+
+    def count_params(self):
+        return sum(ly.count_params() for ly in self.layers)
+
+    def get_layer(self, name):
+        for ly in self.layers:
+            if ly.name == name:
+                return ly
+        raise ValueError(f"No such layer: {name}")
+
+    # checkpoints: a .keras file is a zip; the weights member is an .npz because h5py is not
+    # available in this image (documented deviation).
+    def save(self, path):
+        path = str(path)
+        buf = io.BytesIO()
+        np.savez(buf, **{f"w{i:04d}": a for i, a in enumerate(self.get_weights())})
+        cfg = {"name": self.name, "layers": [{"class": type(ly).__name__, "config": ly.get_config()} for ly in self.layers],
+               "weight_names": [w["name"] for w in self.weights]}
+        with zipfile.ZipFile(path, "w") as z:
+            z.writestr("config.json", json.dumps(cfg, default=str))
+            z.writestr("metadata.json", json.dumps({"format": "b200unet-npz", "keras_version": "3.3.3-compatible-api"}))
+            z.writestr("model.weights.npz", buf.getvalue())
+
+    save_weights = save
+
+    def load_weights(self, path):
+        path = str(path)
+        with zipfile.ZipFile(path) as z:
+            names = z.namelist()
+            if "model.weights.npz" not in names:
+                raise B200Error(f"{path}: no model.weights.npz member (HDF5 .keras archives need h5py, "
+                                "which this image lacks; convert with tools/keras_to_npz.py)")
+            data = np.load(io.BytesIO(z.read("model.weights.npz")))
+        self.set_weights([data[k] for k in sorted(data.files)])
+
+    # ------------------------------------------------------------------ summary
+    def summary(self, print_fn=print, line_length=78):
+        rows = []
+        for nd in self._nodes:
+            ly = nd.layer
+            conn = ", ".join(t.name for t in nd.inputs) or "-"
+            shape = "(" + ", ".join("None" if d is None else str(d) for d in nd.output.shape) + ")"
+            params = ly.count_params() if nd.call_index == 0 else 0
+            rows.append((f"{ly.name} ({type(ly).__name__})", shape, f"{params:,}", conn))
+        w = [max(len(r[i]) for r in rows + [("Layer (type)", "Output Shape", "Param #", "Connected to")]) for i in range(4)]
+        fmt = lambda r: " | ".join(s.ljust(w[i]) for i, s in enumerate(r))
+        print_fn(f'Model: "{self.name}"')
+        print_fn(fmt(("Layer (type)", "Output Shape", "Param #", "Connected to")))
+        print_fn("-+-".join("-" * x for x in w))
+        for r in rows:
+            print_fn(fmt(r))
+        total = self.count_params()
+        train = sum(int(np.prod(x["shape"])) for x in self.weights if x["trainable"])
+        mb = lambda n: f"{n * 4 / 2**20:.2f} MB"
+        print_fn(f" Total params: {total:,} ({mb(total)})")
+        print_fn(f" Trainable params: {train:,} ({mb(train)})")
+        print_fn(f" Non-trainable params: {total - train:,} ({mb(total - train)})")
+
+    # ------------------------------------------------------------------ compile
+    def compile(self, optimizer=None, loss=None, metrics=None, jit_compile=False, **kwargs):
+        from . import losses as LS
+        from . import optimizers as O
+        self.optimizer = optimizer if optimizer is not None else O.Adam()
+        if isinstance(self.optimizer, str):
+            self.optimizer = {"adam": O.Adam}[self.optimizer.lower()]()
+        self.loss = LS.resolve_loss(loss)
+        self.metrics_fns = list(metrics or [])
+        self._plans = {k: v for k, v in self._plans.items() if not k[1]}
+        self._graphs = {}
+
+    def distribute(self, process_group=None):
+        """Batch-sharded data parallelism: one process per GPU, gradients summed with NCCL
+        (torch.distributed) inside the captured step.  Call after torch.distributed is initialised."""
+        import torch.distributed as dist
+        self._dist = (dist, process_group)
+        self._graphs = {}
+        self._ensure_built()
+        dist.broadcast(self.P, src=0, group=process_group)
+        dist.broadcast(self.NT, src=0, group=process_group)
+        self._refresh_shadow()
+
+    # ------------------------------------------------------------------ plans
+    def _plan(self, batch, training) -> Plan:
+        self._ensure_built()
+        key = (batch, training)
+        if key not in self._plans:
+            self._plans[key] = Plan(self, batch, training)
+        return self._plans[key]
+
+    def _world(self):
+        if self._dist is None:
+            return 1
+        return self._dist[0].get_world_size(self._dist[1])
+
+    def _train_body(self, plan: Plan, st):
+        """The launches of one training step, in stream order."""
+        self.G.zero_()
+        plan.run_pre()
+        plan.run_forward()
+        self.loss.launch(plan, st, grad_scale=1.0 / self._world())
+        plan.run_backward()
+        if self._dist is not None:
+            self._dist[0].all_reduce(self.G, group=self._dist[1])
+        self.optimizer.apply(self)
+
+    def _train_state(self, batch):
+        key = ("train", batch)
+        if key in self._graphs:
+            return self._graphs[key]
+        plan = self._plan(batch, True)
+        st = self.loss.make_state(plan)
+        self.optimizer.ensure_state(self)
+        entry = {"plan": plan, "state": st, "graph": None}
+        if self.use_cuda_graph:
+            # warm-up on a side stream (sets kernel attributes, initialises NCCL), then capture
+            snap = (self.P.clone(), self.optimizer.snapshot(), self.NT.clone())
+            s = torch.cuda.Stream()
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):
+                self._train_body(plan, st)
+            torch.cuda.current_stream().wait_stream(s)
+            torch.cuda.synchronize()
+            self.P.copy_(snap[0]); self.optimizer.restore(snap[1]); self.NT.copy_(snap[2])
+            self._refresh_shadow()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._train_body(plan, st)
+            entry["graph"] = g
+            # capture executes nothing, but be explicit that state is unchanged
+        self._graphs[key] = entry
+        return entry
+
+    def _eval_state(self, batch, with_loss):
+        key = ("eval", batch, with_loss)
+        if key in self._graphs:
+            return self._graphs[key]
+        plan = self._plan(batch, False)
+        st = self.loss.make_state(plan) if with_loss else None
+
+        def body():
+            plan.run_pre()
+            plan.run_forward()
+            if with_loss:
+                self.loss.launch(plan, st, grad_scale=1.0, with_grad=False)
+
+        entry = {"plan": plan, "state": st, "graph": None, "body": body}
+        if self.use_cuda_graph:
+            s = torch.cuda.Stream()
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):
+                body()
+            torch.cuda.current_stream().wait_stream(s)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                body()
+            entry["graph"] = g
+        self._graphs[key] = entry
+        return entry
+
+    @staticmethod
+    def _to_device(dst: torch.Tensor, src):
+        if isinstance(src, np.ndarray):
+            src = torch.from_numpy(src)
+        if src.dtype != dst.dtype and not src.is_cuda:
+            src = src.to(dst.dtype)
+        dst.copy_(src.reshape(dst.shape), non_blocking=True)
+
+    # ------------------------------------------------------------------ steps
+    def train_on_batch(self, x, y, return_tensors=False):
+        """One optimisation step; returns {"loss": ..., metric: ...} (device tensors if asked)."""
+        if self.loss is None:
+            raise RuntimeError("compile() the model before training")
+        batch = int(x.shape[0])
+        e = self._train_state(batch)
+        plan, st = e["plan"], e["state"]
+        self._to_device(plan.input_vals[0].buf, x)
+        self.loss.set_target(st, y)
+        self.optimizer.before_step()
+        if e["graph"] is not None:
+            e["graph"].replay()
+        else:
+            self._train_body(plan, st)
+        logs = self.loss.logs(st)
+        return logs if return_tensors else {k: float(v) for k, v in logs.items()}
+
+    def test_on_batch(self, x, y):
+        batch = int(x.shape[0])
+        e = self._eval_state(batch, True)
+        plan, st = e["plan"], e["state"]
+        self._to_device(plan.input_vals[0].buf, x)
+        self.loss.set_target(st, y)
+        e["graph"].replay() if e["graph"] is not None else e["body"]()
+        return self.loss.logs(st)
+
+    def __call__(self, x, training=False):
+        if training:
+            raise NotImplementedError("Model(x, training=True): use train_on_batch / fit")
+        batch = int(x.shape[0])
+        e = self._eval_state(batch, False)
+        plan = e["plan"]
+        self._to_device(plan.input_vals[0].buf, x)
+        e["graph"].replay() if e["graph"] is not None else e["body"]()
+        return plan.output_val.buf.clone()
+
+    def predict(self, x, batch_size=32, verbose=0):
+        outs = []
+        for i in range(0, len(x), batch_size):
+            outs.append(self(x[i:i + batch_size]).float().cpu().numpy())
+        return np.concatenate(outs, axis=0)
+
+    # ------------------------------------------------------------------ fit / evaluate
+    def evaluate(self, dataset, steps=None, return_dict=False, verbose=0):
+        sums, n = {}, 0
+        for i, (x, y) in enumerate(dataset):
+            if steps is not None and i >= steps:
+                break
+            logs = self.test_on_batch(x, y)
+            for k, v in logs.items():
+                sums[k] = sums.get(k, 0.0) + float(v)
+            n += 1
+        res = {k: v / max(n, 1) for k, v in sums.items()}
+        return res if return_dict else list(res.values())
+
+    def fit(self, x=None, y=None, epochs=1, initial_epoch=0, steps_per_epoch=None, validation_data=None,
+            validation_steps=None, validation_freq=1, callbacks=None, verbose=1, batch_size=None, **kwargs):
+        from .callbacks import CallbackList
+        history = History()
+        cbs = CallbackList(callbacks or [], self)
+        cbs.history = history
+        self.stop_training = False
+        cbs.on_train_begin()
+        start_epoch = cbs.initial_epoch(initial_epoch)
+        train_iter = iter(x)
+        for epoch in range(start_epoch, epochs):
+            if self.stop_training:
+                break
+            cbs.on_epoch_begin(epoch)
+            t0 = time.time()
+            acc: Dict[str, torch.Tensor] = {}
+            steps = 0
+            while steps_per_epoch is None or steps < steps_per_epoch:
+                try:
+                    xb, yb = next(train_iter)
+                except StopIteration:
+                    if steps_per_epoch is None:
+                        break
+                    train_iter = iter(x)
+                    xb, yb = next(train_iter)
+                logs = self.train_on_batch(xb, yb, return_tensors=True)
+                for k, v in logs.items():
+                    acc[k] = v.clone() if k not in acc else acc[k] + v
+                steps += 1
+            if steps_per_epoch is None:
+                train_iter = iter(x)
+            logs = {k: float(v) / max(steps, 1) for k, v in acc.items()}
+            if validation_data is not None and (epoch + 1) % validation_freq == 0:
+                val = self.evaluate(validation_data, steps=validation_steps, return_dict=True)
+                logs.update({f"val_{k}": v for k, v in val.items()})
+            if hasattr(self.optimizer, "current_lr"):
+                logs["learning_rate"] = self.optimizer.current_lr()
+            dt = time.time() - t0
+            if verbose:
+                # keras verbose=2 line, kept parseable by the reference's export_log_metrics.py:29-74
+                ms = 1000.0 * dt / max(steps, 1)
+                per = f"{ms:.0f}ms/step" if ms >= 1 else f"{ms * 1000:.0f}us/step"
+                items = " - ".join(f"{k}: {v:.4f}" if abs(v) >= 1e-3 or v == 0 else f"{k}: {v:.4e}"
+                                   for k, v in logs.items())
+                print(f"Epoch {epoch + 1}/{epochs}")
+                print(f"{steps}/{steps} - {dt:.0f}s - {per} - {items}", flush=True)
+            history.epoch.append(epoch)
+            for k, v in logs.items():
+                history.history.setdefault(k, []).append(v)
+            cbs.on_epoch_end(epoch, logs)
+        cbs.on_train_end()
+        return history

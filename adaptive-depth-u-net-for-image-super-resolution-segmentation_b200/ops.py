@@ -24,6 +24,10 @@ def lib():
     return _ffi.load()
 
 
+def launch_count(reset: bool = False) -> int:
+    return int(lib().b200_launch_count(int(reset)))
+
+
 def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 

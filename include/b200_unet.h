@@ -77,6 +77,8 @@ const char* b200_version(void);
 const char* b200_last_error(void);
 /* host out-params: SM count, compute capability. */
 int b200_device_info(int* sm_count, int* cc_major, int* cc_minor);
+/* number of kernels this library has launched in the calling process (optionally reset). */
+long long b200_launch_count(int reset);
 
 /* ---- convolution (keras Conv2D, stride 1, padding "same") ---------------
  * Replaces L.Conv2D at train_adaptive_unet.py:202,207,259,267; seg :326,329,361;
@@ -182,7 +184,8 @@ int b200_softmax_ce_loss(const b200_tensor* prob, const int32_t* labels, float g
                          const b200_tensor* dlogits, float* ws, void* stream);
 
 /* ---- Adam -- train_adaptive_unet.py:490 -----------------------------------
- * hyper (device fp32[4]) = {lr, beta1, beta2, eps}; step (device int32[1]) is the
+ * hyper (device fp32[6]) = {lr, beta1, beta2, eps, 1-beta1, 1-beta2} (the last two evaluated in
+ * double on the host and then rounded, as keras does); step (device int32[1]) is the
  * 1-based step count, incremented by b200_adam_advance.  Updates p/m/v in place and
  * writes the compute-dtype shadow copy of p (bf16 or NULL). */
 int b200_adam_advance(int32_t* step, void* stream);

@@ -26,7 +26,7 @@ def _K():
 
 # ----------------------------------------------------------------------------- conv (SIMT)
 @pytest.mark.parametrize("dtype", DTYPES)
-@pytest.mark.parametrize("shape", [(2, 13, 9, 3, 64, 3), (1, 16, 16, 64, 32, 3), (2, 8, 8, 20, 3, 1), (1, 5, 7, 64, 21, 1)])
+@pytest.mark.parametrize("shape", [(2, 13, 9, 3, 64, 3), (1, 16, 16, 64, 32, 3), (2, 8, 8, 20, 3, 1), (1, 5, 7, 64, 21, 1), (1, 9, 8, 64, 192, 3), (1, 8, 9, 192, 64, 3)])
 def test_conv_simt(dtype, shape):
     ops, K = _ops(), _K()
     n, h, w, ci, co, ks = shape
@@ -251,19 +251,20 @@ def test_batchnorm(dtype, c):
 @pytest.mark.parametrize("dtype", DTYPES)
 @pytest.mark.parametrize("sizes", [((16, 16), (8, 8)), ((13, 9), (4, 3)), ((8, 8), (32, 32)), ((45, 45), (63, 63)), ((2, 2), (1, 1)), ((1, 1), (2, 2)), ((20, 20), (14, 14))])
 @pytest.mark.parametrize("c", [64, 3])
-def test_resample(dtype, sizes, c):
+@pytest.mark.parametrize("aa", [True, False])
+def test_resample(dtype, sizes, c, aa):
     ops, K = _ops(), _K()
     (h, w), (oh, ow) = sizes
     x = rand((2, h, w, c), 71, dtype)
     dy = rand((2, oh, ow, c), 72, dtype)
-    ph = ops.ResamplePlan(h, oh, True, "cuda"); pw = ops.ResamplePlan(w, ow, True, "cuda")
+    ph = ops.ResamplePlan(h, oh, aa, "cuda"); pw = ops.ResamplePlan(w, ow, aa, "cuda")
     y = torch.empty((2, oh, ow, c), dtype=dtype, device="cuda")
     ops.resample2d(x, y, ph, pw)
     base = rand((2, h, w, c), 73, dtype)
     dx = base.clone()
     ops.resample2d_bwd(dy, dx, ph, pw, accumulate=True)
     xr = f32(x).requires_grad_()
-    yr = K.resize_bilinear(xr, oh, ow)
+    yr = K.resize_bilinear(xr, oh, ow, aa)
     (yr * f32(dy)).sum().backward()
     assert relerr(y, yr) < TOL[dtype]
     assert relerr(dx, xr.grad + f32(base)) < TOL[dtype]
@@ -388,7 +389,7 @@ def test_adam():
     ops, K = _ops(), _K()
     n = 1003
     p = rand((n,), 141); g = rand((n,), 142, scale=0.1); m = torch.zeros(n, device="cuda"); v = torch.zeros(n, device="cuda")
-    hyper = torch.tensor([1e-3, 0.9, 0.999, 1e-7], device="cuda"); step = torch.zeros(1, dtype=torch.int32, device="cuda")
+    hyper = torch.tensor([1e-3, 0.9, 0.999, 1e-7, 1 - 0.9, 1 - 0.999], device="cuda"); step = torch.zeros(1, dtype=torch.int32, device="cuda")
     shadow = torch.empty(n, dtype=torch.bfloat16, device="cuda")
     pr, mr, vr = f32(p), torch.zeros(n), torch.zeros(n)
     for t in range(1, 4):
