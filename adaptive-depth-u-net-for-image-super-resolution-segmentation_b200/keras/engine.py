@@ -221,10 +221,19 @@ class Plan:
 
     # ------------------------------------------------------------------ forward
     def _build_forward(self):
-        m, S = self.model, self.steps
+        m = self.model
         npix = lambda v: self.batch * v.h * v.w
+        self.step_tags: List[str] = []
+
+        class _Tagged(list):
+            def append(inner, fn, _tags=self.step_tags):
+                _tags.append(self._cur_tag)
+                list.append(inner, fn)
+
+        S = self.steps = _Tagged()
         for op in self.ops:
             k = op.kind
+            self._cur_tag = k + (":tc" if k == "conv" and self.is_tc(op) else (":simt" if k == "conv" else ""))
             if k == "cast_input":
                 S.append(lambda a=op.inputs[0], b=op.output: ops.copy_tensor(a.buf, b.buf))
             elif k == "conv":
@@ -279,7 +288,15 @@ class Plan:
 
     # ------------------------------------------------------------------ backward
     def _build_backward(self):
-        m, B = self.model, self.bwd_steps
+        m = self.model
+        self.bwd_tags: List[str] = []
+
+        class _Tagged(list):
+            def append(inner, fn, _tags=self.bwd_tags):
+                _tags.append(self._cur_tag)
+                list.append(inner, fn)
+
+        B = self.bwd_steps = _Tagged()
         ws_bytes = 0
         for op in self.ops:
             if op.kind == "conv" and op.layer.kernel_size == (3, 3):
@@ -296,19 +313,24 @@ class Plan:
             k, out = op.kind, op.output
             if k == "cast_input" or not out.needs_grad:
                 continue
+            self._cur_tag = k
             if k == "conv":
                 x, ly = op.inputs[0], op.layer
                 filt = m._filter(ly)
                 dbias = m._grad(ly, "bias")
                 kh = ly.kernel_size[0]
+                sfx = ":tc" if self.is_tc(op) else ":simt"
+                self._cur_tag = "bias_act"
                 if op.act != ACT_NONE:
                     B.append(lambda o=out, a=op.act, db=dbias: ops.bias_act_bwd(o.grad, o.buf, a, o.grad, db))
                 elif not op.norm_bias and dbias is not None:
                     B.append(lambda o=out, db=dbias: ops.bias_act_bwd(o.grad, o.buf, ACT_NONE, o.grad, db))
                 dw = m._grad(ly, "kernel").view(-1)
+                self._cur_tag = "wgrad" + sfx
                 B.append(lambda x=x, o=out, dw=dw, kh=kh: ops.conv2d_wgrad(x.buf, o.grad, kh, kh, dw, self.wgrad_ws))
                 if x.needs_grad:
                     acc = write_flag(x)
+                    self._cur_tag = "dgrad" + sfx
                     B.append(lambda x=x, o=out, f=filt, acc=acc: ops.conv2d_dgrad(o.grad, f, x.grad, acc))
             elif k == "ln":
                 z, ly = op.inputs[0], op.layer
@@ -366,6 +388,13 @@ class Plan:
                 op.inputs[0].mark_grad_written()
             else:
                 raise AssertionError(k)
+
+    @staticmethod
+    def is_tc(op) -> bool:
+        """True when the conv op's shapes select the tcgen05 kernels (mirrors conv_tc_supported)."""
+        x, y, ly = op.inputs[0], op.output, op.layer
+        return (ly.kernel_size == (3, 3) and x.dtype == torch.bfloat16 and x.c % 64 == 0 and y.c % 64 == 0
+                and (y.c == 64 or y.c % 128 == 0))
 
     # ------------------------------------------------------------------ execution
     def run_pre(self):
