@@ -84,6 +84,7 @@ SIGNATURES = {
     "b200_copy_tensor": (_i, [_TP, _TP, _vp]),
     "b200_scale_inplace": (_i, [_vp, _sz, _f, _vp]),
     "b200_debug_umma_probe": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _vp, _vp]),
+    "b200_debug_umma_rate": (_i, [_i, _i, _i, _vp, _i, _vp]),
 }
 
 _lib = None

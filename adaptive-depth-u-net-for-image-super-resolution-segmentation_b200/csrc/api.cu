@@ -37,6 +37,14 @@ int filter_pack(const void*, void*, int, int, int, int, cudaStream_t);
 bool conv_tc_supported(const b200_tensor*, int, int, const b200_tensor*, int);
 int conv_tc_launch(const b200_tensor*, const void*, int, int, int, const float*, const b200_tensor*, int, int, cudaStream_t);
 int umma_probe(const void*, int, const void*, int, int, int, int, float*, cudaStream_t);
+int umma_rate(int, int, int, long long*, int, cudaStream_t);
+bool stem_supported(const b200_tensor*, const b200_tensor*, int);
+int stem_fprop(const b200_tensor*, const void*, const float*, const b200_tensor*, int, cudaStream_t);
+int stem_wgrad(const b200_tensor*, const b200_tensor*, float*, cudaStream_t);
+bool head_supported(const b200_tensor*, const b200_tensor*, int);
+int head_fprop(const b200_tensor*, const void*, const float*, const b200_tensor*, int, cudaStream_t);
+int head_dgrad(const b200_tensor*, const void*, const b200_tensor*, int, cudaStream_t);
+int head_wgrad(const b200_tensor*, const b200_tensor*, float*, cudaStream_t);
 bool wgrad_tc_supported(const b200_tensor*, const b200_tensor*, int);
 size_t wgrad_tc_workspace(const b200_tensor*, const b200_tensor*);
 int wgrad_tc_launch(const b200_tensor*, const b200_tensor*, float*, void*, size_t, cudaStream_t);
@@ -117,6 +125,10 @@ int b200_conv2d_fprop(const b200_tensor* x, const b200_filter* f, const float* b
     B200_REQUIRE(tc_ok, B200_ERR_UNSUPPORTED, "conv2d_fprop: tcgen05 path does not support this shape/dtype");
     return conv_tc_launch(x, f->ohwi, f->cin, f->cout, 0, bias, y, act, 0, ST(stream));
   }
+  if (algo == B200_ALGO_AUTO && f->dtype == x->dtype && f->kh == f->kw) {
+    if (stem_supported(x, y, f->kh) && act != B200_ACT_SIGMOID) return stem_fprop(x, f->hwio, bias, y, act, ST(stream));
+    if (head_supported(x, y, f->kh)) return head_fprop(x, f->hwio, bias, y, act, ST(stream));
+  }
   return conv_simt_fprop(x, f, bias, y, act, 0, false, ST(stream));
 }
 
@@ -133,6 +145,8 @@ int b200_conv2d_dgrad(const b200_tensor* dy, const b200_filter* f, const b200_te
     B200_REQUIRE(tc_ok, B200_ERR_UNSUPPORTED, "conv2d_dgrad: tcgen05 path does not support this shape/dtype");
     return conv_tc_launch(dy, f->hwio, f->cout, f->cin, 1, nullptr, dx, B200_ACT_NONE, accumulate, ST(stream));
   }
+  if (algo == B200_ALGO_AUTO && f->dtype == dx->dtype && f->kh == f->kw && head_supported(dx, dy, f->kh))
+    return head_dgrad(dy, f->hwio, dx, accumulate, ST(stream));
   return conv_simt_fprop(dy, f, nullptr, dx, B200_ACT_NONE, accumulate, true, ST(stream));
 }
 
@@ -152,6 +166,10 @@ int b200_conv2d_wgrad(const b200_tensor* x, const b200_tensor* dy, int kh, int k
   if (algo == B200_ALGO_TCGEN05 || (algo == B200_ALGO_AUTO && tc_ok)) {
     B200_REQUIRE(tc_ok, B200_ERR_UNSUPPORTED, "conv2d_wgrad: tcgen05 path does not support this shape/dtype");
     return wgrad_tc_launch(x, dy, dw, ws, ws_bytes, ST(stream));
+  }
+  if (algo == B200_ALGO_AUTO) {
+    if (stem_supported(x, dy, kh)) return stem_wgrad(x, dy, dw, ST(stream));
+    if (head_supported(x, dy, kh)) return head_wgrad(x, dy, dw, ST(stream));
   }
   return conv_simt_wgrad(x, dy, kh, dw, ST(stream));
 }
@@ -303,6 +321,11 @@ int b200_debug_umma_probe(const void* a, int a_rows, const void* b, int start_by
                           int mn_major, float* out, void* s) {
   B200_REQUIRE(a && b && out, B200_ERR_BAD_ARG, "umma_probe: NULL argument");
   return umma_probe(a, a_rows, b, start_bytes, sbo_bytes, lbo_bytes, mn_major, out, ST(s));
+}
+
+int b200_debug_umma_rate(int n, int iters, int a_stride_bytes, long long* cycles, int grid, void* s) {
+  B200_REQUIRE(cycles && (n == 64 || n == 128 || n == 256) && grid > 0, B200_ERR_BAD_ARG, "umma_rate: bad argument");
+  return umma_rate(n, iters, a_stride_bytes, cycles, grid, ST(s));
 }
 
 }  // extern "C"

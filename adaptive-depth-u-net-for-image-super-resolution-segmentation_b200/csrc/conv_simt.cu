@@ -186,15 +186,24 @@ wgrad_direct_kernel(TView x, TView dy, float* __restrict__ dw, int tiles_w, int 
   }
 }
 
+// [tap][cin][cout] -> [tap][cout][cin], 32x32 tiles through shared memory (coalesced both ways)
 template <typename T>
-__global__ void filter_pack_kernel(const T* __restrict__ hwio, T* __restrict__ ohwi, int taps, int cin, int cout) {
-  long long total = (long long)taps * cin * cout;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    int c = i % cin;
-    int o = (i / cin) % cout;
-    int t = i / ((long long)cin * cout);
-    ohwi[i] = hwio[((long long)t * cin + c) * cout + o];
+__global__ void __launch_bounds__(256)
+filter_pack_kernel(const T* __restrict__ hwio, T* __restrict__ ohwi, int cin, int cout) {
+  __shared__ T tile[32][33];
+  const int t = blockIdx.z;
+  const int c0 = blockIdx.x * 32, o0 = blockIdx.y * 32;
+  const int tx = threadIdx.x % 32, ty = threadIdx.x / 32;   // 32 x 8
+  const T* src = hwio + (long long)t * cin * cout;
+  T* dst = ohwi + (long long)t * cin * cout;
+  for (int r = ty; r < 32; r += 8) {
+    const int c = c0 + r, o = o0 + tx;
+    if (c < cin && o < cout) tile[r][tx] = src[(long long)c * cout + o];
+  }
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {
+    const int o = o0 + r, c = c0 + tx;
+    if (o < cout && c < cin) dst[(long long)o * cin + c] = tile[tx][r];
   }
 }
 
@@ -249,11 +258,9 @@ int conv_simt_wgrad(const b200_tensor* x, const b200_tensor* dy, int ks, float* 
 }
 
 int filter_pack(const void* hwio, void* ohwi, int taps, int cin, int cout, int dtype, cudaStream_t st) {
-  long long total = (long long)taps * cin * cout;
-  int blocks = (int)((total + 255) / 256);
-  if (blocks > 4096) blocks = 4096;
+  dim3 grid((cin + 31) / 32, (cout + 31) / 32, taps);
   B200_DISPATCH_DTYPE(dtype, T, {
-    filter_pack_kernel<T><<<blocks, 256, 0, st>>>(reinterpret_cast<const T*>(hwio), reinterpret_cast<T*>(ohwi), taps, cin, cout);
+    filter_pack_kernel<T><<<grid, 256, 0, st>>>(reinterpret_cast<const T*>(hwio), reinterpret_cast<T*>(ohwi), cin, cout);
   });
   return check_launch("filter_pack_kernel");
 }

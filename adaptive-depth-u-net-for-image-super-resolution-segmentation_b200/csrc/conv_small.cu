@@ -1,0 +1,385 @@
+// Specialised SIMT kernels for the two convolution shapes tensor cores cannot help:
+//   * the RGB stem: 3x3 conv with Cin <= 4 (K = 27), fprop and wgrad   -- FMA/LDS bound
+//   * the 1x1 heads with Cout <= 4 (residual_rgb 64->3, lesion_mask 64->1): fprop, dgrad, wgrad -- HBM bound
+// (the stem needs no dgrad: the network input has no gradient).
+//
+// Replaces keras Conv2D at Super_resolution/code/train_adaptive_unet.py:202 (first call) and :267-274,
+// Segmenation/code/train_adaptive_unet.py:326 (first call) and :361 (reference: /root/reference).
+#include "common.cuh"
+
+namespace b200 {
+namespace {
+
+// ---------------------------------------------------------------------------------------------
+// Stem fprop: tile of 16x16 pixels per block, 256 threads = 128 pixel pairs x 2 halves of 32 couts.
+// Weights [27][64] sit in shared memory and are read as warp-wide broadcasts.
+// ---------------------------------------------------------------------------------------------
+constexpr int ST_T = 16;           // tile edge
+constexpr int ST_IW = ST_T + 2;
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+stem_fprop_kernel(TView x, const T* __restrict__ wgt, const float* __restrict__ bias, TView y, int act, int tiles_w,
+                  int tiles_h) {
+  __shared__ float s_x[3][ST_IW][ST_IW + 1];
+  __shared__ __align__(16) float s_w[27][64];
+  __shared__ float s_b[64];
+  const int tid = threadIdx.x;
+  int bt = blockIdx.x;
+  const int tw = bt % tiles_w; bt /= tiles_w;
+  const int th = bt % tiles_h;
+  const int n = bt / tiles_h;
+  const int h0 = th * ST_T, w0 = tw * ST_T;
+  const int co0 = blockIdx.y * 64;
+  const int Cin = x.c, Cout = y.c;
+  const T* xp = reinterpret_cast<const T*>(x.data);
+
+  for (int i = tid; i < 3 * ST_IW * ST_IW; i += 256) {
+    const int c = i % 3, pix = i / 3;
+    const int r = pix / ST_IW, q = pix % ST_IW;
+    const int ih = h0 + r - 1, iw = w0 + q - 1;
+    float v = 0.f;
+    if (c < Cin && ih >= 0 && ih < x.h && iw >= 0 && iw < x.w) v = ldf(xp + pix_offset(x, n, ih, iw) + c);
+    s_x[c][r][q] = v;
+  }
+  for (int i = tid; i < 27 * 64; i += 256) {
+    const int o = i % 64, k = i / 64;          // k = tap*3 + c
+    const int tap = k / 3, c = k % 3;
+    float v = 0.f;
+    if (c < Cin && co0 + o < Cout) v = ldf(wgt + ((long long)tap * Cin + c) * Cout + co0 + o);
+    s_w[k][o] = v;
+  }
+  if (tid < 64) s_b[tid] = (bias && co0 + tid < Cout) ? bias[co0 + tid] : 0.f;
+  __syncthreads();
+
+  const int half = tid / 128;                  // warp-uniform: which 32 couts
+  const int pp = tid % 128;                    // pixel pair: row pp/8, cols 2*(pp%8), +1
+  const int pr = pp / 8, pc = (pp % 8) * 2;
+  float acc[2][32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) { acc[0][j] = s_b[half * 32 + j]; acc[1][j] = acc[0][j]; }
+#pragma unroll
+  for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+    for (int kw = 0; kw < 3; ++kw)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const float x0 = s_x[c][pr + kh][pc + kw], x1 = s_x[c][pr + kh][pc + kw + 1];
+        const float4* w4 = reinterpret_cast<const float4*>(&s_w[(kh * 3 + kw) * 3 + c][half * 32]);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 w = w4[j];
+          acc[0][4 * j + 0] += x0 * w.x; acc[0][4 * j + 1] += x0 * w.y; acc[0][4 * j + 2] += x0 * w.z; acc[0][4 * j + 3] += x0 * w.w;
+          acc[1][4 * j + 0] += x1 * w.x; acc[1][4 * j + 1] += x1 * w.y; acc[1][4 * j + 2] += x1 * w.z; acc[1][4 * j + 3] += x1 * w.w;
+        }
+      }
+  T* yp = reinterpret_cast<T*>(y.data);
+  const int oh = h0 + pr;
+  if (oh >= y.h) return;
+#pragma unroll
+  for (int p = 0; p < 2; ++p) {
+    const int ow = w0 + pc + p;
+    if (ow >= y.w) continue;
+    T* dst = yp + pix_offset(y, n, oh, ow) + co0 + half * 32;
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      float o[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float v = acc[p][g * 8 + i];
+        o[i] = act == B200_ACT_RELU ? fmaxf(v, 0.f) : v;
+      }
+      if (co0 + half * 32 + g * 8 + 8 <= Cout) Vec8<T>::store(dst + g * 8, o);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Stem wgrad: dW[k = tap*3+c][co] = sum_pixels patch[k] * dz[co].  256 threads = 4 pixel streams x
+// (16 groups of 4 couts) x (4 groups of 7 k); register tile 7 x 4 per thread; per-block reduction in
+// shared memory, then one atomic per output per block.
+// ---------------------------------------------------------------------------------------------
+constexpr int SW_TH = 8, SW_TW = 16;      // 128 pixels per tile
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+stem_wgrad_kernel(TView x, TView dy, float* __restrict__ dw, int tiles_w, int tiles_h, int total_tiles) {
+  __shared__ float s_x[3][SW_TH + 2][SW_TW + 3];
+  __shared__ __align__(16) float s_dz[SW_TH * SW_TW][64];
+  const int tid = threadIdx.x;
+  const int stream = tid / 64;
+  const int cg = tid % 16, kg = (tid % 64) / 16;
+  const int co0 = blockIdx.y * 64;
+  const int Cin = x.c, Cout = dy.c;
+  const T* xp = reinterpret_cast<const T*>(x.data);
+  const T* dp = reinterpret_cast<const T*>(dy.data);
+  float acc[7][4];
+#pragma unroll
+  for (int a = 0; a < 7; ++a)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[a][j] = 0.f;
+  // this thread's (kh, kw, c) triples
+  int t_kh[7], t_kw[7], t_c[7];
+#pragma unroll
+  for (int a = 0; a < 7; ++a) {
+    int k = kg * 7 + a;
+    if (k > 26) k = 26;                   // the 28th slot duplicates k=26 and is dropped at the end
+    t_kh[a] = (k / 3) / 3; t_kw[a] = (k / 3) % 3; t_c[a] = k % 3;
+  }
+  for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    int bt = tile;
+    const int tw = bt % tiles_w; bt /= tiles_w;
+    const int th = bt % tiles_h;
+    const int n = bt / tiles_h;
+    const int h0 = th * SW_TH, w0 = tw * SW_TW;
+    __syncthreads();
+    for (int i = tid; i < 3 * (SW_TH + 2) * (SW_TW + 2); i += 256) {
+      const int c = i % 3, pix = i / 3;
+      const int r = pix / (SW_TW + 2), q = pix % (SW_TW + 2);
+      const int ih = h0 + r - 1, iw = w0 + q - 1;
+      float v = 0.f;
+      if (c < Cin && ih >= 0 && ih < x.h && iw >= 0 && iw < x.w) v = ldf(xp + pix_offset(x, n, ih, iw) + c);
+      s_x[c][r][q] = v;
+    }
+    for (int i = tid; i < SW_TH * SW_TW * 64; i += 256) {
+      const int o = i % 64, pix = i / 64;
+      const int oh = h0 + pix / SW_TW, ow = w0 + pix % SW_TW;
+      float v = 0.f;
+      if (oh < dy.h && ow < dy.w && co0 + o < Cout) v = ldf(dp + pix_offset(dy, n, oh, ow) + co0 + o);
+      s_dz[pix][o] = v;
+    }
+    __syncthreads();
+    for (int p = stream; p < SW_TH * SW_TW; p += 4) {
+      const int pr = p / SW_TW, pc = p % SW_TW;
+      const float4 d = *reinterpret_cast<const float4*>(&s_dz[p][cg * 4]);
+#pragma unroll
+      for (int a = 0; a < 7; ++a) {
+        const float xv = s_x[t_c[a]][pr + t_kh[a]][pc + t_kw[a]];
+        acc[a][0] += xv * d.x; acc[a][1] += xv * d.y; acc[a][2] += xv * d.z; acc[a][3] += xv * d.w;
+      }
+    }
+  }
+  // reduce the 4 streams through shared memory (reuse s_dz as [27][64] accumulator)
+  __syncthreads();
+  float* red = &s_dz[0][0];
+  for (int i = tid; i < 27 * 64; i += 256) red[i] = 0.f;
+  __syncthreads();
+#pragma unroll
+  for (int a = 0; a < 7; ++a) {
+    const int k = kg * 7 + a;
+    if (k <= 26) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) atomicAdd(&red[k * 64 + cg * 4 + j], acc[a][j]);
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < 27 * 64; i += 256) {
+    const int o = i % 64, k = i / 64;
+    const int tap = k / 3, c = k % 3;
+    if (c < Cin && co0 + o < Cout) atomicAdd(dw + ((long long)tap * Cin + c) * Cout + co0 + o, red[i]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// 1x1 heads with COUT <= 4: one thread per pixel (fprop, dgrad), 8 threads per pixel (wgrad).
+// ---------------------------------------------------------------------------------------------
+template <typename T, int COUT>
+__global__ void __launch_bounds__(256)
+head_fprop_kernel(TView x, const T* __restrict__ wgt, const float* __restrict__ bias, TView y, int act, long long npix) {
+  extern __shared__ float s_w[];   // [Cin][COUT]
+  const int Cin = x.c;
+  for (int i = threadIdx.x; i < Cin * COUT; i += 256) s_w[i] = ldf(wgt + i);
+  __syncthreads();
+  const T* xp = reinterpret_cast<const T*>(x.data);
+  T* yp = reinterpret_cast<T*>(y.data);
+  for (long long p = (long long)blockIdx.x * 256 + threadIdx.x; p < npix; p += (long long)gridDim.x * 256) {
+    const int w = (int)(p % x.w);
+    const long long q = p / x.w;
+    const int h = (int)(q % x.h), n = (int)(q / x.h);
+    const T* src = xp + pix_offset(x, n, h, w);
+    float acc[COUT];
+#pragma unroll
+    for (int o = 0; o < COUT; ++o) acc[o] = bias ? bias[o] : 0.f;
+    for (int c0 = 0; c0 < Cin; c0 += 8) {
+      float v[8];
+      Vec8<T>::load(src + c0, v);
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int o = 0; o < COUT; ++o) acc[o] += v[i] * s_w[(c0 + i) * COUT + o];
+    }
+    T* dst = yp + pix_offset(y, n, h, w);
+#pragma unroll
+    for (int o = 0; o < COUT; ++o) {
+      float v = acc[o];
+      if (act == B200_ACT_RELU) v = fmaxf(v, 0.f);
+      else if (act == B200_ACT_SIGMOID) v = 1.f / (1.f + __expf(-v));
+      stf(dst + o, v);
+    }
+  }
+}
+
+// dx[c] (+)= sum_o dz[o] * W[c][o]
+template <typename T, int COUT>
+__global__ void __launch_bounds__(256)
+head_dgrad_kernel(TView dy, const T* __restrict__ wgt, TView dx, int accumulate, long long npix) {
+  extern __shared__ float s_w[];
+  const int Cin = dx.c;
+  for (int i = threadIdx.x; i < Cin * COUT; i += 256) s_w[i] = ldf(wgt + i);
+  __syncthreads();
+  const T* dp = reinterpret_cast<const T*>(dy.data);
+  T* xp = reinterpret_cast<T*>(dx.data);
+  for (long long p = (long long)blockIdx.x * 256 + threadIdx.x; p < npix; p += (long long)gridDim.x * 256) {
+    const int w = (int)(p % dx.w);
+    const long long q = p / dx.w;
+    const int h = (int)(q % dx.h), n = (int)(q / dx.h);
+    const T* src = dp + pix_offset(dy, n, h, w);
+    float d[COUT];
+#pragma unroll
+    for (int o = 0; o < COUT; ++o) d[o] = ldf(src + o);
+    T* dst = xp + pix_offset(dx, n, h, w);
+    for (int c0 = 0; c0 < Cin; c0 += 8) {
+      float v[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float a = 0.f;
+#pragma unroll
+        for (int o = 0; o < COUT; ++o) a += d[o] * s_w[(c0 + i) * COUT + o];
+        v[i] = a;
+      }
+      if (accumulate) {
+        float e[8];
+        Vec8<T>::load(dst + c0, e);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] += e[i];
+      }
+      Vec8<T>::store(dst + c0, v);
+    }
+  }
+}
+
+// dW[c][o] = sum_pixels x[c] * dz[o]; chunks = Cin/8 threads per pixel (power of two <= 32)
+template <typename T, int COUT>
+__global__ void __launch_bounds__(256)
+head_wgrad_kernel(TView x, TView dy, float* __restrict__ dw, long long npix) {
+  extern __shared__ float s_acc[];   // [Cin][COUT]
+  const int Cin = x.c, chunks = Cin / 8;
+  for (int i = threadIdx.x; i < Cin * COUT; i += 256) s_acc[i] = 0.f;
+  __syncthreads();
+  const int j = threadIdx.x % chunks, ppb = 256 / chunks;
+  const T* xp = reinterpret_cast<const T*>(x.data);
+  const T* dp = reinterpret_cast<const T*>(dy.data);
+  float acc[8][COUT];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int o = 0; o < COUT; ++o) acc[i][o] = 0.f;
+  for (long long p = (long long)blockIdx.x * ppb + threadIdx.x / chunks; p < npix; p += (long long)gridDim.x * ppb) {
+    const int w = (int)(p % x.w);
+    const long long q = p / x.w;
+    const int h = (int)(q % x.h), n = (int)(q / x.h);
+    float v[8], d[COUT];
+    Vec8<T>::load(xp + pix_offset(x, n, h, w) + j * 8, v);
+    const T* src = dp + pix_offset(dy, n, h, w);
+#pragma unroll
+    for (int o = 0; o < COUT; ++o) d[o] = ldf(src + o);
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int o = 0; o < COUT; ++o) acc[i][o] += v[i] * d[o];
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int o = 0; o < COUT; ++o) atomicAdd(&s_acc[(j * 8 + i) * COUT + o], acc[i][o]);
+  __syncthreads();
+  for (int i = threadIdx.x; i < Cin * COUT; i += 256) atomicAdd(dw + i, s_acc[i]);
+}
+
+inline bool pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
+
+}  // namespace
+
+// ---- dispatch helpers ---------------------------------------------------------------------------
+bool stem_supported(const b200_tensor* x, const b200_tensor* y, int ks) {
+  return ks == 3 && x->c <= 3 && y->c % 8 == 0 && vec_aligned(y, 8) && x->dtype == y->dtype;
+}
+
+int stem_fprop(const b200_tensor* x, const void* wgt, const float* bias, const b200_tensor* y, int act, cudaStream_t st) {
+  const int tiles_w = (y->w + ST_T - 1) / ST_T, tiles_h = (y->h + ST_T - 1) / ST_T;
+  dim3 grid(tiles_w * tiles_h * y->n, (y->c + 63) / 64);
+  TView xv = view_of(x), yv = view_of(y);
+  B200_DISPATCH_DTYPE(x->dtype, T, {
+    stem_fprop_kernel<T><<<grid, 256, 0, st>>>(xv, reinterpret_cast<const T*>(wgt), bias, yv, act, tiles_w, tiles_h);
+  });
+  return check_launch("stem_fprop_kernel");
+}
+
+int stem_wgrad(const b200_tensor* x, const b200_tensor* dy, float* dw, cudaStream_t st) {
+  const int tiles_w = (dy->w + SW_TW - 1) / SW_TW, tiles_h = (dy->h + SW_TH - 1) / SW_TH;
+  const int total = tiles_w * tiles_h * dy->n;
+  int gx = 2 * sm_count();
+  if (gx > total) gx = total;
+  cudaMemsetAsync(dw, 0, sizeof(float) * 9 * x->c * dy->c, st);
+  dim3 grid(gx, (dy->c + 63) / 64);
+  TView xv = view_of(x), dv = view_of(dy);
+  B200_DISPATCH_DTYPE(x->dtype, T, { stem_wgrad_kernel<T><<<grid, 256, 0, st>>>(xv, dv, dw, tiles_w, tiles_h, total); });
+  return check_launch("stem_wgrad_kernel");
+}
+
+bool head_supported(const b200_tensor* x, const b200_tensor* y, int ks) {
+  return ks == 1 && (y->c == 1 || y->c == 3) && x->c % 8 == 0 && pow2(x->c / 8) && x->c / 8 <= 32 && vec_aligned(x, 8) &&
+         x->dtype == y->dtype;
+}
+
+#define B200_HEAD_DISPATCH(cout, ...)            \
+  do {                                           \
+    if ((cout) == 1) { constexpr int COUT = 1; __VA_ARGS__ } \
+    else { constexpr int COUT = 3; __VA_ARGS__ }  \
+  } while (0)
+
+static int head_grid(long long npix, int per_block) {
+  long long b = (npix + per_block - 1) / per_block;
+  long long cap = 8LL * sm_count();
+  return (int)(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+int head_fprop(const b200_tensor* x, const void* wgt, const float* bias, const b200_tensor* y, int act, cudaStream_t st) {
+  const long long npix = (long long)x->n * x->h * x->w;
+  TView xv = view_of(x), yv = view_of(y);
+  const size_t smem = sizeof(float) * x->c * y->c;
+  B200_DISPATCH_DTYPE(x->dtype, T, {
+    B200_HEAD_DISPATCH(y->c, {
+      head_fprop_kernel<T, COUT><<<head_grid(npix, 256), 256, smem, st>>>(xv, reinterpret_cast<const T*>(wgt), bias, yv, act, npix);
+    });
+  });
+  return check_launch("head_fprop_kernel");
+}
+
+int head_dgrad(const b200_tensor* dy, const void* wgt, const b200_tensor* dx, int accumulate, cudaStream_t st) {
+  const long long npix = (long long)dx->n * dx->h * dx->w;
+  TView dv = view_of(dy), xv = view_of(dx);
+  const size_t smem = sizeof(float) * dx->c * dy->c;
+  B200_DISPATCH_DTYPE(dx->dtype, T, {
+    B200_HEAD_DISPATCH(dy->c, {
+      head_dgrad_kernel<T, COUT><<<head_grid(npix, 256), 256, smem, st>>>(dv, reinterpret_cast<const T*>(wgt), xv, accumulate, npix);
+    });
+  });
+  return check_launch("head_dgrad_kernel");
+}
+
+int head_wgrad(const b200_tensor* x, const b200_tensor* dy, float* dw, cudaStream_t st) {
+  const long long npix = (long long)x->n * x->h * x->w;
+  TView xv = view_of(x), dv = view_of(dy);
+  const size_t smem = sizeof(float) * x->c * dy->c;
+  cudaMemsetAsync(dw, 0, smem, st);
+  const int ppb = 256 / (x->c / 8);
+  long long blocks = (npix + ppb - 1) / ppb;
+  if (blocks > 2LL * sm_count()) blocks = 2LL * sm_count();
+  B200_DISPATCH_DTYPE(x->dtype, T, {
+    B200_HEAD_DISPATCH(dy->c, { head_wgrad_kernel<T, COUT><<<(int)blocks, 256, smem, st>>>(xv, dv, dw, npix); });
+  });
+  return check_launch("head_wgrad_kernel");
+}
+
+}  // namespace b200

@@ -48,13 +48,13 @@ static EncodeTiledFn encode_fn() {
   return fn;
 }
 
-// NHWC bf16 activation view -> 4D map {C, W, H, N}, box {64, bw, bh, 1}, 128B swizzle, zero OOB fill
-int make_act_tmap(CUtensorMap* m, const b200_tensor* t, int box_w, int box_h) {
+// NHWC bf16 activation view -> 4D map {C, W, H, N}, box {64, bw, bh, bn}, 128B swizzle, zero OOB fill
+int make_act_tmap(CUtensorMap* m, const b200_tensor* t, int box_w, int box_h, int box_n) {
   EncodeTiledFn fn = encode_fn();
   B200_REQUIRE(fn, B200_ERR_LAUNCH, "cuTensorMapEncodeTiled unavailable");
   cuuint64_t dims[4] = {(cuuint64_t)t->c, (cuuint64_t)t->w, (cuuint64_t)t->h, (cuuint64_t)t->n};
   cuuint64_t strides[3] = {(cuuint64_t)t->stride_w * 2, (cuuint64_t)t->stride_h * 2, (cuuint64_t)t->stride_n * 2};
-  cuuint32_t box[4] = {64, (cuuint32_t)box_w, (cuuint32_t)box_h, 1};
+  cuuint32_t box[4] = {64, (cuuint32_t)box_w, (cuuint32_t)box_h, (cuuint32_t)box_n};
   cuuint32_t es[4] = {1, 1, 1, 1};
   CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, t->data, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -91,10 +91,32 @@ constexpr int SMEM_LIMIT = 232448;                // 227 KB
 struct ConvTcParams {
   int N, H, W, Cout, KB, BN, n_tiles, tiles_h, tiles_w, total_items;
   int tap_rev, live_mask, resident, nsw, nsb, act, accumulate;
+  // small images (H <= 7) are stacked: one tile holds `nb` images, each `srows` = H+2 window rows
+  int nb, srows, win_bytes;
   const float* bias;
   __nv_bfloat16* y;
   long long ysn, ysh, ysw;
 };
+
+// D[tmem] (+)= A * B^T with the descriptors given as (lo, hi) words: the hi words are loop
+// invariants and the lo words advance by plain 32-bit adds in the single issuing thread.
+__device__ __forceinline__ void umma_lohi(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                          uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 p, %6, 0;\n\t"
+      "mov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %4};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}\n"
+      ::"r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+__device__ __forceinline__ void decode_item(const ConvTcParams& p, int item, int& j, int& tw, int& th, int& n) {
+  j = item % p.n_tiles;
+  int t = item / p.n_tiles;
+  tw = t % p.tiles_w; t /= p.tiles_w;
+  th = t % p.tiles_h;
+  n = (t / p.tiles_h) * p.nb;     // first image of the tile
+}
 
 __global__ void __launch_bounds__(NTHREADS, 1)
 conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_b,
@@ -111,6 +133,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
   const uint32_t wt0 = smem0 + (uint32_t)p.nsw * WIN_STAGE;
   const uint32_t wt_bytes = (uint32_t)p.BN * 128u;
   const uint32_t tmem_cols = 2u * (uint32_t)p.BN;
+  float* s_bias = reinterpret_cast<float*>(smem_raw + (wt0 - smem_u32(smem_raw)) + (size_t)p.nsb * wt_bytes);
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < p.nsw; ++i) { mbar_init(smem_u32(&bar_full_w[i]), 1); mbar_init(smem_u32(&bar_empty_w[i]), 1); }
@@ -118,6 +141,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
     for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&bar_tmem_full[i]), 1); mbar_init(smem_u32(&bar_tmem_empty[i]), 4); }
     fence_barrier_init();
   }
+  for (int i = threadIdx.x; i < p.Cout; i += NTHREADS) s_bias[i] = p.bias ? p.bias[i] : 0.f;
   if (warp == 0 && lane == 0) { prefetch_tmap(&tm_x); prefetch_tmap(&tm_b); }
   if (warp == 1) { tmem_alloc(smem_u32(&tmem_base_smem), tmem_cols); tmem_relinquish(); }
   tc_fence_before();
@@ -140,14 +164,11 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
           }
       }
       for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
-        const int j = item % p.n_tiles;
-        int t = item / p.n_tiles;
-        const int tw = t % p.tiles_w; t /= p.tiles_w;
-        const int th = t % p.tiles_h;
-        const int n = t / p.tiles_h;
+        int j, tw, th, n;
+        decode_item(p, item, j, tw, th, n);
         for (int kb = 0; kb < p.KB; ++kb) {
           mbar_wait(smem_u32(&bar_empty_w[sw]), pw ^ 1);
-          mbar_arrive_expect_tx(smem_u32(&bar_full_w[sw]), WIN_BYTES);
+          mbar_arrive_expect_tx(smem_u32(&bar_full_w[sw]), (uint32_t)p.win_bytes);
           tma_load_4d(win0 + sw * WIN_STAGE, &tm_x, smem_u32(&bar_full_w[sw]), kb * 64, tw * TILE_W - 1,
                       th * TILE_H - 1, n);
           if (++sw == p.nsw) { sw = 0; pw ^= 1; }
@@ -169,8 +190,17 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
     // ============================ MMA issuer ==============================
     if (lane == 0) {
       const uint32_t idesc = idesc_bf16(128, p.BN, 0, 0);
+      const uint32_t a_hi = (uint32_t)(smem_desc_sw128(0, 0, WIN_PITCH) >> 32);
+      const uint32_t b_hi = (uint32_t)(smem_desc_sw128(0, 0, 1024) >> 32);
+      const uint32_t wt_step = wt_bytes >> 4;
+      const bool all_live = p.live_mask == 0x1FF;
       int sw = 0, pw = 0, sb = 0, pb = 0, as = 0, pa = 0;
-      bool first_item = true;
+      if (p.resident) {   // the weights are loaded once: wait for every tile up front
+        for (int kb = 0; kb < p.KB; ++kb)
+          for (int tap = 0; tap < 9; ++tap)
+            if ((p.live_mask >> tap) & 1) mbar_wait(smem_u32(&bar_full_b[kb * 9 + tap]), 0);
+        tc_fence_after();
+      }
       for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
         mbar_wait(smem_u32(&bar_tmem_empty[as]), pa ^ 1);
         tc_fence_after();
@@ -179,29 +209,42 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
         for (int kb = 0; kb < p.KB; ++kb) {
           mbar_wait(smem_u32(&bar_full_w[sw]), pw);
           tc_fence_after();
-          const uint32_t win = win0 + sw * WIN_STAGE;
-          for (int tap = 0; tap < 9; ++tap) {
-            if (!((p.live_mask >> tap) & 1)) continue;
-            uint32_t wt;
-            if (p.resident) {
-              const int slot = kb * 9 + tap;
-              if (first_item) { mbar_wait(smem_u32(&bar_full_b[slot]), 0); tc_fence_after(); }
-              wt = wt0 + slot * wt_bytes;
-            } else {
-              mbar_wait(smem_u32(&bar_full_b[sb]), pb);
-              tc_fence_after();
-              wt = wt0 + sb * wt_bytes;
-            }
-            const uint32_t a_addr = win + (uint32_t)((tap / 3) * WIN_W + (tap % 3)) * 128u;
+          const uint32_t a_lo0 = (win0 + sw * WIN_STAGE) >> 4;
+          if (p.resident && all_live) {
+            // hot path of the full-resolution layers: 36 MMAs, descriptor words by 32-bit adds only
+            const uint32_t b_lo0 = (wt0 >> 4) + (uint32_t)(kb * 9) * wt_step;
 #pragma unroll
-            for (int ks = 0; ks < 4; ++ks) {
-              umma_bf16(d_tmem, smem_desc_sw128(a_addr + ks * 32, 0, WIN_PITCH), smem_desc_sw128(wt + ks * 32, 0, 1024),
-                        idesc, accumulate);
-              accumulate = 1;
+            for (int tap = 0; tap < 9; ++tap) {
+              const uint32_t a_lo = a_lo0 + (uint32_t)((tap / 3) * WIN_W + (tap % 3)) * 8u;
+              const uint32_t b_lo = b_lo0 + (uint32_t)tap * wt_step;
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks) {
+                umma_lohi(d_tmem, a_lo + ks * 2, a_hi, b_lo + ks * 2, b_hi, idesc, accumulate);
+                accumulate = 1;
+              }
             }
-            if (!p.resident) {
-              umma_commit(smem_u32(&bar_empty_b[sb]));
-              if (++sb == p.nsb) { sb = 0; pb ^= 1; }
+          } else {
+#pragma unroll 1
+            for (int tap = 0; tap < 9; ++tap) {
+              if (!((p.live_mask >> tap) & 1)) continue;
+              uint32_t b_lo;
+              if (p.resident) {
+                b_lo = (wt0 >> 4) + (uint32_t)(kb * 9 + tap) * wt_step;
+              } else {
+                mbar_wait(smem_u32(&bar_full_b[sb]), pb);
+                tc_fence_after();
+                b_lo = (wt0 >> 4) + (uint32_t)sb * wt_step;
+              }
+              const uint32_t a_lo = a_lo0 + (uint32_t)((tap / 3) * WIN_W + (tap % 3)) * 8u;
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks) {
+                umma_lohi(d_tmem, a_lo + ks * 2, a_hi, b_lo + ks * 2, b_hi, idesc, accumulate);
+                accumulate = 1;
+              }
+              if (!p.resident) {
+                umma_commit(smem_u32(&bar_empty_b[sb]));
+                if (++sb == p.nsb) { sb = 0; pb ^= 1; }
+              }
             }
           }
           umma_commit(smem_u32(&bar_empty_w[sw]));
@@ -209,7 +252,6 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
         }
         umma_commit(smem_u32(&bar_tmem_full[as]));
         if (++as == 2) { as = 0; pa ^= 1; }
-        first_item = false;
       }
     }
     __syncwarp();
@@ -218,16 +260,16 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
     const int q = warp % 4;                 // TMEM lane quarter this warp may read
     const int r = q * 32 + lane;            // GEMM row = pixel of the tile
     const int ty = r / TILE_W, tx = r % TILE_W;
+    const int sb_img = ty / p.srows, sb_row = ty % p.srows;   // stacked small images (srows huge otherwise)
     int as = 0, pa = 0;
     for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
-      const int j = item % p.n_tiles;
-      int t = item / p.n_tiles;
-      const int tw = t % p.tiles_w; t /= p.tiles_w;
-      const int th = t % p.tiles_h;
-      const int n = t / p.tiles_h;
-      const int oh = th * TILE_H + ty, ow = tw * TILE_W + tx;
-      const bool valid = oh < p.H && ow < p.W;
-      __nv_bfloat16* dst = p.y + (long long)n * p.ysn + (long long)oh * p.ysh + (long long)ow * p.ysw + j * p.BN;
+      int j, tw, th, n;
+      decode_item(p, item, j, tw, th, n);
+      const int oh = th * TILE_H + sb_row, ow = tw * TILE_W + tx;
+      const int img = n + sb_img;
+      const bool valid = oh < p.H && ow < p.W && sb_img < p.nb && img < p.N;
+      __nv_bfloat16* dst = p.y + (long long)img * p.ysn + (long long)oh * p.ysh + (long long)ow * p.ysw + j * p.BN;
+      const float* bias = s_bias + j * p.BN;
       mbar_wait(smem_u32(&bar_tmem_full[as]), pa);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * p.BN);
@@ -238,13 +280,15 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
         if (valid) {
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
-            float o[8];
+            const float4 b0 = *reinterpret_cast<const float4*>(bias + c0 + g * 8);
+            const float4 b1 = *reinterpret_cast<const float4*>(bias + c0 + g * 8 + 4);
+            float o[8] = {__uint_as_float(v[g * 8 + 0]) + b0.x, __uint_as_float(v[g * 8 + 1]) + b0.y,
+                          __uint_as_float(v[g * 8 + 2]) + b0.z, __uint_as_float(v[g * 8 + 3]) + b0.w,
+                          __uint_as_float(v[g * 8 + 4]) + b1.x, __uint_as_float(v[g * 8 + 5]) + b1.y,
+                          __uint_as_float(v[g * 8 + 6]) + b1.z, __uint_as_float(v[g * 8 + 7]) + b1.w};
+            if (p.act == B200_ACT_RELU) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              float f = __uint_as_float(v[g * 8 + i]);
-              if (p.bias) f += __ldg(p.bias + j * p.BN + c0 + g * 8 + i);
-              if (p.act == B200_ACT_RELU) f = fmaxf(f, 0.f);
-              o[i] = f;
+              for (int i = 0; i < 8; ++i) o[i] = fmaxf(o[i], 0.f);
             }
             __nv_bfloat16* d8 = dst + c0 + g * 8;
             if (p.accumulate) {
@@ -326,6 +370,47 @@ umma_probe_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
   if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem_base, 64); }
 }
 
+// ---------------------------------------------------------------------------
+// MMA issue-rate probe: every CTA issues `iters` x 4 tcgen05.mma (M=128, N=n, K=16 each) on fixed
+// shared-memory operands and reports the cycles one thread saw from first issue to completion.
+// Used to find the real tensor-pipe ceiling of the SS-mode (both operands in smem) N=64/128/256 shapes.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(128, 1)
+umma_rate_kernel(int n, int iters, int a_stride_bytes, long long* __restrict__ cycles) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bar_mma;
+  __shared__ uint32_t tmem_base_smem;
+  const int warp = threadIdx.x / 32;
+  const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t a_smem = smem0, b_smem = smem0 + 32768;
+  for (int i = threadIdx.x; i < (32768 + 32768) / 4; i += blockDim.x)
+    reinterpret_cast<uint32_t*>(smem_raw + (smem0 - smem_u32(smem_raw)))[i] = 0x3c003c00u;  // bf16 ~0.0078
+  fence_proxy_async();
+  if (threadIdx.x == 0) { mbar_init(smem_u32(&bar_mma), 1); fence_barrier_init(); }
+  if (warp == 0) { tmem_alloc(smem_u32(&tmem_base_smem), 512); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+  if (threadIdx.x == 0) {
+    const uint32_t idesc = idesc_bf16(128, n, 0, 0);
+    const long long t0 = clock64();
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks)
+        umma_bf16(tmem_base + (uint32_t)((it & 1) * n), smem_desc_sw128(a_smem + ks * 32, 0, a_stride_bytes),
+                  smem_desc_sw128(b_smem + ks * 32, 0, 1024), idesc, 1);
+    }
+    umma_commit(smem_u32(&bar_mma));
+    mbar_wait(smem_u32(&bar_mma), 0);
+    cycles[blockIdx.x] = clock64() - t0;
+  }
+  __syncthreads();
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+}
+
 }  // namespace
 
 bool conv_tc_supported(const b200_tensor* x, int cin, int cout, const b200_tensor* y, int ks) {
@@ -340,14 +425,34 @@ bool conv_tc_supported(const b200_tensor* x, int cin, int cout, const b200_tenso
   return ok(x) && ok(y);
 }
 
+// Images of 1x1 pixels only ever use the centre tap, so the batch can be laid out as the pixels of
+// one image: [N,1,1,C] -> [1, N/8, 8, C] (or [1,1,N,C]); 128 images then share one MMA tile.
+static bool flatten_1x1(const b200_tensor* t, b200_tensor* out) {
+  if (t->h != 1 || t->w != 1) return false;
+  *out = *t;
+  out->n = 1;
+  if (t->n % 8 == 0) { out->h = t->n / 8; out->w = 8; out->stride_w = t->stride_n; out->stride_h = 8 * t->stride_n; }
+  else { out->h = 1; out->w = t->n; out->stride_w = t->stride_n; out->stride_h = t->stride_n * t->n; }
+  out->stride_n = t->stride_n * t->n;
+  return true;
+}
+
 // x: input activations (C = K total), wmat: [9][cout][cin] K-major bf16, y: output (C = cout)
-int conv_tc_launch(const b200_tensor* x, const void* wmat, int cin, int cout, int tap_rev, const float* bias,
-                   const b200_tensor* y, int act, int accumulate, cudaStream_t st) {
-  B200_REQUIRE(conv_tc_supported(x, cin, cout, y, 3), B200_ERR_UNSUPPORTED,
+int conv_tc_launch(const b200_tensor* x_in, const void* wmat, int cin, int cout, int tap_rev, const float* bias,
+                   const b200_tensor* y_in, int act, int accumulate, cudaStream_t st) {
+  B200_REQUIRE(conv_tc_supported(x_in, cin, cout, y_in, 3), B200_ERR_UNSUPPORTED,
                "conv3x3 tcgen05: unsupported shape cin=%d cout=%d (need bf16, multiples of 64, 16-byte aligned)", cin,
                cout);
-  B200_REQUIRE(x->n == y->n && x->h == y->h && x->w == y->w && x->c == cin && y->c == cout, B200_ERR_BAD_ARG,
-               "conv3x3 tcgen05: tensor shapes do not match the filter");
+  B200_REQUIRE(x_in->n == y_in->n && x_in->h == y_in->h && x_in->w == y_in->w && x_in->c == cin && y_in->c == cout,
+               B200_ERR_BAD_ARG, "conv3x3 tcgen05: tensor shapes do not match the filter");
+  b200_tensor xf, yf;
+  const b200_tensor *x = x_in, *y = y_in;
+  int live_mask = 0;
+  for (int t = 0; t < 9; ++t) {
+    const bool dead = (x_in->h == 1 && t / 3 != 1) || (x_in->w == 1 && t % 3 != 1);
+    if (!dead) live_mask |= 1 << t;
+  }
+  if (flatten_1x1(x_in, &xf) && flatten_1x1(y_in, &yf)) { x = &xf; y = &yf; }   // live_mask stays centre-only
   ConvTcParams p;
   p.N = y->n; p.H = y->h; p.W = y->w; p.Cout = cout;
   p.KB = cin / 64;
@@ -355,15 +460,24 @@ int conv_tc_launch(const b200_tensor* x, const void* wmat, int cin, int cout, in
   p.n_tiles = cout / p.BN;
   p.tiles_h = (p.H + TILE_H - 1) / TILE_H;
   p.tiles_w = (p.W + TILE_W - 1) / TILE_W;
-  p.total_items = p.N * p.tiles_h * p.tiles_w * p.n_tiles;
-  p.tap_rev = tap_rev;
-  p.live_mask = 0;
-  for (int t = 0; t < 9; ++t) {
-    const bool dead = (p.H == 1 && t / 3 != 1) || (p.W == 1 && t % 3 != 1);
-    if (!dead) p.live_mask |= 1 << t;
+  // stack several small images in one tile: image b occupies window rows [b*(H+2), (b+1)*(H+2))
+  p.nb = 1; p.srows = 1 << 20;
+  int box_h = WIN_H, box_n = 1;
+  if (p.H + 2 <= 9 && p.N > 1) {
+    p.srows = p.H + 2;
+    p.nb = WIN_H / p.srows;
+    while ((p.nb - 1) * p.srows + p.H - 1 > TILE_H - 1) --p.nb;
+    if (p.nb > p.N) p.nb = p.N;
+    box_h = p.srows; box_n = p.nb;
   }
+  p.win_bytes = WIN_W * box_h * box_n * 128;
+  const int groups = (p.N + p.nb - 1) / p.nb;
+  p.total_items = groups * p.tiles_h * p.tiles_w * p.n_tiles;
+  p.tap_rev = tap_rev;
+  p.live_mask = live_mask;
   const int wt_bytes = p.BN * 128;
-  const int budget = SMEM_LIMIT - 1024 /*align slack*/ - 1024 /*static*/;
+  const int bias_bytes = ((cout * 4 + 1023) / 1024) * 1024;
+  const int budget = SMEM_LIMIT - 1024 /*align slack*/ - 1024 /*static*/ - bias_bytes;
   const int all_w = 9 * p.KB * wt_bytes;
   p.resident = (p.n_tiles == 1 && 9 * p.KB <= MAX_WSLOTS && budget - all_w >= 2 * WIN_STAGE) ? 1 : 0;
   if (p.resident) {
@@ -380,12 +494,12 @@ int conv_tc_launch(const b200_tensor* x, const void* wmat, int cin, int cout, in
   p.ysn = y->stride_n; p.ysh = y->stride_h; p.ysw = y->stride_w;
 
   CUtensorMap tm_x, tm_b;
-  int rc = make_act_tmap(&tm_x, x, WIN_W, WIN_H);
+  int rc = make_act_tmap(&tm_x, x, WIN_W, box_h, box_n);
   if (rc) return rc;
   rc = make_mat_tmap(&tm_b, wmat, 9LL * cout, cin, p.BN);
   if (rc) return rc;
 
-  const size_t smem = 1024 + (size_t)p.nsw * WIN_STAGE + (size_t)p.nsb * wt_bytes;
+  const size_t smem = 1024 + (size_t)p.nsw * WIN_STAGE + (size_t)p.nsb * wt_bytes + bias_bytes;
   static bool attr_set = false;
   if (!attr_set) {
     cudaFuncSetAttribute(conv3x3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT - 1024);
@@ -411,4 +525,13 @@ int umma_probe(const void* a, int a_rows, const void* b, int start_bytes, int sb
   return check_launch("umma_probe_kernel");
 }
 
+}  // namespace b200
+
+namespace b200 {
+int umma_rate(int n, int iters, int a_stride_bytes, long long* cycles, int grid, cudaStream_t st) {
+  const size_t smem = 1024 + 65536;
+  cudaFuncSetAttribute(umma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  umma_rate_kernel<<<grid, 128, smem, st>>>(n, iters, a_stride_bytes, cycles);
+  return check_launch("umma_rate_kernel");
+}
 }  // namespace b200

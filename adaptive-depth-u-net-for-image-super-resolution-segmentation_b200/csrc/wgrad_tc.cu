@@ -24,7 +24,7 @@ namespace b200 {
 
 using namespace ptx;
 
-int make_act_tmap(CUtensorMap* m, const b200_tensor* t, int box_w, int box_h);
+int make_act_tmap(CUtensorMap* m, const b200_tensor* t, int box_w, int box_h, int box_n);
 
 namespace {
 
@@ -41,8 +41,19 @@ constexpr int NPAIRS = 5;
 struct WgradParams {
   int N, H, W, Cin, Cout;
   int tiles_h, tiles_w, total_tiles, splits, cblocks, oblocks;
+  int nb, ksteps, stage_bytes, zero_smem;   // stacked small images: nb images per tile, ksteps 16-pixel K steps
   float* partial;  // [splits][9][Cin][Cout]
 };
+
+__device__ __forceinline__ void umma_lohi(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                          uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 p, %6, 0;\n\t"
+      "mov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %4};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}\n"
+      ::"r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 
 // first tap of each pair, and the distance (in window pixel rows) to the second tap
 __device__ __forceinline__ int pair_first(int pi) { return pi < 4 ? 2 * pi : 7; }
@@ -66,6 +77,12 @@ wgrad3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
   const int t_begin = (int)((long long)p.total_tiles * s / p.splits);
   const int t_end = (int)((long long)p.total_tiles * (s + 1) / p.splits);
 
+  if (p.zero_smem) {
+    // stacked tiles leave K rows past the TMA boxes untouched: make them exact zeros once
+    uint4* z = reinterpret_cast<uint4*>(smem_raw + (smem0 - smem_u32(smem_raw)));
+    for (int i = threadIdx.x; i < NSTAGES * STAGE / 16; i += NTHREADS) z[i] = make_uint4(0, 0, 0, 0);
+    fence_proxy_async();
+  }
   if (threadIdx.x == 0) {
     for (int i = 0; i < NSTAGES; ++i) { mbar_init(smem_u32(&bar_full[i]), 1); mbar_init(smem_u32(&bar_empty[i]), 1); }
     mbar_init(smem_u32(&bar_done), 1);
@@ -85,10 +102,10 @@ wgrad3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
         int q = t;
         const int tw = q % p.tiles_w; q /= p.tiles_w;
         const int th = q % p.tiles_h;
-        const int n = q / p.tiles_h;
+        const int n = (q / p.tiles_h) * p.nb;
         mbar_wait(smem_u32(&bar_empty[st]), ph ^ 1);
         const uint32_t base = smem0 + st * STAGE;
-        mbar_arrive_expect_tx(smem_u32(&bar_full[st]), WIN_BYTES + DZ_BYTES);
+        mbar_arrive_expect_tx(smem_u32(&bar_full[st]), (uint32_t)p.stage_bytes);
         tma_load_4d(base, &tm_x, smem_u32(&bar_full[st]), cb * 64, tw * TILE_W - 1, th * TILE_H - 1, n);
         tma_load_4d(base + WIN_STAGE, &tm_dz, smem_u32(&bar_full[st]), ob * 64, tw * TILE_W, th * TILE_H, n);
         if (++st == NSTAGES) { st = 0; ph ^= 1; }
@@ -98,23 +115,30 @@ wgrad3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
   } else if (warp == 1) {
     if (lane == 0) {
       const uint32_t idesc = idesc_bf16(128, 64, 1, 1);
+      const uint32_t b_hi = (uint32_t)(smem_desc_sw128(0, 0, 1024) >> 32);
+      // A descriptor hi word is shared (SBO = window pitch); the lo word carries LBO = distance
+      // between the two taps of the pair
+      const uint32_t a_hi = (uint32_t)(smem_desc_sw128(0, 0, WIN_W * 128) >> 32);
+      uint32_t a_off[NPAIRS];
+#pragma unroll
+      for (int pi = 0; pi < NPAIRS; ++pi) {
+        const int t0 = pair_first(pi);
+        const uint32_t lbo = (uint32_t)(tap_row(t0 + 1) - tap_row(t0)) * 128u;
+        a_off[pi] = ((uint32_t)tap_row(t0) * 128u >> 4) | ((lbo >> 4) << 16);
+      }
       int st = 0, ph = 0;
       for (int t = t_begin; t < t_end; ++t) {
         mbar_wait(smem_u32(&bar_full[st]), ph);
         tc_fence_after();
-        const uint32_t win = smem0 + st * STAGE;
-        const uint32_t dz = win + WIN_STAGE;
+        const uint32_t win_lo = (smem0 + st * STAGE) >> 4;
+        const uint32_t dz_lo = win_lo + (WIN_STAGE >> 4);
 #pragma unroll 1
-        for (int ks = 0; ks < 8; ++ks) {
-          const uint64_t bdesc = smem_desc_sw128(dz + ks * 2048, 0, 1024);
+        for (int ks = 0; ks < p.ksteps; ++ks) {
           const uint32_t acc = (t > t_begin || ks > 0) ? 1u : 0u;
+          const uint32_t a_ks = win_lo + (uint32_t)ks * (2u * WIN_W * 128u >> 4);
+          const uint32_t b_lo = dz_lo + (uint32_t)ks * (2048u >> 4);
 #pragma unroll
-          for (int pi = 0; pi < NPAIRS; ++pi) {
-            const int t0 = pair_first(pi);
-            const uint32_t a_addr = win + (uint32_t)tap_row(t0) * 128u + (uint32_t)ks * 2u * (WIN_W * 128u);
-            const uint32_t lbo = (uint32_t)(tap_row(t0 + 1) - tap_row(t0)) * 128u;
-            umma_bf16(tmem_base + pi * 64, smem_desc_sw128(a_addr, lbo, WIN_W * 128), bdesc, idesc, acc);
-          }
+          for (int pi = 0; pi < NPAIRS; ++pi) umma_lohi(tmem_base + pi * 64, a_ks + a_off[pi], a_hi, b_lo, b_hi, idesc, acc);
         }
         umma_commit(smem_u32(&bar_empty[st]));
         if (++st == NSTAGES) { st = 0; ph ^= 1; }
@@ -152,11 +176,14 @@ wgrad3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
 }
 
 __global__ void __launch_bounds__(256)
-wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw, long long count, int splits) {
+wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw, long long count, int splits,
+                    int live_mask, long long per_tap) {
   const long long n4 = count / 4;
   for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n4; i += (long long)gridDim.x * 256) {
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int s = 0; s < splits; ++s) {
+    const int tap = (int)(i * 4 / per_tap);
+    const int nsum = ((live_mask >> tap) & 1) ? splits : 0;   // taps that only ever see padding are exactly zero
+    for (int s = 0; s < nsum; ++s) {
       const float4 v = reinterpret_cast<const float4*>(partial + (long long)s * count)[i];
       acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
     }
@@ -164,11 +191,51 @@ wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw, l
   }
 }
 
-inline void plan(const b200_tensor* x, const b200_tensor* dy, WgradParams& p) {
-  p.N = x->n; p.H = x->h; p.W = x->w; p.Cin = x->c; p.Cout = dy->c;
+struct WgradGeom {
+  b200_tensor x, dy;      // possibly re-viewed tensors
+  int box_h, box_n, live_mask;
+};
+
+static bool flatten_1x1(const b200_tensor* t, b200_tensor* out) {
+  if (t->h != 1 || t->w != 1) return false;
+  *out = *t;
+  out->n = 1;
+  if (t->n % 8 == 0) { out->h = t->n / 8; out->w = 8; out->stride_w = t->stride_n; out->stride_h = 8 * t->stride_n; }
+  else { out->h = 1; out->w = t->n; out->stride_w = t->stride_n; out->stride_h = t->stride_n * t->n; }
+  out->stride_n = t->stride_n * t->n;
+  return true;
+}
+
+inline void plan(const b200_tensor* x_in, const b200_tensor* dy_in, WgradParams& p, WgradGeom& g) {
+  g.x = *x_in; g.dy = *dy_in;
+  g.live_mask = 0;
+  for (int t = 0; t < 9; ++t) {
+    const bool dead = (x_in->h == 1 && t / 3 != 1) || (x_in->w == 1 && t % 3 != 1);
+    if (!dead) g.live_mask |= 1 << t;
+  }
+  b200_tensor xf, yf;
+  if (flatten_1x1(x_in, &xf) && flatten_1x1(dy_in, &yf)) { g.x = xf; g.dy = yf; }
+  const b200_tensor* x = &g.x;
+  p.N = x->n; p.H = x->h; p.W = x->w; p.Cin = x->c; p.Cout = g.dy.c;
   p.tiles_h = (p.H + TILE_H - 1) / TILE_H;
   p.tiles_w = (p.W + TILE_W - 1) / TILE_W;
-  p.total_tiles = p.N * p.tiles_h * p.tiles_w;
+  p.nb = 1; p.ksteps = 8; p.zero_smem = 0;
+  g.box_h = WIN_H; g.box_n = 1;
+  p.stage_bytes = WIN_BYTES + DZ_BYTES;
+  if (p.H + 2 <= 9 && p.N > 1) {   // stack small images: image b owns window rows [b*(H+2), (b+1)*(H+2))
+    const int srows = p.H + 2;
+    p.nb = WIN_H / srows;
+    while ((p.nb - 1) * srows + p.H - 1 > TILE_H - 1) --p.nb;
+    if (p.nb > TILE_H / srows) p.nb = TILE_H / srows;   // the dz tile holds 16 pixel rows
+    if (p.nb > p.N) p.nb = p.N;
+    g.box_h = srows; g.box_n = p.nb;
+    p.ksteps = (p.nb * srows + 1) / 2;
+    if (p.ksteps > 8) p.ksteps = 8;
+    p.zero_smem = 1;
+    p.stage_bytes = p.nb * srows * (WIN_W + TILE_W) * 128;
+  }
+  const int groups = (p.N + p.nb - 1) / p.nb;
+  p.total_tiles = groups * p.tiles_h * p.tiles_w;
   p.cblocks = p.Cin / 64;
   p.oblocks = p.Cout / 64;
   const int pairs = p.cblocks * p.oblocks;
@@ -193,14 +260,16 @@ bool wgrad_tc_supported(const b200_tensor* x, const b200_tensor* dy, int ks) {
 
 size_t wgrad_tc_workspace(const b200_tensor* x, const b200_tensor* dy) {
   WgradParams p;
-  plan(x, dy, p);
+  WgradGeom g;
+  plan(x, dy, p, g);
   return sizeof(float) * (size_t)p.splits * 9 * p.Cin * p.Cout;
 }
 
 int wgrad_tc_launch(const b200_tensor* x, const b200_tensor* dy, float* dw, void* ws, size_t ws_bytes,
                     cudaStream_t st) {
   WgradParams p;
-  plan(x, dy, p);
+  WgradGeom g;
+  plan(x, dy, p, g);
   const size_t need = sizeof(float) * (size_t)p.splits * 9 * p.Cin * p.Cout;
   B200_REQUIRE(ws && ws_bytes >= need, B200_ERR_BAD_ARG, "conv2d_wgrad: workspace too small (%zu < %zu bytes)",
                ws_bytes, need);
@@ -208,9 +277,9 @@ int wgrad_tc_launch(const b200_tensor* x, const b200_tensor* dy, float* dw, void
                "conv2d_wgrad: workspace/dw must be 16-byte aligned");
   p.partial = reinterpret_cast<float*>(ws);
   CUtensorMap tm_x, tm_dz;
-  int rc = make_act_tmap(&tm_x, x, WIN_W, WIN_H);
+  int rc = make_act_tmap(&tm_x, &g.x, WIN_W, g.box_h, g.box_n);
   if (rc) return rc;
-  rc = make_act_tmap(&tm_dz, dy, TILE_W, TILE_H);
+  rc = make_act_tmap(&tm_dz, &g.dy, TILE_W, g.box_n > 1 || g.box_h != WIN_H ? g.box_h : TILE_H, g.box_n);
   if (rc) return rc;
   const size_t smem = 1024 + (size_t)NSTAGES * STAGE;
   static bool attr_set = false;
@@ -225,7 +294,7 @@ int wgrad_tc_launch(const b200_tensor* x, const b200_tensor* dy, float* dw, void
   const long long count = 9LL * p.Cin * p.Cout;
   long long blocks = (count / 4 + 255) / 256;
   if (blocks > 4LL * sm_count()) blocks = 4LL * sm_count();
-  wgrad_reduce_kernel<<<(int)blocks, 256, 0, st>>>(p.partial, dw, count, p.splits);  // counted by check_launch
+  wgrad_reduce_kernel<<<(int)blocks, 256, 0, st>>>(p.partial, dw, count, p.splits, g.live_mask, (long long)p.Cin * p.Cout);  // counted by check_launch
   return check_launch("wgrad_reduce_kernel");
 }
 

