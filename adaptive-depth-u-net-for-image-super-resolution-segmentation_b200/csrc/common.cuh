@@ -27,6 +27,7 @@ struct TView {
   void* data;
   int n, h, w, c;
   long long sn, sh, sw;
+  int lin;   // pixels are evenly spaced: offset(pixel p) = p * sw (dense tensors and channel slices)
 };
 
 inline TView view_of(const b200_tensor* t) {
@@ -34,6 +35,7 @@ inline TView view_of(const b200_tensor* t) {
   v.data = t->data;
   v.n = t->n; v.h = t->h; v.w = t->w; v.c = t->c;
   v.sn = t->stride_n; v.sh = t->stride_h; v.sw = t->stride_w;
+  v.lin = (v.sh == (long long)v.w * v.sw && v.sn == (long long)v.h * v.sh) ? 1 : 0;
   return v;
 }
 
@@ -101,6 +103,13 @@ __device__ __forceinline__ float warp_sum(float v) {
 
 __device__ __forceinline__ long long pix_offset(const TView& t, int n, int h, int w) {
   return (long long)n * t.sn + (long long)h * t.sh + (long long)w * t.sw;
+}
+// offset of flat pixel index p (n-major, then h, then w); no divisions for evenly spaced pixels
+__device__ __forceinline__ long long pix_offset_flat(const TView& t, long long p) {
+  if (t.lin) return p * t.sw;
+  const int w = (int)(p % t.w);
+  const long long q = p / t.w;
+  return (q / t.h) * t.sn + (q % t.h) * t.sh + (long long)w * t.sw;
 }
 
 inline int sm_count() {

@@ -141,12 +141,17 @@ stem_wgrad_kernel(TView x, TView dy, float* __restrict__ dw, int tiles_w, int ti
       if (c < Cin && ih >= 0 && ih < x.h && iw >= 0 && iw < x.w) v = ldf(xp + pix_offset(x, n, ih, iw) + c);
       s_x[c][r][q] = v;
     }
-    for (int i = tid; i < SW_TH * SW_TW * 64; i += 256) {
-      const int o = i % 64, pix = i / 64;
+    for (int i = tid; i < SW_TH * SW_TW * 8; i += 256) {   // 16-byte loads: 8 channels per thread
+      const int o8 = i % 8, pix = i / 8;
       const int oh = h0 + pix / SW_TW, ow = w0 + pix % SW_TW;
-      float v = 0.f;
-      if (oh < dy.h && ow < dy.w && co0 + o < Cout) v = ldf(dp + pix_offset(dy, n, oh, ow) + co0 + o);
-      s_dz[pix][o] = v;
+      float v[8];
+      if (oh < dy.h && ow < dy.w && co0 + o8 * 8 + 8 <= Cout) Vec8<T>::load(dp + pix_offset(dy, n, oh, ow) + co0 + o8 * 8, v);
+      else {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = 0.f;
+      }
+      *reinterpret_cast<float4*>(&s_dz[pix][o8 * 8]) = make_float4(v[0], v[1], v[2], v[3]);
+      *reinterpret_cast<float4*>(&s_dz[pix][o8 * 8 + 4]) = make_float4(v[4], v[5], v[6], v[7]);
     }
     __syncthreads();
     for (int p = stream; p < SW_TH * SW_TW; p += 4) {
@@ -183,38 +188,43 @@ stem_wgrad_kernel(TView x, TView dy, float* __restrict__ dw, int tiles_w, int ti
 // ---------------------------------------------------------------------------------------------
 // 1x1 heads with COUT <= 4: one thread per pixel (fprop, dgrad), 8 threads per pixel (wgrad).
 // ---------------------------------------------------------------------------------------------
+// C/8 threads per pixel (each 8 channels = one 16-byte load), shuffle reduction, lane 0 of the group stores
 template <typename T, int COUT>
 __global__ void __launch_bounds__(256)
 head_fprop_kernel(TView x, const T* __restrict__ wgt, const float* __restrict__ bias, TView y, int act, long long npix) {
-  extern __shared__ float s_w[];   // [Cin][COUT]
-  const int Cin = x.c;
-  for (int i = threadIdx.x; i < Cin * COUT; i += 256) s_w[i] = ldf(wgt + i);
-  __syncthreads();
+  const int Cin = x.c, chunks = Cin / 8;
+  const int j = threadIdx.x % chunks, ppb = 256 / chunks;
+  float w[8][COUT];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int o = 0; o < COUT; ++o) w[i][o] = ldf(wgt + (j * 8 + i) * COUT + o);
   const T* xp = reinterpret_cast<const T*>(x.data);
   T* yp = reinterpret_cast<T*>(y.data);
-  for (long long p = (long long)blockIdx.x * 256 + threadIdx.x; p < npix; p += (long long)gridDim.x * 256) {
-    const int w = (int)(p % x.w);
-    const long long q = p / x.w;
-    const int h = (int)(q % x.h), n = (int)(q / x.h);
-    const T* src = xp + pix_offset(x, n, h, w);
+  for (long long base = (long long)blockIdx.x * ppb; base < npix; base += (long long)gridDim.x * ppb) {
+    long long p = base + threadIdx.x / chunks;      // warp-uniform trip count (shuffles below)
+    const bool valid = p < npix;
+    if (!valid) p = npix - 1;
+    float v[8];
+    Vec8<T>::load(xp + pix_offset_flat(x, p) + j * 8, v);
     float acc[COUT];
 #pragma unroll
-    for (int o = 0; o < COUT; ++o) acc[o] = bias ? bias[o] : 0.f;
-    for (int c0 = 0; c0 < Cin; c0 += 8) {
-      float v[8];
-      Vec8<T>::load(src + c0, v);
-#pragma unroll
-      for (int i = 0; i < 8; ++i)
-#pragma unroll
-        for (int o = 0; o < COUT; ++o) acc[o] += v[i] * s_w[(c0 + i) * COUT + o];
-    }
-    T* dst = yp + pix_offset(y, n, h, w);
-#pragma unroll
     for (int o = 0; o < COUT; ++o) {
-      float v = acc[o];
-      if (act == B200_ACT_RELU) v = fmaxf(v, 0.f);
-      else if (act == B200_ACT_SIGMOID) v = 1.f / (1.f + __expf(-v));
-      stf(dst + o, v);
+      float a = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) a += v[i] * w[i][o];
+      for (int s = chunks >> 1; s > 0; s >>= 1) a += __shfl_xor_sync(0xffffffffu, a, s);
+      acc[o] = a;
+    }
+    if (j == 0 && valid) {
+      T* dst = yp + pix_offset_flat(y, p);
+#pragma unroll
+      for (int o = 0; o < COUT; ++o) {
+        float r = acc[o] + (bias ? bias[o] : 0.f);
+        if (act == B200_ACT_RELU) r = fmaxf(r, 0.f);
+        else if (act == B200_ACT_SIGMOID) r = 1.f / (1.f + __expf(-r));
+        stf(dst + o, r);
+      }
     }
   }
 }
@@ -223,38 +233,36 @@ head_fprop_kernel(TView x, const T* __restrict__ wgt, const float* __restrict__ 
 template <typename T, int COUT>
 __global__ void __launch_bounds__(256)
 head_dgrad_kernel(TView dy, const T* __restrict__ wgt, TView dx, int accumulate, long long npix) {
-  extern __shared__ float s_w[];
-  const int Cin = dx.c;
-  for (int i = threadIdx.x; i < Cin * COUT; i += 256) s_w[i] = ldf(wgt + i);
-  __syncthreads();
+  const int Cin = dx.c, chunks = Cin / 8;
+  const int j = threadIdx.x % chunks, ppb = 256 / chunks;
+  float w[8][COUT];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int o = 0; o < COUT; ++o) w[i][o] = ldf(wgt + (j * 8 + i) * COUT + o);
   const T* dp = reinterpret_cast<const T*>(dy.data);
   T* xp = reinterpret_cast<T*>(dx.data);
-  for (long long p = (long long)blockIdx.x * 256 + threadIdx.x; p < npix; p += (long long)gridDim.x * 256) {
-    const int w = (int)(p % dx.w);
-    const long long q = p / dx.w;
-    const int h = (int)(q % dx.h), n = (int)(q / dx.h);
-    const T* src = dp + pix_offset(dy, n, h, w);
+  for (long long p = (long long)blockIdx.x * ppb + threadIdx.x / chunks; p < npix; p += (long long)gridDim.x * ppb) {
+    const T* src = dp + pix_offset_flat(dy, p);
     float d[COUT];
 #pragma unroll
     for (int o = 0; o < COUT; ++o) d[o] = ldf(src + o);
-    T* dst = xp + pix_offset(dx, n, h, w);
-    for (int c0 = 0; c0 < Cin; c0 += 8) {
-      float v[8];
+    float v[8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        float a = 0.f;
+    for (int i = 0; i < 8; ++i) {
+      float a = 0.f;
 #pragma unroll
-        for (int o = 0; o < COUT; ++o) a += d[o] * s_w[(c0 + i) * COUT + o];
-        v[i] = a;
-      }
-      if (accumulate) {
-        float e[8];
-        Vec8<T>::load(dst + c0, e);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) v[i] += e[i];
-      }
-      Vec8<T>::store(dst + c0, v);
+      for (int o = 0; o < COUT; ++o) a += d[o] * w[i][o];
+      v[i] = a;
     }
+    T* dst = xp + pix_offset_flat(dx, p) + j * 8;
+    if (accumulate) {
+      float e[8];
+      Vec8<T>::load(dst, e);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] += e[i];
+    }
+    Vec8<T>::store(dst, v);
   }
 }
 
@@ -275,12 +283,9 @@ head_wgrad_kernel(TView x, TView dy, float* __restrict__ dw, long long npix) {
 #pragma unroll
     for (int o = 0; o < COUT; ++o) acc[i][o] = 0.f;
   for (long long p = (long long)blockIdx.x * ppb + threadIdx.x / chunks; p < npix; p += (long long)gridDim.x * ppb) {
-    const int w = (int)(p % x.w);
-    const long long q = p / x.w;
-    const int h = (int)(q % x.h), n = (int)(q / x.h);
     float v[8], d[COUT];
-    Vec8<T>::load(xp + pix_offset(x, n, h, w) + j * 8, v);
-    const T* src = dp + pix_offset(dy, n, h, w);
+    Vec8<T>::load(xp + pix_offset_flat(x, p) + j * 8, v);
+    const T* src = dp + pix_offset_flat(dy, p);
 #pragma unroll
     for (int o = 0; o < COUT; ++o) d[o] = ldf(src + o);
 #pragma unroll
@@ -302,7 +307,7 @@ inline bool pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
 
 // ---- dispatch helpers ---------------------------------------------------------------------------
 bool stem_supported(const b200_tensor* x, const b200_tensor* y, int ks) {
-  return ks == 3 && x->c <= 3 && y->c % 8 == 0 && vec_aligned(y, 8) && x->dtype == y->dtype;
+  return ks == 3 && x->c <= 3 && y->c % 8 == 0 && vec_aligned(y, 8) && x->dtype == y->dtype;   // y doubles as dy for wgrad
 }
 
 int stem_fprop(const b200_tensor* x, const void* wgt, const float* bias, const b200_tensor* y, int act, cudaStream_t st) {
@@ -318,7 +323,7 @@ int stem_fprop(const b200_tensor* x, const void* wgt, const float* bias, const b
 int stem_wgrad(const b200_tensor* x, const b200_tensor* dy, float* dw, cudaStream_t st) {
   const int tiles_w = (dy->w + SW_TW - 1) / SW_TW, tiles_h = (dy->h + SW_TH - 1) / SW_TH;
   const int total = tiles_w * tiles_h * dy->n;
-  int gx = 2 * sm_count();
+  int gx = 4 * sm_count();
   if (gx > total) gx = total;
   cudaMemsetAsync(dw, 0, sizeof(float) * 9 * x->c * dy->c, st);
   dim3 grid(gx, (dy->c + 63) / 64);
@@ -350,7 +355,7 @@ int head_fprop(const b200_tensor* x, const void* wgt, const float* bias, const b
   const size_t smem = sizeof(float) * x->c * y->c;
   B200_DISPATCH_DTYPE(x->dtype, T, {
     B200_HEAD_DISPATCH(y->c, {
-      head_fprop_kernel<T, COUT><<<head_grid(npix, 256), 256, smem, st>>>(xv, reinterpret_cast<const T*>(wgt), bias, yv, act, npix);
+      head_fprop_kernel<T, COUT><<<head_grid(npix, 256 / (x->c / 8)), 256, 0, st>>>(xv, reinterpret_cast<const T*>(wgt), bias, yv, act, npix);
     });
   });
   return check_launch("head_fprop_kernel");
@@ -362,7 +367,7 @@ int head_dgrad(const b200_tensor* dy, const void* wgt, const b200_tensor* dx, in
   const size_t smem = sizeof(float) * dx->c * dy->c;
   B200_DISPATCH_DTYPE(dx->dtype, T, {
     B200_HEAD_DISPATCH(dy->c, {
-      head_dgrad_kernel<T, COUT><<<head_grid(npix, 256), 256, smem, st>>>(dv, reinterpret_cast<const T*>(wgt), xv, accumulate, npix);
+      head_dgrad_kernel<T, COUT><<<head_grid(npix, 256 / (dx->c / 8)), 256, 0, st>>>(dv, reinterpret_cast<const T*>(wgt), xv, accumulate, npix);
     });
   });
   return check_launch("head_dgrad_kernel");
@@ -375,7 +380,7 @@ int head_wgrad(const b200_tensor* x, const b200_tensor* dy, float* dw, cudaStrea
   cudaMemsetAsync(dw, 0, smem, st);
   const int ppb = 256 / (x->c / 8);
   long long blocks = (npix + ppb - 1) / ppb;
-  if (blocks > 2LL * sm_count()) blocks = 2LL * sm_count();
+  if (blocks > 6LL * sm_count()) blocks = 6LL * sm_count();
   B200_DISPATCH_DTYPE(x->dtype, T, {
     B200_HEAD_DISPATCH(dy->c, { head_wgrad_kernel<T, COUT><<<(int)blocks, 256, smem, st>>>(xv, dv, dw, npix); });
   });

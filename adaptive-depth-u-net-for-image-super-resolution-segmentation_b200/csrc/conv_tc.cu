@@ -188,7 +188,9 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
     __syncwarp();
   } else if (warp == 1) {
     // ============================ MMA issuer ==============================
-    if (lane == 0) {
+    // All 32 lanes run the loop so that control flow stays warp-uniform (descriptor words are then
+    // computed on the uniform datapath); one elected lane issues the MMAs and the commits.
+    {
       const uint32_t idesc = idesc_bf16(128, p.BN, 0, 0);
       const uint32_t a_hi = (uint32_t)(smem_desc_sw128(0, 0, WIN_PITCH) >> 32);
       const uint32_t b_hi = (uint32_t)(smem_desc_sw128(0, 0, 1024) >> 32);
@@ -213,16 +215,18 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
           if (p.resident && all_live) {
             // hot path of the full-resolution layers: 36 MMAs, descriptor words by 32-bit adds only
             const uint32_t b_lo0 = (wt0 >> 4) + (uint32_t)(kb * 9) * wt_step;
+            if (elect_one()) {
 #pragma unroll
-            for (int tap = 0; tap < 9; ++tap) {
-              const uint32_t a_lo = a_lo0 + (uint32_t)((tap / 3) * WIN_W + (tap % 3)) * 8u;
-              const uint32_t b_lo = b_lo0 + (uint32_t)tap * wt_step;
+              for (int tap = 0; tap < 9; ++tap) {
+                const uint32_t a_lo = a_lo0 + (uint32_t)((tap / 3) * WIN_W + (tap % 3)) * 8u;
+                const uint32_t b_lo = b_lo0 + (uint32_t)tap * wt_step;
 #pragma unroll
-              for (int ks = 0; ks < 4; ++ks) {
-                umma_lohi(d_tmem, a_lo + ks * 2, a_hi, b_lo + ks * 2, b_hi, idesc, accumulate);
-                accumulate = 1;
+                for (int ks = 0; ks < 4; ++ks)
+                  umma_lohi(d_tmem, a_lo + ks * 2, a_hi, b_lo + ks * 2, b_hi, idesc, (tap | ks) ? 1u : accumulate);
               }
             }
+            accumulate = 1;
+            __syncwarp();
           } else {
 #pragma unroll 1
             for (int tap = 0; tap < 9; ++tap) {
@@ -236,25 +240,26 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
                 b_lo = (wt0 >> 4) + (uint32_t)sb * wt_step;
               }
               const uint32_t a_lo = a_lo0 + (uint32_t)((tap / 3) * WIN_W + (tap % 3)) * 8u;
+              if (elect_one()) {
 #pragma unroll
-              for (int ks = 0; ks < 4; ++ks) {
-                umma_lohi(d_tmem, a_lo + ks * 2, a_hi, b_lo + ks * 2, b_hi, idesc, accumulate);
-                accumulate = 1;
+                for (int ks = 0; ks < 4; ++ks)
+                  umma_lohi(d_tmem, a_lo + ks * 2, a_hi, b_lo + ks * 2, b_hi, idesc, ks ? 1u : accumulate);
+                if (!p.resident) umma_commit(smem_u32(&bar_empty_b[sb]));
               }
-              if (!p.resident) {
-                umma_commit(smem_u32(&bar_empty_b[sb]));
-                if (++sb == p.nsb) { sb = 0; pb ^= 1; }
-              }
+              accumulate = 1;
+              __syncwarp();
+              if (!p.resident) { if (++sb == p.nsb) { sb = 0; pb ^= 1; } }
             }
           }
-          umma_commit(smem_u32(&bar_empty_w[sw]));
+          if (elect_one()) umma_commit(smem_u32(&bar_empty_w[sw]));
+          __syncwarp();
           if (++sw == p.nsw) { sw = 0; pw ^= 1; }
         }
-        umma_commit(smem_u32(&bar_tmem_full[as]));
+        if (elect_one()) umma_commit(smem_u32(&bar_tmem_full[as]));
+        __syncwarp();
         if (++as == 2) { as = 0; pa ^= 1; }
       }
     }
-    __syncwarp();
   } else {
     // ============================ epilogue ================================
     const int q = warp % 4;                 // TMEM lane quarter this warp may read

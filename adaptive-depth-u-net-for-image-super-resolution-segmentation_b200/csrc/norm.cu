@@ -36,14 +36,22 @@ ln_fwd_kernel(TView z, const float* __restrict__ gamma, const float* __restrict_
   const T* zp = reinterpret_cast<const T*>(z.data);
   T* yp = reinterpret_cast<T*>(y.data);
   const float invC = 1.f / (float)C;
+  float gam[CPT][8], bet[CPT][8];   // this thread's channels never change: keep gamma/beta in registers
+#pragma unroll
+  for (int k = 0; k < CPT; ++k) {
+    const int j = lane_g + k * tpp;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      gam[k][i] = j < chunks ? gamma[j * 8 + i] : 0.f;
+      bet[k][i] = j < chunks ? beta[j * 8 + i] : 0.f;
+    }
+  }
   for (long long base = (long long)blockIdx.x * ppb; base < npix; base += (long long)gridDim.x * ppb) {
     // warp-uniform trip count: groups past the end recompute the last pixel and skip their stores
     long long p = base + threadIdx.x / tpp;
     const bool valid = p < npix;
     if (!valid) p = npix - 1;
-    int n, h, w;
-    pix_decode(p, z.h, z.w, n, h, w);
-    const T* src = zp + pix_offset(z, n, h, w);
+    const T* src = zp + pix_offset_flat(z, p);
     float v[CPT][8];
     float s = 0.f;
 #pragma unroll
@@ -70,7 +78,7 @@ ln_fwd_kernel(TView z, const float* __restrict__ gamma, const float* __restrict_
     }
     const float var = group_sum(q, tpp) * invC;
     const float rs = rsqrtf(var + eps);
-    T* dst = yp + pix_offset(y, n, h, w);
+    T* dst = yp + pix_offset_flat(y, p);
 #pragma unroll
     for (int k = 0; k < CPT; ++k) {
       int j = lane_g + k * tpp;
@@ -78,7 +86,7 @@ ln_fwd_kernel(TView z, const float* __restrict__ gamma, const float* __restrict_
         float o[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          float t = (v[k][i] - mu) * rs * gamma[j * 8 + i] + beta[j * 8 + i];
+          float t = (v[k][i] - mu) * rs * gam[k][i] + bet[k][i];
           o[i] = relu ? fmaxf(t, 0.f) : t;
         }
         Vec8<T>::store(dst + j * 8, o);
@@ -112,15 +120,23 @@ ln_bwd_kernel(TView dy, TView z, const float* __restrict__ mean, const float* __
 #pragma unroll
     for (int i = 0; i < 8; ++i) { a_g[k][i] = 0.f; a_b[k][i] = 0.f; a_z[k][i] = 0.f; }
 
+  float gam[CPT][8], bet[CPT][8];
+#pragma unroll
+  for (int k = 0; k < CPT; ++k) {
+    const int j = lane_g + k * tpp;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      gam[k][i] = j < chunks ? gamma[j * 8 + i] : 0.f;
+      bet[k][i] = j < chunks ? beta[j * 8 + i] : 0.f;
+    }
+  }
   for (long long base = (long long)blockIdx.x * ppb; base < npix; base += (long long)gridDim.x * ppb) {
     // warp-uniform trip count: groups past the end recompute the last pixel and skip their stores
     long long p = base + threadIdx.x / tpp;
     const bool valid = p < npix;
     if (!valid) p = npix - 1;
-    int n, h, w;
-    pix_decode(p, z.h, z.w, n, h, w);
-    const T* zs = zp + pix_offset(z, n, h, w);
-    const T* ds = dyp + pix_offset(dy, n, h, w);
+    const T* zs = zp + pix_offset_flat(z, p);
+    const T* ds = dyp + pix_offset_flat(dy, p);
     const float mu = mean[p], rs = rstd[p];
     float xh[CPT][8], g[CPT][8];
     float s1 = 0.f, s2 = 0.f;
@@ -134,8 +150,8 @@ ln_bwd_kernel(TView dy, TView z, const float* __restrict__ mean, const float* __
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           float x = (zv[i] - mu) * rs;
-          float ga = gamma[j * 8 + i];
-          float t = x * ga + beta[j * 8 + i];
+          float ga = gam[k][i];
+          float t = x * ga + bet[k][i];
           float d = (!valid || (relu && !(t > 0.f))) ? 0.f : dv[i];
           a_g[k][i] += d * x;
           a_b[k][i] += d;
@@ -150,7 +166,7 @@ ln_bwd_kernel(TView dy, TView z, const float* __restrict__ mean, const float* __
     }
     const float m1 = group_sum(s1, tpp) * invC;
     const float m2 = group_sum(s2, tpp) * invC;
-    T* dd = dzp + pix_offset(dz, n, h, w);
+    T* dd = dzp + pix_offset_flat(dz, p);
 #pragma unroll
     for (int k = 0; k < CPT; ++k) {
       int j = lane_g + k * tpp;
@@ -231,18 +247,16 @@ bias_act_bwd_vec_kernel(TView dy, TView y, int act, TView dz, float* __restrict_
 #pragma unroll
   for (int i = 0; i < 8; ++i) acc[i] = 0.f;
   for (long long p = (long long)blockIdx.x * ppb + threadIdx.x / chunks; p < npix; p += (long long)gridDim.x * ppb) {
-    int n, h, w;
-    pix_decode(p, y.h, y.w, n, h, w);
     float d[8], yv[8];
-    Vec8<T>::load(dyp + pix_offset(dy, n, h, w) + j * 8, d);
-    Vec8<T>::load(yp + pix_offset(y, n, h, w) + j * 8, yv);
+    Vec8<T>::load(dyp + pix_offset_flat(dy, p) + j * 8, d);
+    Vec8<T>::load(yp + pix_offset_flat(y, p) + j * 8, yv);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       if (act == B200_ACT_RELU) d[i] = yv[i] > 0.f ? d[i] : 0.f;
       else if (act == B200_ACT_SIGMOID) d[i] = d[i] * yv[i] * (1.f - yv[i]);
       acc[i] += d[i];
     }
-    Vec8<T>::store(dzp + pix_offset(dz, n, h, w) + j * 8, d);
+    Vec8<T>::store(dzp + pix_offset_flat(dz, p) + j * 8, d);
   }
   if (dbias) {
 #pragma unroll
@@ -406,7 +420,7 @@ int layernorm_bwd(const b200_tensor* dy, const b200_tensor* z, const float* mean
   B200_REQUIRE(cpt <= 8, B200_ERR_UNSUPPORTED, "layernorm_bwd: C=%d too wide (max 2048)", C);
   const long long npix = (long long)z->n * z->h * z->w;
   long long blocks = (npix + (NT / tpp) - 1) / (NT / tpp);
-  long long cap = 2LL * sm_count();
+  long long cap = 6LL * sm_count();
   const int grid = (int)(blocks < cap ? (blocks < 1 ? 1 : blocks) : cap);
   const size_t smem = sizeof(float) * 3 * C;
   TView dyv = view_of(dy), zv = view_of(z), dzv = view_of(dz);

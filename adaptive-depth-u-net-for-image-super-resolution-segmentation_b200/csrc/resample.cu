@@ -18,48 +18,45 @@ namespace {
 
 constexpr int NT = 256;
 
+// grid = (ceil(OW * C/8 / 256), OH, N): one block per output-row segment, one thread per
+// (output pixel, 8-channel chunk).  No per-element divisions by H/W; the row's h-taps are block-uniform.
 template <typename T>
 __global__ void __launch_bounds__(NT)
 resample_vec_kernel(TView x, TView y, const int* __restrict__ hs, const float* __restrict__ hw, int ht,
-                    const int* __restrict__ ws, const float* __restrict__ ww, int wt, int accumulate,
-                    long long total) {
-  const int chunks = y.c / 8;
-  const T* xp = reinterpret_cast<const T*>(x.data);
-  T* yp = reinterpret_cast<T*>(y.data);
-  for (long long i = (long long)blockIdx.x * NT + threadIdx.x; i < total; i += (long long)gridDim.x * NT) {
-    const int j = (int)(i % chunks);
-    long long p = i / chunks;
-    const int ow = (int)(p % y.w); p /= y.w;
-    const int oh = (int)(p % y.h);
-    const int n = (int)(p / y.h);
-    float acc[8];
+                    const int* __restrict__ ws, const float* __restrict__ ww, int wt, int accumulate) {
+  const int chunks = y.c >> 3;
+  const int item = blockIdx.x * NT + threadIdx.x;
+  const int ow = item / chunks, j = item - ow * chunks;
+  if (ow >= y.w) return;
+  const int oh = blockIdx.y, n = blockIdx.z;
+  const T* xp = reinterpret_cast<const T*>(x.data) + (long long)n * x.sn + j * 8;
+  T* dst = reinterpret_cast<T*>(y.data) + pix_offset(y, n, oh, ow) + j * 8;
+  float acc[8];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) acc[k] = 0.f;
-    const int h0 = hs[oh], w0 = ws[ow];
-    for (int a = 0; a < ht; ++a) {
-      const float wa = hw[oh * ht + a];
-      if (wa == 0.f) continue;
-      const int ih = min(h0 + a, x.h - 1);
-      for (int b = 0; b < wt; ++b) {
-        const float wb = ww[ow * wt + b];
-        if (wb == 0.f) continue;
-        const int iw = min(w0 + b, x.w - 1);
-        float v[8];
-        Vec8<T>::load(xp + pix_offset(x, n, ih, iw) + j * 8, v);
-        const float wgt = wa * wb;
+  for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+  const int h0 = hs[oh], w0 = ws[ow];
+  const float* wrow = ww + ow * wt;
+  for (int a = 0; a < ht; ++a) {
+    const float wa = hw[oh * ht + a];
+    if (wa == 0.f) continue;
+    const T* row = xp + (long long)min(h0 + a, x.h - 1) * x.sh;
+    for (int b = 0; b < wt; ++b) {
+      const float wb = wrow[b];
+      if (wb == 0.f) continue;
+      float v[8];
+      Vec8<T>::load(row + (long long)min(w0 + b, x.w - 1) * x.sw, v);
+      const float wgt = wa * wb;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) acc[k] += wgt * v[k];
-      }
+      for (int k = 0; k < 8; ++k) acc[k] += wgt * v[k];
     }
-    T* dst = yp + pix_offset(y, n, oh, ow) + j * 8;
-    if (accumulate) {
-      float o[8];
-      Vec8<T>::load(dst, o);
-#pragma unroll
-      for (int k = 0; k < 8; ++k) acc[k] += o[k];
-    }
-    Vec8<T>::store(dst, acc);
   }
+  if (accumulate) {
+    float o[8];
+    Vec8<T>::load(dst, o);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] += o[k];
+  }
+  Vec8<T>::store(dst, acc);
 }
 
 template <typename T>
@@ -249,9 +246,9 @@ int resample2d(const b200_tensor* x, const b200_tensor* y, const int32_t* hs, co
   TView xv = view_of(x), yv = view_of(y);
   const bool vec = vec_aligned(x, 8) && vec_aligned(y, 8);
   B200_DISPATCH_DTYPE(x->dtype, T, {
-    if (vec) {
-      long long total = (long long)y->n * y->h * y->w * (y->c / 8);
-      resample_vec_kernel<T><<<grid_for(total), NT, 0, st>>>(xv, yv, hs, hw, ht, ws, ww, wt, accumulate, total);
+    if (vec && y->h <= 65535 && y->n <= 65535) {
+      dim3 grid((unsigned)(((long long)y->w * (y->c / 8) + NT - 1) / NT), (unsigned)y->h, (unsigned)y->n);
+      resample_vec_kernel<T><<<grid, NT, 0, st>>>(xv, yv, hs, hw, ht, ws, ww, wt, accumulate);
     } else {
       long long total = (long long)y->n * y->h * y->w * y->c;
       resample_scalar_kernel<T><<<grid_for(total), NT, 0, st>>>(xv, yv, hs, hw, ht, ws, ww, wt, accumulate, total);

@@ -113,39 +113,41 @@ wgrad3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
     }
     __syncwarp();
   } else if (warp == 1) {
-    if (lane == 0) {
+    // all lanes run the loop (uniform control flow); one elected lane issues MMAs and commits
+    {
       const uint32_t idesc = idesc_bf16(128, 64, 1, 1);
       const uint32_t b_hi = (uint32_t)(smem_desc_sw128(0, 0, 1024) >> 32);
       // A descriptor hi word is shared (SBO = window pitch); the lo word carries LBO = distance
       // between the two taps of the pair
       const uint32_t a_hi = (uint32_t)(smem_desc_sw128(0, 0, WIN_W * 128) >> 32);
-      uint32_t a_off[NPAIRS];
-#pragma unroll
-      for (int pi = 0; pi < NPAIRS; ++pi) {
-        const int t0 = pair_first(pi);
-        const uint32_t lbo = (uint32_t)(tap_row(t0 + 1) - tap_row(t0)) * 128u;
-        a_off[pi] = ((uint32_t)tap_row(t0) * 128u >> 4) | ((lbo >> 4) << 16);
-      }
       int st = 0, ph = 0;
       for (int t = t_begin; t < t_end; ++t) {
         mbar_wait(smem_u32(&bar_full[st]), ph);
         tc_fence_after();
         const uint32_t win_lo = (smem0 + st * STAGE) >> 4;
         const uint32_t dz_lo = win_lo + (WIN_STAGE >> 4);
+        if (elect_one()) {
 #pragma unroll 1
-        for (int ks = 0; ks < p.ksteps; ++ks) {
-          const uint32_t acc = (t > t_begin || ks > 0) ? 1u : 0u;
-          const uint32_t a_ks = win_lo + (uint32_t)ks * (2u * WIN_W * 128u >> 4);
-          const uint32_t b_lo = dz_lo + (uint32_t)ks * (2048u >> 4);
+          for (int ks = 0; ks < p.ksteps; ++ks) {
+            const uint32_t acc = (t > t_begin || ks > 0) ? 1u : 0u;
+            const uint32_t a_ks = win_lo + (uint32_t)ks * (2u * WIN_W * 128u >> 4);
+            const uint32_t b_lo = dz_lo + (uint32_t)ks * (2048u >> 4);
 #pragma unroll
-          for (int pi = 0; pi < NPAIRS; ++pi) umma_lohi(tmem_base + pi * 64, a_ks + a_off[pi], a_hi, b_lo, b_hi, idesc, acc);
+            for (int pi = 0; pi < NPAIRS; ++pi) {
+              const int t0 = pair_first(pi);
+              const uint32_t lbo = (uint32_t)(tap_row(t0 + 1) - tap_row(t0)) * 128u;
+              const uint32_t a_off = ((uint32_t)tap_row(t0) * 128u >> 4) | ((lbo >> 4) << 16);
+              umma_lohi(tmem_base + pi * 64, a_ks + a_off, a_hi, b_lo, b_hi, idesc, acc);
+            }
+          }
+          umma_commit(smem_u32(&bar_empty[st]));
         }
-        umma_commit(smem_u32(&bar_empty[st]));
+        __syncwarp();
         if (++st == NSTAGES) { st = 0; ph ^= 1; }
       }
-      umma_commit(smem_u32(&bar_done));
+      if (elect_one()) umma_commit(smem_u32(&bar_done));
+      __syncwarp();
     }
-    __syncwarp();
   } else {
     const int q = warp % 4;
     const int r = q * 32 + lane;          // TMEM lane = (tap of the pair, ci)

@@ -220,6 +220,15 @@ def run_gpu(args):
     entry = model._train_state(batch)
     launches_per_step = ops.launch_count() // 2  # body ran once eagerly (warm-up) and once under capture
     plan, st, graph = entry["plan"], entry["state"], entry["graph"]
+
+    class _Eager:   # B200_NO_CUDA_GRAPH=1 (used for the ncu launch list): same launches, issued one by one
+        @staticmethod
+        def replay():
+            model._train_body(plan, st)
+
+    if graph is None:
+        graph = _Eager
+        launches_per_step = ops.launch_count()
     for _ in range(max(args.warmup, 3)):
         graph.replay()
     torch.cuda.synchronize()
