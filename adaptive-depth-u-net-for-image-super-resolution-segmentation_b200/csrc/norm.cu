@@ -99,7 +99,7 @@ ln_fwd_kernel(TView z, const float* __restrict__ gamma, const float* __restrict_
 // LayerNorm backward.  Per-channel partials live in registers across the
 // grid-stride loop, then go through shared memory to one global atomic per block.
 template <typename T, int CPT>
-__global__ void __launch_bounds__(NT)
+__global__ void __launch_bounds__(NT, CPT == 1 ? 3 : 1)
 ln_bwd_kernel(TView dy, TView z, const float* __restrict__ mean, const float* __restrict__ rstd,
               const float* __restrict__ gamma, const float* __restrict__ beta, int relu, TView dz,
               float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dbias, int tpp,

@@ -291,10 +291,22 @@ class Plan:
         m = self.model
         self.bwd_tags: List[str] = []
 
+        self.bwd_writes: List[list] = []   # flat-G ranges (offset, count) written by each backward step
+
         class _Tagged(list):
             def append(inner, fn, _tags=self.bwd_tags):
                 _tags.append(self._cur_tag)
+                self.bwd_writes.append(list(self._cur_writes))
+                self._cur_writes = []
                 list.append(inner, fn)
+
+        self._cur_writes = []
+
+        def writes(ly, *names):
+            for nm in names:
+                r = m._grad_range(ly, nm)
+                if r is not None:
+                    self._cur_writes.append(r)
 
         B = self.bwd_steps = _Tagged()
         ws_bytes = 0
@@ -321,12 +333,15 @@ class Plan:
                 kh = ly.kernel_size[0]
                 sfx = ":tc" if self.is_tc(op) else ":simt"
                 self._cur_tag = "bias_act"
+                if op.act != ACT_NONE or (not op.norm_bias and dbias is not None):
+                    writes(ly, "bias")
                 if op.act != ACT_NONE:
                     B.append(lambda o=out, a=op.act, db=dbias: ops.bias_act_bwd(o.grad, o.buf, a, o.grad, db))
                 elif not op.norm_bias and dbias is not None:
                     B.append(lambda o=out, db=dbias: ops.bias_act_bwd(o.grad, o.buf, ACT_NONE, o.grad, db))
                 dw = m._grad(ly, "kernel").view(-1)
                 self._cur_tag = "wgrad" + sfx
+                writes(ly, "kernel")
                 B.append(lambda x=x, o=out, dw=dw, kh=kh: ops.conv2d_wgrad(x.buf, o.grad, kh, kh, dw, self.wgrad_ws))
                 if x.needs_grad:
                     acc = write_flag(x)
@@ -337,6 +352,9 @@ class Plan:
                 assert not z.grad_written, "LayerNormalization input must have a single consumer"
                 z.mark_grad_written()
                 dbias = m._grad(op.conv_src.layer, "bias") if op.conv_src is not None else None
+                writes(ly, "gamma", "beta")
+                if op.conv_src is not None:
+                    writes(op.conv_src.layer, "bias")
                 B.append(lambda z=z, o=out, op=op, g=m._param(ly, "gamma"), b=m._param(ly, "beta"),
                          dg=m._grad(ly, "gamma"), db=m._grad(ly, "beta"), dbias=dbias:
                          ops.layernorm_bwd(o.grad, z.buf, op.mean, op.rstd, g, b, op.relu, z.grad, dg, db, dbias))
@@ -344,6 +362,7 @@ class Plan:
                 z, ly = op.inputs[0], op.layer
                 assert not z.grad_written, "BatchNormalization input must have a single consumer"
                 z.mark_grad_written()
+                writes(ly, "gamma", "beta")
                 B.append(lambda z=z, o=out, op=op, g=m._param(ly, "gamma"), b=m._param(ly, "beta"),
                          dg=m._grad(ly, "gamma"), db=m._grad(ly, "beta"):
                          ops.batchnorm_bwd(o.grad, z.buf, op.save_mean, op.save_rstd, g, b, op.relu, z.grad, dg, db,
@@ -365,6 +384,7 @@ class Plan:
                     B.append(lambda x=x, o=out, acc=acc: ops.maxpool2_bwd(x.buf, o.buf, o.grad, x.grad, acc))
             elif k == "convT":
                 x, ly = op.inputs[0], op.layer
+                writes(ly, "kernel", "bias")
                 B.append(lambda x=x, o=out, dk=m._grad(ly, "kernel"), db=m._grad(ly, "bias"):
                          ops.convT2x2_wgrad(x.buf, o.grad, dk, db))
                 if x.needs_grad:

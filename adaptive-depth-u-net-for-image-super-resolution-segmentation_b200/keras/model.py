@@ -168,6 +168,13 @@ class Model:
             return None
         return self._view(self.G, ly, name)
 
+    def _grad_range(self, ly, name):
+        key = f"{ly.name}/{name}"
+        if key not in self._pinfo or not self._pinfo[key][0]:
+            return None
+        _, off, shape = self._pinfo[key]
+        return (off, int(np.prod(shape)))
+
     def _shadow(self, ly, name):
         return self._view(self.S, ly, name)
 
@@ -308,21 +315,61 @@ class Model:
             self._plans[key] = Plan(self, batch, training)
         return self._plans[key]
 
+    def _buckets(self, plan):
+        from ..parallel import plan_buckets
+        key = id(plan)
+        if getattr(self, "_bucket_cache", None) is None:
+            self._bucket_cache = {}
+        if key not in self._bucket_cache:
+            elems = int(float(os.environ.get("B200_BUCKET_MB", "32")) * (1 << 20) / 4)
+            self._bucket_cache[key] = plan_buckets(self.G.numel(), plan.bwd_writes, elems)
+        return self._bucket_cache[key]
+
     def _world(self):
         if self._dist is None:
             return 1
         return self._dist[0].get_world_size(self._dist[1])
 
-    def _train_body(self, plan: Plan, st):
-        """The launches of one training step, in stream order."""
+    # ---- one training step, as launch sequences ------------------------------------------------
+    def _seg_forward(self, plan: Plan, st):
         self.G.zero_()
         plan.run_pre()
         plan.run_forward()
         self.loss.launch(plan, st, grad_scale=1.0 / self._world())
-        plan.run_backward()
-        if self._dist is not None:
-            self._dist[0].all_reduce(self.G, group=self._dist[1])
+
+    def _segments(self, plan: Plan):
+        """Backward cut at the points where a gradient bucket becomes complete:
+        [(first_step, last_step_exclusive, [buckets ready after this segment])]."""
+        if self._dist is None:
+            return [(0, len(plan.bwd_steps), [])]
+        segs, start = [], 0
+        by_ready = {}
+        for b in self._buckets(plan):
+            by_ready.setdefault(min(b["ready_after"], len(plan.bwd_steps) - 1), []).append(b)
+        for ready in sorted(by_ready):
+            segs.append((start, ready + 1, by_ready[ready]))
+            start = ready + 1
+        if start < len(plan.bwd_steps):
+            segs.append((start, len(plan.bwd_steps), []))
+        return segs
+
+    def _train_body(self, plan: Plan, st):
+        """The launches of one training step, in stream order (eager form; also what gets captured)."""
+        self._seg_forward(plan, st)
+        works = []
+        for (a, b, buckets) in self._segments(plan):
+            for f in plan.bwd_steps[a:b]:
+                f()
+            works += self._reduce_async(buckets)
+        for w in works:
+            w.wait()
         self.optimizer.apply(self)
+
+    def _reduce_async(self, buckets):
+        if not buckets:
+            return []
+        dist, group = self._dist
+        return [dist.all_reduce(self.G[b["lo"]:b["hi"]], group=group, async_op=True) for b in buckets]
 
     def _train_state(self, batch):
         key = ("train", batch)
@@ -331,7 +378,7 @@ class Model:
         plan = self._plan(batch, True)
         st = self.loss.make_state(plan)
         self.optimizer.ensure_state(self)
-        entry = {"plan": plan, "state": st, "graph": None}
+        entry = {"plan": plan, "state": st, "graph": None, "segments": None}
         if self.use_cuda_graph:
             # warm-up on a side stream (sets kernel attributes, initialises NCCL), then capture
             snap = (self.P.clone(), self.optimizer.snapshot(), self.NT.clone())
@@ -343,13 +390,50 @@ class Model:
             torch.cuda.synchronize()
             self.P.copy_(snap[0]); self.optimizer.restore(snap[1]); self.NT.copy_(snap[2])
             self._refresh_shadow()
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
-                self._train_body(plan, st)
-            entry["graph"] = g
-            # capture executes nothing, but be explicit that state is unchanged
+            if self._dist is None:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._train_body(plan, st)
+                entry["graph"] = g
+            else:
+                # data parallel: the NCCL all-reduces stay OUTSIDE the graphs (launched eagerly, async, on
+                # NCCL's stream) and the backward pass is captured in segments that end where a gradient
+                # bucket becomes complete, so each bucket's exchange overlaps the following segment
+                segs = []
+                for k, (a, b, buckets) in enumerate(self._segments(plan)):
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g):
+                        if k == 0:
+                            self._seg_forward(plan, st)
+                        for f in plan.bwd_steps[a:b]:
+                            f()
+                    segs.append((g, buckets))
+                ga = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(ga):
+                    self.optimizer.apply(self)
+                entry["segments"], entry["adam_graph"] = segs, ga
         self._graphs[key] = entry
         return entry
+
+    def _run_step(self, entry):
+        """Launch one captured (or eager) training step on the data already in the input buffers."""
+        if entry["graph"] is not None:
+            entry["graph"].replay()
+        elif entry["segments"] is not None:
+            works = []
+            for g, buckets in entry["segments"]:
+                g.replay()
+                works += self._reduce_async(buckets)
+            for w in works:
+                w.wait()
+            entry["adam_graph"].replay()
+        else:
+            self._train_body(entry["plan"], entry["state"])
+
+    def release_graphs(self):
+        """Drop every captured graph (call before torch.distributed.destroy_process_group)."""
+        self._graphs = {}
+        torch.cuda.synchronize()
 
     def _eval_state(self, batch, with_loss):
         key = ("eval", batch, with_loss)
@@ -398,10 +482,7 @@ class Model:
         self._to_device(plan.input_vals[0].buf, x)
         self.loss.set_target(st, y)
         self.optimizer.before_step()
-        if e["graph"] is not None:
-            e["graph"].replay()
-        else:
-            self._train_body(plan, st)
+        self._run_step(e)
         logs = self.loss.logs(st)
         return logs if return_tensors else {k: float(v) for k, v in logs.items()}
 

@@ -189,6 +189,7 @@ def run_gpu(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     import b200unet  # noqa: F401  (fails loudly if the CUDA library is missing)
     from b200unet import builders as B, ops
@@ -219,15 +220,14 @@ def run_gpu(args):
     model.train_on_batch(x_pin, y_pin)          # builds the plan, warm-up + capture
     entry = model._train_state(batch)
     launches_per_step = ops.launch_count() // 2  # body ran once eagerly (warm-up) and once under capture
-    plan, st, graph = entry["plan"], entry["state"], entry["graph"]
+    plan, st = entry["plan"], entry["state"]
 
-    class _Eager:   # B200_NO_CUDA_GRAPH=1 (used for the ncu launch list): same launches, issued one by one
-        @staticmethod
+    class graph:   # one step on the device-resident batch: CUDA-graph replay (segmented around the NCCL
+        @staticmethod   # all-reduces when N>1), or eager launches under B200_NO_CUDA_GRAPH=1 (ncu launch list)
         def replay():
-            model._train_body(plan, st)
+            model._run_step(entry)
 
-    if graph is None:
-        graph = _Eager
+    if entry["graph"] is None and entry["segments"] is None:
         launches_per_step = ops.launch_count()
     for _ in range(max(args.warmup, 3)):
         graph.replay()
@@ -271,6 +271,7 @@ def run_gpu(args):
 
     if rank != 0:
         if world > 1:
+            model.release_graphs()
             dist.barrier()
             dist.destroy_process_group()
         return
@@ -333,6 +334,7 @@ def run_gpu(args):
     }
     print(json.dumps(line), flush=True)
     if world > 1:
+        model.release_graphs()
         dist.barrier()
         dist.destroy_process_group()
 

@@ -1,0 +1,98 @@
+"""CPU-only checks of the host side: the C-ABI library loads and exports every declared symbol, the
+host-side resample planner matches the oracle, the Keras-shaped builders reproduce the reference's
+parameter totals / layer names, and the product path refuses to run without a CUDA device."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    from b200unet import _ffi
+    lib = _ffi.load()
+    header = open(os.path.join(ROOT, "include", "b200_unet.h")).read()
+    declared = set(re.findall(r"\b(b200_[a-zA-Z0-9_]+)\s*\(", header))
+    declared -= {"b200_tensor", "b200_filter"}
+    assert declared, "no declarations parsed"
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} declared in include/b200_unet.h but not exported"
+        assert name in _ffi.SIGNATURES, f"{name} has no ctypes prototype"
+    assert b"sm_100a" in lib.b200_version()
+
+
+def test_struct_layout_matches_header():
+    from b200unet import _ffi
+    assert ctypes.sizeof(_ffi.Tensor) == 8 + 4 * 4 + 3 * 8 + 8
+    assert ctypes.sizeof(_ffi.Filter) == 16 + 4 * 4 + 8
+
+
+def test_resample_plan_matches_oracle_tables():
+    import b200unet.ops as ops
+    from oracle import resize_np
+    for (a, b) in [(256, 180), (180, 126), (126, 89), (89, 63), (63, 45), (128, 32), (32, 8), (8, 2), (2, 1), (1, 2),
+                   (32, 128), (50, 16), (64, 64)]:
+        for aa in (True, False):
+            plan = ops.ResamplePlan(a, b, aa, "cpu")
+            if a == b:
+                assert plan.taps == 1 and np.array_equal(plan.host[0], np.arange(a))
+                continue
+            st, wt = resize_np.triangle_spans(a, b, aa)
+            assert np.array_equal(plan.host[0], st) and np.array_equal(plan.host[1], wt), (a, b, aa)
+            # transpose tables reproduce the dense matrix transposed
+            mat = resize_np.resize_matrix(a, b, aa)
+            t_st, t_wt = plan.host[2], plan.host[3]
+            back = np.zeros((a, b), np.float32)
+            for i in range(a):
+                for k in range(t_wt.shape[1]):
+                    if t_wt[i, k] != 0:
+                        back[i, t_st[i] + k] += t_wt[i, k]
+            assert np.array_equal(back, mat.T)
+    assert ops.resize_extent(50, 0.3) == 16 and ops.resize_extent(256, 0.7) == 180 and ops.resize_extent(1, 0.25) == 1
+
+
+def test_builders_match_reference_param_totals_and_names():
+    from b200unet import builders as B
+    from b200unet.keras import clear_session
+    for depth, total in {1: 520_003, 2: 2_144_451, 3: 8_637_379, 4: 34_599_363, 5: 138_427_843}.items():
+        clear_session()
+        model, info = B.build_super_resolution_unet(0.5, depth_override=depth, input_size=256)
+        assert model.count_params() == total
+        assert model.name == f"U-Net_SR_scale0.50_depth{depth}" and info["depth"] == depth
+    names = [ly.name for ly in model.layers]
+    assert names[:5] == ["low_res_input", "conv2d", "layer_normalization", "activation", "conv2d_1"]
+    assert {"enc_down", "dec_up", "residual_rgb", "enhanced_rgb"} <= set(names)
+    clear_session()
+    model, info = B.build_super_resolution_unet(0.7, input_size=256)     # adaptive rule: depth 7 at scale 0.7
+    assert info["depth"] == 7
+    lines = []
+    model.summary(print_fn=lines.append)
+    assert any("Total params" in ln for ln in lines)
+
+
+def test_custom_layers_interface():
+    from b200unet.shared import custom_layers as CL
+    assert CL.ClipAdd is CL.ClippedResidualAdd
+    assert {"resize>ResizeByScale", "resize>ResizeToMatch", "utils>ClippedResidualAdd"} <= set(CL.get_custom_objects())
+    lay = CL.ResizeByScale(0.7, name="enc_down")
+    assert lay.get_config()["scale"] == 0.7 and lay.get_config()["antialias"] is True
+    with pytest.raises(ValueError):
+        CL.custom_depth_from_scale(1.5)
+    assert CL.custom_depth_from_scale(0.5, base_resolution=256) == 4
+    assert CL.infer_depth_from_scale(0.3) == 2 and CL.estimate_bottleneck_size(256, 0.7, 3) == 88
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from b200unet import builders as B
+    from b200unet._ffi import B200Error
+    from b200unet.keras import clear_session
+    clear_session()
+    model, _ = B.build_super_resolution_unet(0.5, depth_override=1, input_size=16)
+    with pytest.raises(B200Error):
+        model(np.zeros((1, 16, 16, 3), np.float32))
