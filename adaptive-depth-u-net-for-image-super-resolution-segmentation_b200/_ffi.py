@@ -52,6 +52,7 @@ SIGNATURES = {
     "b200_device_info": (_i, [C.POINTER(_i)] * 3),
     "b200_launch_count": (C.c_longlong, [_i]),
     "b200_conv2d_fprop": (_i, [_TP, _FP, _vp, _TP, _i, _i, _vp]),
+    "b200_conv2d_ln_fprop": (_i, [_TP, _FP, _vp, _vp, _vp, _f, _i, _TP, _TP, _vp, _vp, _i, _vp]),
     "b200_conv2d_dgrad": (_i, [_TP, _FP, _TP, _i, _i, _vp]),
     "b200_conv2d_wgrad_workspace": (_sz, [_TP, _TP, _i, _i, _i]),
     "b200_conv2d_wgrad": (_i, [_TP, _TP, _i, _i, _vp, _vp, _sz, _i, _vp]),

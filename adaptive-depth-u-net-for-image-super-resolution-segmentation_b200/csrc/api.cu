@@ -35,7 +35,14 @@ int conv_simt_fprop(const b200_tensor*, const b200_filter*, const float*, const 
 int conv_simt_wgrad(const b200_tensor*, const b200_tensor*, int, float*, cudaStream_t);
 int filter_pack(const void*, void*, int, int, int, int, cudaStream_t);
 bool conv_tc_supported(const b200_tensor*, int, int, const b200_tensor*, int);
-int conv_tc_launch(const b200_tensor*, const void*, int, int, int, const float*, const b200_tensor*, int, int, cudaStream_t);
+struct ConvLnArgs {
+  const float* gamma; const float* beta; float eps; int relu;
+  const b200_tensor* z;
+  float* mean; float* rstd;
+};
+bool conv_tc_ln_supported(int cout);
+int conv_tc_launch(const b200_tensor*, const void*, int, int, int, int, const float*, const b200_tensor*, int, int, cudaStream_t,
+                   const ConvLnArgs* ln = nullptr);
 int umma_probe(const void*, int, const void*, int, int, int, int, float*, cudaStream_t);
 int umma_rate(int, int, int, long long*, int, cudaStream_t);
 bool stem_supported(const b200_tensor*, const b200_tensor*, int);
@@ -119,17 +126,39 @@ int b200_conv2d_fprop(const b200_tensor* x, const b200_filter* f, const float* b
   B200_REQUIRE(x->c == f->cin && y->c == f->cout && x->n == y->n && x->h == y->h && x->w == y->w, B200_ERR_BAD_ARG,
                "conv2d_fprop: shapes x[%d,%d,%d,%d] y[%d,%d,%d,%d] filter cin=%d cout=%d disagree", x->n, x->h, x->w,
                x->c, y->n, y->h, y->w, y->c, f->cin, f->cout);
-  const bool tc_ok = f->ohwi && f->kh == 3 && f->kw == 3 && f->dtype == B200_BF16 &&
+  const bool tc_ok = f->kh == 3 && f->kw == 3 && f->dtype == B200_BF16 &&
                      (act == B200_ACT_NONE || act == B200_ACT_RELU) && conv_tc_supported(x, f->cin, f->cout, y, 3);
   if (algo == B200_ALGO_TCGEN05 || (algo == B200_ALGO_AUTO && tc_ok)) {
     B200_REQUIRE(tc_ok, B200_ERR_UNSUPPORTED, "conv2d_fprop: tcgen05 path does not support this shape/dtype");
-    return conv_tc_launch(x, f->ohwi, f->cin, f->cout, 0, bias, y, act, 0, ST(stream));
+    return conv_tc_launch(x, f->hwio, f->cin, f->cout, 0, 1, bias, y, act, 0, ST(stream));
   }
   if (algo == B200_ALGO_AUTO && f->dtype == x->dtype && f->kh == f->kw) {
     if (stem_supported(x, y, f->kh) && act != B200_ACT_SIGMOID) return stem_fprop(x, f->hwio, bias, y, act, ST(stream));
     if (head_supported(x, y, f->kh)) return head_fprop(x, f->hwio, bias, y, act, ST(stream));
   }
   return conv_simt_fprop(x, f, bias, y, act, 0, false, ST(stream));
+}
+
+int b200_conv2d_ln_fprop(const b200_tensor* x, const b200_filter* f, const float* bias, const float* gamma,
+                         const float* beta, float eps, int relu, const b200_tensor* z, const b200_tensor* y, float* mean,
+                         float* rstd, int algo, void* stream) {
+  REQ_T(x, "x"); REQ_T(y, "y");
+  B200_REQUIRE(f && f->hwio && gamma && beta && mean && rstd, B200_ERR_BAD_ARG, "conv2d_ln_fprop: NULL argument");
+  B200_REQUIRE(x->c == f->cin && y->c == f->cout && x->n == y->n && x->h == y->h && x->w == y->w, B200_ERR_BAD_ARG,
+               "conv2d_ln_fprop: shapes disagree with filter cin=%d cout=%d", f->cin, f->cout);
+  const bool have_z = z && z->data;
+  if (have_z) B200_REQUIRE(same_shape(z, y) && z->dtype == y->dtype, B200_ERR_BAD_ARG, "conv2d_ln_fprop: z/y mismatch");
+  const bool fused = f->kh == 3 && f->kw == 3 && f->dtype == B200_BF16 && conv_tc_supported(x, f->cin, f->cout, y, 3) &&
+                     conv_tc_ln_supported(f->cout) && algo != B200_ALGO_SIMT;
+  if (fused) {
+    ConvLnArgs ln{gamma, beta, eps, relu, have_z ? z : nullptr, mean, rstd};
+    return conv_tc_launch(x, f->hwio, f->cin, f->cout, 0, 1, bias, y, B200_ACT_NONE, 0, ST(stream), &ln);
+  }
+  // composition: convolution into z (or into y when the caller keeps no z), then the stand-alone LayerNorm
+  const b200_tensor* zz = have_z ? z : y;
+  int rc = b200_conv2d_fprop(x, f, bias, zz, B200_ACT_NONE, algo, stream);
+  if (rc) return rc;
+  return layernorm_fwd(zz, gamma, beta, eps, relu, y, mean, rstd, ST(stream));
 }
 
 int b200_conv2d_dgrad(const b200_tensor* dy, const b200_filter* f, const b200_tensor* dx, int accumulate, int algo,
@@ -143,7 +172,7 @@ int b200_conv2d_dgrad(const b200_tensor* dy, const b200_filter* f, const b200_te
   const bool tc_ok = f->kh == 3 && f->kw == 3 && f->dtype == B200_BF16 && conv_tc_supported(dy, f->cout, f->cin, dx, 3);
   if (algo == B200_ALGO_TCGEN05 || (algo == B200_ALGO_AUTO && tc_ok)) {
     B200_REQUIRE(tc_ok, B200_ERR_UNSUPPORTED, "conv2d_dgrad: tcgen05 path does not support this shape/dtype");
-    return conv_tc_launch(dy, f->hwio, f->cout, f->cin, 1, nullptr, dx, B200_ACT_NONE, accumulate, ST(stream));
+    return conv_tc_launch(dy, f->hwio, f->cout, f->cin, 1, 0, nullptr, dx, B200_ACT_NONE, accumulate, ST(stream));
   }
   if (algo == B200_ALGO_AUTO && f->dtype == dx->dtype && f->kh == f->kw && head_supported(dx, dy, f->kh))
     return head_dgrad(dy, f->hwio, dx, accumulate, ST(stream));

@@ -21,6 +21,7 @@
 // Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (one thread) + TMEM owner,
 // warps 2..5 = epilogue (TMEM -> registers -> bias/activation -> bf16 -> global).
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "ptx.cuh"
@@ -91,11 +92,24 @@ constexpr int SMEM_LIMIT = 232448;                // 227 KB
 struct ConvTcParams {
   int N, H, W, Cout, KB, BN, n_tiles, tiles_h, tiles_w, total_items;
   int tap_rev, live_mask, resident, nsw, nsb, act, accumulate;
+  int debug;  // B200_CONV_DEBUG: 1 = epilogue only waits/releases, 2 = epilogue without global stores (profiling aid)
+  int b_mn;   // 1: B operand is MN-major (fprop reads the Keras HWIO kernel [tap][cin][cout] as is); 0: K-major (dgrad)
+  int Kc;     // K total (input channels of this convolution)
   // small images (H <= 7) are stacked: one tile holds `nb` images, each `srows` = H+2 window rows
   int nb, srows, win_bytes;
   const float* bias;
   __nv_bfloat16* y;
   long long ysn, ysh, ysw;
+  // fused LayerNormalization(axis=-1) [+ReLU] epilogue (single N tile only): z = bf16(conv + bias) is
+  // stored for the backward pass, y = act(LN(z)) for the next layer, mean/rstd per pixel in fp32
+  int ln, ln_relu;
+  float ln_eps;
+  const float* gamma;
+  const float* beta;
+  __nv_bfloat16* z;          // may be NULL (inference)
+  long long zsn, zsh, zsw;
+  float* mean;
+  float* rstd;
 };
 
 // D[tmem] (+)= A * B^T with the descriptors given as (lo, hi) words: the hi words are loop
@@ -110,12 +124,79 @@ __device__ __forceinline__ void umma_lohi(uint32_t d_tmem, uint32_t a_lo, uint32
       : "memory");
 }
 
+// One {BN x 64} weight tile for (64-channel K block kb, tap, N tile j) into shared memory.
+//   K-major (dgrad):  matrix rows = tap*Cout + n, cols = k      -> one box {64 k, BN rows}
+//   MN-major (fprop): matrix rows = tap*K + k,   cols = n (HWIO) -> BN/64 boxes {64 n, 64 k rows}, 8 KB apart
+__device__ __forceinline__ void load_weight_tile(const ConvTcParams& p, const CUtensorMap* tm_b, uint32_t dst,
+                                                 uint32_t bar, int kb, int tap, int j) {
+  if (p.b_mn) {
+    for (int a = 0; a < p.BN / 64; ++a)
+      tma_load_2d(dst + a * 8192, tm_b, bar, j * p.BN + a * 64, tap * p.Kc + kb * 64);
+  } else {
+    tma_load_2d(dst, tm_b, bar, kb * 64, (p.tap_rev ? 8 - tap : tap) * p.Cout + j * p.BN);
+  }
+}
+
 __device__ __forceinline__ void decode_item(const ConvTcParams& p, int item, int& j, int& tw, int& th, int& n) {
   j = item % p.n_tiles;
   int t = item / p.n_tiles;
   tw = t % p.tiles_w; t /= p.tiles_w;
   th = t % p.tiles_h;
   n = (t / p.tiles_h) * p.nb;     // first image of the tile
+}
+
+__device__ __forceinline__ float bf16_round(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
+
+// LayerNorm epilogue for one pixel (one thread) with all BN_T channels held in registers.
+//   z = bf16(acc + bias)            (what keras stores under the mixed policy; statistics are taken on it)
+//   y = act((z - mean) * rstd * gamma + beta)
+template <int BN_T>
+__device__ __forceinline__ void epilogue_layernorm(const ConvTcParams& p, uint32_t taddr, const float* s_bias,
+                                                   bool valid, __nv_bfloat16* ydst, __nv_bfloat16* zdst,
+                                                   long long pix) {
+  float zf[BN_T];
+  float sum = 0.f;
+#pragma unroll
+  for (int c0 = 0; c0 < BN_T; c0 += 32) {
+    uint32_t v[32];
+    tmem_ld32(taddr + c0, v);
+    tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      const float t = bf16_round(__uint_as_float(v[i]) + s_bias[c0 + i]);
+      zf[c0 + i] = t;
+      sum += t;
+    }
+  }
+  const float mean = sum * (1.f / BN_T);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < BN_T; ++i) { const float d = zf[i] - mean; q += d * d; }
+  const float rstd = rsqrtf(q * (1.f / BN_T) + p.ln_eps);
+  if (!valid) return;
+  const float* gam = s_bias + p.Cout;
+  const float* bet = s_bias + 2 * p.Cout;
+  if (zdst) {
+#pragma unroll
+    for (int g = 0; g < BN_T / 8; ++g) {
+      float o[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o[i] = zf[g * 8 + i];
+      Vec8<__nv_bfloat16>::store(zdst + g * 8, o);
+    }
+  }
+#pragma unroll
+  for (int g = 0; g < BN_T / 8; ++g) {
+    float o[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float t = (zf[g * 8 + i] - mean) * rstd * gam[g * 8 + i] + bet[g * 8 + i];
+      o[i] = p.ln_relu ? fmaxf(t, 0.f) : t;
+    }
+    Vec8<__nv_bfloat16>::store(ydst + g * 8, o);
+  }
+  p.mean[pix] = mean;
+  p.rstd[pix] = rstd;
 }
 
 __global__ void __launch_bounds__(NTHREADS, 1)
@@ -141,7 +222,10 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
     for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&bar_tmem_full[i]), 1); mbar_init(smem_u32(&bar_tmem_empty[i]), 4); }
     fence_barrier_init();
   }
-  for (int i = threadIdx.x; i < p.Cout; i += NTHREADS) s_bias[i] = p.bias ? p.bias[i] : 0.f;
+  for (int i = threadIdx.x; i < p.Cout; i += NTHREADS) {
+    s_bias[i] = p.bias ? p.bias[i] : 0.f;
+    if (p.ln) { s_bias[p.Cout + i] = p.gamma[i]; s_bias[2 * p.Cout + i] = p.beta[i]; }
+  }
   if (warp == 0 && lane == 0) { prefetch_tmap(&tm_x); prefetch_tmap(&tm_b); }
   if (warp == 1) { tmem_alloc(smem_u32(&tmem_base_smem), tmem_cols); tmem_relinquish(); }
   tc_fence_before();
@@ -158,9 +242,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
           for (int tap = 0; tap < 9; ++tap) {
             if (!((p.live_mask >> tap) & 1)) continue;
             const int slot = kb * 9 + tap;
-            const int trow = (p.tap_rev ? 8 - tap : tap) * p.Cout;
             mbar_arrive_expect_tx(smem_u32(&bar_full_b[slot]), wt_bytes);
-            tma_load_2d(wt0 + slot * wt_bytes, &tm_b, smem_u32(&bar_full_b[slot]), kb * 64, trow);
+            load_weight_tile(p, &tm_b, wt0 + slot * wt_bytes, smem_u32(&bar_full_b[slot]), kb, tap, 0);
           }
       }
       for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
@@ -175,10 +258,9 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
           if (!p.resident) {
             for (int tap = 0; tap < 9; ++tap) {
               if (!((p.live_mask >> tap) & 1)) continue;
-              const int trow = (p.tap_rev ? 8 - tap : tap) * p.Cout + j * p.BN;
               mbar_wait(smem_u32(&bar_empty_b[sb]), pb ^ 1);
               mbar_arrive_expect_tx(smem_u32(&bar_full_b[sb]), wt_bytes);
-              tma_load_2d(wt0 + sb * wt_bytes, &tm_b, smem_u32(&bar_full_b[sb]), kb * 64, trow);
+              load_weight_tile(p, &tm_b, wt0 + sb * wt_bytes, smem_u32(&bar_full_b[sb]), kb, tap, j);
               if (++sb == p.nsb) { sb = 0; pb ^= 1; }
             }
           }
@@ -191,9 +273,13 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
     // All 32 lanes run the loop so that control flow stays warp-uniform (descriptor words are then
     // computed on the uniform datapath); one elected lane issues the MMAs and the commits.
     {
-      const uint32_t idesc = idesc_bf16(128, p.BN, 0, 0);
+      const uint32_t idesc = idesc_bf16(128, p.BN, 0, p.b_mn);
       const uint32_t a_hi = (uint32_t)(smem_desc_sw128(0, 0, WIN_PITCH) >> 32);
       const uint32_t b_hi = (uint32_t)(smem_desc_sw128(0, 0, 1024) >> 32);
+      // per-K-step (16 channels) advance of the B descriptor and its LBO field:
+      //   K-major: +32 B inside the 128-byte swizzle row; MN-major: +16 rows of 128 B, 64-column atoms 8 KB apart
+      const uint32_t b_ks = p.b_mn ? (2048u >> 4) : 2u;
+      const uint32_t b_lbo = p.b_mn ? ((8192u >> 4) << 16) : 0u;
       const uint32_t wt_step = wt_bytes >> 4;
       const bool all_live = p.live_mask == 0x1FF;
       int sw = 0, pw = 0, sb = 0, pb = 0, as = 0, pa = 0;
@@ -214,7 +300,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
           const uint32_t a_lo0 = (win0 + sw * WIN_STAGE) >> 4;
           if (p.resident && all_live) {
             // hot path of the full-resolution layers: 36 MMAs, descriptor words by 32-bit adds only
-            const uint32_t b_lo0 = (wt0 >> 4) + (uint32_t)(kb * 9) * wt_step;
+            const uint32_t b_lo0 = ((wt0 >> 4) | b_lbo) + (uint32_t)(kb * 9) * wt_step;
             if (elect_one()) {
 #pragma unroll
               for (int tap = 0; tap < 9; ++tap) {
@@ -222,7 +308,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
                 const uint32_t b_lo = b_lo0 + (uint32_t)tap * wt_step;
 #pragma unroll
                 for (int ks = 0; ks < 4; ++ks)
-                  umma_lohi(d_tmem, a_lo + ks * 2, a_hi, b_lo + ks * 2, b_hi, idesc, (tap | ks) ? 1u : accumulate);
+                  umma_lohi(d_tmem, a_lo + ks * 2, a_hi, b_lo + ks * b_ks, b_hi, idesc, (tap | ks) ? 1u : accumulate);
               }
             }
             accumulate = 1;
@@ -233,17 +319,17 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
               if (!((p.live_mask >> tap) & 1)) continue;
               uint32_t b_lo;
               if (p.resident) {
-                b_lo = (wt0 >> 4) + (uint32_t)(kb * 9 + tap) * wt_step;
+                b_lo = ((wt0 >> 4) | b_lbo) + (uint32_t)(kb * 9 + tap) * wt_step;
               } else {
                 mbar_wait(smem_u32(&bar_full_b[sb]), pb);
                 tc_fence_after();
-                b_lo = (wt0 >> 4) + (uint32_t)sb * wt_step;
+                b_lo = ((wt0 >> 4) | b_lbo) + (uint32_t)sb * wt_step;
               }
               const uint32_t a_lo = a_lo0 + (uint32_t)((tap / 3) * WIN_W + (tap % 3)) * 8u;
               if (elect_one()) {
 #pragma unroll
                 for (int ks = 0; ks < 4; ++ks)
-                  umma_lohi(d_tmem, a_lo + ks * 2, a_hi, b_lo + ks * 2, b_hi, idesc, ks ? 1u : accumulate);
+                  umma_lohi(d_tmem, a_lo + ks * 2, a_hi, b_lo + ks * b_ks, b_hi, idesc, ks ? 1u : accumulate);
                 if (!p.resident) umma_commit(smem_u32(&bar_empty_b[sb]));
               }
               accumulate = 1;
@@ -278,6 +364,13 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
       mbar_wait(smem_u32(&bar_tmem_full[as]), pa);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * p.BN);
+      if (p.debug == 1) {
+      } else if (p.ln) {
+        const long long pix = ((long long)img * p.H + oh) * p.W + ow;
+        __nv_bfloat16* zdst = p.z ? p.z + (long long)img * p.zsn + (long long)oh * p.zsh + (long long)ow * p.zsw : nullptr;
+        if (p.BN == 64) epilogue_layernorm<64>(p, taddr, s_bias, valid, dst, zdst, pix);
+        else epilogue_layernorm<128>(p, taddr, s_bias, valid, dst, zdst, pix);
+      } else
       for (int c0 = 0; c0 < p.BN; c0 += 32) {
         uint32_t v[32];
         tmem_ld32(taddr + c0, v);
@@ -302,7 +395,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
 #pragma unroll
               for (int i = 0; i < 8; ++i) o[i] += e[i];
             }
-            Vec8<__nv_bfloat16>::store(d8, o);
+            if (p.debug != 2 || o[0] == 12345.678f) Vec8<__nv_bfloat16>::store(d8, o);
           }
         }
       }
@@ -401,10 +494,14 @@ umma_rate_kernel(int n, int iters, int a_stride_bytes, long long* __restrict__ c
     const uint32_t idesc = idesc_bf16(128, n, 0, 0);
     const long long t0 = clock64();
     for (int it = 0; it < iters; ++it) {
+      // a_stride 1280 = the convolution's access pattern: per tap a shifted window start and its own B tile
+      const int tap = a_stride_bytes == 1280 ? it % 9 : 0;
+      const uint32_t a_off = (uint32_t)((tap / 3) * 10 + tap % 3) * 128u;
+      const uint32_t b_off = a_stride_bytes == 1280 && n == 64 ? (uint32_t)(tap % 4) * 8192u : 0u;
 #pragma unroll
       for (int ks = 0; ks < 4; ++ks)
-        umma_bf16(tmem_base + (uint32_t)((it & 1) * n), smem_desc_sw128(a_smem + ks * 32, 0, a_stride_bytes),
-                  smem_desc_sw128(b_smem + ks * 32, 0, 1024), idesc, 1);
+        umma_bf16(tmem_base + (uint32_t)((it & 1) * n), smem_desc_sw128(a_smem + a_off + ks * 32, 0, a_stride_bytes),
+                  smem_desc_sw128(b_smem + b_off + ks * 32, 0, 1024), idesc, 1);
     }
     umma_commit(smem_u32(&bar_mma));
     mbar_wait(smem_u32(&bar_mma), 0);
@@ -442,9 +539,19 @@ static bool flatten_1x1(const b200_tensor* t, b200_tensor* out) {
   return true;
 }
 
-// x: input activations (C = K total), wmat: [9][cout][cin] K-major bf16, y: output (C = cout)
-int conv_tc_launch(const b200_tensor* x_in, const void* wmat, int cin, int cout, int tap_rev, const float* bias,
-                   const b200_tensor* y_in, int act, int accumulate, cudaStream_t st) {
+// x: input activations (C = K total); y: output (C = cout).
+//   b_mn = 1: wmat is the Keras HWIO kernel [9][cin][cout] (fprop, B read MN-major)
+//   b_mn = 0: wmat is [9][cout][cin] K-major (dgrad passes the HWIO kernel with cin/cout swapped + tap_rev)
+struct ConvLnArgs {
+  const float* gamma; const float* beta; float eps; int relu;
+  const b200_tensor* z;   // may be NULL
+  float* mean; float* rstd;
+};
+
+bool conv_tc_ln_supported(int cout) { return cout == 64 || cout == 128; }
+
+int conv_tc_launch(const b200_tensor* x_in, const void* wmat, int cin, int cout, int tap_rev, int b_mn, const float* bias,
+                   const b200_tensor* y_in, int act, int accumulate, cudaStream_t st, const ConvLnArgs* ln = nullptr) {
   B200_REQUIRE(conv_tc_supported(x_in, cin, cout, y_in, 3), B200_ERR_UNSUPPORTED,
                "conv3x3 tcgen05: unsupported shape cin=%d cout=%d (need bf16, multiples of 64, 16-byte aligned)", cin,
                cout);
@@ -457,7 +564,12 @@ int conv_tc_launch(const b200_tensor* x_in, const void* wmat, int cin, int cout,
     const bool dead = (x_in->h == 1 && t / 3 != 1) || (x_in->w == 1 && t % 3 != 1);
     if (!dead) live_mask |= 1 << t;
   }
-  if (flatten_1x1(x_in, &xf) && flatten_1x1(y_in, &yf)) { x = &xf; y = &yf; }   // live_mask stays centre-only
+  b200_tensor zf;
+  const b200_tensor* z = ln ? ln->z : nullptr;
+  if (flatten_1x1(x_in, &xf) && flatten_1x1(y_in, &yf)) {   // live_mask stays centre-only
+    x = &xf; y = &yf;
+    if (z && flatten_1x1(z, &zf)) z = &zf;
+  }
   ConvTcParams p;
   p.N = y->n; p.H = y->h; p.W = y->w; p.Cout = cout;
   p.KB = cin / 64;
@@ -479,9 +591,12 @@ int conv_tc_launch(const b200_tensor* x_in, const void* wmat, int cin, int cout,
   const int groups = (p.N + p.nb - 1) / p.nb;
   p.total_items = groups * p.tiles_h * p.tiles_w * p.n_tiles;
   p.tap_rev = tap_rev;
+  { const char* dbg = getenv("B200_CONV_DEBUG"); p.debug = dbg ? atoi(dbg) : 0; }
+  p.b_mn = b_mn;
+  p.Kc = cin;
   p.live_mask = live_mask;
   const int wt_bytes = p.BN * 128;
-  const int bias_bytes = ((cout * 4 + 1023) / 1024) * 1024;
+  const int bias_bytes = ((cout * 4 * (ln ? 3 : 1) + 1023) / 1024) * 1024;
   const int budget = SMEM_LIMIT - 1024 /*align slack*/ - 1024 /*static*/ - bias_bytes;
   const int all_w = 9 * p.KB * wt_bytes;
   p.resident = (p.n_tiles == 1 && 9 * p.KB <= MAX_WSLOTS && budget - all_w >= 2 * WIN_STAGE) ? 1 : 0;
@@ -497,11 +612,22 @@ int conv_tc_launch(const b200_tensor* x_in, const void* wmat, int cin, int cout,
   p.act = act; p.accumulate = accumulate; p.bias = bias;
   p.y = reinterpret_cast<__nv_bfloat16*>(y->data);
   p.ysn = y->stride_n; p.ysh = y->stride_h; p.ysw = y->stride_w;
+  p.ln = ln ? 1 : 0;
+  p.z = nullptr; p.zsn = p.zsh = p.zsw = 0;
+  if (ln) {
+    B200_REQUIRE(p.n_tiles == 1 && conv_tc_ln_supported(cout), B200_ERR_UNSUPPORTED,
+                 "conv3x3+LayerNorm tcgen05: Cout=%d needs a single N tile (64 or 128)", cout);
+    p.ln_relu = ln->relu; p.ln_eps = ln->eps; p.gamma = ln->gamma; p.beta = ln->beta; p.mean = ln->mean; p.rstd = ln->rstd;
+    if (z) {
+      p.z = reinterpret_cast<__nv_bfloat16*>(z->data);
+      p.zsn = z->stride_n; p.zsh = z->stride_h; p.zsw = z->stride_w;
+    }
+  }
 
   CUtensorMap tm_x, tm_b;
   int rc = make_act_tmap(&tm_x, x, WIN_W, box_h, box_n);
   if (rc) return rc;
-  rc = make_mat_tmap(&tm_b, wmat, 9LL * cout, cin, p.BN);
+  rc = b_mn ? make_mat_tmap(&tm_b, wmat, 9LL * cin, cout, 64) : make_mat_tmap(&tm_b, wmat, 9LL * cout, cin, p.BN);
   if (rc) return rc;
 
   const size_t smem = 1024 + (size_t)p.nsw * WIN_STAGE + (size_t)p.nsb * wt_bytes + bias_bytes;

@@ -230,6 +230,37 @@ bias_act_bwd_kernel(TView dy, TView y, int act, TView dz, float* __restrict__ db
     for (int i = threadIdx.x; i < C; i += NT) atomicAdd(dbias + i, s_acc[i]);
 }
 
+// narrow tensors (C <= 4: the RGB / mask heads): one thread per pixel, warp-reduced channel sums
+template <typename T, int C>
+__global__ void __launch_bounds__(NT)
+bias_act_bwd_narrow_kernel(TView dy, TView y, int act, TView dz, float* __restrict__ dbias, long long npix) {
+  const T* dyp = reinterpret_cast<const T*>(dy.data);
+  const T* yp = reinterpret_cast<const T*>(y.data);
+  T* dzp = reinterpret_cast<T*>(dz.data);
+  float acc[C];
+#pragma unroll
+  for (int c = 0; c < C; ++c) acc[c] = 0.f;
+  for (long long p = (long long)blockIdx.x * NT + threadIdx.x; p < npix; p += (long long)gridDim.x * NT) {
+    const long long o1 = pix_offset_flat(dy, p), o2 = pix_offset_flat(y, p), o3 = pix_offset_flat(dz, p);
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      float d = ldf(dyp + o1 + c);
+      const float yv = ldf(yp + o2 + c);
+      if (act == B200_ACT_RELU) d = yv > 0.f ? d : 0.f;
+      else if (act == B200_ACT_SIGMOID) d = d * yv * (1.f - yv);
+      stf(dzp + o3 + c, d);
+      acc[c] += d;
+    }
+  }
+  if (dbias) {
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      const float v = warp_sum(acc[c]);
+      if ((threadIdx.x & 31) == 0) atomicAdd(dbias + c, v);
+    }
+  }
+}
+
 // vectorised variant: C % 8 == 0, C/8 a power of two <= NT
 template <typename T>
 __global__ void __launch_bounds__(NT)
@@ -444,7 +475,11 @@ int bias_act_bwd(const b200_tensor* dy, const b200_tensor* y, int act, const b20
   const bool vec = C % 8 == 0 && is_pow2(C / 8) && C / 8 <= NT && vec_aligned(dy, 8) && vec_aligned(y, 8) &&
                    vec_aligned(dz, 8);
   B200_DISPATCH_DTYPE(y->dtype, T, {
-    if (vec) {
+    if (C == 1 || C == 3) {
+      const int grid = grid_for(npix, NT);
+      if (C == 1) bias_act_bwd_narrow_kernel<T, 1><<<grid, NT, 0, st>>>(dyv, yv, act, dzv, dbias, npix);
+      else bias_act_bwd_narrow_kernel<T, 3><<<grid, NT, 0, st>>>(dyv, yv, act, dzv, dbias, npix);
+    } else if (vec) {
       long long blocks = (npix + (NT / (C / 8)) - 1) / (NT / (C / 8));
       long long cap = 4LL * sm_count();
       int grid = (int)(blocks < cap ? (blocks < 1 ? 1 : blocks) : cap);

@@ -177,19 +177,34 @@ wgrad3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
   if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
 }
 
+// dw[i] = sum over splits of partial[s][i].  A block owns 64 float4 outputs; its 256 threads are
+// 4 split-groups x 64 outputs so that the split loop runs 4-wide, combined through shared memory.
 __global__ void __launch_bounds__(256)
 wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw, long long count, int splits,
                     int live_mask, long long per_tap) {
+  __shared__ float4 s_part[4][64];
   const long long n4 = count / 4;
-  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n4; i += (long long)gridDim.x * 256) {
+  const int lane = threadIdx.x % 64, grp = threadIdx.x / 64;
+  for (long long base = (long long)blockIdx.x * 64; base < n4; base += (long long)gridDim.x * 64) {
+    const long long i = base + lane;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    const int tap = (int)(i * 4 / per_tap);
-    const int nsum = ((live_mask >> tap) & 1) ? splits : 0;   // taps that only ever see padding are exactly zero
-    for (int s = 0; s < nsum; ++s) {
-      const float4 v = reinterpret_cast<const float4*>(partial + (long long)s * count)[i];
-      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    if (i < n4) {
+      const int tap = (int)(i * 4 / per_tap);
+      const int nsum = ((live_mask >> tap) & 1) ? splits : 0;   // taps that only ever see padding are exactly zero
+      for (int s = grp; s < nsum; s += 4) {
+        const float4 v = reinterpret_cast<const float4*>(partial + (long long)s * count)[i];
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+      }
     }
-    reinterpret_cast<float4*>(dw)[i] = acc;
+    s_part[grp][lane] = acc;
+    __syncthreads();
+    if (grp == 0 && i < n4) {
+      float4 r = s_part[0][lane];
+#pragma unroll
+      for (int g = 1; g < 4; ++g) { const float4 v = s_part[g][lane]; r.x += v.x; r.y += v.y; r.z += v.z; r.w += v.w; }
+      reinterpret_cast<float4*>(dw)[i] = r;
+    }
+    __syncthreads();
   }
 }
 
@@ -294,8 +309,8 @@ int wgrad_tc_launch(const b200_tensor* x, const b200_tensor* dy, float* dw, void
   int rc2 = check_launch("wgrad3x3_tc_kernel");
   if (rc2) return rc2;
   const long long count = 9LL * p.Cin * p.Cout;
-  long long blocks = (count / 4 + 255) / 256;
-  if (blocks > 4LL * sm_count()) blocks = 4LL * sm_count();
+  long long blocks = (count / 4 + 63) / 64;
+  if (blocks > 8LL * sm_count()) blocks = 8LL * sm_count();
   wgrad_reduce_kernel<<<(int)blocks, 256, 0, st>>>(p.partial, dw, count, p.splits, g.live_mask, (long long)p.Cin * p.Cout);  // counted by check_launch
   return check_launch("wgrad_reduce_kernel");
 }

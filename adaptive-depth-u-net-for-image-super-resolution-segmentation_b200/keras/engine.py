@@ -231,23 +231,35 @@ class Plan:
                 list.append(inner, fn)
 
         S = self.steps = _Tagged()
+        for op in self.ops:   # Conv2D whose only consumer is a LayerNormalization: run as one fused call
+            if op.kind == "ln" and op.conv_src is not None and op.conv_src.output is op.inputs[0] \
+                    and op.conv_src.layer.kernel_size == (3, 3):
+                op.conv_src.fused_into_ln = True
         for op in self.ops:
             k = op.kind
             self._cur_tag = k + (":tc" if k == "conv" and self.is_tc(op) else (":simt" if k == "conv" else ""))
             if k == "cast_input":
                 S.append(lambda a=op.inputs[0], b=op.output: ops.copy_tensor(a.buf, b.buf))
             elif k == "conv":
+                if getattr(op, "fused_into_ln", False):
+                    continue     # executed by the following LayerNormalization op (one fused kernel)
                 filt, bias = m._filter(op.layer), m._param(op.layer, "bias")
-                if filt.ohwi is not None:
-                    self.pre_steps.append(filt.repack)
                 S.append(lambda x=op.inputs[0], f=filt, b=bias, y=op.output, o=op:
                          ops.conv2d_fprop(x.buf, f, b, y.buf, o.act))
             elif k == "ln":
                 g, b = m._param(op.layer, "gamma"), m._param(op.layer, "beta")
                 op.mean = torch.empty(npix(op.output), dtype=torch.float32, device=self.dev)
                 op.rstd = torch.empty_like(op.mean)
-                S.append(lambda z=op.inputs[0], y=op.output, o=op, g=g, b=b:
-                         ops.layernorm_fwd(z.buf, g, b, o.layer.epsilon, o.relu, y.buf, o.mean, o.rstd))
+                cs = op.conv_src
+                if cs is not None and cs.output is op.inputs[0] and cs.layer.kernel_size == (3, 3):
+                    # Conv2D -> LayerNormalization -> ReLU: one call (fused tcgen05 epilogue for Cout 64/128)
+                    self._cur_tag = "conv+ln" + (":tc" if self.is_tc(cs) else ":simt")
+                    S.append(lambda x=cs.inputs[0], f=m._filter(cs.layer), cb=m._param(cs.layer, "bias"),
+                             z=op.inputs[0], y=op.output, o=op, g=g, b=b:
+                             ops.conv2d_ln_fprop(x.buf, f, cb, g, b, o.layer.epsilon, o.relu, z.buf, y.buf, o.mean, o.rstd))
+                else:
+                    S.append(lambda z=op.inputs[0], y=op.output, o=op, g=g, b=b:
+                             ops.layernorm_fwd(z.buf, g, b, o.layer.epsilon, o.relu, y.buf, o.mean, o.rstd))
             elif k == "bn":
                 g, b = m._param(op.layer, "gamma"), m._param(op.layer, "beta")
                 mm, mv = m._param(op.layer, "moving_mean"), m._param(op.layer, "moving_variance")

@@ -182,11 +182,9 @@ class Model:
         if ly.name not in self._filters:
             hwio = self._shadow(ly, "kernel")
             kh, kw, cin, cout = hwio.shape
-            packed = (hwio.dtype == torch.bfloat16 and (kh, kw) == (3, 3) and cin % 64 == 0 and cout % 64 == 0)
-            f = ops.ConvFilter.__new__(ops.ConvFilter)
+            f = ops.ConvFilter.__new__(ops.ConvFilter)   # a view of the shadow buffer: no copy, no repack
             f.hwio, f.kh, f.kw, f.cin, f.cout = hwio, kh, kw, cin, cout
-            f.ohwi = torch.empty((kh, kw, cout, cin), dtype=hwio.dtype, device=hwio.device) if packed else None
-            f.repack()
+            f.ohwi = None
             self._filters[ly.name] = f
         return self._filters[ly.name]
 

@@ -51,7 +51,7 @@ def tdesc(t: torch.Tensor) -> Tensor:
 class ConvFilter:
     """A Conv2D kernel in the layouts the device code consumes (struct b200_filter)."""
 
-    def __init__(self, hwio: torch.Tensor, packed: bool = True):
+    def __init__(self, hwio: torch.Tensor, packed: bool = False):
         self.hwio = hwio.contiguous()
         self.kh, self.kw, self.cin, self.cout = self.hwio.shape
         self.ohwi = None
@@ -72,6 +72,13 @@ class ConvFilter:
 # ---- convolution -------------------------------------------------------------------
 def conv2d_fprop(x, filt: ConvFilter, bias, y, act=ACT_NONE, algo=ALGO_AUTO):
     check(lib().b200_conv2d_fprop(tdesc(x), filt.struct(), _ptr(bias), tdesc(y), act, algo, _stream()), "conv2d_fprop")
+    return y
+
+
+def conv2d_ln_fprop(x, filt: ConvFilter, bias, gamma, beta, eps, relu, z, y, mean, rstd, algo=ALGO_AUTO):
+    """Conv2D -> LayerNormalization -> (ReLU) in one call; z (pre-norm, kept for backward) may be None."""
+    check(lib().b200_conv2d_ln_fprop(tdesc(x), filt.struct(), _ptr(bias), _ptr(gamma), _ptr(beta), eps, int(relu),
+                                     _opt_desc(z), tdesc(y), _ptr(mean), _ptr(rstd), algo, _stream()), "conv2d_ln_fprop")
     return y
 
 

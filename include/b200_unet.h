@@ -60,10 +60,11 @@ typedef struct b200_tensor {
   int32_t reserved;
 } b200_tensor;
 
-/* A convolution kernel in both layouts the device code consumes.
- *   hwio : Keras layout [kh][kw][cin][cout]            (SIMT kernels; tcgen05 dgrad B operand)
- *   ohwi : packed copy  [kh][kw][cout][cin]            (tcgen05 fprop B operand; b200_filter_pack)
- * `ohwi` may be NULL, in which case only the SIMT kernels are available. */
+/* A convolution kernel.
+ *   hwio : Keras layout [kh][kw][cin][cout].  Every kernel consumes it as is: the tcgen05 fprop reads
+ *          it as an MN-major B operand, the dgrad as a K-major one with the taps reversed.
+ *   ohwi : optional repacked copy [kh][kw][cout][cin] (b200_filter_pack); not needed by any kernel,
+ *          kept for callers that want the transposed layout.  May be NULL. */
 typedef struct b200_filter {
   const void* hwio;
   const void* ohwi;
@@ -85,6 +86,13 @@ long long b200_launch_count(int reset);
  * unet_vinillia.py:44,49,90.  y = act(conv(x, f) + bias); bias is fp32 [cout] or NULL. */
 int b200_conv2d_fprop(const b200_tensor* x, const b200_filter* f, const float* bias,
                       const b200_tensor* y, int act, int algo, void* stream);
+/* Conv2D -> LayerNormalization(axis=-1) [-> ReLU] in one call (conv_block, train_adaptive_unet.py:202-204).
+ * z = conv(x)+bias in the storage dtype (kept for the backward pass; z->data may be NULL for inference),
+ * y = act(LN(z)); mean/rstd fp32 [n*h*w].  Fused into the tcgen05 epilogue when Cout is 64 or 128,
+ * otherwise executed as convolution + b200_layernorm_fwd inside the library. */
+int b200_conv2d_ln_fprop(const b200_tensor* x, const b200_filter* f, const float* bias, const float* gamma,
+                         const float* beta, float eps, int relu, const b200_tensor* z, const b200_tensor* y,
+                         float* mean, float* rstd, int algo, void* stream);
 /* dx (+)= conv_transpose(dy, f)  -- autodiff of the above w.r.t. its input. */
 int b200_conv2d_dgrad(const b200_tensor* dy, const b200_filter* f, const b200_tensor* dx,
                       int accumulate, int algo, void* stream);

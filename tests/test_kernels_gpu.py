@@ -151,6 +151,41 @@ def test_conv_tc_fprop_dgrad(shape):
     assert e1 < 1e-2 and e2 < 1e-2
 
 
+@pytest.mark.parametrize("shape", [(2, 32, 32, 64, 64), (1, 20, 13, 128, 64), (2, 16, 24, 64, 128), (3, 40, 24, 128, 128),
+                                   (9, 2, 2, 64, 64), (16, 1, 1, 128, 128), (5, 6, 6, 64, 128),
+                                   (2, 8, 8, 64, 256), (2, 9, 9, 3, 64)])
+@pytest.mark.parametrize("relu", [True, False])
+def test_conv_ln_fused(shape, relu):
+    """Conv2D -> LayerNormalization -> ReLU as one call: fused tcgen05 epilogue (Cout 64/128) and the
+    in-library composition for the other shapes; z, y, mean, rstd against the oracle."""
+    ops, K = _ops(), _K()
+    n, h, w, ci, co = shape
+    dt = torch.bfloat16
+    x = rand((n, h, w, ci), 61, dt)
+    wt = rand((3, 3, ci, co), 62, dt, 0.1)
+    b = rand((co,), 63, torch.float32, 0.5)
+    g = (1 + 0.3 * rand((co,), 64)).contiguous(); be = rand((co,), 65, scale=0.3)
+    filt = ops.ConvFilter(wt)
+    z = torch.full((n, h, w, co), 7.0, dtype=dt, device="cuda"); y = torch.full_like(z, 7.0)
+    mean = torch.zeros(n * h * w, device="cuda"); rstd = torch.zeros_like(mean)
+    ops.conv2d_ln_fprop(x, filt, b, g, be, 1e-3, relu, z, y, mean, rstd)
+    torch.cuda.synchronize()
+    zr = K.conv2d_same(f32(x), f32(wt), f32(b))
+    zr16 = zr.to(torch.bfloat16).float()
+    yr = K.layer_norm(zr16, f32(g), f32(be))
+    yr = torch.relu(yr) if relu else yr
+    mr = zr16.mean(dim=-1).flatten()
+    rr = torch.rsqrt(zr16.var(dim=-1, unbiased=False) + 1e-3).flatten()
+    e = (relerr(z, zr), relerr(y, yr), relerr(mean, mr), relerr(rstd, rr))
+    print(f"conv+ln {shape} relu={relu}: z {e[0]:.2e} y {e[1]:.2e} mean {e[2]:.2e} rstd {e[3]:.2e}")
+    assert e[0] < 1e-2 and e[1] < 1.5e-2 and e[3] < 1e-2
+    assert (f32(mean) - mr).abs().max() < 2e-2
+    # inference form: no z kept
+    y2 = torch.empty_like(y)
+    ops.conv2d_ln_fprop(x, filt, b, g, be, 1e-3, relu, None, y2, mean, rstd)
+    assert relerr(y2, y) < 1e-6 or co > 128 or ci == 3
+
+
 def test_conv_tc_strided_concat_and_accumulate():
     """Output written into a channel slice of a wider (concat) buffer; dgrad accumulating."""
     ops, K = _ops(), _K()
