@@ -71,6 +71,9 @@ SIGNATURES = {
     "b200_resample_plan": (_i, [_i, _i, _i, _vp, _vp, _i]),
     "b200_resample_plan_transpose": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _i]),
     "b200_resample2d": (_i, [_TP, _TP, _vp, _vp, _i, _vp, _vp, _i, _i, _vp]),
+    "b200_resample_compact": (_i, [_i, _i, _vp, _vp]),
+    "b200_resample_mode": (_i, [_i, _i, _vp]),
+    "b200_resample2d_ex": (_i, [_TP, _TP, _vp, _vp, _i, _vp, _vp, _i, _i, _i, _vp]),
     "b200_maxpool2_fwd": (_i, [_TP, _TP, _vp]),
     "b200_maxpool2_bwd": (_i, [_TP, _TP, _TP, _TP, _i, _vp]),
     "b200_clipadd_fwd": (_i, [_TP, _TP, _TP, _vp]),

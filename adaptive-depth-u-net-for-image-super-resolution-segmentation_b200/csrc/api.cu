@@ -70,7 +70,9 @@ int resample_taps(int, int, int);
 int resample_plan(int, int, int, int32_t*, float*, int);
 int resample_plan_transpose(int, int, int, const int32_t*, const float*, int32_t*, float*, int);
 int resample2d(const b200_tensor*, const b200_tensor*, const int32_t*, const float*, int, const int32_t*, const float*,
-               int, int, cudaStream_t);
+               int, int, int, cudaStream_t);
+int resample_compact(int, int, int32_t*, float*);
+int resample_mode(int, int, const int32_t*);
 int maxpool2_fwd(const b200_tensor*, const b200_tensor*, cudaStream_t);
 int maxpool2_bwd(const b200_tensor*, const b200_tensor*, const b200_tensor*, const b200_tensor*, int, cudaStream_t);
 int clipadd_fwd(const b200_tensor*, const b200_tensor*, const b200_tensor*, cudaStream_t);
@@ -274,7 +276,22 @@ int b200_resample2d(const b200_tensor* x, const b200_tensor* y, const int32_t* h
                     const int32_t* ws, const float* ww, int wt, int accumulate, void* s) {
   REQ_T(x, "x"); REQ_T(y, "y");
   B200_REQUIRE(hs && hw && ws && ww && ht > 0 && wt > 0, B200_ERR_BAD_ARG, "resample2d: NULL table");
-  return resample2d(x, y, hs, hw, ht, ws, ww, wt, accumulate, ST(s));
+  return resample2d(x, y, hs, hw, ht, ws, ww, wt, accumulate, 0, ST(s));
+}
+int b200_resample_compact(int n_out, int taps, int32_t* starts, float* weights) {
+  B200_REQUIRE(starts && weights && n_out > 0 && taps > 0, B200_ERR_BAD_ARG, "resample_compact: bad argument");
+  return resample_compact(n_out, taps, starts, weights);
+}
+int b200_resample_mode(int n_out, int taps, const int32_t* starts) {
+  B200_REQUIRE(starts && n_out > 0 && taps > 0, B200_ERR_BAD_ARG, "resample_mode: bad argument");
+  return resample_mode(n_out, taps, starts);
+}
+int b200_resample2d_ex(const b200_tensor* x, const b200_tensor* y, const int32_t* hs, const float* hw, int ht,
+                       const int32_t* ws, const float* ww, int wt, int accumulate, int h_mode, void* s) {
+  REQ_T(x, "x"); REQ_T(y, "y");
+  B200_REQUIRE(hs && hw && ws && ww && ht > 0 && wt > 0, B200_ERR_BAD_ARG, "resample2d_ex: NULL table");
+  B200_REQUIRE(h_mode >= 0 && h_mode <= 3, B200_ERR_BAD_ARG, "resample2d_ex: h_mode %d out of range", h_mode);
+  return resample2d(x, y, hs, hw, ht, ws, ww, wt, accumulate, h_mode, ST(s));
 }
 
 int b200_maxpool2_fwd(const b200_tensor* x, const b200_tensor* y, void* s) {

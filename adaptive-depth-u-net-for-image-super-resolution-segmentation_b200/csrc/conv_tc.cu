@@ -23,6 +23,8 @@
 #include <cuda.h>
 #include <stdlib.h>
 
+#include <type_traits>
+
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -92,7 +94,10 @@ constexpr int SMEM_LIMIT = 232448;                // 227 KB
 struct ConvTcParams {
   int N, H, W, Cout, KB, BN, n_tiles, tiles_h, tiles_w, total_items;
   int tap_rev, live_mask, resident, nsw, nsb, act, accumulate;
-  int debug;  // B200_CONV_DEBUG: 1 = epilogue only waits/releases, 2 = epilogue without global stores (profiling aid)
+  int debug;  // B200_CONV_DEBUG: 1 = epilogue only waits/releases (profiling aid)
+  // output path: 1 = tiles are staged in shared memory (128-byte swizzle) and written by TMA stores
+  // (ring of `nslots` 16 KB slots, one slot = 128 pixels x 64 channels); 0 = per-thread stores (accumulate)
+  int tma_store, nslots;
   int b_mn;   // 1: B operand is MN-major (fprop reads the Keras HWIO kernel [tap][cin][cout] as is); 0: K-major (dgrad)
   int Kc;     // K total (input channels of this convolution)
   // small images (H <= 7) are stacked: one tile holds `nb` images, each `srows` = H+2 window rows
@@ -146,15 +151,83 @@ __device__ __forceinline__ void decode_item(const ConvTcParams& p, int item, int
 }
 
 __device__ __forceinline__ float bf16_round(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
 
-// LayerNorm epilogue for one pixel (one thread) with all BN_T channels held in registers.
+constexpr int SLOT_BYTES = 128 * 128;   // 128 pixels x 64 bf16 channels
+constexpr int EPI_THREADS = 128;
+
+// Output staging ring of the epilogue warps.  A "job" is one 128-pixel x 64-channel box: the 128
+// epilogue threads each write their pixel's 128 bytes into a slot (swizzled like the TMA expects),
+// and ONE thread (the issuer) hands the slot to the TMA engine.  One named barrier per job: passing
+// the barrier of job k proves that every thread finished (and proxy-fenced) its writes of job k-1,
+// so the issuer launches the store of job k-1 right after it, and that the slot of job k is free
+// (the issuer waited for the bulk group of job k-nslots before arriving).
+struct StoreRing {
+  uint32_t stg0;
+  int nslots, slot;
+  bool issuer;
+  int d_have, d_which, d_c, d_w, d_h, d_n;
+  uint32_t d_slot;
+  const CUtensorMap* tm_y;
+  const CUtensorMap* tm_z;
+
+  __device__ __forceinline__ void flush() {
+    if (issuer && d_have) {
+      tma_store_4d(d_which ? tm_z : tm_y, d_slot, d_c, d_w, d_h, d_n);
+      bulk_commit();
+      d_have = 0;
+    }
+  }
+  __device__ __forceinline__ uint32_t begin() {
+    if (issuer) {
+      if (nslots == 2) bulk_wait_read<0>();
+      else if (nslots == 3) bulk_wait_read<1>();
+      else bulk_wait_read<2>();
+    }
+    __syncwarp();
+    named_bar_sync(1, EPI_THREADS);
+    flush();
+    return stg0 + (uint32_t)slot * SLOT_BYTES;
+  }
+  __device__ __forceinline__ void end(uint32_t slot_addr, int which, int c, int w, int h, int n) {
+    fence_proxy_async();
+    if (issuer) { d_have = 1; d_which = which; d_slot = slot_addr; d_c = c; d_w = w; d_h = h; d_n = n; }
+    if (++slot == nslots) slot = 0;
+  }
+  __device__ __forceinline__ void drain() {
+    __syncwarp();
+    named_bar_sync(1, EPI_THREADS);
+    flush();
+    if (issuer) bulk_wait_all();
+  }
+};
+
+// this thread's pixel row (64 channels, value i = f(i)) -> its 128 bytes of the slot, 16-byte chunks
+// XOR-swizzled by row (the layout a SWIZZLE_128B tensor map expects)
+template <typename F>
+__device__ __forceinline__ void stage_row(uint32_t slot_addr, int r, F f) {
+  const uint32_t base = slot_addr + (uint32_t)r * 128u;
+  const uint32_t sw = (uint32_t)(r & 7);
+#pragma unroll
+  for (int c = 0; c < 8; ++c)
+    st_shared_v4(base + (((uint32_t)c ^ sw) << 4), pack_bf16(f(c * 8 + 0), f(c * 8 + 1)), pack_bf16(f(c * 8 + 2), f(c * 8 + 3)),
+                 pack_bf16(f(c * 8 + 4), f(c * 8 + 5)), pack_bf16(f(c * 8 + 6), f(c * 8 + 7)));
+}
+
+__device__ __forceinline__ float bf16_lo(uint32_t w) { return __uint_as_float(w << 16); }
+__device__ __forceinline__ float bf16_hi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
+
+// LayerNorm epilogue for one pixel (one thread) with all BN_T channels held in registers as packed
+// bf16 pairs (z is stored in bf16 anyway, so the packed words ARE the z tile and cost half the registers):
 //   z = bf16(acc + bias)            (what keras stores under the mixed policy; statistics are taken on it)
 //   y = act((z - mean) * rstd * gamma + beta)
+// Returns after the TMEM reads; the caller releases the accumulator stage, then stages z and y.
 template <int BN_T>
-__device__ __forceinline__ void epilogue_layernorm(const ConvTcParams& p, uint32_t taddr, const float* s_bias,
-                                                   bool valid, __nv_bfloat16* ydst, __nv_bfloat16* zdst,
-                                                   long long pix) {
-  float zf[BN_T];
+__device__ __forceinline__ void ln_load(uint32_t taddr, const float* s_bias, uint32_t (&zp)[BN_T / 2], float& mean,
+                                        float& rstd, float eps) {
   float sum = 0.f;
 #pragma unroll
   for (int c0 = 0; c0 < BN_T; c0 += 32) {
@@ -162,45 +235,25 @@ __device__ __forceinline__ void epilogue_layernorm(const ConvTcParams& p, uint32
     tmem_ld32(taddr + c0, v);
     tmem_ld_wait();
 #pragma unroll
-    for (int i = 0; i < 32; ++i) {
-      const float t = bf16_round(__uint_as_float(v[i]) + s_bias[c0 + i]);
-      zf[c0 + i] = t;
-      sum += t;
+    for (int i = 0; i < 32; i += 2) {
+      const uint32_t w = pack_bf16(__uint_as_float(v[i]) + s_bias[c0 + i], __uint_as_float(v[i + 1]) + s_bias[c0 + i + 1]);
+      zp[(c0 + i) / 2] = w;
+      sum += bf16_lo(w) + bf16_hi(w);
     }
   }
-  const float mean = sum * (1.f / BN_T);
+  mean = sum * (1.f / BN_T);
   float q = 0.f;
 #pragma unroll
-  for (int i = 0; i < BN_T; ++i) { const float d = zf[i] - mean; q += d * d; }
-  const float rstd = rsqrtf(q * (1.f / BN_T) + p.ln_eps);
-  if (!valid) return;
-  const float* gam = s_bias + p.Cout;
-  const float* bet = s_bias + 2 * p.Cout;
-  if (zdst) {
-#pragma unroll
-    for (int g = 0; g < BN_T / 8; ++g) {
-      float o[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) o[i] = zf[g * 8 + i];
-      Vec8<__nv_bfloat16>::store(zdst + g * 8, o);
-    }
+  for (int i = 0; i < BN_T / 2; ++i) {
+    const float d0 = bf16_lo(zp[i]) - mean, d1 = bf16_hi(zp[i]) - mean;
+    q += d0 * d0 + d1 * d1;
   }
-#pragma unroll
-  for (int g = 0; g < BN_T / 8; ++g) {
-    float o[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const float t = (zf[g * 8 + i] - mean) * rstd * gam[g * 8 + i] + bet[g * 8 + i];
-      o[i] = p.ln_relu ? fmaxf(t, 0.f) : t;
-    }
-    Vec8<__nv_bfloat16>::store(ydst + g * 8, o);
-  }
-  p.mean[pix] = mean;
-  p.rstd[pix] = rstd;
+  rstd = rsqrtf(q * (1.f / BN_T) + eps);
 }
 
 __global__ void __launch_bounds__(NTHREADS, 1)
 conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_b,
+                  const __grid_constant__ CUtensorMap tm_y, const __grid_constant__ CUtensorMap tm_z,
                   const ConvTcParams p) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bar_full_w[8], bar_empty_w[8];
@@ -214,7 +267,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
   const uint32_t wt0 = smem0 + (uint32_t)p.nsw * WIN_STAGE;
   const uint32_t wt_bytes = (uint32_t)p.BN * 128u;
   const uint32_t tmem_cols = 2u * (uint32_t)p.BN;
-  float* s_bias = reinterpret_cast<float*>(smem_raw + (wt0 - smem_u32(smem_raw)) + (size_t)p.nsb * wt_bytes);
+  const uint32_t stg0 = wt0 + (uint32_t)p.nsb * wt_bytes;
+  float* s_bias = reinterpret_cast<float*>(smem_raw + (stg0 - smem_u32(smem_raw)) + (size_t)p.nslots * SLOT_BYTES);
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < p.nsw; ++i) { mbar_init(smem_u32(&bar_full_w[i]), 1); mbar_init(smem_u32(&bar_empty_w[i]), 1); }
@@ -226,7 +280,10 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
     s_bias[i] = p.bias ? p.bias[i] : 0.f;
     if (p.ln) { s_bias[p.Cout + i] = p.gamma[i]; s_bias[2 * p.Cout + i] = p.beta[i]; }
   }
-  if (warp == 0 && lane == 0) { prefetch_tmap(&tm_x); prefetch_tmap(&tm_b); }
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tm_x); prefetch_tmap(&tm_b);
+    if (p.tma_store) { prefetch_tmap(&tm_y); if (p.z) prefetch_tmap(&tm_z); }
+  }
   if (warp == 1) { tmem_alloc(smem_u32(&tmem_base_smem), tmem_cols); tmem_relinquish(); }
   tc_fence_before();
   __syncthreads();
@@ -352,6 +409,10 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
     const int r = q * 32 + lane;            // GEMM row = pixel of the tile
     const int ty = r / TILE_W, tx = r % TILE_W;
     const int sb_img = ty / p.srows, sb_row = ty % p.srows;   // stacked small images (srows huge otherwise)
+    StoreRing ring;
+    ring.stg0 = stg0; ring.nslots = p.nslots; ring.slot = 0; ring.issuer = threadIdx.x == 64;
+    ring.d_have = 0; ring.d_which = 0; ring.d_c = ring.d_w = ring.d_h = ring.d_n = 0; ring.d_slot = 0;
+    ring.tm_y = &tm_y; ring.tm_z = &tm_z;
     int as = 0, pa = 0;
     for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
       int j, tw, th, n;
@@ -359,51 +420,113 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
       const int oh = th * TILE_H + sb_row, ow = tw * TILE_W + tx;
       const int img = n + sb_img;
       const bool valid = oh < p.H && ow < p.W && sb_img < p.nb && img < p.N;
-      __nv_bfloat16* dst = p.y + (long long)img * p.ysn + (long long)oh * p.ysh + (long long)ow * p.ysw + j * p.BN;
       const float* bias = s_bias + j * p.BN;
       mbar_wait(smem_u32(&bar_tmem_full[as]), pa);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * p.BN);
+      const uint32_t tmem_empty = smem_u32(&bar_tmem_empty[as]);
+      // the accumulator stage goes back to the MMA warp as soon as this warp holds its values in registers
+      auto release_tmem = [&]() {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tmem_empty);
+      };
+      const int cw = tw * TILE_W, ch = th * TILE_H;   // box origin (stacked tiles: th == 0, box = {64, 8, srows, nb})
       if (p.debug == 1) {
+        release_tmem();
       } else if (p.ln) {
         const long long pix = ((long long)img * p.H + oh) * p.W + ow;
-        __nv_bfloat16* zdst = p.z ? p.z + (long long)img * p.zsn + (long long)oh * p.zsh + (long long)ow * p.zsw : nullptr;
-        if (p.BN == 64) epilogue_layernorm<64>(p, taddr, s_bias, valid, dst, zdst, pix);
-        else epilogue_layernorm<128>(p, taddr, s_bias, valid, dst, zdst, pix);
-      } else
-      for (int c0 = 0; c0 < p.BN; c0 += 32) {
-        uint32_t v[32];
-        tmem_ld32(taddr + c0, v);
-        tmem_ld_wait();
-        if (valid) {
+        const float* gam = s_bias + p.Cout;
+        const float* bet = s_bias + 2 * p.Cout;
+        auto run = [&](auto tag) {
+          constexpr int BN_T = decltype(tag)::value;
+          uint32_t zp[BN_T / 2];
+          float mean, rstd;
+          ln_load<BN_T>(taddr, s_bias, zp, mean, rstd, p.ln_eps);
+          release_tmem();
+          if (valid) { p.mean[pix] = mean; p.rstd[pix] = rstd; }
+          const bool relu = p.ln_relu != 0;
+          const uint32_t rbase = (uint32_t)r * 128u, sw = (uint32_t)(r & 7);
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            const float4 b0 = *reinterpret_cast<const float4*>(bias + c0 + g * 8);
-            const float4 b1 = *reinterpret_cast<const float4*>(bias + c0 + g * 8 + 4);
-            float o[8] = {__uint_as_float(v[g * 8 + 0]) + b0.x, __uint_as_float(v[g * 8 + 1]) + b0.y,
-                          __uint_as_float(v[g * 8 + 2]) + b0.z, __uint_as_float(v[g * 8 + 3]) + b0.w,
-                          __uint_as_float(v[g * 8 + 4]) + b1.x, __uint_as_float(v[g * 8 + 5]) + b1.y,
-                          __uint_as_float(v[g * 8 + 6]) + b1.z, __uint_as_float(v[g * 8 + 7]) + b1.w};
-            if (p.act == B200_ACT_RELU) {
+          for (int hf = 0; hf < BN_T / 64; ++hf) {
+            if (p.z) {
+              const uint32_t slot = ring.begin() + rbase;
 #pragma unroll
-              for (int i = 0; i < 8; ++i) o[i] = fmaxf(o[i], 0.f);
+              for (int c = 0; c < 8; ++c)
+                st_shared_v4(slot + (((uint32_t)c ^ sw) << 4), zp[hf * 32 + c * 4], zp[hf * 32 + c * 4 + 1],
+                             zp[hf * 32 + c * 4 + 2], zp[hf * 32 + c * 4 + 3]);
+              ring.end(slot - rbase, 1, hf * 64, cw, ch, n);
             }
-            __nv_bfloat16* d8 = dst + c0 + g * 8;
-            if (p.accumulate) {
-              float e[8];
-              Vec8<__nv_bfloat16>::load(d8, e);
+            const uint32_t slot = ring.begin() + rbase;
 #pragma unroll
-              for (int i = 0; i < 8; ++i) o[i] += e[i];
+            for (int c = 0; c < 8; ++c) {
+              uint32_t o[4];
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const int ci = hf * 64 + c * 8 + k * 2;
+                const uint32_t w = zp[ci / 2];
+                float t0 = (bf16_lo(w) - mean) * rstd * gam[ci] + bet[ci];
+                float t1 = (bf16_hi(w) - mean) * rstd * gam[ci + 1] + bet[ci + 1];
+                if (relu) { t0 = fmaxf(t0, 0.f); t1 = fmaxf(t1, 0.f); }
+                o[k] = pack_bf16(t0, t1);
+              }
+              st_shared_v4(slot + (((uint32_t)c ^ sw) << 4), o[0], o[1], o[2], o[3]);
             }
-            if (p.debug != 2 || o[0] == 12345.678f) Vec8<__nv_bfloat16>::store(d8, o);
+            ring.end(slot - rbase, 0, hf * 64, cw, ch, n);
+          }
+        };
+        if (p.BN == 64) run(std::integral_constant<int, 64>{});
+        else run(std::integral_constant<int, 128>{});
+      } else if (p.tma_store) {
+        const int halves = p.BN / 64;
+        for (int hf = 0; hf < halves; ++hf) {
+          uint32_t v0[32], v1[32];
+          tmem_ld32(taddr + hf * 64, v0);
+          tmem_ld32(taddr + hf * 64 + 32, v1);
+          tmem_ld_wait();
+          if (hf == halves - 1) release_tmem();
+          const bool relu = p.act == B200_ACT_RELU;
+          const float* bh = bias + hf * 64;
+          const uint32_t slot = ring.begin();
+          stage_row(slot, r, [&](int i) {
+            const float t = __uint_as_float(i < 32 ? v0[i] : v1[i - 32]) + bh[i];
+            return relu ? fmaxf(t, 0.f) : t;
+          });
+          ring.end(slot, 0, j * p.BN + hf * 64, cw, ch, n);
+        }
+      } else {
+        // per-thread read-modify-write stores (gradient accumulation into an existing tensor)
+        __nv_bfloat16* dst = p.y + (long long)img * p.ysn + (long long)oh * p.ysh + (long long)ow * p.ysw + j * p.BN;
+        for (int c0 = 0; c0 < p.BN; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld32(taddr + c0, v);
+          tmem_ld_wait();
+          if (valid) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              float o[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) o[i] = __uint_as_float(v[g * 8 + i]) + bias[c0 + g * 8 + i];
+              if (p.act == B200_ACT_RELU) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) o[i] = fmaxf(o[i], 0.f);
+              }
+              __nv_bfloat16* d8 = dst + c0 + g * 8;
+              if (p.accumulate) {
+                float e[8];
+                Vec8<__nv_bfloat16>::load(d8, e);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) o[i] += e[i];
+              }
+              Vec8<__nv_bfloat16>::store(d8, o);
+            }
           }
         }
+        release_tmem();
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(&bar_tmem_empty[as]));
       if (++as == 2) { as = 0; pa ^= 1; }
     }
+    if (p.tma_store) ring.drain();
   }
 
   tc_fence_before();
@@ -596,18 +719,41 @@ int conv_tc_launch(const b200_tensor* x_in, const void* wmat, int cin, int cout,
   p.Kc = cin;
   p.live_mask = live_mask;
   const int wt_bytes = p.BN * 128;
-  const int bias_bytes = ((cout * 4 * (ln ? 3 : 1) + 1023) / 1024) * 1024;
+  // (>= 2 KB: a stacked-image store box may span 18 tile rows, i.e. read 2 KB past its 16-row slot; those rows are
+  // clipped by the TMA, the bytes only have to exist)
+  int bias_bytes = ((cout * 4 * (ln ? 3 : 1) + 1023) / 1024) * 1024;
+  if (bias_bytes < 2048) bias_bytes = 2048;
   const int budget = SMEM_LIMIT - 1024 /*align slack*/ - 1024 /*static*/ - bias_bytes;
   const int all_w = 9 * p.KB * wt_bytes;
-  p.resident = (p.n_tiles == 1 && 9 * p.KB <= MAX_WSLOTS && budget - all_w >= 2 * WIN_STAGE) ? 1 : 0;
-  if (p.resident) {
-    p.nsb = 9 * p.KB;
-    p.nsw = (budget - all_w) / WIN_STAGE;
+  // output staging ring (TMA stores); gradient accumulation keeps the per-thread read-modify-write path
+  p.tma_store = accumulate ? 0 : 1;
+  B200_REQUIRE(!(ln && accumulate), B200_ERR_BAD_ARG, "conv3x3+LayerNorm tcgen05: accumulate is not supported");
+  const int jobs_per_tile = (p.BN / 64) * ((ln && z) ? 2 : 1);
+  auto plan_smem = [&](int nslots, int min_windows) -> bool {
+    const int left = budget - nslots * SLOT_BYTES;
+    p.nslots = nslots;
+    p.resident = (p.n_tiles == 1 && 9 * p.KB <= MAX_WSLOTS && left - all_w >= min_windows * WIN_STAGE) ? 1 : 0;
+    if (p.resident) {
+      p.nsb = 9 * p.KB;
+      p.nsw = (left - all_w) / WIN_STAGE;
+    } else {
+      p.nsb = 4;
+      p.nsw = (left - p.nsb * wt_bytes) / WIN_STAGE;
+    }
+    if (p.nsw > 8) p.nsw = 8;
+    return p.nsw >= min_windows;
+  };
+  if (!p.tma_store) {
+    plan_smem(0, 2);
   } else {
-    p.nsb = 4;
-    p.nsw = (budget - p.nsb * wt_bytes) / WIN_STAGE;
+    // prefer resident weights; within that, as many slots as one tile's jobs while keeping 3 window stages
+    const int want = jobs_per_tile < 2 ? 2 : (jobs_per_tile > 4 ? 4 : jobs_per_tile);
+    bool ok = false;
+    for (int ns = want; ns >= 2 && !ok; --ns) ok = plan_smem(ns, 3) && p.resident;
+    for (int ns = want; ns >= 2 && !ok; --ns) ok = plan_smem(ns, 2) && p.resident;
+    if (!ok) ok = plan_smem(want, 3);
+    if (!ok) plan_smem(2, 2);
   }
-  if (p.nsw > 8) p.nsw = 8;
   B200_REQUIRE(p.nsw >= 2, B200_ERR_UNSUPPORTED, "conv3x3 tcgen05: shared memory budget too small");
   p.act = act; p.accumulate = accumulate; p.bias = bias;
   p.y = reinterpret_cast<__nv_bfloat16*>(y->data);
@@ -624,20 +770,26 @@ int conv_tc_launch(const b200_tensor* x_in, const void* wmat, int cin, int cout,
     }
   }
 
-  CUtensorMap tm_x, tm_b;
+  CUtensorMap tm_x, tm_b, tm_y, tm_z;
   int rc = make_act_tmap(&tm_x, x, WIN_W, box_h, box_n);
   if (rc) return rc;
   rc = b_mn ? make_mat_tmap(&tm_b, wmat, 9LL * cin, cout, 64) : make_mat_tmap(&tm_b, wmat, 9LL * cout, cin, p.BN);
   if (rc) return rc;
+  // output boxes: {64 ch, 8, 16, 1}, or {64 ch, 8, H+2, nb} for stacked small images (rows past H are clipped)
+  const int obox_h = p.nb > 1 || box_h != WIN_H ? box_h : TILE_H;
+  rc = make_act_tmap(&tm_y, y, TILE_W, obox_h, box_n);
+  if (rc) return rc;
+  rc = make_act_tmap(&tm_z, z ? z : y, TILE_W, obox_h, box_n);
+  if (rc) return rc;
 
-  const size_t smem = 1024 + (size_t)p.nsw * WIN_STAGE + (size_t)p.nsb * wt_bytes + bias_bytes;
+  const size_t smem = 1024 + (size_t)p.nsw * WIN_STAGE + (size_t)p.nsb * wt_bytes + (size_t)p.nslots * SLOT_BYTES + bias_bytes;
   static bool attr_set = false;
   if (!attr_set) {
     cudaFuncSetAttribute(conv3x3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT - 1024);
     attr_set = true;
   }
   int grid = p.total_items < sm_count() ? p.total_items : sm_count();
-  conv3x3_tc_kernel<<<grid, NTHREADS, smem, st>>>(tm_x, tm_b, p);
+  conv3x3_tc_kernel<<<grid, NTHREADS, smem, st>>>(tm_x, tm_b, tm_y, tm_z, p);
   return check_launch("conv3x3_tc_kernel");
 }
 

@@ -5,6 +5,8 @@
 // shuffles.  Replaces keras LayerNormalization(axis=-1)+ReLU
 // (Super_resolution/code/train_adaptive_unet.py:203-204,208-209) and
 // BatchNormalization+ReLU (Segmenation/code/train_adaptive_unet.py:327-331).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace b200 {
@@ -192,6 +194,119 @@ ln_bwd_kernel(TView dy, TView z, const float* __restrict__ mean, const float* __
         atomicAdd(&s_acc[2 * C + j * 8 + i], a_z[k][i]);
       }
     }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < C; i += NT) {
+    if (dgamma) atomicAdd(dgamma + i, s_acc[i]);
+    if (dbeta) atomicAdd(dbeta + i, s_acc[C + i]);
+    if (dbias) atomicAdd(dbias + i, s_acc[2 * C + i]);
+  }
+}
+
+// LayerNorm backward, bf16, C = 8*TPP (64/128/256), evenly spaced pixels.  These kernels are bound by
+// instruction issue, not by HBM (ncu: issue slots 58 % busy at 46 % of HBM peak for the generic kernel
+// above), so this variant is written for instruction count: 32-bit pixel indices, packed f32x2
+// arithmetic (FFMA2/FADD2/FMUL2 of sm_100), bf16 pairs unpacked with one shift / one mask, two
+// pixels in flight per thread.
+__device__ __forceinline__ float2 unpack_bf16x2(uint32_t w) {
+  return make_float2(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u));
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float2 v) {
+  __nv_bfloat162 h = __float22bfloat162_rn(v);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+template <int TPP>
+__global__ void __launch_bounds__(NT, 3)
+ln_bwd_lean_kernel(const __nv_bfloat16* __restrict__ dy, long long dy_sw, const __nv_bfloat16* __restrict__ z,
+                   long long z_sw, const float* __restrict__ mean, const float* __restrict__ rstd,
+                   const float* __restrict__ gamma, const float* __restrict__ beta, int relu,
+                   __nv_bfloat16* __restrict__ dz, long long dz_sw, float* __restrict__ dgamma,
+                   float* __restrict__ dbeta, float* __restrict__ dbias, int npix) {
+  constexpr int C = 8 * TPP, PPB = NT / TPP;
+  __shared__ float s_acc[3 * C];
+  for (int i = threadIdx.x; i < 3 * C; i += NT) s_acc[i] = 0.f;
+  __syncthreads();
+  const int lane_g = threadIdx.x % TPP;
+  const float invC = 1.f / (float)C;
+  float2 gam[4], bet[4], a_g[4], a_b[4], a_z[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    gam[i] = make_float2(gamma[lane_g * 8 + 2 * i], gamma[lane_g * 8 + 2 * i + 1]);
+    bet[i] = make_float2(beta[lane_g * 8 + 2 * i], beta[lane_g * 8 + 2 * i + 1]);
+    a_g[i] = a_b[i] = a_z[i] = make_float2(0.f, 0.f);
+  }
+  const __nv_bfloat16* zq = z + lane_g * 8;
+  const __nv_bfloat16* dq = dy + lane_g * 8;
+  __nv_bfloat16* oq = dz + lane_g * 8;
+  const int step = gridDim.x * PPB;
+  // two pixels per iteration (p and p + step); warp-uniform trip count, the tail pixel is masked
+  for (int base = blockIdx.x * PPB; base < npix; base += 2 * step) {
+    int pp[2] = {base + (int)(threadIdx.x / TPP), base + (int)(threadIdx.x / TPP) + step};
+    bool ok[2];
+    uint4 zr[2], dr[2];
+    float mu[2], rs[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      ok[u] = pp[u] < npix;
+      if (!ok[u]) pp[u] = npix - 1;
+      zr[u] = *reinterpret_cast<const uint4*>(zq + (long long)pp[u] * z_sw);
+      dr[u] = *reinterpret_cast<const uint4*>(dq + (long long)pp[u] * dy_sw);
+      mu[u] = mean[pp[u]];
+      rs[u] = rstd[pp[u]];
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const uint32_t* zw = reinterpret_cast<const uint32_t*>(&zr[u]);
+      const uint32_t* dw = reinterpret_cast<const uint32_t*>(&dr[u]);
+      const float2 rs2 = make_float2(rs[u], rs[u]);
+      const float2 nmr = make_float2(-mu[u] * rs[u], -mu[u] * rs[u]);
+      float2 x[4], gg[4];
+      float2 s1 = make_float2(0.f, 0.f), s2 = make_float2(0.f, 0.f);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        x[i] = __ffma2_rn(unpack_bf16x2(zw[i]), rs2, nmr);            // (z - mu) * rstd
+        float2 d = unpack_bf16x2(dw[i]);
+        if (relu) {
+          const float2 t = __ffma2_rn(x[i], gam[i], bet[i]);
+          d.x = t.x > 0.f ? d.x : 0.f;
+          d.y = t.y > 0.f ? d.y : 0.f;
+        }
+        if (!ok[u]) d = make_float2(0.f, 0.f);
+        a_g[i] = __ffma2_rn(d, x[i], a_g[i]);
+        a_b[i] = __fadd2_rn(a_b[i], d);
+        gg[i] = __fmul2_rn(d, gam[i]);
+        s1 = __fadd2_rn(s1, gg[i]);
+        s2 = __ffma2_rn(gg[i], x[i], s2);
+      }
+      float m1 = s1.x + s1.y, m2 = s2.x + s2.y;
+#pragma unroll
+      for (int o = TPP >> 1; o > 0; o >>= 1) {
+        m1 += __shfl_xor_sync(0xffffffffu, m1, o);
+        m2 += __shfl_xor_sync(0xffffffffu, m2, o);
+      }
+      // dz = rstd * (g - mean(g) - xhat * mean(g * xhat))
+      const float2 c1 = make_float2(-m1 * invC * rs[u], -m1 * invC * rs[u]);
+      const float2 c2 = make_float2(-m2 * invC * rs[u], -m2 * invC * rs[u]);
+      uint4 out;
+      uint32_t* ow = reinterpret_cast<uint32_t*>(&out);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 o2 = __ffma2_rn(x[i], c2, __ffma2_rn(gg[i], rs2, c1));
+        a_z[i] = __fadd2_rn(a_z[i], o2);     // masked tail pixels have d == 0 for the whole group => o2 == 0
+        ow[i] = pack_bf16x2(o2);
+      }
+      if (ok[u]) *reinterpret_cast<uint4*>(oq + (long long)pp[u] * dz_sw) = out;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    atomicAdd(&s_acc[lane_g * 8 + 2 * i], a_g[i].x);
+    atomicAdd(&s_acc[lane_g * 8 + 2 * i + 1], a_g[i].y);
+    atomicAdd(&s_acc[C + lane_g * 8 + 2 * i], a_b[i].x);
+    atomicAdd(&s_acc[C + lane_g * 8 + 2 * i + 1], a_b[i].y);
+    atomicAdd(&s_acc[2 * C + lane_g * 8 + 2 * i], a_z[i].x);
+    atomicAdd(&s_acc[2 * C + lane_g * 8 + 2 * i + 1], a_z[i].y);
   }
   __syncthreads();
   for (int i = threadIdx.x; i < C; i += NT) {
@@ -455,6 +570,21 @@ int layernorm_bwd(const b200_tensor* dy, const b200_tensor* z, const float* mean
   const int grid = (int)(blocks < cap ? (blocks < 1 ? 1 : blocks) : cap);
   const size_t smem = sizeof(float) * 3 * C;
   TView dyv = view_of(dy), zv = view_of(z), dzv = view_of(dz);
+  static const int lean_variant = getenv("B200_LN_BWD_LEAN") ? atoi(getenv("B200_LN_BWD_LEAN")) : 1;
+  if (lean_variant && z->dtype == B200_BF16 && (C == 64 || C == 128 || C == 256) && zv.lin && dyv.lin && dzv.lin &&
+      npix < (1LL << 30)) {
+    const int ppb = NT / (C / 8);
+    long long nb = (npix + 2LL * ppb - 1) / (2LL * ppb);
+    const long long capl = 3LL * sm_count();
+    const int gridl = (int)(nb < capl ? nb : capl);
+    const __nv_bfloat16* dyp = reinterpret_cast<const __nv_bfloat16*>(dy->data);
+    const __nv_bfloat16* zp = reinterpret_cast<const __nv_bfloat16*>(z->data);
+    __nv_bfloat16* dzp = reinterpret_cast<__nv_bfloat16*>(dz->data);
+    if (C == 64) ln_bwd_lean_kernel<8><<<gridl, NT, 0, st>>>(dyp, dy->stride_w, zp, z->stride_w, mean, rstd, gamma, beta, relu, dzp, dz->stride_w, dgamma, dbeta, dbias, (int)npix);
+    else if (C == 128) ln_bwd_lean_kernel<16><<<gridl, NT, 0, st>>>(dyp, dy->stride_w, zp, z->stride_w, mean, rstd, gamma, beta, relu, dzp, dz->stride_w, dgamma, dbeta, dbias, (int)npix);
+    else ln_bwd_lean_kernel<32><<<gridl, NT, 0, st>>>(dyp, dy->stride_w, zp, z->stride_w, mean, rstd, gamma, beta, relu, dzp, dz->stride_w, dgamma, dbeta, dbias, (int)npix);
+    return check_launch("ln_bwd_lean_kernel");
+  }
   B200_DISPATCH_DTYPE(z->dtype, T, {
     if (cpt == 1) ln_bwd_kernel<T, 1><<<grid, NT, smem, st>>>(dyv, zv, mean, rstd, gamma, beta, relu, dzv, dgamma, dbeta, dbias, tpp, npix);
     else if (cpt == 2) ln_bwd_kernel<T, 2><<<grid, NT, smem, st>>>(dyv, zv, mean, rstd, gamma, beta, relu, dzv, dgamma, dbeta, dbias, tpp, npix);

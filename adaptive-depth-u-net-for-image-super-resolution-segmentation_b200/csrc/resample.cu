@@ -9,6 +9,7 @@
 // tables and the device kernel is a pure gather, so forward and backward are the
 // same kernel over a table and its transpose.
 #include <math.h>
+#include <stdlib.h>
 #include <vector>
 
 #include "common.cuh"
@@ -20,7 +21,7 @@ constexpr int NT = 256;
 
 // grid = (ceil(OW * C/8 / 256), OH, N): one block per output-row segment, one thread per
 // (output pixel, 8-channel chunk).  No per-element divisions by H/W; the row's h-taps are block-uniform.
-template <typename T>
+template <typename T, bool BATCHED>
 __global__ void __launch_bounds__(NT)
 resample_vec_kernel(TView x, TView y, const int* __restrict__ hs, const float* __restrict__ hw, int ht,
                     const int* __restrict__ ws, const float* __restrict__ ww, int wt, int accumulate) {
@@ -36,20 +37,20 @@ resample_vec_kernel(TView x, TView y, const int* __restrict__ hs, const float* _
   for (int k = 0; k < 8; ++k) acc[k] = 0.f;
   const int h0 = hs[oh], w0 = ws[ow];
   const float* wrow = ww + ow * wt;
-  for (int a = 0; a < ht; ++a) {
-    const float wa = hw[oh * ht + a];
-    if (wa == 0.f) continue;
-    const T* row = xp + (long long)min(h0 + a, x.h - 1) * x.sh;
-    for (int b = 0; b < wt; ++b) {
-      const float wb = wrow[b];
-      if (wb == 0.f) continue;
-      float v[8];
-      Vec8<T>::load(row + (long long)min(w0 + b, x.w - 1) * x.sw, v);
-      const float wgt = wa * wb;
+    for (int a = 0; a < ht; ++a) {
+      const float wa = hw[oh * ht + a];
+      if (wa == 0.f) continue;
+      const T* row = xp + (long long)min(h0 + a, x.h - 1) * x.sh;
+      for (int b = 0; b < wt; ++b) {
+        const float wb = wrow[b];
+        if (wb == 0.f) continue;
+        float v[8];
+        Vec8<T>::load(row + (long long)min(w0 + b, x.w - 1) * x.sw, v);
+        const float wgt = wa * wb;
 #pragma unroll
-      for (int k = 0; k < 8; ++k) acc[k] += wgt * v[k];
+        for (int k = 0; k < 8; ++k) acc[k] += wgt * v[k];
+      }
     }
-  }
   if (accumulate) {
     float o[8];
     Vec8<T>::load(dst, o);
@@ -57,6 +58,165 @@ resample_vec_kernel(TView x, TView y, const int* __restrict__ hs, const float* _
     for (int k = 0; k < 8; ++k) acc[k] += o[k];
   }
   Vec8<T>::store(dst, acc);
+}
+
+// ---------------------------------------------------------------------------
+// Row-marching bf16 kernels.  The gather kernel above spends ~380 instructions per 16-byte output
+// chunk and is bound by instruction issue (ncu: issue slots 84 % busy at 20 % of HBM peak), so these
+// two do the separable filter as "horizontal taps once per input row, vertical taps from registers":
+// a thread owns one (output column, 8-channel chunk) and walks a segment of rows.
+//   * resample_up_kernel   (vertical taps HT <= 3: up-sampling and the transpose of down-sampling):
+//     driven by output rows; the horizontally filtered input rows h0..h0+HT-1 stay in registers and
+//     are shifted when h0 advances.
+//   * resample_down_kernel (many vertical taps: antialiased down-sampling and the transpose of
+//     up-sampling): driven by input rows; each horizontally filtered row is scattered into the (at
+//     most NSLOT) output rows whose span contains it; a row is stored when its span ends.
+// ---------------------------------------------------------------------------
+struct RsArgs {
+  const __nv_bfloat16* x; long long x_sn, x_sh, x_sw; int xh, xw;
+  __nv_bfloat16* y; long long y_sn, y_sh, y_sw; int yh, yw;
+  int chunks;
+  const int* hs; const float* hw; int ht;
+  const int* ws; const float* ww; int wt;
+  int seg, accumulate;
+};
+
+__device__ __forceinline__ float2 rs_unpack(uint32_t w) {
+  return make_float2(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u));
+}
+__device__ __forceinline__ uint32_t rs_pack(float2 v) {
+  __nv_bfloat162 h = __float22bfloat162_rn(v);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+// horizontally filtered input row: r = sum_b ww[b] * x[row][w0 + b]; taps four at a time, zero taps skipped
+__device__ __forceinline__ void rs_hrow(const __nv_bfloat16* __restrict__ row, long long x_sw, int xw, int w0,
+                                        const float* __restrict__ wrow, int wt, float2 (&r)[4]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) r[i] = make_float2(0.f, 0.f);
+  for (int b0 = 0; b0 < wt; b0 += 4) {
+    float wb[4];
+    uint4 raw[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) wb[k] = (b0 + k < wt) ? wrow[b0 + k] : 0.f;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (wb[k] != 0.f) raw[k] = *reinterpret_cast<const uint4*>(row + (long long)min(w0 + b0 + k, xw - 1) * x_sw);
+      else raw[k] = make_uint4(0u, 0u, 0u, 0u);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 w2 = make_float2(wb[k], wb[k]);
+      const uint32_t* q = reinterpret_cast<const uint32_t*>(&raw[k]);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) r[i] = __ffma2_rn(rs_unpack(q[i]), w2, r[i]);
+    }
+  }
+}
+
+__device__ __forceinline__ void rs_store(__nv_bfloat16* dst, const float2 (&v)[4], int accumulate) {
+  float2 o[4] = {v[0], v[1], v[2], v[3]};
+  if (accumulate) {
+    const uint4 e = *reinterpret_cast<const uint4*>(dst);
+    const uint32_t* q = reinterpret_cast<const uint32_t*>(&e);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) o[i] = __fadd2_rn(o[i], rs_unpack(q[i]));
+  }
+  uint4 out;
+  uint32_t* ow = reinterpret_cast<uint32_t*>(&out);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) ow[i] = rs_pack(o[i]);
+  *reinterpret_cast<uint4*>(dst) = out;
+}
+
+template <int HT>
+__global__ void __launch_bounds__(NT)
+resample_up_kernel(const RsArgs a) {
+  const int item = blockIdx.x * NT + threadIdx.x;
+  const int ow = item / a.chunks, j = item - ow * a.chunks;
+  if (ow >= a.yw) return;
+  const int n = blockIdx.z;
+  const int oh0 = blockIdx.y * a.seg, oh1 = min(oh0 + a.seg, a.yh);
+  const __nv_bfloat16* xp = a.x + (long long)n * a.x_sn + j * 8;
+  __nv_bfloat16* yp = a.y + (long long)n * a.y_sn + (long long)ow * a.y_sw + j * 8;
+  const int w0 = a.ws[ow];
+  const float* wrow = a.ww + ow * a.wt;
+  float2 cache[HT][4];
+  int cur = -(1 << 30);
+  for (int oh = oh0; oh < oh1; ++oh) {
+    const int h0 = a.hs[oh];                 // block-uniform
+    if (h0 != cur) {
+      if (HT > 1 && h0 == cur + 1) {
+#pragma unroll
+        for (int t = 0; t + 1 < HT; ++t)
+#pragma unroll
+          for (int i = 0; i < 4; ++i) cache[t][i] = cache[t + 1][i];
+        rs_hrow(xp + (long long)min(h0 + HT - 1, a.xh - 1) * a.x_sh, a.x_sw, a.xw, w0, wrow, a.wt, cache[HT - 1]);
+      } else {
+#pragma unroll
+        for (int t = 0; t < HT; ++t)
+          rs_hrow(xp + (long long)min(h0 + t, a.xh - 1) * a.x_sh, a.x_sw, a.xw, w0, wrow, a.wt, cache[t]);
+      }
+      cur = h0;
+    }
+    float2 acc[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) acc[i] = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int t = 0; t < HT; ++t) {
+      const float wa = a.hw[oh * HT + t];
+      const float2 w2 = make_float2(wa, wa);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) acc[i] = __ffma2_rn(cache[t][i], w2, acc[i]);
+    }
+    rs_store(yp + (long long)oh * a.y_sh, acc, a.accumulate);
+  }
+}
+
+template <int NSLOT>
+__global__ void __launch_bounds__(NT)
+resample_down_kernel(const RsArgs a) {
+  const int item = blockIdx.x * NT + threadIdx.x;
+  const int ow = item / a.chunks, j = item - ow * a.chunks;
+  if (ow >= a.yw) return;
+  const int n = blockIdx.z;
+  const int oh0 = blockIdx.y * a.seg, oh1 = min(oh0 + a.seg, a.yh);
+  const __nv_bfloat16* xp = a.x + (long long)n * a.x_sn + j * 8;
+  __nv_bfloat16* yp = a.y + (long long)n * a.y_sn + (long long)ow * a.y_sw + j * 8;
+  const int w0 = a.ws[ow];
+  const float* wrow = a.ww + ow * a.wt;
+  constexpr int FAR = 1 << 29;
+  int o_s[NSLOT], lo_s[NSLOT];
+  float2 acc[NSLOT][4];
+#pragma unroll
+  for (int s = 0; s < NSLOT; ++s) {
+    o_s[s] = oh0 + s;
+    lo_s[s] = o_s[s] < oh1 ? a.hs[o_s[s]] : FAR;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) acc[s][i] = make_float2(0.f, 0.f);
+  }
+  const int ih_end = a.hs[oh1 - 1] + a.ht;
+  for (int ih = a.hs[oh0]; ih < ih_end; ++ih) {        // block-uniform trip count and slot state
+    float2 r[4];
+    rs_hrow(xp + (long long)min(ih, a.xh - 1) * a.x_sh, a.x_sw, a.xw, w0, wrow, a.wt, r);
+#pragma unroll
+    for (int s = 0; s < NSLOT; ++s) {
+      const int k = ih - lo_s[s];
+      if (k >= 0 && k < a.ht) {
+        const float wa = a.hw[o_s[s] * a.ht + k];
+        const float2 w2 = make_float2(wa, wa);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc[s][i] = __ffma2_rn(r[i], w2, acc[s][i]);
+        if (k == a.ht - 1) {
+          rs_store(yp + (long long)o_s[s] * a.y_sh, acc[s], a.accumulate);
+          o_s[s] += NSLOT;
+          lo_s[s] = o_s[s] < oh1 ? a.hs[o_s[s]] : FAR;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) acc[s][i] = make_float2(0.f, 0.f);
+        }
+      }
+    }
+  }
 }
 
 template <typename T>
@@ -239,16 +399,82 @@ int resample_plan_transpose(int in_size, int out_size, int taps, const int32_t* 
   return need;
 }
 
+// Shift leading zero weights out of every row (start += shift) and return the effective tap count
+// (largest non-zero extent); rows keep their pitch `taps`.  Host tables, in place.
+int resample_compact(int n_out, int taps, int32_t* starts, float* weights) {
+  int eff = 1;
+  for (int o = 0; o < n_out; ++o) {
+    float* w = weights + (size_t)o * taps;
+    int first = 0;
+    while (first < taps - 1 && w[first] == 0.f) ++first;
+    int last = taps - 1;
+    while (last > first && w[last] == 0.f) --last;
+    if (first > 0) {
+      for (int k = 0; k + first < taps; ++k) w[k] = w[k + first];
+      for (int k = taps - first; k < taps; ++k) w[k] = 0.f;
+      starts[o] += first;
+    }
+    if (last - first + 1 > eff) eff = last - first + 1;
+  }
+  return eff;
+}
+
+// Which marching kernel may run the ROW axis of a (compacted) table: 1 = up (taps <= 3),
+// 2 / 3 = down with 4 / 6 slots (output o + NSLOT must start after output o has ended), 0 = gather only.
+int resample_mode(int n_out, int taps, const int32_t* starts) {
+  if (taps <= 3) return 1;
+  for (int o = 1; o < n_out; ++o)
+    if (starts[o] < starts[o - 1]) return 0;
+  const int slots[2] = {4, 6};
+  for (int m = 0; m < 2; ++m) {
+    bool ok = true;
+    for (int o = 0; o + slots[m] < n_out && ok; ++o) ok = starts[o + slots[m]] - starts[o] >= taps;
+    if (ok) return 2 + m;
+  }
+  return 0;
+}
+
 int resample2d(const b200_tensor* x, const b200_tensor* y, const int32_t* hs, const float* hw, int ht,
-               const int32_t* ws, const float* ww, int wt, int accumulate, cudaStream_t st) {
+               const int32_t* ws, const float* ww, int wt, int accumulate, int mode, cudaStream_t st) {
   B200_REQUIRE(x->n == y->n && x->c == y->c && x->dtype == y->dtype, B200_ERR_BAD_ARG,
                "resample2d: batch/channel/dtype mismatch");
   TView xv = view_of(x), yv = view_of(y);
   const bool vec = vec_aligned(x, 8) && vec_aligned(y, 8);
+  static const int allow_march = getenv("B200_RESAMPLE_V") ? atoi(getenv("B200_RESAMPLE_V")) : 1;
+  if (allow_march && mode > 0 && vec && x->dtype == B200_BF16 && y->n <= 65535 && (mode != 1 || ht <= 3)) {
+    RsArgs a;
+    a.x = reinterpret_cast<const __nv_bfloat16*>(x->data); a.x_sn = x->stride_n; a.x_sh = x->stride_h; a.x_sw = x->stride_w;
+    a.xh = x->h; a.xw = x->w;
+    a.y = reinterpret_cast<__nv_bfloat16*>(y->data); a.y_sn = y->stride_n; a.y_sh = y->stride_h; a.y_sw = y->stride_w;
+    a.yh = y->h; a.yw = y->w;
+    a.chunks = y->c / 8;
+    a.hs = hs; a.hw = hw; a.ht = ht; a.ws = ws; a.ww = ww; a.wt = wt;
+    a.accumulate = accumulate;
+    const int bx = (int)(((long long)y->w * a.chunks + NT - 1) / NT);
+    // rows per thread: long enough to amortise the first rows of a segment, short enough to fill the GPU
+    const long long base_blocks = (long long)bx * y->n;
+    int nseg = (int)((6LL * sm_count() + base_blocks - 1) / base_blocks);
+    const int min_rows = mode == 1 ? 8 : 4;
+    if (nseg > (y->h + min_rows - 1) / min_rows) nseg = (y->h + min_rows - 1) / min_rows;
+    if (nseg < 1) nseg = 1;
+    a.seg = (y->h + nseg - 1) / nseg;
+    nseg = (y->h + a.seg - 1) / a.seg;
+    dim3 grid((unsigned)bx, (unsigned)nseg, (unsigned)y->n);
+    if (mode == 1) {
+      if (ht == 1) resample_up_kernel<1><<<grid, NT, 0, st>>>(a);
+      else if (ht == 2) resample_up_kernel<2><<<grid, NT, 0, st>>>(a);
+      else resample_up_kernel<3><<<grid, NT, 0, st>>>(a);
+    } else if (mode == 2) {
+      resample_down_kernel<4><<<grid, NT, 0, st>>>(a);
+    } else {
+      resample_down_kernel<6><<<grid, NT, 0, st>>>(a);
+    }
+    return check_launch("resample_march_kernel");
+  }
   B200_DISPATCH_DTYPE(x->dtype, T, {
     if (vec && y->h <= 65535 && y->n <= 65535) {
       dim3 grid((unsigned)(((long long)y->w * (y->c / 8) + NT - 1) / NT), (unsigned)y->h, (unsigned)y->n);
-      resample_vec_kernel<T><<<grid, NT, 0, st>>>(xv, yv, hs, hw, ht, ws, ww, wt, accumulate);
+      resample_vec_kernel<T, false><<<grid, NT, 0, st>>>(xv, yv, hs, hw, ht, ws, ww, wt, accumulate);
     } else {
       long long total = (long long)y->n * y->h * y->w * y->c;
       resample_scalar_kernel<T><<<grid_for(total), NT, 0, st>>>(xv, yv, hs, hw, ht, ws, ww, wt, accumulate, total);

@@ -174,26 +174,42 @@ class ResamplePlan:
                                             t_starts.ctypes.data, t_weights.ctypes.data, t_taps)
         if rc < 0:
             check(rc, "resample_plan_transpose")
-        self.taps, self.t_taps = taps, t_taps
-        self.host = (starts, weights, t_starts, t_weights)
-        self.starts = torch.from_numpy(starts).to(device)
-        self.weights = torch.from_numpy(weights).to(device)
-        self.t_starts = torch.from_numpy(t_starts).to(device)
-        self.t_weights = torch.from_numpy(t_weights).to(device)
+        self.host = (starts, weights, t_starts, t_weights)   # the raw ScaleAndTranslate tables (oracle-comparable)
+        # device tables are the compacted ones (leading zero weights shifted out, rows re-packed to the
+        # effective tap count); `mode` / `t_mode` name the row-marching kernel that may walk them
+        cs, cw, self.taps, self.mode = self._compact(starts, weights)
+        ts, tw, self.t_taps, self.t_mode = self._compact(t_starts, t_weights)
+        self.compact_host = (cs, cw, ts, tw)
+        self.starts = torch.from_numpy(cs).to(device)
+        self.weights = torch.from_numpy(cw).to(device)
+        self.t_starts = torch.from_numpy(ts).to(device)
+        self.t_weights = torch.from_numpy(tw).to(device)
+
+    @staticmethod
+    def _compact(starts, weights):
+        L = lib()
+        st, w = starts.copy(), np.ascontiguousarray(weights.copy())
+        n_out, taps = w.shape
+        eff = int(L.b200_resample_compact(n_out, taps, st.ctypes.data, w.ctypes.data))
+        if eff < 0:
+            check(eff, "resample_compact")
+        w = np.ascontiguousarray(w[:, :eff])
+        mode = int(L.b200_resample_mode(n_out, eff, st.ctypes.data))
+        return st, w, eff, max(mode, 0)
 
 
 def resample2d(x, y, plan_h: ResamplePlan, plan_w: ResamplePlan, accumulate=False):
-    check(lib().b200_resample2d(tdesc(x), tdesc(y), _ptr(plan_h.starts), _ptr(plan_h.weights), plan_h.taps,
-                                _ptr(plan_w.starts), _ptr(plan_w.weights), plan_w.taps, int(accumulate), _stream()),
-          "resample2d")
+    check(lib().b200_resample2d_ex(tdesc(x), tdesc(y), _ptr(plan_h.starts), _ptr(plan_h.weights), plan_h.taps,
+                                   _ptr(plan_w.starts), _ptr(plan_w.weights), plan_w.taps, int(accumulate), plan_h.mode,
+                                   _stream()), "resample2d")
     return y
 
 
 def resample2d_bwd(dy, dx, plan_h: ResamplePlan, plan_w: ResamplePlan, accumulate=False):
     """dx (+)= R^T dy: the same gather kernel over the transposed tables."""
-    check(lib().b200_resample2d(tdesc(dy), tdesc(dx), _ptr(plan_h.t_starts), _ptr(plan_h.t_weights), plan_h.t_taps,
-                                _ptr(plan_w.t_starts), _ptr(plan_w.t_weights), plan_w.t_taps, int(accumulate),
-                                _stream()), "resample2d(bwd)")
+    check(lib().b200_resample2d_ex(tdesc(dy), tdesc(dx), _ptr(plan_h.t_starts), _ptr(plan_h.t_weights), plan_h.t_taps,
+                                   _ptr(plan_w.t_starts), _ptr(plan_w.t_weights), plan_w.t_taps, int(accumulate),
+                                   plan_h.t_mode, _stream()), "resample2d(bwd)")
     return dx
 
 

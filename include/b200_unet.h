@@ -161,6 +161,17 @@ int b200_resample_plan_transpose(int in_size, int out_size, int taps, const int3
 int b200_resample2d(const b200_tensor* x, const b200_tensor* y, const int32_t* h_starts,
                     const float* h_weights, int h_taps, const int32_t* w_starts, const float* w_weights,
                     int w_taps, int accumulate, void* stream);
+/* Optional table preparation for the row-marching kernels (host, in place): shift leading zero weights
+ * out of every row and return the effective tap count (rows keep their pitch `taps`; re-pack to that
+ * count before uploading); then ask which kernel may walk the ROW axis of the compacted table:
+ * 0 = gather only, 1 = "up" (taps <= 3), 2 / 3 = "down" with 4 / 6 accumulator slots. */
+int b200_resample_compact(int n_out, int taps, int32_t* starts /*host*/, float* weights /*host*/);
+int b200_resample_mode(int n_out, int taps, const int32_t* starts /*host*/);
+/* b200_resample2d with the row-axis kernel chosen by `h_mode` (from b200_resample_mode on h_starts);
+ * bf16 tensors with C % 8 == 0 take the marching kernels, everything else the gather kernel. */
+int b200_resample2d_ex(const b200_tensor* x, const b200_tensor* y, const int32_t* h_starts,
+                       const float* h_weights, int h_taps, const int32_t* w_starts, const float* w_weights,
+                       int w_taps, int accumulate, int h_mode, void* stream);
 
 /* ---- keras MaxPooling2D(2) -- seg :351, unet_vinillia.py:62 --------------- */
 int b200_maxpool2_fwd(const b200_tensor* x, const b200_tensor* y, void* stream);

@@ -54,6 +54,45 @@ def test_resample_plan_matches_oracle_tables():
     assert ops.resize_extent(50, 0.3) == 16 and ops.resize_extent(256, 0.7) == 180 and ops.resize_extent(1, 0.25) == 1
 
 
+def test_resample_compaction_keeps_the_operator_and_picks_a_marching_kernel():
+    """The compacted device tables (leading zeros shifted out, re-packed) describe the same dense
+    resize matrix, and b200_resample_mode classifies the row axis: up (taps <= 3) for up-sampling and
+    transposed down-sampling, down (4 or 6 slots) for antialiased down-sampling and transposed up-sampling."""
+    import b200unet.ops as ops
+    from oracle import resize_np
+    for (a, b) in [(128, 32), (32, 128), (63, 45), (45, 63), (256, 180), (180, 256), (8, 2), (2, 8), (50, 16), (1, 2),
+                   (2, 1), (100, 90), (90, 100), (1024, 256)]:
+        plan = ops.ResamplePlan(a, b, True, "cpu")
+        mat = resize_np.resize_matrix(a, b, True)
+        cs, cw, ts, tw = plan.compact_host
+        assert cw.shape[1] == plan.taps and tw.shape[1] == plan.t_taps
+        fwd = np.zeros((b, a), np.float32)
+        for o in range(b):
+            for k in range(cw.shape[1]):
+                if cw[o, k] != 0:
+                    fwd[o, cs[o] + k] += cw[o, k]
+        assert np.array_equal(fwd, mat), (a, b)
+        back = np.zeros((a, b), np.float32)
+        for i in range(a):
+            for k in range(tw.shape[1]):
+                if tw[i, k] != 0:
+                    back[i, ts[i] + k] += tw[i, k]
+        assert np.array_equal(back, mat.T), (a, b)
+        for st, w, mode in ((cs, cw, plan.mode), (ts, tw, plan.t_mode)):
+            taps = w.shape[1]
+            if taps <= 3:
+                assert mode == 1
+            elif mode in (2, 3):
+                ns = 4 if mode == 2 else 6
+                assert all(st[o + ns] - st[o] >= taps for o in range(len(st) - ns))
+        if b > a:
+            assert plan.mode == 1 and plan.taps <= 2          # bilinear up-sampling: at most two taps
+        if (a, b) == (128, 32):
+            assert plan.taps == 8 and plan.mode == 2 and plan.t_mode == 1
+        if (a, b) == (32, 128):
+            assert plan.t_taps == 8 and plan.t_mode == 2
+
+
 def test_builders_match_reference_param_totals_and_names():
     from b200unet import builders as B
     from b200unet.keras import clear_session

@@ -334,6 +334,38 @@ def test_resample(dtype, sizes, c, aa):
     assert relerr(dx, xr.grad + f32(base)) < TOL[dtype]
 
 
+@pytest.mark.parametrize("sizes", [((128, 128), (32, 32)), ((32, 32), (128, 128)), ((63, 63), (45, 45)), ((45, 45), (63, 63)),
+                                   ((100, 60), (90, 54)), ((90, 54), (100, 60)), ((33, 17), (9, 5)), ((9, 5), (33, 17)),
+                                   ((64, 64), (13, 13)), ((256, 256), (180, 180))])
+@pytest.mark.parametrize("c", [64, 128, 8])
+def test_resample_marching_kernels(sizes, c):
+    """bf16, C % 8 == 0: the row-marching kernels (up / down, 4 and 6 slots, several row segments) against
+    the oracle, forward and accumulate-backward, on dense tensors and on a channel slice of a wider one."""
+    ops, K = _ops(), _K()
+    (h, w), (oh, ow) = sizes
+    dtype = torch.bfloat16
+    n = 3
+    x = rand((n, h, w, c), 81, dtype)
+    dy = rand((n, oh, ow, c), 82, dtype)
+    ph = ops.ResamplePlan(h, oh, True, "cuda"); pw = ops.ResamplePlan(w, ow, True, "cuda")
+    assert ph.mode in (1, 2, 3) and ph.t_mode in (1, 2, 3), (ph.mode, ph.t_mode)
+    wide = torch.zeros((n, oh, ow, 2 * c), dtype=dtype, device="cuda")
+    y = wide[..., c:]
+    ops.resample2d(x, y, ph, pw)
+    base = rand((n, h, w, c), 83, dtype)
+    dx = base.clone()
+    ops.resample2d_bwd(dy, dx, ph, pw, accumulate=True)
+    dx2 = torch.empty_like(dx)
+    ops.resample2d_bwd(dy, dx2, ph, pw, accumulate=False)
+    xr = f32(x).requires_grad_()
+    yr = K.resize_bilinear(xr, oh, ow, True)
+    (yr * f32(dy)).sum().backward()
+    assert relerr(y, yr) < TOL[dtype]
+    assert float(wide[..., :c].abs().max()) == 0.0
+    assert relerr(dx, xr.grad + f32(base)) < TOL[dtype]
+    assert relerr(dx2, xr.grad) < TOL[dtype]
+
+
 def test_resample_tables_match_oracle():
     ops = _ops()
     from oracle import resize_np
