@@ -42,19 +42,20 @@ struct ConvLnArgs {
 };
 bool conv_tc_ln_supported(int cout);
 int conv_tc_launch(const b200_tensor*, const void*, int, int, int, int, const float*, const b200_tensor*, int, int, cudaStream_t,
-                   const ConvLnArgs* ln = nullptr);
+                   const ConvLnArgs* ln = nullptr, int ks = 3);
 int umma_probe(const void*, int, const void*, int, int, int, int, float*, cudaStream_t);
 int umma_rate(int, int, int, long long*, int, cudaStream_t);
 bool stem_supported(const b200_tensor*, const b200_tensor*, int);
 int stem_fprop(const b200_tensor*, const void*, const float*, const b200_tensor*, int, cudaStream_t);
 int stem_wgrad(const b200_tensor*, const b200_tensor*, float*, cudaStream_t);
+int im2col3x3(const b200_tensor*, const b200_tensor*, cudaStream_t);
 bool head_supported(const b200_tensor*, const b200_tensor*, int);
 int head_fprop(const b200_tensor*, const void*, const float*, const b200_tensor*, int, cudaStream_t);
 int head_dgrad(const b200_tensor*, const void*, const b200_tensor*, int, cudaStream_t);
 int head_wgrad(const b200_tensor*, const b200_tensor*, float*, cudaStream_t);
 bool wgrad_tc_supported(const b200_tensor*, const b200_tensor*, int);
-size_t wgrad_tc_workspace(const b200_tensor*, const b200_tensor*);
-int wgrad_tc_launch(const b200_tensor*, const b200_tensor*, float*, void*, size_t, cudaStream_t);
+size_t wgrad_tc_workspace(const b200_tensor*, const b200_tensor*, int);
+int wgrad_tc_launch(const b200_tensor*, const b200_tensor*, float*, void*, size_t, cudaStream_t, int);
 int layernorm_fwd(const b200_tensor*, const float*, const float*, float, int, const b200_tensor*, float*, float*, cudaStream_t);
 int layernorm_bwd(const b200_tensor*, const b200_tensor*, const float*, const float*, const float*, const float*, int,
                   const b200_tensor*, float*, float*, float*, cudaStream_t);
@@ -128,11 +129,11 @@ int b200_conv2d_fprop(const b200_tensor* x, const b200_filter* f, const float* b
   B200_REQUIRE(x->c == f->cin && y->c == f->cout && x->n == y->n && x->h == y->h && x->w == y->w, B200_ERR_BAD_ARG,
                "conv2d_fprop: shapes x[%d,%d,%d,%d] y[%d,%d,%d,%d] filter cin=%d cout=%d disagree", x->n, x->h, x->w,
                x->c, y->n, y->h, y->w, y->c, f->cin, f->cout);
-  const bool tc_ok = f->kh == 3 && f->kw == 3 && f->dtype == B200_BF16 &&
-                     (act == B200_ACT_NONE || act == B200_ACT_RELU) && conv_tc_supported(x, f->cin, f->cout, y, 3);
+  const bool tc_ok = (f->kh == 3 || f->kh == 1) && f->kw == f->kh && f->dtype == B200_BF16 &&
+                     (act == B200_ACT_NONE || act == B200_ACT_RELU) && conv_tc_supported(x, f->cin, f->cout, y, f->kh);
   if (algo == B200_ALGO_TCGEN05 || (algo == B200_ALGO_AUTO && tc_ok)) {
     B200_REQUIRE(tc_ok, B200_ERR_UNSUPPORTED, "conv2d_fprop: tcgen05 path does not support this shape/dtype");
-    return conv_tc_launch(x, f->hwio, f->cin, f->cout, 0, 1, bias, y, act, 0, ST(stream));
+    return conv_tc_launch(x, f->hwio, f->cin, f->cout, 0, 1, bias, y, act, 0, ST(stream), nullptr, f->kh);
   }
   if (algo == B200_ALGO_AUTO && f->dtype == x->dtype && f->kh == f->kw) {
     if (stem_supported(x, y, f->kh) && act != B200_ACT_SIGMOID) return stem_fprop(x, f->hwio, bias, y, act, ST(stream));
@@ -150,11 +151,12 @@ int b200_conv2d_ln_fprop(const b200_tensor* x, const b200_filter* f, const float
                "conv2d_ln_fprop: shapes disagree with filter cin=%d cout=%d", f->cin, f->cout);
   const bool have_z = z && z->data;
   if (have_z) B200_REQUIRE(same_shape(z, y) && z->dtype == y->dtype, B200_ERR_BAD_ARG, "conv2d_ln_fprop: z/y mismatch");
-  const bool fused = f->kh == 3 && f->kw == 3 && f->dtype == B200_BF16 && conv_tc_supported(x, f->cin, f->cout, y, 3) &&
-                     conv_tc_ln_supported(f->cout) && algo != B200_ALGO_SIMT;
+  const bool fused = (f->kh == 3 || f->kh == 1) && f->kw == f->kh && f->dtype == B200_BF16 &&
+                     conv_tc_supported(x, f->cin, f->cout, y, f->kh) && conv_tc_ln_supported(f->cout) &&
+                     algo != B200_ALGO_SIMT;
   if (fused) {
     ConvLnArgs ln{gamma, beta, eps, relu, have_z ? z : nullptr, mean, rstd};
-    return conv_tc_launch(x, f->hwio, f->cin, f->cout, 0, 1, bias, y, B200_ACT_NONE, 0, ST(stream), &ln);
+    return conv_tc_launch(x, f->hwio, f->cin, f->cout, 0, 1, bias, y, B200_ACT_NONE, 0, ST(stream), &ln, f->kh);
   }
   // composition: convolution into z (or into y when the caller keeps no z), then the stand-alone LayerNorm
   const b200_tensor* zz = have_z ? z : y;
@@ -171,10 +173,12 @@ int b200_conv2d_dgrad(const b200_tensor* dy, const b200_filter* f, const b200_te
                B200_ERR_BAD_ARG, "conv2d_dgrad: shapes disagree with filter cin=%d cout=%d", f->cin, f->cout);
   // dgrad is a convolution of dy (K = cout) producing cin channels; its B operand [tap][cin][cout]
   // is the HWIO kernel itself, read with the tap order reversed.
-  const bool tc_ok = f->kh == 3 && f->kw == 3 && f->dtype == B200_BF16 && conv_tc_supported(dy, f->cout, f->cin, dx, 3);
+  const bool tc_ok = (f->kh == 3 || f->kh == 1) && f->kw == f->kh && f->dtype == B200_BF16 &&
+                     conv_tc_supported(dy, f->cout, f->cin, dx, f->kh);
   if (algo == B200_ALGO_TCGEN05 || (algo == B200_ALGO_AUTO && tc_ok)) {
     B200_REQUIRE(tc_ok, B200_ERR_UNSUPPORTED, "conv2d_dgrad: tcgen05 path does not support this shape/dtype");
-    return conv_tc_launch(dy, f->hwio, f->cout, f->cin, 1, 0, nullptr, dx, B200_ACT_NONE, accumulate, ST(stream));
+    return conv_tc_launch(dy, f->hwio, f->cout, f->cin, 1, 0, nullptr, dx, B200_ACT_NONE, accumulate, ST(stream), nullptr,
+                          f->kh);
   }
   if (algo == B200_ALGO_AUTO && f->dtype == dx->dtype && f->kh == f->kw && head_supported(dx, dy, f->kh))
     return head_dgrad(dy, f->hwio, dx, accumulate, ST(stream));
@@ -182,9 +186,9 @@ int b200_conv2d_dgrad(const b200_tensor* dy, const b200_filter* f, const b200_te
 }
 
 size_t b200_conv2d_wgrad_workspace(const b200_tensor* x, const b200_tensor* dy, int kh, int kw, int algo) {
-  if (algo == B200_ALGO_SIMT || kh != 3 || kw != 3) return 0;
+  if (algo == B200_ALGO_SIMT || kh != kw || (kh != 3 && kh != 1)) return 0;
   if (!wgrad_tc_supported(x, dy, kh)) return 0;
-  return wgrad_tc_workspace(x, dy);
+  return wgrad_tc_workspace(x, dy, kh);
 }
 
 int b200_conv2d_wgrad(const b200_tensor* x, const b200_tensor* dy, int kh, int kw, float* dw, void* ws, size_t ws_bytes,
@@ -196,13 +200,18 @@ int b200_conv2d_wgrad(const b200_tensor* x, const b200_tensor* dy, int kh, int k
   const bool tc_ok = wgrad_tc_supported(x, dy, kh);
   if (algo == B200_ALGO_TCGEN05 || (algo == B200_ALGO_AUTO && tc_ok)) {
     B200_REQUIRE(tc_ok, B200_ERR_UNSUPPORTED, "conv2d_wgrad: tcgen05 path does not support this shape/dtype");
-    return wgrad_tc_launch(x, dy, dw, ws, ws_bytes, ST(stream));
+    return wgrad_tc_launch(x, dy, dw, ws, ws_bytes, ST(stream), kh);
   }
   if (algo == B200_ALGO_AUTO) {
     if (stem_supported(x, dy, kh)) return stem_wgrad(x, dy, dw, ST(stream));
     if (head_supported(x, dy, kh)) return head_wgrad(x, dy, dw, ST(stream));
   }
   return conv_simt_wgrad(x, dy, kh, dw, ST(stream));
+}
+
+int b200_im2col3x3(const b200_tensor* x, const b200_tensor* xcol, void* stream) {
+  REQ_T(x, "x"); REQ_T(xcol, "xcol");
+  return im2col3x3(x, xcol, ST(stream));
 }
 
 int b200_filter_pack(const void* hwio, void* ohwi, int kh, int kw, int cin, int cout, int dtype, void* stream) {

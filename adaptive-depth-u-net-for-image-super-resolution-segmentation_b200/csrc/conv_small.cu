@@ -303,6 +303,43 @@ head_wgrad_kernel(TView x, TView dy, float* __restrict__ dw, long long npix) {
 
 inline bool pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
 
+
+// ---------------------------------------------------------------------------
+// im2col of a narrow input (Cin*9 <= 64, i.e. the RGB stem): xcol[n,h,w, tap*Cin + c] = x[n, h+kh-1, w+kw-1, c]
+// (zero outside the image, zero for channels >= 9*Cin), 64 bf16 channels per pixel.  The 3x3 stem
+// convolution then IS a 1x1 convolution of xcol with the HWIO kernel read as a [9*Cin -> 64][Cout]
+// matrix, which runs on the tcgen05 kernels (fprop with the fused LayerNorm epilogue, wgrad) instead
+// of the FMA-bound SIMT stem kernels.  8 threads per pixel, one 16-byte chunk each: a warp writes
+// 512 contiguous bytes.
+// ---------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+im2col3x3_kernel(TView x, __nv_bfloat16* __restrict__ xcol, long long col_sw, int H, int W, int cin, long long npix) {
+  const T* __restrict__ xp = reinterpret_cast<const T*>(x.data);
+  const int q = threadIdx.x & 7;
+  for (long long p = ((long long)blockIdx.x * 256 + threadIdx.x) >> 3; p < npix; p += ((long long)gridDim.x * 256) >> 3) {
+    const int w = (int)(p % W);
+    const long long t = p / W;
+    const int h = (int)(t % H);
+    const long long n = t / H;
+    uint32_t out[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float v[2];
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int k = q * 8 + i * 2 + e;
+        const int tap = k / cin, c = k - tap * cin;
+        const int ih = h + tap / 3 - 1, iw = w + tap % 3 - 1;
+        v[e] = (tap < 9 && ih >= 0 && ih < H && iw >= 0 && iw < W) ? ldf(xp + n * x.sn + (long long)ih * x.sh + (long long)iw * x.sw + c) : 0.f;
+      }
+      __nv_bfloat162 b = __floats2bfloat162_rn(v[0], v[1]);
+      out[i] = *reinterpret_cast<uint32_t*>(&b);
+    }
+    *reinterpret_cast<uint4*>(xcol + p * col_sw + q * 8) = make_uint4(out[0], out[1], out[2], out[3]);
+  }
+}
+
 }  // namespace
 
 // ---- dispatch helpers ---------------------------------------------------------------------------
@@ -330,6 +367,25 @@ int stem_wgrad(const b200_tensor* x, const b200_tensor* dy, float* dw, cudaStrea
   TView xv = view_of(x), dv = view_of(dy);
   B200_DISPATCH_DTYPE(x->dtype, T, { stem_wgrad_kernel<T><<<grid, 256, 0, st>>>(xv, dv, dw, tiles_w, tiles_h, total); });
   return check_launch("stem_wgrad_kernel");
+}
+
+// xcol: dense or evenly spaced [N,H,W,64] bf16
+int im2col3x3(const b200_tensor* x, const b200_tensor* xcol, cudaStream_t st) {
+  B200_REQUIRE(x->c * 9 <= 64 && xcol->c == 64 && xcol->dtype == B200_BF16 && x->n == xcol->n && x->h == xcol->h &&
+                   x->w == xcol->w,
+               B200_ERR_BAD_ARG, "im2col3x3: need Cin*9 <= 64 and a [N,H,W,64] bf16 destination of the same extent");
+  TView cv = view_of(xcol);
+  B200_REQUIRE(cv.lin && (reinterpret_cast<uintptr_t>(xcol->data) % 16 == 0) && (xcol->stride_w * 2) % 16 == 0,
+               B200_ERR_UNSUPPORTED, "im2col3x3: destination pixels must be evenly spaced and 16-byte aligned");
+  const long long npix = (long long)x->n * x->h * x->w;
+  long long blocks = (npix * 8 + 255) / 256;
+  if (blocks > 16LL * sm_count()) blocks = 16LL * sm_count();
+  TView xv = view_of(x);
+  B200_DISPATCH_DTYPE(x->dtype, T, {
+    im2col3x3_kernel<T><<<(int)blocks, 256, 0, st>>>(xv, reinterpret_cast<__nv_bfloat16*>(xcol->data), xcol->stride_w, x->h, x->w,
+                                                    x->c, npix);
+  });
+  return check_launch("im2col3x3_kernel");
 }
 
 bool head_supported(const b200_tensor* x, const b200_tensor* y, int ks) {

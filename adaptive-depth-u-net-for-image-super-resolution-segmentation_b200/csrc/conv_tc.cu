@@ -100,6 +100,7 @@ struct ConvTcParams {
   int tma_store, nslots;
   int b_mn;   // 1: B operand is MN-major (fprop reads the Keras HWIO kernel [tap][cin][cout] as is); 0: K-major (dgrad)
   int Kc;     // K total (input channels of this convolution)
+  int ntaps, tap0;  // 9, 0 for a 3x3 filter; 1, 4 for a 1x1 filter (centre tap only; its weights are matrix block 0)
   // small images (H <= 7) are stacked: one tile holds `nb` images, each `srows` = H+2 window rows
   int nb, srows, win_bytes;
   const float* bias;
@@ -136,9 +137,9 @@ __device__ __forceinline__ void load_weight_tile(const ConvTcParams& p, const CU
                                                  uint32_t bar, int kb, int tap, int j) {
   if (p.b_mn) {
     for (int a = 0; a < p.BN / 64; ++a)
-      tma_load_2d(dst + a * 8192, tm_b, bar, j * p.BN + a * 64, tap * p.Kc + kb * 64);
+      tma_load_2d(dst + a * 8192, tm_b, bar, j * p.BN + a * 64, (tap - p.tap0) * p.Kc + kb * 64);
   } else {
-    tma_load_2d(dst, tm_b, bar, kb * 64, (p.tap_rev ? 8 - tap : tap) * p.Cout + j * p.BN);
+    tma_load_2d(dst, tm_b, bar, kb * 64, ((p.tap_rev ? 8 - tap : tap) - p.tap0) * p.Cout + j * p.BN);
   }
 }
 
@@ -176,12 +177,16 @@ struct StoreRing {
 
   __device__ __forceinline__ void flush() {
     if (issuer && d_have) {
-      tma_store_4d(d_which ? tm_z : tm_y, d_slot, d_c, d_w, d_h, d_n);
-      bulk_commit();
+      if (dbg != 6) {
+        tma_store_4d(d_which ? tm_z : tm_y, d_slot, d_c, d_w, d_h, d_n);
+        bulk_commit();
+      }
       d_have = 0;
     }
   }
+  int dbg;
   __device__ __forceinline__ uint32_t begin() {
+    if (dbg == 4) { flush(); return stg0 + (uint32_t)slot * SLOT_BYTES; }
     if (issuer) {
       if (nslots == 2) bulk_wait_read<0>();
       else if (nslots == 3) bulk_wait_read<1>();
@@ -193,7 +198,7 @@ struct StoreRing {
     return stg0 + (uint32_t)slot * SLOT_BYTES;
   }
   __device__ __forceinline__ void end(uint32_t slot_addr, int which, int c, int w, int h, int n) {
-    fence_proxy_async();
+    if (dbg != 3) fence_proxy_async();
     if (issuer) { d_have = 1; d_which = which; d_slot = slot_addr; d_c = c; d_w = w; d_h = h; d_n = n; }
     if (++slot == nslots) slot = 0;
   }
@@ -298,7 +303,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
         for (int kb = 0; kb < p.KB; ++kb)
           for (int tap = 0; tap < 9; ++tap) {
             if (!((p.live_mask >> tap) & 1)) continue;
-            const int slot = kb * 9 + tap;
+            const int slot = kb * p.ntaps + tap - p.tap0;
             mbar_arrive_expect_tx(smem_u32(&bar_full_b[slot]), wt_bytes);
             load_weight_tile(p, &tm_b, wt0 + slot * wt_bytes, smem_u32(&bar_full_b[slot]), kb, tap, 0);
           }
@@ -343,7 +348,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
       if (p.resident) {   // the weights are loaded once: wait for every tile up front
         for (int kb = 0; kb < p.KB; ++kb)
           for (int tap = 0; tap < 9; ++tap)
-            if ((p.live_mask >> tap) & 1) mbar_wait(smem_u32(&bar_full_b[kb * 9 + tap]), 0);
+            if ((p.live_mask >> tap) & 1) mbar_wait(smem_u32(&bar_full_b[kb * p.ntaps + tap - p.tap0]), 0);
         tc_fence_after();
       }
       for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
@@ -376,7 +381,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
               if (!((p.live_mask >> tap) & 1)) continue;
               uint32_t b_lo;
               if (p.resident) {
-                b_lo = ((wt0 >> 4) | b_lbo) + (uint32_t)(kb * 9 + tap) * wt_step;
+                b_lo = ((wt0 >> 4) | b_lbo) + (uint32_t)(kb * p.ntaps + tap - p.tap0) * wt_step;
               } else {
                 mbar_wait(smem_u32(&bar_full_b[sb]), pb);
                 tc_fence_after();
@@ -412,7 +417,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
     StoreRing ring;
     ring.stg0 = stg0; ring.nslots = p.nslots; ring.slot = 0; ring.issuer = threadIdx.x == 64;
     ring.d_have = 0; ring.d_which = 0; ring.d_c = ring.d_w = ring.d_h = ring.d_n = 0; ring.d_slot = 0;
-    ring.tm_y = &tm_y; ring.tm_z = &tm_z;
+    ring.tm_y = &tm_y; ring.tm_z = &tm_z; ring.dbg = p.debug;
     int as = 0, pa = 0;
     for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
       int j, tw, th, n;
@@ -639,7 +644,7 @@ umma_rate_kernel(int n, int iters, int a_stride_bytes, long long* __restrict__ c
 }  // namespace
 
 bool conv_tc_supported(const b200_tensor* x, int cin, int cout, const b200_tensor* y, int ks) {
-  if (ks != 3) return false;
+  if (ks != 3 && ks != 1) return false;
   if (x->dtype != B200_BF16 || y->dtype != B200_BF16) return false;
   if (cin % 64 != 0 || cout % 64 != 0) return false;
   if (cout > 64 && cout % 128 != 0) return false;
@@ -674,8 +679,9 @@ struct ConvLnArgs {
 bool conv_tc_ln_supported(int cout) { return cout == 64 || cout == 128; }
 
 int conv_tc_launch(const b200_tensor* x_in, const void* wmat, int cin, int cout, int tap_rev, int b_mn, const float* bias,
-                   const b200_tensor* y_in, int act, int accumulate, cudaStream_t st, const ConvLnArgs* ln = nullptr) {
-  B200_REQUIRE(conv_tc_supported(x_in, cin, cout, y_in, 3), B200_ERR_UNSUPPORTED,
+                   const b200_tensor* y_in, int act, int accumulate, cudaStream_t st, const ConvLnArgs* ln = nullptr,
+                   int ks = 3) {
+  B200_REQUIRE(conv_tc_supported(x_in, cin, cout, y_in, ks), B200_ERR_UNSUPPORTED,
                "conv3x3 tcgen05: unsupported shape cin=%d cout=%d (need bf16, multiples of 64, 16-byte aligned)", cin,
                cout);
   B200_REQUIRE(x_in->n == y_in->n && x_in->h == y_in->h && x_in->w == y_in->w && x_in->c == cin && y_in->c == cout,
@@ -684,7 +690,7 @@ int conv_tc_launch(const b200_tensor* x_in, const void* wmat, int cin, int cout,
   const b200_tensor *x = x_in, *y = y_in;
   int live_mask = 0;
   for (int t = 0; t < 9; ++t) {
-    const bool dead = (x_in->h == 1 && t / 3 != 1) || (x_in->w == 1 && t % 3 != 1);
+    const bool dead = (x_in->h == 1 && t / 3 != 1) || (x_in->w == 1 && t % 3 != 1) || (ks == 1 && t != 4);
     if (!dead) live_mask |= 1 << t;
   }
   b200_tensor zf;
@@ -717,6 +723,8 @@ int conv_tc_launch(const b200_tensor* x_in, const void* wmat, int cin, int cout,
   { const char* dbg = getenv("B200_CONV_DEBUG"); p.debug = dbg ? atoi(dbg) : 0; }
   p.b_mn = b_mn;
   p.Kc = cin;
+  p.ntaps = ks == 1 ? 1 : 9;
+  p.tap0 = ks == 1 ? 4 : 0;
   p.live_mask = live_mask;
   const int wt_bytes = p.BN * 128;
   // (>= 2 KB: a stacked-image store box may span 18 tile rows, i.e. read 2 KB past its 16-row slot; those rows are
@@ -724,7 +732,7 @@ int conv_tc_launch(const b200_tensor* x_in, const void* wmat, int cin, int cout,
   int bias_bytes = ((cout * 4 * (ln ? 3 : 1) + 1023) / 1024) * 1024;
   if (bias_bytes < 2048) bias_bytes = 2048;
   const int budget = SMEM_LIMIT - 1024 /*align slack*/ - 1024 /*static*/ - bias_bytes;
-  const int all_w = 9 * p.KB * wt_bytes;
+  const int all_w = p.ntaps * p.KB * wt_bytes;
   // output staging ring (TMA stores); gradient accumulation keeps the per-thread read-modify-write path
   p.tma_store = accumulate ? 0 : 1;
   B200_REQUIRE(!(ln && accumulate), B200_ERR_BAD_ARG, "conv3x3+LayerNorm tcgen05: accumulate is not supported");
@@ -732,9 +740,9 @@ int conv_tc_launch(const b200_tensor* x_in, const void* wmat, int cin, int cout,
   auto plan_smem = [&](int nslots, int min_windows) -> bool {
     const int left = budget - nslots * SLOT_BYTES;
     p.nslots = nslots;
-    p.resident = (p.n_tiles == 1 && 9 * p.KB <= MAX_WSLOTS && left - all_w >= min_windows * WIN_STAGE) ? 1 : 0;
+    p.resident = (p.n_tiles == 1 && p.ntaps * p.KB <= MAX_WSLOTS && left - all_w >= min_windows * WIN_STAGE) ? 1 : 0;
     if (p.resident) {
-      p.nsb = 9 * p.KB;
+      p.nsb = p.ntaps * p.KB;
       p.nsw = (left - all_w) / WIN_STAGE;
     } else {
       p.nsb = 4;
@@ -747,7 +755,9 @@ int conv_tc_launch(const b200_tensor* x_in, const void* wmat, int cin, int cout,
     plan_smem(0, 2);
   } else {
     // prefer resident weights; within that, as many slots as one tile's jobs while keeping 3 window stages
-    const int want = jobs_per_tile < 2 ? 2 : (jobs_per_tile > 4 ? 4 : jobs_per_tile);
+    static const int max_slots = getenv("B200_CONV_SLOTS") ? atoi(getenv("B200_CONV_SLOTS")) : 4;
+    const int want = max_slots < 2 ? 2 : (max_slots > 4 ? 4 : max_slots);
+    (void)jobs_per_tile;
     bool ok = false;
     for (int ns = want; ns >= 2 && !ok; --ns) ok = plan_smem(ns, 3) && p.resident;
     for (int ns = want; ns >= 2 && !ok; --ns) ok = plan_smem(ns, 2) && p.resident;
@@ -773,7 +783,8 @@ int conv_tc_launch(const b200_tensor* x_in, const void* wmat, int cin, int cout,
   CUtensorMap tm_x, tm_b, tm_y, tm_z;
   int rc = make_act_tmap(&tm_x, x, WIN_W, box_h, box_n);
   if (rc) return rc;
-  rc = b_mn ? make_mat_tmap(&tm_b, wmat, 9LL * cin, cout, 64) : make_mat_tmap(&tm_b, wmat, 9LL * cout, cin, p.BN);
+  rc = b_mn ? make_mat_tmap(&tm_b, wmat, (long long)p.ntaps * cin, cout, 64)
+            : make_mat_tmap(&tm_b, wmat, (long long)p.ntaps * cout, cin, p.BN);
   if (rc) return rc;
   // output boxes: {64 ch, 8, 16, 1}, or {64 ch, 8, H+2, nb} for stacked small images (rows past H are clipped)
   const int obox_h = p.nb > 1 || box_h != WIN_H ? box_h : TILE_H;

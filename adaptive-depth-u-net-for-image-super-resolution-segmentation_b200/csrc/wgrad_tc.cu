@@ -42,6 +42,7 @@ struct WgradParams {
   int N, H, W, Cin, Cout;
   int tiles_h, tiles_w, total_tiles, splits, cblocks, oblocks;
   int nb, ksteps, stage_bytes, zero_smem;   // stacked small images: nb images per tile, ksteps 16-pixel K steps
+  int ntaps;   // 9 (3x3 filter) or 1 (1x1 filter: only the centre tap of the window is accumulated)
   float* partial;  // [splits][9][Cin][Cout]
 };
 
@@ -134,6 +135,7 @@ wgrad3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
             const uint32_t b_lo = dz_lo + (uint32_t)ks * (2048u >> 4);
 #pragma unroll
             for (int pi = 0; pi < NPAIRS; ++pi) {
+              if (p.ntaps == 1 && pi != 2) continue;   // 1x1 filter: the pair that starts at the centre tap only
               const int t0 = pair_first(pi);
               const uint32_t lbo = (uint32_t)(tap_row(t0 + 1) - tap_row(t0)) * 128u;
               const uint32_t a_off = ((uint32_t)tap_row(t0) * 128u >> 4) | ((lbo >> 4) << 16);
@@ -155,9 +157,11 @@ wgrad3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
     mbar_wait(smem_u32(&bar_done), 0);
     tc_fence_after();
     for (int pi = 0; pi < NPAIRS; ++pi) {
+      if (p.ntaps == 1 && pi != 2) continue;
       const int tap = pair_first(pi) + half;
-      const bool dup = (pi == 4 && half == 0);   // rows 0..63 of the last pair repeat tap 7
-      float* dst = p.partial + (((long long)s * 9 + tap) * p.Cin + cb * 64 + ci) * p.Cout + ob * 64;
+      const bool dup = (pi == 4 && half == 0) || (p.ntaps == 1 && half == 1);   // rows 0..63 of the last pair repeat tap 7
+      const int tslot = p.ntaps == 1 ? 0 : tap;
+      float* dst = p.partial + (((long long)s * p.ntaps + tslot) * p.Cin + cb * 64 + ci) * p.Cout + ob * 64;
       for (int c0 = 0; c0 < 64; c0 += 32) {
         uint32_t v[32];
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(pi * 64 + c0), v);
@@ -223,13 +227,15 @@ static bool flatten_1x1(const b200_tensor* t, b200_tensor* out) {
   return true;
 }
 
-inline void plan(const b200_tensor* x_in, const b200_tensor* dy_in, WgradParams& p, WgradGeom& g) {
+inline void plan(const b200_tensor* x_in, const b200_tensor* dy_in, WgradParams& p, WgradGeom& g, int ks) {
   g.x = *x_in; g.dy = *dy_in;
+  p.ntaps = ks == 1 ? 1 : 9;
   g.live_mask = 0;
   for (int t = 0; t < 9; ++t) {
     const bool dead = (x_in->h == 1 && t / 3 != 1) || (x_in->w == 1 && t % 3 != 1);
     if (!dead) g.live_mask |= 1 << t;
   }
+  if (ks == 1) g.live_mask = 1;   // the reduce kernel sees a single tap block
   b200_tensor xf, yf;
   if (flatten_1x1(x_in, &xf) && flatten_1x1(dy_in, &yf)) { g.x = xf; g.dy = yf; }
   const b200_tensor* x = &g.x;
@@ -265,7 +271,7 @@ inline void plan(const b200_tensor* x_in, const b200_tensor* dy_in, WgradParams&
 }  // namespace
 
 bool wgrad_tc_supported(const b200_tensor* x, const b200_tensor* dy, int ks) {
-  if (ks != 3) return false;
+  if (ks != 3 && ks != 1) return false;
   if (x->dtype != B200_BF16 || dy->dtype != B200_BF16) return false;
   if (x->c % 64 != 0 || dy->c % 64 != 0) return false;
   auto ok = [](const b200_tensor* t) {
@@ -275,19 +281,19 @@ bool wgrad_tc_supported(const b200_tensor* x, const b200_tensor* dy, int ks) {
   return ok(x) && ok(dy);
 }
 
-size_t wgrad_tc_workspace(const b200_tensor* x, const b200_tensor* dy) {
+size_t wgrad_tc_workspace(const b200_tensor* x, const b200_tensor* dy, int ks) {
   WgradParams p;
   WgradGeom g;
-  plan(x, dy, p, g);
-  return sizeof(float) * (size_t)p.splits * 9 * p.Cin * p.Cout;
+  plan(x, dy, p, g, ks);
+  return sizeof(float) * (size_t)p.splits * p.ntaps * p.Cin * p.Cout;
 }
 
 int wgrad_tc_launch(const b200_tensor* x, const b200_tensor* dy, float* dw, void* ws, size_t ws_bytes,
-                    cudaStream_t st) {
+                    cudaStream_t st, int ks) {
   WgradParams p;
   WgradGeom g;
-  plan(x, dy, p, g);
-  const size_t need = sizeof(float) * (size_t)p.splits * 9 * p.Cin * p.Cout;
+  plan(x, dy, p, g, ks);
+  const size_t need = sizeof(float) * (size_t)p.splits * p.ntaps * p.Cin * p.Cout;
   B200_REQUIRE(ws && ws_bytes >= need, B200_ERR_BAD_ARG, "conv2d_wgrad: workspace too small (%zu < %zu bytes)",
                ws_bytes, need);
   B200_REQUIRE((uintptr_t)ws % 16 == 0 && (uintptr_t)dw % 16 == 0, B200_ERR_BAD_ARG,
@@ -308,7 +314,7 @@ int wgrad_tc_launch(const b200_tensor* x, const b200_tensor* dy, float* dw, void
   wgrad3x3_tc_kernel<<<grid, NTHREADS, smem, st>>>(tm_x, tm_dz, p);
   int rc2 = check_launch("wgrad3x3_tc_kernel");
   if (rc2) return rc2;
-  const long long count = 9LL * p.Cin * p.Cout;
+  const long long count = (long long)p.ntaps * p.Cin * p.Cout;
   long long blocks = (count / 4 + 63) / 64;
   if (blocks > 8LL * sm_count()) blocks = 8LL * sm_count();
   wgrad_reduce_kernel<<<(int)blocks, 256, 0, st>>>(p.partial, dw, count, p.splits, g.live_mask, (long long)p.Cin * p.Cout);  // counted by check_launch

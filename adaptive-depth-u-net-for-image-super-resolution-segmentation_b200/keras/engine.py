@@ -231,6 +231,10 @@ class Plan:
                 list.append(inner, fn)
 
         S = self.steps = _Tagged()
+        for op in self.ops:   # narrow-input 3x3 convs (the RGB stem): im2col tensor for the tcgen05 1x1 path
+            if op.kind == "conv" and op.layer.kernel_size == (3, 3) and m._stem_padded(op.layer) is not None:
+                x = op.inputs[0]
+                op.xcol = torch.zeros((self.batch, x.h, x.w, 64), dtype=torch.bfloat16, device=self.dev)
         for op in self.ops:   # Conv2D whose only consumer is a LayerNormalization: run as one fused call
             if op.kind == "ln" and op.conv_src is not None and op.conv_src.output is op.inputs[0] \
                     and op.conv_src.layer.kernel_size == (3, 3):
@@ -244,8 +248,13 @@ class Plan:
                 if getattr(op, "fused_into_ln", False):
                     continue     # executed by the following LayerNormalization op (one fused kernel)
                 filt, bias = m._filter(op.layer), m._param(op.layer, "bias")
-                S.append(lambda x=op.inputs[0], f=filt, b=bias, y=op.output, o=op:
-                         ops.conv2d_fprop(x.buf, f, b, y.buf, o.act))
+                src = self._stem_source(op, S)
+                if src is not None:
+                    filt = m._stem_padded(op.layer)[0]
+                    S.append(lambda xc=src, f=filt, b=bias, y=op.output, o=op: ops.conv2d_fprop(xc, f, b, y.buf, o.act))
+                else:
+                    S.append(lambda x=op.inputs[0], f=filt, b=bias, y=op.output, o=op:
+                             ops.conv2d_fprop(x.buf, f, b, y.buf, o.act))
             elif k == "ln":
                 g, b = m._param(op.layer, "gamma"), m._param(op.layer, "beta")
                 op.mean = torch.empty(npix(op.output), dtype=torch.float32, device=self.dev)
@@ -254,9 +263,13 @@ class Plan:
                 if cs is not None and cs.output is op.inputs[0] and cs.layer.kernel_size == (3, 3):
                     # Conv2D -> LayerNormalization -> ReLU: one call (fused tcgen05 epilogue for Cout 64/128)
                     self._cur_tag = "conv+ln" + (":tc" if self.is_tc(cs) else ":simt")
-                    S.append(lambda x=cs.inputs[0], f=m._filter(cs.layer), cb=m._param(cs.layer, "bias"),
+                    src = self._stem_source(cs, S)
+                    xin = src if src is not None else cs.inputs[0].buf
+                    filt = m._stem_padded(cs.layer)[0] if src is not None else m._filter(cs.layer)
+                    self._cur_tag = "conv+ln" + (":tc" if self.is_tc(cs) else ":simt")
+                    S.append(lambda x=xin, f=filt, cb=m._param(cs.layer, "bias"),
                              z=op.inputs[0], y=op.output, o=op, g=g, b=b:
-                             ops.conv2d_ln_fprop(x.buf, f, cb, g, b, o.layer.epsilon, o.relu, z.buf, y.buf, o.mean, o.rstd))
+                             ops.conv2d_ln_fprop(x, f, cb, g, b, o.layer.epsilon, o.relu, z.buf, y.buf, o.mean, o.rstd))
                 else:
                     S.append(lambda z=op.inputs[0], y=op.output, o=op, g=g, b=b:
                              ops.layernorm_fwd(z.buf, g, b, o.layer.epsilon, o.relu, y.buf, o.mean, o.rstd))
@@ -298,6 +311,18 @@ class Plan:
             else:
                 raise AssertionError(k)
 
+    def _stem_source(self, op, S):
+        """Narrow-input 3x3 conv under the bf16 policy: emit the im2col launch and return the [B,H,W,64]
+        tensor the tcgen05 1x1 path consumes (None when the op is not a stem)."""
+        if getattr(op, "xcol", None) is None:
+            return None
+        x = op.inputs[0]
+        tag = self._cur_tag
+        self._cur_tag = "im2col"
+        S.append(lambda x=x, xc=op.xcol: ops.im2col3x3(x.buf, xc))
+        self._cur_tag = tag
+        return op.xcol
+
     # ------------------------------------------------------------------ backward
     def _build_backward(self):
         m = self.model
@@ -324,7 +349,10 @@ class Plan:
         ws_bytes = 0
         for op in self.ops:
             if op.kind == "conv" and op.layer.kernel_size == (3, 3):
-                ws_bytes = max(ws_bytes, ops.conv2d_wgrad_workspace(op.inputs[0].buf, op.output.buf, 3, 3))
+                if getattr(op, "xcol", None) is not None:
+                    ws_bytes = max(ws_bytes, ops.conv2d_wgrad_workspace(op.xcol, op.output.buf, 1, 1))
+                else:
+                    ws_bytes = max(ws_bytes, ops.conv2d_wgrad_workspace(op.inputs[0].buf, op.output.buf, 3, 3))
         self.wgrad_ws = torch.empty(max(ws_bytes, 16) // 4, dtype=torch.float32, device=self.dev)
 
         def write_flag(v: Val) -> bool:
@@ -354,7 +382,11 @@ class Plan:
                 dw = m._grad(ly, "kernel").view(-1)
                 self._cur_tag = "wgrad" + sfx
                 writes(ly, "kernel")
-                B.append(lambda x=x, o=out, dw=dw, kh=kh: ops.conv2d_wgrad(x.buf, o.grad, kh, kh, dw, self.wgrad_ws))
+                if getattr(op, "xcol", None) is not None:     # stem: 1x1 wgrad over the im2col tensor
+                    B.append(lambda xc=op.xcol, o=out, dw=m._stem_padded(ly)[1]:
+                             ops.conv2d_wgrad(xc, o.grad, 1, 1, dw, self.wgrad_ws))
+                else:
+                    B.append(lambda x=x, o=out, dw=dw, kh=kh: ops.conv2d_wgrad(x.buf, o.grad, kh, kh, dw, self.wgrad_ws))
                 if x.needs_grad:
                     acc = write_flag(x)
                     self._cur_tag = "dgrad" + sfx
@@ -425,6 +457,8 @@ class Plan:
     def is_tc(op) -> bool:
         """True when the conv op's shapes select the tcgen05 kernels (mirrors conv_tc_supported)."""
         x, y, ly = op.inputs[0], op.output, op.layer
+        if getattr(op, "xcol", None) is not None:
+            return True    # stem: im2col + 1x1 on the tcgen05 kernels
         return (ly.kernel_size == (3, 3) and x.dtype == torch.bfloat16 and x.c % 64 == 0 and y.c % 64 == 0
                 and (y.c == 64 or y.c % 128 == 0))
 

@@ -112,15 +112,23 @@ class Model:
         self._compute_dtype = torch.float32 if _POLICY["name"] == "float32" else torch.bfloat16
         rng = np.random.default_rng(_SEED["value"])
         self._pinfo: Dict[str, tuple] = {}
+        self._stem_slots: Dict[str, int] = {}
         off_t = off_n = 0
         host_t, host_n = [], []
         for ly in self.layers:
             for w in ly.weight_specs:
                 val = w["value"] if w["value"] is not None else _init_array(w["init"], w["shape"], rng)
                 n = int(np.prod(w["shape"]))
+                slot = n
+                if self._is_stem_kernel(ly, w):
+                    # narrow-input 3x3 kernel [3,3,Cin,Cout] = a [9*Cin][Cout] matrix: its slot is zero-padded to
+                    # [64][Cout] so that parameter, gradient and bf16 shadow are directly the operands of the
+                    # tcgen05 1x1 path over the im2col tensor (the pad rows have zero gradients and stay zero)
+                    slot = 64 * w["shape"][3]
+                    self._stem_slots[w["name"]] = slot
                 if w["trainable"]:
                     self._pinfo[w["name"]] = (True, off_t, w["shape"])
-                    host_t.append((off_t, val)); off_t += (n + 63) // 64 * 64
+                    host_t.append((off_t, val)); off_t += (slot + 63) // 64 * 64
                 else:
                     self._pinfo[w["name"]] = (False, off_n, w["shape"])
                     host_n.append((off_n, val)); off_n += (n + 63) // 64 * 64
@@ -141,6 +149,27 @@ class Model:
         self._filters: Dict[str, ops.ConvFilter] = {}
         self._built = True
         self._refresh_shadow()
+
+    def _is_stem_kernel(self, ly, w) -> bool:
+        shape = w["shape"]
+        return (self._compute_dtype == torch.bfloat16 and w["trainable"] and w["name"].endswith("/kernel")
+                and len(shape) == 4 and shape[0] == 3 and shape[1] == 3 and 9 * shape[2] <= 64
+                and (shape[3] == 64 or shape[3] % 128 == 0) and type(ly).__name__ == "Conv2D"
+                and os.environ.get("B200_STEM_SIMT", "0") != "1")
+
+    def _stem_padded(self, ly):
+        """(bf16 shadow as a [1,1,64,Cout] filter, flat fp32 gradient slot) of a stem kernel, or None."""
+        key = f"{ly.name}/kernel"
+        if key not in self._stem_slots:
+            return None
+        _, off, shape = self._pinfo[key]
+        n = self._stem_slots[key]
+        if key not in self._filters:
+            f = ops.ConvFilter.__new__(ops.ConvFilter)
+            f.hwio = self.S[off:off + n].view(1, 1, 64, shape[3])
+            f.kh, f.kw, f.cin, f.cout, f.ohwi = 1, 1, 64, shape[3], None
+            self._filters[key] = f
+        return self._filters[key], self.G[off:off + n]
 
     def _refresh_shadow(self):
         if self.S is not self.P:
@@ -173,7 +202,7 @@ class Model:
         if key not in self._pinfo or not self._pinfo[key][0]:
             return None
         _, off, shape = self._pinfo[key]
-        return (off, int(np.prod(shape)))
+        return (off, self._stem_slots.get(key, int(np.prod(shape))))
 
     def _shadow(self, ly, name):
         return self._view(self.S, ly, name)

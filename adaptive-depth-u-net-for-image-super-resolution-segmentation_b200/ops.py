@@ -82,6 +82,12 @@ def conv2d_ln_fprop(x, filt: ConvFilter, bias, gamma, beta, eps, relu, z, y, mea
     return y
 
 
+def im2col3x3(x, xcol):
+    """Narrow-input 3x3 im2col into 64 bf16 channels (the stem's tensor-core path)."""
+    check(lib().b200_im2col3x3(tdesc(x), tdesc(xcol), _stream()), "im2col3x3")
+    return xcol
+
+
 def conv2d_dgrad(dy, filt: ConvFilter, dx, accumulate=False, algo=ALGO_AUTO):
     check(lib().b200_conv2d_dgrad(tdesc(dy), filt.struct(), tdesc(dx), int(accumulate), algo, _stream()), "conv2d_dgrad")
     return dx

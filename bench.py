@@ -285,7 +285,8 @@ def run_gpu(args):
     conv_ops = [op for op in plan.ops if op.kind == "conv" and _is_tc(op)]
     flops_fprop = sum(conv_flops(op, batch) for op in conv_ops)
     flops_dgrad = sum(conv_flops(op, batch) for op in conv_ops if op.inputs[0].needs_grad)
-    t_conv = prof.get("fwd:conv:tc", 0.0) + prof.get("bwd:dgrad:tc", 0.0)
+    # every launch of conv3x3_tc_kernel: plain fprop, fprop with the fused LayerNorm epilogue, dgrad
+    t_conv = prof.get("fwd:conv:tc", 0.0) + prof.get("fwd:conv+ln:tc", 0.0) + prof.get("bwd:dgrad:tc", 0.0)
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))

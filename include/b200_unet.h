@@ -103,6 +103,11 @@ int b200_conv2d_wgrad(const b200_tensor* x, const b200_tensor* dy, int kh, int k
                       void* workspace, size_t workspace_bytes, int algo, void* stream);
 /* hwio -> ohwi repack (same dtype). */
 int b200_filter_pack(const void* hwio, void* ohwi, int kh, int kw, int cin, int cout, int dtype, void* stream);
+/* im2col of a narrow 3x3 "same" convolution input (Cin*9 <= 64: the RGB stem, train_adaptive_unet.py:202
+ * with Cin=3): xcol[n,h,w, (kh*3+kw)*Cin + c] = x[n,h+kh-1,w+kw-1,c], zero padded to 64 bf16 channels.
+ * The stem then runs as a 1x1 convolution of xcol on the tcgen05 kernels: the conv2d fprop (plain or with LayerNorm) and
+ * wgrad entry points with kh = kw = 1 and the HWIO kernel zero-padded to [64][Cout]. */
+int b200_im2col3x3(const b200_tensor* x, const b200_tensor* xcol, void* stream);
 
 /* ---- transposed convolution (keras Conv2DTranspose(nf, 2, strides=2)) ----
  * unet_vinillia.py:67.  kernel layout [2][2][cout][cin] in `dtype`, fp32 bias. */

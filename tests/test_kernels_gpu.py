@@ -234,6 +234,81 @@ def test_conv_tc_wgrad(shape):
     assert e < 2e-3
 
 
+@pytest.mark.parametrize("shape", [(2, 32, 32, 64, 64), (1, 20, 13, 128, 64), (3, 16, 24, 64, 128), (2, 9, 7, 128, 256),
+                                   (9, 2, 2, 64, 64), (16, 1, 1, 128, 128), (5, 6, 6, 64, 128)])
+def test_conv1x1_tc(shape):
+    """1x1 convolutions on the tcgen05 kernels (centre tap of the 3x3 machinery): fprop (+ReLU), dgrad, wgrad."""
+    ops, K = _ops(), _K()
+    n, h, w, ci, co = shape
+    dt = torch.bfloat16
+    x = rand((n, h, w, ci), 41, dt)
+    wt = rand((1, 1, ci, co), 42, dt, 0.1)
+    b = rand((co,), 43, torch.float32, 0.5)
+    dy = rand((n, h, w, co), 44, dt)
+    filt = ops.ConvFilter(wt)
+    y = torch.full((n, h, w, co), 7.0, dtype=dt, device="cuda")
+    ops.conv2d_fprop(x, filt, b, y, ops.ACT_RELU, ops.ALGO_TCGEN05)
+    dx = torch.full((n, h, w, ci), 7.0, dtype=dt, device="cuda")
+    ops.conv2d_dgrad(dy, filt, dx, False, ops.ALGO_TCGEN05)
+    dw = torch.full((1, 1, ci, co), 7.0, dtype=torch.float32, device="cuda")
+    nbytes = ops.conv2d_wgrad_workspace(x, dy, 1, 1, ops.ALGO_TCGEN05)
+    ws = torch.empty(max(nbytes, 16) // 4, dtype=torch.float32, device="cuda")
+    ops.conv2d_wgrad(x, dy, 1, 1, dw, ws, ops.ALGO_TCGEN05)
+    torch.cuda.synchronize()
+    xr, wr = f32(x).requires_grad_(), f32(wt).requires_grad_()
+    yr = K.conv2d_same(xr, wr, f32(b))
+    (yr * f32(dy)).sum().backward()
+    assert relerr(y, torch.relu(yr)) < 1e-2
+    assert relerr(dx, xr.grad) < 1e-2
+    assert relerr(dw, wr.grad) < 2e-3
+
+
+@pytest.mark.parametrize("shape", [(2, 37, 21, 3), (3, 16, 16, 3), (1, 5, 9, 7), (4, 2, 2, 3), (2, 1, 1, 3)])
+@pytest.mark.parametrize("src_dtype", DTYPES)
+def test_stem_im2col_tensor_core_path(shape, src_dtype):
+    """The RGB stem as im2col (64 bf16 channels) + 1x1 tcgen05 convolution with the HWIO kernel zero-padded
+    to [64][Cout]: conv + LayerNorm + ReLU forward and the filter gradient against the 3x3 oracle."""
+    ops, K = _ops(), _K()
+    n, h, w, ci = shape
+    co = 64
+    dt = torch.bfloat16
+    x = rand((n, h, w, ci), 51, src_dtype)
+    xb = x.to(dt)                                   # the engine feeds the stem the bf16 cast of the input
+    wt = rand((3, 3, ci, co), 52, dt, 0.2)
+    b = rand((co,), 53, torch.float32, 0.5)
+    g, be = 1 + rand((co,), 54, torch.float32, 0.1), rand((co,), 55, torch.float32, 0.1)
+    dy = rand((n, h, w, co), 56, dt)
+    xcol = torch.full((n, h, w, 64), 7.0, dtype=dt, device="cuda")
+    ops.im2col3x3(xb, xcol)
+    # oracle im2col
+    xp = torch.nn.functional.pad(f32(xb), (0, 0, 1, 1, 1, 1))
+    ref = torch.zeros(n, h, w, 64)
+    for kh in range(3):
+        for kw in range(3):
+            ref[..., (kh * 3 + kw) * ci:(kh * 3 + kw + 1) * ci] = xp[:, kh:kh + h, kw:kw + w, :]
+    assert torch.equal(f32(xcol), ref)
+    wpad = torch.zeros((1, 1, 64, co), dtype=dt, device="cuda")
+    wpad[0, 0, :9 * ci] = wt.reshape(9 * ci, co)
+    filt = ops.ConvFilter(wpad)
+    z = torch.empty((n, h, w, co), dtype=dt, device="cuda"); y = torch.empty_like(z)
+    mean = torch.empty(n * h * w, device="cuda"); rstd = torch.empty_like(mean)
+    ops.conv2d_ln_fprop(xcol, filt, b, g, be, 1e-3, True, z, y, mean, rstd)
+    dw = torch.full((64, co), 7.0, dtype=torch.float32, device="cuda")
+    nbytes = ops.conv2d_wgrad_workspace(xcol, dy, 1, 1)
+    ws = torch.empty(max(nbytes, 16) // 4, dtype=torch.float32, device="cuda")
+    ops.conv2d_wgrad(xcol, dy, 1, 1, dw, ws)
+    torch.cuda.synchronize()
+    wr = f32(wt).requires_grad_()
+    zr = K.conv2d_same(f32(xb), wr, f32(b))
+    (zr * f32(dy)).sum().backward()
+    assert relerr(z, zr) < 1e-2
+    zq = f32(z)
+    yr = torch.relu(K.layer_norm(zq, f32(g), f32(be), 1e-3))
+    assert relerr(y, yr) < 1e-2
+    assert relerr(dw[:9 * ci], wr.grad.reshape(9 * ci, co)) < 2e-3
+    assert float(dw[9 * ci:].abs().max()) == 0.0
+
+
 # ----------------------------------------------------------------------------- layer norm
 @pytest.mark.parametrize("dtype", DTYPES)
 @pytest.mark.parametrize("shape", [(2, 7, 5, 64), (1, 3, 3, 8), (2, 4, 4, 256), (1, 2, 3, 1024), (1, 1, 5, 2048)])
