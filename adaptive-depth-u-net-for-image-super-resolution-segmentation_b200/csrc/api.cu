@@ -41,6 +41,9 @@ struct ConvLnArgs {
   float* mean; float* rstd;
 };
 bool conv_tc_ln_supported(int cout);
+bool conv_gemm_wanted(const b200_tensor*, int, int, int);
+size_t conv_gemm_workspace(const b200_tensor*, int, int, int);
+void set_workspace(void*, size_t);
 int conv_tc_launch(const b200_tensor*, const void*, int, int, int, int, const float*, const b200_tensor*, int, int, cudaStream_t,
                    const ConvLnArgs* ln = nullptr, int ks = 3);
 int umma_probe(const void*, int, const void*, int, int, int, int, float*, cudaStream_t);
@@ -153,7 +156,7 @@ int b200_conv2d_ln_fprop(const b200_tensor* x, const b200_filter* f, const float
   if (have_z) B200_REQUIRE(same_shape(z, y) && z->dtype == y->dtype, B200_ERR_BAD_ARG, "conv2d_ln_fprop: z/y mismatch");
   const bool fused = (f->kh == 3 || f->kh == 1) && f->kw == f->kh && f->dtype == B200_BF16 &&
                      conv_tc_supported(x, f->cin, f->cout, y, f->kh) && conv_tc_ln_supported(f->cout) &&
-                     algo != B200_ALGO_SIMT;
+                     algo != B200_ALGO_SIMT && !conv_gemm_wanted(x, f->cin, f->cout, f->kh);
   if (fused) {
     ConvLnArgs ln{gamma, beta, eps, relu, have_z ? z : nullptr, mean, rstd};
     return conv_tc_launch(x, f->hwio, f->cin, f->cout, 0, 1, bias, y, B200_ACT_NONE, 0, ST(stream), &ln, f->kh);
@@ -183,6 +186,20 @@ int b200_conv2d_dgrad(const b200_tensor* dy, const b200_filter* f, const b200_te
   if (algo == B200_ALGO_AUTO && f->dtype == dx->dtype && f->kh == f->kw && head_supported(dx, dy, f->kh))
     return head_dgrad(dy, f->hwio, dx, accumulate, ST(stream));
   return conv_simt_fprop(dy, f, nullptr, dx, B200_ACT_NONE, accumulate, true, ST(stream));
+}
+
+int b200_set_workspace(void* ws, size_t bytes) {
+  B200_REQUIRE((ws && bytes) || (!ws && !bytes), B200_ERR_BAD_ARG, "set_workspace: pointer and size disagree");
+  B200_REQUIRE((reinterpret_cast<uintptr_t>(ws) % 16) == 0, B200_ERR_BAD_ARG, "set_workspace: needs 16-byte alignment");
+  set_workspace(ws, bytes);
+  return B200_OK;
+}
+
+size_t b200_conv2d_workspace(const b200_tensor* x, const b200_filter* f, int dgrad) {
+  if (!x || !f || f->dtype != B200_BF16 || x->dtype != B200_BF16 || f->kh != f->kw || (f->kh != 3 && f->kh != 1)) return 0;
+  const int cin = dgrad ? f->cout : f->cin, cout = dgrad ? f->cin : f->cout;
+  if (x->c != cin || !conv_gemm_wanted(x, cin, cout, f->kh)) return 0;
+  return conv_gemm_workspace(x, cin, cout, f->kh);
 }
 
 size_t b200_conv2d_wgrad_workspace(const b200_tensor* x, const b200_tensor* dy, int kh, int kw, int algo) {

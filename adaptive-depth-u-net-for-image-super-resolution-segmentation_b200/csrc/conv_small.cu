@@ -312,32 +312,33 @@ inline bool pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
 // of the FMA-bound SIMT stem kernels.  8 threads per pixel, one 16-byte chunk each: a warp writes
 // 512 contiguous bytes.
 // ---------------------------------------------------------------------------
-template <typename T>
+template <typename T, int CIN>
 __global__ void __launch_bounds__(256)
-im2col3x3_kernel(TView x, __nv_bfloat16* __restrict__ xcol, long long col_sw, int H, int W, int cin, long long npix) {
+im2col3x3_kernel(TView x, __nv_bfloat16* __restrict__ xcol, long long col_sw, int H, int W, int cin_rt) {
+  // grid = (ceil(W*8/256), H, N): no per-thread divisions by H or W; CIN > 0 makes k/cin a constant division
+  const int cin = CIN > 0 ? CIN : cin_rt;
   const T* __restrict__ xp = reinterpret_cast<const T*>(x.data);
-  const int q = threadIdx.x & 7;
-  for (long long p = ((long long)blockIdx.x * 256 + threadIdx.x) >> 3; p < npix; p += ((long long)gridDim.x * 256) >> 3) {
-    const int w = (int)(p % W);
-    const long long t = p / W;
-    const int h = (int)(t % H);
-    const long long n = t / H;
-    uint32_t out[4];
+  const int item = blockIdx.x * 256 + threadIdx.x;
+  const int w = item >> 3, q = item & 7;
+  if (w >= W) return;
+  const int h = blockIdx.y, n = blockIdx.z;
+  const T* img = xp + (long long)n * x.sn;
+  uint32_t out[4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      float v[2];
+  for (int i = 0; i < 4; ++i) {
+    float v[2];
 #pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        const int k = q * 8 + i * 2 + e;
-        const int tap = k / cin, c = k - tap * cin;
-        const int ih = h + tap / 3 - 1, iw = w + tap % 3 - 1;
-        v[e] = (tap < 9 && ih >= 0 && ih < H && iw >= 0 && iw < W) ? ldf(xp + n * x.sn + (long long)ih * x.sh + (long long)iw * x.sw + c) : 0.f;
-      }
-      __nv_bfloat162 b = __floats2bfloat162_rn(v[0], v[1]);
-      out[i] = *reinterpret_cast<uint32_t*>(&b);
+    for (int e = 0; e < 2; ++e) {
+      const int k = q * 8 + i * 2 + e;
+      const int tap = k / cin, c = k - tap * cin;
+      const int ih = h + tap / 3 - 1, iw = w + tap % 3 - 1;
+      v[e] = (tap < 9 && ih >= 0 && ih < H && iw >= 0 && iw < W) ? ldf(img + (long long)ih * x.sh + (long long)iw * x.sw + c) : 0.f;
     }
-    *reinterpret_cast<uint4*>(xcol + p * col_sw + q * 8) = make_uint4(out[0], out[1], out[2], out[3]);
+    __nv_bfloat162 b = __floats2bfloat162_rn(v[0], v[1]);
+    out[i] = *reinterpret_cast<uint32_t*>(&b);
   }
+  const long long p = ((long long)n * H + h) * W + w;
+  *reinterpret_cast<uint4*>(xcol + p * col_sw + q * 8) = make_uint4(out[0], out[1], out[2], out[3]);
 }
 
 }  // namespace
@@ -377,13 +378,13 @@ int im2col3x3(const b200_tensor* x, const b200_tensor* xcol, cudaStream_t st) {
   TView cv = view_of(xcol);
   B200_REQUIRE(cv.lin && (reinterpret_cast<uintptr_t>(xcol->data) % 16 == 0) && (xcol->stride_w * 2) % 16 == 0,
                B200_ERR_UNSUPPORTED, "im2col3x3: destination pixels must be evenly spaced and 16-byte aligned");
-  const long long npix = (long long)x->n * x->h * x->w;
-  long long blocks = (npix * 8 + 255) / 256;
-  if (blocks > 16LL * sm_count()) blocks = 16LL * sm_count();
+  B200_REQUIRE(x->h <= 65535 && x->n <= 65535, B200_ERR_UNSUPPORTED, "im2col3x3: H and N must be <= 65535");
   TView xv = view_of(x);
+  dim3 grid((unsigned)((x->w * 8 + 255) / 256), (unsigned)x->h, (unsigned)x->n);
+  __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(xcol->data);
   B200_DISPATCH_DTYPE(x->dtype, T, {
-    im2col3x3_kernel<T><<<(int)blocks, 256, 0, st>>>(xv, reinterpret_cast<__nv_bfloat16*>(xcol->data), xcol->stride_w, x->h, x->w,
-                                                    x->c, npix);
+    if (x->c == 3) im2col3x3_kernel<T, 3><<<grid, 256, 0, st>>>(xv, dst, xcol->stride_w, x->h, x->w, 3);
+    else im2col3x3_kernel<T, 0><<<grid, 256, 0, st>>>(xv, dst, xcol->stride_w, x->h, x->w, x->c);
   });
   return check_launch("im2col3x3_kernel");
 }

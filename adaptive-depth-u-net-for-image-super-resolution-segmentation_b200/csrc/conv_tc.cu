@@ -678,6 +678,11 @@ struct ConvLnArgs {
 
 bool conv_tc_ln_supported(int cout) { return cout == 64 || cout == 128; }
 
+// small-spatial split-K path (conv_gemm.cu)
+bool conv_gemm_ready(const b200_tensor* x, int cin, int cout, int ks);
+int conv_gemm_launch(const b200_tensor* x, const void* wmat, int cin, int cout, int tap_rev, int b_mn, const float* bias,
+                     const b200_tensor* y, int act, int accumulate, int ks, cudaStream_t st);
+
 int conv_tc_launch(const b200_tensor* x_in, const void* wmat, int cin, int cout, int tap_rev, int b_mn, const float* bias,
                    const b200_tensor* y_in, int act, int accumulate, cudaStream_t st, const ConvLnArgs* ln = nullptr,
                    int ks = 3) {
@@ -686,6 +691,8 @@ int conv_tc_launch(const b200_tensor* x_in, const void* wmat, int cin, int cout,
                cout);
   B200_REQUIRE(x_in->n == y_in->n && x_in->h == y_in->h && x_in->w == y_in->w && x_in->c == cin && y_in->c == cout,
                B200_ERR_BAD_ARG, "conv3x3 tcgen05: tensor shapes do not match the filter");
+  if (!ln && conv_gemm_ready(x_in, cin, cout, ks))   // deep levels (images <= 8x8): weight-streaming split-K GEMM
+    return conv_gemm_launch(x_in, wmat, cin, cout, tap_rev, b_mn, bias, y_in, act, accumulate, ks, st);
   b200_tensor xf, yf;
   const b200_tensor *x = x_in, *y = y_in;
   int live_mask = 0;

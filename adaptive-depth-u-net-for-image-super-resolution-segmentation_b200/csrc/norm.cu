@@ -25,6 +25,26 @@ __device__ __forceinline__ float group_sum(float v, int tpp) {
   return v;
 }
 
+
+// Per-channel sums over the pixel groups of a block without shared-memory float atomics (which are
+// compare-and-swap loops and serialise badly when ppb groups hit the same channel): every thread parks
+// its 8 channel values, tpp*8 threads add the ppb rows and issue ONE global atomic per channel.
+// Thread layout: threadIdx.x = pixel_group * tpp + lane_g.  s_tmp holds NT*8 floats.
+__device__ __forceinline__ void block_channel_sum(const float (&v)[8], int tpp, int chunk_base, int C,
+                                                  float* s_tmp, float* __restrict__ dst) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s_tmp[threadIdx.x * 8 + i] = v[i];
+  __syncthreads();
+  if (dst && (int)threadIdx.x < tpp * 8) {
+    const int ppb = NT / tpp;
+    float a = 0.f;
+    for (int g = 0; g < ppb; ++g) a += s_tmp[g * tpp * 8 + threadIdx.x];
+    const int c = chunk_base * 8 + threadIdx.x;   // chunk_base: first 8-channel chunk of lane_g == 0
+    if (c < C) atomicAdd(dst + c, a);
+  }
+  __syncthreads();
+}
+
 // ---------------------------------------------------------------------------
 // LayerNorm forward: TPP threads per pixel (power of two <= 32), CPT chunks/thread
 // ---------------------------------------------------------------------------
@@ -106,12 +126,10 @@ ln_bwd_kernel(TView dy, TView z, const float* __restrict__ mean, const float* __
               const float* __restrict__ gamma, const float* __restrict__ beta, int relu, TView dz,
               float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dbias, int tpp,
               long long npix) {
-  extern __shared__ float s_acc[];  // [3][C]
+  __shared__ float s_acc[NT * 8];
   const int lane_g = threadIdx.x % tpp;
   const int ppb = NT / tpp;
   const int C = z.c, chunks = C / 8;
-  for (int i = threadIdx.x; i < 3 * C; i += NT) s_acc[i] = 0.f;
-  __syncthreads();
   const T* zp = reinterpret_cast<const T*>(z.data);
   const T* dyp = reinterpret_cast<const T*>(dy.data);
   T* dzp = reinterpret_cast<T*>(dz.data);
@@ -183,23 +201,12 @@ ln_bwd_kernel(TView dy, TView z, const float* __restrict__ mean, const float* __
       }
     }
   }
+  // chunk k of lane_g covers channels (lane_g + k*tpp)*8 ..: reduce one (chunk row, quantity) at a time
 #pragma unroll
   for (int k = 0; k < CPT; ++k) {
-    int j = lane_g + k * tpp;
-    if (j < chunks) {
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        atomicAdd(&s_acc[j * 8 + i], a_g[k][i]);
-        atomicAdd(&s_acc[C + j * 8 + i], a_b[k][i]);
-        atomicAdd(&s_acc[2 * C + j * 8 + i], a_z[k][i]);
-      }
-    }
-  }
-  __syncthreads();
-  for (int i = threadIdx.x; i < C; i += NT) {
-    if (dgamma) atomicAdd(dgamma + i, s_acc[i]);
-    if (dbeta) atomicAdd(dbeta + i, s_acc[C + i]);
-    if (dbias) atomicAdd(dbias + i, s_acc[2 * C + i]);
+    block_channel_sum(a_g[k], tpp, k * tpp, C, s_acc, dgamma);
+    block_channel_sum(a_b[k], tpp, k * tpp, C, s_acc, dbeta);
+    block_channel_sum(a_z[k], tpp, k * tpp, C, s_acc, dbias);
   }
 }
 
@@ -224,9 +231,7 @@ ln_bwd_lean_kernel(const __nv_bfloat16* __restrict__ dy, long long dy_sw, const 
                    __nv_bfloat16* __restrict__ dz, long long dz_sw, float* __restrict__ dgamma,
                    float* __restrict__ dbeta, float* __restrict__ dbias, int npix) {
   constexpr int C = 8 * TPP, PPB = NT / TPP;
-  __shared__ float s_acc[3 * C];
-  for (int i = threadIdx.x; i < 3 * C; i += NT) s_acc[i] = 0.f;
-  __syncthreads();
+  __shared__ float s_acc[NT * 8];
   const int lane_g = threadIdx.x % TPP;
   const float invC = 1.f / (float)C;
   float2 gam[4], bet[4], a_g[4], a_b[4], a_z[4];
@@ -299,21 +304,16 @@ ln_bwd_lean_kernel(const __nv_bfloat16* __restrict__ dy, long long dy_sw, const 
       if (ok[u]) *reinterpret_cast<uint4*>(oq + (long long)pp[u] * dz_sw) = out;
     }
   }
+  float v[8];
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    atomicAdd(&s_acc[lane_g * 8 + 2 * i], a_g[i].x);
-    atomicAdd(&s_acc[lane_g * 8 + 2 * i + 1], a_g[i].y);
-    atomicAdd(&s_acc[C + lane_g * 8 + 2 * i], a_b[i].x);
-    atomicAdd(&s_acc[C + lane_g * 8 + 2 * i + 1], a_b[i].y);
-    atomicAdd(&s_acc[2 * C + lane_g * 8 + 2 * i], a_z[i].x);
-    atomicAdd(&s_acc[2 * C + lane_g * 8 + 2 * i + 1], a_z[i].y);
-  }
-  __syncthreads();
-  for (int i = threadIdx.x; i < C; i += NT) {
-    if (dgamma) atomicAdd(dgamma + i, s_acc[i]);
-    if (dbeta) atomicAdd(dbeta + i, s_acc[C + i]);
-    if (dbias) atomicAdd(dbias + i, s_acc[2 * C + i]);
-  }
+  for (int i = 0; i < 4; ++i) { v[2 * i] = a_g[i].x; v[2 * i + 1] = a_g[i].y; }
+  block_channel_sum(v, TPP, 0, C, s_acc, dgamma);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { v[2 * i] = a_b[i].x; v[2 * i + 1] = a_b[i].y; }
+  block_channel_sum(v, TPP, 0, C, s_acc, dbeta);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { v[2 * i] = a_z[i].x; v[2 * i + 1] = a_z[i].y; }
+  block_channel_sum(v, TPP, 0, C, s_acc, dbias);
 }
 
 // ---------------------------------------------------------------------------
@@ -574,7 +574,8 @@ int layernorm_bwd(const b200_tensor* dy, const b200_tensor* z, const float* mean
   if (lean_variant && z->dtype == B200_BF16 && (C == 64 || C == 128 || C == 256) && zv.lin && dyv.lin && dzv.lin &&
       npix < (1LL << 30)) {
     const int ppb = NT / (C / 8);
-    long long nb = (npix + 2LL * ppb - 1) / (2LL * ppb);
+    // at least eight pixels per thread: each block ends with 3*C global atomics on the same addresses
+    long long nb = (npix + 8LL * ppb - 1) / (8LL * ppb);
     const long long capl = 3LL * sm_count();
     const int gridl = (int)(nb < capl ? nb : capl);
     const __nv_bfloat16* dyp = reinterpret_cast<const __nv_bfloat16*>(dy->data);

@@ -270,6 +270,12 @@ inline void plan(const b200_tensor* x_in, const b200_tensor* dy_in, WgradParams&
 
 }  // namespace
 
+// small-spatial path (conv_gemm.cu)
+bool wgrad_small_wanted(const b200_tensor* x, const b200_tensor* dy, int ks);
+size_t wgrad_small_workspace(const b200_tensor* x, const b200_tensor* dy, int ks);
+int wgrad_small_launch(const b200_tensor* x, const b200_tensor* dy, float* out, int ks, int* splits_out, int* live_mask,
+                       cudaStream_t st);
+
 bool wgrad_tc_supported(const b200_tensor* x, const b200_tensor* dy, int ks) {
   if (ks != 3 && ks != 1) return false;
   if (x->dtype != B200_BF16 || dy->dtype != B200_BF16) return false;
@@ -282,6 +288,7 @@ bool wgrad_tc_supported(const b200_tensor* x, const b200_tensor* dy, int ks) {
 }
 
 size_t wgrad_tc_workspace(const b200_tensor* x, const b200_tensor* dy, int ks) {
+  if (wgrad_small_wanted(x, dy, ks)) return wgrad_small_workspace(x, dy, ks);
   WgradParams p;
   WgradGeom g;
   plan(x, dy, p, g, ks);
@@ -290,6 +297,23 @@ size_t wgrad_tc_workspace(const b200_tensor* x, const b200_tensor* dy, int ks) {
 
 int wgrad_tc_launch(const b200_tensor* x, const b200_tensor* dy, float* dw, void* ws, size_t ws_bytes,
                     cudaStream_t st, int ks) {
+  if (wgrad_small_wanted(x, dy, ks)) {
+    // deep levels (images <= 8x8): one CTA per (tap, 128 ci, 128 co[, split]) over densely packed pixel boxes
+    const size_t need_s = wgrad_small_workspace(x, dy, ks);
+    B200_REQUIRE(need_s == 0 || (ws && ws_bytes >= need_s), B200_ERR_BAD_ARG,
+                 "conv2d_wgrad: workspace too small (%zu < %zu bytes)", ws_bytes, need_s);
+    const long long count_s = (long long)(ks == 1 ? 1 : 9) * x->c * dy->c;
+    const bool direct = need_s == 0;
+    if (direct) cudaMemsetAsync(dw, 0, sizeof(float) * count_s, st);   // taps that only see padding stay zero
+    int splits_s = 1, mask_s = 0;
+    int rcs = wgrad_small_launch(x, dy, direct ? dw : reinterpret_cast<float*>(ws), ks, &splits_s, &mask_s, st);
+    if (rcs || direct) return rcs;
+    long long blocks_s = (count_s / 4 + 63) / 64;
+    if (blocks_s > 8LL * sm_count()) blocks_s = 8LL * sm_count();
+    wgrad_reduce_kernel<<<(int)blocks_s, 256, 0, st>>>(reinterpret_cast<const float*>(ws), dw, count_s, splits_s, mask_s,
+                                                       (long long)x->c * dy->c);
+    return check_launch("wgrad_reduce_kernel");
+  }
   WgradParams p;
   WgradGeom g;
   plan(x, dy, p, g, ks);

@@ -231,6 +231,14 @@ class Plan:
                 list.append(inner, fn)
 
         S = self.steps = _Tagged()
+        ws_need = 0           # split-K scratch of the small-spatial (deep-level) convolutions, fprop and dgrad
+        for op in self.ops:
+            if op.kind == "conv" and op.inputs[0].buf.dtype == torch.bfloat16 and op.inputs[0].c % 64 == 0:
+                filt = m._filter(op.layer)
+                ws_need = max(ws_need, ops.conv2d_workspace(op.inputs[0].buf, filt, False))
+                if self.training:
+                    ws_need = max(ws_need, ops.conv2d_workspace(op.output.buf, filt, True))
+        ops.ensure_workspace(ws_need, self.dev)
         for op in self.ops:   # narrow-input 3x3 convs (the RGB stem): im2col tensor for the tcgen05 1x1 path
             if op.kind == "conv" and op.layer.kernel_size == (3, 3) and m._stem_padded(op.layer) is not None:
                 x = op.inputs[0]

@@ -70,6 +70,25 @@ class ConvFilter:
 
 
 # ---- convolution -------------------------------------------------------------------
+_WORKSPACES = []   # every scratch buffer ever registered stays alive: captured CUDA graphs hold their pointers
+
+
+def conv2d_workspace(x, filt: "ConvFilter", dgrad: bool = False) -> int:
+    """Bytes of split-K scratch the small-spatial path wants for this layer (0 = path not taken)."""
+    return int(lib().b200_conv2d_workspace(tdesc(x), filt.struct(), int(dgrad)))
+
+
+def ensure_workspace(nbytes: int, device) -> None:
+    """Register (process-wide) a scratch buffer of at least `nbytes` for the split-K convolution path."""
+    if nbytes <= 0:
+        return
+    if _WORKSPACES and _WORKSPACES[-1].numel() * 4 >= nbytes and _WORKSPACES[-1].device == torch.device(device):
+        return
+    buf = torch.empty((nbytes + 3) // 4, dtype=torch.float32, device=device)
+    _WORKSPACES.append(buf)
+    check(lib().b200_set_workspace(_ptr(buf), buf.numel() * 4), "set_workspace")
+
+
 def conv2d_fprop(x, filt: ConvFilter, bias, y, act=ACT_NONE, algo=ALGO_AUTO):
     check(lib().b200_conv2d_fprop(tdesc(x), filt.struct(), _ptr(bias), tdesc(y), act, algo, _stream()), "conv2d_fprop")
     return y

@@ -96,6 +96,14 @@ int b200_conv2d_ln_fprop(const b200_tensor* x, const b200_filter* f, const float
 /* dx (+)= conv_transpose(dy, f)  -- autodiff of the above w.r.t. its input. */
 int b200_conv2d_dgrad(const b200_tensor* dy, const b200_filter* f, const b200_tensor* dx,
                       int accumulate, int algo, void* stream);
+/* Scratch for the split-K path that serves small-spatial layers (images <= 8x8 pixels, the deep U-Net
+ * levels): b200_conv2d_workspace returns the bytes fprop (dgrad = 0, x = the input) or dgrad (dgrad = 1,
+ * x = dy) of this layer would use (0 = the layer does not take that path).  The caller owns the buffer and
+ * registers it once with b200_set_workspace (process-wide; launches that use it must be ordered on one
+ * stream).  Without a large enough registered buffer those layers run on the halo-window kernel instead. */
+int b200_set_workspace(void* ws, size_t bytes);
+size_t b200_conv2d_workspace(const b200_tensor* x, const b200_filter* f, int dgrad);
+
 /* dw_hwio[kh][kw][cin][cout] (fp32) = sum_pixels x (*) dy.  Overwrites dw.
  * `workspace` must hold b200_conv2d_wgrad_workspace() bytes (may be 0). */
 size_t b200_conv2d_wgrad_workspace(const b200_tensor* x, const b200_tensor* dy, int kh, int kw, int algo);

@@ -263,6 +263,46 @@ def test_conv1x1_tc(shape):
     assert relerr(dw, wr.grad) < 2e-3
 
 
+@pytest.mark.parametrize("shape", [(8, 2, 2, 128, 256, 3), (16, 1, 1, 256, 128, 3), (4, 8, 8, 128, 128, 3), (3, 5, 7, 128, 128, 3),
+                                   (2, 4, 4, 256, 128, 3), (64, 2, 2, 128, 128, 3), (5, 3, 3, 256, 64, 3), (7, 4, 2, 128, 256, 1),
+                                   (130, 1, 1, 128, 128, 3), (1, 8, 8, 256, 384, 3)])
+def test_conv_small_spatial_splitk(shape):
+    """Deep-level layers (images <= 8x8): densely packed pixel boxes + split-K over (channel block, tap) units with
+    an fp32 workspace and a finalize kernel -- fprop (+ReLU), dgrad (plain and accumulating), wgrad."""
+    ops, K = _ops(), _K()
+    n, h, w, ci, co, ks = shape
+    dt = torch.bfloat16
+    x = rand((n, h, w, ci), 61, dt)
+    wt = rand((ks, ks, ci, co), 62, dt, 0.05)
+    b = rand((co,), 63, torch.float32, 0.5)
+    dy = rand((n, h, w, co), 64, dt)
+    filt = ops.ConvFilter(wt)
+    need = max(ops.conv2d_workspace(x, filt, False), ops.conv2d_workspace(dy, filt, True))
+    assert need > 0 or max(h, w) > 4, "images of at most 4x4 pixels should take the split-K path"
+    ops.ensure_workspace(need, "cuda")          # (8x8 layers: split-K wgrad only; fprop/dgrad on the window kernel)
+    wide = torch.zeros((n, h, w, co + 64), dtype=dt, device="cuda")
+    y = wide[..., 64:]                       # channel slice: concat-in-place store
+    ops.conv2d_fprop(x, filt, b, y, ops.ACT_RELU, ops.ALGO_TCGEN05)
+    dx = torch.full((n, h, w, ci), 7.0, dtype=dt, device="cuda")
+    ops.conv2d_dgrad(dy, filt, dx, False, ops.ALGO_TCGEN05)
+    base = rand((n, h, w, ci), 65, dt)
+    dx2 = base.clone()
+    ops.conv2d_dgrad(dy, filt, dx2, True, ops.ALGO_TCGEN05)
+    dw = torch.full((ks, ks, ci, co), 7.0, dtype=torch.float32, device="cuda")
+    nbytes = ops.conv2d_wgrad_workspace(x, dy, ks, ks, ops.ALGO_TCGEN05)
+    ws = torch.empty(max(nbytes, 16) // 4, dtype=torch.float32, device="cuda")
+    ops.conv2d_wgrad(x, dy, ks, ks, dw, ws, ops.ALGO_TCGEN05)
+    torch.cuda.synchronize()
+    xr, wr = f32(x).requires_grad_(), f32(wt).requires_grad_()
+    yr = K.conv2d_same(xr, wr, f32(b))
+    (yr * f32(dy)).sum().backward()
+    assert relerr(y, torch.relu(yr)) < 1e-2
+    assert float(wide[..., :64].abs().max()) == 0.0
+    assert relerr(dx, xr.grad) < 1e-2
+    assert relerr(dx2, xr.grad + f32(base)) < 1e-2
+    assert relerr(dw, wr.grad) < 2e-3
+
+
 @pytest.mark.parametrize("shape", [(2, 37, 21, 3), (3, 16, 16, 3), (1, 5, 9, 7), (4, 2, 2, 3), (2, 1, 1, 3)])
 @pytest.mark.parametrize("src_dtype", DTYPES)
 def test_stem_im2col_tensor_core_path(shape, src_dtype):

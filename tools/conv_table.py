@@ -27,6 +27,29 @@ def timeit(fn, iters=10):
     return a.elapsed_time(b) / iters
 
 
+def timeit_graph(fn, reps=10, iters=5):
+    """GPU time per call with the launches captured in a CUDA graph (no host launch overhead, as in the
+    training step, which replays one graph)."""
+    fn(); torch.cuda.synchronize()
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        fn()
+    torch.cuda.current_stream().wait_stream(s)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for _ in range(reps):
+            fn()
+    g.replay(); torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(iters):
+        g.replay()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / (iters * reps)
+
+
 def mma_rate():
     L = ops.lib()
     sms = torch.cuda.get_device_properties(0).multi_processor_count
@@ -66,16 +89,20 @@ def main():
         dw = torch.empty(3, 3, ci, co, device="cuda")
         bias = torch.zeros(co, device="cuda")
         f = ops.ConvFilter(w)
+        ops.ensure_workspace(max(ops.conv2d_workspace(x, f, False), ops.conv2d_workspace(dy, f, True)), "cuda")
         ws = torch.empty(max(ops.conv2d_wgrad_workspace(x, dy, 3, 3), 16) // 4, device="cuda")
         fl = 2.0 * B * s * s * ci * co * 9
-        t_f = timeit(lambda: ops.conv2d_fprop(x, f, bias, y, 1))
-        t_d = timeit(lambda: ops.conv2d_dgrad(dy, f, dx))
-        t_w = timeit(lambda: ops.conv2d_wgrad(x, dy, 3, 3, dw, ws))
+        tm = timeit_graph if os.environ.get("TABLE_GRAPH", "1") == "1" else timeit
+        t_f = tm(lambda: ops.conv2d_fprop(x, f, bias, y, 1))
+        t_d = tm(lambda: ops.conv2d_dgrad(dy, f, dx))
+        t_w = tm(lambda: ops.conv2d_wgrad(x, dy, 3, 3, dw, ws))
         rows.append({"hw": s, "cin": ci, "cout": co, "gflop": fl / 1e9,
                      "fprop_us": t_f * 1e3, "fprop_tf": fl / t_f / 1e9,
                      "dgrad_us": t_d * 1e3, "dgrad_tf": fl / t_d / 1e9,
                      "wgrad_us": t_w * 1e3, "wgrad_tf": fl / t_w / 1e9})
-        print(rows[-1], flush=True)
+        r = rows[-1]
+        print(f"hw {s:4d} {ci:5d}->{co:5d}  fprop {r['fprop_us']:7.1f} us {r['fprop_tf']:7.1f} TF | dgrad {r['dgrad_us']:7.1f} us "
+              f"{r['dgrad_tf']:7.1f} TF | wgrad {r['wgrad_us']:7.1f} us {r['wgrad_tf']:7.1f} TF", flush=True)
     print(json.dumps({"config": name, "mma_rate": mma_rate(), "layers": rows}))
 
 

@@ -42,7 +42,7 @@ def bf(*shape):
 def main():
     B, P = 64, 128
     dev = "cuda"
-    for C, S in ((64, 128), (128, 32), (256, 8)):
+    for C, S in ((64, 128), (128, 32), (256, 8), (512, 2), (1024, 1)):
         npix = B * S * S
         dy, z, dz = bf(B, S, S, C), bf(B, S, S, C), bf(B, S, S, C)
         y = torch.empty_like(z)
@@ -71,6 +71,9 @@ def main():
         row(f"resize up {small}->{big} C={2 * C} bwd", t, (xs.numel() + yb.numel()) * 2)
     # stem 3->64 and 1x1 head 64->3 at full resolution
     x3 = bf(B, P, P, 3)
+    xcol = torch.empty(B, P, P, 64, device=dev, dtype=torch.bfloat16)
+    t = timeit(lambda: ops.im2col3x3(x3, xcol))
+    row("stem im2col 3 -> 64 (27 live)", t, (x3.numel() + xcol.numel()) * 2)
     y64, dy64 = bf(B, P, P, 64), bf(B, P, P, 64)
     f = ops.ConvFilter((torch.randn(3, 3, 3, 64, device=dev) * 0.1).bfloat16())
     bias = torch.zeros(64, device=dev)
