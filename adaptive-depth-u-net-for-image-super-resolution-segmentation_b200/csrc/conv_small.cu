@@ -301,6 +301,160 @@ head_wgrad_kernel(TView x, TView dy, float* __restrict__ dw, long long npix) {
   for (int i = threadIdx.x; i < Cin * COUT; i += 256) atomicAdd(dw + i, s_acc[i]);
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Lean bf16 head kernels (Cin = 64, COUT <= 4, evenly spaced pixels): 32-bit pixel indices, U pixels in
+// flight per thread (these kernels were latency bound with one 16-byte load per thread), packed bf16
+// unpacking.  8 threads per pixel, one 16-byte chunk each.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void unpack8(const uint4& r, float (&v)[8]) {
+  const uint32_t* q = reinterpret_cast<const uint32_t*>(&r);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { v[2 * i] = __uint_as_float(q[i] << 16); v[2 * i + 1] = __uint_as_float(q[i] & 0xffff0000u); }
+}
+
+template <int COUT, int U>
+__global__ void __launch_bounds__(256)
+head_fprop_lean_kernel(const __nv_bfloat16* __restrict__ x, long long x_sw, const __nv_bfloat16* __restrict__ wgt,
+                       const float* __restrict__ bias, __nv_bfloat16* __restrict__ y, long long y_sw, int act, int npix) {
+  const int j = threadIdx.x & 7;
+  float w[8][COUT];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int o = 0; o < COUT; ++o) w[i][o] = __bfloat162float(wgt[(j * 8 + i) * COUT + o]);
+  const int step = gridDim.x * 32;
+  for (int base = blockIdx.x * 32; base < npix; base += U * step) {      // warp-uniform trip count
+    int p[U];
+    uint4 raw[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      p[u] = base + u * step + (threadIdx.x >> 3);
+      raw[u] = *reinterpret_cast<const uint4*>(x + (long long)min(p[u], npix - 1) * x_sw + j * 8);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      float v[8];
+      unpack8(raw[u], v);
+      float acc[COUT];
+#pragma unroll
+      for (int o = 0; o < COUT; ++o) {
+        float a = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) a += v[i] * w[i][o];
+        a += __shfl_xor_sync(0xffffffffu, a, 4);
+        a += __shfl_xor_sync(0xffffffffu, a, 2);
+        a += __shfl_xor_sync(0xffffffffu, a, 1);
+        acc[o] = a;
+      }
+      if (j == 0 && p[u] < npix) {
+        __nv_bfloat16* dst = y + (long long)p[u] * y_sw;
+#pragma unroll
+        for (int o = 0; o < COUT; ++o) {
+          float r = acc[o] + (bias ? bias[o] : 0.f);
+          if (act == B200_ACT_RELU) r = fmaxf(r, 0.f);
+          else if (act == B200_ACT_SIGMOID) r = 1.f / (1.f + __expf(-r));
+          dst[o] = __float2bfloat16_rn(r);
+        }
+      }
+    }
+  }
+}
+
+// dW[c][o] = sum_p x[p][c] * d[p][o] (+ optional db[o] = sum_p d[p][o])
+template <int COUT, int U>
+__global__ void __launch_bounds__(256)
+head_wgrad_lean_kernel(const __nv_bfloat16* __restrict__ x, long long x_sw, const __nv_bfloat16* __restrict__ d,
+                       long long d_sw, float* __restrict__ dw, float* __restrict__ dbias, int npix) {
+  __shared__ float s_red[256 * 8];
+  const int j = threadIdx.x & 7;
+  float acc[8][COUT], bacc[COUT];
+#pragma unroll
+  for (int o = 0; o < COUT; ++o) {
+    bacc[o] = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i][o] = 0.f;
+  }
+  const int step = gridDim.x * 32;
+  for (int base = blockIdx.x * 32; base < npix; base += U * step) {
+    uint4 raw[U];
+    float dv[U][COUT];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int p = base + u * step + (threadIdx.x >> 3);
+      const bool ok = p < npix;
+      raw[u] = ok ? *reinterpret_cast<const uint4*>(x + (long long)p * x_sw + j * 8) : make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+      for (int o = 0; o < COUT; ++o) dv[u][o] = ok ? __bfloat162float(d[(long long)p * d_sw + o]) : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      float v[8];
+      unpack8(raw[u], v);
+#pragma unroll
+      for (int o = 0; o < COUT; ++o) {
+        bacc[o] += dv[u][o];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i][o] += v[i] * dv[u][o];
+      }
+    }
+  }
+  // block reduction over the 32 pixel groups, one output column at a time (no shared float atomics)
+#pragma unroll
+  for (int o = 0; o < COUT; ++o) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s_red[threadIdx.x * 8 + i] = acc[i][o];
+    __syncthreads();
+    if (threadIdx.x < 64) {
+      float a = 0.f;
+      for (int g = 0; g < 32; ++g) a += s_red[g * 64 + threadIdx.x];
+      atomicAdd(dw + threadIdx.x * COUT + o, a);
+    }
+    __syncthreads();
+  }
+  if (dbias) {
+#pragma unroll
+    for (int o = 0; o < COUT; ++o) {
+      float a = j == 0 ? bacc[o] : 0.f;
+      a = warp_sum(a);
+      if ((threadIdx.x & 31) == 0) atomicAdd(dbias + o, a);
+    }
+  }
+}
+
+// column sums of a dense [npix][3] bf16 tensor (the bias gradient of the RGB head): 48 contiguous bytes
+// (8 pixels) per thread so that the channel of every element is a compile-time constant
+__global__ void __launch_bounds__(256)
+bias_sum_c3_kernel(const __nv_bfloat16* __restrict__ d, long long n_elem, float* __restrict__ dbias) {
+  float a[3] = {0.f, 0.f, 0.f};
+  const long long groups = n_elem / 24;
+  for (long long g = (long long)blockIdx.x * 256 + threadIdx.x; g < groups; g += (long long)gridDim.x * 256) {
+    const uint4* src = reinterpret_cast<const uint4*>(d + g * 24);
+    const uint4 r0 = src[0], r1 = src[1], r2 = src[2];
+    float v[24];
+    float t[8];
+    unpack8(r0, t);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = t[i];
+    unpack8(r1, t);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[8 + i] = t[i];
+    unpack8(r2, t);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[16 + i] = t[i];
+#pragma unroll
+    for (int i = 0; i < 24; ++i) a[i % 3] += v[i];
+  }
+  if (blockIdx.x == 0) {   // tail elements (fewer than 24)
+    for (long long e = groups * 24 + threadIdx.x; e < n_elem; e += 256) a[e % 3] += __bfloat162float(d[e]);
+  }
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const float s = warp_sum(a[c]);
+    if ((threadIdx.x & 31) == 0) atomicAdd(dbias + c, s);
+  }
+}
+
 inline bool pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
 
 
@@ -312,17 +466,29 @@ inline bool pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
 // of the FMA-bound SIMT stem kernels.  8 threads per pixel, one 16-byte chunk each: a warp writes
 // 512 contiguous bytes.
 // ---------------------------------------------------------------------------
+// block = 32 pixels of one image row x 8 chunks.  The three input rows the segment needs are staged in
+// shared memory as fp32 (each row of the patch is 3*Cin CONTIGUOUS input values, so channel k of a pixel is
+// s_rows[k / (3*Cin)][pixel*Cin + k % (3*Cin)]); the thread then only does shared loads and one 16-byte store.
 template <typename T, int CIN>
 __global__ void __launch_bounds__(256)
 im2col3x3_kernel(TView x, __nv_bfloat16* __restrict__ xcol, long long col_sw, int H, int W, int cin_rt) {
-  // grid = (ceil(W*8/256), H, N): no per-thread divisions by H or W; CIN > 0 makes k/cin a constant division
+  constexpr int SEG = 32, MAXC = 7;
+  __shared__ float s_rows[3][(SEG + 2) * MAXC];
   const int cin = CIN > 0 ? CIN : cin_rt;
-  const T* __restrict__ xp = reinterpret_cast<const T*>(x.data);
-  const int item = blockIdx.x * 256 + threadIdx.x;
-  const int w = item >> 3, q = item & 7;
+  const int rowlen = (SEG + 2) * cin;
+  const int w0 = blockIdx.x * SEG, h = blockIdx.y, n = blockIdx.z;
+  const T* img = reinterpret_cast<const T*>(x.data) + (long long)n * x.sn;
+  for (int i = threadIdx.x; i < 3 * rowlen; i += 256) {
+    const int r = i / rowlen, e = i - r * rowlen;
+    const int px = e / cin, c = e - px * cin;
+    const int ih = h + r - 1, iw = w0 + px - 1;
+    s_rows[r][e] = (ih >= 0 && ih < H && iw >= 0 && iw < W) ? ldf(img + (long long)ih * x.sh + (long long)iw * x.sw + c) : 0.f;
+  }
+  __syncthreads();
+  const int pl = threadIdx.x >> 3, q = threadIdx.x & 7;
+  const int w = w0 + pl;
   if (w >= W) return;
-  const int h = blockIdx.y, n = blockIdx.z;
-  const T* img = xp + (long long)n * x.sn;
+  const int k3 = 3 * cin, kmax = 9 * cin;
   uint32_t out[4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
@@ -330,9 +496,8 @@ im2col3x3_kernel(TView x, __nv_bfloat16* __restrict__ xcol, long long col_sw, in
 #pragma unroll
     for (int e = 0; e < 2; ++e) {
       const int k = q * 8 + i * 2 + e;
-      const int tap = k / cin, c = k - tap * cin;
-      const int ih = h + tap / 3 - 1, iw = w + tap % 3 - 1;
-      v[e] = (tap < 9 && ih >= 0 && ih < H && iw >= 0 && iw < W) ? ldf(img + (long long)ih * x.sh + (long long)iw * x.sw + c) : 0.f;
+      const int r = k / k3, m = k - r * k3;
+      v[e] = k < kmax ? s_rows[r][pl * cin + m] : 0.f;
     }
     __nv_bfloat162 b = __floats2bfloat162_rn(v[0], v[1]);
     out[i] = *reinterpret_cast<uint32_t*>(&b);
@@ -380,7 +545,7 @@ int im2col3x3(const b200_tensor* x, const b200_tensor* xcol, cudaStream_t st) {
                B200_ERR_UNSUPPORTED, "im2col3x3: destination pixels must be evenly spaced and 16-byte aligned");
   B200_REQUIRE(x->h <= 65535 && x->n <= 65535, B200_ERR_UNSUPPORTED, "im2col3x3: H and N must be <= 65535");
   TView xv = view_of(x);
-  dim3 grid((unsigned)((x->w * 8 + 255) / 256), (unsigned)x->h, (unsigned)x->n);
+  dim3 grid((unsigned)((x->w + 31) / 32), (unsigned)x->h, (unsigned)x->n);
   __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(xcol->data);
   B200_DISPATCH_DTYPE(x->dtype, T, {
     if (x->c == 3) im2col3x3_kernel<T, 3><<<grid, 256, 0, st>>>(xv, dst, xcol->stride_w, x->h, x->w, 3);
@@ -406,7 +571,31 @@ static int head_grid(long long npix, int per_block) {
   return (int)(b < 1 ? 1 : (b > cap ? cap : b));
 }
 
+static bool head_lean_ok(const b200_tensor* x, const b200_tensor* y) {
+  TView xv = view_of(x), yv = view_of(y);
+  return x->dtype == B200_BF16 && x->c == 64 && y->c == 3 && xv.lin && yv.lin && (long long)x->n * x->h * x->w < (1LL << 30);
+}
+
+// column sums of a dense bf16 [.., 3] tensor into dbias (+=)
+int bias_sum_c3(const b200_tensor* dy, float* dbias, cudaStream_t st) {
+  const long long n_elem = (long long)dy->n * dy->h * dy->w * 3;
+  long long blocks = (n_elem / 24 + 255) / 256;
+  if (blocks > 4LL * sm_count()) blocks = 4LL * sm_count();
+  if (blocks < 1) blocks = 1;
+  bias_sum_c3_kernel<<<(int)blocks, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(dy->data), n_elem, dbias);
+  return check_launch("bias_sum_c3_kernel");
+}
+
 int head_fprop(const b200_tensor* x, const void* wgt, const float* bias, const b200_tensor* y, int act, cudaStream_t st) {
+  if (head_lean_ok(x, y)) {
+    const int npix = x->n * x->h * x->w;
+    long long blocks = (npix + 4 * 32 - 1) / (4 * 32);
+    if (blocks > 8LL * sm_count()) blocks = 8LL * sm_count();
+    head_fprop_lean_kernel<3, 4><<<(int)blocks, 256, 0, st>>>(
+        reinterpret_cast<const __nv_bfloat16*>(x->data), x->stride_w, reinterpret_cast<const __nv_bfloat16*>(wgt), bias,
+        reinterpret_cast<__nv_bfloat16*>(y->data), y->stride_w, act, npix);
+    return check_launch("head_fprop_lean_kernel");
+  }
   const long long npix = (long long)x->n * x->h * x->w;
   TView xv = view_of(x), yv = view_of(y);
   const size_t smem = sizeof(float) * x->c * y->c;
@@ -431,6 +620,16 @@ int head_dgrad(const b200_tensor* dy, const void* wgt, const b200_tensor* dx, in
 }
 
 int head_wgrad(const b200_tensor* x, const b200_tensor* dy, float* dw, cudaStream_t st) {
+  if (head_lean_ok(x, dy)) {
+    const int npix_i = x->n * x->h * x->w;
+    cudaMemsetAsync(dw, 0, sizeof(float) * 64 * 3, st);
+    long long blocks = (npix_i + 4 * 32 - 1) / (4 * 32);
+    if (blocks > 4LL * sm_count()) blocks = 4LL * sm_count();
+    head_wgrad_lean_kernel<3, 4><<<(int)blocks, 256, 0, st>>>(
+        reinterpret_cast<const __nv_bfloat16*>(x->data), x->stride_w, reinterpret_cast<const __nv_bfloat16*>(dy->data),
+        dy->stride_w, dw, nullptr, npix_i);
+    return check_launch("head_wgrad_lean_kernel");
+  }
   const long long npix = (long long)x->n * x->h * x->w;
   TView xv = view_of(x), dv = view_of(dy);
   const size_t smem = sizeof(float) * x->c * dy->c;

@@ -595,10 +595,20 @@ int layernorm_bwd(const b200_tensor* dy, const b200_tensor* z, const float* mean
   return check_launch("ln_bwd_kernel");
 }
 
+int bias_sum_c3(const b200_tensor* dy, float* dbias, cudaStream_t st);
+
 int bias_act_bwd(const b200_tensor* dy, const b200_tensor* y, int act, const b200_tensor* dz, float* dbias,
                  cudaStream_t st) {
   B200_REQUIRE(same_shape(y, dy) && same_shape(y, dz) && y->dtype == dy->dtype && y->dtype == dz->dtype,
                B200_ERR_BAD_ARG, "bias_act_bwd: shape/dtype mismatch");
+  {  // linear layer, in place: nothing to write, the call only wants the bias gradient (the RGB head)
+    TView dv = view_of(dy);
+    if (act == B200_ACT_NONE && dz->data == dy->data && dy->c == 3 && dy->dtype == B200_BF16 && dv.lin && dv.sw == 3 &&
+        reinterpret_cast<uintptr_t>(dy->data) % 16 == 0) {
+      if (!dbias) return B200_OK;
+      return bias_sum_c3(dy, dbias, st);
+    }
+  }
   const int C = y->c;
   const long long npix = (long long)y->n * y->h * y->w;
   TView dyv = view_of(dy), yv = view_of(y), dzv = view_of(dz);

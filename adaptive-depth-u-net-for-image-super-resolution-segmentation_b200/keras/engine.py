@@ -243,6 +243,13 @@ class Plan:
             if op.kind == "conv" and op.layer.kernel_size == (3, 3) and m._stem_padded(op.layer) is not None:
                 x = op.inputs[0]
                 op.xcol = torch.zeros((self.batch, x.h, x.w, 64), dtype=torch.bfloat16, device=self.dev)
+        # a model input whose bf16 cast is read by stem convolutions only: im2col rounds to bf16 itself, skip the cast
+        for cast in [o for o in self.ops if o.kind == "cast_input"]:
+            readers = [o for o in self.ops if cast.output in o.inputs]
+            if readers and all(getattr(o, "xcol", None) is not None for o in readers):
+                for o in readers:
+                    o.stem_raw = cast.inputs[0]
+                cast.skip = True
         for op in self.ops:   # Conv2D whose only consumer is a LayerNormalization: run as one fused call
             if op.kind == "ln" and op.conv_src is not None and op.conv_src.output is op.inputs[0] \
                     and op.conv_src.layer.kernel_size == (3, 3):
@@ -251,6 +258,8 @@ class Plan:
             k = op.kind
             self._cur_tag = k + (":tc" if k == "conv" and self.is_tc(op) else (":simt" if k == "conv" else ""))
             if k == "cast_input":
+                if getattr(op, "skip", False):
+                    continue
                 S.append(lambda a=op.inputs[0], b=op.output: ops.copy_tensor(a.buf, b.buf))
             elif k == "conv":
                 if getattr(op, "fused_into_ln", False):
@@ -324,7 +333,7 @@ class Plan:
         tensor the tcgen05 1x1 path consumes (None when the op is not a stem)."""
         if getattr(op, "xcol", None) is None:
             return None
-        x = op.inputs[0]
+        x = getattr(op, "stem_raw", None) or op.inputs[0]     # the raw fp32 model input when op reads its bf16 cast
         tag = self._cur_tag
         self._cur_tag = "im2col"
         S.append(lambda x=x, xc=op.xcol: ops.im2col3x3(x.buf, xc))

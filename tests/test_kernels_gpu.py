@@ -395,6 +395,20 @@ def test_bias_act_bwd(dtype, c, act):
     assert relerr(db, exp.sum(dim=(0, 1, 2))) < 1e-2
 
 
+@pytest.mark.parametrize("shape", [(2, 37, 21, 3), (64, 16, 16, 3), (1, 1, 5, 3), (3, 8, 8, 3)])
+def test_bias_grad_of_linear_rgb_head_in_place(shape):
+    """bias_act_bwd(ACT_NONE) in place on a dense bf16 [..,3] tensor only has to produce the bias gradient:
+    the column-sum kernel must leave the tensor untouched and accumulate (+=) into dbias."""
+    ops = _ops()
+    dy = rand(shape, 91, torch.bfloat16)
+    keep = dy.clone()
+    db = torch.full((3,), 0.5, device="cuda")
+    ops.bias_act_bwd(dy, dy, 0, dy, db)
+    torch.cuda.synchronize()
+    assert torch.equal(dy, keep)
+    assert relerr(db, f32(keep).sum(dim=(0, 1, 2)) + 0.5) < 1e-4
+
+
 # ----------------------------------------------------------------------------- batch norm
 @pytest.mark.parametrize("dtype", DTYPES)
 @pytest.mark.parametrize("c", [64, 24, 512])
