@@ -432,10 +432,13 @@ class Plan:
                 x = op.inputs[0]
                 if x.needs_grad:
                     acc = write_flag(x)
-                    if op.identity:
-                        if acc:
-                            raise NotImplementedError("identity resize feeding an accumulated gradient")
+                    if op.identity and not acc:
                         B.append(lambda x=x, o=out: ops.copy_tensor(o.grad, x.grad))
+                    elif op.identity:
+                        # same-size resize whose input also feeds a skip connection (e.g. the 1x1 -> 1x1 level of a
+                        # depth-5 net at scale 0.25): dx += dy through the identity span tables
+                        op.ph, op.pw = self._plans((x.h, x.w), (out.h, out.w), op.antialias)
+                        B.append(lambda x=x, o=out, op=op: ops.resample2d_bwd(o.grad, x.grad, op.ph, op.pw, True))
                     else:
                         B.append(lambda x=x, o=out, op=op, acc=acc: ops.resample2d_bwd(o.grad, x.grad, op.ph, op.pw, acc))
             elif k == "maxpool":

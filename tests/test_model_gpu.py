@@ -91,6 +91,48 @@ def test_sr_unet_step(policy):
     print(f"[{policy}] worst grad relerr {worst:.3e}")
 
 
+def test_sr_unet_deep_levels_collapse_to_1x1():
+    """scale 0.25, depth 4 at 20x20: 20 -> 5 -> 2 -> 1 -> 1: depth
+    is forced past the point where the image has shrunk to 1x1 (BASELINE configs 2/3 do this), so the net contains a
+    same-size ResizeByScale whose input also feeds a skip connection, stacked 2x2 tiles and flattened 1x1 batches."""
+    from b200unet import builders as B
+    from b200unet.keras.optimizers import Adam
+    from oracle import keras_ops as K, models as M
+    _setup("float32")
+    scale, depth, P, batch = 0.25, 4, 20, 4
+    from oracle import resize_np
+    assert list(resize_np.size_chain(P, scale, depth)) == [20, 5, 2, 1, 1]
+    model, _ = B.build_super_resolution_unet(scale, depth_override=depth, input_size=P)
+    ws_np = M.init_weights(M.sr_unet_spec(depth), seed=4321, randomize_zero_kernels=True, jitter=0.05)
+    model.set_weights(ws_np)
+    loss, metrics = B.build_losses_and_metrics("l1")
+    model.compile(optimizer=Adam(learning_rate=1e-3), loss=loss, metrics=metrics)
+    rng = np.random.default_rng(99)
+    hr = rng.random((batch, P, P, 3), dtype=np.float32)
+    lr = np.clip(hr + 0.05 * rng.standard_normal(hr.shape).astype(np.float32), 0, 1)
+    fwd = lambda ws, x: M.sr_unet_forward(ws, x, scale, depth)
+    y_ref, l_ref, g_ref = _oracle_step(ws_np, torch.from_numpy(lr), torch.from_numpy(hr), fwd, K.l1_loss, None)
+    logs = model.train_on_batch(lr, hr)
+    torch.cuda.synchronize()
+    assert abs(logs["loss"] - l_ref) < 1e-6 * max(1.0, abs(l_ref))
+    i, bad = 0, []
+    for ly in model.layers:
+        for w in ly.weight_specs:
+            e = relerr(model._grad(ly, w["name"].split("/", 1)[1]), g_ref[i])
+            if not (e < 2e-3 or g_ref[i].abs().max().item() < 1e-7):
+                bad.append((w["name"], e))
+            i += 1
+    assert not bad, bad
+    # the same net under the bf16 policy (tcgen05 + split-K kernels at the 2x2 / 1x1 levels): loss within 1e-3
+    _setup("mixed_bfloat16")
+    model, _ = B.build_super_resolution_unet(scale, depth_override=depth, input_size=P)
+    model.set_weights(ws_np)
+    loss, metrics = B.build_losses_and_metrics("l1")
+    model.compile(optimizer=Adam(learning_rate=1e-3), loss=loss, metrics=metrics)
+    logs = model.train_on_batch(lr, hr)
+    assert abs(logs["loss"] - l_ref) < 2e-3 * max(1.0, abs(l_ref))
+
+
 def test_sr_unet_training_reduces_loss():
     """A few steps on a fixed batch: the loss must go down and stay finite (bf16 policy, graph replay)."""
     from b200unet import builders as B
