@@ -98,48 +98,65 @@ def run_reference(args):
         "e2e": {"value": value, "unit": "patches/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=OUT, flush=True)
 
 
 # --------------------------------------------------------------------------- GPU arm
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled while the timed region runs."""
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock and clock-event (throttle) reasons sampled every ~5 ms through NVML while the timed region runs
+    (the region is only tens of milliseconds long at N=1; `nvidia-smi -lms 100` would see one sample or none)."""
+    NAMES = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
 
     def __init__(self, index):
-        self.rows, self.proc, self.index = [], None, index
+        self.index, self.rows, self.mask, self.max_mhz = index, [], 0, None
+        self._stop = threading.Event()
+        self.th = None
+
+    def _handle(self):
+        import pynvml
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        idx = self.index
+        if vis:
+            ent = [v.strip() for v in vis.split(",") if v.strip()]
+            if idx < len(ent) and ent[idx].isdigit():
+                idx = int(ent[idx])
+            elif idx < len(ent):
+                return pynvml, pynvml.nvmlDeviceGetHandleByUUID(ent[idx].encode() if hasattr(ent[idx], "encode") else ent[idx])
+        return pynvml, pynvml.nvmlDeviceGetHandleByIndex(idx)
 
     def __enter__(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
-            self.th = threading.Thread(target=self._read, daemon=True)
+            nv, h = self._handle()
+            self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+
+            def loop():
+                while not self._stop.is_set():
+                    try:
+                        self.rows.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                        self.mask |= int(reasons(h))
+                    except Exception:
+                        pass
+                    time.sleep(0.005)
+
+            self.th = threading.Thread(target=loop, daemon=True)
             self.th.start()
         except Exception:
-            self.proc = None
+            self.th = None
         return self
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
-
     def __exit__(self, *a):
-        if self.proc:
-            self.proc.terminate()
-            try:
-                self.proc.wait(timeout=2)
-            except Exception:
-                self.proc.kill()
+        self._stop.set()
+        if self.th is not None:
+            self.th.join(timeout=1.0)
 
     def summary(self):
-        sm = sorted(float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit())
+        sm = sorted(self.rows)
         if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(len(r) >= 7 and r[3 + i].lower().startswith("active") for r in self.rows)]
-        mx = max(float(r[1]) for r in self.rows if len(r) >= 7)
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": mx, "reasons": reasons, "samples": len(sm)}
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "samples": 0}
+        reasons = [n for n, bit in self.NAMES.items() if self.mask & bit]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.max_mhz, "reasons": reasons, "samples": len(sm)}
 
 
 def conv_flops(op, batch):
@@ -297,11 +314,24 @@ def run_gpu(args):
     t_wg = prof.get("bwd:wgrad:tc", 0.0)
     ach_wg = flops_fprop / (t_wg / 1000.0) / 1e12 if t_wg > 0 else 0.0
     n_launch = sum(1 for op in conv_ops) + sum(1 for op in conv_ops if op.inputs[0].needs_grad)
+    # algorithmic HBM bytes of those launches: input read once + output written once (bf16), x2 outputs with fused LN
+    def _act_bytes(v):
+        return 2.0 * batch * v.h * v.w * v.c
+    bytes_conv = sum(_act_bytes(op.inputs[0]) + _act_bytes(op.output) * (2 if getattr(op, "fused_into_ln", False) else 1)
+                     for op in conv_ops)
+    bytes_conv += sum(_act_bytes(op.inputs[0]) + _act_bytes(op.output) for op in conv_ops if op.inputs[0].needs_grad)
+    traffic = None            # DRAM bytes per launch of the same kernel, from the committed `ncu --set full` capture
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_v7_conv_traffic.json")))["dram_bytes_per_launch_mean"]
+    except Exception:
+        pass
     roofline = {
         "kernel": "conv3x3_tc_kernel (tcgen05 implicit GEMM; all fprop+dgrad launches of one step)",
         "bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf,
         "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if peaks else "fallback 1400 (of fallback)",
-        "traffic": None, "launches_per_step": n_launch, "avg_launch_ms": t_conv / max(n_launch, 1),
+        "traffic": traffic, "traffic_source": "profiles/r01_v7_conv_traffic.json (ncu dram__bytes_read+write, mean over the captured launches)",
+        "algorithmic_bytes_per_launch": bytes_conv / max(n_launch, 1),
+        "launches_per_step": n_launch, "avg_launch_ms": t_conv / max(n_launch, 1),
         "wgrad_kernel": {"achieved": ach_wg, "frac": ach_wg / peak_tf, "ms_per_step": t_wg},
     }
     fl_sample = OM.sr_flops_per_sample(scale, depth, patch)
@@ -333,17 +363,28 @@ def run_gpu(args):
         "breakdown_ms": {k: round(v, 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1])},
         "eager_step_ms": step_ms_eager,
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=OUT, flush=True)
     if world > 1:
         model.release_graphs()
         dist.barrier()
         dist.destroy_process_group()
 
 
+def _claim_stdout():
+    """Route everything libraries write to fd 1 (NCCL prints its version banner there) to stderr and return a
+    file object on the real stdout for the ONE JSON line."""
+    sys.stdout.flush()
+    real = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    return real
+
+
 def main():
+    global OUT
+    OUT = _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--config", default="c2", choices=sorted(CONFIGS))
