@@ -58,6 +58,7 @@ SIGNATURES = {
     "b200_conv2d_workspace": (_sz, [_TP, C.POINTER(Filter), _i]),
     "b200_conv2d_wgrad_workspace": (_sz, [_TP, _TP, _i, _i, _i]),
     "b200_conv2d_wgrad": (_i, [_TP, _TP, _i, _i, _vp, _vp, _sz, _i, _vp]),
+    "b200_conv2d_wgrad_atomic": (_i, [_TP, _TP, _i, _i, _vp, _vp]),
     "b200_filter_pack": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "b200_im2col3x3": (_i, [_TP, _TP, _vp]),
     "b200_convT2x2_fprop": (_i, [_TP, _vp, _vp, _i, _TP, _vp]),

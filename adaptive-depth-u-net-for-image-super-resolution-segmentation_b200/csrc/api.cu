@@ -58,7 +58,7 @@ int head_dgrad(const b200_tensor*, const void*, const b200_tensor*, int, cudaStr
 int head_wgrad(const b200_tensor*, const b200_tensor*, float*, cudaStream_t);
 bool wgrad_tc_supported(const b200_tensor*, const b200_tensor*, int);
 size_t wgrad_tc_workspace(const b200_tensor*, const b200_tensor*, int);
-int wgrad_tc_launch(const b200_tensor*, const b200_tensor*, float*, void*, size_t, cudaStream_t, int);
+int wgrad_tc_launch(const b200_tensor*, const b200_tensor*, float*, void*, size_t, cudaStream_t, int, int atomic = 0);
 int layernorm_fwd(const b200_tensor*, const float*, const float*, float, int, const b200_tensor*, float*, float*, cudaStream_t);
 int layernorm_bwd(const b200_tensor*, const b200_tensor*, const float*, const float*, const float*, const float*, int,
                   const b200_tensor*, float*, float*, float*, cudaStream_t);
@@ -229,6 +229,16 @@ int b200_conv2d_wgrad(const b200_tensor* x, const b200_tensor* dy, int kh, int k
 int b200_im2col3x3(const b200_tensor* x, const b200_tensor* xcol, void* stream) {
   REQ_T(x, "x"); REQ_T(xcol, "xcol");
   return im2col3x3(x, xcol, ST(stream));
+}
+
+int b200_conv2d_wgrad_atomic(const b200_tensor* x, const b200_tensor* dy, int kh, int kw, float* dw, void* stream) {
+  REQ_T(x, "x"); REQ_T(dy, "dy");
+  B200_REQUIRE(dw, B200_ERR_BAD_ARG, "conv2d_wgrad_atomic: dw is NULL");
+  B200_REQUIRE(kh == kw && x->n == dy->n && x->h == dy->h && x->w == dy->w, B200_ERR_BAD_ARG,
+               "conv2d_wgrad_atomic: shapes disagree");
+  B200_REQUIRE(wgrad_tc_supported(x, dy, kh), B200_ERR_UNSUPPORTED,
+               "conv2d_wgrad_atomic: only the tcgen05 shapes (bf16, channels multiples of 64, 3x3 or 1x1)");
+  return wgrad_tc_launch(x, dy, dw, nullptr, 0, ST(stream), kh, 1);
 }
 
 int b200_filter_pack(const void* hwio, void* ohwi, int kh, int kw, int cin, int cout, int dtype, void* stream) {

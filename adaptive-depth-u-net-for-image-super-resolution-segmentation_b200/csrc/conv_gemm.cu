@@ -276,6 +276,7 @@ struct WgSmallParams {
   int tiles_w, tiles_h, bw, bh, bn, ntaps;
   int live_taps[9];
   float* out;   // [splits][ntaps][Cin][Cout]
+  int atomic;   // 1: `out` is dw[ntaps][Cin][Cout] itself, every split adds into it with vector atomics
 };
 
 __global__ void __launch_bounds__(NTHREADS, 1)
@@ -356,7 +357,7 @@ wgrad_small_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
     const int q = warp % 4;
     const int ci = q * 32 + lane;      // TMEM lane = input channel of the block
     const int tslot = p.ntaps == 1 ? 0 : tap;
-    float* dst = p.out + (((long long)split * p.ntaps + tslot) * p.Cin + cb * 128 + ci) * p.Cout + ob * 128;
+    float* dst = p.out + (((long long)(p.atomic ? 0 : split) * p.ntaps + tslot) * p.Cin + cb * 128 + ci) * p.Cout + ob * 128;
     if (t_end > t_begin) {
       mbar_wait(smem_u32(&bar_done), 0);
       tc_fence_after();
@@ -364,12 +365,19 @@ wgrad_small_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
         uint32_t v[32];
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
         tmem_ld_wait();
+        if (p.atomic) {
 #pragma unroll
-        for (int i = 0; i < 32; i += 4)
-          *reinterpret_cast<float4*>(dst + c0 + i) = make_float4(__uint_as_float(v[i]), __uint_as_float(v[i + 1]),
-                                                                 __uint_as_float(v[i + 2]), __uint_as_float(v[i + 3]));
+          for (int i = 0; i < 32; i += 4)
+            red_add_v4(dst + c0 + i, __uint_as_float(v[i]), __uint_as_float(v[i + 1]), __uint_as_float(v[i + 2]),
+                       __uint_as_float(v[i + 3]));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; i += 4)
+            *reinterpret_cast<float4*>(dst + c0 + i) = make_float4(__uint_as_float(v[i]), __uint_as_float(v[i + 1]),
+                                                                   __uint_as_float(v[i + 2]), __uint_as_float(v[i + 3]));
+        }
       }
-    } else {
+    } else if (!p.atomic) {
       for (int c0 = 0; c0 < 128; c0 += 4) *reinterpret_cast<float4*>(dst + c0) = make_float4(0.f, 0.f, 0.f, 0.f);
     }
   }
@@ -498,7 +506,7 @@ size_t wgrad_small_workspace(const b200_tensor* x, const b200_tensor* dy, int ks
 
 // returns the number of splits written ([splits][ntaps][Cin][Cout] in `out`); dead taps are left untouched
 int wgrad_small_launch(const b200_tensor* x, const b200_tensor* dy, float* out, int ks, int* splits_out, int* live_mask,
-                       cudaStream_t st) {
+                       cudaStream_t st, int atomic) {
   const WgSmallPlan pl = wg_small_plan(x, dy, ks);
   WgSmallParams p;
   p.Cin = x->c; p.Cout = dy->c; p.cblocks = x->c / 128; p.oblocks = dy->c / 128; p.nlive = pl.nlive;
@@ -511,6 +519,7 @@ int wgrad_small_launch(const b200_tensor* x, const b200_tensor* dy, float* out, 
     if (i < pl.nlive) mask |= 1 << (ks == 1 ? 0 : pl.taps[i]);
   }
   p.out = out;
+  p.atomic = atomic;
   CUtensorMap tm_x, tm_dz;
   int rc = make_act_tmap(&tm_x, x, p.bw, p.bh, p.bn);
   if (rc) return rc;

@@ -44,6 +44,7 @@ struct WgradParams {
   int nb, ksteps, stage_bytes, zero_smem;   // stacked small images: nb images per tile, ksteps 16-pixel K steps
   int ntaps;   // 9 (3x3 filter) or 1 (1x1 filter: only the centre tap of the window is accumulated)
   float* partial;  // [splits][9][Cin][Cout]
+  float* dw_atomic;   // non-NULL: skip the partial slabs and add straight into dw[9][Cin][Cout] with vector atomics
 };
 
 __device__ __forceinline__ void umma_lohi(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
@@ -161,17 +162,26 @@ wgrad3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
       const int tap = pair_first(pi) + half;
       const bool dup = (pi == 4 && half == 0) || (p.ntaps == 1 && half == 1);   // rows 0..63 of the last pair repeat tap 7
       const int tslot = p.ntaps == 1 ? 0 : tap;
-      float* dst = p.partial + (((long long)s * p.ntaps + tslot) * p.Cin + cb * 64 + ci) * p.Cout + ob * 64;
+      float* dst = p.dw_atomic
+                       ? p.dw_atomic + (((long long)tslot) * p.Cin + cb * 64 + ci) * p.Cout + ob * 64
+                       : p.partial + (((long long)s * p.ntaps + tslot) * p.Cin + cb * 64 + ci) * p.Cout + ob * 64;
       for (int c0 = 0; c0 < 64; c0 += 32) {
         uint32_t v[32];
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(pi * 64 + c0), v);
         tmem_ld_wait();
         if (!dup) {
+          if (p.dw_atomic) {
 #pragma unroll
-          for (int i = 0; i < 32; i += 4)
-            *reinterpret_cast<float4*>(dst + c0 + i) =
-                make_float4(__uint_as_float(v[i]), __uint_as_float(v[i + 1]), __uint_as_float(v[i + 2]),
-                            __uint_as_float(v[i + 3]));
+            for (int i = 0; i < 32; i += 4)
+              red_add_v4(dst + c0 + i, __uint_as_float(v[i]), __uint_as_float(v[i + 1]), __uint_as_float(v[i + 2]),
+                         __uint_as_float(v[i + 3]));
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; i += 4)
+              *reinterpret_cast<float4*>(dst + c0 + i) =
+                  make_float4(__uint_as_float(v[i]), __uint_as_float(v[i + 1]), __uint_as_float(v[i + 2]),
+                              __uint_as_float(v[i + 3]));
+          }
         }
       }
     }
@@ -274,7 +284,7 @@ inline void plan(const b200_tensor* x_in, const b200_tensor* dy_in, WgradParams&
 bool wgrad_small_wanted(const b200_tensor* x, const b200_tensor* dy, int ks);
 size_t wgrad_small_workspace(const b200_tensor* x, const b200_tensor* dy, int ks);
 int wgrad_small_launch(const b200_tensor* x, const b200_tensor* dy, float* out, int ks, int* splits_out, int* live_mask,
-                       cudaStream_t st);
+                       cudaStream_t st, int atomic = 0);
 
 bool wgrad_tc_supported(const b200_tensor* x, const b200_tensor* dy, int ks) {
   if (ks != 3 && ks != 1) return false;
@@ -296,7 +306,11 @@ size_t wgrad_tc_workspace(const b200_tensor* x, const b200_tensor* dy, int ks) {
 }
 
 int wgrad_tc_launch(const b200_tensor* x, const b200_tensor* dy, float* dw, void* ws, size_t ws_bytes,
-                    cudaStream_t st, int ks) {
+                    cudaStream_t st, int ks, int atomic) {
+  if (atomic && wgrad_small_wanted(x, dy, ks)) {
+    int splits_s = 1, mask_s = 0;
+    return wgrad_small_launch(x, dy, dw, ks, &splits_s, &mask_s, st, 1);
+  }
   if (wgrad_small_wanted(x, dy, ks)) {
     // deep levels (images <= 8x8): one CTA per (tap, 128 ci, 128 co[, split]) over densely packed pixel boxes
     const size_t need_s = wgrad_small_workspace(x, dy, ks);
@@ -318,11 +332,12 @@ int wgrad_tc_launch(const b200_tensor* x, const b200_tensor* dy, float* dw, void
   WgradGeom g;
   plan(x, dy, p, g, ks);
   const size_t need = sizeof(float) * (size_t)p.splits * p.ntaps * p.Cin * p.Cout;
-  B200_REQUIRE(ws && ws_bytes >= need, B200_ERR_BAD_ARG, "conv2d_wgrad: workspace too small (%zu < %zu bytes)",
+  B200_REQUIRE(atomic || (ws && ws_bytes >= need), B200_ERR_BAD_ARG, "conv2d_wgrad: workspace too small (%zu < %zu bytes)",
                ws_bytes, need);
-  B200_REQUIRE((uintptr_t)ws % 16 == 0 && (uintptr_t)dw % 16 == 0, B200_ERR_BAD_ARG,
+  B200_REQUIRE((atomic || (uintptr_t)ws % 16 == 0) && (uintptr_t)dw % 16 == 0, B200_ERR_BAD_ARG,
                "conv2d_wgrad: workspace/dw must be 16-byte aligned");
   p.partial = reinterpret_cast<float*>(ws);
+  p.dw_atomic = atomic ? dw : nullptr;
   CUtensorMap tm_x, tm_dz;
   int rc = make_act_tmap(&tm_x, &g.x, WIN_W, g.box_h, g.box_n);
   if (rc) return rc;
@@ -337,7 +352,7 @@ int wgrad_tc_launch(const b200_tensor* x, const b200_tensor* dy, float* dw, void
   const int grid = p.splits * p.cblocks * p.oblocks;
   wgrad3x3_tc_kernel<<<grid, NTHREADS, smem, st>>>(tm_x, tm_dz, p);
   int rc2 = check_launch("wgrad3x3_tc_kernel");
-  if (rc2) return rc2;
+  if (rc2 || atomic) return rc2;
   const long long count = (long long)p.ntaps * p.Cin * p.Cout;
   long long blocks = (count / 4 + 63) / 64;
   if (blocks > 8LL * sm_count()) blocks = 8LL * sm_count();

@@ -18,6 +18,7 @@ what keras' ``train_step`` does with a GradientTape
 """
 from __future__ import annotations
 
+import os
 from typing import Callable, Dict, List, Optional
 
 import torch
@@ -399,9 +400,17 @@ class Plan:
                 dw = m._grad(ly, "kernel").view(-1)
                 self._cur_tag = "wgrad" + sfx
                 writes(ly, "kernel")
+                # the step zeroes the flat gradient buffer first, so the tcgen05 wgrad kernels add their partial sums
+                # straight into it (vector atomics): no partial slabs, no reduce launch
+                atomic = sfx == ":tc" and os.environ.get("B200_WGRAD_ATOMIC", "1") == "1"
                 if getattr(op, "xcol", None) is not None:     # stem: 1x1 wgrad over the im2col tensor
-                    B.append(lambda xc=op.xcol, o=out, dw=m._stem_padded(ly)[1]:
-                             ops.conv2d_wgrad(xc, o.grad, 1, 1, dw, self.wgrad_ws))
+                    if atomic:
+                        B.append(lambda xc=op.xcol, o=out, dw=m._stem_padded(ly)[1]: ops.conv2d_wgrad_atomic(xc, o.grad, 1, 1, dw))
+                    else:
+                        B.append(lambda xc=op.xcol, o=out, dw=m._stem_padded(ly)[1]:
+                                 ops.conv2d_wgrad(xc, o.grad, 1, 1, dw, self.wgrad_ws))
+                elif atomic:
+                    B.append(lambda x=x, o=out, dw=dw, kh=kh: ops.conv2d_wgrad_atomic(x.buf, o.grad, kh, kh, dw))
                 else:
                     B.append(lambda x=x, o=out, dw=dw, kh=kh: ops.conv2d_wgrad(x.buf, o.grad, kh, kh, dw, self.wgrad_ws))
                 if x.needs_grad:

@@ -123,6 +123,12 @@ def conv2d_wgrad(x, dy, kh, kw, dw, workspace=None, algo=ALGO_AUTO):
     return dw
 
 
+def conv2d_wgrad_atomic(x, dy, kh, kw, dw):
+    """dw += filter gradient through vector atomics (no workspace, no reduce launch); dw must be pre-zeroed."""
+    check(lib().b200_conv2d_wgrad_atomic(tdesc(x), tdesc(dy), kh, kw, _ptr(dw), _stream()), "conv2d_wgrad_atomic")
+    return dw
+
+
 def convT2x2_fprop(x, kernel, bias, y):
     check(lib().b200_convT2x2_fprop(tdesc(x), _ptr(kernel), _ptr(bias), kernel.shape[2], tdesc(y), _stream()), "convT2x2_fprop")
     return y

@@ -109,6 +109,11 @@ size_t b200_conv2d_workspace(const b200_tensor* x, const b200_filter* f, int dgr
 size_t b200_conv2d_wgrad_workspace(const b200_tensor* x, const b200_tensor* dy, int kh, int kw, int algo);
 int b200_conv2d_wgrad(const b200_tensor* x, const b200_tensor* dy, int kh, int kw, float* dw_hwio,
                       void* workspace, size_t workspace_bytes, int algo, void* stream);
+/* dw_hwio += sum_pixels x (*) dy without a workspace: every CTA adds its partial sums straight into dw with
+ * vector atomics (fp32 `red.global.add.v4`), which removes the partial slabs and the reduce launch.  dw must hold
+ * zeros (or a partial gradient to add to) on entry; the summation order, hence the last bits, vary run to run.
+ * tcgen05 shapes only (bf16, Cin and Cout multiples of 64, 3x3 or 1x1); B200_ERR_UNSUPPORTED otherwise. */
+int b200_conv2d_wgrad_atomic(const b200_tensor* x, const b200_tensor* dy, int kh, int kw, float* dw_hwio, void* stream);
 /* hwio -> ohwi repack (same dtype). */
 int b200_filter_pack(const void* hwio, void* ohwi, int kh, int kw, int cin, int cout, int dtype, void* stream);
 /* im2col of a narrow 3x3 "same" convolution input (Cin*9 <= 64: the RGB stem, train_adaptive_unet.py:202

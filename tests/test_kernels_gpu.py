@@ -349,6 +349,24 @@ def test_stem_im2col_tensor_core_path(shape, src_dtype):
     assert float(dw[9 * ci:].abs().max()) == 0.0
 
 
+@pytest.mark.parametrize("shape", [(2, 32, 32, 64, 64, 3), (1, 20, 13, 128, 64, 3), (3, 40, 24, 128, 128, 3), (4, 2, 2, 128, 256, 3),
+                                   (16, 1, 1, 128, 128, 3), (3, 8, 8, 128, 256, 3), (2, 16, 16, 64, 64, 1)])
+def test_conv_wgrad_atomic(shape):
+    """dw += wgrad through vector atomics (no workspace / reduce launch): exact accumulate semantics on a pre-filled dw."""
+    ops, K = _ops(), _K()
+    n, h, w, ci, co, ks = shape
+    dt = torch.bfloat16
+    x = rand((n, h, w, ci), 131, dt)
+    dy = rand((n, h, w, co), 132, dt)
+    base = rand((ks, ks, ci, co), 133, torch.float32)
+    dw = base.clone()
+    ops.conv2d_wgrad_atomic(x, dy, ks, ks, dw)
+    torch.cuda.synchronize()
+    wr = torch.zeros(ks, ks, ci, co, requires_grad=True)
+    (K.conv2d_same(f32(x), wr) * f32(dy)).sum().backward()
+    assert relerr(dw - base, wr.grad) < 2e-3
+
+
 # ----------------------------------------------------------------------------- layer norm
 @pytest.mark.parametrize("dtype", DTYPES)
 @pytest.mark.parametrize("shape", [(2, 7, 5, 64), (1, 3, 3, 8), (2, 4, 4, 256), (1, 2, 3, 1024), (1, 1, 5, 2048)])
