@@ -23,6 +23,7 @@ import torch
 from .. import ops
 from .._ffi import B200Error
 from . import layers as L
+from . import losses
 from .engine import Plan
 
 _POLICY = {"name": "float32"}
@@ -63,6 +64,17 @@ class History:
     def __init__(self):
         self.epoch: List[int] = []
         self.history: Dict[str, List[float]] = {}
+
+
+class PendingStep:
+    """Handle of an enqueued training step (Model.train_on_batch_async)."""
+
+    def __init__(self, event, host, names, slots):
+        self._event, self._host, self._names, self._slots = event, host, names, slots
+
+    def result(self) -> Dict[str, float]:
+        self._event.synchronize()
+        return {n: float(self._host[s]) for n, s in zip(self._names, self._slots)}
 
 
 class Model:
@@ -499,19 +511,83 @@ class Model:
         dst.copy_(src.reshape(dst.shape), non_blocking=True)
 
     # ------------------------------------------------------------------ steps
+    def _feed(self, e, x, y):
+        """Inputs of one training step -> the plan's input / target buffers.
+
+        Host batches go through a two-slot staging ring filled on a COPY stream, so the host->device copy of
+        step i+1 overlaps the kernels of step i (the compute stream only does a device-to-device copy of the slot);
+        device tensors and targets that need a conversion (one-hot -> class ids ...) take the direct path."""
+        plan, st = e["plan"], e["state"]
+        xb, tgt = plan.input_vals[0].buf, st["target"]
+        xs = torch.from_numpy(x) if isinstance(x, np.ndarray) else x
+        ys = torch.from_numpy(y) if isinstance(y, np.ndarray) else y
+        staged = (not xs.is_cuda and not ys.is_cuda and xs.dtype == xb.dtype and ys.dtype == tgt.dtype
+                  and xs.numel() == xb.numel() and ys.numel() == tgt.numel()
+                  and type(self.loss).set_target is losses._PlanLoss.set_target)
+        if not staged:
+            self._to_device(xb, x)
+            self.loss.set_target(st, y)
+            return
+        pipe = e.get("pipe")
+        if pipe is None:
+            pipe = e["pipe"] = {
+                "i": 0, "stream": torch.cuda.Stream(),
+                "x": [torch.empty_like(xb) for _ in range(2)], "y": [torch.empty_like(tgt) for _ in range(2)],
+                "ready": [torch.cuda.Event() for _ in range(2)], "free": [torch.cuda.Event() for _ in range(2)],
+            }
+            cur = torch.cuda.current_stream()
+            for ev in pipe["free"]:
+                ev.record(cur)
+        k = pipe["i"] % 2
+        pipe["i"] += 1
+        cs, cur = pipe["stream"], torch.cuda.current_stream()
+        cs.wait_event(pipe["free"][k])            # the step that last read slot k has copied it out
+        with torch.cuda.stream(cs):
+            pipe["x"][k].copy_(xs.reshape(xb.shape), non_blocking=True)
+            pipe["y"][k].copy_(ys.reshape(tgt.shape), non_blocking=True)
+            pipe["ready"][k].record(cs)
+        cur.wait_event(pipe["ready"][k])
+        xb.copy_(pipe["x"][k])
+        tgt.copy_(pipe["y"][k])
+        pipe["free"][k].record(cur)
+
     def train_on_batch(self, x, y, return_tensors=False):
         """One optimisation step; returns {"loss": ..., metric: ...} (device tensors if asked)."""
         if self.loss is None:
             raise RuntimeError("compile() the model before training")
         batch = int(x.shape[0])
         e = self._train_state(batch)
-        plan, st = e["plan"], e["state"]
-        self._to_device(plan.input_vals[0].buf, x)
-        self.loss.set_target(st, y)
+        self._feed(e, x, y)
         self.optimizer.before_step()
         self._run_step(e)
-        logs = self.loss.logs(st)
+        logs = self.loss.logs(e["state"])
         return logs if return_tensors else {k: float(v) for k, v in logs.items()}
+
+    def train_on_batch_async(self, x, y):
+        """train_on_batch without the host synchronisation: the step is enqueued (its host->device copy on the copy
+        stream, see _feed), the loss / metrics are copied to a pinned host buffer behind it, and a handle is
+        returned; ``handle.result()`` waits for THAT step and returns the float logs.  Keep at most two steps in
+        flight (the pinned result slots are a ring of two)."""
+        if self.loss is None:
+            raise RuntimeError("compile() the model before training")
+        batch = int(x.shape[0])
+        e = self._train_state(batch)
+        self._feed(e, x, y)
+        self.optimizer.before_step()
+        self._run_step(e)
+        st = e["state"]
+        res = e.get("results")
+        if res is None:
+            res = e["results"] = {"i": 0, "host": [torch.empty(st["out"].shape, dtype=st["out"].dtype).pin_memory()
+                                                   for _ in range(2)],
+                                  "done": [torch.cuda.Event() for _ in range(2)]}
+        k = res["i"] % 2
+        res["i"] += 1
+        res["host"][k].copy_(st["out"], non_blocking=True)
+        res["done"][k].record(torch.cuda.current_stream())
+        names = ["loss"] + list(self.loss.metric_names)
+        slots = [0] + list(self.loss.metric_slots)
+        return PendingStep(res["done"][k], res["host"][k], names, slots)
 
     def test_on_batch(self, x, y):
         batch = int(x.shape[0])

@@ -133,6 +133,42 @@ def test_sr_unet_deep_levels_collapse_to_1x1():
     assert abs(logs["loss"] - l_ref) < 2e-3 * max(1.0, abs(l_ref))
 
 
+def test_async_pipelined_steps_match_synchronous_steps():
+    """train_on_batch_async (host->device copies staged on a copy stream, results through pinned host memory, one step
+    in flight) must produce exactly the losses of the synchronous loop on the same batches."""
+    from b200unet import builders as B
+    from b200unet.keras.optimizers import Adam
+    rng = np.random.default_rng(5)
+    batches = []
+    for _ in range(6):
+        hr = rng.random((4, 32, 32, 3), dtype=np.float32)
+        batches.append((np.clip(hr + 0.1 * rng.standard_normal(hr.shape).astype(np.float32), 0, 1), hr))
+    runs = []
+    for mode in ("sync", "async"):
+        _setup("mixed_bfloat16")
+        model, _ = B.build_super_resolution_unet(0.5, depth_override=2, input_size=32)
+        loss, metrics = B.build_losses_and_metrics("charbonnier")
+        model.compile(optimizer=Adam(learning_rate=1e-3), loss=loss, metrics=metrics)
+        out = []
+        if mode == "sync":
+            for lr, hr in batches:
+                out.append(model.train_on_batch(lr, hr))
+        else:
+            prev = None
+            for lr, hr in batches:
+                h = model.train_on_batch_async(torch.from_numpy(lr).pin_memory(), torch.from_numpy(hr).pin_memory())
+                if prev is not None:
+                    out.append(prev.result())
+                prev = h
+            out.append(prev.result())
+        runs.append(out)
+    print([(round(a["loss"], 7), round(b["loss"], 7)) for a, b in zip(*runs)])
+    # step 1 sees identical weights: identical loss; later steps differ in the last bits only (gradient sums use atomics)
+    assert abs(runs[0][0]["loss"] - runs[1][0]["loss"]) <= 1e-6
+    for a, b in zip(*runs):
+        assert abs(a["loss"] - b["loss"]) <= 2e-4 * max(1.0, abs(a["loss"])) and abs(a["psnr"] - b["psnr"]) <= 2e-2, (a, b)
+
+
 def test_sr_unet_training_reduces_loss():
     """A few steps on a fixed batch: the loss must go down and stay finite (bf16 policy, graph replay)."""
     from b200unet import builders as B
