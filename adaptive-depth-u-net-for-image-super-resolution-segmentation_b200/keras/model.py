@@ -125,8 +125,13 @@ class Model:
         rng = np.random.default_rng(_SEED["value"])
         self._pinfo: Dict[str, tuple] = {}
         self._stem_slots: Dict[str, int] = {}
-        off_t = off_n = 0
+        # Flat layout of the trainable parameters: [ every rank-4 kernel, in layer order | pad to 512 | every vector
+        # (bias, gamma, beta), in layer order ].  Data parallelism shards the optimizer over the kernel region
+        # (reduce-scatter -> Adam on the owned shard -> all-gather of the compute-dtype shadow) and keeps the tiny
+        # vector region replicated, because the kernels read biases / gamma / beta from the fp32 master directly.
+        off_n = 0
         host_t, host_n = [], []
+        slots = []
         for ly in self.layers:
             for w in ly.weight_specs:
                 val = w["value"] if w["value"] is not None else _init_array(w["init"], w["shape"], rng)
@@ -139,15 +144,25 @@ class Model:
                     slot = 64 * w["shape"][3]
                     self._stem_slots[w["name"]] = slot
                 if w["trainable"]:
-                    self._pinfo[w["name"]] = (True, off_t, w["shape"])
-                    host_t.append((off_t, val)); off_t += (slot + 63) // 64 * 64
+                    slots.append((w, val, (slot + 63) // 64 * 64, len(w["shape"]) == 4))
                 else:
                     self._pinfo[w["name"]] = (False, off_n, w["shape"])
                     host_n.append((off_n, val)); off_n += (n + 63) // 64 * 64
                 w["value"] = None
             ly._model = self
+        off_t = 0
+        for w, val, size, big in slots:
+            if big:
+                self._pinfo[w["name"]] = (True, off_t, w["shape"])
+                host_t.append((off_t, val)); off_t += size
+        self._kernel_region = off_t = (off_t + 511) // 512 * 512
+        for w, val, size, big in slots:
+            if not big:
+                self._pinfo[w["name"]] = (True, off_t, w["shape"])
+                host_t.append((off_t, val)); off_t += size
+        off_t = (off_t + 511) // 512 * 512
         self._nparams = off_t
-        flat = np.zeros(max(off_t, 64), np.float32)
+        flat = np.zeros(max(off_t, 512), np.float32)
         for o, v in host_t:
             flat[o:o + v.size] = v.ravel()
         flat_n = np.zeros(max(off_n, 64), np.float32)
@@ -184,6 +199,7 @@ class Model:
         return self._filters[key], self.G[off:off + n]
 
     def _refresh_shadow(self):
+        self._sync_master()
         if self.S is not self.P:
             ops.cast(self.P, self.S)
         for f in self._filters.values():
@@ -232,6 +248,7 @@ class Model:
     # weights API ---------------------------------------------------------------
     def _layer_weights(self, ly):
         self._ensure_built()
+        self._sync_master()
         return [self._param(ly, w["name"].split("/", 1)[1]).detach().cpu().numpy().copy() for w in ly.weight_specs]
 
     def _push_layer_weights(self, ly):
@@ -361,8 +378,27 @@ class Model:
             self._bucket_cache = {}
         if key not in self._bucket_cache:
             elems = int(float(os.environ.get("B200_BUCKET_MB", "32")) * (1 << 20) / 4)
-            self._bucket_cache[key] = plan_buckets(self.G.numel(), plan.bwd_writes, elems)
+            world = self._world()
+            if self._sharded():
+                # kernel region: buckets that divide evenly over the ranks (reduce-scatter / sharded Adam / all-gather)
+                bs = plan_buckets(self._kernel_region, plan.bwd_writes, elems, align=64 * world)
+                for b in bs:
+                    b["sharded"] = True
+                # vector region (biases, gamma, beta): one small replicated bucket, complete when backward ends
+                bs.append({"lo": self._kernel_region, "hi": self.G.numel(), "ready_after": len(plan.bwd_steps) - 1,
+                           "sharded": False})
+                bs.sort(key=lambda b: b["ready_after"])
+            else:
+                bs = plan_buckets(self.G.numel(), plan.bwd_writes, elems)
+                for b in bs:
+                    b["sharded"] = False
+            self._bucket_cache[key] = bs
         return self._bucket_cache[key]
+
+    def _sharded(self) -> bool:
+        """Sharded optimizer (ZeRO-1 style) under data parallelism; B200_DP_SHARD=0 selects all-reduce + replicated Adam."""
+        return (self._dist is not None and self._world() > 1 and self._kernel_region > 0
+                and os.environ.get("B200_DP_SHARD", "1") == "1")
 
     def _world(self):
         if self._dist is None:
@@ -402,13 +438,72 @@ class Model:
             works += self._reduce_async(buckets)
         for w in works:
             w.wait()
-        self.optimizer.apply(self)
+        self._apply_optimizer(plan)
+        self._gather_updated(plan)
+        self._last_train_plan = plan
 
     def _reduce_async(self, buckets):
         if not buckets:
             return []
+        from ..parallel import reduce_scatter_bucket
         dist, group = self._dist
-        return [dist.all_reduce(self.G[b["lo"]:b["hi"]], group=group, async_op=True) for b in buckets]
+        works = []
+        for b in buckets:
+            if b["sharded"]:
+                works.append(reduce_scatter_bucket(dist, self.G, b, group=group, async_op=True))
+            else:
+                works.append(dist.all_reduce(self.G[b["lo"]:b["hi"]], group=group, async_op=True))
+        return works
+
+    def _update_ranges(self, plan):
+        """Flat ranges this rank's Adam updates: everything, or (sharded) its shard of every kernel bucket plus the
+        replicated vector region."""
+        if not self._sharded():
+            return None
+        from ..parallel import shard_of
+        dist, group = self._dist
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        return [shard_of(b, rank, world) if b["sharded"] else (b["lo"], b["hi"]) for b in self._buckets(plan)]
+
+    def _apply_optimizer(self, plan):
+        self.optimizer.apply(self, self._update_ranges(plan))
+
+    def _gather_updated(self, plan):
+        """Sharded optimizer: publish the updated shards of the compute-dtype shadow (the fp32 master of the kernel
+        region stays sharded until someone reads the weights, see _sync_master)."""
+        if not self._sharded():
+            return
+        from ..parallel import all_gather_bucket
+        dist, group = self._dist
+        works = [all_gather_bucket(dist, self.S, b, group=group, async_op=True) for b in self._buckets(plan) if b["sharded"]]
+        for w in works:
+            w.wait()
+        self._master_plan = plan if self.S is not self.P else None
+
+    def gathered_gradients(self, plan=None):
+        """Collective (every rank): a copy of the flat gradient buffer with every bucket fully reduced -- under the
+        sharded optimizer a rank only holds the summed gradient of its own shards."""
+        g = self.G.clone()
+        plan = plan or getattr(self, "_last_train_plan", None)
+        if self._sharded() and plan is not None:
+            from ..parallel import all_gather_bucket
+            dist, group = self._dist
+            for b in self._buckets(plan):
+                if b["sharded"]:
+                    all_gather_bucket(dist, g, b, group=group)
+        return g
+
+    def _sync_master(self):
+        """Collective (call on every rank): all-gather the fp32 master of the kernel region after sharded steps."""
+        plan = getattr(self, "_master_plan", None)
+        if plan is None or self._dist is None:
+            return
+        from ..parallel import all_gather_bucket
+        dist, group = self._dist
+        for b in self._buckets(plan):
+            if b["sharded"]:
+                all_gather_bucket(dist, self.P, b, group=group)
+        self._master_plan = None
 
     def _train_state(self, batch):
         key = ("train", batch)
@@ -449,7 +544,7 @@ class Model:
                     segs.append((g, buckets))
                 ga = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(ga):
-                    self.optimizer.apply(self)
+                    self._apply_optimizer(plan)
                 entry["segments"], entry["adam_graph"] = segs, ga
         self._graphs[key] = entry
         return entry
@@ -466,6 +561,8 @@ class Model:
             for w in works:
                 w.wait()
             entry["adam_graph"].replay()
+            self._gather_updated(entry["plan"])
+            self._last_train_plan = entry["plan"]
         else:
             self._train_body(entry["plan"], entry["state"])
 

@@ -67,11 +67,18 @@ class Adam:
                 self._push_hyper()
         self.iterations += 1
 
-    def apply(self, model):
+    def apply(self, model, ranges=None):
+        """One Adam step over the flat buffers, or over `ranges` = [(lo, hi), ...] of them (sharded optimizer)."""
         st = self._state
         ops.adam_advance(st["step"])
-        ops.adam_step(model.P, model.G, st["m"], st["v"], st["hyper"], st["step"],
-                      model.S if model.S is not model.P else None)
+        shadow = model.S if model.S is not model.P else None
+        if ranges is None:
+            ops.adam_step(model.P, model.G, st["m"], st["v"], st["hyper"], st["step"], shadow)
+            return
+        for lo, hi in ranges:
+            if hi > lo:
+                ops.adam_step(model.P[lo:hi], model.G[lo:hi], st["m"][lo:hi], st["v"][lo:hi], st["hyper"], st["step"],
+                              None if shadow is None else shadow[lo:hi])
 
     def snapshot(self):
         st = self._state

@@ -61,6 +61,50 @@ def _worker(rank, world, port, out):
     dist.destroy_process_group()
 
 
+def _worker_sharded(rank, world, port, out):
+    """Sharded optimizer on CPU tensors: reduce-scatter (gloo: emulated by all-reduce) -> Adam on the owned shard ->
+    all-gather; every rank must end with the parameters of a single-process Adam step on the summed gradient."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from b200unet.parallel import all_gather_bucket, plan_buckets, reduce_scatter_bucket, shard_of
+    torch.manual_seed(0)
+    total, align = 64 * world * 37, 64 * world
+    p0 = torch.randn(total)
+    g_ranks = [torch.randn(total, generator=torch.Generator().manual_seed(10 + r)) for r in range(world)]
+    writes = [[(o, 700)] for o in reversed(range(0, total - 700, 700))] + [[(total - total % 700 if total % 700 else total - 700, 10)]]
+    buckets = plan_buckets(total, writes, bucket_elems=3000, align=align)
+    assert sum(b["hi"] - b["lo"] for b in buckets) == total and all((b["hi"] - b["lo"]) % align == 0 for b in buckets)
+    g = g_ranks[rank].clone()
+    for b in buckets:
+        reduce_scatter_bucket(dist, g, b)
+    p = p0.clone()
+    m = torch.zeros(total); v = torch.zeros(total)
+    for b in buckets:
+        lo, hi = shard_of(b, rank, world)
+        pn, _, _ = K.adam_step(p[lo:hi], g[lo:hi], m[lo:hi], v[lo:hi], 1, 1e-3)
+        p[lo:hi] = pn
+    for b in buckets:
+        all_gather_bucket(dist, p, b)
+    ref, _, _ = K.adam_step(p0, sum(g_ranks), torch.zeros(total), torch.zeros(total), 1, 1e-3)
+    out.put((rank, ((p - ref).norm() / ref.norm()).item()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sharded_optimizer_equivalence_gloo():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_sharded, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    errs = dict(q.get(timeout=240) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert set(errs) == {0, 1} and max(errs.values()) < 1e-6, errs
+
+
 def test_dp_gradient_equivalence_gloo():
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
@@ -83,6 +127,11 @@ def test_shard_range_and_bucket_plan():
     writes = [[(900, 100)], [(800, 50), (850, 50)], [(0, 800)]]
     b = plan_buckets(1000, writes, 120)
     assert b == [{"lo": 850, "hi": 1000, "ready_after": 1}, {"lo": 0, "hi": 850, "ready_after": 2}]
+    # aligned plan (sharded optimizer): boundaries are multiples of `align`, a straddling range counts for both buckets
+    a = plan_buckets(1024, [[(960, 64)], [(500, 460)], [(0, 500)]], 200, align=128)
+    assert all(x["lo"] % 128 == 0 and x["hi"] % 128 == 0 for x in a) and sum(x["hi"] - x["lo"] for x in a) == 1024
+    lows = sorted(x["lo"] for x in a)
+    assert lows[0] == 0 and {x["ready_after"] for x in a if x["lo"] <= 500 < x["hi"]} == {2}
     # every element is covered exactly once whatever the bucket size
     for size in (1, 64, 10_000):
         bs = sorted(plan_buckets(1000, writes, size), key=lambda d: d["lo"])

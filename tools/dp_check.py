@@ -43,8 +43,13 @@ def main():
     m_dp = make(True)
     logs = m_dp.train_on_batch(lr[lo:hi], hr[lo:hi])
     torch.cuda.synchronize()
-    g_dp = m_dp.G.clone()
+    g_dp = m_dp.gathered_gradients()      # collective: under the sharded optimizer a rank holds only its shards' sums
+    m_dp._sync_master()                   # collective: all-gather the fp32 master of the kernel region
     p_dp = m_dp.P.clone()
+    s_dp = m_dp.S.clone().float()
+    s_ref = s_dp.clone()
+    dist.broadcast(s_ref, src=0)
+    assert bool((s_ref == s_dp).all().item()), "compute-dtype shadow differs between ranks"
     # every rank must hold identical weights after the step
     p_ref = p_dp.clone()
     dist.broadcast(p_ref, src=0)
