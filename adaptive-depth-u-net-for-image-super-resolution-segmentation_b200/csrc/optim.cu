@@ -132,38 +132,28 @@ convT2_dgrad_kernel(TView dy, const T* __restrict__ k, TView dx, long long total
   }
 }
 
-// dK[a,b,o,c] = sum_{n,i,j} dy[n,2i+a,2j+b,o] * x[n,i,j,c]; one block per (a,b,o), threads over c, atomics-free
+// dK[a,b,o,c] = sum_{n,i,j} dy[n,2i+a,2j+b,o] * x[n,i,j,c]; grid = (4*Cout, pixel splits), threads over c, one atomic
+// per (block, c) into the zeroed dk  (fallback for channel counts the tensor-core path does not take)
 template <typename T>
 __global__ void __launch_bounds__(NT)
-convT2_wgrad_kernel(TView x, TView dy, float* __restrict__ dk, float* __restrict__ dbias) {
+convT2_wgrad_kernel(TView x, TView dy, float* __restrict__ dk) {
   const T* xp = reinterpret_cast<const T*>(x.data);
   const T* dyp = reinterpret_cast<const T*>(dy.data);
   const int Cin = x.c, Cout = dy.c;
   const int o = blockIdx.x % Cout, ab = blockIdx.x / Cout;
   const int a = ab / 2, b = ab % 2;
   const long long npix = (long long)x.n * x.h * x.w;
+  const long long p0 = npix * blockIdx.y / gridDim.y, p1 = npix * (blockIdx.y + 1) / gridDim.y;
   for (int c = threadIdx.x; c < Cin; c += NT) {
     float acc = 0.f;
-    for (long long p = 0; p < npix; ++p) {
+    for (long long p = p0; p < p1; ++p) {
       int w = (int)(p % x.w);
       long long q = p / x.w;
       int h = (int)(q % x.h);
       int n = (int)(q / x.h);
       acc += ldf(dyp + pix_offset(dy, n, 2 * h + a, 2 * w + b) + o) * ldf(xp + pix_offset(x, n, h, w) + c);
     }
-    dk[((long long)ab * Cout + o) * Cin + c] = acc;
-  }
-  if (dbias && ab == 0 && threadIdx.x == 0) {
-    float acc = 0.f;
-    const long long opix = (long long)dy.n * dy.h * dy.w;
-    for (long long p = 0; p < opix; ++p) {
-      int w = (int)(p % dy.w);
-      long long q = p / dy.w;
-      int h = (int)(q % dy.h);
-      int n = (int)(q / dy.h);
-      acc += ldf(dyp + pix_offset(dy, n, h, w) + o);
-    }
-    dbias[o] += acc;
+    atomicAdd(dk + ((long long)ab * Cout + o) * Cin + c, acc);
   }
 }
 
@@ -214,10 +204,41 @@ int scale_inplace(float* p, size_t count, float s, cudaStream_t st) {
   return check_launch("scale_kernel");
 }
 
+// ---- tensor-core form: Conv2DTranspose(k2, s2) is four 1x1 convolutions, one per output parity (a, b), whose
+// output (fprop) / input (dgrad, wgrad) is the strided view y[:, a::2, b::2, :] -- the tensor descriptors and the
+// TMA maps take arbitrary strides, so the pixel shuffle costs nothing.
+bool conv_tc_supported(const b200_tensor* x, int cin, int cout, const b200_tensor* y, int ks);
+int conv_tc_launch(const b200_tensor* x, const void* wmat, int cin, int cout, int tap_rev, int b_mn, const float* bias,
+                   const b200_tensor* y, int act, int accumulate, cudaStream_t st, const struct ConvLnArgs* ln, int ks);
+bool wgrad_tc_supported(const b200_tensor* x, const b200_tensor* dy, int ks);
+int wgrad_tc_launch(const b200_tensor* x, const b200_tensor* dy, float* dw, void* ws, size_t ws_bytes, cudaStream_t st,
+                    int ks, int atomic);
+int bias_act_bwd(const b200_tensor* dy, const b200_tensor* y, int act, const b200_tensor* dz, float* dbias, cudaStream_t st);
+
+static b200_tensor parity_view(const b200_tensor* y, int a, int b) {
+  b200_tensor v = *y;
+  v.data = reinterpret_cast<char*>(y->data) + ((long long)a * y->stride_h + (long long)b * y->stride_w) * (long long)dtype_size(y->dtype);
+  v.h = y->h / 2; v.w = y->w / 2;
+  v.stride_h = 2 * y->stride_h; v.stride_w = 2 * y->stride_w;
+  return v;
+}
+
 int convT2_fprop(const b200_tensor* x, const void* kernel, const float* bias, int cout, const b200_tensor* y,
                  cudaStream_t st) {
   B200_REQUIRE(y->h == 2 * x->h && y->w == 2 * x->w && y->n == x->n && y->c == cout && x->dtype == y->dtype,
                B200_ERR_BAD_ARG, "convT2x2_fprop: shape mismatch");
+  {
+    b200_tensor y00 = parity_view(y, 0, 0);
+    if (x->dtype == B200_BF16 && conv_tc_supported(x, x->c, cout, &y00, 1)) {
+      for (int ab = 0; ab < 4; ++ab) {
+        b200_tensor yv = parity_view(y, ab / 2, ab % 2);
+        const __nv_bfloat16* k_ab = reinterpret_cast<const __nv_bfloat16*>(kernel) + (long long)ab * cout * x->c;   // [cout][cin], K-major
+        int rc = conv_tc_launch(x, k_ab, x->c, cout, 0, 0, bias, &yv, B200_ACT_NONE, 0, st, nullptr, 1);
+        if (rc) return rc;
+      }
+      return B200_OK;
+    }
+  }
   long long total = (long long)y->n * y->h * y->w * y->c;
   TView xv = view_of(x), yv = view_of(y);
   B200_DISPATCH_DTYPE(x->dtype, T, {
@@ -229,6 +250,18 @@ int convT2_fprop(const b200_tensor* x, const void* kernel, const float* bias, in
 int convT2_dgrad(const b200_tensor* dy, const void* kernel, int cout, const b200_tensor* dx, cudaStream_t st) {
   B200_REQUIRE(dy->h == 2 * dx->h && dy->w == 2 * dx->w && dy->n == dx->n && dy->c == cout && dx->dtype == dy->dtype,
                B200_ERR_BAD_ARG, "convT2x2_dgrad: shape mismatch");
+  {
+    b200_tensor d00 = parity_view(dy, 0, 0);
+    if (dx->dtype == B200_BF16 && conv_tc_supported(&d00, cout, dx->c, dx, 1)) {
+      for (int ab = 0; ab < 4; ++ab) {
+        b200_tensor dv = parity_view(dy, ab / 2, ab % 2);
+        const __nv_bfloat16* k_ab = reinterpret_cast<const __nv_bfloat16*>(kernel) + (long long)ab * cout * dx->c;  // [K = cout][N = cin], MN-major
+        int rc = conv_tc_launch(&dv, k_ab, cout, dx->c, 0, 1, nullptr, dx, B200_ACT_NONE, ab > 0 ? 1 : 0, st, nullptr, 1);
+        if (rc) return rc;
+      }
+      return B200_OK;
+    }
+  }
   long long total = (long long)dx->n * dx->h * dx->w * dx->c;
   TView dv = view_of(dy), xv = view_of(dx);
   B200_DISPATCH_DTYPE(dx->dtype, T, {
@@ -240,9 +273,28 @@ int convT2_dgrad(const b200_tensor* dy, const void* kernel, int cout, const b200
 int convT2_wgrad(const b200_tensor* x, const b200_tensor* dy, float* dk, float* dbias, cudaStream_t st) {
   B200_REQUIRE(dy->h == 2 * x->h && dy->w == 2 * x->w && dy->n == x->n && x->dtype == dy->dtype, B200_ERR_BAD_ARG,
                "convT2x2_wgrad: shape mismatch");
-  TView xv = view_of(x), dv = view_of(dy);
-  B200_DISPATCH_DTYPE(x->dtype, T, { convT2_wgrad_kernel<T><<<4 * dy->c, NT, 0, st>>>(xv, dv, dk, dbias); });
-  return check_launch("convT2_wgrad_kernel");
+  const long long kcount = 4LL * dy->c * x->c;
+  cudaMemsetAsync(dk, 0, sizeof(float) * kcount, st);
+  b200_tensor d00 = parity_view(dy, 0, 0);
+  if (x->dtype == B200_BF16 && wgrad_tc_supported(&d00, x, 1)) {
+    // dK[a,b][o][c] = sum_pixels dy_ab[p][o] * x[p][c]: the 1x1 filter gradient with dy_ab in the activation role
+    for (int ab = 0; ab < 4; ++ab) {
+      b200_tensor dv = parity_view(dy, ab / 2, ab % 2);
+      int rc = wgrad_tc_launch(&dv, x, dk + (long long)ab * dy->c * x->c, nullptr, 0, st, 1, 1);
+      if (rc) return rc;
+    }
+  } else {
+    TView xv = view_of(x), dv = view_of(dy);
+    const long long npix = (long long)x->n * x->h * x->w;
+    int splits = (int)((npix + 2047) / 2048);
+    if (splits > 64) splits = 64;
+    dim3 grid(4 * dy->c, splits);
+    B200_DISPATCH_DTYPE(x->dtype, T, { convT2_wgrad_kernel<T><<<grid, NT, 0, st>>>(xv, dv, dk); });
+    int rc = check_launch("convT2_wgrad_kernel");
+    if (rc) return rc;
+  }
+  if (dbias) return bias_act_bwd(dy, dy, B200_ACT_NONE, dy, dbias, st);   // column sums of dy, added to dbias
+  return B200_OK;
 }
 
 }  // namespace b200

@@ -558,6 +558,27 @@ def test_conv_transpose(dtype):
     assert relerr(y, yr) < tol and relerr(dx, xr.grad) < tol and relerr(dk, kr.grad) < tol and relerr(dbias, br.grad) < tol
 
 
+@pytest.mark.parametrize("shape", [(2, 8, 8, 128, 64), (1, 4, 6, 64, 128), (3, 1, 1, 128, 128), (2, 16, 16, 256, 128), (5, 2, 2, 64, 64)])
+def test_conv_transpose_tensor_core(shape):
+    """Conv2DTranspose(k2, s2) as four 1x1 tcgen05 convolutions over the parity views y[:, a::2, b::2, :] (fprop writes
+    them, dgrad / wgrad read them), on a channel slice of a wider output buffer (concat in place)."""
+    ops, K = _ops(), _K()
+    n, h, w, ci, co = shape
+    dt = torch.bfloat16
+    x = rand((n, h, w, ci), 95, dt); k = rand((2, 2, co, ci), 96, dt, 0.1); b = rand((co,), 97, scale=0.2)
+    wide = torch.zeros((n, 2 * h, 2 * w, co + 64), dtype=dt, device="cuda")
+    y = wide[..., :co]
+    ops.convT2x2_fprop(x, k, b, y)
+    dy = rand((n, 2 * h, 2 * w, co), 98, dt)
+    dx = torch.full_like(x, 7.0); dk = torch.full((2, 2, co, ci), 7.0, device="cuda"); dbias = torch.zeros(co, device="cuda")
+    ops.convT2x2_dgrad(dy, k, dx); ops.convT2x2_wgrad(x, dy, dk, dbias)
+    xr, kr, br = f32(x).requires_grad_(), f32(k).requires_grad_(), f32(b).requires_grad_()
+    yr = K.conv2d_transpose_2x2(xr, kr, br)
+    (yr * f32(dy)).sum().backward()
+    assert relerr(y, yr) < 1e-2 and float(wide[..., co:].abs().max()) == 0.0
+    assert relerr(dx, xr.grad) < 1e-2 and relerr(dk, kr.grad) < 2e-3 and relerr(dbias, br.grad) < 1e-3
+
+
 # ----------------------------------------------------------------------------- head / losses / optimiser
 @pytest.mark.parametrize("dtype", DTYPES)
 def test_clipadd(dtype):
