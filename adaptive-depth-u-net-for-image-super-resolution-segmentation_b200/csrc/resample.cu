@@ -114,6 +114,27 @@ __device__ __forceinline__ void rs_hrow(const __nv_bfloat16* __restrict__ row, l
   }
 }
 
+// same with the (at most NW) horizontal weights already in registers: every load of the row is issued back to back
+template <int NW>
+__device__ __forceinline__ void rs_hrow_reg(const __nv_bfloat16* __restrict__ row, long long x_sw, int xw, int w0,
+                                            const float (&wv)[NW], float2 (&r)[4]) {
+  uint4 raw[NW];
+#pragma unroll
+  for (int k = 0; k < NW; ++k) {
+    if (wv[k] != 0.f) raw[k] = *reinterpret_cast<const uint4*>(row + (long long)min(w0 + k, xw - 1) * x_sw);
+    else raw[k] = make_uint4(0u, 0u, 0u, 0u);
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) r[i] = make_float2(0.f, 0.f);
+#pragma unroll
+  for (int k = 0; k < NW; ++k) {
+    const float2 w2 = make_float2(wv[k], wv[k]);
+    const uint32_t* q = reinterpret_cast<const uint32_t*>(&raw[k]);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) r[i] = __ffma2_rn(rs_unpack(q[i]), w2, r[i]);
+  }
+}
+
 __device__ __forceinline__ void rs_store(__nv_bfloat16* dst, const float2 (&v)[4], int accumulate) {
   float2 o[4] = {v[0], v[1], v[2], v[3]};
   if (accumulate) {
@@ -143,6 +164,15 @@ resample_up_kernel(const RsArgs a) {
   const float* wrow = a.ww + ow * a.wt;
   float2 cache[HT][4];
   int cur = -(1 << 30);
+  const bool regw = a.wt <= 4;
+  float wv[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) wv[k] = (regw && k < a.wt) ? wrow[k] : 0.f;
+  auto hrow = [&](int ih, float2 (&dst)[4]) {
+    const __nv_bfloat16* row = xp + (long long)min(ih, a.xh - 1) * a.x_sh;
+    if (regw) rs_hrow_reg<4>(row, a.x_sw, a.xw, w0, wv, dst);
+    else rs_hrow(row, a.x_sw, a.xw, w0, wrow, a.wt, dst);
+  };
   for (int oh = oh0; oh < oh1; ++oh) {
     const int h0 = a.hs[oh];                 // block-uniform
     if (h0 != cur) {
@@ -151,11 +181,10 @@ resample_up_kernel(const RsArgs a) {
         for (int t = 0; t + 1 < HT; ++t)
 #pragma unroll
           for (int i = 0; i < 4; ++i) cache[t][i] = cache[t + 1][i];
-        rs_hrow(xp + (long long)min(h0 + HT - 1, a.xh - 1) * a.x_sh, a.x_sw, a.xw, w0, wrow, a.wt, cache[HT - 1]);
+        hrow(h0 + HT - 1, cache[HT - 1]);
       } else {
 #pragma unroll
-        for (int t = 0; t < HT; ++t)
-          rs_hrow(xp + (long long)min(h0 + t, a.xh - 1) * a.x_sh, a.x_sw, a.xw, w0, wrow, a.wt, cache[t]);
+        for (int t = 0; t < HT; ++t) hrow(h0 + t, cache[t]);
       }
       cur = h0;
     }
@@ -173,7 +202,7 @@ resample_up_kernel(const RsArgs a) {
   }
 }
 
-template <int NSLOT>
+template <int NSLOT, int NW>
 __global__ void __launch_bounds__(NT)
 resample_down_kernel(const RsArgs a) {
   const int item = blockIdx.x * NT + threadIdx.x;
@@ -195,10 +224,16 @@ resample_down_kernel(const RsArgs a) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) acc[s][i] = make_float2(0.f, 0.f);
   }
+  float wv[NW > 0 ? NW : 1];
+  if (NW > 0) {
+#pragma unroll
+    for (int k = 0; k < NW; ++k) wv[k] = k < a.wt ? wrow[k] : 0.f;
+  }
   const int ih_end = a.hs[oh1 - 1] + a.ht;
   for (int ih = a.hs[oh0]; ih < ih_end; ++ih) {        // block-uniform trip count and slot state
     float2 r[4];
-    rs_hrow(xp + (long long)min(ih, a.xh - 1) * a.x_sh, a.x_sw, a.xw, w0, wrow, a.wt, r);
+    if (NW > 0) rs_hrow_reg<(NW > 0 ? NW : 1)>(xp + (long long)min(ih, a.xh - 1) * a.x_sh, a.x_sw, a.xw, w0, wv, r);
+    else rs_hrow(xp + (long long)min(ih, a.xh - 1) * a.x_sh, a.x_sw, a.xw, w0, wrow, a.wt, r);
 #pragma unroll
     for (int s = 0; s < NSLOT; ++s) {
       const int k = ih - lo_s[s];
@@ -453,8 +488,10 @@ int resample2d(const b200_tensor* x, const b200_tensor* y, const int32_t* hs, co
     const int bx = (int)(((long long)y->w * a.chunks + NT - 1) / NT);
     // rows per thread: long enough to amortise the first rows of a segment, short enough to fill the GPU
     const long long base_blocks = (long long)bx * y->n;
-    int nseg = (int)((6LL * sm_count() + base_blocks - 1) / base_blocks);
-    const int min_rows = mode == 1 ? 8 : 4;
+    static const int blocks_per_sm = getenv("B200_RS_BLOCKS") ? atoi(getenv("B200_RS_BLOCKS")) : 6;
+    static const int min_rows_down = getenv("B200_RS_MINROWS") ? atoi(getenv("B200_RS_MINROWS")) : 4;
+    int nseg = (int)(((long long)blocks_per_sm * sm_count() + base_blocks - 1) / base_blocks);
+    const int min_rows = mode == 1 ? 8 : min_rows_down;
     if (nseg > (y->h + min_rows - 1) / min_rows) nseg = (y->h + min_rows - 1) / min_rows;
     if (nseg < 1) nseg = 1;
     a.seg = (y->h + nseg - 1) / nseg;
@@ -465,9 +502,12 @@ int resample2d(const b200_tensor* x, const b200_tensor* y, const int32_t* hs, co
       else if (ht == 2) resample_up_kernel<2><<<grid, NT, 0, st>>>(a);
       else resample_up_kernel<3><<<grid, NT, 0, st>>>(a);
     } else if (mode == 2) {
-      resample_down_kernel<4><<<grid, NT, 0, st>>>(a);
+      if (wt <= 4) resample_down_kernel<4, 4><<<grid, NT, 0, st>>>(a);
+      else if (wt <= 8) resample_down_kernel<4, 8><<<grid, NT, 0, st>>>(a);
+      else resample_down_kernel<4, 0><<<grid, NT, 0, st>>>(a);
     } else {
-      resample_down_kernel<6><<<grid, NT, 0, st>>>(a);
+      if (wt <= 4) resample_down_kernel<6, 4><<<grid, NT, 0, st>>>(a);
+      else resample_down_kernel<6, 0><<<grid, NT, 0, st>>>(a);
     }
     return check_launch("resample_march_kernel");
   }
