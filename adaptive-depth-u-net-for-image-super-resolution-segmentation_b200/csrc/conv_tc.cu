@@ -553,7 +553,7 @@ umma_probe_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
   const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t a_smem = smem0, b_smem = smem0 + 65536;
   if (threadIdx.x == 0) { mbar_init(smem_u32(&bar_load), 1); mbar_init(smem_u32(&bar_mma), 1); fence_barrier_init(); }
-  if (warp == 0) { tmem_alloc(smem_u32(&tmem_base_smem), 64); tmem_relinquish(); }
+  if (warp == 0) { tmem_alloc(smem_u32(&tmem_base_smem), 128); tmem_relinquish(); }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -565,7 +565,16 @@ umma_probe_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
     tma_load_2d(b_smem, &tm_b, smem_u32(&bar_load), 0, 0);
     mbar_wait(smem_u32(&bar_load), 0);
     tc_fence_after();
-    if (!mn_major) {
+    if (mn_major == 2) {
+      // weight-stationary pairs: D0 = A[rows 0..127] * B, D1 = A[rows 128..255] * B; B filled once per K step
+      const uint32_t idesc = idesc_bf16(128, 64, 0, 0);
+      for (int ks = 0; ks < 4; ++ks) {
+        const uint64_t bd = smem_desc_sw128(b_smem + ks * 32, 0, 1024);
+        umma_ws_bf16<false>(tmem_base, smem_desc_sw128(a_smem + start_bytes + ks * 32, lbo_bytes, sbo_bytes), bd, idesc, ks > 0);
+        umma_ws_bf16<true>(tmem_base + 64, smem_desc_sw128(a_smem + 128 * 128 + start_bytes + ks * 32, lbo_bytes, sbo_bytes), bd,
+                           idesc, ks > 0);
+      }
+    } else if (!mn_major) {
       const uint32_t idesc = idesc_bf16(128, 64, 0, 0);
       for (int ks = 0; ks < 4; ++ks)
         umma_bf16(tmem_base, smem_desc_sw128(a_smem + start_bytes + ks * 32, lbo_bytes, sbo_bytes),
@@ -584,16 +593,16 @@ umma_probe_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
   mbar_wait(smem_u32(&bar_mma), 0);
   tc_fence_after();
   const int row = warp * 32 + lane;
-  for (int c0 = 0; c0 < 64; c0 += 32) {
+  for (int c0 = 0; c0 < (mn_major == 2 ? 128 : 64); c0 += 32) {
     uint32_t v[32];
     tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + c0, v);
     tmem_ld_wait();
 #pragma unroll
-    for (int i = 0; i < 32; ++i) out[row * 64 + c0 + i] = __uint_as_float(v[i]);
+    for (int i = 0; i < 32; ++i) out[((c0 / 64) * 128 + row) * 64 + (c0 % 64) + i] = __uint_as_float(v[i]);
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem_base, 64); }
+  if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem_base, 128); }
 }
 
 // ---------------------------------------------------------------------------
@@ -621,6 +630,25 @@ umma_rate_kernel(int n, int iters, int a_stride_bytes, long long* __restrict__ c
   if (threadIdx.x == 0) {
     const uint32_t idesc = idesc_bf16(128, n, 0, 0);
     const long long t0 = clock64();
+    if (a_stride_bytes == 2048) {     // weight-stationary pairs: two A tiles per B tile (fill + lastuse)
+      for (int it = 0; it < iters; it += 2) {
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+          const uint64_t bd = smem_desc_sw128(b_smem + ks * 32, 0, 1024);
+          umma_ws_bf16<false>(tmem_base, smem_desc_sw128(a_smem + ks * 32, 0, 1024), bd, idesc, 1);
+          umma_ws_bf16<true>(tmem_base + (uint32_t)n, smem_desc_sw128(a_smem + 16384 + ks * 32, 0, 1024), bd, idesc, 1);
+        }
+      }
+    } else if (a_stride_bytes == 2049) {     // the same two-tile loop with ordinary MMAs (B read from shared memory twice)
+      for (int it = 0; it < iters; it += 2) {
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+          const uint64_t bd = smem_desc_sw128(b_smem + ks * 32, 0, 1024);
+          umma_bf16(tmem_base, smem_desc_sw128(a_smem + ks * 32, 0, 1024), bd, idesc, 1);
+          umma_bf16(tmem_base + (uint32_t)n, smem_desc_sw128(a_smem + 16384 + ks * 32, 0, 1024), bd, idesc, 1);
+        }
+      }
+    } else
     for (int it = 0; it < iters; ++it) {
       // a_stride 1280 = the convolution's access pattern: per tap a shifted window start and its own B tile
       const int tap = a_stride_bytes == 1280 ? it % 9 : 0;
