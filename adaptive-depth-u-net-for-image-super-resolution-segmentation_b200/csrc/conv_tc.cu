@@ -65,6 +65,22 @@ int make_act_tmap(CUtensorMap* m, const b200_tensor* t, int box_w, int box_h, in
   return B200_OK;
 }
 
+// NHWC bf16 activation view -> 4D map with the image index BEFORE the row index: {C, W, N, H}, box {64, bw, bn, bh}.
+// A box then lands in shared memory as [row][image][column][channel]: the rows of `bn` small images interleaved,
+// which keeps the 8-pixel row groups of a two-image tile equally spaced (see "pair" tiles in conv3x3_tc_kernel).
+int make_act_tmap_nh(CUtensorMap* m, const b200_tensor* t, int box_w, int box_n, int box_h) {
+  EncodeTiledFn fn = encode_fn();
+  B200_REQUIRE(fn, B200_ERR_LAUNCH, "cuTensorMapEncodeTiled unavailable");
+  cuuint64_t dims[4] = {(cuuint64_t)t->c, (cuuint64_t)t->w, (cuuint64_t)t->n, (cuuint64_t)t->h};
+  cuuint64_t strides[3] = {(cuuint64_t)t->stride_w * 2, (cuuint64_t)t->stride_n * 2, (cuuint64_t)t->stride_h * 2};
+  cuuint32_t box[4] = {64, (cuuint32_t)box_w, (cuuint32_t)box_n, (cuuint32_t)box_h};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, t->data, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  B200_REQUIRE(r == CUDA_SUCCESS, B200_ERR_LAUNCH, "cuTensorMapEncodeTiled(activation, N before H) failed: %d", (int)r);
+  return B200_OK;
+}
+
 // row-major bf16 matrix [rows][cols] -> 2D map, box {64 cols, box_rows}, 128B swizzle
 int make_mat_tmap(CUtensorMap* m, const void* base, long long rows, long long cols, int box_rows) {
   EncodeTiledFn fn = encode_fn();
@@ -87,6 +103,7 @@ constexpr int WIN_W = TILE_W + 2, WIN_H = TILE_H + 2;
 constexpr int WIN_BYTES = WIN_W * WIN_H * 128;    // 23040
 constexpr int WIN_STAGE = 23552;                  // padded to a multiple of 1024
 constexpr int WIN_PITCH = WIN_W * 128;            // 1280: byte distance between tile rows = SBO
+constexpr int PAIR_WIN_STAGE = WIN_W * 2 * (8 + 2) * 128;   // 25600: two interleaved 8-row images + halos
 constexpr int MAX_WSLOTS = 18;
 constexpr int NTHREADS = 192;
 constexpr int SMEM_LIMIT = 232448;                // 227 KB
@@ -103,6 +120,9 @@ struct ConvTcParams {
   int ntaps, tap0;  // 9, 0 for a 3x3 filter; 1, 4 for a 1x1 filter (centre tap only; its weights are matrix block 0)
   // small images (H <= 7) are stacked: one tile holds `nb` images, each `srows` = H+2 window rows
   int nb, srows, win_bytes;
+  // pair tiles (8-row images): two images per tile with their rows INTERLEAVED in the window ([row][image][10 px]), so
+  // that row group g = row*2 + image sits g*1280 bytes into the window for every tap; tap (kh,kw) starts (kh*20+kw) pixels in
+  int pair, win_stage;
   const float* bias;
   __nv_bfloat16* y;
   long long ysn, ysh, ysw;
@@ -256,6 +276,7 @@ __device__ __forceinline__ void ln_load(uint32_t taddr, const float* s_bias, uin
   rstd = rsqrtf(q * (1.f / BN_T) + eps);
 }
 
+template <bool PAIR>
 __global__ void __launch_bounds__(NTHREADS, 1)
 conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_b,
                   const __grid_constant__ CUtensorMap tm_y, const __grid_constant__ CUtensorMap tm_z,
@@ -269,7 +290,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
   const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t win0 = smem0;
-  const uint32_t wt0 = smem0 + (uint32_t)p.nsw * WIN_STAGE;
+  const uint32_t wt0 = smem0 + (uint32_t)p.nsw * (uint32_t)(PAIR ? PAIR_WIN_STAGE : WIN_STAGE);
   const uint32_t wt_bytes = (uint32_t)p.BN * 128u;
   const uint32_t tmem_cols = 2u * (uint32_t)p.BN;
   const uint32_t stg0 = wt0 + (uint32_t)p.nsb * wt_bytes;
@@ -314,8 +335,11 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
         for (int kb = 0; kb < p.KB; ++kb) {
           mbar_wait(smem_u32(&bar_empty_w[sw]), pw ^ 1);
           mbar_arrive_expect_tx(smem_u32(&bar_full_w[sw]), (uint32_t)p.win_bytes);
-          tma_load_4d(win0 + sw * WIN_STAGE, &tm_x, smem_u32(&bar_full_w[sw]), kb * 64, tw * TILE_W - 1,
-                      th * TILE_H - 1, n);
+          if (PAIR)   // map dims are (C, W, N, H)
+            tma_load_4d(win0 + sw * PAIR_WIN_STAGE, &tm_x, smem_u32(&bar_full_w[sw]), kb * 64, tw * TILE_W - 1, n, -1);
+          else
+            tma_load_4d(win0 + sw * WIN_STAGE, &tm_x, smem_u32(&bar_full_w[sw]), kb * 64, tw * TILE_W - 1,
+                        th * TILE_H - 1, n);
           if (++sw == p.nsw) { sw = 0; pw ^= 1; }
           if (!p.resident) {
             for (int tap = 0; tap < 9; ++tap) {
@@ -359,8 +383,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
         for (int kb = 0; kb < p.KB; ++kb) {
           mbar_wait(smem_u32(&bar_full_w[sw]), pw);
           tc_fence_after();
-          const uint32_t a_lo0 = (win0 + sw * WIN_STAGE) >> 4;
-          if (p.resident && all_live) {
+          const uint32_t a_lo0 = (win0 + sw * (PAIR ? PAIR_WIN_STAGE : WIN_STAGE)) >> 4;
+          if (!PAIR && p.resident && all_live) {
             // hot path of the full-resolution layers: 36 MMAs, descriptor words by 32-bit adds only
             const uint32_t b_lo0 = ((wt0 >> 4) | b_lbo) + (uint32_t)(kb * 9) * wt_step;
             if (elect_one()) {
@@ -387,7 +411,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
                 tc_fence_after();
                 b_lo = ((wt0 >> 4) | b_lbo) + (uint32_t)sb * wt_step;
               }
-              const uint32_t a_lo = a_lo0 + (uint32_t)((tap / 3) * WIN_W + (tap % 3)) * 8u;
+              const uint32_t a_lo = a_lo0 + (uint32_t)((tap / 3) * (PAIR ? 2 * WIN_W : WIN_W) + (tap % 3)) * 8u;
               if (elect_one()) {
 #pragma unroll
                 for (int ks = 0; ks < 4; ++ks)
@@ -413,7 +437,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
     const int q = warp % 4;                 // TMEM lane quarter this warp may read
     const int r = q * 32 + lane;            // GEMM row = pixel of the tile
     const int ty = r / TILE_W, tx = r % TILE_W;
-    const int sb_img = ty / p.srows, sb_row = ty % p.srows;   // stacked small images (srows huge otherwise)
+    // stacked small images (srows huge otherwise) or pair tiles (rows of two images interleaved)
+    const int sb_img = PAIR ? (ty & 1) : ty / p.srows, sb_row = PAIR ? (ty >> 1) : ty % p.srows;
     StoreRing ring;
     ring.stg0 = stg0; ring.nslots = p.nslots; ring.slot = 0; ring.issuer = threadIdx.x == 64;
     ring.d_have = 0; ring.d_which = 0; ring.d_c = ring.d_w = ring.d_h = ring.d_n = 0; ring.d_slot = 0;
@@ -436,7 +461,9 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
         __syncwarp();
         if (lane == 0) mbar_arrive(tmem_empty);
       };
-      const int cw = tw * TILE_W, ch = th * TILE_H;   // box origin (stacked tiles: th == 0, box = {64, 8, srows, nb})
+      // box origin (stacked tiles: th == 0, box = {64, 8, srows, nb}); pair tiles: the store map's dims are (C, W, N, H),
+      // so the image index goes where the row coordinate normally is and the row origin (0) last
+      const int cw = tw * TILE_W, ch = PAIR ? n : th * TILE_H, cn = PAIR ? 0 : n;
       if (p.debug == 1) {
         release_tmem();
       } else if (p.ln) {
@@ -460,7 +487,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
               for (int c = 0; c < 8; ++c)
                 st_shared_v4(slot + (((uint32_t)c ^ sw) << 4), zp[hf * 32 + c * 4], zp[hf * 32 + c * 4 + 1],
                              zp[hf * 32 + c * 4 + 2], zp[hf * 32 + c * 4 + 3]);
-              ring.end(slot - rbase, 1, hf * 64, cw, ch, n);
+              ring.end(slot - rbase, 1, hf * 64, cw, ch, cn);
             }
             const uint32_t slot = ring.begin() + rbase;
 #pragma unroll
@@ -477,7 +504,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
               }
               st_shared_v4(slot + (((uint32_t)c ^ sw) << 4), o[0], o[1], o[2], o[3]);
             }
-            ring.end(slot - rbase, 0, hf * 64, cw, ch, n);
+            ring.end(slot - rbase, 0, hf * 64, cw, ch, cn);
           }
         };
         if (p.BN == 64) run(std::integral_constant<int, 64>{});
@@ -497,7 +524,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
             const float t = __uint_as_float(i < 32 ? v0[i] : v1[i - 32]) + bh[i];
             return relu ? fmaxf(t, 0.f) : t;
           });
-          ring.end(slot, 0, j * p.BN + hf * 64, cw, ch, n);
+          ring.end(slot, 0, j * p.BN + hf * 64, cw, ch, cn);
         }
       } else {
         // per-thread read-modify-write stores (gradient accumulation into an existing tensor)
@@ -752,6 +779,15 @@ int conv_tc_launch(const b200_tensor* x_in, const void* wmat, int cin, int cout,
     box_h = p.srows; box_n = p.nb;
   }
   p.win_bytes = WIN_W * box_h * box_n * 128;
+  p.pair = 0; p.win_stage = WIN_STAGE;
+  static const int allow_pair = getenv("B200_CONV_PAIR") ? atoi(getenv("B200_CONV_PAIR")) : 1;
+  if (allow_pair && p.H == 8 && p.N > 1 && p.nb == 1) {
+    // 8-row images fill half a 16x8 tile: put two images in one tile with interleaved rows
+    p.pair = 1; p.nb = 2; p.srows = 1 << 20;
+    p.win_bytes = WIN_W * 2 * (8 + 2) * 128;          // 25600
+    p.win_stage = PAIR_WIN_STAGE;
+    p.tiles_h = 1;
+  }
   const int groups = (p.N + p.nb - 1) / p.nb;
   p.total_items = groups * p.tiles_h * p.tiles_w * p.n_tiles;
   p.tap_rev = tap_rev;
@@ -775,13 +811,13 @@ int conv_tc_launch(const b200_tensor* x_in, const void* wmat, int cin, int cout,
   auto plan_smem = [&](int nslots, int min_windows) -> bool {
     const int left = budget - nslots * SLOT_BYTES;
     p.nslots = nslots;
-    p.resident = (p.n_tiles == 1 && p.ntaps * p.KB <= MAX_WSLOTS && left - all_w >= min_windows * WIN_STAGE) ? 1 : 0;
+    p.resident = (p.n_tiles == 1 && p.ntaps * p.KB <= MAX_WSLOTS && left - all_w >= min_windows * p.win_stage) ? 1 : 0;
     if (p.resident) {
       p.nsb = p.ntaps * p.KB;
-      p.nsw = (left - all_w) / WIN_STAGE;
+      p.nsw = (left - all_w) / p.win_stage;
     } else {
       p.nsb = 4;
-      p.nsw = (left - p.nsb * wt_bytes) / WIN_STAGE;
+      p.nsw = (left - p.nsb * wt_bytes) / p.win_stage;
     }
     if (p.nsw > 8) p.nsw = 8;
     return p.nsw >= min_windows;
@@ -816,26 +852,28 @@ int conv_tc_launch(const b200_tensor* x_in, const void* wmat, int cin, int cout,
   }
 
   CUtensorMap tm_x, tm_b, tm_y, tm_z;
-  int rc = make_act_tmap(&tm_x, x, WIN_W, box_h, box_n);
+  int rc = p.pair ? make_act_tmap_nh(&tm_x, x, WIN_W, 2, 8 + 2) : make_act_tmap(&tm_x, x, WIN_W, box_h, box_n);
   if (rc) return rc;
   rc = b_mn ? make_mat_tmap(&tm_b, wmat, (long long)p.ntaps * cin, cout, 64)
             : make_mat_tmap(&tm_b, wmat, (long long)p.ntaps * cout, cin, p.BN);
   if (rc) return rc;
   // output boxes: {64 ch, 8, 16, 1}, or {64 ch, 8, H+2, nb} for stacked small images (rows past H are clipped)
   const int obox_h = p.nb > 1 || box_h != WIN_H ? box_h : TILE_H;
-  rc = make_act_tmap(&tm_y, y, TILE_W, obox_h, box_n);
+  rc = p.pair ? make_act_tmap_nh(&tm_y, y, TILE_W, 2, 8) : make_act_tmap(&tm_y, y, TILE_W, obox_h, box_n);
   if (rc) return rc;
-  rc = make_act_tmap(&tm_z, z ? z : y, TILE_W, obox_h, box_n);
+  rc = p.pair ? make_act_tmap_nh(&tm_z, z ? z : y, TILE_W, 2, 8) : make_act_tmap(&tm_z, z ? z : y, TILE_W, obox_h, box_n);
   if (rc) return rc;
 
-  const size_t smem = 1024 + (size_t)p.nsw * WIN_STAGE + (size_t)p.nsb * wt_bytes + (size_t)p.nslots * SLOT_BYTES + bias_bytes;
+  const size_t smem = 1024 + (size_t)p.nsw * p.win_stage + (size_t)p.nsb * wt_bytes + (size_t)p.nslots * SLOT_BYTES + bias_bytes;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaFuncSetAttribute(conv3x3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT - 1024);
+    cudaFuncSetAttribute(conv3x3_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT - 1024);
+    cudaFuncSetAttribute(conv3x3_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT - 1024);
     attr_set = true;
   }
   int grid = p.total_items < sm_count() ? p.total_items : sm_count();
-  conv3x3_tc_kernel<<<grid, NTHREADS, smem, st>>>(tm_x, tm_b, tm_y, tm_z, p);
+  if (p.pair) conv3x3_tc_kernel<true><<<grid, NTHREADS, smem, st>>>(tm_x, tm_b, tm_y, tm_z, p);
+  else conv3x3_tc_kernel<false><<<grid, NTHREADS, smem, st>>>(tm_x, tm_b, tm_y, tm_z, p);
   return check_launch("conv3x3_tc_kernel");
 }
 

@@ -125,6 +125,8 @@ TC_SHAPES = [
     # small images: stacked several per tile (H <= 7) / flattened (1x1)
     (16, 1, 1, 128, 128), (13, 1, 1, 64, 64), (9, 2, 2, 64, 64), (7, 3, 5, 64, 128), (5, 4, 4, 128, 64),
     (3, 5, 11, 64, 64), (5, 6, 6, 64, 64), (3, 7, 7, 64, 64), (11, 1, 6, 64, 64), (1, 2, 2, 64, 64),
+    # 8-row images: two per tile with interleaved rows (pair tiles), odd batch, several tiles wide, streamed weights
+    (3, 8, 8, 128, 128), (4, 8, 13, 64, 64), (5, 8, 8, 256, 256), (2, 8, 20, 128, 64),
 ]
 
 
@@ -153,7 +155,7 @@ def test_conv_tc_fprop_dgrad(shape):
 
 @pytest.mark.parametrize("shape", [(2, 32, 32, 64, 64), (1, 20, 13, 128, 64), (2, 16, 24, 64, 128), (3, 40, 24, 128, 128),
                                    (9, 2, 2, 64, 64), (16, 1, 1, 128, 128), (5, 6, 6, 64, 128),
-                                   (2, 8, 8, 64, 256), (2, 9, 9, 3, 64)])
+                                   (2, 8, 8, 64, 256), (2, 9, 9, 3, 64), (5, 8, 8, 64, 64), (3, 8, 11, 128, 128)])
 @pytest.mark.parametrize("relu", [True, False])
 def test_conv_ln_fused(shape, relu):
     """Conv2D -> LayerNormalization -> ReLU as one call: fused tcgen05 epilogue (Cout 64/128) and the
