@@ -276,7 +276,9 @@ __device__ __forceinline__ void ln_load(uint32_t taddr, const float* s_bias, uin
   rstd = rsqrtf(q * (1.f / BN_T) + eps);
 }
 
-template <bool PAIR>
+// EPI selects which epilogues an instantiation contains (the LayerNorm epilogue's code generation is sensitive to
+// what else lives in the kernel): 0 = all, 1 = LayerNorm over 64 channels, 2 = LayerNorm over 128, 3 = no LayerNorm
+template <bool PAIR, int EPI>
 __global__ void __launch_bounds__(NTHREADS, 1)
 conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_b,
                   const __grid_constant__ CUtensorMap tm_y, const __grid_constant__ CUtensorMap tm_z,
@@ -466,7 +468,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
       const int cw = tw * TILE_W, ch = PAIR ? n : th * TILE_H, cn = PAIR ? 0 : n;
       if (p.debug == 1) {
         release_tmem();
-      } else if (p.ln) {
+      } else if (EPI != 3 && p.ln) {
         const long long pix = ((long long)img * p.H + oh) * p.W + ow;
         const float* gam = s_bias + p.Cout;
         const float* bet = s_bias + 2 * p.Cout;
@@ -507,9 +509,11 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
             ring.end(slot - rbase, 0, hf * 64, cw, ch, cn);
           }
         };
-        if (p.BN == 64) run(std::integral_constant<int, 64>{});
+        if (EPI == 1) run(std::integral_constant<int, 64>{});
+        else if (EPI == 2) run(std::integral_constant<int, 128>{});
+        else if (p.BN == 64) run(std::integral_constant<int, 64>{});
         else run(std::integral_constant<int, 128>{});
-      } else if (p.tma_store) {
+      } else if ((EPI == 0 || EPI == 3) && p.tma_store) {
         const int halves = p.BN / 64;
         for (int hf = 0; hf < halves; ++hf) {
           uint32_t v0[32], v1[32];
@@ -526,7 +530,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
           });
           ring.end(slot, 0, j * p.BN + hf * 64, cw, ch, cn);
         }
-      } else {
+      } else if (EPI == 0 || EPI == 3) {
         // per-thread read-modify-write stores (gradient accumulation into an existing tensor)
         __nv_bfloat16* dst = p.y + (long long)img * p.ysn + (long long)oh * p.ysh + (long long)ow * p.ysw + j * p.BN;
         for (int c0 = 0; c0 < p.BN; c0 += 32) {
@@ -867,13 +871,17 @@ int conv_tc_launch(const b200_tensor* x_in, const void* wmat, int cin, int cout,
   const size_t smem = 1024 + (size_t)p.nsw * p.win_stage + (size_t)p.nsb * wt_bytes + (size_t)p.nslots * SLOT_BYTES + bias_bytes;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaFuncSetAttribute(conv3x3_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT - 1024);
-    cudaFuncSetAttribute(conv3x3_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT - 1024);
+    cudaFuncSetAttribute(conv3x3_tc_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT - 1024);
+    cudaFuncSetAttribute(conv3x3_tc_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT - 1024);
+    cudaFuncSetAttribute(conv3x3_tc_kernel<false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT - 1024);
+    cudaFuncSetAttribute(conv3x3_tc_kernel<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT - 1024);
     attr_set = true;
   }
   int grid = p.total_items < sm_count() ? p.total_items : sm_count();
-  if (p.pair) conv3x3_tc_kernel<true><<<grid, NTHREADS, smem, st>>>(tm_x, tm_b, tm_y, tm_z, p);
-  else conv3x3_tc_kernel<false><<<grid, NTHREADS, smem, st>>>(tm_x, tm_b, tm_y, tm_z, p);
+  if (p.pair) conv3x3_tc_kernel<true, 0><<<grid, NTHREADS, smem, st>>>(tm_x, tm_b, tm_y, tm_z, p);
+  else if (p.ln && p.BN == 64) conv3x3_tc_kernel<false, 1><<<grid, NTHREADS, smem, st>>>(tm_x, tm_b, tm_y, tm_z, p);
+  else if (p.ln) conv3x3_tc_kernel<false, 2><<<grid, NTHREADS, smem, st>>>(tm_x, tm_b, tm_y, tm_z, p);
+  else conv3x3_tc_kernel<false, 3><<<grid, NTHREADS, smem, st>>>(tm_x, tm_b, tm_y, tm_z, p);
   return check_launch("conv3x3_tc_kernel");
 }
 
