@@ -106,6 +106,7 @@ constexpr int WIN_PITCH = WIN_W * 128;            // 1280: byte distance between
 constexpr int PAIR_WIN_STAGE = WIN_W * 2 * (8 + 2) * 128;   // 25600: two interleaved 8-row images + halos
 constexpr int MAX_WSLOTS = 18;
 constexpr int NTHREADS = 192;
+constexpr int NTHREADS2 = 320;   // LayerNorm-64 instantiation: a second group of four epilogue warps (two warps per scheduler)
 constexpr int SMEM_LIMIT = 232448;                // 227 KB
 
 struct ConvTcParams {
@@ -115,6 +116,9 @@ struct ConvTcParams {
   // output path: 1 = tiles are staged in shared memory (128-byte swizzle) and written by TMA stores
   // (ring of `nslots` 16 KB slots, one slot = 128 pixels x 64 channels); 0 = per-thread stores (accumulate)
   int tma_store, nslots;
+  // epilogue groups (EPI == 1 only): 2 = two 4-warp groups alternate tiles, group g owns accumulator stage g and half of
+  // the slots, so the LayerNorm epilogue's dependent-instruction latency overlaps between two warps per scheduler
+  int egroups;
   int b_mn;   // 1: B operand is MN-major (fprop reads the Keras HWIO kernel [tap][cin][cout] as is); 0: K-major (dgrad)
   int Kc;     // K total (input channels of this convolution)
   int ntaps, tap0;  // 9, 0 for a 3x3 filter; 1, 4 for a 1x1 filter (centre tap only; its weights are matrix block 0)
@@ -194,6 +198,7 @@ struct StoreRing {
   uint32_t d_slot;
   const CUtensorMap* tm_y;
   const CUtensorMap* tm_z;
+  uint32_t bar_id;     // named barrier of this epilogue group
 
   __device__ __forceinline__ void flush() {
     if (issuer && d_have) {
@@ -213,7 +218,7 @@ struct StoreRing {
       else bulk_wait_read<2>();
     }
     __syncwarp();
-    named_bar_sync(1, EPI_THREADS);
+    named_bar_sync(bar_id, EPI_THREADS);
     flush();
     return stg0 + (uint32_t)slot * SLOT_BYTES;
   }
@@ -224,7 +229,7 @@ struct StoreRing {
   }
   __device__ __forceinline__ void drain() {
     __syncwarp();
-    named_bar_sync(1, EPI_THREADS);
+    named_bar_sync(bar_id, EPI_THREADS);
     flush();
     if (issuer) bulk_wait_all();
   }
@@ -279,7 +284,7 @@ __device__ __forceinline__ void ln_load(uint32_t taddr, const float* s_bias, uin
 // EPI selects which epilogues an instantiation contains (the LayerNorm epilogue's code generation is sensitive to
 // what else lives in the kernel): 0 = all, 1 = LayerNorm over 64 channels, 2 = LayerNorm over 128, 3 = no LayerNorm
 template <bool PAIR, int EPI>
-__global__ void __launch_bounds__(NTHREADS, 1)
+__global__ void __launch_bounds__(EPI == 1 ? NTHREADS2 : NTHREADS, 1)
 conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_b,
                   const __grid_constant__ CUtensorMap tm_y, const __grid_constant__ CUtensorMap tm_z,
                   const ConvTcParams p) {
@@ -304,7 +309,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
     for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&bar_tmem_full[i]), 1); mbar_init(smem_u32(&bar_tmem_empty[i]), 4); }
     fence_barrier_init();
   }
-  for (int i = threadIdx.x; i < p.Cout; i += NTHREADS) {
+  for (int i = threadIdx.x; i < p.Cout; i += blockDim.x) {
     s_bias[i] = p.bias ? p.bias[i] : 0.f;
     if (p.ln) { s_bias[p.Cout + i] = p.gamma[i]; s_bias[2 * p.Cout + i] = p.beta[i]; }
   }
@@ -441,12 +446,20 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
     const int ty = r / TILE_W, tx = r % TILE_W;
     // stacked small images (srows huge otherwise) or pair tiles (rows of two images interleaved)
     const int sb_img = PAIR ? (ty & 1) : ty / p.srows, sb_row = PAIR ? (ty >> 1) : ty % p.srows;
+    const int group = (warp - 2) >> 2;      // 0: warps 2..5, 1: warps 6..9 (EPI == 1 launches only)
+    const int egroups = EPI == 1 ? p.egroups : 1;
     StoreRing ring;
-    ring.stg0 = stg0; ring.nslots = p.nslots; ring.slot = 0; ring.issuer = threadIdx.x == 64;
+    ring.nslots = p.nslots / egroups; ring.slot = 0; ring.issuer = threadIdx.x == 64 + group * EPI_THREADS;
+    ring.stg0 = stg0 + (uint32_t)(group * ring.nslots) * SLOT_BYTES;
+    ring.bar_id = 1 + group;
     ring.d_have = 0; ring.d_which = 0; ring.d_c = ring.d_w = ring.d_h = ring.d_n = 0; ring.d_slot = 0;
     ring.tm_y = &tm_y; ring.tm_z = &tm_z; ring.dbg = p.debug;
-    int as = 0, pa = 0;
+    int it = -1;
+    if (group < egroups)
     for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
+      ++it;
+      if (egroups == 2 && (it & 1) != group) continue;        // the other group's tile
+      const int as = it & 1, pa = (it >> 1) & 1;              // accumulator stage and its mbarrier phase
       int j, tw, th, n;
       decode_item(p, item, j, tw, th, n);
       const int oh = th * TILE_H + sb_row, ow = tw * TILE_W + tx;
@@ -560,9 +573,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
         }
         release_tmem();
       }
-      if (++as == 2) { as = 0; pa ^= 1; }
     }
-    if (p.tma_store) ring.drain();
+    if (p.tma_store && group < egroups) ring.drain();
   }
 
   tc_fence_before();
@@ -840,6 +852,8 @@ int conv_tc_launch(const b200_tensor* x_in, const void* wmat, int cin, int cout,
     if (!ok) plan_smem(2, 2);
   }
   B200_REQUIRE(p.nsw >= 2, B200_ERR_UNSUPPORTED, "conv3x3 tcgen05: shared memory budget too small");
+  static const int want_groups = getenv("B200_CONV_EGROUPS") ? atoi(getenv("B200_CONV_EGROUPS")) : 2;
+  p.egroups = (ln && p.BN == 64 && !p.pair && p.tma_store && p.nslots >= 4 && want_groups == 2) ? 2 : 1;
   p.act = act; p.accumulate = accumulate; p.bias = bias;
   p.y = reinterpret_cast<__nv_bfloat16*>(y->data);
   p.ysn = y->stride_n; p.ysh = y->stride_h; p.ysw = y->stride_w;
@@ -879,7 +893,7 @@ int conv_tc_launch(const b200_tensor* x_in, const void* wmat, int cin, int cout,
   }
   int grid = p.total_items < sm_count() ? p.total_items : sm_count();
   if (p.pair) conv3x3_tc_kernel<true, 0><<<grid, NTHREADS, smem, st>>>(tm_x, tm_b, tm_y, tm_z, p);
-  else if (p.ln && p.BN == 64) conv3x3_tc_kernel<false, 1><<<grid, NTHREADS, smem, st>>>(tm_x, tm_b, tm_y, tm_z, p);
+  else if (p.ln && p.BN == 64) conv3x3_tc_kernel<false, 1><<<grid, NTHREADS2, smem, st>>>(tm_x, tm_b, tm_y, tm_z, p);
   else if (p.ln) conv3x3_tc_kernel<false, 2><<<grid, NTHREADS, smem, st>>>(tm_x, tm_b, tm_y, tm_z, p);
   else conv3x3_tc_kernel<false, 3><<<grid, NTHREADS, smem, st>>>(tm_x, tm_b, tm_y, tm_z, p);
   return check_launch("conv3x3_tc_kernel");
