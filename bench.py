@@ -326,17 +326,24 @@ def run_gpu(args):
     bytes_conv = sum(_act_bytes(op.inputs[0]) + _act_bytes(op.output) * (2 if getattr(op, "fused_into_ln", False) else 1)
                      for op in conv_ops)
     bytes_conv += sum(_act_bytes(op.inputs[0]) + _act_bytes(op.output) for op in conv_ops if op.inputs[0].needs_grad)
+    # the same figure over the launches that are conv3x3_tc_kernel proper (images larger than 4x4; the deep levels run
+    # the split-K conv_gemm_kernel, whose traffic is weights) -- the population of the ncu `traffic` number
+    win_ops = [op for op in conv_ops if max(op.output.h, op.output.w) > 4]
+    bytes_win = sum(_act_bytes(op.inputs[0]) + _act_bytes(op.output) * (2 if getattr(op, "fused_into_ln", False) else 1)
+                    for op in win_ops)
+    bytes_win += sum(_act_bytes(op.inputs[0]) + _act_bytes(op.output) for op in win_ops if op.inputs[0].needs_grad)
+    n_win = len(win_ops) + sum(1 for op in win_ops if op.inputs[0].needs_grad)
     traffic = None            # DRAM bytes per launch of the same kernel, from the committed `ncu --set full` capture
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_v7_conv_traffic.json")))["dram_bytes_per_launch_mean"]
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_v9_conv_traffic.json")))["dram_bytes_per_launch_mean"]
     except Exception:
         pass
     roofline = {
-        "kernel": "conv3x3_tc_kernel (tcgen05 implicit GEMM; all fprop+dgrad launches of one step)",
+        "kernel": "conv3x3_tc_kernel (tcgen05 implicit GEMM; every fprop / fprop+LayerNorm / dgrad launch of one step, incl. the split-K conv_gemm_kernel launches of the deep levels)",
         "bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf,
         "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if peaks else "fallback 1400 (of fallback)",
-        "traffic": traffic, "traffic_source": "profiles/r01_v7_conv_traffic.json (ncu dram__bytes_read+write, mean over the captured launches)",
-        "algorithmic_bytes_per_launch": bytes_conv / max(n_launch, 1),
+        "traffic": traffic, "traffic_source": "profiles/r01_v9_conv_traffic.json (ncu dram__bytes_read+write, mean over the 33 conv3x3_tc_kernel launches of one step)",
+        "algorithmic_bytes_per_launch": bytes_win / max(n_win, 1),
         "launches_per_step": n_launch, "avg_launch_ms": t_conv / max(n_launch, 1),
         "wgrad_kernel": {"achieved": ach_wg, "frac": ach_wg / peak_tf, "ms_per_step": t_wg},
     }
