@@ -5,6 +5,9 @@ Mirror of /root/reference/Super_resolution/code/train_adaptive_unet.py (train :3
 Keras-style epoch log lines and the same post-training evaluation (Y-channel MSE / PSNR / SSIM / MS-SSIM
 with a `2*round(1/scale)` border shave).  The model, losses and train step run through ``b200unet``.
 Extra flags: ``--precision {fp32,bf16}`` and ``--synthetic N`` (train on N random images, no dataset).
+Data parallel: launch under ``python -m torch.distributed.run --nproc-per-node N --master-addr 127.0.0.1 ...``; every rank
+reads the same patch stream and trains on ITS contiguous slice of each global batch (``--batch_size`` is the GLOBAL
+batch and must divide by N), gradients are exchanged inside ``Model.distribute()``; rank 0 writes the artefacts.
 """
 import argparse
 import glob
@@ -43,8 +46,39 @@ def _synthetic_dir(n, size, seed):
     return d
 
 
+class _ShardedBatches:
+    """Re-iterable view of a (lr, hr) batch stream that yields this rank's slice of every full global batch."""
+
+    def __init__(self, ds, rank, world):
+        self.ds, self.rank, self.world = ds, rank, world
+
+    def __iter__(self):
+        from b200unet.parallel import shard_range
+        for lr, hr in self.ds:
+            if lr.shape[0] % self.world:
+                continue                      # ragged tail batch: equal shards are required (mean of shard means)
+            lo, hi = shard_range(lr.shape[0], self.rank, self.world)
+            yield lr[lo:hi], hr[lo:hi]
+
+
+def _init_distributed():
+    """(rank, world) from the torchrun environment; initialises NCCL when world > 1."""
+    import os
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world <= 1:
+        return 0, 1
+    import torch
+    import torch.distributed as dist
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if not dist.is_initialized():
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    return dist.get_rank(), world
+
+
 def train(args: argparse.Namespace) -> None:
     import torch
+    rank, world = _init_distributed()
     from b200unet import builders as B, metrics as MT
     from b200unet.keras import mixed_precision, set_random_seed
     from b200unet.keras.callbacks import BackupAndRestore, EarlyStopping, ModelCheckpoint, TensorBoard
@@ -99,6 +133,12 @@ def train(args: argparse.Namespace) -> None:
                                                 max_depth=args.max_depth)
     loss_fn, metrics = B.build_losses_and_metrics(args.loss)
     model.compile(optimizer=Adam(learning_rate=args.learning_rate), loss=loss_fn, metrics=metrics, jit_compile=False)
+    if world > 1:
+        _require(args.batch_size % world == 0, f"--batch_size {args.batch_size} must divide by the {world} ranks")
+        model.distribute()
+        train_ds = _ShardedBatches(train_ds, rank, world)
+        if val_fit_ds is not None:
+            val_fit_ds = _ShardedBatches(val_fit_ds, rank, world)
 
     if args.resume_from:
         cand = Path(args.resume_from).expanduser()
@@ -120,6 +160,9 @@ def train(args: argparse.Namespace) -> None:
     print("\n".join(summary))
 
     model_dir = Path(args.model_dir).expanduser()
+    if rank > 0:      # weight reads are collective under the sharded optimizer: every rank saves, rank 0's files are canonical
+        model_dir = model_dir / f"rank{rank}"
+        args.log_dir = str(Path(args.log_dir).expanduser() / f"rank{rank}")
     model_dir.mkdir(parents=True, exist_ok=True)
     ckpt_path = model_dir / f"unet_adaptive_scale_new_loss{args.scale:.2f}_depth{info['depth']}.keras"
     stamp = datetime.now().strftime("%Y%m%d-%H%M%S")

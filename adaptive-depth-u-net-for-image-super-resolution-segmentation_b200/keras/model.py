@@ -721,8 +721,20 @@ class Model:
             for k, v in logs.items():
                 sums[k] = sums.get(k, 0.0) + float(v)
             n += 1
-        res = {k: v / max(n, 1) for k, v in sums.items()}
+        res = self._mean_over_ranks({k: v / max(n, 1) for k, v in sums.items()})
         return res if return_dict else list(res.values())
+
+    def _mean_over_ranks(self, logs: Dict[str, float]) -> Dict[str, float]:
+        """Data parallel: every rank sees its shard only; callbacks (EarlyStopping, ModelCheckpoint, ReduceLROnPlateau)
+        must take the same decisions everywhere, so epoch-level logs are averaged over the ranks (collective)."""
+        if self._dist is None or self._world() == 1 or not logs:
+            return logs
+        dist, group = self._dist
+        keys = sorted(logs)
+        t = torch.tensor([float(logs[k]) for k in keys], dtype=torch.float64, device=self._device)
+        dist.all_reduce(t, group=group)
+        t /= self._world()
+        return {k: float(v) for k, v in zip(keys, t.tolist())}
 
     def fit(self, x=None, y=None, epochs=1, initial_epoch=0, steps_per_epoch=None, validation_data=None,
             validation_steps=None, validation_freq=1, callbacks=None, verbose=1, batch_size=None, **kwargs):
@@ -755,7 +767,7 @@ class Model:
                 steps += 1
             if steps_per_epoch is None:
                 train_iter = iter(x)
-            logs = {k: float(v) / max(steps, 1) for k, v in acc.items()}
+            logs = self._mean_over_ranks({k: float(v) / max(steps, 1) for k, v in acc.items()})
             if validation_data is not None and (epoch + 1) % validation_freq == 0:
                 val = self.evaluate(validation_data, steps=validation_steps, return_dict=True)
                 logs.update({f"val_{k}": v for k, v in val.items()})
