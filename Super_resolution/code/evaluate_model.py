@@ -69,21 +69,13 @@ def load_checkpoint_model(model_path, scale: float, patch_size: int, depth_overr
 
 
 def evaluate(model, dataset, eval_shave: int) -> Tuple[EvalResults, List[Dict[str, float]]]:
-    import torch
     from b200unet import metrics as MT
     vals = {"psnr": [], "ssim": [], "msssim": [], "mse": []}
     per_image: List[Dict[str, float]] = []
     offset = 0
     for lr_batch, hr_batch in dataset:
-        pred = model(lr_batch, training=False).float().clamp(0.0, 1.0)
-        hr = torch.from_numpy(np.asarray(hr_batch, np.float32)).to(pred.device)
-        py, hy = MT.rgb_to_luma_bt601(pred), MT.rgb_to_luma_bt601(hr)
-        if eval_shave > 0:
-            py = py[:, eval_shave:-eval_shave, eval_shave:-eval_shave, :]
-            hy = hy[:, eval_shave:-eval_shave, eval_shave:-eval_shave, :]
-        b = {"psnr": MT.psnr(hy, py).cpu().numpy(), "ssim": MT.ssim(hy, py).cpu().numpy(),
-             "msssim": MT.ssim_multiscale(hy, py).cpu().numpy(),
-             "mse": ((hy - py) ** 2).mean(dim=(1, 2, 3)).cpu().numpy()}
+        pred = model(lr_batch, training=False)        # clipped to [0,1] inside the fused luma kernel
+        b = MT.eval_luma_metrics(pred, hr_batch, eval_shave)
         for k in vals:
             vals[k].append(b[k])
         for i in range(len(b["psnr"])):
@@ -137,6 +129,7 @@ def parse_args(argv=None) -> argparse.Namespace:
     p.add_argument("--use-train-split", action="store_true", help="Evaluate against the training split defaults instead of validation.")
     p.add_argument("--precision", choices=["fp32", "bf16"], default="fp32", help="Compute/storage precision.")
     p.add_argument("--synthetic", type=int, default=0, help="Evaluate on this many random images instead of --hr-dir.")
+    p.add_argument("--device-pipeline", action="store_true", help="Crop and degrade the evaluation patches on the GPU.")
     p.add_argument("--random-init", action="store_true", help="Skip the checkpoint (smoke runs of the forward path).")
     return p.parse_args(argv)
 
@@ -162,7 +155,8 @@ def main(argv=None) -> EvalResults:
         raise ValueError(f"No high-resolution PNG files found in {hr_dir}")
     # the offline evaluator degrades by --scale (reference :233-239), unlike training's fixed 0.5
     eval_ds, total_patches, patch_labels = make_eval_patch_dataset(hr_files, patch_size=args.patch_size, scale=args.scale,
-                                                                   batch_size=args.batch_size, stride=args.eval_stride)
+                                                                   batch_size=args.batch_size, stride=args.eval_stride,
+                                                                   device="cuda" if args.device_pipeline else None)
     model = load_checkpoint_model(args.model_path.expanduser() if args.model_path else None, args.scale, args.patch_size,
                                   args.depth_override, args.precision, args.random_init)
     eval_shave = infer_eval_shave(args.scale, args.eval_shave)

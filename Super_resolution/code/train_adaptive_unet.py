@@ -13,6 +13,7 @@ import argparse
 import glob
 import json
 import math
+import os
 import sys
 from datetime import datetime
 from pathlib import Path
@@ -111,11 +112,13 @@ def train(args: argparse.Namespace) -> None:
     tr, va, te = split_indices(len(hr_paths), train_frac, args.val_split, args.test_split, args.seed)
     train_paths, val_paths, test_paths = ([hr_paths[i] for i in idx] for idx in (tr, va, te))
 
+    # crop / degrade / shuffle buffer on the GPU (same pairs, same order as the host OpenCV stream)
+    pipe_dev = "cuda" if (args.device_pipeline or os.environ.get("B200_DEVICE_PIPELINE") == "1") else None
     eval_ds = lambda paths: make_eval_patch_dataset(paths, patch_size=P, scale=DATA_LR_SHRINK,
-                                                    batch_size=args.batch_size, stride=args.eval_stride)
+                                                    batch_size=args.batch_size, stride=args.eval_stride, device=pipe_dev)
     train_ds, n_train = make_training_patch_dataset(train_paths, patch_size=P, patches_per_image=args.patches_per_image,
                                                     scale=DATA_LR_SHRINK, batch_size=args.batch_size, seed=args.seed,
-                                                    shuffle_buffer=args.shuffle_buffer)
+                                                    shuffle_buffer=args.shuffle_buffer, device=pipe_dev)
     val_fit_ds, n_val = None, 0
     if val_paths:
         val_fit_ds, n_val, _ = eval_ds(val_paths)
@@ -213,14 +216,9 @@ def train(args: argparse.Namespace) -> None:
         acc = {"mse": [], "psnr": [], "ssim": [], "msssim": []}
         seen = 0
         for lr_b, hr_b in ds:
-            pred = model(lr_b, training=False).float().clamp(0.0, 1.0)
-            py, hy = MT.rgb_to_luma_bt601(pred), MT.rgb_to_luma_bt601(torch.from_numpy(hr_b).to(pred.device))
-            if shave > 0:
-                py, hy = py[:, shave:-shave, shave:-shave, :], hy[:, shave:-shave, shave:-shave, :]
-            acc["psnr"].append(MT.psnr(hy, py).cpu().numpy())
-            acc["ssim"].append(MT.ssim(hy, py).cpu().numpy())
-            acc["msssim"].append(MT.ssim_multiscale(hy, py).cpu().numpy())
-            acc["mse"].append(((hy - py) ** 2).mean(dim=(1, 2, 3)).cpu().numpy())
+            b = MT.eval_luma_metrics(model(lr_b, training=False), hr_b, shave)
+            for k in ("psnr", "ssim", "msssim", "mse"):
+                acc[k].append(b[k])
             seen += hr_b.shape[0]
         if not seen:
             print(f"{name}: no samples, skipping metric aggregation.")
@@ -272,6 +270,8 @@ def parse_args(argv=None) -> argparse.Namespace:
     p.add_argument("--initial_epoch", type=int, default=0,
                    help="Epoch index to begin training from when resuming (must be < --epochs).")
     p.add_argument("--synthetic", type=int, default=0, help="Train on this many random images instead of a dataset.")
+    p.add_argument("--device_pipeline", action="store_true",
+                   help="Crop, degrade (INTER_AREA/INTER_CUBIC) and shuffle patches on the GPU (also B200_DEVICE_PIPELINE=1).")
     return p.parse_args(argv)
 
 

@@ -12,7 +12,8 @@ from pathlib import Path
 HERE = Path(__file__).resolve().parent
 LIB_PATH = HERE / "lib" / "libb200unet.so"
 
-F32, BF16 = 0, 1
+F32, BF16, U8 = 0, 1, 2
+CV_INTER_AREA, CV_INTER_CUBIC = 0, 1
 ACT_NONE, ACT_RELU, ACT_SIGMOID = 0, 1, 2
 ALGO_AUTO, ALGO_SIMT, ALGO_TCGEN05 = 0, 1, 2
 LOSS_CHARBONNIER, LOSS_L1, LOSS_MSE = 0, 1, 2
@@ -91,6 +92,14 @@ SIGNATURES = {
     "b200_cast": (_i, [_vp, _i, _vp, _i, _sz, _vp]),
     "b200_copy_tensor": (_i, [_TP, _TP, _vp]),
     "b200_scale_inplace": (_i, [_vp, _sz, _f, _vp]),
+    "b200_cv_resize_taps": (_i, [_i, _i, _i]),
+    "b200_cv_resize_plan": (_i, [_i, _i, _i, _vp, _vp, _i]),
+    "b200_patch_extract": (_i, [_vp, _i, _i, _i, _vp, _TP, _vp]),
+    "b200_gather2d": (_i, [_TP, _TP, _vp, _vp, _i, _vp, _vp, _i, _i, _vp]),
+    "b200_copy_rows": (_i, [_vp, _vp, _vp, _vp, _i, C.c_longlong, _vp]),
+    "b200_luma_pair": (_i, [_TP, _TP, _i, _vp, _vp, _vp, _vp]),
+    "b200_ssim_planes": (_i, [_vp, _vp, _i, _i, _i, _f, _vp, _vp]),
+    "b200_avgpool2_planes": (_i, [_vp, _i, _i, _i, _vp, _vp]),
     "b200_debug_umma_probe": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _vp, _vp]),
     "b200_debug_umma_rate": (_i, [_i, _i, _i, _vp, _i, _vp]),
 }

@@ -94,6 +94,15 @@ int scale_inplace(float*, size_t, float, cudaStream_t);
 int convT2_fprop(const b200_tensor*, const void*, const float*, int, const b200_tensor*, cudaStream_t);
 int convT2_dgrad(const b200_tensor*, const void*, int, const b200_tensor*, cudaStream_t);
 int convT2_wgrad(const b200_tensor*, const b200_tensor*, float*, float*, cudaStream_t);
+int cv_resize_taps(int, int, int);
+int cv_resize_plan(int, int, int, int32_t*, float*, int);
+int patch_extract(const void*, int, int, int, const int32_t*, const b200_tensor*, cudaStream_t);
+int gather2d(const b200_tensor*, const b200_tensor*, const int32_t*, const float*, int, const int32_t*, const float*, int,
+             int, cudaStream_t);
+int copy_rows(const float*, const int32_t*, float*, const int32_t*, int, long long, cudaStream_t);
+int luma_pair(const b200_tensor*, const b200_tensor*, int, float*, float*, float*, cudaStream_t);
+int ssim_planes(const float*, const float*, int, int, int, float, float*, cudaStream_t);
+int avgpool2_planes(const float*, int, int, int, float*, cudaStream_t);
 
 }  // namespace b200
 
@@ -397,6 +406,69 @@ int b200_scale_inplace(float* p, size_t count, float sc, void* s) {
   B200_REQUIRE(p, B200_ERR_BAD_ARG, "scale_inplace: NULL argument");
   if (count == 0) return B200_OK;
   return scale_inplace(p, count, sc, ST(s));
+}
+
+// ---- patch pipeline ---------------------------------------------------------------------------
+int b200_cv_resize_taps(int in_size, int out_size, int interp) {
+  B200_REQUIRE(in_size > 0 && out_size > 0, B200_ERR_BAD_ARG, "cv_resize_taps: sizes must be positive");
+  B200_REQUIRE(interp == B200_CV_INTER_AREA || interp == B200_CV_INTER_CUBIC, B200_ERR_BAD_ARG,
+               "cv_resize_taps: unknown interpolation %d", interp);
+  B200_REQUIRE(interp == B200_CV_INTER_CUBIC || out_size <= in_size, B200_ERR_UNSUPPORTED,
+               "cv_resize_taps: INTER_AREA tables are for shrinking (%d -> %d)", in_size, out_size);
+  return cv_resize_taps(in_size, out_size, interp);
+}
+int b200_cv_resize_plan(int in_size, int out_size, int interp, int32_t* idx, float* weights, int taps) {
+  B200_REQUIRE(idx && weights, B200_ERR_BAD_ARG, "cv_resize_plan: NULL table");
+  const int need = b200_cv_resize_taps(in_size, out_size, interp);
+  if (need < 0) return need;
+  B200_REQUIRE(taps >= need, B200_ERR_BAD_ARG, "cv_resize_plan: %d taps given, %d needed", taps, need);
+  return cv_resize_plan(in_size, out_size, interp, idx, weights, taps);
+}
+int b200_patch_extract(const void* image, int image_dtype, int img_h, int img_w, const int32_t* origins,
+                       const b200_tensor* hr, void* s) {
+  REQ_T(hr, "hr");
+  B200_REQUIRE(image && origins, B200_ERR_BAD_ARG, "patch_extract: NULL argument");
+  B200_REQUIRE(image_dtype == B200_U8 || image_dtype == B200_F32, B200_ERR_BAD_ARG, "patch_extract: image dtype %d",
+               image_dtype);
+  B200_REQUIRE(hr->dtype == B200_F32 && hr->c == 3 && hr->stride_w == 3 && hr->h == hr->w, B200_ERR_BAD_ARG,
+               "patch_extract: hr must be fp32 [n,P,P,3] with dense rows");
+  B200_REQUIRE(img_h >= hr->h && img_w >= hr->w, B200_ERR_BAD_ARG, "patch_extract: patch_size exceeds image dimensions");
+  return patch_extract(image, image_dtype, img_h, img_w, origins, hr, ST(s));
+}
+int b200_gather2d(const b200_tensor* x, const b200_tensor* y, const int32_t* h_idx, const float* h_w, int h_taps,
+                  const int32_t* w_idx, const float* w_w, int w_taps, int clip01, void* s) {
+  REQ_T(x, "x"); REQ_T(y, "y");
+  B200_REQUIRE(h_idx && h_w && w_idx && w_w && h_taps > 0 && w_taps > 0, B200_ERR_BAD_ARG, "gather2d: bad tables");
+  B200_REQUIRE(x->dtype == B200_F32 && y->dtype == B200_F32 && x->c == y->c && x->n == y->n, B200_ERR_BAD_ARG,
+               "gather2d: fp32 tensors with equal batch and channels expected");
+  return gather2d(x, y, h_idx, h_w, h_taps, w_idx, w_w, w_taps, clip01, ST(s));
+}
+int b200_copy_rows(const float* src, const int32_t* src_rows, float* dst, const int32_t* dst_rows, int n_rows,
+                   long long row_elems, void* s) {
+  B200_REQUIRE(src && dst && row_elems > 0 && n_rows >= 0 && n_rows <= 65535, B200_ERR_BAD_ARG, "copy_rows: bad argument");
+  if (n_rows == 0) return B200_OK;
+  return copy_rows(src, src_rows, dst, dst_rows, n_rows, row_elems, ST(s));
+}
+
+// ---- evaluation metrics -------------------------------------------------------------------------
+int b200_luma_pair(const b200_tensor* pred, const b200_tensor* hr, int shave, float* pred_y, float* hr_y, float* sse,
+                   void* s) {
+  REQ_T(pred, "pred_rgb"); REQ_T(hr, "hr_rgb");
+  B200_REQUIRE(pred_y && hr_y && sse, B200_ERR_BAD_ARG, "luma_pair: NULL output");
+  B200_REQUIRE(same_shape(pred, hr) && pred->c == 3 && hr->dtype == B200_F32, B200_ERR_BAD_ARG,
+               "luma_pair: prediction and fp32 target must both be [n,h,w,3]");
+  B200_REQUIRE(shave >= 0 && 2 * shave < pred->h && 2 * shave < pred->w && pred->n <= 65535, B200_ERR_BAD_ARG,
+               "luma_pair: shave %d removes the full %dx%d frame", shave, pred->h, pred->w);
+  return luma_pair(pred, hr, shave, pred_y, hr_y, sse, ST(s));
+}
+int b200_ssim_planes(const float* a, const float* b, int n, int h, int w, float max_val, float* out, void* s) {
+  B200_REQUIRE(a && b && out && n > 0 && n <= 65535, B200_ERR_BAD_ARG, "ssim_planes: bad argument");
+  B200_REQUIRE(h >= 11 && w >= 11, B200_ERR_BAD_ARG, "ssim_planes: %dx%d is smaller than the 11x11 window", h, w);
+  return ssim_planes(a, b, n, h, w, max_val, out, ST(s));
+}
+int b200_avgpool2_planes(const float* x, int n, int h, int w, float* y, void* s) {
+  B200_REQUIRE(x && y && n > 0 && h > 0 && w > 0, B200_ERR_BAD_ARG, "avgpool2_planes: bad argument");
+  return avgpool2_planes(x, n, h, w, y, ST(s));
 }
 
 int b200_debug_umma_probe(const void* a, int a_rows, const void* b, int start_bytes, int sbo_bytes, int lbo_bytes,

@@ -605,6 +605,10 @@ class Model:
             src = torch.from_numpy(src)
         if src.dtype != dst.dtype and not src.is_cuda:
             src = src.to(dst.dtype)
+        if (src.is_cuda and src.dtype != dst.dtype and src.dtype in ops._DT and dst.dtype in ops._DT and dst.dim() == 4
+                and src.is_contiguous() and src.numel() == dst.numel()):
+            ops.copy_tensor(src.reshape(dst.shape), dst)      # device batches (DevicePatchDataset): converting copy kernel
+            return
         dst.copy_(src.reshape(dst.shape), non_blocking=True)
 
     # ------------------------------------------------------------------ steps

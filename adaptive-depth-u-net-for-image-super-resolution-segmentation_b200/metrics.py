@@ -1,65 +1,118 @@
-"""Evaluation metrics of the reference's eval loops (not on the training hot path; torch ops).
+"""Evaluation metrics of the reference's eval loops on the GPU (kernels of ``csrc/metrics.cu``).
 
-BT.601 luma, PSNR, SSIM and MS-SSIM with tf.image semantics
-(/root/reference/Super_resolution/code/train_adaptive_unet.py:144-157, 673-721): 11x11 Gaussian
-window (sigma 1.5), K1 0.01, K2 0.03, "valid" filtering, per-image mean; MS-SSIM over 5 scales with
-the standard weights and 2x2 average pooling between scales.
+BT.601 luma, border shave, MSE(Y), PSNR(Y), SSIM(Y) and MS-SSIM(Y) with tf.image semantics
+(/root/reference/Super_resolution/code/train_adaptive_unet.py:144-157, 673-721;
+evaluate_model.py:94-163).  One fused kernel turns the RGB prediction and target into the two shaved luma
+planes and the per-image squared error; the SSIM kernel filters a, b, a^2, b^2, ab with the separable 11x11
+Gaussian in shared memory and reduces the SSIM / contrast-structure maps per image; MS-SSIM chains it over
+five scales with the 2x2 pooling kernel.  Only the last step (a few floats per image: log10, the five-factor
+product) runs on the host.  There is no CPU path: tensors must live on a CUDA device.
 """
 from __future__ import annotations
 
+from typing import Dict
+
+import numpy as np
 import torch
-import torch.nn.functional as F
+
+from . import ops
 
 _MS_WEIGHTS = (0.0448, 0.2856, 0.3001, 0.2363, 0.1333)
+_WIN = 11
 
 
-def rgb_to_luma_bt601(image: torch.Tensor) -> torch.Tensor:
-    """RGB in [0,1], (N,H,W,3) or (H,W,3) -> BT.601 luma in [0,1] with a trailing singleton channel."""
-    image = image.float()
-    coeffs = torch.tensor([65.481, 128.553, 24.966], device=image.device)
-    y = (image * coeffs).sum(dim=-1, keepdim=True) + 16.0
-    return (y / 255.0).clamp(0.0, 1.0)
+def _cuda(t, dtype=None) -> torch.Tensor:
+    if isinstance(t, np.ndarray):
+        t = torch.from_numpy(t)
+    if not t.is_cuda:
+        if not torch.cuda.is_available():
+            raise ops._ffi.B200Error("b200unet.metrics needs a CUDA device: there is no CPU fallback")
+        t = t.cuda()
+    if dtype is not None and t.dtype != dtype:
+        t = t.to(dtype)
+    return t.contiguous()
 
 
-def psnr(a: torch.Tensor, b: torch.Tensor, max_val: float = 1.0) -> torch.Tensor:
-    mse = ((a.float() - b.float()) ** 2).mean(dim=(1, 2, 3))
-    return 10.0 * torch.log10(max_val * max_val / mse)
+def luma_planes(pred_rgb, hr_rgb, shave: int = 0):
+    """(pred_y, hr_y, sse): shaved BT.601 luma planes [n,h',w'] (fp32; prediction clipped to [0,1] first) and
+    the per-image sum of squared luma differences."""
+    pred = _cuda(pred_rgb)
+    if pred.dtype not in (torch.float32, torch.bfloat16):
+        pred = pred.float()
+    hr = _cuda(hr_rgb, torch.float32)
+    n, h, w, _ = pred.shape
+    oh, ow = h - 2 * shave, w - 2 * shave
+    py = torch.empty((n, oh, ow), dtype=torch.float32, device=pred.device)
+    hy = torch.empty_like(py)
+    sse = torch.empty((n,), dtype=torch.float32, device=pred.device)
+    ops.luma_pair(pred, hr, shave, py, hy, sse)
+    return py, hy, sse
 
 
-def _gauss(size=11, sigma=1.5, device="cpu"):
-    x = torch.arange(size, dtype=torch.float32, device=device) - (size - 1) / 2.0
-    g = torch.exp(-(x * x) / (2 * sigma * sigma))
-    g = g / g.sum()
-    return (g[:, None] * g[None, :])[None, None]
+def rgb_to_luma_bt601(image) -> torch.Tensor:
+    """RGB in [0,1], (N,H,W,3) or (H,W,3) -> BT.601 luma in [0,1] with a trailing singleton channel.
+
+    Note: the input is clipped to [0,1] first (the eval loops clip the prediction before the call; an HR image
+    is in range already)."""
+    img = _cuda(image, torch.float32)
+    single = img.dim() == 3
+    if single:
+        img = img[None]
+    _, y, _ = luma_planes(img, img, 0)
+    y = y[..., None]
+    return y[0] if single else y
 
 
-def _ssim_cs(a, b, max_val=1.0):
-    """a, b: (N,H,W,C).  Returns per-image (ssim, cs)."""
-    a, b = a.float().permute(0, 3, 1, 2), b.float().permute(0, 3, 1, 2)
-    c = a.shape[1]
-    k = _gauss(device=a.device).expand(c, 1, 11, 11)
-    f = lambda t: F.conv2d(t, k, groups=c)
-    mu_a, mu_b = f(a), f(b)
-    var_a, var_b, cov = f(a * a) - mu_a * mu_a, f(b * b) - mu_b * mu_b, f(a * b) - mu_a * mu_b
-    c1, c2 = (0.01 * max_val) ** 2, (0.03 * max_val) ** 2
-    cs = (2 * cov + c2) / (var_a + var_b + c2)
-    lum = (2 * mu_a * mu_b + c1) / (mu_a * mu_a + mu_b * mu_b + c1)
-    return (lum * cs).mean(dim=(1, 2, 3)), cs.mean(dim=(1, 2, 3))
+def _planes(t) -> torch.Tensor:
+    t = _cuda(t, torch.float32)
+    if t.dim() == 4:
+        if t.shape[3] != 1:
+            raise ValueError("metrics operate on single-channel (luma) images")
+        t = t[..., 0]
+    return t.contiguous()
 
 
-def ssim(a, b, max_val=1.0):
-    return _ssim_cs(a, b, max_val)[0]
+def _ssim_cs(a: torch.Tensor, b: torch.Tensor, max_val: float) -> np.ndarray:
+    """Per-image means of the SSIM map and of its contrast-structure factor: float64 numpy [n,2]."""
+    n, h, w = a.shape
+    out = torch.empty((n, 2), dtype=torch.float32, device=a.device)
+    ops.ssim_planes(a, b, out, max_val)
+    return out.cpu().numpy().astype(np.float64) / float((h - _WIN + 1) * (w - _WIN + 1))
 
 
-def ssim_multiscale(a, b, max_val=1.0):
-    """tf.image.ssim_multiscale; NaN when the image is too small for 5 scales (< 176 px), where TF raises."""
-    if min(a.shape[1], a.shape[2]) < 11 * 2 ** 4:
-        return torch.full((a.shape[0],), float("nan"), device=a.device)
-    vals = []
-    for i, w in enumerate(_MS_WEIGHTS):
-        s, cs = _ssim_cs(a, b, max_val)
-        vals.append(torch.relu(s if i == len(_MS_WEIGHTS) - 1 else cs) ** w)
+def ssim(a, b, max_val: float = 1.0) -> np.ndarray:
+    """tf.image.ssim per image (float32 numpy [n])."""
+    return _ssim_cs(_planes(a), _planes(b), max_val)[:, 0].astype(np.float32)
+
+
+def ssim_multiscale(a, b, max_val: float = 1.0) -> np.ndarray:
+    """tf.image.ssim_multiscale per image; NaN when the image is too small for 5 scales (< 176 px), where TF raises."""
+    a, b = _planes(a), _planes(b)
+    n, h, w = a.shape
+    if min(h, w) < _WIN * 2 ** (len(_MS_WEIGHTS) - 1):
+        return np.full((n,), np.nan, dtype=np.float32)
+    factors = []
+    for i in range(len(_MS_WEIGHTS)):
+        sc = _ssim_cs(a, b, max_val)
+        factors.append(sc[:, 0] if i == len(_MS_WEIGHTS) - 1 else sc[:, 1])
         if i < len(_MS_WEIGHTS) - 1:
-            a = F.avg_pool2d(a.float().permute(0, 3, 1, 2), 2).permute(0, 2, 3, 1)
-            b = F.avg_pool2d(b.float().permute(0, 3, 1, 2), 2).permute(0, 2, 3, 1)
-    return torch.stack(vals, dim=0).prod(dim=0)
+            h2, w2 = (a.shape[1] + 1) // 2, (a.shape[2] + 1) // 2
+            a2 = torch.empty((n, h2, w2), dtype=torch.float32, device=a.device)
+            b2 = torch.empty_like(a2)
+            ops.avgpool2_planes(a, a2)
+            ops.avgpool2_planes(b, b2)
+            a, b = a2, b2
+    f = np.maximum(np.stack(factors, axis=1), 0.0)                       # [n,5]: a few floats per image
+    return np.prod(f ** np.asarray(_MS_WEIGHTS)[None, :], axis=1).astype(np.float32)
+
+
+def eval_luma_metrics(pred_rgb, hr_rgb, shave: int = 0) -> Dict[str, np.ndarray]:
+    """One eval-loop iteration (evaluate_model.py:104-121): per-image psnr / ssim / msssim / mse of the luma planes."""
+    py, hy, sse = luma_planes(pred_rgb, hr_rgb, shave)
+    n, h, w = py.shape
+    mse_v = sse.double().cpu().numpy() / float(h * w)
+    with np.errstate(divide="ignore"):
+        psnr_v = 10.0 * np.log10(1.0 / mse_v)
+    ssim_v = ssim(hy, py) if min(h, w) >= _WIN else np.full((n,), np.nan, dtype=np.float32)
+    return {"psnr": psnr_v.astype(np.float32), "ssim": ssim_v, "msssim": ssim_multiscale(hy, py),
+            "mse": mse_v.astype(np.float32)}

@@ -14,8 +14,8 @@ import numpy as np
 import torch
 
 from . import _ffi
-from ._ffi import (ACT_NONE, ACT_RELU, ACT_SIGMOID, ALGO_AUTO, ALGO_SIMT, ALGO_TCGEN05, BF16, F32, Filter, Tensor,
-                   check)
+from ._ffi import (ACT_NONE, ACT_RELU, ACT_SIGMOID, ALGO_AUTO, ALGO_SIMT, ALGO_TCGEN05, BF16, CV_INTER_AREA, CV_INTER_CUBIC,
+                   F32, U8, Filter, Tensor, check)
 
 _DT = {torch.float32: F32, torch.bfloat16: BF16}
 
@@ -314,6 +314,74 @@ def copy_tensor(src, dst):
 
 def scale_inplace(p, s):
     check(lib().b200_scale_inplace(_ptr(p), p.numel(), float(s), _stream()), "scale_inplace")
+
+
+# ---- patch pipeline (shared/pipeline.py:79-136 of the reference, on the device) -----------------
+class CvResizePlan:
+    """OpenCV tap table of one axis (INTER_AREA shrink or INTER_CUBIC), built by the library, uploaded once."""
+
+    def __init__(self, in_size: int, out_size: int, interp: int, device):
+        L = lib()
+        self.in_size, self.out_size, self.interp = int(in_size), int(out_size), int(interp)
+        taps = int(L.b200_cv_resize_taps(self.in_size, self.out_size, self.interp))
+        if taps < 0:
+            check(taps, "cv_resize_taps")
+        idx = np.zeros((self.out_size, taps), dtype=np.int32)
+        w = np.zeros((self.out_size, taps), dtype=np.float32)
+        check(L.b200_cv_resize_plan(self.in_size, self.out_size, self.interp, idx.ctypes.data, w.ctypes.data, taps),
+              "cv_resize_plan")
+        self.taps, self.host = taps, (idx, w)
+        self.idx = torch.from_numpy(idx).to(device)
+        self.weights = torch.from_numpy(w).to(device)
+
+
+def patch_extract(image: torch.Tensor, origins: torch.Tensor, hr: torch.Tensor):
+    """hr[i] = image[top_i:top_i+P, left_i:left_i+P] as fp32; image: cuda uint8/float32 [H,W,3]; origins: cuda int32 [n,2]."""
+    if not image.is_cuda or image.dim() != 3 or image.shape[2] != 3 or not image.is_contiguous():
+        raise ValueError("image must be a contiguous CUDA HxWx3 tensor")
+    if image.dtype not in (torch.uint8, torch.float32):
+        raise ValueError("image must be uint8 or float32")
+    if origins.dtype != torch.int32 or not origins.is_cuda or tuple(origins.shape) != (hr.shape[0], 2):
+        raise ValueError("origins must be a CUDA int32 [n,2] tensor")
+    check(lib().b200_patch_extract(_ptr(image), U8 if image.dtype == torch.uint8 else F32, int(image.shape[0]),
+                                   int(image.shape[1]), _ptr(origins.contiguous()), tdesc(hr), _stream()), "patch_extract")
+    return hr
+
+
+def gather2d(x, y, plan_h: CvResizePlan, plan_w: CvResizePlan, clip01: bool = False):
+    check(lib().b200_gather2d(tdesc(x), tdesc(y), _ptr(plan_h.idx), _ptr(plan_h.weights), plan_h.taps, _ptr(plan_w.idx),
+                              _ptr(plan_w.weights), plan_w.taps, int(clip01), _stream()), "gather2d")
+    return y
+
+
+def copy_rows(src, src_rows, dst, dst_rows, n_rows: int):
+    """dst[dst_rows[r]] = src[src_rows[r]] over fp32 rows (first axis); either index tensor may be None (= r)."""
+    row = src[0].numel()
+    if dst[0].numel() != row or src.dtype != torch.float32 or dst.dtype != torch.float32:
+        raise ValueError("copy_rows: fp32 tensors with equal row sizes expected")
+    if not src.is_contiguous() or not dst.is_contiguous():
+        raise ValueError("copy_rows: contiguous tensors expected")
+    check(lib().b200_copy_rows(_ptr(src), _ptr(src_rows), _ptr(dst), _ptr(dst_rows), int(n_rows), row, _stream()),
+          "copy_rows")
+    return dst
+
+
+# ---- evaluation metrics (train_adaptive_unet.py:144-157, 673-721) --------------------------------
+def luma_pair(pred, hr, shave, pred_y, hr_y, sse):
+    check(lib().b200_luma_pair(tdesc(pred), tdesc(hr), int(shave), _ptr(pred_y), _ptr(hr_y), _ptr(sse), _stream()),
+          "luma_pair")
+
+
+def ssim_planes(a, b, out, max_val: float = 1.0):
+    n, h, w = a.shape
+    check(lib().b200_ssim_planes(_ptr(a), _ptr(b), n, h, w, float(max_val), _ptr(out), _stream()), "ssim_planes")
+    return out
+
+
+def avgpool2_planes(x, y):
+    n, h, w = x.shape
+    check(lib().b200_avgpool2_planes(_ptr(x), n, h, w, _ptr(y), _stream()), "avgpool2_planes")
+    return y
 
 
 def umma_probe(a, b, start_bytes, sbo_bytes, lbo_bytes, mn_major, out):

@@ -37,7 +37,7 @@ typedef enum b200_status {
   B200_ERR_LAUNCH = -3
 } b200_status;
 
-typedef enum b200_dtype { B200_F32 = 0, B200_BF16 = 1 } b200_dtype;
+typedef enum b200_dtype { B200_F32 = 0, B200_BF16 = 1, B200_U8 = 2 /* images of the patch pipeline only */ } b200_dtype;
 
 /* Epilogue / activation selector. */
 typedef enum b200_act {
@@ -228,6 +228,45 @@ int b200_softmax_ce_loss(const b200_tensor* prob, const int32_t* labels, float g
 int b200_adam_advance(int32_t* step, void* stream);
 int b200_adam_step(float* p, const float* g, float* m, float* v, size_t count, const float* hyper,
                    const int32_t* step, void* shadow_bf16, void* stream);
+
+/* ---- patch pipeline on the device -- shared/pipeline.py:79-136, 177-246 -------------
+ * random_patches / grid_patches + degrade_image (cv2 INTER_AREA shrink to round(P*scale), INTER_CUBIC
+ * enlargement back to P, input clipped to [0,1], output not clipped) on a decoded image that is
+ * already resident in HBM.  OpenCV's resize is a separable tap table per axis; the host helpers build
+ * the tables OpenCV builds (explicit source indices, border taps clamped), b200_gather2d applies them
+ * horizontal-first in fp32.  Patch origins are drawn on the host (numpy Generator, the reference's
+ * seed discipline) and uploaded. */
+typedef enum b200_cv_interp { B200_CV_INTER_AREA = 0, B200_CV_INTER_CUBIC = 1 } b200_cv_interp;
+int b200_cv_resize_taps(int in_size, int out_size, int interp);          /* taps per output index (host) */
+int b200_cv_resize_plan(int in_size, int out_size, int interp, int32_t* idx /*host [out*taps]*/,
+                        float* weights /*host [out*taps]*/, int taps);
+/* hr[i] = image[top_i : top_i+P, left_i : left_i+P, :] as fp32 (uint8 images are scaled by 1/255, as
+ * load_rgb_image_full :70-76 does).  image: device, HxWx3 dense, B200_U8 or B200_F32.  origins: device
+ * int32 [n][2] = (top, left), clamped into the image by the kernel.  hr: fp32 [n,P,P,3], dense rows. */
+int b200_patch_extract(const void* image, int image_dtype, int img_h, int img_w, const int32_t* origins,
+                       const b200_tensor* hr, void* stream);
+/* y[n,oy,ox,:] = sum_j hw[oy][j] * sum_k ww[ox][k] * f(x[n, hi[oy][j], wi[ox][k], :]); f = clip to [0,1]
+ * when clip01, identity otherwise.  fp32, 1 or 3 channels.  Tables: device. */
+int b200_gather2d(const b200_tensor* x, const b200_tensor* y, const int32_t* h_idx, const float* h_w, int h_taps,
+                  const int32_t* w_idx, const float* w_w, int w_taps, int clip01, void* stream);
+/* dst[dst_rows ? dst_rows[r] : r][:] = src[src_rows ? src_rows[r] : r][:] for r < n_rows (fp32 rows of
+ * row_elems elements): the shuffle buffer of make_training_patch_dataset :214-246 kept in HBM. */
+int b200_copy_rows(const float* src, const int32_t* src_rows, float* dst, const int32_t* dst_rows, int n_rows,
+                   long long row_elems, void* stream);
+
+/* ---- evaluation metrics -- train_adaptive_unet.py:144-157, 673-721; evaluate_model.py:94-163 ---
+ * b200_luma_pair: prediction clipped to [0,1]; BT.601 luma (65.481 R + 128.553 G + 24.966 B + 16)/255 of
+ * prediction (f32/bf16 [n,h,w,3]) and target (f32 [n,h,w,3]), clipped to [0,1]; `shave` border pixels
+ * dropped; writes the two fp32 planes [n][h-2s][w-2s] and the per-image sum of squared luma differences
+ * sse[n] (zeroed by the call) -> MSE(Y), PSNR(Y). */
+int b200_luma_pair(const b200_tensor* pred_rgb, const b200_tensor* hr_rgb, int shave, float* pred_y, float* hr_y,
+                   float* sse, void* stream);
+/* tf.image.ssim on single-channel fp32 planes [n][h][w] (h, w >= 11): out[n][0] = sum of the SSIM map,
+ * out[n][1] = sum of its contrast-structure factor over the (h-10)(w-10) valid window positions
+ * (zeroed by the call; divide by that count for the means tf.image.ssim / ssim_multiscale use). */
+int b200_ssim_planes(const float* a, const float* b, int n, int h, int w, float max_val, float* out, void* stream);
+/* 2x2 average pooling between MS-SSIM scales; odd extents padded symmetrically: y is [n][(h+1)/2][(w+1)/2]. */
+int b200_avgpool2_planes(const float* x, int n, int h, int w, float* y, void* stream);
 
 /* ---- utilities -------------------------------------------------------------- */
 int b200_cast(const void* src, int src_dtype, void* dst, int dst_dtype, size_t count, void* stream);
