@@ -129,7 +129,8 @@ def parse_args(argv=None) -> argparse.Namespace:
     p.add_argument("--use-train-split", action="store_true", help="Evaluate against the training split defaults instead of validation.")
     p.add_argument("--precision", choices=["fp32", "bf16"], default="fp32", help="Compute/storage precision.")
     p.add_argument("--synthetic", type=int, default=0, help="Evaluate on this many random images instead of --hr-dir.")
-    p.add_argument("--device-pipeline", action="store_true", help="Crop and degrade the evaluation patches on the GPU.")
+    p.add_argument("--host-pipeline", action="store_true",
+                   help="Crop and degrade the evaluation patches on the host with OpenCV (default: on the GPU).")
     p.add_argument("--random-init", action="store_true", help="Skip the checkpoint (smoke runs of the forward path).")
     return p.parse_args(argv)
 
@@ -156,7 +157,7 @@ def main(argv=None) -> EvalResults:
     # the offline evaluator degrades by --scale (reference :233-239), unlike training's fixed 0.5
     eval_ds, total_patches, patch_labels = make_eval_patch_dataset(hr_files, patch_size=args.patch_size, scale=args.scale,
                                                                    batch_size=args.batch_size, stride=args.eval_stride,
-                                                                   device="cuda" if args.device_pipeline else None)
+                                                                   device=None if args.host_pipeline else "cuda")
     model = load_checkpoint_model(args.model_path.expanduser() if args.model_path else None, args.scale, args.patch_size,
                                   args.depth_override, args.precision, args.random_init)
     eval_shave = infer_eval_shave(args.scale, args.eval_shave)

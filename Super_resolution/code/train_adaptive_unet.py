@@ -112,8 +112,9 @@ def train(args: argparse.Namespace) -> None:
     tr, va, te = split_indices(len(hr_paths), train_frac, args.val_split, args.test_split, args.seed)
     train_paths, val_paths, test_paths = ([hr_paths[i] for i in idx] for idx in (tr, va, te))
 
-    # crop / degrade / shuffle buffer on the GPU (same pairs, same order as the host OpenCV stream)
-    pipe_dev = "cuda" if (args.device_pipeline or os.environ.get("B200_DEVICE_PIPELINE") == "1") else None
+    # crop / degrade / shuffle buffer on the GPU (same pairs, same order as the host OpenCV stream); --host_pipeline
+    # or B200_HOST_PIPELINE=1 keeps the reference's host-side OpenCV stream
+    pipe_dev = None if (args.host_pipeline or os.environ.get("B200_HOST_PIPELINE") == "1") else "cuda"
     eval_ds = lambda paths: make_eval_patch_dataset(paths, patch_size=P, scale=DATA_LR_SHRINK,
                                                     batch_size=args.batch_size, stride=args.eval_stride, device=pipe_dev)
     train_ds, n_train = make_training_patch_dataset(train_paths, patch_size=P, patches_per_image=args.patches_per_image,
@@ -270,8 +271,9 @@ def parse_args(argv=None) -> argparse.Namespace:
     p.add_argument("--initial_epoch", type=int, default=0,
                    help="Epoch index to begin training from when resuming (must be < --epochs).")
     p.add_argument("--synthetic", type=int, default=0, help="Train on this many random images instead of a dataset.")
-    p.add_argument("--device_pipeline", action="store_true",
-                   help="Crop, degrade (INTER_AREA/INTER_CUBIC) and shuffle patches on the GPU (also B200_DEVICE_PIPELINE=1).")
+    p.add_argument("--host_pipeline", action="store_true",
+                   help="Crop / degrade / shuffle patches on the host with OpenCV as the reference does "
+                        "(default: on the GPU, same pairs in the same order; also B200_HOST_PIPELINE=1).")
     return p.parse_args(argv)
 
 

@@ -2,6 +2,8 @@
 
   * ``conv_block`` / ``build_super_resolution_unet`` / ``build_losses_and_metrics``
       /root/reference/Super_resolution/code/train_adaptive_unet.py:200-210, :217-287, :294-373
+  * ``build_vanilla_super_resolution_unet`` (the reference's second ``build_super_resolution_unet``)
+      /root/reference/Super_resolution/code/u-net-vinillia.py:128-167
   * ``seg_conv_block`` / ``build_adaptive_depth_unet``
       /root/reference/Segmenation/code/train_adaptive_unet.py:325-332, :335-362
   * ``encoder_block`` / ``decoder_block`` / ``build_unet``
@@ -76,6 +78,29 @@ def build_losses_and_metrics(loss_name: str):
         raise NotImplementedError("loss 'combined' needs downloaded VGG19 ImageNet weights (no network here); "
                                   "use 'charbonnier' or 'l1'")
     raise ValueError(f"Unknown loss '{loss_name}'. Expected one of: 'charbonnier', 'l1', 'combined'.")
+
+
+def build_vanilla_super_resolution_unet(input_shape=(256, 256, 3), base_channels: int = 64, depth: int = 4) -> Model:
+    """The fixed-depth baseline of ``u-net-vinillia.py``: BatchNorm conv blocks, MaxPool2D down, bilinear
+    UpSampling2D + Conv3x3/ReLU up, concat[up, skip], 3-channel sigmoid head (``base_channels`` / ``depth`` are
+    64 / 4 in the reference, exposed here for small test nets).  Train it with ``"mse"`` (the MSE term of its
+    ``combined`` loss; the SSIM and VGG19 terms need downloaded ImageNet weights -- out of scope)."""
+    inputs = Input(shape=tuple(input_shape), name="low_res_input")
+    x, skips, nf = inputs, [], base_channels
+    for _ in range(depth):
+        skip = seg_conv_block(x, nf)
+        skips.append((nf, skip))
+        x = L.MaxPooling2D(pool_size=(2, 2))(skip)
+        nf *= 2
+    x = seg_conv_block(x, nf)
+    for nf, skip in skips[::-1]:
+        x = L.UpSampling2D(size=(2, 2), interpolation="bilinear")(x)
+        x = L.Conv2D(nf, 3, padding="same", activation="relu")(x)
+        x = L.Concatenate()([x, skip])
+        x = seg_conv_block(x, nf)
+    outputs = L.Conv2D(3, 1, padding="same", activation="sigmoid", name="enhanced_rgb")(x)
+    h, w = input_shape[0], input_shape[1]
+    return Model(inputs, outputs, name=f"U-Net_SR_{h}x{w}")
 
 
 # --------------------------------------------------------------------------- segmentation

@@ -137,6 +137,24 @@ def seg_adaptive_spec(depth, base_channels) -> Spec:
     return b.spec
 
 
+def sr_vanilla_spec(depth=4, base_channels=64) -> Spec:
+    """``build_super_resolution_unet(input_shape)`` of Super_resolution/code/u-net-vinillia.py:128-167."""
+    b = _SpecBuilder()
+    nf, cin, chans = base_channels, 3, []
+    for _ in range(depth):
+        b.conv(cin, nf, 3); b.bn(nf); b.conv(nf, nf, 3); b.bn(nf)
+        chans.append(nf)
+        cin, nf = nf, nf * 2
+    b.conv(cin, nf, 3); b.bn(nf); b.conv(nf, nf, 3); b.bn(nf)
+    cin = nf
+    for nf in reversed(chans):
+        b.conv(cin, nf, 3)                       # post-upsample conv + ReLU (:147)
+        b.conv(2 * nf, nf, 3); b.bn(nf); b.conv(nf, nf, 3); b.bn(nf)
+        cin = nf
+    b.conv(cin, 3, 1, name="enhanced_rgb")
+    return b.spec
+
+
 def seg_vanilla_spec(depth, base_channels=32, num_classes=1) -> Spec:
     b = _SpecBuilder()
     nf, cin = base_channels, 3
@@ -290,6 +308,31 @@ def seg_adaptive_forward(ws, x, depth, training=True, rnd: Callable = _ident, ne
     x = _conv_bn_relu(x, w, rnd, training, new_stats)
     for skip in reversed(skips):
         x = rnd(K.upsample2_bilinear(x))
+        x = torch.cat([x, skip], dim=-1)
+        x = _conv_bn_relu(x, w, rnd, training, new_stats)
+        x = _conv_bn_relu(x, w, rnd, training, new_stats)
+    k, b = w.take(2)
+    w.done()
+    return torch.sigmoid(K.conv2d_same(x, k, b))
+
+
+def sr_vanilla_forward(ws, x, depth=4, training=True, rnd: Callable = _ident, new_stats=None):
+    """BatchNorm / MaxPool / bilinear-UpSampling SR U-Net with a 3-channel sigmoid head
+    (Super_resolution/code/u-net-vinillia.py:128-167): decoder = UpSampling2D -> Conv3x3+ReLU -> concat[x, skip] -> conv_block."""
+    w = _W(ws)
+    new_stats = [] if new_stats is None else new_stats
+    skips = []
+    for _ in range(depth):
+        x = _conv_bn_relu(x, w, rnd, training, new_stats)
+        x = _conv_bn_relu(x, w, rnd, training, new_stats)
+        skips.append(x)
+        x = K.max_pool2(x)
+    x = _conv_bn_relu(x, w, rnd, training, new_stats)
+    x = _conv_bn_relu(x, w, rnd, training, new_stats)
+    for skip in reversed(skips):
+        x = rnd(K.upsample2_bilinear(x))
+        k, b = w.take(2)
+        x = rnd(K.relu(K.conv2d_same(x, k, b)))
         x = torch.cat([x, skip], dim=-1)
         x = _conv_bn_relu(x, w, rnd, training, new_stats)
         x = _conv_bn_relu(x, w, rnd, training, new_stats)

@@ -34,12 +34,16 @@ def _reset():
     clear_session()
 
 
-def test_sr_trainer_and_offline_evaluator(tmp_path, capsys):
+@pytest.mark.parametrize("pipeline", ["device", "host"])
+def test_sr_trainer_and_offline_evaluator(tmp_path, capsys, pipeline):
+    """pipeline: patches cropped / degraded / shuffled on the GPU (default) or by the host OpenCV stream."""
+    host = ["--host_pipeline"] if pipeline == "host" else []
     _reset()
     tr = _load("Super_resolution/code/train_adaptive_unet.py", "train_adaptive_unet")
     args = tr.parse_args(["--scale", "0.5", "--depth_override", "2", "--patch_size", "32", "--batch_size", "4",
                           "--epochs", "2", "--patches_per_image", "2", "--synthetic", "6", "--precision", "bf16",
-                          "--model_dir", str(tmp_path / "models"), "--log_dir", str(tmp_path / "logs"), "--run_name", "t"])
+                          "--model_dir", str(tmp_path / "models"), "--log_dir", str(tmp_path / "logs"), "--run_name", "t"]
+                         + host)
     hist = tr.train(args)
     out = capsys.readouterr().out
     assert re.search(r"Epoch 2/2\n\d+/\d+ - \d+s - \d+(ms|us)/step - loss: ", out), out[-2000:]
@@ -53,7 +57,8 @@ def test_sr_trainer_and_offline_evaluator(tmp_path, capsys):
     _reset()
     ev = _load("Super_resolution/code/evaluate_model.py", "evaluate_model")
     summary = ev.main(["--model-path", str(ckpt), "--scale", "0.5", "--depth-override", "2", "--patch-size", "32",
-                       "--batch-size", "4", "--synthetic", "2", "--output-dir", str(tmp_path / "eval"), "--run-name", "e"])
+                       "--batch-size", "4", "--synthetic", "2", "--output-dir", str(tmp_path / "eval"), "--run-name", "e"]
+                      + [h.replace("_", "-") for h in host])
     rep = tmp_path / "eval" / "e"
     m = json.loads((rep / "metrics.json").read_text())
     assert set(m) == {"mse_mean", "mse_std", "psnr_mean", "psnr_std", "ssim_mean", "ssim_std", "msssim_mean",

@@ -302,3 +302,47 @@ def test_save_load_roundtrip(tmp_path):
     m2.load_weights(path)
     for a, b in zip(m1.get_weights(), m2.get_weights()):
         assert np.array_equal(a, b)
+
+
+def test_sr_vanilla_bn_unet_step():
+    """The reference's fixed-depth baseline (Super_resolution/code/u-net-vinillia.py:128-167): BatchNorm blocks, MaxPool,
+    bilinear UpSampling2D + Conv3x3/ReLU, concat[up, skip], 3-channel sigmoid head, trained on the MSE term."""
+    from b200unet import builders as B
+    from b200unet.keras import losses as LS
+    from b200unet.keras.optimizers import Adam
+    from oracle import keras_ops as K, models as M
+    _setup("float32")
+    depth, base, P, batch = 2, 64, 32, 4
+    model = B.build_vanilla_super_resolution_unet((P, P, 3), base, depth)
+    spec = M.sr_vanilla_spec(depth, base)
+    assert model.count_params() == M.param_count(spec)
+    ws_np = M.init_weights(spec, seed=11, jitter=0.05)
+    model.set_weights(ws_np)
+    model.compile(optimizer=Adam(1e-3), loss=LS.SRLoss("mse"), metrics=[LS.PSNRMetric()])
+    rng = np.random.default_rng(5)
+    hr = rng.random((batch, P, P, 3), dtype=np.float32)
+    lr = np.clip(hr + 0.05 * rng.standard_normal(hr.shape).astype(np.float32), 0, 1)
+    fwd = lambda ws, xx: M.sr_vanilla_forward(ws, xx, depth, True)
+    y_ref, l_ref, g_ref = _oracle_step(ws_np, torch.from_numpy(lr), torch.from_numpy(hr), fwd, K.mse_loss, None,
+                                       dtype=torch.float64)
+    logs = model.train_on_batch(lr, hr)
+    print(f"sr vanilla loss {logs['loss']:.7f} vs {l_ref:.7f}")
+    assert abs(logs["loss"] - l_ref) < 1e-5
+    i, bad = 0, []
+    for ly in model.layers:
+        for w in ly.weight_specs:
+            nm = w["name"].split("/", 1)[1]
+            if w["trainable"]:
+                e = relerr(model._grad(ly, nm), g_ref[i])
+                pre_bn_bias = nm == "bias" and type(ly).__name__ == "Conv2D" and ly.activation is None
+                # same bar as the BatchNorm segmentation net: BN backward is ill-conditioned in fp32
+                if not (e < 2e-2 or pre_bn_bias or g_ref[i].abs().max() < 1e-7):
+                    bad.append((w["name"], e))
+            i += 1
+    assert not bad, bad
+    _setup("mixed_bfloat16")
+    model = B.build_vanilla_super_resolution_unet((P, P, 3), base, depth)
+    model.compile(optimizer=Adam(1e-3), loss=LS.SRLoss("mse"), metrics=[LS.PSNRMetric()])
+    ls = [model.train_on_batch(lr, hr)["loss"] for _ in range(12)]
+    assert np.isfinite(ls).all() and ls[-1] < ls[0]
+    _setup("float32")
