@@ -546,11 +546,12 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
       } else if (EPI == 0 || EPI == 3) {
         // per-thread read-modify-write stores (gradient accumulation into an existing tensor)
         __nv_bfloat16* dst = p.y + (long long)img * p.ysn + (long long)oh * p.ysh + (long long)ow * p.ysw + j * p.BN;
+        const int cmax = p.Cout - j * p.BN;     // 32-channel outputs fill half of a 64-column tile
         for (int c0 = 0; c0 < p.BN; c0 += 32) {
           uint32_t v[32];
           tmem_ld32(taddr + c0, v);
           tmem_ld_wait();
-          if (valid) {
+          if (valid && c0 < cmax) {
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
               float o[8];
@@ -717,7 +718,9 @@ umma_rate_kernel(int n, int iters, int a_stride_bytes, long long* __restrict__ c
 bool conv_tc_supported(const b200_tensor* x, int cin, int cout, const b200_tensor* y, int ks) {
   if (ks != 3 && ks != 1) return false;
   if (x->dtype != B200_BF16 || y->dtype != B200_BF16) return false;
-  if (cin % 64 != 0 || cout % 64 != 0) return false;
+  // 32-channel tensors ride the 64-channel tiles: the TMA boxes are 64 channels wide and everything past the
+  // tensor's 32 is the out-of-bounds zero fill on loads and clipped on stores (half of the MMA work is padding)
+  if ((cin % 64 != 0 && cin != 32) || (cout % 64 != 0 && cout != 32)) return false;
   if (cout > 64 && cout % 128 != 0) return false;
   auto ok = [](const b200_tensor* t) {
     return ((uintptr_t)t->data % 16 == 0) && (t->stride_w * 2) % 16 == 0 && (t->stride_h * 2) % 16 == 0 &&
@@ -762,7 +765,7 @@ int conv_tc_launch(const b200_tensor* x_in, const void* wmat, int cin, int cout,
                cout);
   B200_REQUIRE(x_in->n == y_in->n && x_in->h == y_in->h && x_in->w == y_in->w && x_in->c == cin && y_in->c == cout,
                B200_ERR_BAD_ARG, "conv3x3 tcgen05: tensor shapes do not match the filter");
-  if (!ln && conv_gemm_ready(x_in, cin, cout, ks))   // deep levels (images <= 8x8): weight-streaming split-K GEMM
+  if (!ln && cin % 64 == 0 && cout % 64 == 0 && conv_gemm_ready(x_in, cin, cout, ks))   // deep levels (images <= 8x8): weight-streaming split-K GEMM
     return conv_gemm_launch(x_in, wmat, cin, cout, tap_rev, b_mn, bias, y_in, act, accumulate, ks, st);
   b200_tensor xf, yf;
   const b200_tensor *x = x_in, *y = y_in;
@@ -779,9 +782,9 @@ int conv_tc_launch(const b200_tensor* x_in, const void* wmat, int cin, int cout,
   }
   ConvTcParams p;
   p.N = y->n; p.H = y->h; p.W = y->w; p.Cout = cout;
-  p.KB = cin / 64;
-  p.BN = cout == 64 ? 64 : 128;
-  p.n_tiles = cout / p.BN;
+  p.KB = (cin + 63) / 64;
+  p.BN = cout <= 64 ? 64 : 128;
+  p.n_tiles = (cout + p.BN - 1) / p.BN;
   p.tiles_h = (p.H + TILE_H - 1) / TILE_H;
   p.tiles_w = (p.W + TILE_W - 1) / TILE_W;
   // stack several small images in one tile: image b occupies window rows [b*(H+2), (b+1)*(H+2))

@@ -165,11 +165,13 @@ wgrad3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
       float* dst = p.dw_atomic
                        ? p.dw_atomic + (((long long)tslot) * p.Cin + cb * 64 + ci) * p.Cout + ob * 64
                        : p.partial + (((long long)s * p.ntaps + tslot) * p.Cin + cb * 64 + ci) * p.Cout + ob * 64;
+      const bool live = !dup && cb * 64 + ci < p.Cin;          // 32-channel inputs fill half of the 64 rows
+      const int ncols = p.Cout - ob * 64;                      // 32-channel gradients fill half of the 64 columns
       for (int c0 = 0; c0 < 64; c0 += 32) {
         uint32_t v[32];
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(pi * 64 + c0), v);
         tmem_ld_wait();
-        if (!dup) {
+        if (live && c0 < ncols) {
           if (p.dw_atomic) {
 #pragma unroll
             for (int i = 0; i < 32; i += 4)
@@ -269,8 +271,8 @@ inline void plan(const b200_tensor* x_in, const b200_tensor* dy_in, WgradParams&
   }
   const int groups = (p.N + p.nb - 1) / p.nb;
   p.total_tiles = groups * p.tiles_h * p.tiles_w;
-  p.cblocks = p.Cin / 64;
-  p.oblocks = p.Cout / 64;
+  p.cblocks = (p.Cin + 63) / 64;
+  p.oblocks = (p.Cout + 63) / 64;
   const int pairs = p.cblocks * p.oblocks;
   int splits = (sm_count() + pairs - 1) / pairs;
   if (splits > p.total_tiles) splits = p.total_tiles;
@@ -289,7 +291,8 @@ int wgrad_small_launch(const b200_tensor* x, const b200_tensor* dy, float* out, 
 bool wgrad_tc_supported(const b200_tensor* x, const b200_tensor* dy, int ks) {
   if (ks != 3 && ks != 1) return false;
   if (x->dtype != B200_BF16 || dy->dtype != B200_BF16) return false;
-  if (x->c % 64 != 0 || dy->c % 64 != 0) return false;
+  // 32-channel tensors: the 64-channel TMA boxes zero-fill the missing half, the epilogue skips those rows / columns
+  if ((x->c % 64 != 0 && x->c != 32) || (dy->c % 64 != 0 && dy->c != 32)) return false;
   auto ok = [](const b200_tensor* t) {
     return ((uintptr_t)t->data % 16 == 0) && (t->stride_w * 2) % 16 == 0 && (t->stride_h * 2) % 16 == 0 &&
            (t->stride_n * 2) % 16 == 0;

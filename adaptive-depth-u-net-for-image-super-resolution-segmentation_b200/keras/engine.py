@@ -488,8 +488,8 @@ class Plan:
         x, y, ly = op.inputs[0], op.output, op.layer
         if getattr(op, "xcol", None) is not None:
             return True    # stem: im2col + 1x1 on the tcgen05 kernels
-        return (ly.kernel_size == (3, 3) and x.dtype == torch.bfloat16 and x.c % 64 == 0 and y.c % 64 == 0
-                and (y.c == 64 or y.c % 128 == 0))
+        return (ly.kernel_size == (3, 3) and x.dtype == torch.bfloat16 and (x.c % 64 == 0 or x.c == 32)
+                and (y.c in (32, 64) or y.c % 128 == 0))
 
     # ------------------------------------------------------------------ execution
     def run_pre(self):

@@ -181,7 +181,7 @@ class Model:
         shape = w["shape"]
         return (self._compute_dtype == torch.bfloat16 and w["trainable"] and w["name"].endswith("/kernel")
                 and len(shape) == 4 and shape[0] == 3 and shape[1] == 3 and 9 * shape[2] <= 64
-                and (shape[3] == 64 or shape[3] % 128 == 0) and type(ly).__name__ == "Conv2D"
+                and (shape[3] in (32, 64) or shape[3] % 128 == 0) and type(ly).__name__ == "Conv2D"
                 and os.environ.get("B200_STEM_SIMT", "0") != "1")
 
     def _stem_padded(self, ly):

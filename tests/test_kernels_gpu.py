@@ -127,6 +127,10 @@ TC_SHAPES = [
     (3, 5, 11, 64, 64), (5, 6, 6, 64, 64), (3, 7, 7, 64, 64), (11, 1, 6, 64, 64), (1, 2, 2, 64, 64),
     # 8-row images: two per tile with interleaved rows (pair tiles), odd batch, several tiles wide, streamed weights
     (3, 8, 8, 128, 128), (4, 8, 13, 64, 64), (5, 8, 8, 256, 256), (2, 8, 20, 128, 64),
+    # 32-channel tensors on the 64-channel tiles (TMA zero fill / clipped stores): full-size, mixed widths, pair tiles,
+    # stacked and flattened small images
+    (2, 32, 32, 32, 32), (1, 20, 13, 64, 32), (2, 16, 16, 32, 64), (2, 24, 16, 32, 128), (2, 24, 16, 128, 32),
+    (3, 8, 8, 32, 32), (9, 2, 2, 32, 32), (16, 1, 1, 32, 32), (5, 6, 6, 64, 32),
 ]
 
 
@@ -217,6 +221,36 @@ def test_conv_tc_strided_concat_and_accumulate():
     assert relerr(dx, xr.grad + f32(base)) < 1e-2
 
 
+def test_conv_tc_32_channel_slices_and_accumulate():
+    """The 32-channel level of the reference's default segmentation U-Net (base_channels=32): producers write the two
+    32-channel halves of a 64-channel concat buffer in place (the 64-wide store box is clipped at the slice's 32
+    channels), a consumer reads one half (zero-filled to 64 by the load box), dgrad accumulates into a half."""
+    ops, K = _ops(), _K()
+    dt = torch.bfloat16
+    n, h, w = 2, 24, 16
+    x = rand((n, h, w, 32), 61, dt)
+    w1 = rand((3, 3, 32, 32), 62, dt, 0.1)
+    f1 = ops.ConvFilter(w1)
+    cat = torch.full((n, h, w, 64), 3.0, dtype=dt, device="cuda")
+    ops.conv2d_fprop(x, f1, None, cat[..., 32:], ops.ACT_NONE, ops.ALGO_TCGEN05)
+    assert relerr(cat[..., 32:], K.conv2d_same(f32(x), f32(w1))) < 1e-2
+    assert torch.equal(cat[..., :32], torch.full_like(cat[..., :32], 3.0))          # the other half is untouched
+    ops.conv2d_fprop(x, f1, None, cat[..., :32], ops.ACT_RELU, ops.ALGO_TCGEN05)
+    assert relerr(cat[..., :32], torch.relu(K.conv2d_same(f32(x), f32(w1)))) < 1e-2
+    assert relerr(cat[..., 32:], K.conv2d_same(f32(x), f32(w1))) < 1e-2              # ... and so is the first one now
+    y2 = torch.empty((n, h, w, 32), dtype=dt, device="cuda")
+    ops.conv2d_fprop(cat[..., 32:], f1, None, y2, ops.ACT_NONE, ops.ALGO_TCGEN05)    # reads ONLY its half
+    assert relerr(y2, K.conv2d_same(f32(cat[..., 32:]), f32(w1))) < 1e-2
+    dy = rand((n, h, w, 32), 63, dt)
+    base = rand((n, h, w, 64), 64, dt)
+    dcat = base.clone()
+    ops.conv2d_dgrad(dy, f1, dcat[..., 32:], True, ops.ALGO_TCGEN05)                 # accumulate into a half
+    xr = f32(x).requires_grad_()
+    (K.conv2d_same(xr, f32(w1)) * f32(dy)).sum().backward()
+    assert relerr(dcat[..., 32:], xr.grad + f32(base[..., 32:])) < 1e-2
+    assert torch.equal(dcat[..., :32], base[..., :32])
+
+
 @pytest.mark.parametrize("shape", TC_SHAPES)
 def test_conv_tc_wgrad(shape):
     ops, K = _ops(), _K()
@@ -237,7 +271,8 @@ def test_conv_tc_wgrad(shape):
 
 
 @pytest.mark.parametrize("shape", [(2, 32, 32, 64, 64), (1, 20, 13, 128, 64), (3, 16, 24, 64, 128), (2, 9, 7, 128, 256),
-                                   (9, 2, 2, 64, 64), (16, 1, 1, 128, 128), (5, 6, 6, 64, 128)])
+                                   (9, 2, 2, 64, 64), (16, 1, 1, 128, 128), (5, 6, 6, 64, 128),
+                                   (2, 32, 32, 64, 32), (2, 9, 7, 32, 32), (1, 16, 24, 32, 64)])
 def test_conv1x1_tc(shape):
     """1x1 convolutions on the tcgen05 kernels (centre tap of the 3x3 machinery): fprop (+ReLU), dgrad, wgrad."""
     ops, K = _ops(), _K()
@@ -305,14 +340,14 @@ def test_conv_small_spatial_splitk(shape):
     assert relerr(dw, wr.grad) < 2e-3
 
 
-@pytest.mark.parametrize("shape", [(2, 37, 21, 3), (3, 16, 16, 3), (1, 5, 9, 7), (4, 2, 2, 3), (2, 1, 1, 3)])
+@pytest.mark.parametrize("shape", [(2, 37, 21, 3), (3, 16, 16, 3), (1, 5, 9, 7), (4, 2, 2, 3), (2, 1, 1, 3), (2, 20, 13, 3, 32)])
 @pytest.mark.parametrize("src_dtype", DTYPES)
 def test_stem_im2col_tensor_core_path(shape, src_dtype):
     """The RGB stem as im2col (64 bf16 channels) + 1x1 tcgen05 convolution with the HWIO kernel zero-padded
     to [64][Cout]: conv + LayerNorm + ReLU forward and the filter gradient against the 3x3 oracle."""
     ops, K = _ops(), _K()
-    n, h, w, ci = shape
-    co = 64
+    n, h, w, ci = shape[:4]
+    co = shape[4] if len(shape) > 4 else 64      # 32: composed conv + stand-alone LayerNorm (no fused epilogue)
     dt = torch.bfloat16
     x = rand((n, h, w, ci), 51, src_dtype)
     xb = x.to(dt)                                   # the engine feeds the stem the bf16 cast of the input
@@ -352,7 +387,8 @@ def test_stem_im2col_tensor_core_path(shape, src_dtype):
 
 
 @pytest.mark.parametrize("shape", [(2, 32, 32, 64, 64, 3), (1, 20, 13, 128, 64, 3), (3, 40, 24, 128, 128, 3), (4, 2, 2, 128, 256, 3),
-                                   (16, 1, 1, 128, 128, 3), (3, 8, 8, 128, 256, 3), (2, 16, 16, 64, 64, 1)])
+                                   (16, 1, 1, 128, 128, 3), (3, 8, 8, 128, 256, 3), (2, 16, 16, 64, 64, 1),
+                                   (2, 32, 32, 32, 32, 3), (2, 16, 16, 64, 32, 3), (2, 16, 16, 32, 64, 1)])
 def test_conv_wgrad_atomic(shape):
     """dw += wgrad through vector atomics (no workspace / reduce launch): exact accumulate semantics on a pre-filled dw."""
     ops, K = _ops(), _K()
@@ -560,7 +596,8 @@ def test_conv_transpose(dtype):
     assert relerr(y, yr) < tol and relerr(dx, xr.grad) < tol and relerr(dk, kr.grad) < tol and relerr(dbias, br.grad) < tol
 
 
-@pytest.mark.parametrize("shape", [(2, 8, 8, 128, 64), (1, 4, 6, 64, 128), (3, 1, 1, 128, 128), (2, 16, 16, 256, 128), (5, 2, 2, 64, 64)])
+@pytest.mark.parametrize("shape", [(2, 8, 8, 128, 64), (1, 4, 6, 64, 128), (3, 1, 1, 128, 128), (2, 16, 16, 256, 128), (5, 2, 2, 64, 64),
+                                   (2, 8, 8, 64, 32), (1, 4, 6, 32, 32), (2, 16, 16, 32, 64)])
 def test_conv_transpose_tensor_core(shape):
     """Conv2DTranspose(k2, s2) as four 1x1 tcgen05 convolutions over the parity views y[:, a::2, b::2, :] (fprop writes
     them, dgrad / wgrad read them), on a channel slice of a wider output buffer (concat in place)."""

@@ -346,3 +346,42 @@ def test_sr_vanilla_bn_unet_step():
     ls = [model.train_on_batch(lr, hr)["loss"] for _ in range(12)]
     assert np.isfinite(ls).all() and ls[-1] < ls[0]
     _setup("float32")
+
+
+def test_seg_vanilla_base32_bf16_on_tensor_cores():
+    """The reference's default width (base_channels=32, BASELINE config 4) under the bf16 policy: the 32-channel level
+    (stem 3->32, 32->32, 64->32, Conv2DTranspose 64->32) runs on the tcgen05 kernels through zero-filled 64-channel
+    tiles.  Loss and weight gradients against the oracle evaluated with bf16 storage rounding."""
+    from b200unet import builders as B
+    from b200unet.keras import losses as LS
+    from b200unet.keras.engine import Plan
+    from b200unet.keras.optimizers import Adam
+    from oracle import keras_ops as K, models as M
+    _setup("mixed_bfloat16")
+    depth, base, P, batch, classes = 2, 32, 32, 4, 5
+    model = B.build_unet(P, num_classes=classes, base_channels=base, depth=depth)
+    ws_np = M.init_weights(M.seg_vanilla_spec(depth, base, classes), seed=11, jitter=0.05)
+    model.set_weights(ws_np)
+    model.compile(optimizer=Adam(1e-3), loss=LS.CategoricalCrossentropy())
+    rng = np.random.default_rng(5)
+    x = rng.random((batch, P, P, 3), dtype=np.float32)
+    t = rng.integers(0, classes, (batch, P, P)).astype(np.int32)
+    tt = torch.nn.functional.one_hot(torch.from_numpy(t).long(), classes).float()
+    fwd = lambda ws, xx: M.seg_vanilla_forward(ws, M.bf16_round(xx), depth, classes, M.bf16_round)
+    y_ref, l_ref, g_ref = _oracle_step(ws_np, torch.from_numpy(x), tt, fwd, K.categorical_crossentropy, M.bf16_round)
+    logs = model.train_on_batch(x, t)
+    plan = model._train_state(batch)["plan"]
+    convs = [op for op in plan.ops if op.kind == "conv" and op.layer.kernel_size == (3, 3)]
+    assert convs and all(Plan.is_tc(op) for op in convs)          # no 3x3 convolution is left on the SIMT kernels
+    print(f"seg vanilla base32 bf16: loss {logs['loss']:.5f} vs {l_ref:.5f}")
+    assert abs(logs["loss"] - l_ref) < 2e-2 * max(1, abs(l_ref))
+    i, worst = 0, 0.0
+    for ly in model.layers:
+        for w in ly.weight_specs:
+            e = relerr(model._grad(ly, w["name"].split("/", 1)[1]), g_ref[i])
+            if g_ref[i].abs().max() >= 1e-7:
+                worst = max(worst, e)
+                assert e < 5e-2, (w["name"], e)
+            i += 1
+    print(f"   worst weight-gradient relerr {worst:.3e}")
+    _setup("float32")
