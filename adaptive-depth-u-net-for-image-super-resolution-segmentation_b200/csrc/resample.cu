@@ -335,6 +335,73 @@ maxpool2_bwd_kernel(TView x, TView y, TView dy, TView dx, int accumulate, long l
   }
 }
 
+// vector forms (C % 8 == 0, 16-byte aligned, even H and W): one thread per (output pixel, 8-channel chunk) moves the
+// 2x2 window as four 16-byte loads -- the scalar kernels above issue 2-byte accesses and three divisions per element
+template <typename T>
+__global__ void __launch_bounds__(NT)
+maxpool2_fwd_vec_kernel(TView x, TView y, long long total) {
+  const T* xp = reinterpret_cast<const T*>(x.data);
+  T* yp = reinterpret_cast<T*>(y.data);
+  const int chunks = y.c / 8;
+  for (long long i = (long long)blockIdx.x * NT + threadIdx.x; i < total; i += (long long)gridDim.x * NT) {
+    const int c = (int)(i % chunks) * 8;
+    long long p = i / chunks;
+    const int ow = (int)(p % y.w); p /= y.w;
+    const int oh = (int)(p % y.h);
+    const int n = (int)(p / y.h);
+    const T* s = xp + pix_offset(x, n, 2 * oh, 2 * ow) + c;
+    float a[8], b[8], d[8], e[8];
+    Vec8<T>::load(s, a); Vec8<T>::load(s + x.sw, b); Vec8<T>::load(s + x.sh, d); Vec8<T>::load(s + x.sh + x.sw, e);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) a[k] = fmaxf(fmaxf(a[k], b[k]), fmaxf(d[k], e[k]));
+    Vec8<T>::store(yp + pix_offset(y, n, oh, ow) + c, a);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(NT)
+maxpool2_bwd_vec_kernel(TView x, TView y, TView dy, TView dx, int accumulate, long long total) {
+  const T* xp = reinterpret_cast<const T*>(x.data);
+  const T* yp = reinterpret_cast<const T*>(y.data);
+  const T* dyp = reinterpret_cast<const T*>(dy.data);
+  T* dxp = reinterpret_cast<T*>(dx.data);
+  const int chunks = y.c / 8;
+  for (long long i = (long long)blockIdx.x * NT + threadIdx.x; i < total; i += (long long)gridDim.x * NT) {
+    const int c = (int)(i % chunks) * 8;
+    long long p = i / chunks;
+    const int ow = (int)(p % y.w); p /= y.w;
+    const int oh = (int)(p % y.h);
+    const int n = (int)(p / y.h);
+    float m[8], g[8], v[4][8];
+    Vec8<T>::load(yp + pix_offset(y, n, oh, ow) + c, m);
+    Vec8<T>::load(dyp + pix_offset(dy, n, oh, ow) + c, g);
+    const long long xo = pix_offset(x, n, 2 * oh, 2 * ow) + c;
+    Vec8<T>::load(xp + xo, v[0]); Vec8<T>::load(xp + xo + x.sw, v[1]);
+    Vec8<T>::load(xp + xo + x.sh, v[2]); Vec8<T>::load(xp + xo + x.sh + x.sw, v[3]);
+    float o[4][8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      // the gradient goes to the FIRST maximum of the window in row-major order (TF MaxPoolGrad)
+      const int first = v[0][k] == m[k] ? 0 : (v[1][k] == m[k] ? 1 : (v[2][k] == m[k] ? 2 : 3));
+#pragma unroll
+      for (int q = 0; q < 4; ++q) o[q][k] = first == q ? g[k] : 0.f;
+    }
+    const long long dO = pix_offset(dx, n, 2 * oh, 2 * ow) + c;
+    const long long offs[4] = {0, dx.sw, dx.sh, dx.sh + dx.sw};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      T* dst = dxp + dO + offs[q];
+      if (accumulate) {
+        float e[8];
+        Vec8<T>::load(dst, e);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) o[q][k] += e[k];
+      }
+      Vec8<T>::store(dst, o[q]);
+    }
+  }
+}
+
 inline int grid_for(long long items) {
   long long b = (items + NT - 1) / NT;
   long long cap = 16LL * sm_count();
@@ -523,11 +590,23 @@ int resample2d(const b200_tensor* x, const b200_tensor* y, const int32_t* hs, co
   return check_launch("resample_kernel");
 }
 
+// 8-channel vectors need 16-byte aligned pixels for bf16, 32-byte (two 16-byte halves: 16 is enough) for fp32
+static bool pool_vec_ok(const b200_tensor* t) {
+  const size_t es = dtype_size(t->dtype);
+  return t->c % 8 == 0 && reinterpret_cast<uintptr_t>(t->data) % 16 == 0 && (t->stride_w * es) % 16 == 0 &&
+         (t->stride_h * es) % 16 == 0 && (t->stride_n * es) % 16 == 0;
+}
+
 int maxpool2_fwd(const b200_tensor* x, const b200_tensor* y, cudaStream_t st) {
   B200_REQUIRE(x->n == y->n && x->c == y->c && y->h == x->h / 2 && y->w == x->w / 2 && x->dtype == y->dtype,
                B200_ERR_BAD_ARG, "maxpool2_fwd: shape mismatch");
   long long total = (long long)y->n * y->h * y->w * y->c;
   TView xv = view_of(x), yv = view_of(y);
+  if (pool_vec_ok(x) && pool_vec_ok(y)) {
+    total /= 8;
+    B200_DISPATCH_DTYPE(x->dtype, T, { maxpool2_fwd_vec_kernel<T><<<grid_for(total), NT, 0, st>>>(xv, yv, total); });
+    return check_launch("maxpool2_fwd_vec_kernel");
+  }
   B200_DISPATCH_DTYPE(x->dtype, T, { maxpool2_fwd_kernel<T><<<grid_for(total), NT, 0, st>>>(xv, yv, total); });
   return check_launch("maxpool2_fwd_kernel");
 }
@@ -538,6 +617,13 @@ int maxpool2_bwd(const b200_tensor* x, const b200_tensor* y, const b200_tensor* 
                B200_ERR_BAD_ARG, "maxpool2_bwd: shape mismatch");
   long long total = (long long)x->n * x->h * x->w * x->c;
   TView xv = view_of(x), yv = view_of(y), dyv = view_of(dy), dxv = view_of(dx);
+  if (x->h % 2 == 0 && x->w % 2 == 0 && pool_vec_ok(x) && pool_vec_ok(y) && pool_vec_ok(dy) && pool_vec_ok(dx)) {
+    const long long items = (long long)y->n * y->h * y->w * (y->c / 8);
+    B200_DISPATCH_DTYPE(x->dtype, T, {
+      maxpool2_bwd_vec_kernel<T><<<grid_for(items), NT, 0, st>>>(xv, yv, dyv, dxv, accumulate, items);
+    });
+    return check_launch("maxpool2_bwd_vec_kernel");
+  }
   B200_DISPATCH_DTYPE(x->dtype, T, {
     maxpool2_bwd_kernel<T><<<grid_for(total), NT, 0, st>>>(xv, yv, dyv, dxv, accumulate, total);
   });

@@ -212,7 +212,6 @@ def run_gpu(args):
     from b200unet import builders as B, ops
     from b200unet.keras import mixed_precision
     from b200unet.keras.optimizers import Adam
-    from oracle import models as OM   # FLOP count only (shape arithmetic)
 
     depth, scale, patch, batch, desc = CONFIGS[args.config]
     mixed_precision.set_global_policy("mixed_bfloat16")
@@ -347,15 +346,15 @@ def run_gpu(args):
         "launches_per_step": n_launch, "avg_launch_ms": t_conv / max(n_launch, 1),
         "wgrad_kernel": {"achieved": ach_wg, "frac": ach_wg / peak_tf, "ms_per_step": t_wg},
     }
-    fl_sample = OM.sr_flops_per_sample(scale, depth, patch)
-    step_tflop = 3.0 * fl_sample * batch / 1e12
+    # algorithmic FLOPs of one step: 3 x the forward FLOPs of every Conv2D of the model's own graph
+    step_tflop = 3.0 * sum(conv_flops(op, batch) for op in plan.ops if op.kind == "conv") / 1e12
     ms_per_step = total_ms / args.steps
 
     # ---- CPU baseline: the oracle, bounded sample ---------------------------------------------------
     cpu = None
     if not args.no_cpu_baseline:
-        sb = 4
-        times, cores = cpu_reference_steps(depth, scale, patch, sb, 2, 1)
+        sb = 8                                   # ~10 s of host work on the box's cores (0.7 s per batch-8 step at 16 cores)
+        times, cores = cpu_reference_steps(depth, scale, patch, sb, 12, 1)
         cpu = {"value": sb * len(times) / sum(times), "unit": "patches/s", "cores": cores, "kind": "port",
                "sample": f"{len(times)} steps of batch {sb} of the same workload shapes, torch-CPU restatement of the Keras graph"}
 

@@ -581,6 +581,38 @@ def test_maxpool(dtype, hw):
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("c", [32, 3])
+def test_maxpool_ties_slices_accumulate(dtype, c):
+    """Vector (C % 8 == 0) and scalar kernels: windows with tied maxima (gradient to the FIRST maximum, row-major, as TF's
+    MaxPoolGrad), inputs / gradients that are channel slices of wider buffers, accumulation into an existing gradient."""
+    ops, K = _ops(), _K()
+    n, h, w = 3, 12, 10
+    g = torch.Generator().manual_seed(7)
+    wide = (torch.randint(0, 3, (n, h, w, c + 8), generator=g).float() * 0.5).to(dtype).cuda()     # many ties
+    x = wide[..., 8:] if c % 8 == 0 else wide[..., :c]
+    y = torch.empty((n, h // 2, w // 2, c), dtype=dtype, device="cuda")
+    ops.maxpool2_fwd(x, y)
+    dy = rand(tuple(y.shape), 83, dtype)
+    base = rand((n, h, w, c + 8), 84, dtype)
+    dwide = base.clone()
+    dx = dwide[..., 8:] if c % 8 == 0 else dwide[..., :c]
+    ops.maxpool2_bwd(x, y, dy, dx, accumulate=True)
+    xr = f32(x).requires_grad_()
+    yr = K.max_pool2(xr)
+    (yr * f32(dy)).sum().backward()
+    assert torch.equal(f32(y), yr.detach())
+    keep = base[..., :8] if c % 8 == 0 else base[..., c:]
+    kept = dwide[..., :8] if c % 8 == 0 else dwide[..., c:]
+    assert torch.equal(kept, keep)
+    ref = xr.grad + f32(base[..., 8:] if c % 8 == 0 else base[..., :c])
+    assert relerr(dx, ref) < (1e-7 if dtype == torch.float32 else 4e-3)
+    # each window hands its gradient to exactly one element
+    dx0 = torch.empty_like(x.contiguous())
+    ops.maxpool2_bwd(x.contiguous(), y, dy, dx0)
+    assert torch.equal(f32(dx0), xr.grad)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
 def test_conv_transpose(dtype):
     ops, K = _ops(), _K()
     x = rand((2, 5, 4, 16), 91, dtype); k = rand((2, 2, 8, 16), 92, dtype, 0.3); b = rand((8,), 93, scale=0.2)
