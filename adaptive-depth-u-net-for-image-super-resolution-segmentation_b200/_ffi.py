@@ -98,8 +98,8 @@ SIGNATURES = {
     "b200_gather2d": (_i, [_TP, _TP, _vp, _vp, _i, _vp, _vp, _i, _i, _vp]),
     "b200_copy_rows": (_i, [_vp, _vp, _vp, _vp, _i, C.c_longlong, _vp]),
     "b200_luma_pair": (_i, [_TP, _TP, _i, _vp, _vp, _vp, _vp]),
-    "b200_ssim_planes": (_i, [_vp, _vp, _i, _i, _i, _f, _vp, _vp]),
-    "b200_avgpool2_planes": (_i, [_vp, _i, _i, _i, _vp, _vp]),
+    "b200_ssim_planes": (_i, [_vp, _vp, _i, _i, _i, _i, _f, _vp, _vp]),
+    "b200_avgpool2_planes": (_i, [_vp, _i, _i, _i, _i, _vp, _vp]),
     "b200_debug_umma_probe": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _vp, _vp]),
     "b200_debug_umma_rate": (_i, [_i, _i, _i, _vp, _i, _vp]),
 }

@@ -101,8 +101,8 @@ int gather2d(const b200_tensor*, const b200_tensor*, const int32_t*, const float
              int, cudaStream_t);
 int copy_rows(const float*, const int32_t*, float*, const int32_t*, int, long long, cudaStream_t);
 int luma_pair(const b200_tensor*, const b200_tensor*, int, float*, float*, float*, cudaStream_t);
-int ssim_planes(const float*, const float*, int, int, int, float, float*, cudaStream_t);
-int avgpool2_planes(const float*, int, int, int, float*, cudaStream_t);
+int ssim_planes(const float*, const float*, int, int, int, int, float, float*, cudaStream_t);
+int avgpool2_planes(const float*, int, int, int, int, float*, cudaStream_t);
 
 }  // namespace b200
 
@@ -461,14 +461,16 @@ int b200_luma_pair(const b200_tensor* pred, const b200_tensor* hr, int shave, fl
                "luma_pair: shave %d removes the full %dx%d frame", shave, pred->h, pred->w);
   return luma_pair(pred, hr, shave, pred_y, hr_y, sse, ST(s));
 }
-int b200_ssim_planes(const float* a, const float* b, int n, int h, int w, float max_val, float* out, void* s) {
-  B200_REQUIRE(a && b && out && n > 0 && n <= 65535, B200_ERR_BAD_ARG, "ssim_planes: bad argument");
+int b200_ssim_planes(const float* a, const float* b, int n, int h, int w, int channels, float max_val, float* out,
+                     void* s) {
+  B200_REQUIRE(a && b && out && n > 0 && channels > 0 && (long long)n * channels <= 65535, B200_ERR_BAD_ARG,
+               "ssim_planes: bad argument");
   B200_REQUIRE(h >= 11 && w >= 11, B200_ERR_BAD_ARG, "ssim_planes: %dx%d is smaller than the 11x11 window", h, w);
-  return ssim_planes(a, b, n, h, w, max_val, out, ST(s));
+  return ssim_planes(a, b, n, h, w, channels, max_val, out, ST(s));
 }
-int b200_avgpool2_planes(const float* x, int n, int h, int w, float* y, void* s) {
-  B200_REQUIRE(x && y && n > 0 && h > 0 && w > 0, B200_ERR_BAD_ARG, "avgpool2_planes: bad argument");
-  return avgpool2_planes(x, n, h, w, y, ST(s));
+int b200_avgpool2_planes(const float* x, int n, int h, int w, int channels, float* y, void* s) {
+  B200_REQUIRE(x && y && n > 0 && h > 0 && w > 0 && channels > 0, B200_ERR_BAD_ARG, "avgpool2_planes: bad argument");
+  return avgpool2_planes(x, n, h, w, channels, y, ST(s));
 }
 
 int b200_debug_umma_probe(const void* a, int a_rows, const void* b, int start_bytes, int sbo_bytes, int lbo_bytes,

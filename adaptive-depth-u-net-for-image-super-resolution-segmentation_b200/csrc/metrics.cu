@@ -1,8 +1,8 @@
 // Evaluation metrics of the reference's eval loops as fused reductions
 // (Super_resolution/code/train_adaptive_unet.py:144-157, 673-721; evaluate_model.py:94-163):
 //   luma_pair   : clip(pred) -> BT.601 luma of pred and hr -> border shave -> the two luma planes + per-image SSE
-//   ssim_planes : tf.image.ssim on single-channel planes (11x11 Gaussian, sigma 1.5, K1 .01, K2 .03, "valid"):
-//                 per-image sums of the SSIM map and of its contrast-structure factor (for MS-SSIM)
+//   ssim_planes : tf.image.ssim (11x11 Gaussian, sigma 1.5, K1 .01, K2 .03, "valid") per (image, channel) plane of a
+//                 channel-interleaved tensor: sums of the SSIM map and of its contrast-structure factor (for MS-SSIM)
 //   avgpool2    : the 2x2 average pooling between MS-SSIM scales (odd extents padded symmetrically, as TF does)
 // All HBM-bound: every plane is read once per kernel (plus the 10-pixel halo, which hits L2).
 #include <math.h>
@@ -66,21 +66,23 @@ constexpr int kWin = 11, kTile = 32, kIn = kTile + kWin - 1;   // 42x42 inputs p
 struct Gauss { float g[kWin]; };
 
 __global__ void __launch_bounds__(256)
-ssim_kernel(const float* __restrict__ a, const float* __restrict__ b, int h, int w, Gauss gw, float c1, float c2,
+ssim_kernel(const float* __restrict__ a, const float* __restrict__ b, int h, int w, int ch, Gauss gw, float c1, float c2,
             float* __restrict__ out) {
   __shared__ float sa[kIn][kIn + 1], sb[kIn][kIn + 1];
   __shared__ float hz[5][kIn][kTile];      // horizontally filtered a, b, a*a, b*b, a*b
   __shared__ float red[2][8];
+  // plane n = (image n / ch, channel n % ch) of a channel-interleaved [images][h][w][ch] tensor (ch = 1: plain planes)
   const int n = blockIdx.z;
   const int x0 = blockIdx.x * kTile, y0 = blockIdx.y * kTile;
-  const float* pa = a + (long long)n * h * w;
-  const float* pb = b + (long long)n * h * w;
+  const long long base = (long long)(n / ch) * h * w * ch + (n % ch);
+  const float* pa = a + base;
+  const float* pb = b + base;
   for (int i = threadIdx.x; i < kIn * kIn; i += blockDim.x) {
     const int r = i / kIn, c = i % kIn;
     const int y = y0 + r, x = x0 + c;
     const bool in = y < h && x < w;
-    sa[r][c] = in ? pa[(long long)y * w + x] : 0.0f;
-    sb[r][c] = in ? pb[(long long)y * w + x] : 0.0f;
+    sa[r][c] = in ? pa[((long long)y * w + x) * ch] : 0.0f;
+    sb[r][c] = in ? pb[((long long)y * w + x) * ch] : 0.0f;
   }
   __syncthreads();
   for (int i = threadIdx.x; i < kIn * kTile; i += blockDim.x) {
@@ -126,7 +128,7 @@ ssim_kernel(const float* __restrict__ a, const float* __restrict__ b, int h, int
   }
 }
 
-int ssim_planes(const float* a, const float* b, int n, int h, int w, float max_val, float* out, cudaStream_t st) {
+int ssim_planes(const float* a, const float* b, int n, int h, int w, int ch, float max_val, float* out, cudaStream_t st) {
   Gauss gw;
   double g[kWin], sum = 0.0;
   for (int k = 0; k < kWin; ++k) {
@@ -136,33 +138,35 @@ int ssim_planes(const float* a, const float* b, int n, int h, int w, float max_v
   }
   for (int k = 0; k < kWin; ++k) gw.g[k] = (float)(g[k] / sum);
   const float c1 = (0.01f * max_val) * (0.01f * max_val), c2 = (0.03f * max_val) * (0.03f * max_val);
-  cudaMemsetAsync(out, 0, sizeof(float) * 2 * n, st);
+  cudaMemsetAsync(out, 0, sizeof(float) * 2 * n * ch, st);
   const int vh = h - kWin + 1, vw = w - kWin + 1;
-  dim3 grid((vw + kTile - 1) / kTile, (vh + kTile - 1) / kTile, n);
-  ssim_kernel<<<grid, 256, 0, st>>>(a, b, h, w, gw, c1, c2, out);
+  dim3 grid((vw + kTile - 1) / kTile, (vh + kTile - 1) / kTile, n * ch);
+  ssim_kernel<<<grid, 256, 0, st>>>(a, b, h, w, ch, gw, c1, c2, out);
   return check_launch("ssim_kernel");
 }
 
 // ---- 2x2 average pooling between MS-SSIM scales ---------------------------------------------------
 __global__ void __launch_bounds__(256)
-avgpool2_planes_kernel(const float* __restrict__ x, int n, int h, int w, float* __restrict__ y) {
+avgpool2_planes_kernel(const float* __restrict__ x, int n, int h, int w, int ch, float* __restrict__ y) {
   const int oh = (h + 1) / 2, ow = (w + 1) / 2;
-  const long long total = (long long)n * oh * ow;
+  const long long total = (long long)n * oh * ow * ch;      // channel-interleaved [n][h][w][ch] -> [n][oh][ow][ch]
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int ox = (int)(i % ow);
-    const long long q = i / ow;
+    const int c = (int)(i % ch);
+    long long q = i / ch;
+    const int ox = (int)(q % ow); q /= ow;
     const int oy = (int)(q % oh);
-    const float* p = x + (q / oh) * (long long)h * w;
+    const float* p = x + (q / oh) * (long long)h * w * ch + c;
     const int y0 = 2 * oy, y1 = min(2 * oy + 1, h - 1), x0 = 2 * ox, x1 = min(2 * ox + 1, w - 1);   // symmetric pad
-    y[i] = (p[(long long)y0 * w + x0] + p[(long long)y0 * w + x1] + p[(long long)y1 * w + x0] + p[(long long)y1 * w + x1]) * 0.25f;
+    y[i] = (p[((long long)y0 * w + x0) * ch] + p[((long long)y0 * w + x1) * ch] + p[((long long)y1 * w + x0) * ch] +
+            p[((long long)y1 * w + x1) * ch]) * 0.25f;
   }
 }
 
-int avgpool2_planes(const float* x, int n, int h, int w, float* y, cudaStream_t st) {
-  const long long total = (long long)n * ((h + 1) / 2) * ((w + 1) / 2);
+int avgpool2_planes(const float* x, int n, int h, int w, int ch, float* y, cudaStream_t st) {
+  const long long total = (long long)n * ((h + 1) / 2) * ((w + 1) / 2) * ch;
   long long want = (total + 255) / 256;
   const int grid = (int)(want < (long long)sm_count() * 16 ? want : (long long)sm_count() * 16);
-  avgpool2_planes_kernel<<<grid, 256, 0, st>>>(x, n, h, w, y);
+  avgpool2_planes_kernel<<<grid, 256, 0, st>>>(x, n, h, w, ch, y);
   return check_launch("avgpool2_planes_kernel");
 }
 

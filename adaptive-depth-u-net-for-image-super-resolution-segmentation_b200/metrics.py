@@ -15,7 +15,7 @@ from typing import Dict
 import numpy as np
 import torch
 
-from . import ops
+from . import _ffi, ops
 
 _MS_WEIGHTS = (0.0448, 0.2856, 0.3001, 0.2363, 0.1333)
 _WIN = 11
@@ -63,47 +63,59 @@ def rgb_to_luma_bt601(image) -> torch.Tensor:
     return y[0] if single else y
 
 
-def _planes(t) -> torch.Tensor:
+def _images(t) -> torch.Tensor:
+    """(N,H,W) / (N,H,W,C) -> contiguous fp32 CUDA [N,H,W,C]."""
     t = _cuda(t, torch.float32)
-    if t.dim() == 4:
-        if t.shape[3] != 1:
-            raise ValueError("metrics operate on single-channel (luma) images")
-        t = t[..., 0]
+    if t.dim() == 3:
+        t = t[..., None]
     return t.contiguous()
 
 
 def _ssim_cs(a: torch.Tensor, b: torch.Tensor, max_val: float) -> np.ndarray:
-    """Per-image means of the SSIM map and of its contrast-structure factor: float64 numpy [n,2]."""
-    n, h, w = a.shape
-    out = torch.empty((n, 2), dtype=torch.float32, device=a.device)
+    """Per-image, per-channel means of the SSIM map and of its contrast-structure factor: float64 numpy [n,ch,2]."""
+    n, h, w, ch = a.shape
+    out = torch.empty((n * ch, 2), dtype=torch.float32, device=a.device)
     ops.ssim_planes(a, b, out, max_val)
-    return out.cpu().numpy().astype(np.float64) / float((h - _WIN + 1) * (w - _WIN + 1))
+    return out.cpu().numpy().astype(np.float64).reshape(n, ch, 2) / float((h - _WIN + 1) * (w - _WIN + 1))
 
 
 def ssim(a, b, max_val: float = 1.0) -> np.ndarray:
-    """tf.image.ssim per image (float32 numpy [n])."""
-    return _ssim_cs(_planes(a), _planes(b), max_val)[:, 0].astype(np.float32)
+    """tf.image.ssim per image (float32 numpy [n]): per-channel SSIM averaged over the channels."""
+    return _ssim_cs(_images(a), _images(b), max_val)[:, :, 0].mean(axis=1).astype(np.float32)
 
 
 def ssim_multiscale(a, b, max_val: float = 1.0) -> np.ndarray:
     """tf.image.ssim_multiscale per image; NaN when the image is too small for 5 scales (< 176 px), where TF raises."""
-    a, b = _planes(a), _planes(b)
-    n, h, w = a.shape
+    a, b = _images(a), _images(b)
+    n, h, w, ch = a.shape
     if min(h, w) < _WIN * 2 ** (len(_MS_WEIGHTS) - 1):
         return np.full((n,), np.nan, dtype=np.float32)
     factors = []
     for i in range(len(_MS_WEIGHTS)):
         sc = _ssim_cs(a, b, max_val)
-        factors.append(sc[:, 0] if i == len(_MS_WEIGHTS) - 1 else sc[:, 1])
+        factors.append(sc[:, :, 0] if i == len(_MS_WEIGHTS) - 1 else sc[:, :, 1])
         if i < len(_MS_WEIGHTS) - 1:
             h2, w2 = (a.shape[1] + 1) // 2, (a.shape[2] + 1) // 2
-            a2 = torch.empty((n, h2, w2), dtype=torch.float32, device=a.device)
+            a2 = torch.empty((n, h2, w2, ch), dtype=torch.float32, device=a.device)
             b2 = torch.empty_like(a2)
             ops.avgpool2_planes(a, a2)
             ops.avgpool2_planes(b, b2)
             a, b = a2, b2
-    f = np.maximum(np.stack(factors, axis=1), 0.0)                       # [n,5]: a few floats per image
-    return np.prod(f ** np.asarray(_MS_WEIGHTS)[None, :], axis=1).astype(np.float32)
+    f = np.maximum(np.stack(factors, axis=2), 0.0)                       # [n,ch,5]: a few floats per image
+    return np.prod(f ** np.asarray(_MS_WEIGHTS)[None, None, :], axis=2).mean(axis=1).astype(np.float32)
+
+
+def psnr_rgb(a, b, max_val: float = 1.0) -> np.ndarray:
+    """tf.image.psnr per image over all channels (u-net-vinillia.py:226): the SR-loss kernel's squared-error sum."""
+    a, b = _images(a), _images(b)
+    n = a.shape[0]
+    out = np.empty((n,), dtype=np.float32)
+    res = torch.empty((2,), dtype=torch.float32, device=a.device)
+    ws = torch.empty((2 + n,), dtype=torch.float32, device=a.device)
+    for i in range(n):      # the loss kernel reduces a whole tensor: one launch per image (evaluation only)
+        ops.sr_loss(a[i:i + 1], b[i:i + 1], _ffi.LOSS_MSE, 0.0, 1.0, res, None, ws)
+        out[i] = 10.0 * np.log10(max_val * max_val / max(float(res[0]), 1e-30))
+    return out
 
 
 def eval_luma_metrics(pred_rgb, hr_rgb, shave: int = 0) -> Dict[str, np.ndarray]:

@@ -373,14 +373,15 @@ def luma_pair(pred, hr, shave, pred_y, hr_y, sse):
 
 
 def ssim_planes(a, b, out, max_val: float = 1.0):
-    n, h, w = a.shape
-    check(lib().b200_ssim_planes(_ptr(a), _ptr(b), n, h, w, float(max_val), _ptr(out), _stream()), "ssim_planes")
+    """a, b: contiguous fp32 [n,h,w,ch]; out: fp32 [n*ch, 2] (sums of the SSIM / contrast-structure maps per plane)."""
+    n, h, w, ch = a.shape
+    check(lib().b200_ssim_planes(_ptr(a), _ptr(b), n, h, w, ch, float(max_val), _ptr(out), _stream()), "ssim_planes")
     return out
 
 
 def avgpool2_planes(x, y):
-    n, h, w = x.shape
-    check(lib().b200_avgpool2_planes(_ptr(x), n, h, w, _ptr(y), _stream()), "avgpool2_planes")
+    n, h, w, ch = x.shape
+    check(lib().b200_avgpool2_planes(_ptr(x), n, h, w, ch, _ptr(y), _stream()), "avgpool2_planes")
     return y
 
 

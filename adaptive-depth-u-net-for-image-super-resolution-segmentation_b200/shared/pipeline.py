@@ -27,6 +27,18 @@ def sorted_alphanumeric(items: Iterable[str]) -> List[str]:
     return sorted(items, key=key)
 
 
+def load_image_stack(directory, size: int, limit: Optional[int] = None) -> np.ndarray:
+    """All images of a directory (natural order), INTER_AREA-resized to size x size, float32 RGB in [0, 1]: (N, size, size, 3)."""
+    directory = Path(directory)
+    names = sorted_alphanumeric([p.name for p in directory.iterdir() if p.is_file()])
+    if limit is not None:
+        names = names[:limit]
+    images = [load_rgb_image(directory / name, size) for name in names]
+    if not images:
+        raise ValueError(f"No images found in {directory}")
+    return np.stack(images, axis=0)
+
+
 def load_rgb_image_full(path) -> np.ndarray:
     """Decode an image file to float32 RGB in [0, 1] at its native size."""
     cv2 = _cv2()
@@ -37,9 +49,14 @@ def load_rgb_image_full(path) -> np.ndarray:
 
 
 def load_rgb_image(path, size: int) -> np.ndarray:
+    """Decode, INTER_AREA-resize the uint8 image to size x size (rounded to integers, as the reference does: the resize
+    comes BEFORE the float conversion, pipeline.py:60-67), then scale to [0, 1]."""
     cv2 = _cv2()
-    img = load_rgb_image_full(path)
-    return cv2.resize(img, (size, size), interpolation=cv2.INTER_AREA)
+    bgr = cv2.imread(str(path), cv2.IMREAD_COLOR)
+    if bgr is None:
+        raise FileNotFoundError(f"Unable to read image: {path}")
+    rgb = cv2.resize(cv2.cvtColor(bgr, cv2.COLOR_BGR2RGB), (size, size), interpolation=cv2.INTER_AREA)
+    return rgb.astype(np.float32) / 255.0
 
 
 def degrade_image(image: np.ndarray, scale: float, output_size: int) -> np.ndarray:

@@ -261,12 +261,15 @@ int b200_copy_rows(const float* src, const int32_t* src_rows, float* dst, const 
  * sse[n] (zeroed by the call) -> MSE(Y), PSNR(Y). */
 int b200_luma_pair(const b200_tensor* pred_rgb, const b200_tensor* hr_rgb, int shave, float* pred_y, float* hr_y,
                    float* sse, void* stream);
-/* tf.image.ssim on single-channel fp32 planes [n][h][w] (h, w >= 11): out[n][0] = sum of the SSIM map,
- * out[n][1] = sum of its contrast-structure factor over the (h-10)(w-10) valid window positions
- * (zeroed by the call; divide by that count for the means tf.image.ssim / ssim_multiscale use). */
-int b200_ssim_planes(const float* a, const float* b, int n, int h, int w, float max_val, float* out, void* stream);
-/* 2x2 average pooling between MS-SSIM scales; odd extents padded symmetrically: y is [n][(h+1)/2][(w+1)/2]. */
-int b200_avgpool2_planes(const float* x, int n, int h, int w, float* y, void* stream);
+/* tf.image.ssim on fp32 images [n][h][w][channels] (h, w >= 11; channels = 1 for the luma planes, 3 for the RGB
+ * evaluation of u-net-vinillia.py:222-230), every channel filtered on its own as TF's depthwise filter does:
+ * out[n*channels + c][0] = sum of the SSIM map, [1] = sum of its contrast-structure factor over the
+ * (h-10)(w-10) valid window positions (zeroed by the call; divide by that count for the per-channel means,
+ * average those over the channels for tf.image.ssim). */
+int b200_ssim_planes(const float* a, const float* b, int n, int h, int w, int channels, float max_val, float* out,
+                     void* stream);
+/* 2x2 average pooling between MS-SSIM scales; odd extents padded symmetrically: y is [n][(h+1)/2][(w+1)/2][channels]. */
+int b200_avgpool2_planes(const float* x, int n, int h, int w, int channels, float* y, void* stream);
 
 /* ---- utilities -------------------------------------------------------------- */
 int b200_cast(const void* src, int src_dtype, void* dst, int dst_dtype, size_t count, void* stream);

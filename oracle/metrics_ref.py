@@ -46,7 +46,7 @@ def _gauss(size=11, sigma=1.5, device="cpu", dtype=torch.float32):
 
 
 def _ssim_cs(a, b, max_val=1.0):
-    """a, b: (N,H,W,C).  Returns per-image (ssim, cs)."""
+    """a, b: (N,H,W,C).  Returns per-image, per-channel (ssim, cs) of shape (N,C) (tf _ssim_per_channel)."""
     a, b = _fp(a).permute(0, 3, 1, 2), _fp(b).permute(0, 3, 1, 2)
     c = a.shape[1]
     k = _gauss(device=a.device, dtype=a.dtype).expand(c, 1, 11, 11)
@@ -56,11 +56,12 @@ def _ssim_cs(a, b, max_val=1.0):
     c1, c2 = (0.01 * max_val) ** 2, (0.03 * max_val) ** 2
     cs = (2 * cov + c2) / (var_a + var_b + c2)
     lum = (2 * mu_a * mu_b + c1) / (mu_a * mu_a + mu_b * mu_b + c1)
-    return (lum * cs).mean(dim=(1, 2, 3)), cs.mean(dim=(1, 2, 3))
+    return (lum * cs).mean(dim=(2, 3)), cs.mean(dim=(2, 3))
 
 
 def ssim(a, b, max_val=1.0):
-    return _ssim_cs(a, b, max_val)[0]
+    """tf.image.ssim: the per-channel SSIM averaged over the channels."""
+    return _ssim_cs(a, b, max_val)[0].mean(dim=1)
 
 
 def ssim_multiscale(a, b, max_val=1.0):
@@ -74,7 +75,7 @@ def ssim_multiscale(a, b, max_val=1.0):
         vals.append(torch.relu(s if i == len(_MS_WEIGHTS) - 1 else cs) ** w)
         if i < len(_MS_WEIGHTS) - 1:
             a, b = _pool2(a), _pool2(b)
-    return torch.stack(vals, dim=0).prod(dim=0)
+    return torch.stack(vals, dim=0).prod(dim=0).mean(dim=1)     # product over scales per channel, then channel mean
 
 
 def _pool2(t):

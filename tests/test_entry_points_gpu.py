@@ -8,6 +8,7 @@ import os
 import re
 import sys
 
+import numpy as np
 import pytest
 
 pytestmark = pytest.mark.gpu
@@ -100,3 +101,23 @@ def test_seg_vanilla_trainer(tmp_path, num_classes):
     hist = tr.train(args)
     assert len(hist.history["loss"]) == 2 and hist.history["loss"][-1] == hist.history["loss"][-1]   # not NaN
     assert (tmp_path / "m" / "v_final.keras").exists()
+
+
+def test_sr_vanilla_baseline_trainer(tmp_path, capsys):
+    """Super_resolution/code/u-net-vinillia.py: BatchNorm baseline, whole-image stacks, RGB PSNR / SSIM / MS-SSIM evaluation."""
+    _reset()
+    mod = _load("Super_resolution/code/u-net-vinillia.py", "sr_unet_vanilla")
+    args = mod.parse_args(["--synthetic", "10", "--hr_size", "192", "--batch_size", "2", "--epochs", "2", "--precision", "bf16",
+                           "--model_dir", str(tmp_path / "m")])
+    hist, res = mod.main(args)
+    out = capsys.readouterr().out
+    assert "Validation metrics:" in out and "Test metrics:" in out
+    assert len(hist.history["loss"]) == 2 and "val_psnr" in hist.history
+    assert (tmp_path / "m" / "unet_vanilla_best.keras").exists()
+    for split in ("validation", "test"):
+        m = res[split]
+        assert set(m) == {"psnr", "ssim", "ms_ssim"} and all(np.isfinite(v[0]) for v in m.values())
+        assert 0.0 < m["ssim"][0] <= 1.0 and 0.0 < m["ms_ssim"][0] <= 1.0
+    with pytest.raises(NotImplementedError):
+        mod.main(mod.parse_args(["--synthetic", "4", "--loss", "combined"]))
+    _reset()

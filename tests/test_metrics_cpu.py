@@ -74,7 +74,7 @@ def test_ssim_oracle_vs_numpy(h, w):
     ta, tb = torch.from_numpy(a)[None, :, :, None], torch.from_numpy(b)[None, :, :, None]    # float64
     s, cs = MR._ssim_cs(ta, tb)
     ns, ncs = _np_ssim_cs(a, b)
-    assert abs(s.item() - ns) < 1e-10 and abs(cs.item() - ncs) < 1e-10
+    assert tuple(s.shape) == (1, 1) and abs(s.item() - ns) < 1e-10 and abs(cs.item() - ncs) < 1e-10
     assert abs(MR.ssim(ta.float(), tb.float()).item() - ns) < 2e-4       # fp32 evaluation (cancellation in E[x^2]-E[x]^2)
     assert abs(MR.ssim(ta, ta).item() - 1.0) < 1e-12
 
@@ -85,6 +85,19 @@ def test_msssim_oracle_vs_numpy(h, w):
     ta, tb = torch.from_numpy(a)[None, :, :, None], torch.from_numpy(b)[None, :, :, None]
     assert abs(MR.ssim_multiscale(ta, tb).item() - _np_msssim(a, b)) < 1e-10
     assert torch.isnan(MR.ssim_multiscale(ta[:, :175], tb[:, :175])).all()   # < 11 * 2^4 pixels: TF raises
+
+
+def test_multichannel_is_per_channel_then_mean():
+    """tf.image.ssim / ssim_multiscale on RGB (u-net-vinillia.py:222-230): every channel on its own, then the channel mean
+    (for MS-SSIM the product over scales is taken per channel first)."""
+    a0, b0 = _pair(180, 190, 1)
+    a1, b1 = _pair(180, 190, 2, noise=0.2)
+    ta = torch.from_numpy(np.stack([a0, a1], -1))[None]
+    tb = torch.from_numpy(np.stack([b0, b1], -1))[None]
+    want = 0.5 * (_np_ssim_cs(a0, b0)[0] + _np_ssim_cs(a1, b1)[0])
+    assert abs(MR.ssim(ta, tb).item() - want) < 1e-10
+    want = 0.5 * (_np_msssim(a0, b0) + _np_msssim(a1, b1))
+    assert abs(MR.ssim_multiscale(ta, tb).item() - want) < 1e-10
 
 
 def test_product_metrics_need_a_gpu():

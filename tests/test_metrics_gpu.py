@@ -68,6 +68,18 @@ def test_msssim_vs_oracle(h, w):
     assert np.isnan(MT.ssim_multiscale(t[:, :175].float().cuda(), p[:, :175].float().cuda())).all()
 
 
+def test_rgb_metrics_vs_oracle():
+    """The vanilla baseline evaluates on RGB (u-net-vinillia.py:222-230): channel-interleaved tensors go through the same
+    kernels, one plane per (image, channel)."""
+    from b200unet import metrics as MT
+    from oracle import metrics_ref as MR
+    pred, hr = _rgb_pair(2, 181, 190, 3)
+    pred = pred.clamp(0, 1)
+    assert np.abs(MT.ssim(hr.cuda(), pred.cuda()) - MR.ssim(hr.double(), pred.double()).numpy()).max() <= 2e-4
+    assert np.abs(MT.ssim_multiscale(hr.cuda(), pred.cuda()) - MR.ssim_multiscale(hr.double(), pred.double()).numpy()).max() <= 2e-4
+    assert np.abs(MT.psnr_rgb(hr.cuda(), pred.cuda()) - MR.psnr(hr.double(), pred.double()).numpy()).max() <= 1e-3
+
+
 def test_eval_luma_metrics_full_size():
     """One eval-loop iteration at the reference's evaluation patch size (256x256, shave 4, batch 8)."""
     from b200unet import metrics as MT

@@ -129,3 +129,55 @@ def test_device_dataset_needs_a_gpu():
     from b200unet.shared import pipeline as PL
     with pytest.raises(_ffi.B200Error):
         PL.make_training_patch_dataset(["x.png"], 32, 2, 0.5, 4, 0, device="cuda")
+
+
+REF_PIPELINE = "/root/reference/shared/pipeline.py"
+
+
+@pytest.mark.skipif(not os.path.exists(REF_PIPELINE), reason="reference checkout not present (build container only)")
+def test_host_mirror_equals_the_reference_functions(tmp_path):
+    """With the reference checkout at hand, run ITS pipeline functions (behind an empty tensorflow stub: the module only
+    needs TF for the tf.data wrappers) next to the host mirror on the same files: identical arrays, identical order."""
+    cv2 = pytest.importorskip("cv2")
+    import importlib.util
+    import sys
+    import types
+    from b200unet.shared import pipeline as PL
+    stub = types.ModuleType("tensorflow")
+    stub.data = types.SimpleNamespace(Dataset=object, AUTOTUNE=-1)
+    had = sys.modules.get("tensorflow")
+    sys.modules["tensorflow"] = stub
+    try:
+        spec = importlib.util.spec_from_file_location("ref_pipeline", REF_PIPELINE)
+        ref = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(ref)
+    finally:
+        if had is None:
+            sys.modules.pop("tensorflow", None)
+        else:
+            sys.modules["tensorflow"] = had
+    rng = np.random.default_rng(0)
+    files = []
+    for i in (1, 2, 10):
+        path = str(tmp_path / f"im{i}.png")
+        cv2.imwrite(path, rng.integers(0, 256, (50 + i, 70, 3), dtype=np.uint8))
+        files.append(path)
+    assert np.array_equal(ref.load_image_stack(tmp_path, 32), PL.load_image_stack(tmp_path, 32))
+    assert np.array_equal(ref.load_rgb_image(files[1], 24), PL.load_rgb_image(files[1], 24))
+    full = ref.load_rgb_image_full(files[2])
+    assert np.array_equal(full, PL.load_rgb_image_full(files[2]))
+    assert np.array_equal(PL.load_rgb_image_u8(files[2]).astype(np.float32) / 255.0, full)
+    names = ["a10", "a2", "B1", "a1", "img_007x", "img_7y"]
+    assert ref.sorted_alphanumeric(names) == PL.sorted_alphanumeric(names)
+    assert np.array_equal(ref.degrade_image(full[:48, :48], 0.5, 48), PL.degrade_image(full[:48, :48], 0.5, 48))
+    assert np.array_equal(ref.random_patches(full, 32, 5, rng=np.random.default_rng(4)),
+                          PL.random_patches(full, 32, 5, rng=np.random.default_rng(4)))
+    assert np.array_equal(ref.grid_patches(full, 32, stride=20), PL.grid_patches(full, 32, stride=20))
+    # the generators behind the tf.data wrappers: same (lr, hr) pairs in the same order
+    want = ref._iter_random_patch_pairs(files, 32, 2, 0.5, seed=3)
+    got = PL._random_pairs(files, 32, 2, 0.5, 3)
+    for _ in range(8):
+        (wl, wh), (gl, gh) = next(want), next(got)
+        assert np.array_equal(wl, gl) and np.array_equal(wh, gh)
+    for (wl, wh), (gl, gh) in zip(ref._iter_grid_patch_pairs(files, 32, 20, 0.5), PL._grid_pairs(files, 32, 20, 0.5)):
+        assert np.array_equal(wl, gl) and np.array_equal(wh, gh)

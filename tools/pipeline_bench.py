@@ -65,10 +65,11 @@ def main():
     hy, sse, out = torch.empty_like(py), torch.empty(n, device="cuda"), torch.empty((n, 2), device="cuda")
     ms = timed(lambda: ops.luma_pair(pred, tgt, 4, py, hy, sse), flush)
     rows.append(("luma_pair_kernel", f"{n}x{h}x{h} bf16 pred + f32 target, shave 4", n * (h - 8) ** 2 * (6 + 12 + 8), ms))
-    ms = timed(lambda: ops.ssim_planes(py, hy, out), flush)
+    py4, hy4 = py[..., None], hy[..., None]
+    ms = timed(lambda: ops.ssim_planes(py4, hy4, out), flush)
     rows.append(("ssim_kernel", f"{n} planes of {h - 8}x{h - 8}", 2 * 4 * n * (h - 8) ** 2, ms))
-    p2 = torch.empty((n, (h - 7) // 2, (h - 7) // 2), dtype=torch.float32, device="cuda")
-    ms = timed(lambda: ops.avgpool2_planes(py, p2), flush)
+    p2 = torch.empty((n, (h - 7) // 2, (h - 7) // 2, 1), dtype=torch.float32, device="cuda")
+    ms = timed(lambda: ops.avgpool2_planes(py4, p2), flush)
     rows.append(("avgpool2_planes_kernel", f"{n} planes", 4 * n * ((h - 8) ** 2 + p2.shape[1] ** 2), ms))
     for name, what, nbytes, ms in rows:
         gbps = nbytes / (ms * 1e-3) / 1e9
