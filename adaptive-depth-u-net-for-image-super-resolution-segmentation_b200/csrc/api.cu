@@ -94,6 +94,10 @@ int scale_inplace(float*, size_t, float, cudaStream_t);
 int convT2_fprop(const b200_tensor*, const void*, const float*, int, const b200_tensor*, cudaStream_t);
 int convT2_dgrad(const b200_tensor*, const void*, int, const b200_tensor*, cudaStream_t);
 int convT2_wgrad(const b200_tensor*, const b200_tensor*, float*, float*, cudaStream_t);
+bool head_mid_supported(const b200_tensor*, const b200_tensor*, int);
+int head_mid_fprop(const b200_tensor*, const void*, const float*, const b200_tensor*, int, cudaStream_t);
+int head_mid_dgrad(const b200_tensor*, const void*, const b200_tensor*, int, cudaStream_t);
+int head_mid_wgrad(const b200_tensor*, const b200_tensor*, float*, cudaStream_t);
 int cv_resize_taps(int, int, int);
 int cv_resize_plan(int, int, int, int32_t*, float*, int);
 int patch_extract(const void*, int, int, int, const int32_t*, const b200_tensor*, cudaStream_t);
@@ -150,6 +154,7 @@ int b200_conv2d_fprop(const b200_tensor* x, const b200_filter* f, const float* b
   if (algo == B200_ALGO_AUTO && f->dtype == x->dtype && f->kh == f->kw) {
     if (stem_supported(x, y, f->kh) && act != B200_ACT_SIGMOID) return stem_fprop(x, f->hwio, bias, y, act, ST(stream));
     if (head_supported(x, y, f->kh)) return head_fprop(x, f->hwio, bias, y, act, ST(stream));
+    if (head_mid_supported(x, y, f->kh)) return head_mid_fprop(x, f->hwio, bias, y, act, ST(stream));
   }
   return conv_simt_fprop(x, f, bias, y, act, 0, false, ST(stream));
 }
@@ -194,6 +199,8 @@ int b200_conv2d_dgrad(const b200_tensor* dy, const b200_filter* f, const b200_te
   }
   if (algo == B200_ALGO_AUTO && f->dtype == dx->dtype && f->kh == f->kw && head_supported(dx, dy, f->kh))
     return head_dgrad(dy, f->hwio, dx, accumulate, ST(stream));
+  if (algo == B200_ALGO_AUTO && f->dtype == dx->dtype && f->kh == f->kw && head_mid_supported(dx, dy, f->kh))
+    return head_mid_dgrad(dy, f->hwio, dx, accumulate, ST(stream));
   return conv_simt_fprop(dy, f, nullptr, dx, B200_ACT_NONE, accumulate, true, ST(stream));
 }
 
@@ -231,6 +238,7 @@ int b200_conv2d_wgrad(const b200_tensor* x, const b200_tensor* dy, int kh, int k
   if (algo == B200_ALGO_AUTO) {
     if (stem_supported(x, dy, kh)) return stem_wgrad(x, dy, dw, ST(stream));
     if (head_supported(x, dy, kh)) return head_wgrad(x, dy, dw, ST(stream));
+    if (head_mid_supported(x, dy, kh)) return head_mid_wgrad(x, dy, dw, ST(stream));
   }
   return conv_simt_wgrad(x, dy, kh, dw, ST(stream));
 }

@@ -50,9 +50,13 @@ def test_conv_simt(dtype, shape):
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
-@pytest.mark.parametrize("shape", [(2, 37, 21, 3, 64, 3), (1, 16, 16, 3, 32, 3), (2, 19, 23, 64, 3, 1), (3, 9, 7, 64, 1, 1), (1, 8, 8, 128, 3, 1)])
+@pytest.mark.parametrize("shape", [(2, 37, 21, 3, 64, 3), (1, 16, 16, 3, 32, 3), (2, 19, 23, 64, 3, 1), (3, 9, 7, 64, 1, 1), (1, 8, 8, 128, 3, 1),
+                                   # multi-class heads (4 <= Cout <= 32 from 32 / 64 channels): ragged pixel counts, odd Cout
+                                   (2, 19, 23, 32, 21, 1), (1, 5, 5, 32, 21, 1), (1, 16, 16, 64, 5, 1), (3, 9, 7, 64, 24, 1),
+                                   (2, 8, 8, 32, 4, 1), (2, 32, 32, 64, 21, 1)])
 def test_conv_small_specialised(dtype, shape):
-    """ALGO_AUTO routes the RGB stem (Cin=3) and the Cout<=3 1x1 heads to the specialised SIMT kernels."""
+    """ALGO_AUTO routes the RGB stem (Cin=3), the Cout<=3 1x1 heads and the multi-class 1x1 heads to the specialised SIMT
+    kernels."""
     ops, K = _ops(), _K()
     n, h, w, ci, co, ks = shape
     x = rand((n, h, w, ci), 1, dtype)
