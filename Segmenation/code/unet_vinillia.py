@@ -78,7 +78,7 @@ def train(args: argparse.Namespace):
     from b200unet import builders as B
     from b200unet.keras import mixed_precision, set_random_seed
     from b200unet.keras.callbacks import EarlyStopping, ModelCheckpoint, ReduceLROnPlateau
-    from b200unet.keras.losses import BinaryCrossentropy, CategoricalCrossentropy, dice_metric
+    from b200unet.keras.losses import BinaryCrossentropy, CategoricalCrossentropy, global_dice_metric
     from b200unet.keras.optimizers import Adam
 
     precision = "bf16" if (args.mixed_precision or args.precision == "bf16") else "fp32"
@@ -89,8 +89,8 @@ def train(args: argparse.Namespace):
     model = B.build_unet(args.image_size, num_classes=args.num_classes, base_channels=args.base_channels, depth=args.depth)
     binary = args.num_classes == 1
     model.compile(optimizer=Adam(learning_rate=args.learning_rate),
-                  loss=BinaryCrossentropy() if binary else CategoricalCrossentropy(),
-                  metrics=[dice_metric] if binary else [])
+                  loss=BinaryCrossentropy(global_dice=True) if binary else CategoricalCrossentropy(),
+                  metrics=[global_dice_metric] if binary else [])      # :94-99: Dice as one ratio over the batch
     args.model_dir.mkdir(parents=True, exist_ok=True)
     checkpoint_path = args.model_dir / f"{args.run_name}_best.keras"
     print(f"Checkpoints will be written to {checkpoint_path}")

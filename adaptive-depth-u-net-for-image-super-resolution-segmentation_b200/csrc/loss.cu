@@ -148,16 +148,18 @@ __global__ void bce_dice_finalize_kernel(const float* __restrict__ ws, int n, fl
                                          float* out) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   const float smooth = 1e-6f;
-  float dice = 0.f, iou = 0.f;
+  float dice = 0.f, iou = 0.f, isum = 0.f, usum = 0.f;
   for (int i = 0; i < n; ++i) {
     float I = ws[1 + 3 * i], U = ws[2 + 3 * i];
     dice += (2.f * I + smooth) / (U + smooth);
     iou += (I + smooth) / (U - I + smooth);
+    isum += I; usum += U;
   }
   dice /= (float)n; iou /= (float)n;
   float bce = ws[0] / total;
   out[0] = bw * bce + dw * (1.f - dice);
   out[1] = bce; out[2] = dice; out[3] = iou;
+  out[4] = (2.f * isum + smooth) / (usum + smooth);   // unet_vinillia.py:94-99: ONE ratio over the whole batch
 }
 
 template <typename TP, typename TT>

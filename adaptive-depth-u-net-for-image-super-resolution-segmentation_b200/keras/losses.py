@@ -27,7 +27,7 @@ class _PlanLoss:
 
     def make_state(self, plan):
         ov = plan.output_val
-        st = {"out": torch.zeros(4, dtype=torch.float32, device=plan.dev),
+        st = {"out": torch.zeros(8, dtype=torch.float32, device=plan.dev),
               "target": torch.zeros((plan.batch,) + self._target_shape(ov), dtype=self.target_dtype, device=plan.dev)}
         self._more_state(plan, st)
         return st
@@ -95,9 +95,11 @@ class BceDiceLoss(_PlanLoss):
     metric_names = ("dice", "iou")
     metric_slots = (2, 3)
 
-    def __init__(self, bce_weight=1.0, dice_weight=0.0, name="bce_dice"):
+    def __init__(self, bce_weight=1.0, dice_weight=0.0, name="bce_dice", global_dice=False):
         self.bw, self.dw = float(bce_weight), float(dice_weight)
         self.__name__ = name
+        if global_dice:      # the baseline trainer's metric: one Dice ratio over the whole batch (unet_vinillia.py:94-99)
+            self.metric_slots = (4, 3)
 
     def _more_state(self, plan, st):
         st["ws"] = torch.zeros(1 + 3 * plan.batch, dtype=torch.float32, device=plan.dev)
@@ -108,15 +110,15 @@ class BceDiceLoss(_PlanLoss):
                           ov.grad if with_grad else None, st["ws"])
 
     def __call__(self, y_true, y_pred):
-        out = torch.zeros(4, device=y_pred.device)
+        out = torch.zeros(8, device=y_pred.device)
         ws = torch.zeros(1 + 3 * y_pred.shape[0], device=y_pred.device)
         ops.bce_dice_loss(y_pred.contiguous(), y_true.to(y_pred.device).float().contiguous(), self.bw, self.dw, 1.0, out,
                           None, ws)
         return out[0]
 
 
-def BinaryCrossentropy():
-    return BceDiceLoss(1.0, 0.0, name="binary_crossentropy")
+def BinaryCrossentropy(global_dice=False):
+    return BceDiceLoss(1.0, 0.0, name="binary_crossentropy", global_dice=global_dice)
 
 
 class CategoricalCrossentropy(_PlanLoss):
@@ -179,11 +181,12 @@ class _SegMetric:
         self.slot, self.__name__ = slot, name
 
     def __call__(self, y_true, y_pred):
-        out = torch.zeros(4, device=y_pred.device)
+        out = torch.zeros(8, device=y_pred.device)
         ws = torch.zeros(1 + 3 * y_pred.shape[0], device=y_pred.device)
         ops.bce_dice_loss(y_pred.contiguous(), y_true.to(y_pred.device).float().contiguous(), 1.0, 0.0, 1.0, out, None, ws)
         return out[self.slot]
 
 
-dice_metric = _SegMetric(2, "dice")
+dice_metric = _SegMetric(2, "dice")                 # per-sample ratios averaged (Segmenation/code/train_adaptive_unet.py:258-265)
 iou_metric = _SegMetric(3, "iou")
+global_dice_metric = _SegMetric(4, "dice")          # one ratio over the batch (Segmenation/code/unet_vinillia.py:94-99)

@@ -209,7 +209,8 @@ int b200_sr_loss(const b200_tensor* pred, const b200_tensor* target, int kind, f
                  float* out, const b200_tensor* dpred, float* ws, void* stream);
 
 /* ---- BCE + Dice (+IoU) on probabilities -- seg :258-304 ---------------------
- * out[0]=loss, out[1]=bce, out[2]=dice, out[3]=iou.  ws: fp32 [1 + 3*n], zeroed by the call. */
+ * out (fp32 [5]): [0]=loss, [1]=bce, [2]=dice (per-sample ratios averaged, seg :258-265), [3]=iou (:272-280),
+ * [4]=dice as ONE ratio over the whole batch (unet_vinillia.py:94-99).  ws: fp32 [1 + 3*n], zeroed by the call. */
 int b200_bce_dice_loss(const b200_tensor* pred, const b200_tensor* target, float bce_weight,
                        float dice_weight, float grad_scale, float* out, const b200_tensor* dpred, float* ws,
                        void* stream);

@@ -193,6 +193,11 @@ def dice_coefficient(y_true, y_pred, smooth=1e-6):
     return ((2.0 * inter + smooth) / (union + smooth)).mean()
 
 
+def dice_coefficient_global(y_true, y_pred, smooth=1e-6):
+    """The baseline trainer's Dice: ONE ratio over the whole batch, no clipping.  Segmenation/code/unet_vinillia.py:94-99."""
+    return (2.0 * (y_true * y_pred).sum() + smooth) / ((y_true + y_pred).sum() + smooth)
+
+
 def iou_score(y_true, y_pred, smooth=1e-6):
     """Segmenation/code/train_adaptive_unet.py:272-280."""
     p = torch.clamp(y_pred, _EPS7, 1.0 - _EPS7)

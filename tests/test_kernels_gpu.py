@@ -694,7 +694,7 @@ def test_bce_dice(dtype):
     ops, K = _ops(), _K()
     pred = torch.sigmoid(3 * rand((3, 8, 8, 1), 121)).to(dtype)
     tgt = (rand((3, 8, 8, 1), 122) > 0).float()
-    out = torch.zeros(4, device="cuda"); ws = torch.zeros(1 + 9, device="cuda"); dp = torch.empty_like(pred)
+    out = torch.zeros(5, device="cuda"); ws = torch.zeros(1 + 9, device="cuda"); dp = torch.empty_like(pred)
     ops.bce_dice_loss(pred, tgt, 0.4, 0.6, 1.0, out, dp, ws)
     pr = f32(pred).requires_grad_()
     l = K.bce_dice_loss(f32(tgt), pr, 0.4, 0.6)
@@ -702,6 +702,7 @@ def test_bce_dice(dtype):
     assert abs(out[0].item() - l.item()) < 1e-5
     assert abs(out[2].item() - K.dice_coefficient(f32(tgt), f32(pred)).item()) < 1e-5
     assert abs(out[3].item() - K.iou_score(f32(tgt), f32(pred)).item()) < 1e-5
+    assert abs(out[4].item() - K.dice_coefficient_global(f32(tgt), f32(pred)).item()) < 1e-5     # unet_vinillia's Dice
     assert relerr(dp, pr.grad) < TOL[dtype]
 
 
