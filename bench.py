@@ -364,7 +364,7 @@ def run_gpu(args):
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {"workload": desc, "depth": depth, "scale": scale, "patch": patch, "per_gpu_batch": batch,
                    "global_batch": batch * world, "loss": "charbonnier", "optimizer": "adam",
-                   "parallelism": f"dp{world}", "l2": "per-step working set (>2 GB of activations) far exceeds the 126 MB L2",
+                   "parallelism": f"dp{world}", "streams": "dgrad / norm backward on the main stream, wgrad forked to a second stream inside the captured step" if getattr(model, "overlap_wgrad", False) else "single stream", "l2": "per-step working set (>2 GB of activations) far exceeds the 126 MB L2",
                    "params": model.count_params(), "step_tflop_algorithmic": step_tflop,
                    "step_frac_of_conv_roofline": step_tflop / (ms_per_step / 1000.0) / peak_tf},
         "clocks": clocks.summary(),

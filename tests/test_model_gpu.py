@@ -385,3 +385,31 @@ def test_seg_vanilla_base32_bf16_on_tensor_cores():
             i += 1
     print(f"   worst weight-gradient relerr {worst:.3e}")
     _setup("float32")
+
+
+def test_wgrad_side_stream_matches_single_stream():
+    """Filter-gradient kernels forked onto a second stream inside the captured step (Model._run_bwd) against the
+    single-stream order: same loss, same gradients (up to the summation order of the atomic partial sums), over several
+    replays of the captured graph."""
+    from b200unet import builders as B
+    from b200unet.keras.optimizers import Adam
+    rng = np.random.default_rng(2)
+    hr = rng.random((8, 64, 64, 3), dtype=np.float32)
+    lr = np.clip(hr + 0.05 * rng.standard_normal(hr.shape).astype(np.float32), 0, 1)
+    runs = []
+    for overlap in (False, True):
+        _setup("mixed_bfloat16")
+        model, _ = B.build_super_resolution_unet(0.5, depth_override=3, input_size=64)
+        model.overlap_wgrad = overlap
+        head = model.get_layer("residual_rgb")
+        head.weight_specs[0]["value"] = np.random.default_rng(3).uniform(-0.2, 0.2, (1, 1, 64, 3)).astype(np.float32)
+        loss, metrics = B.build_losses_and_metrics("charbonnier")
+        model.compile(optimizer=Adam(learning_rate=1e-4), loss=loss, metrics=metrics)
+        losses = [model.train_on_batch(lr, hr)["loss"] for _ in range(4)]
+        runs.append((losses, model.G.clone(), [w.copy() for w in model.get_weights()]))
+    (l0, g0, w0), (l1, g1, w1) = runs
+    assert abs(l0[0] - l1[0]) <= 1e-6
+    assert all(abs(a - b) <= 2e-4 * max(1.0, abs(a)) for a, b in zip(l0, l1)), (l0, l1)
+    assert relerr(g1, g0) < 1e-3
+    assert max(float(np.abs(a - b).max()) for a, b in zip(w0, w1)) < 1e-3
+    _setup("float32")
