@@ -405,11 +405,16 @@ def test_wgrad_side_stream_matches_single_stream():
         head.weight_specs[0]["value"] = np.random.default_rng(3).uniform(-0.2, 0.2, (1, 1, 64, 3)).astype(np.float32)
         loss, metrics = B.build_losses_and_metrics("charbonnier")
         model.compile(optimizer=Adam(learning_rate=1e-4), loss=loss, metrics=metrics)
-        losses = [model.train_on_batch(lr, hr)["loss"] for _ in range(4)]
-        runs.append((losses, model.G.clone(), [w.copy() for w in model.get_weights()]))
-    (l0, g0, w0), (l1, g1, w1) = runs
+        losses = [model.train_on_batch(lr, hr)["loss"]]
+        g_first = model.G.clone()             # gradients of the first step: identical weights in both runs
+        losses += [model.train_on_batch(lr, hr)["loss"] for _ in range(3)]
+        runs.append((losses, g_first))
+    (l0, g0), (l1, g1) = runs
+    e = relerr(g1, g0)
+    print(f"side-stream wgrad: first-step gradient rel-L2 vs single stream {e:.3e}; losses {l0} / {l1}")
     assert abs(l0[0] - l1[0]) <= 1e-6
+    assert e < 1e-5          # only the summation order of the atomic partial sums may differ
+    # later steps see weights that differ in their last bits (Adam turns rounding-level gradient differences of
+    # near-zero gradients into +-lr steps), so only the loss trajectory is compared
     assert all(abs(a - b) <= 2e-4 * max(1.0, abs(a)) for a, b in zip(l0, l1)), (l0, l1)
-    assert relerr(g1, g0) < 1e-3
-    assert max(float(np.abs(a - b).max()) for a, b in zip(w0, w1)) < 1e-3
     _setup("float32")

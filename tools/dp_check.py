@@ -1,7 +1,9 @@
 """DP equivalence on real GPUs (run under torchrun, N >= 2): the all-reduced gradient of the sharded
 global batch must equal the single-GPU gradient of the whole batch, and the weights after one Adam
 step must agree on every rank.
-    python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 tools/dp_check.py"""
+    python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 tools/dp_check.py
+B200_DP_CHECK_ONE_GPU=1 (with B200_DP_SHARD=0) runs every rank on cuda:0 over the gloo backend: the same segmented
+capture / bucket exchange / fork-join logic, checkable on a one-GPU box (NCCL refuses two ranks on one device)."""
 import os
 import sys
 
@@ -14,8 +16,12 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
-    torch.cuda.set_device(local)
-    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if os.environ.get("B200_DP_CHECK_ONE_GPU") == "1":
+        torch.cuda.set_device(0)
+        dist.init_process_group("gloo")
+    else:
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     from b200unet import builders as B
     from b200unet.keras import clear_session, mixed_precision
     from b200unet.keras.optimizers import Adam
