@@ -114,6 +114,8 @@ class Model:
         # (C2: 5.06 -> 4.61 ms/step; B200_OVERLAP_WGRAD=0 restores the single-stream order)
         self.overlap_wgrad = os.environ.get("B200_OVERLAP_WGRAD", "1") == "1"
         self._side_stream = None
+        # EXPERIMENTAL (off): Adam of a layer's kernel range on the second stream right behind its wgrad (N=1 only)
+        self.overlap_adam = os.environ.get("B200_OVERLAP_ADAM", "0") == "1"
         self.input_shape = self.inputs[0].shape
         self.output_shape = self.outputs[0].shape
 
@@ -445,15 +447,28 @@ class Model:
         if self._side_stream is None:
             self._side_stream = torch.cuda.Stream()
         main, side, forked = torch.cuda.current_stream(), self._side_stream, False
+        early = self._early_adam = [] if (self.overlap_adam and self._dist is None) else None
+        pending = []          # kernel ranges whose wgrad is on the side stream but whose dgrad may still read the shadow
+        if early is not None:
+            self.optimizer.advance()
         for i in range(a, b):
             if plan.bwd_tags[i].startswith("wgrad"):
-                side.wait_stream(main)
+                side.wait_stream(main)          # ... which the wait just issued settles: the layer's dgrad is behind us
                 with torch.cuda.stream(side):
+                    if early is not None and pending:
+                        self.optimizer.apply_ranges(self, pending)
+                        early += pending
                     plan.bwd_steps[i]()
+                pending = [(lo, lo + n) for lo, n in plan.bwd_writes[i]] if early is not None else []
                 forked = True
             else:
                 plan.bwd_steps[i]()
         if forked:
+            if early is not None and pending:
+                side.wait_stream(main)
+                with torch.cuda.stream(side):
+                    self.optimizer.apply_ranges(self, pending)
+                early += pending
             main.wait_stream(side)
 
     def _train_body(self, plan: Plan, st):
@@ -493,6 +508,19 @@ class Model:
         return [shard_of(b, rank, world) if b["sharded"] else (b["lo"], b["hi"]) for b in self._buckets(plan)]
 
     def _apply_optimizer(self, plan):
+        early = getattr(self, "_early_adam", None)
+        if early:
+            # the kernel ranges were updated behind their wgrad kernels (_run_bwd): finish with everything else
+            rest, pos = [], 0
+            for lo, hi in sorted(early):
+                if lo > pos:
+                    rest.append((pos, lo))
+                pos = max(pos, hi)
+            if pos < self.G.numel():
+                rest.append((pos, self.G.numel()))
+            self.optimizer.apply_ranges(self, rest)
+            self._early_adam = None
+            return
         self.optimizer.apply(self, self._update_ranges(plan))
 
     def _gather_updated(self, plan):

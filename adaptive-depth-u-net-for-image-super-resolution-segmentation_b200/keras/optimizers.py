@@ -67,6 +67,19 @@ class Adam:
                 self._push_hyper()
         self.iterations += 1
 
+    def advance(self):
+        """Increment the device-resident step counter (once per training step, before any apply_ranges)."""
+        ops.adam_advance(self._state["step"])
+
+    def apply_ranges(self, model, ranges):
+        """Adam over [(lo, hi), ...] of the flat buffers WITHOUT advancing the step counter (see advance)."""
+        st = self._state
+        shadow = model.S if model.S is not model.P else None
+        for lo, hi in ranges:
+            if hi > lo:
+                ops.adam_step(model.P[lo:hi], model.G[lo:hi], st["m"][lo:hi], st["v"][lo:hi], st["hyper"], st["step"],
+                              None if shadow is None else shadow[lo:hi])
+
     def apply(self, model, ranges=None):
         """One Adam step over the flat buffers, or over `ranges` = [(lo, hi), ...] of them (sharded optimizer)."""
         st = self._state

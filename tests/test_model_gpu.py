@@ -389,32 +389,41 @@ def test_seg_vanilla_base32_bf16_on_tensor_cores():
 
 def test_wgrad_side_stream_matches_single_stream():
     """Filter-gradient kernels forked onto a second stream inside the captured step (Model._run_bwd) against the
-    single-stream order: same loss, same gradients (up to the summation order of the atomic partial sums), over several
-    replays of the captured graph."""
+    single-stream order: same loss, same first-step gradients and weights (up to the summation order of the atomic partial
+    sums), same loss trajectory over several replays of the captured graph.  Third run: the experimental per-layer Adam
+    behind each wgrad (B200_OVERLAP_ADAM) on top of it."""
     from b200unet import builders as B
     from b200unet.keras.optimizers import Adam
     rng = np.random.default_rng(2)
     hr = rng.random((8, 64, 64, 3), dtype=np.float32)
     lr = np.clip(hr + 0.05 * rng.standard_normal(hr.shape).astype(np.float32), 0, 1)
     runs = []
-    for overlap in (False, True):
+    for overlap, adam in ((False, False), (True, False), (True, True)):
         _setup("mixed_bfloat16")
         model, _ = B.build_super_resolution_unet(0.5, depth_override=3, input_size=64)
-        model.overlap_wgrad = overlap
+        model.overlap_wgrad, model.overlap_adam = overlap, adam
         head = model.get_layer("residual_rgb")
         head.weight_specs[0]["value"] = np.random.default_rng(3).uniform(-0.2, 0.2, (1, 1, 64, 3)).astype(np.float32)
         loss, metrics = B.build_losses_and_metrics("charbonnier")
         model.compile(optimizer=Adam(learning_rate=1e-4), loss=loss, metrics=metrics)
+        p_init = None
         losses = [model.train_on_batch(lr, hr)["loss"]]
-        g_first = model.G.clone()             # gradients of the first step: identical weights in both runs
+        g_first, p_first, s_first = model.G.clone(), model.P.clone(), model.S.clone().float()
+        m_first = model.optimizer._state["m"].clone()
         losses += [model.train_on_batch(lr, hr)["loss"] for _ in range(3)]
-        runs.append((losses, g_first))
-    (l0, g0), (l1, g1) = runs
-    e = relerr(g1, g0)
-    print(f"side-stream wgrad: first-step gradient rel-L2 vs single stream {e:.3e}; losses {l0} / {l1}")
-    assert abs(l0[0] - l1[0]) <= 1e-6
-    assert e < 1e-5          # only the summation order of the atomic partial sums may differ
-    # later steps see weights that differ in their last bits (Adam turns rounding-level gradient differences of
-    # near-zero gradients into +-lr steps), so only the loss trajectory is compared
-    assert all(abs(a - b) <= 2e-4 * max(1.0, abs(a)) for a, b in zip(l0, l1)), (l0, l1)
+        runs.append((losses, g_first, p_first, s_first, m_first))
+    l0, g0, p0, s0, m0 = runs[0]
+    for name, (l1, g1, p1, s1, m1) in zip(("wgrad on the side stream", "+ per-layer Adam behind it"), runs[1:]):
+        e = relerr(g1, g0)
+        print(f"{name}: first-step gradient rel-L2 vs single stream {e:.3e}, Adam m {relerr(m1, m0):.3e}, "
+              f"weights {relerr(p1, p0):.3e}; losses {l1}")
+        assert abs(l0[0] - l1[0]) <= 1e-6
+        assert e < 1e-5          # only the summation order of the atomic partial sums may differ
+        assert relerr(m1, m0) < 1e-5                                  # the optimizer saw the COMPLETE gradients
+        # the first Adam step is sign-like (+-lr): an element whose tiny gradient changes sign with the summation order
+        # moves by 2 lr, so the weights are compared loosely and the first moment (above) tightly
+        assert relerr(p1, p0) < 1e-4 and relerr(s1, s0) < 1e-3
+        # later steps see weights that differ in their last bits (Adam turns rounding-level gradient differences of
+        # near-zero gradients into +-lr steps), so only the loss trajectory is compared
+        assert all(abs(a - b) <= 2e-4 * max(1.0, abs(a)) for a, b in zip(l0, l1)), (l0, l1)
     _setup("float32")
