@@ -511,14 +511,8 @@ class Model:
         early = getattr(self, "_early_adam", None)
         if early:
             # the kernel ranges were updated behind their wgrad kernels (_run_bwd): finish with everything else
-            rest, pos = [], 0
-            for lo, hi in sorted(early):
-                if lo > pos:
-                    rest.append((pos, lo))
-                pos = max(pos, hi)
-            if pos < self.G.numel():
-                rest.append((pos, self.G.numel()))
-            self.optimizer.apply_ranges(self, rest)
+            from ..parallel import complement_ranges
+            self.optimizer.apply_ranges(self, complement_ranges(early, self.G.numel()))
             self._early_adam = None
             return
         self.optimizer.apply(self, self._update_ranges(plan))

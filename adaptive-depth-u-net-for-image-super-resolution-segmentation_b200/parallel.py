@@ -28,6 +28,20 @@ def shard_range(n: int, rank: int, world: int) -> Tuple[int, int]:
     return rank * per, (rank + 1) * per
 
 
+def complement_ranges(done: Sequence[Tuple[int, int]], total: int) -> List[Tuple[int, int]]:
+    """[lo, hi) ranges of [0, total) NOT covered by `done` (half-open ranges, any order, may touch or overlap)."""
+    rest, pos = [], 0
+    for lo, hi in sorted(done):
+        if lo > pos:
+            rest.append((pos, min(lo, total)))
+        pos = max(pos, hi)
+        if pos >= total:
+            break
+    if pos < total:
+        rest.append((pos, total))
+    return [(lo, hi) for lo, hi in rest if hi > lo]
+
+
 def plan_buckets(total: int, writes: Sequence[Sequence[Tuple[int, int]]], bucket_elems: int, align: int = 1) -> List[dict]:
     """Cut [0, total) into buckets of about `bucket_elems` elements, filled from the END of the buffer
     (backward writes the last layers first), and find for each bucket the index of the last backward

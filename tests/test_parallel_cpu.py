@@ -137,3 +137,26 @@ def test_shard_range_and_bucket_plan():
         bs = sorted(plan_buckets(1000, writes, size), key=lambda d: d["lo"])
         assert bs[0]["lo"] == 0 and bs[-1]["hi"] == 1000
         assert all(a["hi"] == c["lo"] for a, c in zip(bs, bs[1:]))
+
+
+def test_complement_ranges():
+    """The flat-buffer ranges left for the final optimizer pass after some were updated early (Model._apply_optimizer)."""
+    from b200unet.parallel import complement_ranges as C
+    assert C([], 10) == [(0, 10)]
+    assert C([(0, 10)], 10) == []
+    assert C([(2, 4), (6, 8)], 10) == [(0, 2), (4, 6), (8, 10)]
+    assert C([(6, 8), (2, 4), (3, 7)], 10) == [(0, 2), (8, 10)]            # unordered, overlapping
+    assert C([(0, 3), (3, 5)], 5) == []                                     # touching
+    assert C([(4, 20)], 10) == [(0, 4)]                                     # past the end
+    rng = np.random.default_rng(0)
+    for _ in range(50):
+        total = int(rng.integers(1, 60))
+        done = [tuple(sorted(rng.integers(0, total + 5, 2).tolist())) for _ in range(int(rng.integers(0, 6)))]
+        mask = np.zeros(total, bool)
+        for lo, hi in done:
+            mask[lo:hi] = True
+        got = np.zeros(total, bool)
+        for lo, hi in C(done, total):
+            assert 0 <= lo < hi <= total and not got[lo:hi].any()
+            got[lo:hi] = True
+        assert np.array_equal(got, ~mask)
