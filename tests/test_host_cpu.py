@@ -135,3 +135,18 @@ def test_no_cpu_fallback():
     model, _ = B.build_super_resolution_unet(0.5, depth_override=1, input_size=16)
     with pytest.raises(B200Error):
         model(np.zeros((1, 16, 16, 3), np.float32))
+
+
+@pytest.mark.parametrize("first", ["b200unet.shared.custom_layers", "b200unet.keras.engine", "b200unet.builders",
+                                   "b200unet.shared.pipeline", "b200unet.metrics"])
+def test_any_module_can_be_the_first_import(first):
+    """The reference's scripts start with ``from shared.custom_layers import ...`` (train_adaptive_unet.py:27-34); the swapped
+    import must work as the FIRST import of a fresh interpreter (custom_layers <-> keras.engine import each other)."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = (f"import sys; sys.path.insert(0, {root!r}); import importlib; importlib.import_module({first!r}); "
+            "from b200unet.shared.custom_layers import ResizeByScale, ResizeToMatch, ClippedResidualAdd, ClipAdd; "
+            "from b200unet.builders import build_super_resolution_unet; print('ok')")
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and r.stdout.strip().endswith("ok"), r.stderr[-2000:]

@@ -1,0 +1,231 @@
+"""Drop-in boundary against the REFERENCE'S OWN entry points (build container only: needs /root/reference).
+
+The reference's scripts are Python on TensorFlow/Keras, which cannot be installed here -- but their command lines and
+their pure-Python helpers do not need TF to run.  An import hook hands out inert stand-ins for every ``tensorflow`` /
+``keras`` / ``optuna`` module, the unmodified reference files are imported next to the mirrors of this repo, and the
+test compares (a) every command-line flag (option strings, type, choices, default, store_true-ness) of the five entry
+points, (b) the helper functions both sides share (depth rules, index splits, eval shave, natural sort, mask-file
+matching) on grids of inputs, (c) the training protocols' hyper-parameters."""
+import argparse
+import importlib.abc
+import importlib.machinery
+import importlib.util
+import os
+import sys
+import types
+from pathlib import Path
+from unittest.mock import MagicMock
+
+import numpy as np
+import pytest
+
+REF = "/root/reference"
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+pytestmark = pytest.mark.skipif(not os.path.isdir(REF), reason="reference checkout not present (build container only)")
+
+
+class _StubModule(types.ModuleType):
+    __path__ = []
+
+    def __getattr__(self, name):
+        if name.startswith("__"):
+            raise AttributeError(name)
+        m = MagicMock(name=f"{self.__name__}.{name}")
+        setattr(self, name, m)
+        return m
+
+
+class _StubFinder(importlib.abc.MetaPathFinder, importlib.abc.Loader):
+    ROOTS = ("tensorflow", "keras", "optuna")
+
+    def find_spec(self, fullname, path, target=None):
+        if fullname.split(".")[0] in self.ROOTS:
+            return importlib.machinery.ModuleSpec(fullname, self, is_package=True)
+        return None
+
+    def create_module(self, spec):
+        return _StubModule(spec.name)
+
+    def exec_module(self, module):
+        pass
+
+
+def _load(path, name, extra_paths):
+    for p in extra_paths:
+        sys.path.insert(0, p)
+    sys.modules.pop("dataset_paths", None)          # every code directory has its own
+    try:
+        spec = importlib.util.spec_from_file_location(name, path)
+        mod = importlib.util.module_from_spec(spec)
+        sys.modules[name] = mod
+        spec.loader.exec_module(mod)
+        return mod
+    finally:
+        for p in extra_paths:
+            sys.path.remove(p)
+
+
+ENTRY_POINTS = {
+    # relative path: (code dir, minimal argv that satisfies the reference's required flags)
+    "Super_resolution/code/train_adaptive_unet.py": ("Super_resolution/code", ["--scale", "0.5"]),
+    "Super_resolution/code/evaluate_model.py": ("Super_resolution/code", ["--scale", "0.5", "--model-path", "m.keras"]),
+    "Super_resolution/code/u-net-vinillia.py": ("Super_resolution/code", ["--high_res_dir", "a", "--low_res_dir", "b"]),
+    "Segmenation/code/train_adaptive_unet.py": ("Segmenation/code", []),
+    "Segmenation/code/unet_vinillia.py": ("Segmenation/code", []),
+}
+
+
+@pytest.fixture(scope="module")
+def sides():
+    """{rel: (reference module, mirror module)} with the TF stand-ins installed only while this module's tests run."""
+    finder = _StubFinder()
+    before = set(sys.modules)
+    sys.meta_path.insert(0, finder)
+    try:
+        out = {}
+        for rel, (code_dir, _) in ENTRY_POINTS.items():
+            tag = os.path.basename(rel)[:-3].replace("-", "_")
+            ref = _load(os.path.join(REF, rel), f"_ref_{code_dir[:3]}_{tag}", [REF, os.path.join(REF, code_dir)])
+            mine = _load(os.path.join(ROOT, rel), f"_mine_{code_dir[:3]}_{tag}", [os.path.join(ROOT, code_dir)])
+            out[rel] = (ref, mine)
+        out["custom_layers"] = (_load(os.path.join(REF, "shared/custom_layers.py"), "_ref_custom_layers", [REF]), None)
+        yield out
+    finally:
+        sys.meta_path.remove(finder)
+        for name in set(sys.modules) - before:
+            if name.split(".")[0] in _StubFinder.ROOTS or name.startswith(("_ref_", "_mine_")) or name == "dataset_paths":
+                sys.modules.pop(name, None)
+
+
+def _parser_of(mod, argv, pass_argv):
+    """The ArgumentParser a module's parse_args() builds (captured at its parse_args call)."""
+    cap = {}
+    orig = argparse.ArgumentParser.parse_args
+
+    def spy(self, args=None, namespace=None):
+        cap["parser"] = self
+        return orig(self, argv, namespace)
+
+    argparse.ArgumentParser.parse_args = spy
+    try:
+        mod.parse_args(argv) if pass_argv else mod.parse_args()
+    finally:
+        argparse.ArgumentParser.parse_args = orig
+    return cap["parser"]
+
+
+def _flags(parser):
+    out = {}
+    for a in parser._actions:
+        if a.option_strings and a.dest != "help":
+            out[a.dest] = {"options": tuple(a.option_strings), "action": type(a).__name__, "default": a.default,
+                           "type": getattr(a.type, "__name__", a.type), "choices": tuple(a.choices) if a.choices else None,
+                           "required": a.required}
+    return out
+
+
+# defaults that are site paths of the authors' cluster / of this checkout, and flags this repo makes optional because
+# --synthetic / --random-init can stand in for them
+SITE_PATHS = {"model_dir", "log_dir", "hr_dir", "output_dir", "high_res_dir", "low_res_dir", "train_image_dir",
+              "train_mask_dir", "val_image_dir", "val_mask_dir", "image_dir", "mask_dir"}
+RELAXED_REQUIRED = {"model_path", "high_res_dir", "low_res_dir"}
+
+
+@pytest.mark.parametrize("rel", list(ENTRY_POINTS))
+def test_command_line_flags_match_the_reference(sides, rel):
+    ref_mod, mine_mod = sides[rel]
+    argv = ENTRY_POINTS[rel][1]
+    ref, mine = _flags(_parser_of(ref_mod, argv, False)), _flags(_parser_of(mine_mod, argv, True))
+    assert ref, rel
+    for dest, spec in ref.items():
+        assert dest in mine, f"{rel}: flag {spec['options']} of the reference is missing"
+        got = mine[dest]
+        for key in ("options", "action", "type", "choices"):
+            assert got[key] == spec[key], (rel, dest, key, spec[key], got[key])
+        if dest not in SITE_PATHS:
+            assert got["default"] == spec["default"], (rel, dest, spec["default"], got["default"])
+        assert got["required"] == spec["required"] or (dest in RELAXED_REQUIRED and not got["required"]), (rel, dest)
+    extra = set(mine) - set(ref)        # additions must be optional: a reference command line runs unchanged
+    assert all(not mine[d]["required"] for d in extra), extra
+
+
+def test_depth_and_shape_rules_match(sides):
+    ref = sides["custom_layers"][0]
+    from b200unet.shared import custom_layers as CL
+    scales = [0.1, 0.2, 0.25, 0.3, 0.33, 0.4, 0.45, 0.5, 0.6, 0.7, 0.75, 0.8, 0.9]
+    for s in scales:
+        assert CL.infer_depth_from_scale(s) == ref.infer_depth_from_scale(s)
+        for res in (64, 128, 256, 512):
+            for md in (3, 7):
+                assert CL.custom_depth_from_scale(s, max_depth=md, base_resolution=res) == \
+                    ref.custom_depth_from_scale(s, max_depth=md, base_resolution=res), (s, res, md)
+            for d in (1, 2, 3, 5):
+                assert CL.estimate_bottleneck_size(res, s, d) == ref.estimate_bottleneck_size(res, s, d)
+        assert CL.depth_and_sizes(s) == ref.depth_and_sizes(s)
+    for bad in (0.0, 1.0, -0.5, 1.5):
+        with pytest.raises(ValueError):
+            ref.custom_depth_from_scale(bad)
+        with pytest.raises(ValueError):
+            CL.custom_depth_from_scale(bad)
+
+
+def test_index_split_eval_shave_and_sort_match(sides):
+    from b200unet.shared import pipeline as PL
+    ref_train = sides["Super_resolution/code/train_adaptive_unet.py"][0]
+    ref_van = sides["Super_resolution/code/u-net-vinillia.py"][0]
+    ref_eval, mine_eval = sides["Super_resolution/code/evaluate_model.py"]
+    for n in (1, 2, 3, 5, 10, 37, 800):
+        for tr, va, te in ((0.8, 0.1, 0.1), (0.9, 0.1, 0.0), (0.5, 0.25, 0.25), (0.98, 0.01, 0.01)):
+            for seed in (0, 1234):
+                try:
+                    want = ref_train.split_indices(n, tr, va, te, seed)
+                except ValueError:
+                    with pytest.raises(ValueError):
+                        PL.split_indices(n, tr, va, te, seed)
+                    continue
+                got = PL.split_indices(n, tr, va, te, seed)
+                assert all(np.array_equal(a, b) for a, b in zip(want, got)), (n, tr, va, te, seed)
+                v = ref_van.split_indices(n_samples=n, train=tr, val=va, test=te, seed=seed)
+                assert all(np.array_equal(a, b) for a, b in zip(v, got))
+    for s in (0.2, 0.25, 0.3, 0.5, 0.7, 0.9):
+        for override in (None, 0, 3, -2):
+            assert mine_eval.infer_eval_shave(s, override) == ref_eval.infer_eval_shave(s, override)
+    for names in (["10.png", "9.png", "0001.png", "1.png", "100.png"],
+                  ["img_12a.png", "IMG_3.png", "img_2b10.png", "img_2b9.png", "a", "B", "img_", "IMG_03.png"]):
+        assert PL.sorted_alphanumeric(names) == ref_train.sorted_alphanumeric(names) == ref_van.sorted_alphanumeric(names)
+    mixed = ["10.png", "img_1.png"]       # a digit-led and a letter-led name compare int with str: both sides raise
+    for fn in (PL.sorted_alphanumeric, ref_train.sorted_alphanumeric):
+        with pytest.raises(TypeError):
+            fn(mixed)
+
+
+def test_segmentation_protocols_and_file_matching(sides, tmp_path):
+    ref, mine = sides["Segmenation/code/train_adaptive_unet.py"]
+    mp = mine._protocols()
+    assert set(mp) == set(ref.PROTOCOLS)
+    for key, rp in ref.PROTOCOLS.items():
+        for field in ("key", "initial_lr", "epochs", "batch_size", "cosine_schedule", "early_stopping_patience"):
+            assert getattr(mp[key], field) == getattr(rp, field), (key, field)
+    from b200unet.shared import seg_data as SD
+    ref_van = sides["Segmenation/code/unet_vinillia.py"][0]
+    for name in ("ISIC_0000001.jpg", "ISIC_0000001_segmentation.png", "isic_12_Segmentation.PNG", "plain.jpeg"):
+        assert SD.canonical_key(Path(name)) == ref.normalise_isic_key(Path(name)) == ref_van._canonical_key(Path(name)), name
+    for name in ("x_mask.png", "city_000_leftImg8bit.png", "city_000_gtFine_labelIds.png", "a_gtCoarse_color.png"):
+        assert SD.canonical_key(Path(name)) == ref_van._canonical_key(Path(name)), name     # the baseline's longer token list
+    img, msk = tmp_path / "img", tmp_path / "msk"
+    img.mkdir(); msk.mkdir()
+    for stem in ("ISIC_0000010", "ISIC_0000002", "ISIC_0000033", "ISIC_0000002_superpixels"):
+        (img / f"{stem}.jpg").write_bytes(b"x")
+    for stem in ("ISIC_0000002", "ISIC_0000010", "ISIC_0000099", "ISIC_0000033"):
+        (msk / f"{stem}_segmentation.png").write_bytes(b"x")
+    want = ref.collect_isic_pairs(img, msk)
+    got = SD.collect_pairs(img, msk)
+    assert [(Path(a).name, Path(b).name) for a, b in got] == [(Path(a).name, Path(b).name) for a, b in want]
+    assert len(got) == 3                                        # superpixel images skipped, the spare mask ignored
+    (img / "ISIC_0000500.jpg").write_bytes(b"x")                # an image without a mask: both sides refuse
+    for fn in (ref.collect_isic_pairs, SD.collect_pairs):
+        with pytest.raises(ValueError):
+            fn(img, msk)
+    for fn in (ref.collect_isic_pairs, SD.collect_pairs):
+        with pytest.raises(FileNotFoundError):
+            fn(tmp_path / "nope", msk)
