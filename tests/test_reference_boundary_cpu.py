@@ -229,3 +229,126 @@ def test_segmentation_protocols_and_file_matching(sides, tmp_path):
     for fn in (ref.collect_isic_pairs, SD.collect_pairs):
         with pytest.raises(FileNotFoundError):
             fn(tmp_path / "nope", msk)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Model builders: run the REFERENCE'S builder code and this repo's builder code against the same recording stand-ins for
+# Input / layers / Model and compare what they construct -- every layer (kind, constructor arguments normalised through
+# the Keras signatures), every call (which tensors go in, in which order: the concat order [up, skip] matters), the model
+# name.  Equal event lists = the same graph.
+# ------------------------------------------------------------------------------------------------------------------
+class _Tok:
+    def __init__(self, i):
+        self.id = i
+
+
+class _GraphRecorder:
+    ALIASES = {"MaxPool2D": "MaxPooling2D", "ClipAdd": "ClippedResidualAdd"}
+
+    def __init__(self):
+        self.events, self.n_tok, self.n_layer = [], 0, 0
+
+    def _new_tok(self):
+        self.n_tok += 1
+        return _Tok(self.n_tok)
+
+    def _canon(self, kind, args, kwargs):
+        import inspect
+        from b200unet.keras import layers as ML
+        from b200unet.shared import custom_layers as CL
+        cls = getattr(ML, kind, None) or getattr(CL, kind)
+        sig = inspect.signature(cls.__init__)
+        known = {k: v for k, v in kwargs.items() if k in sig.parameters}
+        bound = sig.bind(None, *args, **known)
+        bound.apply_defaults()
+        d = {k: v for k, v in bound.arguments.items() if k not in ("self", "kwargs")}
+        d.update({k: v for k, v in kwargs.items() if k not in sig.parameters})
+        for k in ("kernel_size", "pool_size", "size", "strides"):
+            if k in d and d[k] is not None and not isinstance(d[k], tuple):
+                d[k] = (d[k], d[k])
+        return tuple(sorted((k, repr(v)) for k, v in d.items()))
+
+    def layer(self, kind):
+        kind = self.ALIASES.get(kind, kind)
+
+        def ctor(*args, **kwargs):
+            lid = self.n_layer
+            self.n_layer += 1
+            self.events.append(("layer", lid, kind, self._canon(kind, args, kwargs)))
+
+            def call(inputs):
+                ins = tuple(t.id for t in inputs) if isinstance(inputs, (list, tuple)) else (inputs.id,)
+                out = self._new_tok()
+                self.events.append(("call", lid, ins, out.id))
+                return out
+            return call
+        return ctor
+
+    def input(self, shape=None, name=None, **kw):
+        t = self._new_tok()
+        self.events.append(("input", tuple(shape), name, t.id))
+        return t
+
+    def model(self, *args, **kwargs):
+        inputs = kwargs.get("inputs", args[0] if args else None)
+        outputs = kwargs.get("outputs", args[1] if len(args) > 1 else None)
+        self.events.append(("model", inputs.id, outputs.id, kwargs.get("name")))
+        return ("model", kwargs.get("name"))
+
+    def patch(self, monkeypatch, mod):
+        rec = self
+
+        class _Layers:
+            def __getattr__(_, kind):
+                return rec.layer(kind)
+        monkeypatch.setattr(mod, "L", _Layers(), raising=False)
+        monkeypatch.setattr(mod, "Input", self.input, raising=False)
+        monkeypatch.setattr(mod, "Model", self.model, raising=False)
+        for kind in ("ResizeByScale", "ResizeToMatch", "ClippedResidualAdd"):
+            if hasattr(mod, kind):
+                monkeypatch.setattr(mod, kind, self.layer(kind))
+
+
+def _record(monkeypatch, mod, fn_name, *args, **kwargs):
+    rec = _GraphRecorder()
+    with monkeypatch.context() as mp:
+        rec.patch(mp, mod)
+        result = getattr(mod, fn_name)(*args, **kwargs)
+    return rec.events, result
+
+
+def test_builders_construct_the_reference_graphs(sides, monkeypatch):
+    from b200unet import builders as B
+    ref_sr = sides["Super_resolution/code/train_adaptive_unet.py"][0]
+    ref_van = sides["Super_resolution/code/u-net-vinillia.py"][0]
+    ref_seg = sides["Segmenation/code/train_adaptive_unet.py"][0]
+    ref_base = sides["Segmenation/code/unet_vinillia.py"][0]
+    n = 0
+    # adaptive-depth SR U-Net: explicit depths and the depth rule (train_adaptive_unet.py:217-287)
+    for kw in (dict(scale=0.5, depth_override=3, input_size=64), dict(scale=0.25, depth_override=4, input_size=128),
+               dict(scale=0.25, depth_override=5, input_size=128), dict(scale=0.7, input_size=256),
+               dict(scale=0.2, input_size=256, max_depth=3), dict(scale=0.5, base_channels=32, residual_head_channels=16,
+                                                                 depth_override=1, input_size=32)):
+        (want, (_, winfo)), (got, (_, ginfo)) = (_record(monkeypatch, ref_sr, "build_super_resolution_unet", **kw),
+                                                 _record(monkeypatch, B, "build_super_resolution_unet", **kw))
+        assert got == want, kw
+        assert ginfo == winfo, kw
+        n += len(want)
+    # fixed-depth BatchNorm SR baseline (u-net-vinillia.py:128-167)
+    want, _ = _record(monkeypatch, ref_van, "build_super_resolution_unet", (256, 256, 3))
+    got, _ = _record(monkeypatch, B, "build_vanilla_super_resolution_unet", (256, 256, 3))
+    assert got == want
+    n += len(want)
+    # segmentation: adaptive BatchNorm U-Net (:335-362) and the LayerNorm / Conv2DTranspose baseline (unet_vinillia.py:72-91)
+    for size, base, depth in ((256, 64, 4), (128, 32, 2), (256, 48, 5)):
+        want, _ = _record(monkeypatch, ref_seg, "build_adaptive_depth_unet", size, base, depth)
+        got, _ = _record(monkeypatch, B, "build_adaptive_depth_unet", size, base, depth)
+        assert got == want, (size, base, depth)
+        n += len(want)
+    for kw in (dict(input_size=256), dict(input_size=256, num_classes=21, base_channels=32, depth=4),
+               dict(input_size=64, num_classes=1, base_channels=16, depth=2)):
+        want, _ = _record(monkeypatch, ref_base, "build_unet", **kw)
+        got, _ = _record(monkeypatch, B, "build_unet", **kw)
+        assert got == want, kw
+        n += len(want)
+    assert n > 1000          # layers + calls compared
