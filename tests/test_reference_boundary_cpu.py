@@ -24,13 +24,44 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 pytestmark = pytest.mark.skipif(not os.path.isdir(REF), reason="reference checkout not present (build container only)")
 
 
+SERIALIZABLE_KEYS = {}
+
+
+class _LayerBase:
+    """Stand-in for keras.layers.Layer: enough for the reference's custom layers to be REAL classes whose code runs."""
+
+    def __init__(self, name=None, **kwargs):
+        self.name = name
+
+    def get_config(self):
+        return {"name": self.name}
+
+    def __call__(self, inputs):
+        return self.call(inputs)
+
+
+def _register_keras_serializable(package="Custom", name=None):
+    def deco(cls):
+        SERIALIZABLE_KEYS[f"{package}>{name or cls.__name__}"] = cls
+        return cls
+    return deco
+
+
 class _StubModule(types.ModuleType):
     __path__ = []
 
     def __getattr__(self, name):
         if name.startswith("__"):
             raise AttributeError(name)
-        m = MagicMock(name=f"{self.__name__}.{name}")
+        if name in ("keras", "layers", "saving"):        # ``from tensorflow.keras import layers as L``: a stand-in MODULE
+            import importlib
+            m = importlib.import_module(f"{self.__name__}.{name}")
+        elif name == "Layer":
+            m = _LayerBase
+        elif name == "register_keras_serializable":
+            m = _register_keras_serializable
+        else:
+            m = MagicMock(name=f"{self.__name__}.{name}")
         setattr(self, name, m)
         return m
 
@@ -352,3 +383,122 @@ def test_builders_construct_the_reference_graphs(sides, monkeypatch):
         assert got == want, kw
         n += len(want)
     assert n > 1000          # layers + calls compared
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# The reference's loss / metric / custom-layer CODE executed on numpy: a stand-in ``tf`` that maps the elementary ops
+# these functions use (cast, reduce_mean/sum, square, sqrt, abs, clip_by_value, ceil, maximum, shape ...) onto numpy
+# float32.  What is pinned is the COMPOSITION the reference wrote (which epsilon, where the clip sits, per-sample versus
+# whole-batch sums, smoothing constants, the float32 size rule) -- the elementary ops are unambiguous.  The two library
+# calls that are not elementary are stated here: tf.image.psnr = 10 log10(max^2 / per-image MSE); keras
+# BinaryCrossentropy() = mean over all elements of the cross-entropy of probabilities clipped to [1e-7, 1 - 1e-7];
+# tf.image.resize is only RECORDED (target size, method, antialias), its arithmetic stays with oracle/resize_np.py.
+# ------------------------------------------------------------------------------------------------------------------
+class _NumpyTF:
+    float32, int32, Tensor = np.float32, np.int32, np.ndarray
+
+    def __init__(self):
+        self.resize_calls = []
+        tf = self
+
+        class _Math:
+            ceil = staticmethod(np.ceil)
+
+        class _Image:
+            @staticmethod
+            def psnr(a, b, max_val):
+                mse = np.mean(np.square(np.asarray(a, np.float32) - np.asarray(b, np.float32)), axis=(-3, -2, -1))
+                return (10.0 * np.log10(np.float32(max_val) ** 2 / mse)).astype(np.float32)
+
+            @staticmethod
+            def resize(x, size, method=None, antialias=False):
+                tf.resize_calls.append((tuple(int(v) for v in size), method, antialias))
+                return np.zeros((x.shape[0], int(size[0]), int(size[1]), x.shape[3]), np.float32)
+
+        class _BCE:
+            def __call__(self, y_true, y_pred):
+                p = np.clip(np.asarray(y_pred, np.float32), 1e-7, 1.0 - 1e-7)
+                t = np.asarray(y_true, np.float32)
+                return np.mean(-(t * np.log(p) + (1.0 - t) * np.log(1.0 - p)), dtype=np.float32)
+
+        self.math, self.image = _Math, _Image
+        self.keras = types.SimpleNamespace(losses=types.SimpleNamespace(BinaryCrossentropy=_BCE))
+
+    cast = staticmethod(lambda x, dtype: np.asarray(x).astype(dtype))
+    constant = staticmethod(lambda v, dtype=None: np.asarray(v, dtype=dtype))
+    reshape = staticmethod(lambda x, shape: np.reshape(x, shape))
+    square, sqrt, abs = staticmethod(np.square), staticmethod(np.sqrt), staticmethod(np.abs)
+    maximum = staticmethod(np.maximum)
+    clip_by_value = staticmethod(lambda x, lo, hi: np.clip(x, lo, hi))
+    shape = staticmethod(lambda x: np.asarray(x.shape, dtype=np.int32))
+
+    @staticmethod
+    def reduce_mean(x, axis=None, keepdims=False):
+        return np.mean(x, axis=tuple(axis) if isinstance(axis, list) else axis, keepdims=keepdims)
+
+    @staticmethod
+    def reduce_sum(x, axis=None, keepdims=False):
+        return np.sum(x, axis=tuple(axis) if isinstance(axis, list) else axis, keepdims=keepdims)
+
+
+def test_reference_loss_metric_and_layer_code_on_numpy(sides, monkeypatch):
+    import torch
+    from oracle import keras_ops as K, metrics_ref as MR
+    from b200unet.shared import custom_layers as CL
+    ref_sr = sides["Super_resolution/code/train_adaptive_unet.py"][0]
+    ref_seg = sides["Segmenation/code/train_adaptive_unet.py"][0]
+    ref_base = sides["Segmenation/code/unet_vinillia.py"][0]
+    ref_cl = sides["custom_layers"][0]
+    tf = _NumpyTF()
+    for mod in (ref_sr, ref_seg, ref_base, ref_cl):
+        monkeypatch.setattr(mod, "tf", tf)
+    rng = np.random.default_rng(0)
+    t = lambda a: torch.from_numpy(np.asarray(a, np.float32))
+
+    # SR losses and the PSNR metric (train_adaptive_unet.py:294-334) against the oracle restatements
+    y = rng.random((3, 16, 16, 3), dtype=np.float32)
+    p = (y + 0.1 * rng.standard_normal(y.shape)).astype(np.float32)          # leaves [0, 1]
+    charb, (psnr,) = ref_sr.build_losses_and_metrics("charbonnier")
+    l1, _ = ref_sr.build_losses_and_metrics("l1")
+    assert abs(float(charb(y, p)) - K.charbonnier_loss(t(y), t(p)).item()) < 1e-6
+    assert abs(float(l1(y, p)) - K.l1_loss(t(y), t(p)).item()) < 1e-6
+    assert abs(float(psnr(y, p)) - K.psnr_metric(t(y), t(p)).item()) < 1e-4
+    with pytest.raises(ValueError):
+        ref_sr.build_losses_and_metrics("huber")
+    # BT.601 luma of the eval loops (:144-157)
+    assert np.abs(ref_sr.rgb_to_luma_bt601(p) - MR.rgb_to_luma_bt601(t(p)).numpy()).max() < 1e-6
+
+    # segmentation: per-sample dice / iou, the two hybrid losses (seg :258-304), the baseline's whole-batch dice (:94-99)
+    m = (rng.random((4, 12, 12, 1)) > 0.6).astype(np.float32)
+    q = rng.random((4, 12, 12, 1), dtype=np.float32)
+    q[0, :2] = 0.0; q[1, :2] = 1.0                                              # probabilities on the clip bounds
+    assert abs(float(ref_seg.dice_coefficient(m, q)) - K.dice_coefficient(t(m), t(q)).item()) < 1e-6
+    assert abs(float(ref_seg.iou_score(m, q)) - K.iou_score(t(m), t(q)).item()) < 1e-6
+    for maker, (a, b) in ((ref_seg.make_hybrid_ce_dice_loss, (0.4, 0.6)), (ref_seg.make_bce_dice_loss, (0.5, 1.0))):
+        assert abs(float(maker(a, b)(m, q)) - K.bce_dice_loss(t(m), t(q), a, b).item()) < 2e-6
+    assert abs(float(ref_base.dice_coefficient(m, q)) - K.dice_coefficient_global(t(m), t(q)).item()) < 1e-6
+
+    # custom layers: the reference classes are real here (stand-in base class), their call() code runs on numpy
+    assert set(SERIALIZABLE_KEYS) >= {"resize>ResizeByScale", "resize>ResizeToMatch", "utils>ClippedResidualAdd"}
+    assert set(CL.get_custom_objects()) >= {"resize>ResizeByScale", "resize>ResizeToMatch", "utils>ClippedResidualAdd"}
+    assert ref_cl.ClipAdd is ref_cl.ClippedResidualAdd and CL.ClipAdd is CL.ClippedResidualAdd
+    inp = rng.random((2, 5, 5, 3), dtype=np.float32)
+    res = (0.8 * rng.standard_normal(inp.shape)).astype(np.float32)
+    out = ref_cl.ClippedResidualAdd(name="enhanced_rgb").call([inp, res])
+    assert np.abs(out - K.clipped_residual_add(t(inp), t(res)).numpy()).max() < 1e-7 and out.dtype == np.float32
+    for scale in (0.2, 0.25, 0.3, 0.5, 0.7, 0.9):
+        for h, w in ((256, 256), (180, 126), (89, 63), (45, 45), (7, 3), (1, 1)):
+            tf.resize_calls.clear()
+            ref_cl.ResizeByScale(scale, name="enc_down").call(np.zeros((1, h, w, 4), np.float32))
+            (size, method, aa), = tf.resize_calls
+            mine = CL.ResizeByScale(scale).compute_output_shape([(1, h, w, 4)])
+            assert size == (mine[1], mine[2]) == (CL.resized_extent(h, scale), CL.resized_extent(w, scale)), (scale, h, w)
+            assert method == "bilinear" and aa is True
+    tf.resize_calls.clear()
+    ref_cl.ResizeToMatch(name="dec_up").call((np.zeros((1, 8, 9, 4), np.float32), np.zeros((1, 31, 17, 6), np.float32)))
+    assert tf.resize_calls == [((31, 17), "bilinear", True)]
+    assert CL.ResizeToMatch().compute_output_shape([(1, 8, 9, 4), (1, 31, 17, 6)]) == (1, 31, 17, 4)
+    rc, mc = ref_cl.ResizeByScale(0.3, name="d").get_config(), CL.ResizeByScale(0.3, name="d").get_config()
+    assert {k: mc[k] for k in rc} == rc
+    rc, mc = ref_cl.ResizeToMatch(name="u").get_config(), CL.ResizeToMatch(name="u").get_config()
+    assert {k: mc[k] for k in rc} == rc
