@@ -502,3 +502,24 @@ def test_reference_loss_metric_and_layer_code_on_numpy(sides, monkeypatch):
     assert {k: mc[k] for k in rc} == rc
     rc, mc = ref_cl.ResizeToMatch(name="u").get_config(), CL.ResizeToMatch(name="u").get_config()
     assert {k: mc[k] for k in rc} == rc
+
+
+def test_epoch_lines_parse_with_the_reference_log_exporter(tmp_path):
+    """Model.fit(verbose=2) prints what Super_resolution/code/export_log_metrics.py turns into CSV rows: run the reference's
+    parser on lines produced by this repo's formatter."""
+    from b200unet.keras.model import format_epoch_line
+    spec = importlib.util.spec_from_file_location("_ref_export_log_metrics",
+                                                  os.path.join(REF, "Super_resolution/code/export_log_metrics.py"))
+    exp = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(exp)
+    logs = {"loss": 0.012345, "psnr": 31.2468, "val_loss": 0.00045678, "val_psnr": 30.5, "learning_rate": 1e-4}
+    row = exp.parse_metrics_line(format_epoch_line(250, 103.4, logs))
+    assert row["steps_completed"] == row["steps_total"] == 250 and row["duration_s"] == 103 and row["ms_per_step"] == 414
+    for k, v in logs.items():
+        assert abs(row[k] - v) <= 5e-5 * max(1.0, abs(v)) + 5e-8, (k, row[k], v)
+    log = tmp_path / "run-simple-1.log"
+    text = ["some banner", "Epoch 1/2", format_epoch_line(250, 103.4, logs), "Epoch 1: val_loss improved from inf to 0.00046",
+            "Epoch 2/2", format_epoch_line(250, 99.0, {**logs, "loss": 0.011}), "Training complete."]
+    log.write_text("\n".join(text) + "\n")
+    rows = exp.extract_epoch_rows(log)
+    assert [int(r["epoch"]) for r in rows] == [1, 2] and abs(rows[1]["loss"] - 0.011) < 1e-6
