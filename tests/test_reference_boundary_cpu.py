@@ -523,3 +523,119 @@ def test_epoch_lines_parse_with_the_reference_log_exporter(tmp_path):
     log.write_text("\n".join(text) + "\n")
     rows = exp.extract_epoch_rows(log)
     assert [int(r["epoch"]) for r in rows] == [1, 2] and abs(rows[1]["loss"] - 0.011) < 1e-6
+
+
+def test_offline_evaluator_artefacts_are_byte_identical(sides, tmp_path):
+    """evaluate_model.py's result files (config.json, metrics.json, per_image_metrics.csv :166-190): the reference's writer and
+    this repo's, on the same results, produce the same bytes."""
+    import dataclasses
+    ref, mine = sides["Super_resolution/code/evaluate_model.py"]
+    assert [f.name for f in dataclasses.fields(ref.EvalResults)] == [f.name for f in dataclasses.fields(mine.EvalResults)]
+    vals = (1.25e-3, 4e-4, 31.25, 1.5, 0.9123, 0.02, float("nan"), float("nan"), 3)
+    per = lambda: [{"index": i, "psnr_y": 30.0 + i, "ssim_y": 0.9 + 0.01 * i, "msssim_y": float("nan"), "mse_y": 1e-3 / (i + 1)}
+                   for i in range(3)]
+    names = ["0801.png#patch0000", "0801.png#patch0001", "0802.png#patch0000"]
+    config = {"model_path": "m.keras", "scale": 0.5, "patch_size": 256, "eval_shave": 4, "samples": 3}
+    out = {}
+    for tag, mod in (("ref", ref), ("mine", mine)):
+        rows = per()
+        mod.attach_filenames(rows, names)
+        mod.write_outputs(tmp_path / tag, mod.EvalResults(*vals), rows, config, True)
+        out[tag] = {f.name: f.read_bytes() for f in sorted((tmp_path / tag).iterdir())}
+        with pytest.raises(ValueError):
+            mod.attach_filenames(per(), names[:2])
+    assert set(out["ref"]) == {"config.json", "metrics.json", "per_image_metrics.csv"}
+    assert out["mine"] == out["ref"]
+    ref.write_outputs(tmp_path / "r2", ref.EvalResults(*vals), per(), config, False)
+    mine.write_outputs(tmp_path / "m2", mine.EvalResults(*vals), per(), config, False)
+    assert sorted(p.name for p in (tmp_path / "m2").iterdir()) == sorted(p.name for p in (tmp_path / "r2").iterdir())
+
+
+def test_sr_training_protocol_matches_the_reference_trainer(sides, tmp_path, monkeypatch, capsys):
+    """Run the reference's ``train(args)`` (its Keras calls land on inert stand-ins that record them) and this repo's
+    ``train(args)`` (``Model.fit`` / ``Model.__call__`` / the metric kernels replaced by recorders: no GPU here) on the same
+    image directory and the same command line.  Compared: the run's ``config.json`` (splits, patch counts, steps per epoch
+    ...), the ``compile`` and ``fit`` arguments, the callbacks and their settings, the checkpoint name, the info line."""
+    cv2 = pytest.importorskip("cv2")
+    import json
+    import torch
+    ref, mine = sides["Super_resolution/code/train_adaptive_unet.py"]
+    from b200unet import metrics as MT
+    from b200unet.keras import clear_session, model as MM
+    data = tmp_path / "hr"
+    data.mkdir()
+    rng = np.random.default_rng(0)
+    for i in range(9):
+        cv2.imwrite(str(data / f"{i:04d}.png"), rng.integers(0, 256, (80, 90, 3), dtype=np.uint8))
+
+    def argv(tag):
+        return ["--scale", "0.5", "--high_res_dir", str(data), "--patch_size", "32", "--batch_size", "4", "--epochs", "3",
+                "--patches_per_image", "3", "--learning_rate", "2e-4", "--patience", "7", "--eval_stride", "24",
+                "--model_dir", str(tmp_path / tag / "m"), "--log_dir", str(tmp_path / tag / "l"), "--run_name", "t"]
+
+    # ---- the reference trainer on stand-ins
+    for name in ("Model", "EarlyStopping", "ModelCheckpoint", "BackupAndRestore"):
+        monkeypatch.setattr(ref, name, MagicMock(name=name))
+    monkeypatch.setattr(sys, "argv", ["train_adaptive_unet.py"] + argv("ref"))
+    ref.train(ref.parse_args())
+    ref_out = capsys.readouterr().out
+    rmodel = ref.Model.return_value
+    r_fit, r_compile = rmodel.fit.call_args, rmodel.compile.call_args
+    r_cfg = json.loads((tmp_path / "ref" / "l" / "t" / "config.json").read_text())
+
+    # ---- this repo's trainer with the GPU work replaced by recorders
+    rec = {}
+
+    def fake_fit(self, x=None, **kw):
+        rec["fit"], rec["model"] = kw, self
+        h = MM.History()
+        h.epoch, h.history = [0, 1, 2], {"loss": [1.0, 0.5, 0.4]}
+        return h
+
+    clear_session()
+    monkeypatch.setattr(MM.Model, "fit", fake_fit)
+    monkeypatch.setattr(MM.Model, "__call__", lambda self, x, training=False: torch.zeros(tuple(x.shape)))
+    monkeypatch.setattr(MT, "eval_luma_metrics",
+                        lambda pred, hr, shave=0: {k: np.ones(len(hr), np.float32) for k in ("psnr", "ssim", "msssim", "mse")})
+    mine.train(mine.parse_args(argv("mine") + ["--host_pipeline"]))
+    mine_out = capsys.readouterr().out
+    m_cfg = json.loads((tmp_path / "mine" / "l" / "t" / "config.json").read_text())
+    clear_session()
+
+    # config.json: same keys in the same order, same values except the output locations and the time stamp
+    assert list(m_cfg) == list(r_cfg)
+    for k in r_cfg:
+        if k not in ("model_dir", "log_dir", "created_at"):
+            assert m_cfg[k] == r_cfg[k], (k, r_cfg[k], m_cfg[k])
+    assert (tmp_path / "mine" / "l" / "t" / "model_summary.txt").exists() and (tmp_path / "ref" / "l" / "t" / "model_summary.txt").exists()
+    # fit(...)
+    for k in ("epochs", "initial_epoch", "steps_per_epoch", "validation_steps", "validation_freq", "verbose"):
+        assert rec["fit"][k] == r_fit.kwargs[k], (k, r_fit.kwargs[k], rec["fit"][k])
+    assert (rec["fit"]["validation_data"] is None) == (r_fit.kwargs["validation_data"] is None)
+    # callbacks, in order, with their settings
+    r_cbs = r_fit.kwargs["callbacks"]
+    m_cbs = rec["fit"]["callbacks"]
+    assert [type(c).__name__ for c in m_cbs] == ["EarlyStopping", "ModelCheckpoint", "BackupAndRestore", "TensorBoard"]
+    assert r_cbs[0] is ref.EarlyStopping.return_value and r_cbs[1] is ref.ModelCheckpoint.return_value
+    assert r_cbs[2] is ref.BackupAndRestore.return_value
+    es, ck = ref.EarlyStopping.call_args.kwargs, ref.ModelCheckpoint.call_args.kwargs
+    assert (m_cbs[0].monitor, m_cbs[0].patience, m_cbs[0].restore_best_weights) == (es["monitor"], es["patience"], es["restore_best_weights"])
+    assert (m_cbs[1].monitor, m_cbs[1].save_best_only) == (ck["monitor"], ck["save_best_only"])
+    assert os.path.basename(m_cbs[1].filepath) == os.path.basename(ck["filepath"]) == \
+        f"unet_adaptive_scale_new_loss0.50_depth{r_cfg['depth']}.keras"
+    assert os.path.basename(str(m_cbs[2].dir)) == os.path.basename(ref.BackupAndRestore.call_args.args[0]) == "train_backup"
+    tb = ref.tf.keras.callbacks.TensorBoard.call_args.kwargs
+    assert os.path.basename(m_cbs[3].log_dir) == os.path.basename(tb["log_dir"]) == "t"
+    # compile(...): Adam with the command-line learning rate, the named loss, the psnr metric, no XLA
+    assert ref.tf.keras.optimizers.Adam.call_args.kwargs == {"learning_rate": 2e-4}
+    opt = rec["model"].optimizer
+    assert type(opt).__name__ == "Adam" and opt.learning_rate == 2e-4 and (opt.beta_1, opt.beta_2, opt.epsilon) == (0.9, 0.999, 1e-7)
+    assert r_compile.kwargs["jit_compile"] is False and r_compile.kwargs["loss"].__name__ == "charbonnier_loss"
+    assert [m.__name__ for m in r_compile.kwargs["metrics"]] == ["psnr"]
+    assert type(rec["model"].loss).__name__ == "SRLoss" and list(rec["model"].loss.metric_names) == ["psnr"]
+    # what the run prints at the end
+    pick = lambda text, head: [ln for ln in text.splitlines() if ln.startswith(head)]
+    assert pick(mine_out, "Model info:") == pick(ref_out, "Model info:")
+    assert pick(mine_out, "Training complete.") == pick(ref_out, "Training complete.") == ["Training complete."]
+    assert [os.path.basename(ln) for ln in pick(mine_out, "Checkpoint saved to:")] == \
+        [os.path.basename(ln) for ln in pick(ref_out, "Checkpoint saved to:")]
