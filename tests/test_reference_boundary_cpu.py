@@ -639,3 +639,98 @@ def test_sr_training_protocol_matches_the_reference_trainer(sides, tmp_path, mon
     assert pick(mine_out, "Training complete.") == pick(ref_out, "Training complete.") == ["Training complete."]
     assert [os.path.basename(ln) for ln in pick(mine_out, "Checkpoint saved to:")] == \
         [os.path.basename(ln) for ln in pick(ref_out, "Checkpoint saved to:")]
+
+
+@pytest.mark.parametrize("protocol", ["A", "B"])
+def test_seg_training_protocol_matches_the_reference_trainer(sides, tmp_path, monkeypatch, capsys, protocol):
+    """The adaptive segmentation trainer (Segmenation/code/train_adaptive_unet.py:463-560), protocols A and B: the reference's
+    train(args) on stand-ins next to this repo's train(args) with fit / evaluate replaced by recorders, same ISIC-style
+    directories and command line.  Compared: config.json, the fit arguments, the callbacks, the optimizer (cosine schedule of
+    protocol A), the loss the protocol builds, the printed validation metrics."""
+    cv2 = pytest.importorskip("cv2")
+    import json
+    ref, mine = sides["Segmenation/code/train_adaptive_unet.py"]
+    from b200unet.keras import clear_session, model as MM
+    rng = np.random.default_rng(1)
+    dirs = {}
+    for split, n in (("train", 11), ("val", 5)):
+        for kind in ("img", "msk"):
+            d = dirs[split, kind] = tmp_path / f"{split}_{kind}"
+            d.mkdir()
+        for i in range(n):
+            cv2.imwrite(str(dirs[split, "img"] / f"ISIC_{i:07d}.jpg"), rng.integers(0, 256, (40, 50, 3), dtype=np.uint8))
+            cv2.imwrite(str(dirs[split, "msk"] / f"ISIC_{i:07d}_segmentation.png"),
+                        (rng.random((40, 50)) > 0.5).astype(np.uint8) * 255)
+
+    def argv(tag):
+        return ["--protocol", protocol, "--train_images", str(dirs["train", "img"]), "--train_masks", str(dirs["train", "msk"]),
+                "--val_images", str(dirs["val", "img"]), "--val_masks", str(dirs["val", "msk"]), "--image_size", "32",
+                "--base_channels", "64", "--depth", "2", "--seed", "5", "--run_name", "r",
+                "--model_dir", str(tmp_path / tag / "m"), "--log_dir", str(tmp_path / tag / "l")]
+
+    metrics = {"loss": 0.4321, "dice_metric": 0.75, "iou_metric": 0.6}
+    # ---- reference on stand-ins
+    for name in ("Model", "EarlyStopping", "ModelCheckpoint", "BackupAndRestore", "TensorBoard", "CosineDecay"):
+        monkeypatch.setattr(ref, name, MagicMock(name=name))
+    rmodel = ref.Model.return_value
+    rmodel.fit.return_value.history = {"loss": [1.0, 0.5]}
+    rmodel.evaluate.return_value = dict(metrics)
+    monkeypatch.setattr(sys, "argv", ["train_adaptive_unet.py"] + argv("ref"))
+    ref.train(ref.parse_args())
+    ref_out = capsys.readouterr().out
+    r_cfg = json.loads((tmp_path / "ref" / "l" / "r" / "config.json").read_text())
+    r_fit = rmodel.fit.call_args
+
+    # ---- this repo's trainer, GPU work replaced
+    rec = {}
+
+    def fake_fit(self, x=None, **kw):
+        rec["fit"], rec["model"] = kw, self
+        h = MM.History()
+        h.epoch, h.history = [0, 1], {"loss": [1.0, 0.5]}
+        return h
+
+    clear_session()
+    monkeypatch.setattr(MM.Model, "fit", fake_fit)
+    monkeypatch.setattr(MM.Model, "evaluate", lambda self, ds, **kw: dict(metrics))
+    mine.train(mine.parse_args(argv("mine")))
+    mine_out = capsys.readouterr().out
+    m_cfg = json.loads((tmp_path / "mine" / "l" / "r" / "config.json").read_text())
+    clear_session()
+
+    assert list(m_cfg) == list(r_cfg)
+    for k in r_cfg:
+        if k != "model_checkpoint":
+            assert m_cfg[k] == r_cfg[k], (k, r_cfg[k], m_cfg[k])
+    assert os.path.basename(m_cfg["model_checkpoint"]) == os.path.basename(r_cfg["model_checkpoint"]) == "r.keras"
+    for k in ("epochs", "verbose"):
+        assert rec["fit"][k] == r_fit.kwargs[k], (k, r_fit.kwargs[k], rec["fit"][k])
+    # callbacks
+    m_cbs, r_cbs = rec["fit"]["callbacks"], r_fit.kwargs["callbacks"]
+    want = ["ModelCheckpoint", "BackupAndRestore", "TensorBoard"] + (["EarlyStopping"] if ref.PROTOCOLS[protocol].early_stopping_patience else [])
+    assert [type(c).__name__ for c in m_cbs] == want and len(r_cbs) == len(want)
+    ck = ref.ModelCheckpoint.call_args.kwargs
+    assert (m_cbs[0].monitor, m_cbs[0].save_best_only) == (ck["monitor"], ck["save_best_only"]) == ("val_dice", True)
+    if "EarlyStopping" in want:
+        es = ref.EarlyStopping.call_args.kwargs
+        assert (m_cbs[3].monitor, m_cbs[3].patience, m_cbs[3].restore_best_weights) == (es["monitor"], es["patience"], True)
+    else:
+        assert not ref.EarlyStopping.called
+    # optimizer: Adam on a cosine schedule over epochs * steps (A) or a constant rate (B)
+    opt = rec["model"].optimizer
+    if ref.PROTOCOLS[protocol].cosine_schedule:
+        cd = ref.CosineDecay.call_args.kwargs
+        sched = opt.learning_rate
+        assert (sched.initial_learning_rate, sched.decay_steps, sched.alpha) == (cd["initial_learning_rate"], cd["decay_steps"], cd["alpha"])
+        assert ref.tf.keras.optimizers.Adam.call_args.kwargs["learning_rate"] is ref.CosineDecay.return_value
+    else:
+        assert not ref.CosineDecay.called
+        assert ref.tf.keras.optimizers.Adam.call_args.kwargs == {"learning_rate": opt.learning_rate} == {"learning_rate": 3e-4}
+    # loss of the protocol and the metrics
+    r_compile = rmodel.compile.call_args.kwargs
+    assert r_compile["loss"].__name__ == rec["model"].loss.__name__ == ("hybrid_ce_dice" if protocol == "A" else "bce_dice")
+    assert (rec["model"].loss.bw, rec["model"].loss.dw) == ((0.4, 0.6) if protocol == "A" else (0.5, 1.0))
+    assert [m.__name__ for m in r_compile["metrics"]] == list(rec["model"].loss.metric_names) == ["dice", "iou"]
+    assert r_compile["jit_compile"] is False
+    tail = lambda text: text[text.index("Validation metrics:"):]
+    assert tail(mine_out) == tail(ref_out)
