@@ -94,7 +94,7 @@ def train(args: argparse.Namespace):
     args.model_dir.mkdir(parents=True, exist_ok=True)
     checkpoint_path = args.model_dir / f"{args.run_name}_best.keras"
     print(f"Checkpoints will be written to {checkpoint_path}")
-    monitor, mode = ("val_dice", "max") if binary else ("val_loss", "min")
+    monitor, mode = ("val_dice_coefficient", "max") if binary else ("val_loss", "min")
     callbacks = [
         ModelCheckpoint(filepath=str(checkpoint_path), monitor=monitor, mode=mode, save_best_only=True, verbose=1),
         EarlyStopping(monitor=monitor, patience=10, mode=mode, restore_best_weights=True, verbose=1),

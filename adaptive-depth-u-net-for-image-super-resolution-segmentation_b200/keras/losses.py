@@ -98,8 +98,9 @@ class BceDiceLoss(_PlanLoss):
     def __init__(self, bce_weight=1.0, dice_weight=0.0, name="bce_dice", global_dice=False):
         self.bw, self.dw = float(bce_weight), float(dice_weight)
         self.__name__ = name
-        if global_dice:      # the baseline trainer's metric: one Dice ratio over the whole batch (unet_vinillia.py:94-99)
-            self.metric_slots = (4, 3)
+        if global_dice:      # the baseline trainer's metric: one Dice ratio over the whole batch (unet_vinillia.py:94-99),
+            # logged under the function's name as keras does ("dice_coefficient" / "val_dice_coefficient", :270-273)
+            self.metric_names, self.metric_slots = ("dice_coefficient", "iou"), (4, 3)
 
     def _more_state(self, plan, st):
         st["ws"] = torch.zeros(1 + 3 * plan.batch, dtype=torch.float32, device=plan.dev)
@@ -189,4 +190,4 @@ class _SegMetric:
 
 dice_metric = _SegMetric(2, "dice")                 # per-sample ratios averaged (Segmenation/code/train_adaptive_unet.py:258-265)
 iou_metric = _SegMetric(3, "iou")
-global_dice_metric = _SegMetric(4, "dice")          # one ratio over the batch (Segmenation/code/unet_vinillia.py:94-99)
+global_dice_metric = _SegMetric(4, "dice_coefficient")   # one ratio over the batch (Segmenation/code/unet_vinillia.py:94-99)

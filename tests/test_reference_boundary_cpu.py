@@ -734,3 +734,107 @@ def test_seg_training_protocol_matches_the_reference_trainer(sides, tmp_path, mo
     assert r_compile["jit_compile"] is False
     tail = lambda text: text[text.index("Validation metrics:"):]
     assert tail(mine_out) == tail(ref_out)
+
+
+def test_baseline_trainers_match_the_reference(sides, tmp_path, monkeypatch, capsys):
+    """The two fixed-depth baselines: Segmenation/code/unet_vinillia.py:236-296 and Super_resolution/code/u-net-vinillia.py:
+    246-290, reference train()/main() on stand-ins next to this repo's with fit / save / evaluation replaced by recorders."""
+    cv2 = pytest.importorskip("cv2")
+    import torch
+    from b200unet.keras import clear_session, model as MM
+    rng = np.random.default_rng(2)
+
+    def recorder(rec):
+        def fake_fit(self, x=None, **kw):
+            rec["fit"], rec["model"], rec["x"] = kw, self, x
+            h = MM.History()
+            h.epoch, h.history = [0], {"loss": [1.0]}
+            return h
+        return fake_fit
+
+    # ---------------------------------------------------------------- segmentation baseline
+    ref, mine = sides["Segmenation/code/unet_vinillia.py"]
+    dirs = {}
+    for split, n in (("train", 7), ("val", 3)):
+        for kind in ("img", "msk"):
+            d = dirs[split, kind] = tmp_path / f"{split}_{kind}"
+            d.mkdir()
+        for i in range(n):
+            cv2.imwrite(str(dirs[split, "img"] / f"ISIC_{i:07d}.jpg"), rng.integers(0, 256, (40, 50, 3), dtype=np.uint8))
+            cv2.imwrite(str(dirs[split, "msk"] / f"ISIC_{i:07d}_segmentation.png"), (rng.random((40, 50)) > 0.5).astype(np.uint8) * 255)
+    argv = lambda tag: ["--train_image_dir", str(dirs["train", "img"]), "--train_mask_dir", str(dirs["train", "msk"]),
+                        "--val_image_dir", str(dirs["val", "img"]), "--val_mask_dir", str(dirs["val", "msk"]),
+                        "--image_size", "32", "--batch_size", "2", "--epochs", "4", "--learning_rate", "3e-4", "--depth", "2",
+                        "--model_dir", str(tmp_path / tag), "--run_name", "v", "--limit_train", "5"]
+    for name in ("Model", "EarlyStopping", "ModelCheckpoint", "ReduceLROnPlateau", "Adam"):
+        monkeypatch.setattr(ref, name, MagicMock(name=name))
+    monkeypatch.setattr(sys, "argv", ["unet_vinillia.py"] + argv("ref"))
+    ref.train(ref.parse_args())
+    ref_out = capsys.readouterr().out
+    rmodel = ref.Model.return_value
+    rec = {}
+    clear_session()
+    monkeypatch.setattr(MM.Model, "fit", recorder(rec))
+    monkeypatch.setattr(MM.Model, "save", lambda self, path: rec.setdefault("saved", str(path)))
+    mine.train(mine.parse_args(argv("mine")))
+    mine_out = capsys.readouterr().out
+    clear_session()
+    first = lambda text, head: [ln for ln in text.splitlines() if ln.startswith(head)][0]
+    assert first(mine_out, "Loaded ") == first(ref_out, "Loaded ") == "Loaded 5 training samples and 3 validation samples."
+    assert os.path.basename(first(mine_out, "Checkpoints will be written to")) == os.path.basename(first(ref_out, "Checkpoints will be written to"))
+    r_fit = rmodel.fit.call_args.kwargs
+    assert (rec["fit"]["epochs"], rec["fit"]["verbose"]) == (r_fit["epochs"], r_fit["verbose"]) == (4, 2)
+    m_cbs = rec["fit"]["callbacks"]
+    assert [type(c).__name__ for c in m_cbs] == ["ModelCheckpoint", "EarlyStopping", "ReduceLROnPlateau"]
+    ck, es, rl = ref.ModelCheckpoint.call_args.kwargs, ref.EarlyStopping.call_args.kwargs, ref.ReduceLROnPlateau.call_args.kwargs
+    assert (m_cbs[0].monitor, m_cbs[0].save_best_only, os.path.basename(m_cbs[0].filepath)) == \
+        (ck["monitor"], ck["save_best_only"], os.path.basename(ck["filepath"])) == ("val_dice_coefficient", True, "v_best.keras")
+    assert (m_cbs[1].monitor, m_cbs[1].patience, m_cbs[1].restore_best_weights) == (es["monitor"], es["patience"], es["restore_best_weights"])
+    assert (m_cbs[2].monitor, m_cbs[2].factor, m_cbs[2].patience, m_cbs[2].min_lr) == (rl["monitor"], rl["factor"], rl["patience"], rl["min_lr"])
+    assert ref.Adam.call_args.kwargs == {"learning_rate": rec["model"].optimizer.learning_rate} == {"learning_rate": 3e-4}
+    assert "dice_coefficient" in rec["model"].loss.metric_names            # keras logs the metric under the function's name
+    assert os.path.basename(rec["saved"]) == os.path.basename(str(rmodel.save.call_args.args[0])) == "v_final.keras"
+
+    # ---------------------------------------------------------------- SR baseline (whole images from an LR and an HR directory)
+    ref, mine = sides["Super_resolution/code/u-net-vinillia.py"]
+    hr_dir, lr_dir = tmp_path / "hr", tmp_path / "lr"
+    hr_dir.mkdir(); lr_dir.mkdir()
+    for i in range(10):
+        img = rng.integers(0, 256, (48, 48, 3), dtype=np.uint8)
+        cv2.imwrite(str(hr_dir / f"{i}.png"), img)
+        cv2.imwrite(str(lr_dir / f"{i}.png"), cv2.resize(cv2.resize(img, (24, 24)), (48, 48)))
+    argv = lambda tag: ["--high_res_dir", str(hr_dir), "--low_res_dir", str(lr_dir), "--hr_size", "32", "--batch_size", "3",
+                        "--epochs", "2", "--learning_rate", "5e-4", "--patience", "4", "--model_dir", str(tmp_path / ("sr_" + tag))]
+    for name in ("Model", "EarlyStopping", "ModelCheckpoint", "BackupAndRestore", "Adam", "build_losses", "evaluate", "make_tf_dataset"):
+        monkeypatch.setattr(ref, name, MagicMock(name=name))
+    ref.build_losses.return_value = ("combined_loss", ["psnr"])
+    ref.evaluate.return_value = {"psnr": (1.0, 0.0)}
+    monkeypatch.setattr(sys, "argv", ["u-net-vinillia.py"] + argv("ref"))
+    ref_args = ref.parse_args()
+    ref_args.seed, ref_args.limit = 1234, None          # read by main() but not declared by the reference's parser
+    ref.main(ref_args)
+    capsys.readouterr()
+    rec = {}
+    clear_session()
+    monkeypatch.setattr(MM.Model, "fit", recorder(rec))
+    monkeypatch.setattr(mine, "evaluate", lambda model, ds: {"psnr": (1.0, 0.0)})
+    mine.main(mine.parse_args(argv("mine")))
+    capsys.readouterr()
+    clear_session()
+    # the same images in the same splits reach fit / evaluation
+    splits = [c.args[2] for c in ref.make_tf_dataset.call_args_list]          # (lr, hr, indices, batch, shuffle, seed)
+    r_lr, r_hr = ref.make_tf_dataset.call_args_list[0].args[:2]
+    assert np.array_equal(rec["x"].lr, r_lr) and np.array_equal(rec["x"].hr, r_hr) and r_hr.shape == (10, 32, 32, 3)
+    assert np.array_equal(rec["x"].idx, splits[0]) and np.array_equal(rec["fit"]["validation_data"].idx, splits[1])
+    assert [c.args[3] for c in ref.make_tf_dataset.call_args_list] == [3, 3, 3] and rec["x"].bs == 3
+    r_fit = ref.Model.return_value.fit.call_args.kwargs
+    assert (rec["fit"]["epochs"], rec["fit"]["verbose"]) == (r_fit["epochs"], r_fit["verbose"]) == (2, 2)
+    m_cbs = rec["fit"]["callbacks"]
+    assert [type(c).__name__ for c in m_cbs] == ["EarlyStopping", "ModelCheckpoint", "BackupAndRestore"]
+    es, ck = ref.EarlyStopping.call_args.kwargs, ref.ModelCheckpoint.call_args.kwargs
+    assert (m_cbs[0].monitor, m_cbs[0].patience, m_cbs[0].restore_best_weights) == (es["monitor"], es["patience"], es["restore_best_weights"])
+    assert (m_cbs[1].monitor, m_cbs[1].save_best_only, os.path.basename(m_cbs[1].filepath)) == \
+        (ck["monitor"], ck["save_best_only"], os.path.basename(ck["filepath"])) == ("val_loss", True, "unet_vanilla_best.keras")
+    assert os.path.basename(str(m_cbs[2].dir)) == os.path.basename(ref.BackupAndRestore.call_args.args[0]) == "train_backup"
+    assert ref.Adam.call_args.kwargs == {"learning_rate": rec["model"].optimizer.learning_rate} == {"learning_rate": 5e-4}
+    assert rec["model"].name == "U-Net_SR_32x32"
