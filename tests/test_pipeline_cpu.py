@@ -181,3 +181,65 @@ def test_host_mirror_equals_the_reference_functions(tmp_path):
         assert np.array_equal(wl, gl) and np.array_equal(wh, gh)
     for (wl, wh), (gl, gh) in zip(ref._iter_grid_patch_pairs(files, 32, 20, 0.5), PL._grid_pairs(files, 32, 20, 0.5)):
         assert np.array_equal(wl, gl) and np.array_equal(wh, gh)
+
+
+class _CpuDeviceDataset:
+    """DevicePatchDataset with its three device calls replaced by CPU equivalents (oracle crop + degrade, index copies), so
+    that the batching / shuffle-pool / epoch logic of __iter__ runs here and can be compared with the host stream."""
+
+    @staticmethod
+    def make(files, patch, scale, batch, monkeypatch, **kw):
+        import torch
+        from b200unet import ops
+        from b200unet.shared import pipeline as PL
+        ds = PL.DevicePatchDataset.__new__(PL.DevicePatchDataset)
+        ds.files, ds.patch, ds.scale, ds.batch_size = list(files), patch, scale, batch
+        ds.per_image, ds.stride, ds.seed = kw.get("per_image", 0), kw.get("stride"), kw.get("seed", 0)
+        ds.shuffle_buffer, ds.infinite = kw.get("shuffle_buffer", 0), kw.get("infinite", False)
+        ds.device, ds.small, ds._epoch, ds._pool = torch.device("cpu"), max(1, int(round(patch * scale))), 0, None
+
+        def patches_of(image_u8, origins):
+            hr = R.crop(image_u8, origins, patch)
+            return torch.from_numpy(PL_degrade(hr)), torch.from_numpy(hr)
+
+        def PL_degrade(hr):
+            return np.stack([PL.degrade_image(p, scale, patch) for p in hr])      # the host stream's own cv2 degrade
+
+        def copy_rows(src, src_rows, dst, dst_rows, n):
+            s = src_rows.long() if src_rows is not None else torch.arange(n)
+            d = dst_rows.long() if dst_rows is not None else torch.arange(n)
+            dst[d] = src[s]
+            return dst
+        ds.patches_of = patches_of
+        monkeypatch.setattr(ops, "copy_rows", copy_rows)
+        return ds
+
+
+@pytest.mark.parametrize("cap", [0, 5, 64])
+def test_device_dataset_batching_logic_on_cpu(tmp_path, monkeypatch, cap):
+    """Finite streams with a shuffle pool (fill, replace, end-of-stream flush), partial last batches, a second pass over the
+    dataset (new shuffle epoch) and the infinite training stream: batch for batch equal to the host PatchDataset."""
+    cv2 = pytest.importorskip("cv2")
+    from b200unet.shared import pipeline as PL
+    rng = np.random.default_rng(0)
+    files = []
+    for i in range(4):
+        path = str(tmp_path / f"im{i}.png")
+        cv2.imwrite(path, rng.integers(0, 256, (int(rng.integers(40, 60)), int(rng.integers(40, 70)), 3), dtype=np.uint8))
+        files.append(path)
+    P, scale, B = 16, 0.5, 5
+    # finite grid stream through a shuffle pool: two passes (the second reshuffles with seed + 1)
+    host = PL.PatchDataset(lambda: PL._grid_pairs(files, P, 24, scale), B, cap, seed=3)
+    dev = _CpuDeviceDataset.make(files, P, scale, B, monkeypatch, stride=24, shuffle_buffer=cap, seed=3)
+    for _ in range(2):
+        hb, db = list(host), list(dev)
+        assert len(hb) == len(db) > 2 and hb[-1][0].shape[0] == db[-1][0].shape[0] < B      # a ragged tail batch
+        for (hl, hh), (dl, dh) in zip(hb, db):
+            assert np.array_equal(hh, dh.numpy()) and np.array_equal(hl, dl.numpy())
+    # infinite random stream (the training dataset)
+    host, _ = PL.make_training_patch_dataset(files, P, 3, scale, B, seed=11, shuffle_buffer=cap)
+    dev = _CpuDeviceDataset.make(files, P, scale, B, monkeypatch, per_image=3, shuffle_buffer=cap, seed=11, infinite=True)
+    for i, ((hl, hh), (dl, dh)) in enumerate(zip(host, dev)):
+        assert np.array_equal(hh, dh.numpy()) and np.array_equal(hl, dl.numpy()), i
+        if i == 30:
+            break
