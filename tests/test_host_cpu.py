@@ -150,3 +150,98 @@ def test_any_module_can_be_the_first_import(first):
             "from b200unet.builders import build_super_resolution_unet; print('ok')")
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and r.stdout.strip().endswith("ok"), r.stderr[-2000:]
+
+
+def test_backward_stream_schedule(monkeypatch):
+    """Model._run_bwd with recording stand-ins for the CUDA streams: every filter-gradient launch goes to the side stream
+    behind a wait on the main stream, everything else stays on the main stream in order, the side stream is joined at the end
+    of the range; with the per-layer Adam switch a layer's kernel range is updated on the side stream only after a wait
+    issued AFTER that layer's dgrad (which reads the weights), and the final optimizer pass covers exactly the rest."""
+    import contextlib
+    import types
+    import torch
+    from b200unet.keras.model import Model
+    from b200unet.parallel import complement_ranges
+
+    log = []
+
+    class FakeStream:
+        def __init__(self, name):
+            self.name = name
+
+        def wait_stream(self, other):
+            log.append(("wait", self.name, other.name))
+
+    main, cur = FakeStream("main"), []
+    cur.append(main)
+
+    @contextlib.contextmanager
+    def use(stream):
+        cur.append(stream)
+        try:
+            yield
+        finally:
+            cur.pop()
+
+    monkeypatch.setattr(torch.cuda, "current_stream", lambda *a, **k: cur[-1])
+    monkeypatch.setattr(torch.cuda, "Stream", lambda *a, **k: FakeStream("side"))
+    monkeypatch.setattr(torch.cuda, "stream", use)
+
+    tags = ["bias_act", "wgrad:tc", "dgrad:tc", "ln", "wgrad:tc", "dgrad:tc", "resize", "ln", "wgrad:simt"]
+    writes = [[(900, 10)], [(200, 100)], [], [(910, 8)], [(100, 100)], [], [], [(918, 4)], [(0, 100)]]
+    plan = types.SimpleNamespace(bwd_tags=tags, bwd_writes=writes,
+                                 bwd_steps=[(lambda i=i: log.append(("run", i, tags[i], cur[-1].name))) for i in range(len(tags))])
+
+    class Opt:
+        def advance(self):
+            log.append(("advance", cur[-1].name))
+
+        def apply_ranges(self, model, ranges):
+            log.append(("adam", tuple(ranges), cur[-1].name))
+
+        def apply(self, model, ranges=None):
+            log.append(("adam_all", cur[-1].name))
+
+    def run(overlap, adam):
+        log.clear()
+        me = types.SimpleNamespace(overlap_wgrad=overlap, overlap_adam=adam, _side_stream=None, _dist=None, optimizer=Opt(),
+                                   G=types.SimpleNamespace(numel=lambda: 1000), _update_ranges=lambda plan: None)
+        Model._run_bwd(me, plan, 0, len(tags))
+        Model._apply_optimizer(me, plan)
+        return list(log)
+
+    # single stream: plain order, one optimizer pass
+    ev = run(False, False)
+    assert [e[1] for e in ev if e[0] == "run"] == list(range(len(tags))) and all(e[3] == "main" for e in ev if e[0] == "run")
+    assert ev[-1] == ("adam_all", "main") and not any(e[0] == "wait" for e in ev)
+
+    # wgrad on the side stream
+    ev = run(True, False)
+    runs = [e for e in ev if e[0] == "run"]
+    assert [e[1] for e in runs] == list(range(len(tags)))
+    for e in runs:
+        assert e[3] == ("side" if e[2].startswith("wgrad") else "main"), e
+    for k, e in enumerate(ev):
+        if e[0] == "run" and e[2].startswith("wgrad"):
+            assert ev[k - 1] == ("wait", "side", "main")               # its dz is final
+    assert ev[-2] == ("wait", "main", "side") and ev[-1] == ("adam_all", "main")   # joined before the optimizer
+
+    # + per-layer Adam behind the wgrad kernels
+    ev = run(True, True)
+    assert ev[0] == ("advance", "main")
+    pos = {("run", i): k for k, e in enumerate(ev) if e[0] == "run" for i in [e[1]]}
+    done = []
+    for k, e in enumerate(ev):
+        if e[0] == "adam" and e[2] == "side":
+            for lo, hi in e[1]:
+                w = next(i for i, wr in enumerate(writes) if (lo, hi - lo) in wr)     # the wgrad step that wrote this range
+                assert tags[w].startswith("wgrad") and pos["run", w] < k                # same stream, after its wgrad
+                dgrads = [i for i in range(w + 1, len(tags)) if tags[i].startswith("dgrad")]
+                if dgrads:                                                              # ... and after a wait issued behind its dgrad
+                    d = pos["run", dgrads[0]]
+                    assert any(ev[j] == ("wait", "side", "main") for j in range(d + 1, k)), (e, d, k)
+                done.append((lo, hi))
+    assert sorted(done) == [(0, 100), (100, 200), (200, 300)]
+    final = [e for e in ev if e[0] == "adam" and e[2] == "main"]
+    assert len(final) == 1 and list(final[0][1]) == complement_ranges(done, 1000) == [(300, 1000)]
+    assert ev.index(("wait", "main", "side")) < ev.index(final[0])
