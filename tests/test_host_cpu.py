@@ -245,3 +245,42 @@ def test_backward_stream_schedule(monkeypatch):
     final = [e for e in ev if e[0] == "adam" and e[2] == "main"]
     assert len(final) == 1 and list(final[0][1]) == complement_ranges(done, 1000) == [(300, 1000)]
     assert ev.index(("wait", "main", "side")) < ev.index(final[0])
+
+
+def test_lowering_structure_on_cpu():
+    """keras/engine.lower (pure graph -> op list): ReLU folded into the producing conv / norm, conv bias gradients routed
+    through the following norm, both concat inputs aliased into the concat buffer (written in place, no copy op), and -- under
+    the bf16 policy -- every 3x3 convolution of the four reference nets selects the tcgen05 kernels (the RGB stems go through
+    the im2col path the Plan adds), including the 32-channel level of the default segmentation width."""
+    import torch
+    from b200unet import builders as B
+    from b200unet.keras import clear_session
+    from b200unet.keras.engine import Plan, lower
+    from b200unet._ffi import ACT_RELU
+    clear_session()
+    nets = {
+        "sr": B.build_super_resolution_unet(0.25, depth_override=4, input_size=128)[0],
+        "sr_vanilla": B.build_vanilla_super_resolution_unet((64, 64, 3), 64, 2),
+        "seg_adaptive": B.build_adaptive_depth_unet(64, 64, 2),
+        "seg_base32": B.build_unet(256, num_classes=21, base_channels=32, depth=4),
+    }
+    for name, model in nets.items():
+        model._compute_dtype = torch.bfloat16
+        ops_, _ = lower(model)
+        kinds = [op.kind for op in ops_]
+        assert "activation" not in kinds and set(kinds) <= {"cast_input", "conv", "ln", "bn", "resize", "maxpool", "convT",
+                                                            "concat", "clipadd", "softmax"}, (name, set(kinds))
+        norms = [op for op in ops_ if op.kind in ("ln", "bn")]
+        assert norms and all(op.relu and op.conv_src is not None and op.conv_src.norm_bias for op in norms), name
+        concats = [op for op in ops_ if op.kind == "concat"]
+        assert concats and all(not op.copies for op in concats), name           # skip-concat written in place
+        for op in concats:
+            a, b = op.inputs
+            assert a.parent is op.output and b.parent is op.output and (a.offset, b.offset) == (0, a.c)   # [up, skip]
+        convs3 = [op for op in ops_ if op.kind == "conv" and op.layer.kernel_size == (3, 3)]
+        stems = [op for op in convs3 if op.inputs[0].c == 3]
+        assert len(stems) == 1 and all(Plan.is_tc(op) for op in convs3 if op not in stems), name
+        plain = [op for op in convs3 if not op.norm_bias]                       # decoder post-upsample conv: bias + ReLU epilogue
+        assert all(op.act == ACT_RELU for op in plain), name
+    assert {op.output.c for op in lower(nets["seg_base32"])[0] if op.kind == "conv"} == {32, 64, 128, 256, 512, 21}
+    clear_session()
