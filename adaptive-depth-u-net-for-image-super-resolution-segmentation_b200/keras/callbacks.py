@@ -35,6 +35,11 @@ def _better(mode, monitor):
 
 
 class EarlyStopping(Callback):
+    """keras 3 semantics (the reference pins keras==3.3.3): ``wait`` counts epochs without an improvement of more than
+    ``min_delta``; training stops when it reaches ``patience`` (never after the very first epoch); with
+    ``restore_best_weights`` the best epoch's weights are put back at the END of training -- also when ``fit`` ran out of
+    epochs without stopping early."""
+
     def __init__(self, monitor="val_loss", min_delta=0.0, patience=0, verbose=0, mode="auto", restore_best_weights=False,
                  **kwargs):
         self.monitor, self.min_delta, self.patience, self.verbose = monitor, abs(min_delta), patience, verbose
@@ -42,29 +47,31 @@ class EarlyStopping(Callback):
         self._cmp, self._worst = _better(mode, monitor)
 
     def on_train_begin(self, logs=None):
-        self.best, self.wait, self.best_weights, self.stopped_epoch = self._worst, 0, None, 0
+        self.best, self.wait, self.best_weights, self.stopped_epoch, self.best_epoch = self._worst, 0, None, 0, 0
 
     def on_epoch_end(self, epoch, logs=None):
         cur = (logs or {}).get(self.monitor)
         if cur is None:
             return
+        if self.restore_best_weights and self.best_weights is None:      # nothing recorded yet: these are the best so far
+            self.best_weights, self.best_epoch = self.model.get_weights(), epoch
         if self._cmp(cur, self.best, self.min_delta):
-            self.best, self.wait = cur, 0
+            self.best, self.wait, self.best_epoch = cur, 0, epoch
             if self.restore_best_weights:
                 self.best_weights = self.model.get_weights()
-        else:
-            self.wait += 1
-            if self.wait >= self.patience and epoch > 0:
-                self.stopped_epoch = epoch
-                self.model.stop_training = True
-                if self.restore_best_weights and self.best_weights is not None:
-                    if self.verbose:
-                        print("Restoring model weights from the end of the best epoch.")
-                    self.model.set_weights(self.best_weights)
+            return
+        self.wait += 1
+        if self.wait >= self.patience and epoch > 0:
+            self.stopped_epoch = epoch
+            self.model.stop_training = True
 
     def on_train_end(self, logs=None):
         if self.stopped_epoch and self.verbose:
             print(f"Epoch {self.stopped_epoch + 1}: early stopping")
+        if self.restore_best_weights and self.best_weights is not None:
+            if self.verbose:
+                print(f"Restoring model weights from the end of the best epoch: {self.best_epoch + 1}.")
+            self.model.set_weights(self.best_weights)
 
 
 class ModelCheckpoint(Callback):
