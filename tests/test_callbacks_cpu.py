@@ -148,3 +148,59 @@ def test_backup_and_restore_state_files(tmp_path, monkeypatch):
     assert float(fresh.restored[1][0]) == 2.0
     cb2.on_train_end()
     assert not list((tmp_path / "bk").iterdir())
+
+
+def test_fit_loop_semantics_on_cpu(monkeypatch, capsys):
+    """Model.fit's epoch loop with the GPU step replaced: steps per epoch (an infinite stream keeps its position across epochs,
+    a finite one restarts), epoch logs = mean over the steps, validation every validation_freq epochs under val_ names,
+    learning_rate in the logs, History layout, initial_epoch, EarlyStopping ending the loop, the verbose=2 lines."""
+    import itertools
+    import torch
+    from b200unet import builders as B
+    from b200unet.keras import clear_session
+    from b200unet.keras.optimizers import Adam
+    clear_session()
+    model, _ = B.build_super_resolution_unet(0.5, depth_override=1, input_size=16)
+    model.compile(optimizer=Adam(learning_rate=2e-4), loss="charbonnier")
+    seen = []
+
+    def fake_step(x, y, return_tensors=False):
+        seen.append(int(x[0]))
+        return {"loss": torch.tensor(float(x[0])), "psnr": torch.tensor(30.0 + len(seen))}
+
+    monkeypatch.setattr(model, "train_on_batch", fake_step)
+    val_calls = []
+    monkeypatch.setattr(model, "evaluate", lambda ds, steps=None, return_dict=False, verbose=0:
+                        (val_calls.append(steps) or {"loss": 0.5 / len(val_calls), "psnr": 20.0 + len(val_calls)}))
+    batches = lambda: ((np.full((2,), i), np.zeros(2)) for i in itertools.count())
+    hist = model.fit(batches(), epochs=3, steps_per_epoch=4, validation_data=[1], validation_steps=7, validation_freq=2, verbose=2)
+    assert seen == list(range(12))                                             # the stream is not rewound between epochs
+    assert hist.epoch == [0, 1, 2]
+    assert hist.history["loss"] == [1.5, 5.5, 9.5]                             # mean over the epoch's steps
+    assert hist.history["val_loss"] == [0.5] and hist.history["val_psnr"] == [21.0] and val_calls == [7]   # only epoch 2
+    assert hist.history["learning_rate"] == [2e-4] * 3
+    out = capsys.readouterr().out
+    assert "Epoch 2/3" in out and " - loss: 5.5000 - psnr: " in out and "val_loss: 0.5000" in out and "learning_rate: 2.0000e-04" in out
+    # a finite dataset without steps_per_epoch: one pass per epoch, restarted every epoch
+    seen.clear()
+    finite = [(np.full((2,), i), np.zeros(2)) for i in range(3)]
+    hist = model.fit(finite, epochs=2, verbose=0)
+    assert seen == [0, 1, 2, 0, 1, 2] and hist.history["loss"] == [1.0, 1.0]
+    # ... and with steps_per_epoch larger than the dataset it wraps around
+    seen.clear()
+    model.fit(finite, epochs=1, steps_per_epoch=5, verbose=0)
+    assert seen == [0, 1, 2, 0, 1]
+    # initial_epoch skips epochs; EarlyStopping ends the loop
+    seen.clear()
+    hist = model.fit(batches(), epochs=5, initial_epoch=3, steps_per_epoch=1, verbose=0)
+    assert hist.epoch == [3, 4] and len(seen) == 2
+    seen.clear()
+    val_calls.clear()
+    monkeypatch.setattr(model, "evaluate", lambda ds, steps=None, return_dict=False, verbose=0:
+                        (val_calls.append(steps) or {"loss": 1.0 + len(val_calls)}))
+    monkeypatch.setattr(model, "get_weights", lambda: [np.zeros(1)])
+    monkeypatch.setattr(model, "set_weights", lambda w: None)
+    hist = model.fit(batches(), epochs=10, steps_per_epoch=1, validation_data=[1], verbose=0,
+                     callbacks=[EarlyStopping(monitor="val_loss", patience=2, restore_best_weights=True)])
+    assert hist.epoch == [0, 1, 2] and model.stop_training
+    clear_session()
