@@ -204,3 +204,37 @@ def test_fit_loop_semantics_on_cpu(monkeypatch, capsys):
                      callbacks=[EarlyStopping(monitor="val_loss", patience=2, restore_best_weights=True)])
     assert hist.epoch == [0, 1, 2] and model.stop_training
     clear_session()
+
+
+def test_cosine_decay_and_adam_host_bookkeeping():
+    """CosineDecay as keras defines it (Segmenation/code/train_adaptive_unet.py:451-460), and Adam's host side: the
+    schedule is evaluated at the 0-based count of updates already made, the device-resident hyper-parameters are pushed when
+    the rate changes, (1 - beta) is formed in double precision before rounding to float32."""
+    import math
+    import types
+    import torch
+    from b200unet.keras.optimizers import Adam, CosineDecay
+    sched = CosineDecay(initial_learning_rate=1e-3, decay_steps=100, alpha=0.0)
+    for step in (0, 1, 25, 50, 99, 100, 250):
+        s = min(step, 100)
+        assert sched(step) == pytest.approx(1e-3 * 0.5 * (1.0 + math.cos(math.pi * s / 100)), rel=1e-12, abs=1e-18)
+    assert sched(0) == 1e-3 and sched(100) == pytest.approx(0.0, abs=1e-18) and sched(10 ** 6) == sched(100)
+    assert CosineDecay(1e-3, 10, alpha=0.1)(10) == pytest.approx(1e-4)
+    opt = Adam(learning_rate=sched)
+    fake = types.SimpleNamespace(P=torch.zeros(4))
+    opt.ensure_state(fake)
+    h = opt._state["hyper"]
+    assert h.dtype == torch.float32 and h.tolist()[:4] == [np.float32(1e-3), np.float32(0.9), np.float32(0.999), np.float32(1e-7)]
+    assert h[4].item() == np.float32(1 - 0.9) and h[5].item() == np.float32(1 - 0.999)     # double precision, then rounded
+    assert h[5].item() != np.float32(np.float32(1) - np.float32(0.999))                      # ... not float32 arithmetic
+    lrs = []
+    for _ in range(3):
+        opt.before_step()
+        lrs.append(opt._state["hyper"][0].item())
+    assert lrs == [np.float32(sched(0)), np.float32(sched(1)), np.float32(sched(2))] and opt.iterations == 3
+    const = Adam(learning_rate=3e-4)
+    const.ensure_state(fake)
+    const.before_step()
+    assert const.current_lr() == 3e-4 and const._state["hyper"][0].item() == np.float32(3e-4)
+    const.set_learning_rate(1.5e-4)                       # what ReduceLROnPlateau calls
+    assert const._state["hyper"][0].item() == np.float32(1.5e-4)
