@@ -334,13 +334,20 @@ class Model:
 
     # ------------------------------------------------------------------ summary
     def summary(self, print_fn=print, line_length=78):
-        rows = []
+        # one row per LAYER, as keras prints it: a layer called several times (the shared enc_down / dec_up resizes) appears
+        # where it is first called, with the inputs of all its calls and the output shape of its last call
+        rows, first = [], {}
         for nd in self._nodes:
             ly = nd.layer
-            conn = ", ".join(t.name for t in nd.inputs) or "-"
+            conn = [t.name for t in nd.inputs]
             shape = "(" + ", ".join("None" if d is None else str(d) for d in nd.output.shape) + ")"
-            params = ly.count_params() if nd.call_index == 0 else 0
-            rows.append((f"{ly.name} ({type(ly).__name__})", shape, f"{params:,}", conn))
+            if id(ly) in first:
+                row = rows[first[id(ly)]]
+                row[1], row[3] = shape, row[3] + conn
+                continue
+            first[id(ly)] = len(rows)
+            rows.append([f"{ly.name} ({type(ly).__name__})", shape, f"{ly.count_params():,}", conn])
+        rows = [(a, b, c, ", ".join(d) or "-") for a, b, c, d in rows]
         w = [max(len(r[i]) for r in rows + [("Layer (type)", "Output Shape", "Param #", "Connected to")]) for i in range(4)]
         fmt = lambda r: " | ".join(s.ljust(w[i]) for i, s in enumerate(r))
         print_fn(f'Model: "{self.name}"')

@@ -70,3 +70,81 @@ def test_sr_flops():
     assert abs(M.sr_flops_per_sample(0.5, 3, 64) / 1e9 - 6.811) < 1e-3
     assert abs(M.sr_flops_per_sample(0.25, 4, 128) / 1e9 - 12.331) < 1e-3
     assert abs(M.sr_flops_per_sample(0.25, 5, 128) / 1e9 - 12.539) < 1e-3
+
+
+def _keras_summary_rows(text):
+    """Rows of a keras 3 ``model.summary()`` table: [(layer name, type, output shape, params, connected-to)], cells that
+    keras wrapped over several lines re-joined, names / types / inputs it truncated kept with their '…'."""
+    rows, cur = [], None
+    for line in text.splitlines():
+        if line.startswith(("├", "└", "┡")):
+            if cur:
+                rows.append(cur)
+            cur = None
+            continue
+        if line.startswith("│"):
+            cells = [c.strip() for c in line.strip("│").split("│")]
+            if cur is None:
+                cur = [[c] if c else [] for c in cells]
+            else:
+                for acc, c in zip(cur, cells):
+                    if c:
+                        acc.append(c)
+    out = []
+    for name_cell, shape, params, conn in rows:
+        joined = " ".join(name_cell)
+        name, _, typ = joined.partition(" (")
+        out.append((name.strip(), typ.rstrip(")").strip(), " ".join(shape), int(params[0].replace(",", "")),
+                    [c.rstrip(",") for c in conn]))
+    return out
+
+
+def test_reference_summaries_row_by_row():
+    """Every row of the reference's 15 keras ``model.summary()`` dumps -- produced by the real Keras implementation of the
+    model -- against this repo's builder: layer order, names, types, output shapes, parameter counts, and which layers feed
+    which (the concat order [up, skip], the shared resize layers)."""
+    root = "/root/reference/Super_resolution/experiments"
+    if not os.path.isdir(root):
+        pytest.skip("reference not mounted (GPU box)")
+    import glob
+    import re
+    from b200unet import builders as B
+    from b200unet.keras import clear_session
+    files = sorted(glob.glob(os.path.join(root, "*", "model_summary", "*.txt")))
+    assert len(files) == 15
+    checked = 0
+
+    def same(ref, mine):          # keras truncates long cells with an ellipsis
+        return mine.startswith(ref[:-1]) if ref.endswith("…") else ref == mine
+
+    for f in files:
+        txt = open(f, encoding="utf-8").read()
+        m = re.search(r'Model: "U-Net_SR_scale([0-9.]+)_depth(\d+)"', txt)
+        scale, depth = float(m.group(1)), int(m.group(2))
+        clear_session()
+        model, _ = B.build_super_resolution_unet(scale, depth_override=depth, input_size=256)
+        assert f'Model: "{model.name}"' in txt
+        mine = []
+        model.summary(print_fn=mine.append)
+        mine_rows = []
+        for line in mine:
+            parts = [p.strip() for p in line.split("|")]
+            if len(parts) == 4 and parts[0] not in ("Layer (type)",) and not set(parts[0]) <= set("-+"):
+                name, _, typ = parts[0].partition(" (")
+                mine_rows.append((name, typ.rstrip(")"), parts[1], int(parts[2].replace(",", "")), parts[3].split(", ")))
+        ref_rows = _keras_summary_rows(txt)
+        assert len(ref_rows) == len(mine_rows) > 20, f
+        for (rn, rt, rs, rp, rc), (mn, mt, ms, mp, mc) in zip(ref_rows, mine_rows):
+            if rt == "ClipAdd":      # some dumps predate the rename; the reference keeps ClipAdd as an alias (custom_layers.py:142)
+                rt = "ClippedResidualAdd"
+            assert same(rn, mn) and same(rt, mt), (f, rn, rt, mn, mt)
+            assert rp == mp, (f, rn, rp, mp)
+            assert rs == ms, (f, rn, rs, ms)          # a shared layer's row shows the shape of its LAST call, as keras does
+            if rc != ["-"]:
+                assert len(rc) == len(mc) and all(same(a, b) for a, b in zip(rc, mc)), (f, rn, rc, mc)
+            checked += 1
+        for key in ("Total params", "Trainable params", "Non-trainable params"):
+            want = re.search(rf"{key}: ([0-9,]+)", txt).group(1)
+            assert any(re.search(rf"{key}: {want}\b", line) for line in mine), (f, key, want)
+    clear_session()
+    assert checked == 885          # rows of the 15 dumps
