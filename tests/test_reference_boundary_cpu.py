@@ -838,3 +838,88 @@ def test_baseline_trainers_match_the_reference(sides, tmp_path, monkeypatch, cap
     assert os.path.basename(str(m_cbs[2].dir)) == os.path.basename(ref.BackupAndRestore.call_args.args[0]) == "train_backup"
     assert ref.Adam.call_args.kwargs == {"learning_rate": rec["model"].optimizer.learning_rate} == {"learning_rate": 5e-4}
     assert rec["model"].name == "U-Net_SR_32x32"
+
+
+def test_offline_evaluator_main_matches_and_real_artefacts_agree(sides, tmp_path, monkeypatch, capsys):
+    """evaluate_model.py end to end (model loading and the metric loop replaced on both sides by the same recorder): the
+    reference's main() and this repo's main(argv) over the same image directory write the same config.json (but the time
+    stamp), metrics.json and per_image_metrics.csv, patch labels included, and print the same report.  Then the REAL
+    artefacts the reference shipped (experiments/*/evaluation/*: produced by its evaluator on DIV2K) are read: same keys in
+    the same order as this repo's files, the recorded eval_shave equals infer_eval_shave(scale), the label format matches."""
+    cv2 = pytest.importorskip("cv2")
+    import glob
+    import json
+    import re
+    ref, mine = sides["Super_resolution/code/evaluate_model.py"]
+    data = tmp_path / "hr"
+    data.mkdir()
+    rng = np.random.default_rng(4)
+    for i in (801, 802, 810):
+        cv2.imwrite(str(data / f"{i:04d}.png"), rng.integers(0, 256, (70 + i % 7, 100, 3), dtype=np.uint8))
+
+    def fake_eval(mod):
+        def evaluate(model, dataset, eval_shave):
+            rows, k = [], 0
+            for lr, hr in dataset:
+                assert lr.shape == hr.shape and lr.shape[1:] == (32, 32, 3)
+                for j in range(len(hr)):
+                    rows.append({"index": k, "psnr_y": 30.0 + float(np.mean(hr[j])), "ssim_y": 0.9, "msssim_y": float("nan"),
+                                 "mse_y": float(np.mean((lr[j] - hr[j]) ** 2))})
+                    k += 1
+            return mod.EvalResults(1e-3, 1e-4, 30.0, 1.0, 0.9, 0.01, float("nan"), float("nan"), len(rows)), rows
+        return evaluate
+
+    argv = lambda tag: ["--model-path", str(tmp_path / "m.keras"), "--scale", "0.3", "--hr-dir", str(data), "--patch-size", "32",
+                        "--eval-stride", "24", "--batch-size", "4", "--output-dir", str(tmp_path / tag), "--run-name", "e"]
+    outs = {}
+    for tag, mod in (("ref", ref), ("mine", mine)):
+        monkeypatch.setattr(mod, "load_checkpoint_model", lambda *a, **k: "model")
+        monkeypatch.setattr(mod, "evaluate", fake_eval(mod))
+        if tag == "ref":
+            # the reference wraps its generator in tf.data; hand it the host mirror's dataset (same generator, same labels:
+            # tests/test_pipeline_cpu.py) so that its main() has batches to iterate
+            from b200unet.shared.pipeline import make_eval_patch_dataset
+            monkeypatch.setattr(ref, "make_eval_patch_dataset", make_eval_patch_dataset)
+            monkeypatch.setattr(sys, "argv", ["evaluate_model.py"] + argv(tag))
+            ref.main()
+        else:
+            mine.main(argv(tag) + ["--host-pipeline"])
+        outs[tag] = capsys.readouterr().out
+    files = {tag: {p.name: p.read_text() for p in sorted((tmp_path / tag / "e").iterdir())} for tag in ("ref", "mine")}
+    assert set(files["ref"]) == {"config.json", "metrics.json", "per_image_metrics.csv"}
+    assert files["mine"]["metrics.json"] == files["ref"]["metrics.json"]
+    assert files["mine"]["per_image_metrics.csv"] == files["ref"]["per_image_metrics.csv"]
+    rc, mc = json.loads(files["ref"]["config.json"]), json.loads(files["mine"]["config.json"])
+    assert list(rc) == list(mc) and {k: v for k, v in rc.items() if k != "created_at"} == {k: v for k, v in mc.items() if k != "created_at"}
+    assert rc["eval_shave"] == 6 and rc["samples"] > 10 and rc["images"] == 3
+    strip = lambda text: [ln for ln in text.splitlines() if not ln.startswith("[done]")]
+    assert strip(outs["mine"]) == strip(outs["ref"]) and outs["ref"].startswith("Evaluated ")
+
+    # the reference's own dataset factories (tf.data calls land on stand-ins): patch counts and labels equal the mirror's
+    from b200unet.shared import pipeline as PL
+    RP = sys.modules["shared.pipeline"]
+    pngs = PL.sorted_alphanumeric(glob.glob(str(data / "*.png")))
+    for stride in (None, 24, 40):
+        _, r_total, r_labels = RP.make_eval_patch_dataset(pngs, patch_size=32, scale=0.3, batch_size=4, stride=stride)
+        _, m_total, m_labels = PL.make_eval_patch_dataset(pngs, 32, 0.3, 4, stride=stride)
+        assert (r_total, r_labels) == (m_total, m_labels) and r_total == len(r_labels) > 0
+    assert RP.make_training_patch_dataset(pngs, 32, 5, 0.5, 4, seed=1)[1] == PL.make_training_patch_dataset(pngs, 32, 5, 0.5, 4, 1)[1] == 15
+    for bad in (dict(hr_files=[], patch_size=32, patches_per_image=1), dict(hr_files=pngs, patch_size=32, patches_per_image=0)):
+        for fn in (RP.make_training_patch_dataset, PL.make_training_patch_dataset):
+            with pytest.raises(ValueError):
+                fn(bad["hr_files"], bad["patch_size"], bad["patches_per_image"], 0.5, 4, 0)
+
+    # the artefacts of the reference's own evaluation runs
+    real = sorted(glob.glob(os.path.join(REF, "Super_resolution/experiments/*/evaluation/*/config.json")))
+    assert len(real) >= 15
+    for cfg_path in real:
+        cfg = json.loads(open(cfg_path).read())
+        assert list(cfg) == list(mc), cfg_path
+        assert cfg["eval_shave"] == mine.infer_eval_shave(cfg["scale"], None), cfg_path
+        met = json.loads(open(os.path.join(os.path.dirname(cfg_path), "metrics.json")).read())
+        assert list(met) == list(json.loads(files["mine"]["metrics.json"])) and met["samples"] == cfg["samples"]
+        with open(os.path.join(os.path.dirname(cfg_path), "per_image_metrics.csv")) as handle:
+            head, first = handle.readline().strip(), handle.readline().strip()
+        assert head == files["mine"]["per_image_metrics.csv"].splitlines()[0]
+        assert re.match(r"^0,\d{4}\.png#patch0000,", first), first
+        assert re.match(r"^0,\d{4}\.png#patch0000,", files["mine"]["per_image_metrics.csv"].splitlines()[1])
