@@ -85,12 +85,17 @@ def evaluate(model, dataset, eval_shave: int) -> Tuple[EvalResults, List[Dict[st
     if not per_image:
         raise RuntimeError("Evaluation dataset yielded no samples.")
 
+    return summarise(vals, len(per_image)), per_image
+
+
+def summarise(vals: Dict[str, List[np.ndarray]], samples: int) -> EvalResults:
+    """Run-level statistics of the per-patch values (reference :146-163): float64 mean and POPULATION standard deviation."""
     def stats(v):
         arr = np.concatenate(v, axis=0).astype(np.float64)
         return float(np.mean(arr)), float(np.std(arr))
 
     (mse_m, mse_s), (ps_m, ps_s), (ss_m, ss_s), (ms_m, ms_s) = (stats(vals[k]) for k in ("mse", "psnr", "ssim", "msssim"))
-    return EvalResults(mse_m, mse_s, ps_m, ps_s, ss_m, ss_s, ms_m, ms_s, len(per_image)), per_image
+    return EvalResults(mse_m, mse_s, ps_m, ps_s, ss_m, ss_s, ms_m, ms_s, samples)
 
 
 def attach_filenames(per_image: List[Dict[str, float]], filenames: Sequence[str]) -> None:

@@ -923,3 +923,15 @@ def test_offline_evaluator_main_matches_and_real_artefacts_agree(sides, tmp_path
         assert head == files["mine"]["per_image_metrics.csv"].splitlines()[0]
         assert re.match(r"^0,\d{4}\.png#patch0000,", first), first
         assert re.match(r"^0,\d{4}\.png#patch0000,", files["mine"]["per_image_metrics.csv"].splitlines()[1])
+        # run-level statistics: this repo's aggregation of the reference's per-patch values reproduces its metrics.json
+        import csv
+        import dataclasses
+        with open(os.path.join(os.path.dirname(cfg_path), "per_image_metrics.csv")) as handle:
+            rows = list(csv.DictReader(handle))
+        vals = {k: [np.array([float(r[k + "_y"]) for r in rows], dtype=np.float32)] for k in ("psnr", "ssim", "msssim", "mse")}
+        got = dataclasses.asdict(mine.summarise(vals, len(rows)))
+        for key, want in met.items():
+            if isinstance(want, float) and not np.isfinite(want):
+                assert not np.isfinite(got[key]), (cfg_path, key)            # a patch with zero error: PSNR = inf
+            else:
+                assert got[key] == pytest.approx(want, rel=1e-12, abs=0.0), (cfg_path, key, want, got[key])
