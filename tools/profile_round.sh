@@ -3,6 +3,8 @@
 #   bash tools/profile_round.sh r01_v7 launches   plain bench JSON line, ncu launch list of the same command, conv/HBM tables
 #   bash tools/profile_round.sh r01_v7 traffic    DRAM bytes + tensor-pipe % of every conv/wgrad launch of one step (light metric set)
 #   bash tools/profile_round.sh r01_v7 full       `ncu --set full` of 24 consecutive conv3x3_tc/wgrad3x3_tc launches of one step
+#   bash tools/profile_round.sh r01_v7 widen      the rows next to the hot path: single- vs two-stream step, BASELINE configs 4 / 5,
+#                                                 patch-pipeline / eval-metric kernel bandwidth, DP check on one GPU (gloo)
 tag=${1:-r01}
 what=${2:-launches}
 out=gpurun_out
@@ -14,6 +16,21 @@ if [ "$what" = "launches" ]; then
   python tools/conv_table.py c2 2>&1 | grep "^hw" > $out/${tag}_conv_table_c2.txt
   python tools/mem_table.py > $out/${tag}_mem_table.txt 2>&1
   head -c 300 $out/${tag}_bench.json; echo
+elif [ "$what" = "widen" ]; then
+  B200_OVERLAP_WGRAD=0 python bench.py --no-cpu-baseline > $out/${tag}_bench_c2_n1_single_stream.json 2> /dev/null
+  python bench.py --no-cpu-baseline > $out/${tag}_bench_c2_n1.json 2> /dev/null
+  python tools/config_sweep.py c4 > $out/${tag}_c4_base32.json 2> /dev/null
+  python tools/config_sweep.py c5 > $out/${tag}_c5.json 2> /dev/null
+  python tools/pipeline_bench.py > $out/${tag}_pipeline_bench.jsonl 2> /dev/null
+  B200_BUCKET_MB=4 B200_DP_SHARD=0 B200_DP_CHECK_ONE_GPU=1 timeout -s KILL 120 python -m torch.distributed.run --nnodes=1 \
+      --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29517 tools/dp_check.py > $out/${tag}_dp_check_one_gpu_gloo.log 2>&1
+  python -c "
+import json
+for f in ('bench_c2_n1_single_stream', 'bench_c2_n1'):
+    d = json.load(open('$out/${tag}_%s.json' % f)); print(f, round(d['value']), d['ms_per_step'])
+for f in ('c4_base32', 'c5'):
+    d = json.load(open('$out/${tag}_%s.json' % f)); print(f, {k: v for k, v in d.items() if k in ('ms_per_step', 'ms_per_batch', 'images_per_s')})
+"; tail -1 $out/${tag}_dp_check_one_gpu_gloo.log | cut -c1-200
 elif [ "$what" = "traffic" ]; then
   # DRAM bytes / tensor-pipe cycles of EVERY conv3x3_tc / wgrad launch of one step (same population as bench's `achieved`)
   B200_NO_CUDA_GRAPH=1 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active \
