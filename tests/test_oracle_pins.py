@@ -148,3 +148,19 @@ def test_reference_summaries_row_by_row():
             assert any(re.search(rf"{key}: {want}\b", line) for line in mine), (f, key, want)
     clear_session()
     assert checked == 885          # rows of the 15 dumps
+
+
+def test_resize_rule_matches_pillow():
+    """A third independent implementation of the antialiased triangle filter: Pillow's float ('F' mode) BILINEAR resize
+    (support widened by the shrink factor, weights at pixel centres, renormalised at the borders -- the algorithm
+    tf.image.resize(antialias=True) states it follows) against the ScaleAndTranslate restatement, shrinking and enlarging,
+    non-square."""
+    Image = pytest.importorskip("PIL.Image")
+    rng = np.random.default_rng(0)
+    for a, b in [(256, 180), (126, 89), (77, 24), (128, 32), (8, 2), (2, 1), (32, 128), (45, 63), (100, 100), (256, 52),
+                 (63, 45), (1, 2)]:
+        x = rng.random((a, a + 3), dtype=np.float32)
+        oh, ow = b, max(1, int(round((a + 3) * b / a)))
+        want = np.asarray(Image.fromarray(x, mode="F").resize((ow, oh), Image.BILINEAR), dtype=np.float32)
+        got = K.resize_bilinear(torch.from_numpy(x)[None, :, :, None], oh, ow, True)[0, :, :, 0].numpy()
+        assert np.abs(got - want).max() < 2e-5, (a, b)
