@@ -42,7 +42,13 @@ class Filter(C.Structure):
     ]
 
 
+class Scratch(C.Structure):
+    """struct b200_scratch"""
+    _fields_ = [("ptr", C.c_void_p), ("bytes", C.c_size_t)]
+
+
 _TP = C.POINTER(Tensor)
+_SP = C.POINTER(Scratch)
 _FP = C.POINTER(Filter)
 _vp, _i, _f, _sz = C.c_void_p, C.c_int, C.c_float, C.c_size_t
 
@@ -52,18 +58,18 @@ SIGNATURES = {
     "b200_last_error": (C.c_char_p, []),
     "b200_device_info": (_i, [C.POINTER(_i)] * 3),
     "b200_launch_count": (C.c_longlong, [_i]),
-    "b200_conv2d_fprop": (_i, [_TP, _FP, _vp, _TP, _i, _i, _vp]),
-    "b200_conv2d_ln_fprop": (_i, [_TP, _FP, _vp, _vp, _vp, _f, _i, _TP, _TP, _vp, _vp, _i, _vp]),
-    "b200_conv2d_dgrad": (_i, [_TP, _FP, _TP, _i, _i, _vp]),
-    "b200_set_workspace": (_i, [_vp, _sz]),
+    "b200_conv2d_fprop": (_i, [_TP, _FP, _vp, _TP, _i, _i, _SP, _vp]),
+    "b200_conv2d_ln_fprop": (_i, [_TP, _FP, _vp, _vp, _vp, _f, _i, _TP, _TP, _vp, _vp, _i, _SP, _vp]),
+    "b200_conv2d_dgrad": (_i, [_TP, _FP, _TP, _i, _i, _SP, _vp]),
     "b200_conv2d_workspace": (_sz, [_TP, C.POINTER(Filter), _i]),
     "b200_conv2d_wgrad_workspace": (_sz, [_TP, _TP, _i, _i, _i]),
     "b200_conv2d_wgrad": (_i, [_TP, _TP, _i, _i, _vp, _vp, _sz, _i, _vp]),
     "b200_conv2d_wgrad_atomic": (_i, [_TP, _TP, _i, _i, _vp, _vp]),
     "b200_filter_pack": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "b200_im2col3x3": (_i, [_TP, _TP, _vp]),
-    "b200_convT2x2_fprop": (_i, [_TP, _vp, _vp, _i, _TP, _vp]),
-    "b200_convT2x2_dgrad": (_i, [_TP, _vp, _i, _TP, _vp]),
+    "b200_convT2x2_fprop": (_i, [_TP, _vp, _vp, _i, _TP, _SP, _vp]),
+    "b200_convT2x2_dgrad": (_i, [_TP, _vp, _i, _TP, _SP, _vp]),
+    "b200_convT2x2_workspace": (_sz, [_TP, _i, _i, _i]),
     "b200_convT2x2_wgrad": (_i, [_TP, _TP, _vp, _vp, _vp]),
     "b200_bias_act_bwd": (_i, [_TP, _TP, _i, _TP, _vp, _vp]),
     "b200_layernorm_fwd": (_i, [_TP, _vp, _vp, _f, _i, _TP, _vp, _vp, _vp]),

@@ -43,9 +43,8 @@ struct ConvLnArgs {
 bool conv_tc_ln_supported(int cout);
 bool conv_gemm_wanted(const b200_tensor*, int, int, int);
 size_t conv_gemm_workspace(const b200_tensor*, int, int, int);
-void set_workspace(void*, size_t);
 int conv_tc_launch(const b200_tensor*, const void*, int, int, int, int, const float*, const b200_tensor*, int, int, cudaStream_t,
-                   const ConvLnArgs* ln = nullptr, int ks = 3);
+                   const ConvLnArgs* ln, int ks, void* ws, size_t ws_bytes);
 int umma_probe(const void*, int, const void*, int, int, int, int, float*, cudaStream_t);
 int umma_rate(int, int, int, long long*, int, cudaStream_t);
 bool stem_supported(const b200_tensor*, const b200_tensor*, int);
@@ -91,8 +90,9 @@ int adam_step(float*, const float*, float*, float*, size_t, const float*, const 
 int cast(const void*, int, void*, int, size_t, cudaStream_t);
 int copy_tensor(const b200_tensor*, const b200_tensor*, cudaStream_t);
 int scale_inplace(float*, size_t, float, cudaStream_t);
-int convT2_fprop(const b200_tensor*, const void*, const float*, int, const b200_tensor*, cudaStream_t);
-int convT2_dgrad(const b200_tensor*, const void*, int, const b200_tensor*, cudaStream_t);
+size_t convT2_workspace(const b200_tensor*, int, int, int);
+int convT2_fprop(const b200_tensor*, const void*, const float*, int, const b200_tensor*, void*, size_t, cudaStream_t);
+int convT2_dgrad(const b200_tensor*, const void*, int, const b200_tensor*, void*, size_t, cudaStream_t);
 int convT2_wgrad(const b200_tensor*, const b200_tensor*, float*, float*, cudaStream_t);
 bool head_mid_supported(const b200_tensor*, const b200_tensor*, int);
 int head_mid_fprop(const b200_tensor*, const void*, const float*, const b200_tensor*, int, cudaStream_t);
@@ -138,8 +138,11 @@ int b200_device_info(int* sms, int* major, int* minor) {
   return B200_OK;
 }
 
+#define WS_PTR(ws) ((ws) ? (ws)->ptr : nullptr)
+#define WS_BYTES(ws) ((ws) ? (ws)->bytes : (size_t)0)
+
 int b200_conv2d_fprop(const b200_tensor* x, const b200_filter* f, const float* bias, const b200_tensor* y, int act,
-                      int algo, void* stream) {
+                      int algo, const b200_scratch* ws, void* stream) {
   REQ_T(x, "x"); REQ_T(y, "y");
   B200_REQUIRE(f && f->hwio, B200_ERR_BAD_ARG, "conv2d_fprop: filter missing");
   B200_REQUIRE(x->c == f->cin && y->c == f->cout && x->n == y->n && x->h == y->h && x->w == y->w, B200_ERR_BAD_ARG,
@@ -149,7 +152,7 @@ int b200_conv2d_fprop(const b200_tensor* x, const b200_filter* f, const float* b
                      (act == B200_ACT_NONE || act == B200_ACT_RELU) && conv_tc_supported(x, f->cin, f->cout, y, f->kh);
   if (algo == B200_ALGO_TCGEN05 || (algo == B200_ALGO_AUTO && tc_ok)) {
     B200_REQUIRE(tc_ok, B200_ERR_UNSUPPORTED, "conv2d_fprop: tcgen05 path does not support this shape/dtype");
-    return conv_tc_launch(x, f->hwio, f->cin, f->cout, 0, 1, bias, y, act, 0, ST(stream), nullptr, f->kh);
+    return conv_tc_launch(x, f->hwio, f->cin, f->cout, 0, 1, bias, y, act, 0, ST(stream), nullptr, f->kh, WS_PTR(ws), WS_BYTES(ws));
   }
   if (algo == B200_ALGO_AUTO && f->dtype == x->dtype && f->kh == f->kw) {
     if (stem_supported(x, y, f->kh) && act != B200_ACT_SIGMOID) return stem_fprop(x, f->hwio, bias, y, act, ST(stream));
@@ -161,7 +164,7 @@ int b200_conv2d_fprop(const b200_tensor* x, const b200_filter* f, const float* b
 
 int b200_conv2d_ln_fprop(const b200_tensor* x, const b200_filter* f, const float* bias, const float* gamma,
                          const float* beta, float eps, int relu, const b200_tensor* z, const b200_tensor* y, float* mean,
-                         float* rstd, int algo, void* stream) {
+                         float* rstd, int algo, const b200_scratch* ws, void* stream) {
   REQ_T(x, "x"); REQ_T(y, "y");
   B200_REQUIRE(f && f->hwio && gamma && beta && mean && rstd, B200_ERR_BAD_ARG, "conv2d_ln_fprop: NULL argument");
   B200_REQUIRE(x->c == f->cin && y->c == f->cout && x->n == y->n && x->h == y->h && x->w == y->w, B200_ERR_BAD_ARG,
@@ -173,17 +176,17 @@ int b200_conv2d_ln_fprop(const b200_tensor* x, const b200_filter* f, const float
                      algo != B200_ALGO_SIMT && !conv_gemm_wanted(x, f->cin, f->cout, f->kh);
   if (fused) {
     ConvLnArgs ln{gamma, beta, eps, relu, have_z ? z : nullptr, mean, rstd};
-    return conv_tc_launch(x, f->hwio, f->cin, f->cout, 0, 1, bias, y, B200_ACT_NONE, 0, ST(stream), &ln, f->kh);
+    return conv_tc_launch(x, f->hwio, f->cin, f->cout, 0, 1, bias, y, B200_ACT_NONE, 0, ST(stream), &ln, f->kh, nullptr, 0);
   }
   // composition: convolution into z (or into y when the caller keeps no z), then the stand-alone LayerNorm
   const b200_tensor* zz = have_z ? z : y;
-  int rc = b200_conv2d_fprop(x, f, bias, zz, B200_ACT_NONE, algo, stream);
+  int rc = b200_conv2d_fprop(x, f, bias, zz, B200_ACT_NONE, algo, ws, stream);
   if (rc) return rc;
   return layernorm_fwd(zz, gamma, beta, eps, relu, y, mean, rstd, ST(stream));
 }
 
 int b200_conv2d_dgrad(const b200_tensor* dy, const b200_filter* f, const b200_tensor* dx, int accumulate, int algo,
-                      void* stream) {
+                      const b200_scratch* ws, void* stream) {
   REQ_T(dy, "dy"); REQ_T(dx, "dx");
   B200_REQUIRE(f && f->hwio, B200_ERR_BAD_ARG, "conv2d_dgrad: filter missing");
   B200_REQUIRE(dy->c == f->cout && dx->c == f->cin && dx->n == dy->n && dx->h == dy->h && dx->w == dy->w,
@@ -195,20 +198,13 @@ int b200_conv2d_dgrad(const b200_tensor* dy, const b200_filter* f, const b200_te
   if (algo == B200_ALGO_TCGEN05 || (algo == B200_ALGO_AUTO && tc_ok)) {
     B200_REQUIRE(tc_ok, B200_ERR_UNSUPPORTED, "conv2d_dgrad: tcgen05 path does not support this shape/dtype");
     return conv_tc_launch(dy, f->hwio, f->cout, f->cin, 1, 0, nullptr, dx, B200_ACT_NONE, accumulate, ST(stream), nullptr,
-                          f->kh);
+                          f->kh, WS_PTR(ws), WS_BYTES(ws));
   }
   if (algo == B200_ALGO_AUTO && f->dtype == dx->dtype && f->kh == f->kw && head_supported(dx, dy, f->kh))
     return head_dgrad(dy, f->hwio, dx, accumulate, ST(stream));
   if (algo == B200_ALGO_AUTO && f->dtype == dx->dtype && f->kh == f->kw && head_mid_supported(dx, dy, f->kh))
     return head_mid_dgrad(dy, f->hwio, dx, accumulate, ST(stream));
   return conv_simt_fprop(dy, f, nullptr, dx, B200_ACT_NONE, accumulate, true, ST(stream));
-}
-
-int b200_set_workspace(void* ws, size_t bytes) {
-  B200_REQUIRE((ws && bytes) || (!ws && !bytes), B200_ERR_BAD_ARG, "set_workspace: pointer and size disagree");
-  B200_REQUIRE((reinterpret_cast<uintptr_t>(ws) % 16) == 0, B200_ERR_BAD_ARG, "set_workspace: needs 16-byte alignment");
-  set_workspace(ws, bytes);
-  return B200_OK;
 }
 
 size_t b200_conv2d_workspace(const b200_tensor* x, const b200_filter* f, int dgrad) {
@@ -263,13 +259,19 @@ int b200_filter_pack(const void* hwio, void* ohwi, int kh, int kw, int cin, int 
   return filter_pack(hwio, ohwi, kh * kw, cin, cout, dtype, ST(stream));
 }
 
-int b200_convT2x2_fprop(const b200_tensor* x, const void* k, const float* bias, int cout, const b200_tensor* y, void* s) {
-  REQ_T(x, "x"); REQ_T(y, "y");
-  return convT2_fprop(x, k, bias, cout, y, ST(s));
+size_t b200_convT2x2_workspace(const b200_tensor* x, int cin, int cout, int dgrad) {
+  if (!valid_tensor(x)) return 0;
+  return convT2_workspace(x, cin, cout, dgrad);
 }
-int b200_convT2x2_dgrad(const b200_tensor* dy, const void* k, int cout, const b200_tensor* dx, void* s) {
+int b200_convT2x2_fprop(const b200_tensor* x, const void* k, const float* bias, int cout, const b200_tensor* y,
+                        const b200_scratch* ws, void* s) {
+  REQ_T(x, "x"); REQ_T(y, "y");
+  return convT2_fprop(x, k, bias, cout, y, WS_PTR(ws), WS_BYTES(ws), ST(s));
+}
+int b200_convT2x2_dgrad(const b200_tensor* dy, const void* k, int cout, const b200_tensor* dx, const b200_scratch* ws,
+                        void* s) {
   REQ_T(dy, "dy"); REQ_T(dx, "dx");
-  return convT2_dgrad(dy, k, cout, dx, ST(s));
+  return convT2_dgrad(dy, k, cout, dx, WS_PTR(ws), WS_BYTES(ws), ST(s));
 }
 int b200_convT2x2_wgrad(const b200_tensor* x, const b200_tensor* dy, float* dk, float* db, void* s) {
   REQ_T(x, "x"); REQ_T(dy, "dy");

@@ -113,14 +113,28 @@ __device__ __forceinline__ long long pix_offset_flat(const TView& t, long long p
 }
 
 inline int sm_count() {
-  static int sms = 0;
-  if (!sms) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (sms <= 0) sms = 148;
+  static int sms[64] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) return 148;
+  if (!sms[dev]) {
+    cudaDeviceGetAttribute(&sms[dev], cudaDevAttrMultiProcessorCount, dev);
+    if (sms[dev] <= 0) sms[dev] = 148;
   }
-  return sms;
+  return sms[dev];
+}
+
+// true the first time `slot` (a per-kernel id, < 16) is seen on the CURRENT device: function attributes
+// (dynamic shared memory limits) are per device, so a process that drives several GPUs sets them on each
+inline bool first_use_on_device(int slot) {
+  static unsigned seen[64] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) return true;
+  const unsigned bit = 1u << slot;
+  if (seen[dev] & bit) return false;
+  seen[dev] |= bit;
+  return true;
 }
 
 // dtype dispatch: DISPATCH_DTYPE(dt, T, { body using T })

@@ -29,11 +29,6 @@ using namespace ptx;
 int make_act_tmap(CUtensorMap* m, const b200_tensor* t, int box_w, int box_h, int box_n);
 int make_mat_tmap(CUtensorMap* m, const void* base, long long rows, long long cols, int box_rows);
 
-// caller-provided scratch for split-K partial sums (b200_set_workspace)
-static void* g_ws = nullptr;
-static size_t g_ws_bytes = 0;
-void set_workspace(void* p, size_t bytes) { g_ws = p; g_ws_bytes = bytes; }
-
 namespace {
 
 constexpr int NTHREADS = 192;
@@ -432,15 +427,14 @@ size_t conv_gemm_workspace(const b200_tensor* x, int cin, int cout, int ks) {
   return gemm_plan(x, cin, cout, ks).ws_bytes;
 }
 
-bool conv_gemm_ready(const b200_tensor* x, int cin, int cout, int ks) {
-  return conv_gemm_wanted(x, cin, cout, ks) && g_ws && g_ws_bytes >= conv_gemm_workspace(x, cin, cout, ks);
-}
-
+// The split-K scratch is passed per call (the caller -- one Plan -- owns it and orders the launches that share it on one
+// stream): which path a layer takes is a pure function of its shapes, never of what an earlier caller registered.
 int conv_gemm_launch(const b200_tensor* x, const void* wmat, int cin, int cout, int tap_rev, int b_mn, const float* bias,
-                     const b200_tensor* y, int act, int accumulate, int ks, cudaStream_t st) {
+                     const b200_tensor* y, int act, int accumulate, int ks, void* ws, size_t ws_bytes, cudaStream_t st) {
   const GemmPlan pl = gemm_plan(x, cin, cout, ks);
-  B200_REQUIRE(g_ws && g_ws_bytes >= pl.ws_bytes, B200_ERR_BAD_ARG, "conv (split-K): workspace too small (%zu < %zu bytes)",
-               g_ws_bytes, pl.ws_bytes);
+  B200_REQUIRE(ws && ws_bytes >= pl.ws_bytes && (uintptr_t)ws % 16 == 0, B200_ERR_BAD_ARG,
+               "conv (split-K, images <= 4x4): this layer needs %zu bytes of 16-byte aligned scratch (b200_conv2d_workspace), "
+               "got %zu", pl.ws_bytes, ws ? ws_bytes : (size_t)0);
   GemmParams p;
   p.KB = pl.KB; p.BN = pl.BN; p.n_tiles = pl.n_tiles; p.m_tiles = pl.g.m_tiles; p.splits = pl.splits; p.units = pl.units;
   p.nlive = pl.nlive;
@@ -448,7 +442,7 @@ int conv_gemm_launch(const b200_tensor* x, const void* wmat, int cin, int cout, 
   p.tiles_w = pl.g.tiles_w; p.tiles_h = pl.g.tiles_h; p.bw = pl.g.bw; p.bh = pl.g.bh; p.bn = pl.g.bn;
   p.b_mn = b_mn; p.tap_rev = tap_rev; p.Kc = cin; p.Cout = cout;
   p.ntaps = ks == 1 ? 1 : 9; p.tap0 = ks == 1 ? 4 : 0;
-  p.ws = reinterpret_cast<float*>(g_ws);
+  p.ws = reinterpret_cast<float*>(ws);
   CUtensorMap tm_x, tm_b;
   int rc = make_act_tmap(&tm_x, x, p.bw, p.bh, p.bn);
   if (rc) return rc;
@@ -456,11 +450,8 @@ int conv_gemm_launch(const b200_tensor* x, const void* wmat, int cin, int cout, 
             : make_mat_tmap(&tm_b, wmat, (long long)p.ntaps * cout, cin, p.BN);
   if (rc) return rc;
   const size_t smem = 1024 + (size_t)MAX_STAGES * (A_BYTES + p.BN * 128);
-  static bool attr_set = false;
-  if (!attr_set) {
+  if (first_use_on_device(0))
     cudaFuncSetAttribute(conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 1024 + MAX_STAGES * (A_BYTES + 128 * 128));
-    attr_set = true;
-  }
   const int grid = p.splits * p.m_tiles * p.n_tiles;
   conv_gemm_kernel<<<grid, NTHREADS, smem, st>>>(tm_x, tm_b, p);
   rc = check_launch("conv_gemm_kernel");
@@ -526,11 +517,8 @@ int wgrad_small_launch(const b200_tensor* x, const b200_tensor* dy, float* out, 
   rc = make_act_tmap(&tm_dz, dy, p.bw, p.bh, p.bn);
   if (rc) return rc;
   const size_t smem = 1024 + (size_t)WG_STAGES * WG_STAGE;
-  static bool attr_set = false;
-  if (!attr_set) {
+  if (first_use_on_device(1))
     cudaFuncSetAttribute(wgrad_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    attr_set = true;
-  }
   const int grid = p.splits * p.nlive * p.cblocks * p.oblocks;
   wgrad_small_kernel<<<grid, NTHREADS, smem, st>>>(tm_x, tm_dz, p);
   *splits_out = p.splits;

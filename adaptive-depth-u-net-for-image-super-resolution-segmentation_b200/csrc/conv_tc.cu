@@ -753,20 +753,22 @@ struct ConvLnArgs {
 bool conv_tc_ln_supported(int cout) { return cout == 64 || cout == 128; }
 
 // small-spatial split-K path (conv_gemm.cu)
-bool conv_gemm_ready(const b200_tensor* x, int cin, int cout, int ks);
+bool conv_gemm_wanted(const b200_tensor* x, int cin, int cout, int ks);
 int conv_gemm_launch(const b200_tensor* x, const void* wmat, int cin, int cout, int tap_rev, int b_mn, const float* bias,
-                     const b200_tensor* y, int act, int accumulate, int ks, cudaStream_t st);
+                     const b200_tensor* y, int act, int accumulate, int ks, void* ws, size_t ws_bytes, cudaStream_t st);
 
 int conv_tc_launch(const b200_tensor* x_in, const void* wmat, int cin, int cout, int tap_rev, int b_mn, const float* bias,
-                   const b200_tensor* y_in, int act, int accumulate, cudaStream_t st, const ConvLnArgs* ln = nullptr,
-                   int ks = 3) {
+                   const b200_tensor* y_in, int act, int accumulate, cudaStream_t st, const ConvLnArgs* ln, int ks,
+                   void* ws, size_t ws_bytes) {
   B200_REQUIRE(conv_tc_supported(x_in, cin, cout, y_in, ks), B200_ERR_UNSUPPORTED,
                "conv3x3 tcgen05: unsupported shape cin=%d cout=%d (need bf16, multiples of 64, 16-byte aligned)", cin,
                cout);
   B200_REQUIRE(x_in->n == y_in->n && x_in->h == y_in->h && x_in->w == y_in->w && x_in->c == cin && y_in->c == cout,
                B200_ERR_BAD_ARG, "conv3x3 tcgen05: tensor shapes do not match the filter");
-  if (!ln && cin % 64 == 0 && cout % 64 == 0 && conv_gemm_ready(x_in, cin, cout, ks))   // deep levels (images <= 8x8): weight-streaming split-K GEMM
-    return conv_gemm_launch(x_in, wmat, cin, cout, tap_rev, b_mn, bias, y_in, act, accumulate, ks, st);
+  // deep levels (images <= 4x4): weight-streaming split-K GEMM.  The choice depends on the shapes only; a caller that
+  // passes too little scratch gets an error, never another algorithm.
+  if (!ln && conv_gemm_wanted(x_in, cin, cout, ks))
+    return conv_gemm_launch(x_in, wmat, cin, cout, tap_rev, b_mn, bias, y_in, act, accumulate, ks, ws, ws_bytes, st);
   b200_tensor xf, yf;
   const b200_tensor *x = x_in, *y = y_in;
   int live_mask = 0;
@@ -886,13 +888,11 @@ int conv_tc_launch(const b200_tensor* x_in, const void* wmat, int cin, int cout,
   if (rc) return rc;
 
   const size_t smem = 1024 + (size_t)p.nsw * p.win_stage + (size_t)p.nsb * wt_bytes + (size_t)p.nslots * SLOT_BYTES + bias_bytes;
-  static bool attr_set = false;
-  if (!attr_set) {
+  if (first_use_on_device(3)) {
     cudaFuncSetAttribute(conv3x3_tc_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT - 1024);
     cudaFuncSetAttribute(conv3x3_tc_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT - 1024);
     cudaFuncSetAttribute(conv3x3_tc_kernel<false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT - 1024);
     cudaFuncSetAttribute(conv3x3_tc_kernel<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT - 1024);
-    attr_set = true;
   }
   int grid = p.total_items < sm_count() ? p.total_items : sm_count();
   if (p.pair) conv3x3_tc_kernel<true, 0><<<grid, NTHREADS, smem, st>>>(tm_x, tm_b, tm_y, tm_z, p);

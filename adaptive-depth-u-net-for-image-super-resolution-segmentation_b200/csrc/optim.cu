@@ -209,7 +209,10 @@ int scale_inplace(float* p, size_t count, float s, cudaStream_t st) {
 // TMA maps take arbitrary strides, so the pixel shuffle costs nothing.
 bool conv_tc_supported(const b200_tensor* x, int cin, int cout, const b200_tensor* y, int ks);
 int conv_tc_launch(const b200_tensor* x, const void* wmat, int cin, int cout, int tap_rev, int b_mn, const float* bias,
-                   const b200_tensor* y, int act, int accumulate, cudaStream_t st, const struct ConvLnArgs* ln, int ks);
+                   const b200_tensor* y, int act, int accumulate, cudaStream_t st, const struct ConvLnArgs* ln, int ks,
+                   void* ws, size_t ws_bytes);
+bool conv_gemm_wanted(const b200_tensor* x, int cin, int cout, int ks);
+size_t conv_gemm_workspace(const b200_tensor* x, int cin, int cout, int ks);
 bool wgrad_tc_supported(const b200_tensor* x, const b200_tensor* dy, int ks);
 int wgrad_tc_launch(const b200_tensor* x, const b200_tensor* dy, float* dw, void* ws, size_t ws_bytes, cudaStream_t st,
                     int ks, int atomic);
@@ -223,8 +226,15 @@ static b200_tensor parity_view(const b200_tensor* y, int a, int b) {
   return v;
 }
 
+// scratch bytes the four 1x1 launches of the tensor-core form want (they run back to back on one stream and share it)
+size_t convT2_workspace(const b200_tensor* x, int cin, int cout, int dgrad) {
+  if (x->dtype != B200_BF16) return 0;
+  b200_tensor v = dgrad ? parity_view(x, 0, 0) : *x;      // dgrad: x is dy, read through its parity views
+  return conv_gemm_wanted(&v, cin, cout, 1) ? conv_gemm_workspace(&v, cin, cout, 1) : 0;
+}
+
 int convT2_fprop(const b200_tensor* x, const void* kernel, const float* bias, int cout, const b200_tensor* y,
-                 cudaStream_t st) {
+                 void* ws, size_t ws_bytes, cudaStream_t st) {
   B200_REQUIRE(y->h == 2 * x->h && y->w == 2 * x->w && y->n == x->n && y->c == cout && x->dtype == y->dtype,
                B200_ERR_BAD_ARG, "convT2x2_fprop: shape mismatch");
   {
@@ -233,7 +243,7 @@ int convT2_fprop(const b200_tensor* x, const void* kernel, const float* bias, in
       for (int ab = 0; ab < 4; ++ab) {
         b200_tensor yv = parity_view(y, ab / 2, ab % 2);
         const __nv_bfloat16* k_ab = reinterpret_cast<const __nv_bfloat16*>(kernel) + (long long)ab * cout * x->c;   // [cout][cin], K-major
-        int rc = conv_tc_launch(x, k_ab, x->c, cout, 0, 0, bias, &yv, B200_ACT_NONE, 0, st, nullptr, 1);
+        int rc = conv_tc_launch(x, k_ab, x->c, cout, 0, 0, bias, &yv, B200_ACT_NONE, 0, st, nullptr, 1, ws, ws_bytes);
         if (rc) return rc;
       }
       return B200_OK;
@@ -247,7 +257,8 @@ int convT2_fprop(const b200_tensor* x, const void* kernel, const float* bias, in
   return check_launch("convT2_fprop_kernel");
 }
 
-int convT2_dgrad(const b200_tensor* dy, const void* kernel, int cout, const b200_tensor* dx, cudaStream_t st) {
+int convT2_dgrad(const b200_tensor* dy, const void* kernel, int cout, const b200_tensor* dx, void* ws, size_t ws_bytes,
+                 cudaStream_t st) {
   B200_REQUIRE(dy->h == 2 * dx->h && dy->w == 2 * dx->w && dy->n == dx->n && dy->c == cout && dx->dtype == dy->dtype,
                B200_ERR_BAD_ARG, "convT2x2_dgrad: shape mismatch");
   {
@@ -256,7 +267,7 @@ int convT2_dgrad(const b200_tensor* dy, const void* kernel, int cout, const b200
       for (int ab = 0; ab < 4; ++ab) {
         b200_tensor dv = parity_view(dy, ab / 2, ab % 2);
         const __nv_bfloat16* k_ab = reinterpret_cast<const __nv_bfloat16*>(kernel) + (long long)ab * cout * dx->c;  // [K = cout][N = cin], MN-major
-        int rc = conv_tc_launch(&dv, k_ab, cout, dx->c, 0, 1, nullptr, dx, B200_ACT_NONE, ab > 0 ? 1 : 0, st, nullptr, 1);
+        int rc = conv_tc_launch(&dv, k_ab, cout, dx->c, 0, 1, nullptr, dx, B200_ACT_NONE, ab > 0 ? 1 : 0, st, nullptr, 1, ws, ws_bytes);
         if (rc) return rc;
       }
       return B200_OK;

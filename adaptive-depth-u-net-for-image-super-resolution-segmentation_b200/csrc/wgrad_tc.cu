@@ -11,7 +11,9 @@
 // MMAs: the 128 rows are TWO taps x 64 input channels -- the second tap is the same window
 // shifted, expressed through the descriptor's leading-byte-offset.  The 9x64x64 fp32 partial
 // sums stay in TMEM (5 x 64 columns) until the CTA has consumed all its tiles, then go to a
-// workspace that a second kernel reduces deterministically over the CTAs.
+// workspace that a second kernel reduces deterministically over the CTAs (b200_conv2d_wgrad), or -- the
+// training step's default, b200_conv2d_wgrad_atomic -- are added straight into the zeroed gradient buffer
+// with `red.global.add.v4.f32` (no slabs, no reduce launch; the summation order then varies run to run).
 //
 // Replaces the autodiff (filter gradient) of keras Conv2D at
 // Super_resolution/code/train_adaptive_unet.py:202,207,259 (reference: /root/reference).
@@ -347,11 +349,8 @@ int wgrad_tc_launch(const b200_tensor* x, const b200_tensor* dy, float* dw, void
   rc = make_act_tmap(&tm_dz, &g.dy, TILE_W, g.box_n > 1 || g.box_h != WIN_H ? g.box_h : TILE_H, g.box_n);
   if (rc) return rc;
   const size_t smem = 1024 + (size_t)NSTAGES * STAGE;
-  static bool attr_set = false;
-  if (!attr_set) {
+  if (first_use_on_device(2))
     cudaFuncSetAttribute(wgrad3x3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    attr_set = true;
-  }
   const int grid = p.splits * p.cblocks * p.oblocks;
   wgrad3x3_tc_kernel<<<grid, NTHREADS, smem, st>>>(tm_x, tm_dz, p);
   int rc2 = check_launch("wgrad3x3_tc_kernel");

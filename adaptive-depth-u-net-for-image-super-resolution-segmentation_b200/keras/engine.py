@@ -29,6 +29,9 @@ from ..shared.custom_layers import ClippedResidualAdd, ResizeByScale, ResizeToMa
 from . import layers as L
 
 
+_POISON = os.environ.get("B200_POISON", "0") == "1"
+
+
 class Val:
     """A concrete activation tensor of the plan (one per KTensor, minus folded nodes)."""
 
@@ -184,7 +187,17 @@ class Plan:
 
     # ------------------------------------------------------------------ buffers
     def _new(self, v: Val, grad=False):
+        if _POISON:
+            # debug mode (B200_POISON=1): every activation / gradient buffer starts as NaN instead of zeros, so a kernel
+            # that reads an element nobody wrote (or accumulates into a never-initialised one) poisons the loss
+            return torch.full((self.batch, v.h, v.w, v.c), float("nan"), dtype=v.dtype, device=self.dev)
         return torch.zeros((self.batch, v.h, v.w, v.c), dtype=v.dtype, device=self.dev)
+
+    def _scratch(self, shape, dtype):
+        """Scratch every element of which is written before it is read (NaN-filled under B200_POISON=1)."""
+        if _POISON and dtype in (torch.float32, torch.float64, torch.bfloat16):
+            return torch.full(shape if isinstance(shape, tuple) else (shape,), float("nan"), dtype=dtype, device=self.dev)
+        return torch.empty(shape, dtype=dtype, device=self.dev)
 
     def _alloc(self):
         all_vals = []
@@ -232,14 +245,21 @@ class Plan:
                 list.append(inner, fn)
 
         S = self.steps = _Tagged()
-        ws_need = 0           # split-K scratch of the small-spatial (deep-level) convolutions, fprop and dgrad
+        # split-K scratch of the small-spatial (deep-level) convolutions, fprop and dgrad: ONE buffer per plan, handed to
+        # every call that may need it (all of them run on the plan's main stream, so they may share it)
+        ws_need = 0
         for op in self.ops:
             if op.kind == "conv" and op.inputs[0].buf.dtype == torch.bfloat16 and op.inputs[0].c % 64 == 0:
                 filt = m._filter(op.layer)
                 ws_need = max(ws_need, ops.conv2d_workspace(op.inputs[0].buf, filt, False))
                 if self.training:
                     ws_need = max(ws_need, ops.conv2d_workspace(op.output.buf, filt, True))
-        ops.ensure_workspace(ws_need, self.dev)
+            elif op.kind == "convT" and op.inputs[0].buf.dtype == torch.bfloat16:
+                x, y = op.inputs[0], op.output
+                ws_need = max(ws_need, ops.convT2x2_workspace(x.buf, x.c, y.c, False))
+                if self.training:
+                    ws_need = max(ws_need, ops.convT2x2_workspace(y.buf, y.c, x.c, True))
+        self.conv_ws = ops.new_workspace(ws_need, self.dev)
         for op in self.ops:   # narrow-input 3x3 convs (the RGB stem): im2col tensor for the tcgen05 1x1 path
             if op.kind == "conv" and op.layer.kernel_size == (3, 3) and m._stem_padded(op.layer) is not None:
                 x = op.inputs[0]
@@ -269,14 +289,15 @@ class Plan:
                 src = self._stem_source(op, S)
                 if src is not None:
                     filt = m._stem_padded(op.layer)[0]
-                    S.append(lambda xc=src, f=filt, b=bias, y=op.output, o=op: ops.conv2d_fprop(xc, f, b, y.buf, o.act))
+                    S.append(lambda xc=src, f=filt, b=bias, y=op.output, o=op:
+                             ops.conv2d_fprop(xc, f, b, y.buf, o.act, ws=self.conv_ws))
                 else:
                     S.append(lambda x=op.inputs[0], f=filt, b=bias, y=op.output, o=op:
-                             ops.conv2d_fprop(x.buf, f, b, y.buf, o.act))
+                             ops.conv2d_fprop(x.buf, f, b, y.buf, o.act, ws=self.conv_ws))
             elif k == "ln":
                 g, b = m._param(op.layer, "gamma"), m._param(op.layer, "beta")
-                op.mean = torch.empty(npix(op.output), dtype=torch.float32, device=self.dev)
-                op.rstd = torch.empty_like(op.mean)
+                op.mean = self._scratch(npix(op.output), torch.float32)
+                op.rstd = self._scratch(npix(op.output), torch.float32)
                 cs = op.conv_src
                 if cs is not None and cs.output is op.inputs[0] and cs.layer.kernel_size == (3, 3):
                     # Conv2D -> LayerNormalization -> ReLU: one call (fused tcgen05 epilogue for Cout 64/128)
@@ -287,7 +308,8 @@ class Plan:
                     self._cur_tag = "conv+ln" + (":tc" if self.is_tc(cs) else ":simt")
                     S.append(lambda x=xin, f=filt, cb=m._param(cs.layer, "bias"),
                              z=op.inputs[0], y=op.output, o=op, g=g, b=b:
-                             ops.conv2d_ln_fprop(x, f, cb, g, b, o.layer.epsilon, o.relu, z.buf, y.buf, o.mean, o.rstd))
+                             ops.conv2d_ln_fprop(x, f, cb, g, b, o.layer.epsilon, o.relu, z.buf, y.buf, o.mean, o.rstd,
+                                                 ws=self.conv_ws))
                 else:
                     S.append(lambda z=op.inputs[0], y=op.output, o=op, g=g, b=b:
                              ops.layernorm_fwd(z.buf, g, b, o.layer.epsilon, o.relu, y.buf, o.mean, o.rstd))
@@ -295,9 +317,9 @@ class Plan:
                 g, b = m._param(op.layer, "gamma"), m._param(op.layer, "beta")
                 mm, mv = m._param(op.layer, "moving_mean"), m._param(op.layer, "moving_variance")
                 c = op.output.c
-                op.save_mean = torch.empty(c, dtype=torch.float32, device=self.dev)
-                op.save_rstd = torch.empty_like(op.save_mean)
-                op.stats_ws = torch.empty(2 * c, dtype=torch.float64, device=self.dev)
+                op.save_mean = self._scratch(c, torch.float32)
+                op.save_rstd = self._scratch(c, torch.float32)
+                op.stats_ws = self._scratch(2 * c, torch.float64)
                 if self.training:
                     S.append(lambda z=op.inputs[0], y=op.output, o=op, g=g, b=b, mm=mm, mv=mv:
                              ops.batchnorm_fwd_train(z.buf, g, b, o.layer.epsilon, o.layer.momentum, o.relu, y.buf,
@@ -318,7 +340,8 @@ class Plan:
                 S.append(lambda x=op.inputs[0], y=op.output: ops.maxpool2_fwd(x.buf, y.buf))
             elif k == "convT":
                 kern, bias = m._shadow(op.layer, "kernel"), m._param(op.layer, "bias")
-                S.append(lambda x=op.inputs[0], y=op.output, kk=kern, b=bias: ops.convT2x2_fprop(x.buf, kk, b, y.buf))
+                S.append(lambda x=op.inputs[0], y=op.output, kk=kern, b=bias:
+                         ops.convT2x2_fprop(x.buf, kk, b, y.buf, ws=self.conv_ws))
             elif k == "concat":
                 for vin, off in op.copies:
                     S.append(lambda a=vin, y=op.output, off=off: ops.copy_tensor(a.buf, y.buf[..., off:off + a.c]))
@@ -371,7 +394,7 @@ class Plan:
                     ws_bytes = max(ws_bytes, ops.conv2d_wgrad_workspace(op.xcol, op.output.buf, 1, 1))
                 else:
                     ws_bytes = max(ws_bytes, ops.conv2d_wgrad_workspace(op.inputs[0].buf, op.output.buf, 3, 3))
-        self.wgrad_ws = torch.empty(max(ws_bytes, 16) // 4, dtype=torch.float32, device=self.dev)
+        self.wgrad_ws = self._scratch(max(ws_bytes, 16) // 4, torch.float32)
 
         def write_flag(v: Val) -> bool:
             acc = v.grad_written
@@ -416,7 +439,7 @@ class Plan:
                 if x.needs_grad:
                     acc = write_flag(x)
                     self._cur_tag = "dgrad" + sfx
-                    B.append(lambda x=x, o=out, f=filt, acc=acc: ops.conv2d_dgrad(o.grad, f, x.grad, acc))
+                    B.append(lambda x=x, o=out, f=filt, acc=acc: ops.conv2d_dgrad(o.grad, f, x.grad, acc, ws=self.conv_ws))
             elif k == "ln":
                 z, ly = op.inputs[0], op.layer
                 assert not z.grad_written, "LayerNormalization input must have a single consumer"
@@ -463,7 +486,8 @@ class Plan:
                 if x.needs_grad:
                     if write_flag(x):
                         raise NotImplementedError("Conv2DTranspose input with several consumers")
-                    B.append(lambda x=x, o=out, kk=m._shadow(ly, "kernel"): ops.convT2x2_dgrad(o.grad, kk, x.grad))
+                    B.append(lambda x=x, o=out, kk=m._shadow(ly, "kernel"):
+                             ops.convT2x2_dgrad(o.grad, kk, x.grad, ws=self.conv_ws))
             elif k == "concat":
                 for vin, off in op.copies:
                     if vin.needs_grad:

@@ -8,6 +8,7 @@ wider buffers are passed with their real strides (concat written in place).
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Optional
 
 import numpy as np
@@ -15,7 +16,7 @@ import torch
 
 from . import _ffi
 from ._ffi import (ACT_NONE, ACT_RELU, ACT_SIGMOID, ALGO_AUTO, ALGO_SIMT, ALGO_TCGEN05, BF16, CV_INTER_AREA, CV_INTER_CUBIC,
-                   F32, U8, Filter, Tensor, check)
+                   F32, U8, Filter, Scratch, Tensor, check)
 
 _DT = {torch.float32: F32, torch.bfloat16: BF16}
 
@@ -70,34 +71,43 @@ class ConvFilter:
 
 
 # ---- convolution -------------------------------------------------------------------
-_WORKSPACES = []   # every scratch buffer ever registered stays alive: captured CUDA graphs hold their pointers
-
-
 def conv2d_workspace(x, filt: "ConvFilter", dgrad: bool = False) -> int:
-    """Bytes of split-K scratch the small-spatial path wants for this layer (0 = path not taken)."""
+    """Bytes of split-K scratch this layer needs in `ws` (0 = it does not take the small-spatial path)."""
     return int(lib().b200_conv2d_workspace(tdesc(x), filt.struct(), int(dgrad)))
 
 
-def ensure_workspace(nbytes: int, device) -> None:
-    """Register (process-wide) a scratch buffer of at least `nbytes` for the split-K convolution path."""
+def convT2x2_workspace(x, cin: int, cout: int, dgrad: bool = False) -> int:
+    return int(lib().b200_convT2x2_workspace(tdesc(x), int(cin), int(cout), int(dgrad)))
+
+
+def _scratch(ws: Optional[torch.Tensor]):
+    """b200_scratch for a caller-owned buffer (None -> NULL): passed per call, never registered."""
+    if ws is None:
+        return None
+    return C.byref(Scratch(ws.data_ptr(), ws.numel() * ws.element_size()))
+
+
+def new_workspace(nbytes: int, device) -> Optional[torch.Tensor]:
+    """A scratch buffer of `nbytes` (None when 0); NaN-filled under B200_POISON=1."""
     if nbytes <= 0:
-        return
-    if _WORKSPACES and _WORKSPACES[-1].numel() * 4 >= nbytes and _WORKSPACES[-1].device == torch.device(device):
-        return
+        return None
     buf = torch.empty((nbytes + 3) // 4, dtype=torch.float32, device=device)
-    _WORKSPACES.append(buf)
-    check(lib().b200_set_workspace(_ptr(buf), buf.numel() * 4), "set_workspace")
+    if os.environ.get("B200_POISON", "0") == "1":
+        buf.fill_(float("nan"))
+    return buf
 
 
-def conv2d_fprop(x, filt: ConvFilter, bias, y, act=ACT_NONE, algo=ALGO_AUTO):
-    check(lib().b200_conv2d_fprop(tdesc(x), filt.struct(), _ptr(bias), tdesc(y), act, algo, _stream()), "conv2d_fprop")
+def conv2d_fprop(x, filt: ConvFilter, bias, y, act=ACT_NONE, algo=ALGO_AUTO, ws=None):
+    check(lib().b200_conv2d_fprop(tdesc(x), filt.struct(), _ptr(bias), tdesc(y), act, algo, _scratch(ws), _stream()),
+          "conv2d_fprop")
     return y
 
 
-def conv2d_ln_fprop(x, filt: ConvFilter, bias, gamma, beta, eps, relu, z, y, mean, rstd, algo=ALGO_AUTO):
+def conv2d_ln_fprop(x, filt: ConvFilter, bias, gamma, beta, eps, relu, z, y, mean, rstd, algo=ALGO_AUTO, ws=None):
     """Conv2D -> LayerNormalization -> (ReLU) in one call; z (pre-norm, kept for backward) may be None."""
     check(lib().b200_conv2d_ln_fprop(tdesc(x), filt.struct(), _ptr(bias), _ptr(gamma), _ptr(beta), eps, int(relu),
-                                     _opt_desc(z), tdesc(y), _ptr(mean), _ptr(rstd), algo, _stream()), "conv2d_ln_fprop")
+                                     _opt_desc(z), tdesc(y), _ptr(mean), _ptr(rstd), algo, _scratch(ws), _stream()),
+          "conv2d_ln_fprop")
     return y
 
 
@@ -107,8 +117,9 @@ def im2col3x3(x, xcol):
     return xcol
 
 
-def conv2d_dgrad(dy, filt: ConvFilter, dx, accumulate=False, algo=ALGO_AUTO):
-    check(lib().b200_conv2d_dgrad(tdesc(dy), filt.struct(), tdesc(dx), int(accumulate), algo, _stream()), "conv2d_dgrad")
+def conv2d_dgrad(dy, filt: ConvFilter, dx, accumulate=False, algo=ALGO_AUTO, ws=None):
+    check(lib().b200_conv2d_dgrad(tdesc(dy), filt.struct(), tdesc(dx), int(accumulate), algo, _scratch(ws), _stream()),
+          "conv2d_dgrad")
     return dx
 
 
@@ -129,13 +140,15 @@ def conv2d_wgrad_atomic(x, dy, kh, kw, dw):
     return dw
 
 
-def convT2x2_fprop(x, kernel, bias, y):
-    check(lib().b200_convT2x2_fprop(tdesc(x), _ptr(kernel), _ptr(bias), kernel.shape[2], tdesc(y), _stream()), "convT2x2_fprop")
+def convT2x2_fprop(x, kernel, bias, y, ws=None):
+    check(lib().b200_convT2x2_fprop(tdesc(x), _ptr(kernel), _ptr(bias), kernel.shape[2], tdesc(y), _scratch(ws), _stream()),
+          "convT2x2_fprop")
     return y
 
 
-def convT2x2_dgrad(dy, kernel, dx):
-    check(lib().b200_convT2x2_dgrad(tdesc(dy), _ptr(kernel), kernel.shape[2], tdesc(dx), _stream()), "convT2x2_dgrad")
+def convT2x2_dgrad(dy, kernel, dx, ws=None):
+    check(lib().b200_convT2x2_dgrad(tdesc(dy), _ptr(kernel), kernel.shape[2], tdesc(dx), _scratch(ws), _stream()),
+          "convT2x2_dgrad")
     return dx
 
 

@@ -73,6 +73,14 @@ typedef struct b200_filter {
   int32_t reserved;
 } b200_filter;
 
+/* Caller-owned device scratch handed to ONE call (16-byte aligned).  The library keeps no pointer to it after
+ * the launches of that call are enqueued; calls that share a buffer must be ordered on one stream.  NULL (or
+ * {NULL, 0}) where a call needs none. */
+typedef struct b200_scratch {
+  void* ptr;
+  size_t bytes;
+} b200_scratch;
+
 /* ---- library ---------------------------------------------------------- */
 const char* b200_version(void);
 const char* b200_last_error(void);
@@ -85,23 +93,23 @@ long long b200_launch_count(int reset);
  * Replaces L.Conv2D at train_adaptive_unet.py:202,207,259,267; seg :326,329,361;
  * unet_vinillia.py:44,49,90.  y = act(conv(x, f) + bias); bias is fp32 [cout] or NULL. */
 int b200_conv2d_fprop(const b200_tensor* x, const b200_filter* f, const float* bias,
-                      const b200_tensor* y, int act, int algo, void* stream);
+                      const b200_tensor* y, int act, int algo, const b200_scratch* ws, void* stream);
 /* Conv2D -> LayerNormalization(axis=-1) [-> ReLU] in one call (conv_block, train_adaptive_unet.py:202-204).
  * z = conv(x)+bias in the storage dtype (kept for the backward pass; z->data may be NULL for inference),
  * y = act(LN(z)); mean/rstd fp32 [n*h*w].  Fused into the tcgen05 epilogue when Cout is 64 or 128,
  * otherwise executed as convolution + b200_layernorm_fwd inside the library. */
 int b200_conv2d_ln_fprop(const b200_tensor* x, const b200_filter* f, const float* bias, const float* gamma,
                          const float* beta, float eps, int relu, const b200_tensor* z, const b200_tensor* y,
-                         float* mean, float* rstd, int algo, void* stream);
+                         float* mean, float* rstd, int algo, const b200_scratch* ws, void* stream);
 /* dx (+)= conv_transpose(dy, f)  -- autodiff of the above w.r.t. its input. */
 int b200_conv2d_dgrad(const b200_tensor* dy, const b200_filter* f, const b200_tensor* dx,
-                      int accumulate, int algo, void* stream);
-/* Scratch for the split-K path that serves small-spatial layers (images <= 8x8 pixels, the deep U-Net
+                      int accumulate, int algo, const b200_scratch* ws, void* stream);
+/* Scratch of the split-K path that serves small-spatial layers (images <= 4x4 pixels, the deep U-Net
  * levels): b200_conv2d_workspace returns the bytes fprop (dgrad = 0, x = the input) or dgrad (dgrad = 1,
- * x = dy) of this layer would use (0 = the layer does not take that path).  The caller owns the buffer and
- * registers it once with b200_set_workspace (process-wide; launches that use it must be ordered on one
- * stream).  Without a large enough registered buffer those layers run on the halo-window kernel instead. */
-int b200_set_workspace(void* ws, size_t bytes);
+ * x = dy) of this layer needs in `ws` (0 = the layer does not take that path; `ws` may then be NULL).
+ * Which path a layer takes is a function of its shapes only -- a call that passes too little scratch fails
+ * with B200_ERR_BAD_ARG, it never runs another algorithm.  There is no process-wide registration: the
+ * caller (one plan) passes its buffer with every call. */
 size_t b200_conv2d_workspace(const b200_tensor* x, const b200_filter* f, int dgrad);
 
 /* dw_hwio[kh][kw][cin][cout] (fp32) = sum_pixels x (*) dy.  Overwrites dw.
@@ -125,8 +133,11 @@ int b200_im2col3x3(const b200_tensor* x, const b200_tensor* xcol, void* stream);
 /* ---- transposed convolution (keras Conv2DTranspose(nf, 2, strides=2)) ----
  * unet_vinillia.py:67.  kernel layout [2][2][cout][cin] in `dtype`, fp32 bias. */
 int b200_convT2x2_fprop(const b200_tensor* x, const void* kernel, const float* bias, int cout,
-                        const b200_tensor* y, void* stream);
-int b200_convT2x2_dgrad(const b200_tensor* dy, const void* kernel, int cout, const b200_tensor* dx, void* stream);
+                        const b200_tensor* y, const b200_scratch* ws, void* stream);
+int b200_convT2x2_dgrad(const b200_tensor* dy, const void* kernel, int cout, const b200_tensor* dx,
+                        const b200_scratch* ws, void* stream);
+/* scratch bytes of the two calls above (x = the input for fprop, = dy for dgrad; 0 for most shapes). */
+size_t b200_convT2x2_workspace(const b200_tensor* x, int cin, int cout, int dgrad);
 int b200_convT2x2_wgrad(const b200_tensor* x, const b200_tensor* dy, float* dkernel, float* dbias, void* stream);
 
 /* ---- bias/activation backward -------------------------------------------

@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 import torch
 
-from util import TOL, f32, rand, relerr
+from util import conv_ws, TOL, f32, rand, relerr
 
 pytestmark = pytest.mark.gpu
 
@@ -17,6 +17,11 @@ DTYPES = [torch.float32, torch.bfloat16]
 def _ops():
     import b200unet.ops as ops
     return ops
+
+
+def _ffi():
+    import b200unet._ffi as ffi
+    return ffi
 
 
 def _K():
@@ -149,9 +154,10 @@ def test_conv_tc_fprop_dgrad(shape):
     dy = rand((n, h, w, co), 14, dt)
     filt = ops.ConvFilter(wt)
     y = torch.full((n, h, w, co), 7.0, dtype=dt, device="cuda")
-    ops.conv2d_fprop(x, filt, b, y, ops.ACT_RELU, ops.ALGO_TCGEN05)
+    cws = conv_ws(ops, x, filt, dy)
+    ops.conv2d_fprop(x, filt, b, y, ops.ACT_RELU, ops.ALGO_TCGEN05, ws=cws)
     dx = torch.full((n, h, w, ci), 7.0, dtype=dt, device="cuda")
-    ops.conv2d_dgrad(dy, filt, dx, False, ops.ALGO_TCGEN05)
+    ops.conv2d_dgrad(dy, filt, dx, False, ops.ALGO_TCGEN05, ws=cws)
     torch.cuda.synchronize()
     xr, wr = f32(x).requires_grad_(), f32(wt).requires_grad_()
     yr = K.conv2d_same(xr, wr, f32(b))
@@ -288,9 +294,10 @@ def test_conv1x1_tc(shape):
     dy = rand((n, h, w, co), 44, dt)
     filt = ops.ConvFilter(wt)
     y = torch.full((n, h, w, co), 7.0, dtype=dt, device="cuda")
-    ops.conv2d_fprop(x, filt, b, y, ops.ACT_RELU, ops.ALGO_TCGEN05)
+    cws = conv_ws(ops, x, filt, dy)
+    ops.conv2d_fprop(x, filt, b, y, ops.ACT_RELU, ops.ALGO_TCGEN05, ws=cws)
     dx = torch.full((n, h, w, ci), 7.0, dtype=dt, device="cuda")
-    ops.conv2d_dgrad(dy, filt, dx, False, ops.ALGO_TCGEN05)
+    ops.conv2d_dgrad(dy, filt, dx, False, ops.ALGO_TCGEN05, ws=cws)
     dw = torch.full((1, 1, ci, co), 7.0, dtype=torch.float32, device="cuda")
     nbytes = ops.conv2d_wgrad_workspace(x, dy, 1, 1, ops.ALGO_TCGEN05)
     ws = torch.empty(max(nbytes, 16) // 4, dtype=torch.float32, device="cuda")
@@ -320,15 +327,21 @@ def test_conv_small_spatial_splitk(shape):
     filt = ops.ConvFilter(wt)
     need = max(ops.conv2d_workspace(x, filt, False), ops.conv2d_workspace(dy, filt, True))
     assert need > 0 or max(h, w) > 4, "images of at most 4x4 pixels should take the split-K path"
-    ops.ensure_workspace(need, "cuda")          # (8x8 layers: split-K wgrad only; fprop/dgrad on the window kernel)
+    cws = ops.new_workspace(need, "cuda")       # (8x8 layers: split-K wgrad only; fprop/dgrad on the window kernel)
+    if cws is not None:
+        cws.fill_(float("nan"))                 # scratch contents must not matter
     wide = torch.zeros((n, h, w, co + 64), dtype=dt, device="cuda")
     y = wide[..., 64:]                       # channel slice: concat-in-place store
-    ops.conv2d_fprop(x, filt, b, y, ops.ACT_RELU, ops.ALGO_TCGEN05)
+    if need > 0:
+        # the path is chosen from the shapes alone: without (enough) scratch the call fails loudly, it does not switch kernels
+        with pytest.raises(_ffi().B200Error, match="scratch"):
+            ops.conv2d_fprop(x, filt, b, y, ops.ACT_RELU, ops.ALGO_TCGEN05)
+    ops.conv2d_fprop(x, filt, b, y, ops.ACT_RELU, ops.ALGO_TCGEN05, ws=cws)
     dx = torch.full((n, h, w, ci), 7.0, dtype=dt, device="cuda")
-    ops.conv2d_dgrad(dy, filt, dx, False, ops.ALGO_TCGEN05)
+    ops.conv2d_dgrad(dy, filt, dx, False, ops.ALGO_TCGEN05, ws=cws)
     base = rand((n, h, w, ci), 65, dt)
     dx2 = base.clone()
-    ops.conv2d_dgrad(dy, filt, dx2, True, ops.ALGO_TCGEN05)
+    ops.conv2d_dgrad(dy, filt, dx2, True, ops.ALGO_TCGEN05, ws=cws)
     dw = torch.full((ks, ks, ci, co), 7.0, dtype=torch.float32, device="cuda")
     nbytes = ops.conv2d_wgrad_workspace(x, dy, ks, ks, ops.ALGO_TCGEN05)
     ws = torch.empty(max(nbytes, 16) // 4, dtype=torch.float32, device="cuda")
@@ -643,10 +656,11 @@ def test_conv_transpose_tensor_core(shape):
     x = rand((n, h, w, ci), 95, dt); k = rand((2, 2, co, ci), 96, dt, 0.1); b = rand((co,), 97, scale=0.2)
     wide = torch.zeros((n, 2 * h, 2 * w, co + 64), dtype=dt, device="cuda")
     y = wide[..., :co]
-    ops.convT2x2_fprop(x, k, b, y)
     dy = rand((n, 2 * h, 2 * w, co), 98, dt)
+    cws = ops.new_workspace(max(ops.convT2x2_workspace(x, ci, co, False), ops.convT2x2_workspace(dy, co, ci, True)), "cuda")
+    ops.convT2x2_fprop(x, k, b, y, ws=cws)
     dx = torch.full_like(x, 7.0); dk = torch.full((2, 2, co, ci), 7.0, device="cuda"); dbias = torch.zeros(co, device="cuda")
-    ops.convT2x2_dgrad(dy, k, dx); ops.convT2x2_wgrad(x, dy, dk, dbias)
+    ops.convT2x2_dgrad(dy, k, dx, ws=cws); ops.convT2x2_wgrad(x, dy, dk, dbias)
     xr, kr, br = f32(x).requires_grad_(), f32(k).requires_grad_(), f32(b).requires_grad_()
     yr = K.conv2d_transpose_2x2(xr, kr, br)
     (yr * f32(dy)).sum().backward()

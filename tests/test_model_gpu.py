@@ -388,16 +388,27 @@ def test_seg_vanilla_base32_bf16_on_tensor_cores():
 
 
 def test_wgrad_side_stream_matches_single_stream():
-    """Filter-gradient kernels forked onto a second stream inside the captured step (Model._run_bwd) against the
-    single-stream order: same loss, same first-step gradients and weights (up to the summation order of the atomic partial
-    sums), same loss trajectory over several replays of the captured graph.  Third run: the experimental per-layer Adam
-    behind each wgrad (B200_OVERLAP_ADAM) on top of it."""
+    """Filter-gradient kernels forked onto a second stream inside the captured step (Model._run_bwd), and the experimental
+    per-layer Adam behind each of them (B200_OVERLAP_ADAM), against the single-stream order -- in LOCKSTEP over four steps:
+    before every step the reference run's state (fp32 master, bf16 shadow, Adam moments and step counter) is copied into
+    the other runs, then every run replays its own captured graph.
+
+    Forward and activation-gradient kernels use no atomics, so from identical state every activation, every LayerNorm
+    statistic and every activation gradient must be BIT-identical whatever the stream schedule -- any race between a
+    side-stream wgrad and the main stream would show up as a differing bit.  Parameter gradients are summed with fp32
+    atomics (summation order differs from run to run): compared per tensor at 1e-5.
+
+    Why lockstep and not free-running trajectories (round-1 failure, root-caused with tools/trajectory_probe.py,
+    profiles/r02_trajectory_probe_*.json): the atomic-order noise leaves ~13 000 of the 8.6 M fp32 master weights one ulp
+    apart after a step, which now and then rounds ONE OR TWO bf16 shadow weights the other way; in this fast-moving phase of
+    training (loss 0.36 -> 0.17 in four steps) a single such flip moves the step-2 loss by 2e-5 .. 4e-4.  The same spread
+    shows up between two runs of the SAME schedule, in isolation and in-suite; it is not a property of the second stream."""
     from b200unet import builders as B
     from b200unet.keras.optimizers import Adam
     rng = np.random.default_rng(2)
     hr = rng.random((8, 64, 64, 3), dtype=np.float32)
     lr = np.clip(hr + 0.05 * rng.standard_normal(hr.shape).astype(np.float32), 0, 1)
-    runs = []
+    models = []
     for overlap, adam in ((False, False), (True, False), (True, True)):
         _setup("mixed_bfloat16")
         model, _ = B.build_super_resolution_unet(0.5, depth_override=3, input_size=64)
@@ -406,24 +417,46 @@ def test_wgrad_side_stream_matches_single_stream():
         head.weight_specs[0]["value"] = np.random.default_rng(3).uniform(-0.2, 0.2, (1, 1, 64, 3)).astype(np.float32)
         loss, metrics = B.build_losses_and_metrics("charbonnier")
         model.compile(optimizer=Adam(learning_rate=1e-4), loss=loss, metrics=metrics)
-        p_init = None
-        losses = [model.train_on_batch(lr, hr)["loss"]]
-        g_first, p_first, s_first = model.G.clone(), model.P.clone(), model.S.clone().float()
-        m_first = model.optimizer._state["m"].clone()
-        losses += [model.train_on_batch(lr, hr)["loss"] for _ in range(3)]
-        runs.append((losses, g_first, p_first, s_first, m_first))
-    l0, g0, p0, s0, m0 = runs[0]
-    for name, (l1, g1, p1, s1, m1) in zip(("wgrad on the side stream", "+ per-layer Adam behind it"), runs[1:]):
-        e = relerr(g1, g0)
-        print(f"{name}: first-step gradient rel-L2 vs single stream {e:.3e}, Adam m {relerr(m1, m0):.3e}, "
-              f"weights {relerr(p1, p0):.3e}; losses {l1}")
-        assert abs(l0[0] - l1[0]) <= 1e-6
-        assert e < 1e-5          # only the summation order of the atomic partial sums may differ
-        assert relerr(m1, m0) < 1e-5                                  # the optimizer saw the COMPLETE gradients
-        # the first Adam step is sign-like (+-lr): an element whose tiny gradient changes sign with the summation order
-        # moves by 2 lr, so the weights are compared loosely and the first moment (above) tightly
-        assert relerr(p1, p0) < 1e-4 and relerr(s1, s0) < 1e-3
-        # later steps see weights that differ in their last bits (Adam turns rounding-level gradient differences of
-        # near-zero gradients into +-lr steps), so only the loss trajectory is compared
-        assert all(abs(a - b) <= 2e-4 * max(1.0, abs(a)) for a, b in zip(l0, l1)), (l0, l1)
+        models.append(model)
+
+    def bits(t):
+        return t.view(torch.int16 if t.dtype == torch.bfloat16 else torch.int32)
+
+    ref = models[0]
+    losses = [[], [], []]
+    for step in range(4):
+        if step:                                   # lockstep: everyone enters the step from the reference state
+            rs = ref.optimizer._state
+            for m in models[1:]:
+                ms = m.optimizer._state
+                m.P.copy_(ref.P); m.S.copy_(ref.S)
+                ms["m"].copy_(rs["m"]); ms["v"].copy_(rs["v"]); ms["step"].copy_(rs["step"])
+        snaps = []
+        for k, m in enumerate(models):
+            losses[k].append(m.train_on_batch(lr, hr)["loss"])
+            torch.cuda.synchronize()
+            plan = m._train_state(8)["plan"]
+            roots = [v for v in plan.all_vals if v.parent is None]
+            snaps.append(([(v.name, v.buf.clone()) for v in roots],
+                          [(v.name, v.grad.clone()) for v in roots if v.grad is not None],
+                          [(op.output.name, op.mean.clone(), op.rstd.clone()) for op in plan.ops if op.kind == "ln"],
+                          m.G.clone(), m.optimizer._state["m"].clone()))
+        acts0, grads0, stats0, g0, m0 = snaps[0]
+        for k in (1, 2):
+            acts, grads, stats, g, mm = snaps[k]
+            for (n0, a), (_, b) in zip(acts0, acts):
+                assert torch.equal(bits(a), bits(b)), f"step {step}, run {k}: activation {n0} differs"
+            for (n0, mu0, r0), (_, mu, r) in zip(stats0, stats):
+                assert torch.equal(bits(mu0), bits(mu)) and torch.equal(bits(r0), bits(r)), f"step {step}: LN stats {n0}"
+            for (n0, a), (_, b) in zip(grads0, grads):
+                assert torch.equal(bits(a), bits(b)), f"step {step}, run {k}: activation gradient {n0} differs"
+            assert abs(losses[0][-1] - losses[k][-1]) <= 2e-6       # the loss sum itself is an atomic reduction
+            for ly in ref.layers:                                     # parameter gradients: atomic summation order only
+                for w in ly.weight_specs:
+                    r = ref._grad_range(ly, w["name"].split("/", 1)[1]) if w["trainable"] else None
+                    if r is not None and g0[r[0]:r[0] + r[1]].abs().max() > 0:
+                        assert relerr(g[r[0]:r[0] + r[1]], g0[r[0]:r[0] + r[1]]) < 1e-5, (step, k, w["name"])
+            assert relerr(mm, m0) < 1e-5                              # the optimizer saw the COMPLETE gradients
+    print("lockstep losses:", losses)
+    assert losses[0][-1] < 0.6 * losses[0][0]                         # and it trains
     _setup("float32")

@@ -21,3 +21,14 @@ def f32(t):
 
 
 TOL = {torch.float32: 2e-5, torch.bfloat16: 1e-2}
+
+
+def conv_ws(ops, x, filt, dy=None):
+    """Per-call split-K scratch of a convolution (None when the shapes do not take that path), NaN-filled."""
+    need = ops.conv2d_workspace(x, filt, False)
+    if dy is not None:
+        need = max(need, ops.conv2d_workspace(dy, filt, True))
+    ws = ops.new_workspace(need, "cuda")
+    if ws is not None:
+        ws.fill_(float("nan"))
+    return ws

@@ -89,12 +89,12 @@ def main():
         dw = torch.empty(3, 3, ci, co, device="cuda")
         bias = torch.zeros(co, device="cuda")
         f = ops.ConvFilter(w)
-        ops.ensure_workspace(max(ops.conv2d_workspace(x, f, False), ops.conv2d_workspace(dy, f, True)), "cuda")
+        cws = ops.new_workspace(max(ops.conv2d_workspace(x, f, False), ops.conv2d_workspace(dy, f, True)), "cuda")
         ws = torch.empty(max(ops.conv2d_wgrad_workspace(x, dy, 3, 3), 16) // 4, device="cuda")
         fl = 2.0 * B * s * s * ci * co * 9
         tm = timeit_graph if os.environ.get("TABLE_GRAPH", "1") == "1" else timeit
-        t_f = tm(lambda: ops.conv2d_fprop(x, f, bias, y, 1))
-        t_d = tm(lambda: ops.conv2d_dgrad(dy, f, dx))
+        t_f = tm(lambda: ops.conv2d_fprop(x, f, bias, y, 1, ws=cws))
+        t_d = tm(lambda: ops.conv2d_dgrad(dy, f, dx, ws=cws))
         t_w = tm(lambda: ops.conv2d_wgrad(x, dy, 3, 3, dw, ws))
         rows.append({"hw": s, "cin": ci, "cout": co, "gflop": fl / 1e9,
                      "fprop_us": t_f * 1e3, "fprop_tf": fl / t_f / 1e9,
