@@ -226,13 +226,16 @@ softmax_ce_kernel(TView prob, const int* __restrict__ labels, float gscale, floa
     pix_decode(i, prob.h, prob.w, n, h, w);
     const T* s = pp + pix_offset(prob, n, h, w);
     const int y = labels[i];
+    // a label outside [0, C) (e.g. a 255 "ignore" id) has no one-hot row: the pixel contributes no loss and no gradient
+    // (it still counts in the mean's denominator, as an all-zero one-hot target does in keras) -- never an out-of-bounds read
+    const bool known = y >= 0 && y < C;
     float sum = 0.f;
     for (int c = 0; c < C; ++c) sum += ldf(s + c);
-    float q = ldf(s + y) / sum;
+    float q = known ? ldf(s + y) / sum : 1.f;
     float qc = fminf(fmaxf(q, 1e-7f), 1.f - 1e-7f);
-    lsum += -logf(qc);
+    if (known) lsum += -logf(qc);
     if (gp) {
-      const float pass = (q >= 1e-7f && q <= 1.f - 1e-7f) ? inv_n : 0.f;
+      const float pass = (known && q >= 1e-7f && q <= 1.f - 1e-7f) ? inv_n : 0.f;
       T* d = gp + pix_offset(dz, n, h, w);
       for (int c = 0; c < C; ++c) stf(d + c, pass * (ldf(s + c) / sum - (c == y ? 1.f : 0.f)));
     }

@@ -60,6 +60,14 @@ def _init_array(kind, shape, rng):
     raise NotImplementedError(f"initializer {kind!r}")
 
 
+def _to_snake_case(name: str) -> str:
+    """keras.src.utils.naming.to_snake_case (the rule behind the group names of model.weights.h5)."""
+    import re
+    name = re.sub(r"\W+", "", name)
+    name = re.sub("(.)([A-Z][a-z]+)", r"\1_\2", name)
+    return re.sub("([a-z])([A-Z])", r"\1_\2", name).lower()
+
+
 def format_epoch_line(steps: int, seconds: float, logs: Dict[str, float]) -> str:
     """The keras ``verbose=2`` epoch summary (``3/3 - 1s - 412ms/step - loss: 0.0123 - psnr: 31.2 ...``), kept parseable by the
     reference's log exporter (Super_resolution/code/export_log_metrics.py:29-74)."""
@@ -307,30 +315,173 @@ class Model:
                 return ly
         raise ValueError(f"No such layer: {name}")
 
-    # checkpoints: a .keras file is a zip; the weights member is an .npz because h5py is not
-    # available in this image (documented deviation).
-    def save(self, path):
+    # ------------------------------------------------------------------ checkpoints (keras-3 layout)
+    def _h5_layer_names(self):
+        """The group name keras gives each layer inside model.weights.h5: the snake-cased CLASS name, numbered per class
+        in `model.layers` order ("conv2d", "conv2d_1", ... -- keras.src.saving.saving_lib._save_container_state; layer
+        names are deliberately not used there).  Our `layers` order equals keras' (pinned by the 885 summary rows)."""
+        used, out = {}, []
+        for ly in self.layers:
+            base = _to_snake_case(type(ly).__name__)
+            if base in used:
+                used[base] += 1
+                out.append(f"{base}_{used[base]}")
+            else:
+                used[base] = 0
+                out.append(base)
+        return out
+
+    def _weights_tree(self, include_optimizer=True):
+        tree = {"vars": {}, "layers": {}}
+        for ly, h5name in zip(self.layers, self._h5_layer_names()):
+            tree["layers"][h5name] = {"vars": {str(i): a for i, a in enumerate(self._layer_weights(ly))}}
+        opt = self.optimizer
+        if include_optimizer and opt is not None and getattr(opt, "_state", None) is not None:
+            # keras Adam: [iterations, learning_rate, m_0, v_0, m_1, v_1, ...] over model.trainable_variables
+            st = opt._state
+            ov = {"0": np.array(int(opt.iterations), dtype=np.int64), "1": np.array(opt.current_lr(), dtype=np.float32)}
+            k = 2
+            m_all, v_all = st["m"], st["v"]
+            if self._sharded():
+                m_all, v_all = self._gather_flat(m_all), self._gather_flat(v_all)
+            for ly in self.layers:
+                for w in ly.weight_specs:
+                    if w["trainable"]:
+                        nm = w["name"].split("/", 1)[1]
+                        ov[str(k)] = self._view(m_all, ly, nm).detach().cpu().numpy().copy()
+                        ov[str(k + 1)] = self._view(v_all, ly, nm).detach().cpu().numpy().copy()
+                        k += 2
+            tree["optimizer"] = {"vars": ov}
+        return tree
+
+    def _gather_flat(self, flat):
+        """Collective: a copy of a flat per-parameter buffer (Adam m / v) with every sharded bucket all-gathered."""
+        out = flat.clone()
+        plan = getattr(self, "_last_train_plan", None)
+        if plan is not None and self._sharded():
+            from ..parallel import all_gather_bucket
+            dist, group = self._dist
+            for b in self._buckets(plan):
+                if b["sharded"]:
+                    all_gather_bucket(dist, out, b, group=group)
+        return out
+
+    def save(self, path, include_optimizer=True, **kwargs):
+        """``model.save("x.keras")`` / ``save_weights("x.weights.h5")`` in the keras-3 on-disk layout: a `.keras` file is a
+        zip of config.json, metadata.json and model.weights.h5, whose groups are ``layers/<class_snake[_k]>/vars/<i>`` (+
+        ``optimizer/vars/<i>``) -- the file keras' ``load_weights`` reads (train_adaptive_unet.py:511-516,
+        evaluate_model.py:57-91).  The HDF5 bytes come from the in-tree writer (h5lite; h5py is absent here).
+        config.json describes the layers (class + get_config()) but is not a keras functional config:
+        ``keras.models.load_model`` on it takes the reference evaluator's rebuild-and-load_weights branch."""
+        from .. import h5lite
         path = str(path)
-        buf = io.BytesIO()
-        np.savez(buf, **{f"w{i:04d}": a for i, a in enumerate(self.get_weights())})
-        cfg = {"name": self.name, "layers": [{"class": type(ly).__name__, "config": ly.get_config()} for ly in self.layers],
+        blob = h5lite.write_h5(self._weights_tree(include_optimizer))
+        if not path.endswith(".keras"):
+            with open(path, "wb") as f:
+                f.write(blob)
+            return
+        cfg = {"module": "b200unet.keras", "class_name": "Functional", "name": self.name,
+               "layers": [{"class": type(ly).__name__, "name": ly.name, "config": ly.get_config()} for ly in self.layers],
                "weight_names": [w["name"] for w in self.weights]}
+        meta = {"keras_version": "3.3.3", "date_saved": time.strftime("%Y-%m-%d@%H:%M:%S"), "writer": "b200unet"}
         with zipfile.ZipFile(path, "w") as z:
+            z.writestr("metadata.json", json.dumps(meta))
             z.writestr("config.json", json.dumps(cfg, default=str))
-            z.writestr("metadata.json", json.dumps({"format": "b200unet-npz", "keras_version": "3.3.3-compatible-api"}))
-            z.writestr("model.weights.npz", buf.getvalue())
+            z.writestr("model.weights.h5", blob)
 
     save_weights = save
 
-    def load_weights(self, path):
+    def load_weights(self, path, skip_mismatch=False, **kwargs):
+        """Load a keras-3 `.keras` archive / `.weights.h5` file (written by keras + h5py or by ``save`` above), or a
+        round-1 archive with an ``.npz`` member.  Every layer's variable count and shapes are checked against the model;
+        a file from another depth / variant fails with the first mismatching layer named."""
+        from .. import h5lite
         path = str(path)
-        with zipfile.ZipFile(path) as z:
-            names = z.namelist()
-            if "model.weights.npz" not in names:
-                raise B200Error(f"{path}: no model.weights.npz member (HDF5 .keras archives need h5py, "
-                                "which this image lacks; convert with tools/keras_to_npz.py)")
-            data = np.load(io.BytesIO(z.read("model.weights.npz")))
-        self.set_weights([data[k] for k in sorted(data.files)])
+        with open(path, "rb") as f:
+            head = f.read(8)
+        tree = None
+        if head[:4] == b"PK\x03\x04":
+            with zipfile.ZipFile(path) as z:
+                names = z.namelist()
+                if "model.weights.h5" in names:
+                    tree = h5lite.read_h5(z.read("model.weights.h5"))
+                elif "model.weights.npz" in names:           # round-1 archives: positional arrays + stored weight names
+                    data = np.load(io.BytesIO(z.read("model.weights.npz")))
+                    cfg = json.loads(z.read("config.json")) if "config.json" in names else {}
+                    stored = cfg.get("weight_names")
+                    mine = [w["name"] for w in self.weights]
+                    if stored is not None and list(stored) != mine:
+                        raise B200Error(f"{path}: the archive holds weights {stored[:3]}... of another model "
+                                        f"({len(stored)} arrays; this model has {len(mine)}: {mine[:3]}...)")
+                    self.set_weights([data[k] for k in sorted(data.files)])
+                    return
+                else:
+                    raise B200Error(f"{path}: no model.weights.h5 member -- not a keras-3 archive (members: {names})")
+        else:
+            try:
+                tree = h5lite.read_h5(open(path, "rb").read())
+            except h5lite.H5Error as e:
+                raise B200Error(f"{path}: neither a .keras zip archive nor a readable HDF5 weights file ({e})") from e
+        layers = tree.get("layers")
+        if not isinstance(layers, dict):
+            raise B200Error(f"{path}: no 'layers' group in the weights file (top-level: {sorted(tree)}); files saved by "
+                            "keras 2.x / tf.keras use another layout")
+        values = []
+        for ly, h5name in zip(self.layers, self._h5_layer_names()):
+            specs = ly.weight_specs
+            got = layers.get(h5name, {}).get("vars", {}) if isinstance(layers.get(h5name), dict) else {}
+            if len(got) != len(specs):
+                if skip_mismatch:
+                    values += [None] * len(specs)
+                    continue
+                raise B200Error(f"{path}: layer '{ly.name}' ({h5name}) expects {len(specs)} variables, the file holds "
+                                f"{len(got)} -- a checkpoint of a different architecture (depth / variant)?")
+            for i, w in enumerate(specs):
+                a = np.asarray(got[str(i)])
+                if tuple(a.shape) != tuple(w["shape"]):
+                    if skip_mismatch:
+                        values.append(None)
+                        continue
+                    raise B200Error(f"{path}: {w['name']} ({h5name}/vars/{i}) has shape {tuple(a.shape)} in the file, "
+                                    f"{tuple(w['shape'])} in the model")
+                values.append(a.astype(np.float32))
+        extra = sorted(set(layers) - set(self._h5_layer_names()))
+        if extra and not skip_mismatch:
+            raise B200Error(f"{path}: the file holds layers this model does not have: {extra[:5]}")
+        if any(v is None for v in values):
+            cur = self.get_weights()
+            values = [c if v is None else v for v, c in zip(values, cur)]
+        self.set_weights(values)
+        self._load_optimizer_state(tree.get("optimizer"))
+
+    def _load_optimizer_state(self, node):
+        """Adam state of a checkpoint (keras layout, see _weights_tree) into a compiled model; silently skipped when the
+        file has none and with a warning when the variable count does not match (keras does the same)."""
+        opt = self.optimizer
+        if not isinstance(node, dict) or opt is None or self._sharded():
+            return
+        ov = node.get("vars", {})
+        trainable = [(ly, w["name"].split("/", 1)[1], w["shape"]) for ly in self.layers for w in ly.weight_specs if w["trainable"]]
+        if len(ov) != 2 + 2 * len(trainable):
+            if ov:
+                import warnings
+                warnings.warn(f"skipping optimizer state: the file holds {len(ov)} optimizer variables, this model's Adam "
+                              f"has {2 + 2 * len(trainable)}")
+            return
+        self._ensure_built()
+        opt.ensure_state(self)
+        st = opt._state
+        k = 2
+        for ly, nm, shape in trainable:
+            m, v = np.asarray(ov[str(k)], np.float32), np.asarray(ov[str(k + 1)], np.float32)
+            if tuple(m.shape) != tuple(shape) or tuple(v.shape) != tuple(shape):
+                return
+            self._view(st["m"], ly, nm).copy_(torch.from_numpy(m).to(self._device))
+            self._view(st["v"], ly, nm).copy_(torch.from_numpy(v).to(self._device))
+            k += 2
+        it = int(np.asarray(ov["0"]))
+        opt.iterations = it
+        st["step"].fill_(it)
 
     # ------------------------------------------------------------------ summary
     def summary(self, print_fn=print, line_length=78):
@@ -781,28 +932,39 @@ class Model:
 
     # ------------------------------------------------------------------ fit / evaluate
     def evaluate(self, dataset, steps=None, return_dict=False, verbose=0):
-        sums, n = {}, 0
+        sums, weight = {}, 0.0
         for i, (x, y) in enumerate(dataset):
             if steps is not None and i >= steps:
                 break
             logs = self.test_on_batch(x, y)
+            b = float(x.shape[0])
             for k, v in logs.items():
-                sums[k] = sums.get(k, 0.0) + float(v)
-            n += 1
-        res = self._mean_over_ranks({k: v / max(n, 1) for k, v in sums.items()})
+                sums[k] = sums.get(k, 0.0) + float(v) * b
+            weight += b
+        res = self._weighted_mean(sums, weight)
         return res if return_dict else list(res.values())
 
-    def _mean_over_ranks(self, logs: Dict[str, float]) -> Dict[str, float]:
-        """Data parallel: every rank sees its shard only; callbacks (EarlyStopping, ModelCheckpoint, ReduceLROnPlateau)
-        must take the same decisions everywhere, so epoch-level logs are averaged over the ranks (collective)."""
-        if self._dist is None or self._world() == 1 or not logs:
-            return logs
-        dist, group = self._dist
-        keys = sorted(logs)
-        t = torch.tensor([float(logs[k]) for k in keys], dtype=torch.float64, device=self._device)
-        dist.all_reduce(t, group=group)
-        t /= self._world()
-        return {k: float(v) for k, v in zip(keys, t.tolist())}
+    def _log_keys(self):
+        return ["loss"] + list(getattr(self.loss, "metric_names", ()))
+
+    def _weighted_mean(self, sums: Dict[str, float], weight: float) -> Dict[str, float]:
+        """Epoch-level logs as keras computes them: every batch weighted by its sample count (a ragged last batch counts
+        for less), i.e. sum(value * batch) / sum(batch).  Data parallel: the sums and the sample count are all-reduced, so
+        callbacks (EarlyStopping, ModelCheckpoint, ReduceLROnPlateau) take the same decisions on every rank -- and EVERY
+        rank takes part in the collective, also one that saw no batch (it contributes zeros)."""
+        keys = self._log_keys() if self.loss is not None else sorted(sums)
+        keys = keys + [k for k in sorted(sums) if k not in keys]
+        if self._dist is not None and self._world() > 1:
+            dist, group = self._dist
+            t = torch.tensor([float(sums.get(k, 0.0)) for k in keys] + [float(weight)], dtype=torch.float64,
+                             device=self._device)
+            dist.all_reduce(t, group=group)
+            vals = t.tolist()
+            weight = vals[-1]
+            sums = {k: v for k, v in zip(keys, vals[:-1])}
+        if weight <= 0:
+            return {}
+        return {k: float(sums[k]) / weight for k in keys if k in sums}
 
     def fit(self, x=None, y=None, epochs=1, initial_epoch=0, steps_per_epoch=None, validation_data=None,
             validation_steps=None, validation_freq=1, callbacks=None, verbose=1, batch_size=None, **kwargs):
@@ -820,7 +982,7 @@ class Model:
             cbs.on_epoch_begin(epoch)
             t0 = time.time()
             acc: Dict[str, torch.Tensor] = {}
-            steps = 0
+            steps, samples = 0, 0.0
             while steps_per_epoch is None or steps < steps_per_epoch:
                 try:
                     xb, yb = next(train_iter)
@@ -830,12 +992,14 @@ class Model:
                     train_iter = iter(x)
                     xb, yb = next(train_iter)
                 logs = self.train_on_batch(xb, yb, return_tensors=True)
+                b = float(xb.shape[0])
                 for k, v in logs.items():
-                    acc[k] = v.clone() if k not in acc else acc[k] + v
+                    acc[k] = v.double() * b if k not in acc else acc[k] + v.double() * b
                 steps += 1
+                samples += b
             if steps_per_epoch is None:
                 train_iter = iter(x)
-            logs = self._mean_over_ranks({k: float(v) / max(steps, 1) for k, v in acc.items()})
+            logs = self._weighted_mean({k: float(v) for k, v in acc.items()}, samples)
             if validation_data is not None and (epoch + 1) % validation_freq == 0:
                 val = self.evaluate(validation_data, steps=validation_steps, return_dict=True)
                 logs.update({f"val_{k}": v for k, v in val.items()})

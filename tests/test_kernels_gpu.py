@@ -184,7 +184,7 @@ def test_conv_ln_fused(shape, relu):
     filt = ops.ConvFilter(wt)
     z = torch.full((n, h, w, co), 7.0, dtype=dt, device="cuda"); y = torch.full_like(z, 7.0)
     mean = torch.zeros(n * h * w, device="cuda"); rstd = torch.zeros_like(mean)
-    ops.conv2d_ln_fprop(x, filt, b, g, be, 1e-3, relu, z, y, mean, rstd)
+    ops.conv2d_ln_fprop(x, filt, b, g, be, 1e-3, relu, z, y, mean, rstd, ws=conv_ws(ops, x, filt))
     torch.cuda.synchronize()
     zr = K.conv2d_same(f32(x), f32(wt), f32(b))
     zr16 = zr.to(torch.bfloat16).float()
@@ -198,7 +198,7 @@ def test_conv_ln_fused(shape, relu):
     assert (f32(mean) - mr).abs().max() < 2e-2
     # inference form: no z kept
     y2 = torch.empty_like(y)
-    ops.conv2d_ln_fprop(x, filt, b, g, be, 1e-3, relu, None, y2, mean, rstd)
+    ops.conv2d_ln_fprop(x, filt, b, g, be, 1e-3, relu, None, y2, mean, rstd, ws=conv_ws(ops, x, filt))
     assert relerr(y2, y) < 1e-6 or co > 128 or ci == 3
 
 
@@ -737,6 +737,19 @@ def test_softmax_ce(dtype):
     assert relerr(p, pr) < TOL[dtype]
     assert abs(out[0].item() - l.item()) < (1e-5 if dtype == torch.float32 else 2e-2)
     assert relerr(dz, zr.grad) < (1e-4 if dtype == torch.float32 else 3e-2)
+    # labels outside [0, C) (an "ignore" id such as 255, or -1): an all-zero one-hot row -- no loss, no gradient, no
+    # out-of-bounds read; the mean keeps its denominator
+    lab2 = labels.clone()
+    lab2[0, 0, :2] = 255
+    lab2[1, 2, 1] = -1
+    ops.softmax_ce_loss(p, lab2, 1.0, out, dz, ws)
+    oh2 = onehot.clone()
+    oh2[0, 0, :2] = 0
+    oh2[1, 2, 1] = 0
+    pr2 = torch.softmax(f32(z), dim=-1)
+    l2 = -(oh2 * torch.log(pr2.clamp(1e-7, 1 - 1e-7))).sum(-1).mean()
+    assert abs(out[0].item() - l2.item()) < (1e-5 if dtype == torch.float32 else 2e-2)
+    assert float(f32(dz)[0, 0, :2].abs().max()) == 0.0 and float(f32(dz)[1, 2, 1].abs().max()) == 0.0
 
 
 def test_adam():

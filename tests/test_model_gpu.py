@@ -290,18 +290,71 @@ def test_seg_vanilla_step(num_classes):
 
 
 def test_save_load_roundtrip(tmp_path):
-    from b200unet import builders as B
+    """`.keras` archives in the keras-3 layout (zip: config.json, metadata.json, model.weights.h5 with
+    layers/<class_snake[_k]>/vars/<i> and optimizer/vars/<i>): weights and Adam state survive a round trip, the bare
+    `.weights.h5` form loads too, and a checkpoint of another architecture is refused with the layer named
+    (/root/reference: train_adaptive_unet.py:496-531, 617; evaluate_model.py:57-91)."""
+    import io, json, zipfile
+    from b200unet import builders as B, h5lite
+    from b200unet._ffi import B200Error
+    from b200unet.keras import clear_session
+    from b200unet.keras.optimizers import Adam
     _setup("float32")
     m1, _ = B.build_super_resolution_unet(0.5, depth_override=1, input_size=16)
+    loss, metrics = B.build_losses_and_metrics("charbonnier")
+    m1.compile(optimizer=Adam(1e-3), loss=loss, metrics=metrics)
+    rng = np.random.default_rng(0)
+    hr = rng.random((2, 16, 16, 3), dtype=np.float32)
+    head = m1.get_layer("residual_rgb")
     m1._ensure_built()
+    w = m1.get_weights(); w[-2] = rng.uniform(-0.2, 0.2, w[-2].shape).astype(np.float32); m1.set_weights(w)
+    for _ in range(3):
+        m1.train_on_batch(hr * 0.9, hr)
     path = tmp_path / "ckpt.keras"
     m1.save(path)
-    from b200unet.keras import clear_session
+    with zipfile.ZipFile(path) as z:
+        assert sorted(z.namelist()) == ["config.json", "metadata.json", "model.weights.h5"]
+        assert json.loads(z.read("metadata.json"))["keras_version"] == "3.3.3"
+        blob = z.read("model.weights.h5")
+    h5lite.validate(blob)
+    tree = h5lite.read_h5(blob)
+    assert tree["layers"]["conv2d"]["vars"]["0"].shape == (3, 3, 3, 64) and tree["layers"]["input_layer"]["vars"] == {}
+    assert int(tree["optimizer"]["vars"]["0"]) == 3
     clear_session()
     m2, _ = B.build_super_resolution_unet(0.5, depth_override=1, input_size=16)
+    m2.compile(optimizer=Adam(1e-3), loss=loss, metrics=metrics)
     m2.load_weights(path)
     for a, b in zip(m1.get_weights(), m2.get_weights()):
         assert np.array_equal(a, b)
+    assert m2.optimizer.iterations == 3
+    assert torch.equal(m1.optimizer._state["m"], m2.optimizer._state["m"])
+    assert torch.equal(m1.optimizer._state["v"], m2.optimizer._state["v"])
+    l1 = m1.train_on_batch(hr * 0.9, hr)["loss"]           # and training resumes on the same trajectory
+    l2 = m2.train_on_batch(hr * 0.9, hr)["loss"]
+    assert abs(l1 - l2) <= 1e-6 * max(1.0, abs(l1))
+    # bare weights file
+    m1.save_weights(tmp_path / "w.weights.h5")
+    clear_session()
+    m3, _ = B.build_super_resolution_unet(0.5, depth_override=1, input_size=16)
+    m3.load_weights(tmp_path / "w.weights.h5")
+    assert all(np.array_equal(a, b) for a, b in zip(m1.get_weights(), m3.get_weights()))
+    # another depth: refused, naming the first layer that does not fit
+    clear_session()
+    m4, _ = B.build_super_resolution_unet(0.5, depth_override=2, input_size=16)
+    with pytest.raises(B200Error, match="conv2d|expects"):
+        m4.load_weights(path)
+    (tmp_path / "junk.keras").write_bytes(b"not a checkpoint at all, just bytes" * 40)
+    with pytest.raises(B200Error, match="neither"):
+        m3.load_weights(tmp_path / "junk.keras")
+    # round-1 archives (npz member) still load, and their stored weight names are checked
+    buf = io.BytesIO()
+    np.savez(buf, **{f"w{i:04d}": a for i, a in enumerate(m1.get_weights())})
+    with zipfile.ZipFile(tmp_path / "old.keras", "w") as z:
+        z.writestr("config.json", json.dumps({"weight_names": [x["name"] for x in m1.weights]}))
+        z.writestr("model.weights.npz", buf.getvalue())
+    m3.load_weights(tmp_path / "old.keras")
+    with pytest.raises(B200Error, match="another model"):
+        m4.load_weights(tmp_path / "old.keras")
 
 
 def test_sr_vanilla_bn_unet_step():
