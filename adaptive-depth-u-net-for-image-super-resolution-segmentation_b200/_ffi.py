@@ -15,7 +15,7 @@ LIB_PATH = HERE / "lib" / "libb200unet.so"
 F32, BF16, U8 = 0, 1, 2
 CV_INTER_AREA, CV_INTER_CUBIC = 0, 1
 ACT_NONE, ACT_RELU, ACT_SIGMOID = 0, 1, 2
-ALGO_AUTO, ALGO_SIMT, ALGO_TCGEN05 = 0, 1, 2
+ALGO_AUTO, ALGO_SIMT, ALGO_TCGEN05, ALGO_TCGEN05_1CTA = 0, 1, 2, 3
 LOSS_CHARBONNIER, LOSS_L1, LOSS_MSE = 0, 1, 2
 
 

@@ -44,7 +44,7 @@ bool conv_tc_ln_supported(int cout);
 bool conv_gemm_wanted(const b200_tensor*, int, int, int);
 size_t conv_gemm_workspace(const b200_tensor*, int, int, int);
 int conv_tc_launch(const b200_tensor*, const void*, int, int, int, int, const float*, const b200_tensor*, int, int, cudaStream_t,
-                   const ConvLnArgs* ln, int ks, void* ws, size_t ws_bytes);
+                   const ConvLnArgs* ln, int ks, void* ws, size_t ws_bytes, const void* wmat_k = nullptr, int allow_pairs = 1);
 int umma_probe(const void*, int, const void*, int, int, int, int, float*, cudaStream_t);
 int umma_rate(int, int, int, long long*, int, cudaStream_t);
 bool stem_supported(const b200_tensor*, const b200_tensor*, int);
@@ -150,9 +150,10 @@ int b200_conv2d_fprop(const b200_tensor* x, const b200_filter* f, const float* b
                x->c, y->n, y->h, y->w, y->c, f->cin, f->cout);
   const bool tc_ok = (f->kh == 3 || f->kh == 1) && f->kw == f->kh && f->dtype == B200_BF16 &&
                      (act == B200_ACT_NONE || act == B200_ACT_RELU) && conv_tc_supported(x, f->cin, f->cout, y, f->kh);
-  if (algo == B200_ALGO_TCGEN05 || (algo == B200_ALGO_AUTO && tc_ok)) {
+  if (algo == B200_ALGO_TCGEN05 || algo == B200_ALGO_TCGEN05_1CTA || (algo == B200_ALGO_AUTO && tc_ok)) {
     B200_REQUIRE(tc_ok, B200_ERR_UNSUPPORTED, "conv2d_fprop: tcgen05 path does not support this shape/dtype");
-    return conv_tc_launch(x, f->hwio, f->cin, f->cout, 0, 1, bias, y, act, 0, ST(stream), nullptr, f->kh, WS_PTR(ws), WS_BYTES(ws));
+    return conv_tc_launch(x, f->hwio, f->cin, f->cout, 0, 1, bias, y, act, 0, ST(stream), nullptr, f->kh, WS_PTR(ws), WS_BYTES(ws),
+                          f->ohwi, algo != B200_ALGO_TCGEN05_1CTA);
   }
   if (algo == B200_ALGO_AUTO && f->dtype == x->dtype && f->kh == f->kw) {
     if (stem_supported(x, y, f->kh) && act != B200_ACT_SIGMOID) return stem_fprop(x, f->hwio, bias, y, act, ST(stream));
@@ -176,7 +177,8 @@ int b200_conv2d_ln_fprop(const b200_tensor* x, const b200_filter* f, const float
                      algo != B200_ALGO_SIMT && !conv_gemm_wanted(x, f->cin, f->cout, f->kh);
   if (fused) {
     ConvLnArgs ln{gamma, beta, eps, relu, have_z ? z : nullptr, mean, rstd};
-    return conv_tc_launch(x, f->hwio, f->cin, f->cout, 0, 1, bias, y, B200_ACT_NONE, 0, ST(stream), &ln, f->kh, nullptr, 0);
+    return conv_tc_launch(x, f->hwio, f->cin, f->cout, 0, 1, bias, y, B200_ACT_NONE, 0, ST(stream), &ln, f->kh, nullptr, 0,
+                          f->ohwi, algo != B200_ALGO_TCGEN05_1CTA);
   }
   // composition: convolution into z (or into y when the caller keeps no z), then the stand-alone LayerNorm
   const b200_tensor* zz = have_z ? z : y;
@@ -195,10 +197,10 @@ int b200_conv2d_dgrad(const b200_tensor* dy, const b200_filter* f, const b200_te
   // is the HWIO kernel itself, read with the tap order reversed.
   const bool tc_ok = (f->kh == 3 || f->kh == 1) && f->kw == f->kh && f->dtype == B200_BF16 &&
                      conv_tc_supported(dy, f->cout, f->cin, dx, f->kh);
-  if (algo == B200_ALGO_TCGEN05 || (algo == B200_ALGO_AUTO && tc_ok)) {
+  if (algo == B200_ALGO_TCGEN05 || algo == B200_ALGO_TCGEN05_1CTA || (algo == B200_ALGO_AUTO && tc_ok)) {
     B200_REQUIRE(tc_ok, B200_ERR_UNSUPPORTED, "conv2d_dgrad: tcgen05 path does not support this shape/dtype");
     return conv_tc_launch(dy, f->hwio, f->cout, f->cin, 1, 0, nullptr, dx, B200_ACT_NONE, accumulate, ST(stream), nullptr,
-                          f->kh, WS_PTR(ws), WS_BYTES(ws));
+                          f->kh, WS_PTR(ws), WS_BYTES(ws), nullptr, algo != B200_ALGO_TCGEN05_1CTA);
   }
   if (algo == B200_ALGO_AUTO && f->dtype == dx->dtype && f->kh == f->kw && head_supported(dx, dy, f->kh))
     return head_dgrad(dy, f->hwio, dx, accumulate, ST(stream));

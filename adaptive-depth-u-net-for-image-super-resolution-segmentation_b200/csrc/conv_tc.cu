@@ -119,6 +119,9 @@ struct ConvTcParams {
   // epilogue groups (EPI == 1 only): 2 = two 4-warp groups alternate tiles, group g owns accumulator stage g and half of
   // the slots, so the LayerNorm epilogue's dependent-instruction latency overlaps between two warps per scheduler
   int egroups;
+  // CTA pairs (cta_group::2): the two CTAs of a cluster work on two neighbouring pixel tiles with ONE M = 256 MMA stream
+  // issued by the leader; each CTA stages its own window and its HALF of every weight tile (wt_bytes = BN/2 rows)
+  int cg2, wt_bytes;
   int b_mn;   // 1: B operand is MN-major (fprop reads the Keras HWIO kernel [tap][cin][cout] as is); 0: K-major (dgrad)
   int Kc;     // K total (input channels of this convolution)
   int ntaps, tap0;  // 9, 0 for a 3x3 filter; 1, 4 for a 1x1 filter (centre tap only; its weights are matrix block 0)
@@ -144,22 +147,39 @@ struct ConvTcParams {
 
 // D[tmem] (+)= A * B^T with the descriptors given as (lo, hi) words: the hi words are loop
 // invariants and the lo words advance by plain 32-bit adds in the single issuing thread.
+template <bool CG2 = false>
 __device__ __forceinline__ void umma_lohi(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
                                           uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 p, %6, 0;\n\t"
-      "mov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %4};\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}\n"
-      ::"r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
-      : "memory");
+  if (CG2)
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 p, %6, 0;\n\t"
+        "mov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %4};\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %5, p;\n\t}\n"
+        ::"r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+        : "memory");
+  else
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 p, %6, 0;\n\t"
+        "mov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %4};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}\n"
+        ::"r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+        : "memory");
 }
 
 // One {BN x 64} weight tile for (64-channel K block kb, tap, N tile j) into shared memory.
 //   K-major (dgrad):  matrix rows = tap*Cout + n, cols = k      -> one box {64 k, BN rows}
 //   MN-major (fprop): matrix rows = tap*K + k,   cols = n (HWIO) -> BN/64 boxes {64 n, 64 k rows}, 8 KB apart
+// CTA pairs: CTA `crank` loads ITS half of the tile (N columns [crank*BN/2, (crank+1)*BN/2)) and signals the leader's barrier.
+template <bool CG2>
 __device__ __forceinline__ void load_weight_tile(const ConvTcParams& p, const CUtensorMap* tm_b, uint32_t dst,
-                                                 uint32_t bar, int kb, int tap, int j) {
-  if (p.b_mn) {
+                                                 uint32_t bar, int kb, int tap, int j, uint32_t crank) {
+  if (CG2) {
+    if (p.b_mn)   // BN = 128 only: one 64-column atom per CTA
+      tma_load_2d_cg2(dst, tm_b, bar, j * p.BN + (int)crank * 64, (tap - p.tap0) * p.Kc + kb * 64);
+    else
+      tma_load_2d_cg2(dst, tm_b, bar, kb * 64,
+                      ((p.tap_rev ? 8 - tap : tap) - p.tap0) * p.Cout + j * p.BN + (int)crank * (p.BN / 2));
+  } else if (p.b_mn) {
     for (int a = 0; a < p.BN / 64; ++a)
       tma_load_2d(dst + a * 8192, tm_b, bar, j * p.BN + a * 64, (tap - p.tap0) * p.Kc + kb * 64);
   } else {
@@ -283,7 +303,7 @@ __device__ __forceinline__ void ln_load(uint32_t taddr, const float* s_bias, uin
 
 // EPI selects which epilogues an instantiation contains (the LayerNorm epilogue's code generation is sensitive to
 // what else lives in the kernel): 0 = all, 1 = LayerNorm over 64 channels, 2 = LayerNorm over 128, 3 = no LayerNorm
-template <bool PAIR, int EPI>
+template <bool PAIR, int EPI, bool CG2 = false>
 __global__ void __launch_bounds__(EPI == 1 ? NTHREADS2 : NTHREADS, 1)
 conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_b,
                   const __grid_constant__ CUtensorMap tm_y, const __grid_constant__ CUtensorMap tm_z,
@@ -298,15 +318,27 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
   const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t win0 = smem0;
   const uint32_t wt0 = smem0 + (uint32_t)p.nsw * (uint32_t)(PAIR ? PAIR_WIN_STAGE : WIN_STAGE);
-  const uint32_t wt_bytes = (uint32_t)p.BN * 128u;
+  const uint32_t wt_bytes = (uint32_t)p.wt_bytes;
   const uint32_t tmem_cols = 2u * (uint32_t)p.BN;
   const uint32_t stg0 = wt0 + (uint32_t)p.nsb * wt_bytes;
   float* s_bias = reinterpret_cast<float*>(smem_raw + (stg0 - smem_u32(smem_raw)) + (size_t)p.nslots * SLOT_BYTES);
+  // CTA pair: rank within the cluster (0 = leader, the MMA issuer), and the work-item walk of this CTA: item q of the
+  // cluster is the tile pair (2t, 2t+1) for N tile j; this CTA takes tile 2t + crank (a tile past the end is all padding)
+  const uint32_t crank = CG2 ? cluster_ctarank() : 0u;
+  const int q0 = CG2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int qstep = CG2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  auto item_of = [&](int q) { return CG2 ? ((q / p.n_tiles) * 2 + (int)crank) * p.n_tiles + q % p.n_tiles : q; };
+  // "full" barriers and the accumulator-free barriers live in the LEADER and count arrivals of both CTAs
+  auto lead = [&](uint64_t* bar) { return CG2 ? mapa_shared(smem_u32(bar), 0) : smem_u32(bar); };
+  // (plain CTA-scope waits also for barriers the peer arrives on: what they order is the async proxy's shared-memory /
+  // tensor-memory traffic, fenced by tcgen05.fence; a cluster-scope acquire would cost an L1 invalidate -- CCTL.IVALL -- per wait)
+  auto wait = [&](uint32_t bar, uint32_t parity) { mbar_wait(bar, parity); };
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < p.nsw; ++i) { mbar_init(smem_u32(&bar_full_w[i]), 1); mbar_init(smem_u32(&bar_empty_w[i]), 1); }
-    for (int i = 0; i < p.nsb; ++i) { mbar_init(smem_u32(&bar_full_b[i]), 1); mbar_init(smem_u32(&bar_empty_b[i]), 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&bar_tmem_full[i]), 1); mbar_init(smem_u32(&bar_tmem_empty[i]), 4); }
+    const uint32_t np = CG2 ? 2u : 1u;
+    for (int i = 0; i < p.nsw; ++i) { mbar_init(smem_u32(&bar_full_w[i]), np); mbar_init(smem_u32(&bar_empty_w[i]), 1); }
+    for (int i = 0; i < p.nsb; ++i) { mbar_init(smem_u32(&bar_full_b[i]), np); mbar_init(smem_u32(&bar_empty_b[i]), 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&bar_tmem_full[i]), 1); mbar_init(smem_u32(&bar_tmem_empty[i]), 4 * np); }
     fence_barrier_init();
   }
   for (int i = threadIdx.x; i < p.Cout; i += blockDim.x) {
@@ -317,7 +349,11 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
     prefetch_tmap(&tm_x); prefetch_tmap(&tm_b);
     if (p.tma_store) { prefetch_tmap(&tm_y); if (p.z) prefetch_tmap(&tm_z); }
   }
-  if (warp == 1) { tmem_alloc(smem_u32(&tmem_base_smem), tmem_cols); tmem_relinquish(); }
+  if (CG2) {   // both CTAs are running and their barriers initialised before anyone arrives remotely / allocates as a pair
+    __syncthreads();
+    cluster_sync_all();
+    if (warp == 1) { tmem_alloc_cg2(smem_u32(&tmem_base_smem), tmem_cols); tmem_relinquish_cg2(); }
+  } else if (warp == 1) { tmem_alloc(smem_u32(&tmem_base_smem), tmem_cols); tmem_relinquish(); }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -327,33 +363,40 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
     // ============================ TMA producer ============================
     if (lane == 0) {
       int sw = 0, pw = 0, sb = 0, pb = 0;
+      auto expect = [&](uint32_t bar, uint32_t bytes) {
+        if (CG2) mbar_arrive_expect_tx_cluster(bar, bytes); else mbar_arrive_expect_tx(bar, bytes);
+      };
       if (p.resident) {
         for (int kb = 0; kb < p.KB; ++kb)
           for (int tap = 0; tap < 9; ++tap) {
             if (!((p.live_mask >> tap) & 1)) continue;
             const int slot = kb * p.ntaps + tap - p.tap0;
-            mbar_arrive_expect_tx(smem_u32(&bar_full_b[slot]), wt_bytes);
-            load_weight_tile(p, &tm_b, wt0 + slot * wt_bytes, smem_u32(&bar_full_b[slot]), kb, tap, 0);
+            const uint32_t bar = lead(&bar_full_b[slot]);
+            expect(bar, wt_bytes);
+            load_weight_tile<CG2>(p, &tm_b, wt0 + slot * wt_bytes, bar, kb, tap, 0, crank);
           }
       }
-      for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
+      for (int q = q0; q < p.total_items; q += qstep) {
         int j, tw, th, n;
-        decode_item(p, item, j, tw, th, n);
+        decode_item(p, item_of(q), j, tw, th, n);
         for (int kb = 0; kb < p.KB; ++kb) {
-          mbar_wait(smem_u32(&bar_empty_w[sw]), pw ^ 1);
-          mbar_arrive_expect_tx(smem_u32(&bar_full_w[sw]), (uint32_t)p.win_bytes);
+          wait(smem_u32(&bar_empty_w[sw]), pw ^ 1);
+          const uint32_t bar = lead(&bar_full_w[sw]);
+          expect(bar, (uint32_t)p.win_bytes);
           if (PAIR)   // map dims are (C, W, N, H)
-            tma_load_4d(win0 + sw * PAIR_WIN_STAGE, &tm_x, smem_u32(&bar_full_w[sw]), kb * 64, tw * TILE_W - 1, n, -1);
+            tma_load_4d(win0 + sw * PAIR_WIN_STAGE, &tm_x, bar, kb * 64, tw * TILE_W - 1, n, -1);
+          else if (CG2)
+            tma_load_4d_cg2(win0 + sw * WIN_STAGE, &tm_x, bar, kb * 64, tw * TILE_W - 1, th * TILE_H - 1, n);
           else
-            tma_load_4d(win0 + sw * WIN_STAGE, &tm_x, smem_u32(&bar_full_w[sw]), kb * 64, tw * TILE_W - 1,
-                        th * TILE_H - 1, n);
+            tma_load_4d(win0 + sw * WIN_STAGE, &tm_x, bar, kb * 64, tw * TILE_W - 1, th * TILE_H - 1, n);
           if (++sw == p.nsw) { sw = 0; pw ^= 1; }
           if (!p.resident) {
             for (int tap = 0; tap < 9; ++tap) {
               if (!((p.live_mask >> tap) & 1)) continue;
-              mbar_wait(smem_u32(&bar_empty_b[sb]), pb ^ 1);
-              mbar_arrive_expect_tx(smem_u32(&bar_full_b[sb]), wt_bytes);
-              load_weight_tile(p, &tm_b, wt0 + sb * wt_bytes, smem_u32(&bar_full_b[sb]), kb, tap, j);
+              wait(smem_u32(&bar_empty_b[sb]), pb ^ 1);
+              const uint32_t bb = lead(&bar_full_b[sb]);
+              expect(bb, wt_bytes);
+              load_weight_tile<CG2>(p, &tm_b, wt0 + sb * wt_bytes, bb, kb, tap, j, crank);
               if (++sb == p.nsb) { sb = 0; pb ^= 1; }
             }
           }
@@ -365,8 +408,9 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
     // ============================ MMA issuer ==============================
     // All 32 lanes run the loop so that control flow stays warp-uniform (descriptor words are then
     // computed on the uniform datapath); one elected lane issues the MMAs and the commits.
-    {
-      const uint32_t idesc = idesc_bf16(128, p.BN, 0, p.b_mn);
+    // CTA pairs: only the leader's warp issues (M = 256 over both CTAs); its commits reach the barriers of both.
+    if (!CG2 || crank == 0) {
+      const uint32_t idesc = idesc_bf16(CG2 ? 256 : 128, p.BN, 0, p.b_mn);
       const uint32_t a_hi = (uint32_t)(smem_desc_sw128(0, 0, WIN_PITCH) >> 32);
       const uint32_t b_hi = (uint32_t)(smem_desc_sw128(0, 0, 1024) >> 32);
       // per-K-step (16 channels) advance of the B descriptor and its LBO field:
@@ -375,20 +419,21 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
       const uint32_t b_lbo = p.b_mn ? ((8192u >> 4) << 16) : 0u;
       const uint32_t wt_step = wt_bytes >> 4;
       const bool all_live = p.live_mask == 0x1FF;
+      auto commit = [&](uint64_t* bar) { if (CG2) umma_commit_cg2(smem_u32(bar)); else umma_commit(smem_u32(bar)); };
       int sw = 0, pw = 0, sb = 0, pb = 0, as = 0, pa = 0;
       if (p.resident) {   // the weights are loaded once: wait for every tile up front
         for (int kb = 0; kb < p.KB; ++kb)
           for (int tap = 0; tap < 9; ++tap)
-            if ((p.live_mask >> tap) & 1) mbar_wait(smem_u32(&bar_full_b[kb * p.ntaps + tap - p.tap0]), 0);
+            if ((p.live_mask >> tap) & 1) wait(smem_u32(&bar_full_b[kb * p.ntaps + tap - p.tap0]), 0);
         tc_fence_after();
       }
-      for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
-        mbar_wait(smem_u32(&bar_tmem_empty[as]), pa ^ 1);
+      for (int q = q0; q < p.total_items; q += qstep) {
+        wait(smem_u32(&bar_tmem_empty[as]), pa ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(as * p.BN);
         uint32_t accumulate = 0;
         for (int kb = 0; kb < p.KB; ++kb) {
-          mbar_wait(smem_u32(&bar_full_w[sw]), pw);
+          wait(smem_u32(&bar_full_w[sw]), pw);
           tc_fence_after();
           const uint32_t a_lo0 = (win0 + sw * (PAIR ? PAIR_WIN_STAGE : WIN_STAGE)) >> 4;
           if (!PAIR && p.resident && all_live) {
@@ -401,7 +446,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
                 const uint32_t b_lo = b_lo0 + (uint32_t)tap * wt_step;
 #pragma unroll
                 for (int ks = 0; ks < 4; ++ks)
-                  umma_lohi(d_tmem, a_lo + ks * 2, a_hi, b_lo + ks * b_ks, b_hi, idesc, (tap | ks) ? 1u : accumulate);
+                  umma_lohi<CG2>(d_tmem, a_lo + ks * 2, a_hi, b_lo + ks * b_ks, b_hi, idesc, (tap | ks) ? 1u : accumulate);
               }
             }
             accumulate = 1;
@@ -414,7 +459,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
               if (p.resident) {
                 b_lo = ((wt0 >> 4) | b_lbo) + (uint32_t)(kb * p.ntaps + tap - p.tap0) * wt_step;
               } else {
-                mbar_wait(smem_u32(&bar_full_b[sb]), pb);
+                wait(smem_u32(&bar_full_b[sb]), pb);
                 tc_fence_after();
                 b_lo = ((wt0 >> 4) | b_lbo) + (uint32_t)sb * wt_step;
               }
@@ -422,27 +467,27 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
               if (elect_one()) {
 #pragma unroll
                 for (int ks = 0; ks < 4; ++ks)
-                  umma_lohi(d_tmem, a_lo + ks * 2, a_hi, b_lo + ks * b_ks, b_hi, idesc, ks ? 1u : accumulate);
-                if (!p.resident) umma_commit(smem_u32(&bar_empty_b[sb]));
+                  umma_lohi<CG2>(d_tmem, a_lo + ks * 2, a_hi, b_lo + ks * b_ks, b_hi, idesc, ks ? 1u : accumulate);
+                if (!p.resident) commit(&bar_empty_b[sb]);
               }
               accumulate = 1;
               __syncwarp();
               if (!p.resident) { if (++sb == p.nsb) { sb = 0; pb ^= 1; } }
             }
           }
-          if (elect_one()) umma_commit(smem_u32(&bar_empty_w[sw]));
+          if (elect_one()) commit(&bar_empty_w[sw]);
           __syncwarp();
           if (++sw == p.nsw) { sw = 0; pw ^= 1; }
         }
-        if (elect_one()) umma_commit(smem_u32(&bar_tmem_full[as]));
+        if (elect_one()) commit(&bar_tmem_full[as]);
         __syncwarp();
         if (++as == 2) { as = 0; pa ^= 1; }
       }
     }
   } else {
     // ============================ epilogue ================================
-    const int q = warp % 4;                 // TMEM lane quarter this warp may read
-    const int r = q * 32 + lane;            // GEMM row = pixel of the tile
+    const int wq = warp % 4;                // TMEM lane quarter this warp may read
+    const int r = wq * 32 + lane;           // GEMM row = pixel of the tile
     const int ty = r / TILE_W, tx = r % TILE_W;
     // stacked small images (srows huge otherwise) or pair tiles (rows of two images interleaved)
     const int sb_img = PAIR ? (ty & 1) : ty / p.srows, sb_row = PAIR ? (ty >> 1) : ty % p.srows;
@@ -456,7 +501,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
     ring.tm_y = &tm_y; ring.tm_z = &tm_z; ring.dbg = p.debug;
     int it = -1;
     if (group < egroups)
-    for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
+    for (int q = q0; q < p.total_items; q += qstep) {
+      const int item = item_of(q);
       ++it;
       if (egroups == 2 && (it & 1) != group) continue;        // the other group's tile
       const int as = it & 1, pa = (it >> 1) & 1;              // accumulator stage and its mbarrier phase
@@ -466,15 +512,15 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
       const int img = n + sb_img;
       const bool valid = oh < p.H && ow < p.W && sb_img < p.nb && img < p.N;
       const float* bias = s_bias + j * p.BN;
-      mbar_wait(smem_u32(&bar_tmem_full[as]), pa);
+      wait(smem_u32(&bar_tmem_full[as]), pa);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * p.BN);
-      const uint32_t tmem_empty = smem_u32(&bar_tmem_empty[as]);
+      const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(as * p.BN);
+      const uint32_t tmem_empty = lead(&bar_tmem_empty[as]);     // CTA pairs: the leader's barrier counts both CTAs' warps
       // the accumulator stage goes back to the MMA warp as soon as this warp holds its values in registers
       auto release_tmem = [&]() {
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(tmem_empty);
+        if (lane == 0) { if (CG2) mbar_arrive_cluster(tmem_empty); else mbar_arrive(tmem_empty); }
       };
       // box origin (stacked tiles: th == 0, box = {64, 8, srows, nb}); pair tiles: the store map's dims are (C, W, N, H),
       // so the image index goes where the row coordinate normally is and the row origin (0) last
@@ -580,7 +626,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, tmem_cols); }
+  if (CG2) cluster_sync_all();   // the peer's MMAs read this CTA's shared memory and its epilogue arrives on our barriers
+  if (warp == 1) { tc_fence_after(); if (CG2) tmem_dealloc_cg2(tmem_base, tmem_cols); else tmem_dealloc(tmem_base, tmem_cols); }
 }
 
 // ---------------------------------------------------------------------------
@@ -757,9 +804,11 @@ bool conv_gemm_wanted(const b200_tensor* x, int cin, int cout, int ks);
 int conv_gemm_launch(const b200_tensor* x, const void* wmat, int cin, int cout, int tap_rev, int b_mn, const float* bias,
                      const b200_tensor* y, int act, int accumulate, int ks, void* ws, size_t ws_bytes, cudaStream_t st);
 
+// wmat_k: optional K-major copy [tap][cout][cin] of an MN-major `wmat` (fprop: the b200_filter's ohwi pack); it lets
+// Cout = 64 layers run as CTA pairs, whose 32-column weight halves have no 128-byte-swizzled MN-major form.
 int conv_tc_launch(const b200_tensor* x_in, const void* wmat, int cin, int cout, int tap_rev, int b_mn, const float* bias,
                    const b200_tensor* y_in, int act, int accumulate, cudaStream_t st, const ConvLnArgs* ln, int ks,
-                   void* ws, size_t ws_bytes) {
+                   void* ws, size_t ws_bytes, const void* wmat_k, int allow_pairs) {
   B200_REQUIRE(conv_tc_supported(x_in, cin, cout, y_in, ks), B200_ERR_UNSUPPORTED,
                "conv3x3 tcgen05: unsupported shape cin=%d cout=%d (need bf16, multiples of 64, 16-byte aligned)", cin,
                cout);
@@ -810,7 +859,18 @@ int conv_tc_launch(const b200_tensor* x_in, const void* wmat, int cin, int cout,
     p.tiles_h = 1;
   }
   const int groups = (p.N + p.nb - 1) / p.nb;
-  p.total_items = groups * p.tiles_h * p.tiles_w * p.n_tiles;
+  const int spatial_tiles = groups * p.tiles_h * p.tiles_w;
+  p.total_items = spatial_tiles * p.n_tiles;
+  // CTA pairs (cta_group::2): plain 16x8 tiles (no stacked / paired small images), TMA-store epilogues, 64-multiple
+  // channel counts; MN-major weights need 64-column halves (BN = 128) or the K-major pack
+  static const int allow_cg2 = getenv("B200_CONV_CG2") ? atoi(getenv("B200_CONV_CG2")) : 1;
+  p.cg2 = 0;
+  if (allow_cg2 && allow_pairs && !p.pair && p.nb == 1 && !accumulate && spatial_tiles >= 2 && cin % 64 == 0 && cout % 64 == 0 &&
+      (!b_mn || p.BN == 128 || wmat_k)) {
+    p.cg2 = 1;
+    if (b_mn && p.BN == 64) { wmat = wmat_k; b_mn = 0; tap_rev = 0; }   // [tap][cout][cin]: K-major, natural tap order
+    p.total_items = ((spatial_tiles + 1) / 2) * p.n_tiles;              // work items of a cluster = tile pairs
+  }
   p.tap_rev = tap_rev;
   { const char* dbg = getenv("B200_CONV_DEBUG"); p.debug = dbg ? atoi(dbg) : 0; }
   p.b_mn = b_mn;
@@ -818,7 +878,8 @@ int conv_tc_launch(const b200_tensor* x_in, const void* wmat, int cin, int cout,
   p.ntaps = ks == 1 ? 1 : 9;
   p.tap0 = ks == 1 ? 4 : 0;
   p.live_mask = live_mask;
-  const int wt_bytes = p.BN * 128;
+  const int wt_bytes = (p.cg2 ? p.BN / 2 : p.BN) * 128;
+  p.wt_bytes = wt_bytes;
   // (>= 2 KB: a stacked-image store box may span 18 tile rows, i.e. read 2 KB past its 16-row slot; those rows are
   // clipped by the TMA, the bytes only have to exist)
   int bias_bytes = ((cout * 4 * (ln ? 3 : 1) + 1023) / 1024) * 1024;
@@ -837,7 +898,7 @@ int conv_tc_launch(const b200_tensor* x_in, const void* wmat, int cin, int cout,
       p.nsb = p.ntaps * p.KB;
       p.nsw = (left - all_w) / p.win_stage;
     } else {
-      p.nsb = 4;
+      p.nsb = p.cg2 ? 8 : 4;     // (pairs: half-size tiles, and a slot is free only after the round trip through the peer)
       p.nsw = (left - p.nsb * wt_bytes) / p.win_stage;
     }
     if (p.nsw > 8) p.nsw = 8;
@@ -878,7 +939,7 @@ int conv_tc_launch(const b200_tensor* x_in, const void* wmat, int cin, int cout,
   int rc = p.pair ? make_act_tmap_nh(&tm_x, x, WIN_W, 2, 8 + 2) : make_act_tmap(&tm_x, x, WIN_W, box_h, box_n);
   if (rc) return rc;
   rc = b_mn ? make_mat_tmap(&tm_b, wmat, (long long)p.ntaps * cin, cout, 64)
-            : make_mat_tmap(&tm_b, wmat, (long long)p.ntaps * cout, cin, p.BN);
+            : make_mat_tmap(&tm_b, wmat, (long long)p.ntaps * cout, cin, p.cg2 ? p.BN / 2 : p.BN);
   if (rc) return rc;
   // output boxes: {64 ch, 8, 16, 1}, or {64 ch, 8, H+2, nb} for stacked small images (rows past H are clipped)
   const int obox_h = p.nb > 1 || box_h != WIN_H ? box_h : TILE_H;
@@ -893,6 +954,30 @@ int conv_tc_launch(const b200_tensor* x_in, const void* wmat, int cin, int cout,
     cudaFuncSetAttribute(conv3x3_tc_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT - 1024);
     cudaFuncSetAttribute(conv3x3_tc_kernel<false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT - 1024);
     cudaFuncSetAttribute(conv3x3_tc_kernel<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT - 1024);
+  }
+  if (first_use_on_device(4)) {
+    cudaFuncSetAttribute(conv3x3_tc_kernel<false, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT - 1024);
+    cudaFuncSetAttribute(conv3x3_tc_kernel<false, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT - 1024);
+    cudaFuncSetAttribute(conv3x3_tc_kernel<false, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT - 1024);
+  }
+  if (p.cg2) {
+    // one cluster of two CTAs (the two SMs of a TPC) per tile pair; persistent over 74 clusters
+    int clusters = p.total_items < sm_count() / 2 ? p.total_items : sm_count() / 2;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * clusters);
+    cfg.blockDim = dim3(p.ln && p.BN == 64 ? NTHREADS2 : NTHREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    cudaError_t e;
+    if (p.ln && p.BN == 64) e = cudaLaunchKernelEx(&cfg, conv3x3_tc_kernel<false, 1, true>, tm_x, tm_b, tm_y, tm_z, p);
+    else if (p.ln) e = cudaLaunchKernelEx(&cfg, conv3x3_tc_kernel<false, 2, true>, tm_x, tm_b, tm_y, tm_z, p);
+    else e = cudaLaunchKernelEx(&cfg, conv3x3_tc_kernel<false, 3, true>, tm_x, tm_b, tm_y, tm_z, p);
+    if (e != cudaSuccess) { check_launch("conv3x3_tc_kernel (CTA pairs)"); return fail(B200_ERR_LAUNCH, "conv3x3_tc_kernel (CTA pairs): %s", cudaGetErrorString(e)); }
+    return check_launch("conv3x3_tc_kernel");
   }
   int grid = p.total_items < sm_count() ? p.total_items : sm_count();
   if (p.pair) conv3x3_tc_kernel<true, 0><<<grid, NTHREADS, smem, st>>>(tm_x, tm_b, tm_y, tm_z, p);

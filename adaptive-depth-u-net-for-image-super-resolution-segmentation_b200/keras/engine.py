@@ -184,6 +184,11 @@ class Plan:
         self._build_forward()
         if training:
             self._build_backward()
+        # K-major packs of the filters that have one (see Model._filter): re-derived from the shadow at the start of a step
+        packed = {id(f): f for f in (model._filters.get(op.layer.name) for op in self.ops if op.kind == "conv")
+                  if f is not None and f.ohwi is not None}
+        for f in packed.values():
+            self.pre_steps.append(f.repack)
 
     # ------------------------------------------------------------------ buffers
     def _new(self, v: Val, grad=False):

@@ -262,9 +262,15 @@ class Model:
         if ly.name not in self._filters:
             hwio = self._shadow(ly, "kernel")
             kh, kw, cin, cout = hwio.shape
-            f = ops.ConvFilter.__new__(ops.ConvFilter)   # a view of the shadow buffer: no copy, no repack
+            f = ops.ConvFilter.__new__(ops.ConvFilter)   # a view of the shadow buffer: no copy
             f.hwio, f.kh, f.kw, f.cin, f.cout = hwio, kh, kw, cin, cout
             f.ohwi = None
+            # Cout = 64 layers run as CTA pairs (cta_group::2), whose fprop wants the weights K-major ([kh][kw][cout][cin]):
+            # a small packed copy (36..74 K elements per layer), refreshed by the plan at the start of every step
+            if (hwio.dtype == torch.bfloat16 and (kh, kw) == (3, 3) and cout == 64 and cin % 64 == 0
+                    and os.environ.get("B200_CONV_CG2", "1") == "1"):
+                f.ohwi = torch.empty((kh, kw, cout, cin), dtype=hwio.dtype, device=hwio.device)
+                f.repack()
             self._filters[ly.name] = f
         return self._filters[ly.name]
 

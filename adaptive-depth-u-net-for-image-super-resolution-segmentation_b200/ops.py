@@ -15,7 +15,7 @@ import numpy as np
 import torch
 
 from . import _ffi
-from ._ffi import (ACT_NONE, ACT_RELU, ACT_SIGMOID, ALGO_AUTO, ALGO_SIMT, ALGO_TCGEN05, BF16, CV_INTER_AREA, CV_INTER_CUBIC,
+from ._ffi import (ACT_NONE, ACT_RELU, ACT_SIGMOID, ALGO_AUTO, ALGO_SIMT, ALGO_TCGEN05, ALGO_TCGEN05_1CTA, BF16, CV_INTER_AREA, CV_INTER_CUBIC,
                    F32, U8, Filter, Scratch, Tensor, check)
 
 _DT = {torch.float32: F32, torch.bfloat16: BF16}

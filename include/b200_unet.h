@@ -48,7 +48,10 @@ typedef enum b200_act {
 
 /* Kernel selection for the convolutions. AUTO picks tcgen05 when the shape is
  * supported and falls back to the SIMT kernel for the rest (Cin = 3, fp32). */
-typedef enum b200_algo { B200_ALGO_AUTO = 0, B200_ALGO_SIMT = 1, B200_ALGO_TCGEN05 = 2 } b200_algo;
+typedef enum b200_algo {
+  B200_ALGO_AUTO = 0, B200_ALGO_SIMT = 1, B200_ALGO_TCGEN05 = 2,
+  B200_ALGO_TCGEN05_1CTA = 3   /* tcgen05 without CTA pairs (cta_group::1 only): the reference point of the pair kernels */
+} b200_algo;
 
 typedef enum b200_sr_loss_kind { B200_LOSS_CHARBONNIER = 0, B200_LOSS_L1 = 1, B200_LOSS_MSE = 2 } b200_sr_loss_kind;
 

@@ -143,8 +143,19 @@ TC_SHAPES = [
 ]
 
 
-@pytest.mark.parametrize("shape", TC_SHAPES)
-def test_conv_tc_fprop_dgrad(shape):
+CG2_SHAPES = [  # CTA-pair (cta_group::2) coverage: odd tile counts (a padding tile in the last pair), several N tiles,
+    # resident and streamed weight halves, every (Cin, Cout) class of the model
+    (1, 16, 16, 64, 64), (3, 16, 8, 64, 64), (2, 48, 40, 128, 64), (1, 33, 9, 64, 128), (2, 32, 32, 128, 128),
+    (1, 32, 24, 256, 128), (1, 16, 24, 128, 256), (1, 20, 20, 256, 256), (2, 128, 128, 64, 64),
+]
+
+
+@pytest.mark.parametrize("algo", ["pairs", "1cta"])
+@pytest.mark.parametrize("shape", TC_SHAPES + CG2_SHAPES)
+def test_conv_tc_fprop_dgrad(shape, algo):
+    """tcgen05 implicit GEMM, fprop (+bias+ReLU) and dgrad, against the oracle: the default dispatch (CTA pairs =
+    cta_group::2 wherever the shape allows: plain 16x8 tiles, channel counts multiples of 64) and the single-CTA kernel
+    (B200_ALGO_TCGEN05_1CTA); the two must also agree with each other to bf16 rounding of identical fp32 sums."""
     ops, K = _ops(), _K()
     n, h, w, ci, co = shape
     dt = torch.bfloat16
@@ -152,28 +163,36 @@ def test_conv_tc_fprop_dgrad(shape):
     wt = rand((3, 3, ci, co), 12, dt, 0.1)
     b = rand((co,), 13, torch.float32, 0.5)
     dy = rand((n, h, w, co), 14, dt)
-    filt = ops.ConvFilter(wt)
+    filt = ops.ConvFilter(wt, packed=True)       # + the K-major pack the Cout = 64 pair kernel reads
+    a = ops.ALGO_TCGEN05 if algo == "pairs" else ops.ALGO_TCGEN05_1CTA
     y = torch.full((n, h, w, co), 7.0, dtype=dt, device="cuda")
     cws = conv_ws(ops, x, filt, dy)
-    ops.conv2d_fprop(x, filt, b, y, ops.ACT_RELU, ops.ALGO_TCGEN05, ws=cws)
+    ops.conv2d_fprop(x, filt, b, y, ops.ACT_RELU, a, ws=cws)
     dx = torch.full((n, h, w, ci), 7.0, dtype=dt, device="cuda")
-    ops.conv2d_dgrad(dy, filt, dx, False, ops.ALGO_TCGEN05, ws=cws)
+    ops.conv2d_dgrad(dy, filt, dx, False, a, ws=cws)
     torch.cuda.synchronize()
     xr, wr = f32(x).requires_grad_(), f32(wt).requires_grad_()
     yr = K.conv2d_same(xr, wr, f32(b))
     (yr * f32(dy)).sum().backward()
     e1, e2 = relerr(y, torch.relu(yr)), relerr(dx, xr.grad)
-    print(f"tc conv {shape}: fprop {e1:.3e} dgrad {e2:.3e}")
+    print(f"tc conv {shape} [{algo}]: fprop {e1:.3e} dgrad {e2:.3e}")
     assert e1 < 1e-2 and e2 < 1e-2
+    if algo == "pairs":                          # same K order, same fp32 accumulation: the two kernels agree almost bit for bit
+        y1, dx1 = torch.empty_like(y), torch.empty_like(dx)
+        ops.conv2d_fprop(x, filt, b, y1, ops.ACT_RELU, ops.ALGO_TCGEN05_1CTA, ws=cws)
+        ops.conv2d_dgrad(dy, filt, dx1, False, ops.ALGO_TCGEN05_1CTA, ws=cws)
+        assert relerr(y, y1) < 2e-3 and relerr(dx, dx1) < 2e-3
 
 
 @pytest.mark.parametrize("shape", [(2, 32, 32, 64, 64), (1, 20, 13, 128, 64), (2, 16, 24, 64, 128), (3, 40, 24, 128, 128),
                                    (9, 2, 2, 64, 64), (16, 1, 1, 128, 128), (5, 6, 6, 64, 128),
                                    (2, 8, 8, 64, 256), (2, 9, 9, 3, 64), (5, 8, 8, 64, 64), (3, 8, 11, 128, 128)])
 @pytest.mark.parametrize("relu", [True, False])
-def test_conv_ln_fused(shape, relu):
-    """Conv2D -> LayerNormalization -> ReLU as one call: fused tcgen05 epilogue (Cout 64/128) and the
-    in-library composition for the other shapes; z, y, mean, rstd against the oracle."""
+@pytest.mark.parametrize("packed", [False, True])
+def test_conv_ln_fused(shape, relu, packed):
+    """Conv2D -> LayerNormalization -> ReLU as one call: fused tcgen05 epilogue (Cout 64/128; as CTA pairs when the
+    filter carries its K-major pack or Cout is 128) and the in-library composition for the other shapes; z, y, mean,
+    rstd against the oracle."""
     ops, K = _ops(), _K()
     n, h, w, ci, co = shape
     dt = torch.bfloat16
@@ -181,7 +200,7 @@ def test_conv_ln_fused(shape, relu):
     wt = rand((3, 3, ci, co), 62, dt, 0.1)
     b = rand((co,), 63, torch.float32, 0.5)
     g = (1 + 0.3 * rand((co,), 64)).contiguous(); be = rand((co,), 65, scale=0.3)
-    filt = ops.ConvFilter(wt)
+    filt = ops.ConvFilter(wt, packed=packed)
     z = torch.full((n, h, w, co), 7.0, dtype=dt, device="cuda"); y = torch.full_like(z, 7.0)
     mean = torch.zeros(n * h * w, device="cuda"); rstd = torch.zeros_like(mean)
     ops.conv2d_ln_fprop(x, filt, b, g, be, 1e-3, relu, z, y, mean, rstd, ws=conv_ws(ops, x, filt))
@@ -209,7 +228,7 @@ def test_conv_tc_strided_concat_and_accumulate():
     n, h, w = 2, 24, 16
     x = rand((n, h, w, 128), 21, dt)
     wt = rand((3, 3, 128, 64), 22, dt, 0.1)
-    filt = ops.ConvFilter(wt)
+    filt = ops.ConvFilter(wt, packed=True)
     cat = torch.zeros((n, h, w, 128), dtype=dt, device="cuda")
     ops.conv2d_fprop(x, filt, None, cat[..., 64:], ops.ACT_NONE, ops.ALGO_TCGEN05)
     yr = K.conv2d_same(f32(x), f32(wt))

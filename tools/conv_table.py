@@ -88,21 +88,26 @@ def main():
         dx = torch.empty_like(x)
         dw = torch.empty(3, 3, ci, co, device="cuda")
         bias = torch.zeros(co, device="cuda")
-        f = ops.ConvFilter(w)
+        f = ops.ConvFilter(w, packed=True)
         cws = ops.new_workspace(max(ops.conv2d_workspace(x, f, False), ops.conv2d_workspace(dy, f, True)), "cuda")
         ws = torch.empty(max(ops.conv2d_wgrad_workspace(x, dy, 3, 3), 16) // 4, device="cuda")
         fl = 2.0 * B * s * s * ci * co * 9
         tm = timeit_graph if os.environ.get("TABLE_GRAPH", "1") == "1" else timeit
         t_f = tm(lambda: ops.conv2d_fprop(x, f, bias, y, 1, ws=cws))
         t_d = tm(lambda: ops.conv2d_dgrad(dy, f, dx, ws=cws))
+        t_f1 = tm(lambda: ops.conv2d_fprop(x, f, bias, y, 1, ops.ALGO_TCGEN05_1CTA, ws=cws))
+        t_d1 = tm(lambda: ops.conv2d_dgrad(dy, f, dx, False, ops.ALGO_TCGEN05_1CTA, ws=cws))
         t_w = tm(lambda: ops.conv2d_wgrad(x, dy, 3, 3, dw, ws))
         rows.append({"hw": s, "cin": ci, "cout": co, "gflop": fl / 1e9,
                      "fprop_us": t_f * 1e3, "fprop_tf": fl / t_f / 1e9,
                      "dgrad_us": t_d * 1e3, "dgrad_tf": fl / t_d / 1e9,
-                     "wgrad_us": t_w * 1e3, "wgrad_tf": fl / t_w / 1e9})
+                     "wgrad_us": t_w * 1e3, "wgrad_tf": fl / t_w / 1e9,
+                     "fprop_1cta_us": t_f1 * 1e3, "fprop_1cta_tf": fl / t_f1 / 1e9,
+                     "dgrad_1cta_us": t_d1 * 1e3, "dgrad_1cta_tf": fl / t_d1 / 1e9})
         r = rows[-1]
         print(f"hw {s:4d} {ci:5d}->{co:5d}  fprop {r['fprop_us']:7.1f} us {r['fprop_tf']:7.1f} TF | dgrad {r['dgrad_us']:7.1f} us "
-              f"{r['dgrad_tf']:7.1f} TF | wgrad {r['wgrad_us']:7.1f} us {r['wgrad_tf']:7.1f} TF", flush=True)
+              f"{r['dgrad_tf']:7.1f} TF | wgrad {r['wgrad_us']:7.1f} us {r['wgrad_tf']:7.1f} TF || 1-CTA fprop {r['fprop_1cta_us']:7.1f} us "
+              f"{r['fprop_1cta_tf']:7.1f} TF dgrad {r['dgrad_1cta_us']:7.1f} us {r['dgrad_1cta_tf']:7.1f} TF", flush=True)
     print(json.dumps({"config": name, "mma_rate": mma_rate(), "layers": rows}))
 
 
