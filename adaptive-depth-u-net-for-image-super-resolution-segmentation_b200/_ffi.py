@@ -77,6 +77,9 @@ SIGNATURES = {
     "b200_batchnorm_fwd_train": (_i, [_TP, _vp, _vp, _f, _f, _i, _TP, _vp, _vp, _vp, _vp, _vp, _vp]),
     "b200_batchnorm_fwd_infer": (_i, [_TP, _vp, _vp, _f, _i, _vp, _vp, _TP, _vp]),
     "b200_batchnorm_bwd": (_i, [_TP, _TP, _vp, _vp, _vp, _vp, _i, _TP, _vp, _vp, _vp, _vp, _vp]),
+    "b200_batchnorm_stats": (_i, [_TP, _TP, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp]),
+    "b200_batchnorm_fwd_apply": (_i, [_TP, _vp, _vp, _f, _f, _i, _TP, _vp, _vp, _vp, _vp, _vp, C.c_double, _vp]),
+    "b200_batchnorm_bwd_apply": (_i, [_TP, _TP, _vp, _vp, _vp, _vp, _i, _TP, _vp, C.c_double, _vp]),
     "b200_resize_extent": (_i, [_i, _f]),
     "b200_resample_taps": (_i, [_i, _i, _i]),
     "b200_resample_plan": (_i, [_i, _i, _i, _vp, _vp, _i]),
@@ -93,8 +96,11 @@ SIGNATURES = {
     "b200_bce_dice_loss": (_i, [_TP, _TP, _f, _f, _f, _vp, _TP, _vp, _vp]),
     "b200_softmax_fwd": (_i, [_TP, _TP, _vp]),
     "b200_softmax_ce_loss": (_i, [_TP, _vp, _f, _vp, _TP, _vp, _vp]),
-    "b200_adam_advance": (_i, [_vp, _vp]),
-    "b200_adam_step": (_i, [_vp, _vp, _vp, _vp, _sz, _vp, _vp, _vp, _vp]),
+    "b200_adam_advance": (_i, [_vp, _vp, _vp]),
+    "b200_adam_step": (_i, [_vp, _vp, _vp, _vp, _sz, _vp, _vp, _vp, _vp, _vp]),
+    "b200_loss_scale_apply": (_i, [_vp, _i, _sz, _vp, _vp]),
+    "b200_loss_scale_check": (_i, [_vp, _sz, _vp, _vp]),
+    "b200_loss_scale_update": (_i, [_vp, _f, _vp]),
     "b200_cast": (_i, [_vp, _i, _vp, _i, _sz, _vp]),
     "b200_copy_tensor": (_i, [_TP, _TP, _vp]),
     "b200_scale_inplace": (_i, [_vp, _sz, _f, _vp]),

@@ -68,6 +68,12 @@ int batchnorm_fwd_infer(const b200_tensor*, const float*, const float*, float, i
                         const b200_tensor*, cudaStream_t);
 int batchnorm_bwd(const b200_tensor*, const b200_tensor*, const float*, const float*, const float*, const float*, int,
                   const b200_tensor*, float*, float*, float*, double*, cudaStream_t);
+int batchnorm_stats(const b200_tensor*, const b200_tensor*, const float*, const float*, const float*, const float*, int,
+                    double*, float*, float*, cudaStream_t);
+int batchnorm_fwd_apply(const b200_tensor*, const float*, const float*, float, float, int, const b200_tensor*, float*, float*,
+                        float*, float*, const double*, double, cudaStream_t);
+int batchnorm_bwd_apply(const b200_tensor*, const b200_tensor*, const float*, const float*, const float*, const float*, int,
+                        const b200_tensor*, const double*, double, cudaStream_t);
 int resize_extent(int, float);
 int resample_taps(int, int, int);
 int resample_plan(int, int, int, int32_t*, float*, int);
@@ -85,8 +91,11 @@ int bce_dice_loss(const b200_tensor*, const b200_tensor*, float, float, float, f
                   cudaStream_t);
 int softmax_fwd(const b200_tensor*, const b200_tensor*, cudaStream_t);
 int softmax_ce_loss(const b200_tensor*, const int32_t*, float, float*, const b200_tensor*, float*, cudaStream_t);
-int adam_advance(int32_t*, cudaStream_t);
-int adam_step(float*, const float*, float*, float*, size_t, const float*, const int32_t*, void*, cudaStream_t);
+int adam_advance(int32_t*, const float*, cudaStream_t);
+int adam_step(float*, const float*, float*, float*, size_t, const float*, const int32_t*, void*, const float*, cudaStream_t);
+int loss_scale_apply(void*, int, size_t, const float*, cudaStream_t);
+int loss_scale_check(const float*, size_t, float*, cudaStream_t);
+int loss_scale_update(float*, float, cudaStream_t);
 int cast(const void*, int, void*, int, size_t, cudaStream_t);
 int copy_tensor(const b200_tensor*, const b200_tensor*, cudaStream_t);
 int scale_inplace(float*, size_t, float, cudaStream_t);
@@ -318,6 +327,28 @@ int b200_batchnorm_bwd(const b200_tensor* dy, const b200_tensor* z, const float*
   return batchnorm_bwd(dy, z, sm, sr, g, b, relu, dz, dg, db, dbias, ws, ST(s));
 }
 
+int b200_batchnorm_stats(const b200_tensor* z, const b200_tensor* dy, const float* sm, const float* sr, const float* g,
+                         const float* b, int relu, double* ws, float* dg, float* db, void* s) {
+  REQ_T(z, "z");
+  B200_REQUIRE(ws, B200_ERR_BAD_ARG, "batchnorm_stats: NULL workspace");
+  const bool bwd = dy && dy->data;
+  if (bwd) REQ_T(dy, "dy");
+  return batchnorm_stats(z, bwd ? dy : nullptr, sm, sr, g, b, relu, ws, dg, db, ST(s));
+}
+int b200_batchnorm_fwd_apply(const b200_tensor* z, const float* g, const float* b, float eps, float mom, int relu,
+                             const b200_tensor* y, float* sm, float* sr, float* mm, float* mv, const double* ws,
+                             double count, void* s) {
+  REQ_T(z, "z"); REQ_T(y, "y");
+  B200_REQUIRE(g && b && sm && sr && ws, B200_ERR_BAD_ARG, "batchnorm_fwd_apply: NULL parameter");
+  return batchnorm_fwd_apply(z, g, b, eps, mom, relu, y, sm, sr, mm, mv, ws, count, ST(s));
+}
+int b200_batchnorm_bwd_apply(const b200_tensor* dy, const b200_tensor* z, const float* sm, const float* sr, const float* g,
+                             const float* b, int relu, const b200_tensor* dz, const double* ws, double count, void* s) {
+  REQ_T(dy, "dy"); REQ_T(z, "z"); REQ_T(dz, "dz");
+  B200_REQUIRE(g && b && sm && sr && ws, B200_ERR_BAD_ARG, "batchnorm_bwd_apply: NULL parameter");
+  return batchnorm_bwd_apply(dy, z, sm, sr, g, b, relu, dz, ws, count, ST(s));
+}
+
 int b200_resize_extent(int extent, float scale) { return resize_extent(extent, scale); }
 int b200_resample_taps(int in_size, int out_size, int aa) { return resample_taps(in_size, out_size, aa); }
 int b200_resample_plan(int in_size, int out_size, int aa, int32_t* starts, float* weights, int taps) {
@@ -394,15 +425,29 @@ int b200_softmax_ce_loss(const b200_tensor* prob, const int32_t* labels, float g
   return softmax_ce_loss(prob, labels, gs, out, dl, ws, ST(s));
 }
 
-int b200_adam_advance(int32_t* step, void* s) {
+int b200_adam_advance(int32_t* step, const float* loss_scale, void* s) {
   B200_REQUIRE(step, B200_ERR_BAD_ARG, "adam_advance: NULL step");
-  return adam_advance(step, ST(s));
+  return adam_advance(step, loss_scale, ST(s));
 }
 int b200_adam_step(float* p, const float* g, float* m, float* v, size_t count, const float* hyper, const int32_t* step,
-                   void* shadow, void* s) {
+                   void* shadow, const float* loss_scale, void* s) {
   B200_REQUIRE(p && g && m && v && hyper && step, B200_ERR_BAD_ARG, "adam_step: NULL argument");
   if (count == 0) return B200_OK;
-  return adam_step(p, g, m, v, count, hyper, step, shadow, ST(s));
+  return adam_step(p, g, m, v, count, hyper, step, shadow, loss_scale, ST(s));
+}
+int b200_loss_scale_apply(void* data, int dtype, size_t count, const float* loss_scale, void* s) {
+  B200_REQUIRE(data && loss_scale && (dtype == B200_F32 || dtype == B200_BF16), B200_ERR_BAD_ARG, "loss_scale_apply: bad argument");
+  if (count == 0) return B200_OK;
+  return loss_scale_apply(data, dtype, count, loss_scale, ST(s));
+}
+int b200_loss_scale_check(const float* g, size_t count, float* loss_scale, void* s) {
+  B200_REQUIRE(g && loss_scale && (uintptr_t)g % 16 == 0, B200_ERR_BAD_ARG, "loss_scale_check: bad argument");
+  if (count == 0) return B200_OK;
+  return loss_scale_check(g, count, loss_scale, ST(s));
+}
+int b200_loss_scale_update(float* loss_scale, float growth_interval, void* s) {
+  B200_REQUIRE(loss_scale && growth_interval >= 1.f, B200_ERR_BAD_ARG, "loss_scale_update: bad argument");
+  return loss_scale_update(loss_scale, growth_interval, ST(s));
 }
 
 int b200_cast(const void* src, int sdt, void* dst, int ddt, size_t count, void* s) {

@@ -652,6 +652,61 @@ int batchnorm_fwd_train(const b200_tensor* z, const float* gamma, const float* b
   return check_launch("batchnorm_fwd_train");
 }
 
+// ---- BatchNorm in phases (synchronised BatchNorm under data parallelism) -------------------------------------------
+// stats -> [caller all-reduces the 2*C doubles over the ranks] -> apply with the GLOBAL pixel count.  The backward
+// statistics kernel also adds the LOCAL sums to dgamma / dbeta (they join the ordinary gradient exchange).
+int batchnorm_stats(const b200_tensor* z, const b200_tensor* dy, const float* save_mean, const float* save_rstd,
+                    const float* gamma, const float* beta, int relu, double* stats_ws, float* dgamma, float* dbeta,
+                    cudaStream_t st) {
+  const int C = z->c;
+  const long long npix = (long long)z->n * z->h * z->w;
+  cudaMemsetAsync(stats_ws, 0, sizeof(double) * 2 * C, st);
+  TView zv = view_of(z);
+  if (!dy) {
+    B200_DISPATCH_DTYPE(z->dtype, T, {
+      bn_stats_kernel<T, 0><<<grid_for(npix, 64), NT, sizeof(float) * 2 * C, st>>>(zv, zv, nullptr, nullptr, nullptr, nullptr, 0, stats_ws, npix);
+    });
+    return check_launch("bn_stats_kernel");
+  }
+  B200_REQUIRE(same_shape(z, dy) && z->dtype == dy->dtype && save_mean && save_rstd && gamma && beta, B200_ERR_BAD_ARG,
+               "batchnorm_stats (backward): dy / statistics missing or mismatched");
+  TView dyv = view_of(dy);
+  B200_DISPATCH_DTYPE(z->dtype, T, {
+    bn_stats_kernel<T, 1><<<grid_for(npix, 64), NT, sizeof(float) * 2 * C, st>>>(zv, dyv, save_mean, save_rstd, gamma, beta, relu, stats_ws, npix);
+  });
+  bn_bwd_params_kernel<<<(C + 127) / 128, 128, 0, st>>>(stats_ws, C, dgamma, dbeta);
+  count_launches(1);
+  return check_launch("bn_stats_kernel");
+}
+
+int batchnorm_fwd_apply(const b200_tensor* z, const float* gamma, const float* beta, float eps, float momentum, int relu,
+                        const b200_tensor* y, float* save_mean, float* save_rstd, float* moving_mean, float* moving_var,
+                        const double* stats_ws, double count, cudaStream_t st) {
+  B200_REQUIRE(same_shape(z, y) && z->dtype == y->dtype && count > 0, B200_ERR_BAD_ARG, "batchnorm_fwd_apply: bad argument");
+  const int C = z->c;
+  const long long npix = (long long)z->n * z->h * z->w;
+  TView zv = view_of(z), yv = view_of(y);
+  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(stats_ws, C, count, eps, momentum, save_mean, save_rstd, moving_mean, moving_var);
+  B200_DISPATCH_DTYPE(z->dtype, T, {
+    bn_apply_kernel<T><<<grid_for(npix * C, NT), NT, 0, st>>>(zv, save_mean, save_rstd, gamma, beta, relu, yv, npix * C, nullptr, nullptr, eps);
+  });
+  count_launches(1);
+  return check_launch("batchnorm_fwd_apply");
+}
+
+int batchnorm_bwd_apply(const b200_tensor* dy, const b200_tensor* z, const float* save_mean, const float* save_rstd,
+                        const float* gamma, const float* beta, int relu, const b200_tensor* dz, const double* stats_ws,
+                        double count, cudaStream_t st) {
+  B200_REQUIRE(same_shape(z, dy) && same_shape(z, dz) && z->dtype == dy->dtype && z->dtype == dz->dtype && count > 0,
+               B200_ERR_BAD_ARG, "batchnorm_bwd_apply: bad argument");
+  const long long npix = (long long)z->n * z->h * z->w;
+  TView zv = view_of(z), dyv = view_of(dy), dzv = view_of(dz);
+  B200_DISPATCH_DTYPE(z->dtype, T, {
+    bn_bwd_apply_kernel<T><<<grid_for(npix * z->c, NT), NT, 0, st>>>(dyv, zv, save_mean, save_rstd, gamma, beta, relu, dzv, stats_ws, count, npix * z->c);
+  });
+  return check_launch("batchnorm_bwd_apply");
+}
+
 int batchnorm_fwd_infer(const b200_tensor* z, const float* gamma, const float* beta, float eps, int relu,
                         const float* moving_mean, const float* moving_var, const b200_tensor* y, cudaStream_t st) {
   B200_REQUIRE(same_shape(z, y) && z->dtype == y->dtype, B200_ERR_BAD_ARG, "batchnorm_infer: shape/dtype mismatch");

@@ -18,15 +18,55 @@ inline int grid_for(long long items, int per_thread = 1) {
   return (int)b;
 }
 
-__global__ void adam_advance_kernel(int* step) {
-  if (threadIdx.x == 0 && blockIdx.x == 0) *step += 1;
+// Dynamic loss scaling (keras LossScaleOptimizer, the optimizer wrapper of the reference's mixed_float16 policy,
+// Super_resolution/code/train_adaptive_unet.py:471-477): device-resident state ls = {scale, good steps, found_inf, -}.
+// The loss gradient is multiplied by `scale`; a step whose gradients hold an inf / nan is skipped (no moment, weight or
+// step-counter update) and halves the scale; `growth` finite steps in a row double it.
+__global__ void adam_advance_kernel(int* step, const float* __restrict__ ls) {
+  if (threadIdx.x == 0 && blockIdx.x == 0 && !(ls && ls[2] != 0.f)) *step += 1;
+}
+
+__global__ void __launch_bounds__(NT) scale_by_device_kernel(float* p, size_t count, const float* __restrict__ ls) {
+  const float s = ls[0];
+  for (size_t i = (size_t)blockIdx.x * NT + threadIdx.x; i < count; i += (size_t)gridDim.x * NT) p[i] *= s;
+}
+__global__ void __launch_bounds__(NT) scale_by_device_bf16_kernel(__nv_bfloat16* p, size_t count, const float* __restrict__ ls) {
+  const float s = ls[0];
+  for (size_t i = (size_t)blockIdx.x * NT + threadIdx.x; i < count; i += (size_t)gridDim.x * NT)
+    p[i] = __float2bfloat16_rn(__bfloat162float(p[i]) * s);
+}
+
+__global__ void __launch_bounds__(NT) finite_check_kernel(const float* __restrict__ g, size_t count, float* __restrict__ ls) {
+  bool bad = false;
+  const size_t n4 = count / 4;
+  for (size_t i = (size_t)blockIdx.x * NT + threadIdx.x; i < n4; i += (size_t)gridDim.x * NT) {
+    const float4 v = reinterpret_cast<const float4*>(g)[i];
+    bad |= !(isfinite(v.x) && isfinite(v.y) && isfinite(v.z) && isfinite(v.w));
+  }
+  for (size_t i = n4 * 4 + (size_t)blockIdx.x * NT + threadIdx.x; i < count; i += (size_t)gridDim.x * NT) bad |= !isfinite(g[i]);
+  if (__syncthreads_or(bad) && threadIdx.x == 0) ls[2] = 1.f;      // every writer stores the same value
+}
+
+__global__ void loss_scale_update_kernel(float* ls, float growth) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  if (ls[2] != 0.f) {
+    ls[0] = fmaxf(ls[0] * 0.5f, 1.f);
+    ls[1] = 0.f;
+    ls[2] = 0.f;
+    ls[3] += 1.f;                                                   // skipped steps so far
+  } else {
+    ls[1] += 1.f;
+    if (ls[1] >= growth) { ls[0] *= 2.f; ls[1] = 0.f; }
+  }
 }
 
 // alpha = lr * sqrt(1 - b2^t) / (1 - b1^t); m += (g-m)(1-b1); v += (g^2-v)(1-b2); p -= alpha*m/(sqrt(v)+eps)
 __global__ void __launch_bounds__(NT)
 adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
             size_t count, const float* __restrict__ hyper, const int* __restrict__ step,
-            __nv_bfloat16* __restrict__ shadow) {
+            __nv_bfloat16* __restrict__ shadow, const float* __restrict__ ls) {
+  if (ls && ls[2] != 0.f) return;                 // loss scaling: a non-finite gradient skips the whole step
+  const float inv_scale = ls ? 1.f / ls[0] : 1.f;
   const float lr = hyper[0], b1 = hyper[1], b2 = hyper[2], eps = hyper[3];
   const float omb1 = hyper[4], omb2 = hyper[5];  // (1-beta) evaluated in double by the host, as keras does
   const float t = (float)(*step);
@@ -34,7 +74,8 @@ adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restric
   const size_t n4 = count / 4;
   for (size_t i = (size_t)blockIdx.x * NT + threadIdx.x; i < n4; i += (size_t)gridDim.x * NT) {
     float4 pv = reinterpret_cast<float4*>(p)[i];
-    const float4 gv = reinterpret_cast<const float4*>(g)[i];
+    float4 gv = reinterpret_cast<const float4*>(g)[i];
+    gv.x *= inv_scale; gv.y *= inv_scale; gv.z *= inv_scale; gv.w *= inv_scale;
     float4 mv = reinterpret_cast<float4*>(m)[i];
     float4 vv = reinterpret_cast<float4*>(v)[i];
     float* pp = &pv.x; const float* gg = &gv.x; float* mm = &mv.x; float* vp = &vv.x;
@@ -57,8 +98,9 @@ adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restric
   }
   // tail
   for (size_t i = n4 * 4 + (size_t)blockIdx.x * NT + threadIdx.x; i < count; i += (size_t)gridDim.x * NT) {
-    float mm = m[i] + (g[i] - m[i]) * omb1;
-    float vv = v[i] + (g[i] * g[i] - v[i]) * omb2;
+    const float gi = g[i] * inv_scale;
+    float mm = m[i] + (gi - m[i]) * omb1;
+    float vv = v[i] + (gi * gi - v[i]) * omb2;
     float pp = p[i] - alpha * mm / (sqrtf(vv) + eps);
     m[i] = mm; v[i] = vv; p[i] = pp;
     if (shadow) shadow[i] = __float2bfloat16_rn(pp);
@@ -159,18 +201,32 @@ convT2_wgrad_kernel(TView x, TView dy, float* __restrict__ dk) {
 
 }  // namespace
 
-int adam_advance(int32_t* step, cudaStream_t st) {
-  adam_advance_kernel<<<1, 32, 0, st>>>(step);
+int adam_advance(int32_t* step, const float* ls, cudaStream_t st) {
+  adam_advance_kernel<<<1, 32, 0, st>>>(step, ls);
   return check_launch("adam_advance_kernel");
 }
 
+int loss_scale_apply(void* data, int dtype, size_t count, const float* ls, cudaStream_t st) {
+  if (dtype == B200_BF16) scale_by_device_bf16_kernel<<<grid_for((long long)count), NT, 0, st>>>(reinterpret_cast<__nv_bfloat16*>(data), count, ls);
+  else scale_by_device_kernel<<<grid_for((long long)count), NT, 0, st>>>(reinterpret_cast<float*>(data), count, ls);
+  return check_launch("scale_by_device_kernel");
+}
+int loss_scale_check(const float* g, size_t count, float* ls, cudaStream_t st) {
+  finite_check_kernel<<<grid_for((long long)count, 8), NT, 0, st>>>(g, count, ls);
+  return check_launch("finite_check_kernel");
+}
+int loss_scale_update(float* ls, float growth, cudaStream_t st) {
+  loss_scale_update_kernel<<<1, 32, 0, st>>>(ls, growth);
+  return check_launch("loss_scale_update_kernel");
+}
+
 int adam_step(float* p, const float* g, float* m, float* v, size_t count, const float* hyper, const int32_t* step,
-              void* shadow, cudaStream_t st) {
+              void* shadow, const float* ls, cudaStream_t st) {
   B200_REQUIRE(((uintptr_t)p % 16 == 0) && ((uintptr_t)g % 16 == 0) && ((uintptr_t)m % 16 == 0) &&
                    ((uintptr_t)v % 16 == 0) && ((uintptr_t)shadow % 8 == 0),
                B200_ERR_BAD_ARG, "adam_step: buffers must be 16-byte aligned");
   adam_kernel<<<grid_for((long long)count, 4), NT, 0, st>>>(p, g, m, v, count, hyper, step,
-                                                            reinterpret_cast<__nv_bfloat16*>(shadow));
+                                                            reinterpret_cast<__nv_bfloat16*>(shadow), ls);
   return check_launch("adam_kernel");
 }
 

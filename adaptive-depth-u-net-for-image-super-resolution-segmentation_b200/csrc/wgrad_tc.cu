@@ -275,8 +275,10 @@ inline void plan(const b200_tensor* x_in, const b200_tensor* dy_in, WgradParams&
   p.total_tiles = groups * p.tiles_h * p.tiles_w;
   p.cblocks = (p.Cin + 63) / 64;
   p.oblocks = (p.Cout + 63) / 64;
+  // one wave: splits * (ci blocks * co blocks) CTAs must not exceed the SM count -- rounding UP here put 152 CTAs on
+  // 148 SMs for 8 (ci, co) block pairs (256 -> 128 at 32x32), i.e. a second wave of 4 CTAs and twice the time
   const int pairs = p.cblocks * p.oblocks;
-  int splits = (sm_count() + pairs - 1) / pairs;
+  int splits = sm_count() / pairs;
   if (splits > p.total_tiles) splits = p.total_tiles;
   if (splits < 1) splits = 1;
   p.splits = splits;

@@ -180,6 +180,9 @@ class Plan:
         self.bwd_steps: List[Callable[[], None]] = []   # backward launches (training only)
         self.pre_steps: List[Callable[[], None]] = []   # weight repacks
         self._resample_cache = {}
+        # synchronised BatchNorm: training plans of a distributed model that has BatchNormalization layers
+        self.sync_bn = bool(training and model._dist is not None and model._world() > 1 and model.sync_batchnorm
+                            and any(op.kind == "bn" for op in self.ops))
         self._alloc()
         self._build_forward()
         if training:
@@ -325,7 +328,17 @@ class Plan:
                 op.save_mean = self._scratch(c, torch.float32)
                 op.save_rstd = self._scratch(c, torch.float32)
                 op.stats_ws = self._scratch(2 * c, torch.float64)
-                if self.training:
+                if self.training and self.sync_bn:
+                    # synchronised BatchNorm: per-channel sums over the GLOBAL batch (all-reduced between the phases;
+                    # a host-issued collective, so plans with it are not captured in a CUDA graph)
+                    def fwd_sync(z=op.inputs[0], y=op.output, o=op, g=g, b=b, mm=mm, mv=mv):
+                        dist, group = m._dist
+                        ops.batchnorm_stats(z.buf, o.stats_ws)
+                        dist.all_reduce(o.stats_ws, group=group)
+                        ops.batchnorm_fwd_apply(z.buf, g, b, o.layer.epsilon, o.layer.momentum, o.relu, y.buf, o.save_mean,
+                                                o.save_rstd, mm, mv, o.stats_ws, npix(y) * m._world())
+                    S.append(fwd_sync)
+                elif self.training:
                     S.append(lambda z=op.inputs[0], y=op.output, o=op, g=g, b=b, mm=mm, mv=mv:
                              ops.batchnorm_fwd_train(z.buf, g, b, o.layer.epsilon, o.layer.momentum, o.relu, y.buf,
                                                      o.save_mean, o.save_rstd, mm, mv, o.stats_ws))
@@ -461,10 +474,20 @@ class Plan:
                 assert not z.grad_written, "BatchNormalization input must have a single consumer"
                 z.mark_grad_written()
                 writes(ly, "gamma", "beta")
-                B.append(lambda z=z, o=out, op=op, g=m._param(ly, "gamma"), b=m._param(ly, "beta"),
-                         dg=m._grad(ly, "gamma"), db=m._grad(ly, "beta"):
-                         ops.batchnorm_bwd(o.grad, z.buf, op.save_mean, op.save_rstd, g, b, op.relu, z.grad, dg, db,
-                                           op.stats_ws))
+                if self.sync_bn:
+                    def bwd_sync(z=z, o=out, op=op, g=m._param(ly, "gamma"), b=m._param(ly, "beta"),
+                                 dg=m._grad(ly, "gamma"), db=m._grad(ly, "beta")):
+                        dist, group = m._dist
+                        ops.batchnorm_stats(z.buf, op.stats_ws, o.grad, op.save_mean, op.save_rstd, g, b, op.relu, dg, db)
+                        dist.all_reduce(op.stats_ws, group=group)
+                        ops.batchnorm_bwd_apply(o.grad, z.buf, op.save_mean, op.save_rstd, g, b, op.relu, z.grad,
+                                                op.stats_ws, self.batch * z.h * z.w * m._world())
+                    B.append(bwd_sync)
+                else:
+                    B.append(lambda z=z, o=out, op=op, g=m._param(ly, "gamma"), b=m._param(ly, "beta"),
+                             dg=m._grad(ly, "gamma"), db=m._grad(ly, "beta"):
+                             ops.batchnorm_bwd(o.grad, z.buf, op.save_mean, op.save_rstd, g, b, op.relu, z.grad, dg, db,
+                                               op.stats_ws))
             elif k == "resize":
                 x = op.inputs[0]
                 if x.needs_grad:

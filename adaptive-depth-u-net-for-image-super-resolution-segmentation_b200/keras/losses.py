@@ -46,6 +46,10 @@ class _PlanLoss:
             y = y.to(tgt.dtype)
         tgt.copy_(y.reshape(tgt.shape), non_blocking=True)
 
+    def grad_tensor(self, plan, st):
+        """The contiguous tensor `launch` writes d(loss)/d(prediction) into."""
+        return plan.output_val.grad
+
     def logs(self, st):
         out = st["out"]
         d = {"loss": out[0]}
@@ -144,6 +148,9 @@ class CategoricalCrossentropy(_PlanLoss):
         if y.dim() == 4:
             y = y.argmax(dim=-1)
         st["target"].copy_(y.to(torch.int32).reshape(st["target"].shape), non_blocking=True)
+
+    def grad_tensor(self, plan, st):
+        return st["logits"].grad
 
     def launch(self, plan, st, grad_scale=1.0, with_grad=True):
         ops.softmax_ce_loss(plan.output_val.buf, st["target"], grad_scale, st["out"],

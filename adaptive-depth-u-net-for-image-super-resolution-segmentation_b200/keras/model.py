@@ -31,9 +31,10 @@ _SEED = {"value": 1234}
 
 
 def set_global_policy(name: str):
-    """keras.mixed_precision.set_global_policy.  "mixed_bfloat16" computes/stores activations in
-    bf16 with fp32 master weights; "mixed_float16" (the reference's policy,
-    train_adaptive_unet.py:471-477) is mapped to the same bf16 path -- the B200 kernels are bf16."""
+    """keras.mixed_precision.set_global_policy.  "mixed_bfloat16" computes/stores activations in bf16 with fp32 master
+    weights.  "mixed_float16" (the reference's policy, train_adaptive_unet.py:471-477) runs the same bf16 kernels -- the
+    tcgen05 path here is bf16 -- and, as keras does for that policy, wraps the optimizer in dynamic loss scaling
+    (LossScaleOptimizer semantics: scale 2**15, x2 after 2000 finite steps, /2 and step skipped on inf / nan)."""
     if name not in ("float32", "mixed_bfloat16", "mixed_float16"):
         raise ValueError(f"unknown policy {name!r}")
     _POLICY["name"] = name
@@ -133,6 +134,10 @@ class Model:
         self._side_stream = None
         # EXPERIMENTAL (off): Adam of a layer's kernel range on the second stream right behind its wgrad (N=1 only)
         self.overlap_adam = os.environ.get("B200_OVERLAP_ADAM", "0") == "1"
+        # data parallel: BatchNormalization statistics over the GLOBAL batch (per-channel sums all-reduced inside the
+        # forward and the backward pass), so N ranks x B/N samples train exactly like one rank x B samples
+        # (B200_SYNC_BN=0 keeps per-replica statistics)
+        self.sync_batchnorm = os.environ.get("B200_SYNC_BN", "1") == "1"
         self.input_shape = self.inputs[0].shape
         self.output_shape = self.outputs[0].shape
 
@@ -527,6 +532,8 @@ class Model:
         if isinstance(self.optimizer, str):
             self.optimizer = {"adam": O.Adam}[self.optimizer.lower()]()
         self.loss = LS.resolve_loss(loss)
+        if _POLICY["name"] == "mixed_float16" and hasattr(self.optimizer, "dynamic_loss_scale"):
+            self.optimizer.dynamic_loss_scale = True
         self.metrics_fns = list(metrics or [])
         self._plans = {k: v for k, v in self._plans.items() if not k[1]}
         self._graphs = {}
@@ -590,6 +597,9 @@ class Model:
         plan.run_pre()
         plan.run_forward()
         self.loss.launch(plan, st, grad_scale=1.0 / self._world())
+        ls = self.optimizer.loss_scale_state() if hasattr(self.optimizer, "loss_scale_state") else None
+        if ls is not None:      # dynamic loss scaling: d(loss)/d(pred) *= scale (device-resident, so the graph stays valid)
+            ops.loss_scale_apply(self.loss.grad_tensor(plan, st), ls)
 
     def _segments(self, plan: Plan):
         """Backward cut at the points where a gradient bucket becomes complete:
@@ -620,7 +630,8 @@ class Model:
         if self._side_stream is None:
             self._side_stream = torch.cuda.Stream()
         main, side, forked = torch.cuda.current_stream(), self._side_stream, False
-        early = self._early_adam = [] if (self.overlap_adam and self._dist is None) else None
+        scaled = getattr(self.optimizer, "dynamic_loss_scale", False)     # needs the finite check over the COMPLETE gradient
+        early = self._early_adam = [] if (self.overlap_adam and self._dist is None and not scaled) else None
         pending = []          # kernel ranges whose wgrad is on the side stream but whose dgrad may still read the shadow
         if early is not None:
             self.optimizer.advance()
@@ -653,9 +664,21 @@ class Model:
             works += self._reduce_async(buckets)
         for w in works:
             w.wait()
+        self._check_finite()
         self._apply_optimizer(plan)
         self._gather_updated(plan)
         self._last_train_plan = plan
+
+    def _check_finite(self):
+        """Dynamic loss scaling: raise the optimizer's found_inf flag if the (exchanged) gradient holds an inf / nan; under
+        data parallelism the flag is max-reduced so that every rank skips -- or takes -- the step together."""
+        ls = self.optimizer.loss_scale_state() if hasattr(self.optimizer, "loss_scale_state") else None
+        if ls is None:
+            return
+        ops.loss_scale_check(self.G, ls)
+        if self._dist is not None and self._world() > 1:
+            dist, group = self._dist
+            dist.all_reduce(ls[2:3], op=dist.ReduceOp.MAX, group=group)
 
     def _reduce_async(self, buckets):
         if not buckets:
@@ -735,7 +758,7 @@ class Model:
         st = self.loss.make_state(plan)
         self.optimizer.ensure_state(self)
         entry = {"plan": plan, "state": st, "graph": None, "segments": None}
-        if self.use_cuda_graph:
+        if self.use_cuda_graph and not plan.sync_bn:      # (host-issued collectives inside the passes: eager launches)
             # warm-up on a side stream (sets kernel attributes, initialises NCCL), then capture
             snap = (self.P.clone(), self.optimizer.snapshot(), self.NT.clone())
             s = torch.cuda.Stream()
@@ -781,6 +804,7 @@ class Model:
                 works += self._reduce_async(buckets)
             for w in works:
                 w.wait()
+            self._check_finite()
             entry["adam_graph"].replay()
             self._gather_updated(entry["plan"])
             self._last_train_plan = entry["plan"]

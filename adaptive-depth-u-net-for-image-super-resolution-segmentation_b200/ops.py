@@ -194,6 +194,27 @@ def batchnorm_bwd(dy, z, save_mean, save_rstd, gamma, beta, relu, dz, dgamma, db
     return dz
 
 
+def batchnorm_stats(z, stats_ws, dy=None, save_mean=None, save_rstd=None, gamma=None, beta=None, relu=False, dgamma=None,
+                    dbeta=None):
+    """Phase 1 of synchronised BatchNorm: per-channel (sum z, sum z^2) -- or, with dy, (sum g, sum g*xhat) plus the local
+    dgamma / dbeta -- into stats_ws [2C] float64; the caller all-reduces stats_ws before the apply phase."""
+    check(lib().b200_batchnorm_stats(tdesc(z), _opt_desc(dy), _ptr(save_mean), _ptr(save_rstd), _ptr(gamma), _ptr(beta),
+                                     int(relu), _ptr(stats_ws), _ptr(dgamma), _ptr(dbeta), _stream()), "batchnorm_stats")
+
+
+def batchnorm_fwd_apply(z, gamma, beta, eps, momentum, relu, y, save_mean, save_rstd, moving_mean, moving_var, stats_ws, count):
+    check(lib().b200_batchnorm_fwd_apply(tdesc(z), _ptr(gamma), _ptr(beta), eps, momentum, int(relu), tdesc(y),
+                                         _ptr(save_mean), _ptr(save_rstd), _ptr(moving_mean), _ptr(moving_var),
+                                         _ptr(stats_ws), float(count), _stream()), "batchnorm_fwd_apply")
+    return y
+
+
+def batchnorm_bwd_apply(dy, z, save_mean, save_rstd, gamma, beta, relu, dz, stats_ws, count):
+    check(lib().b200_batchnorm_bwd_apply(tdesc(dy), tdesc(z), _ptr(save_mean), _ptr(save_rstd), _ptr(gamma), _ptr(beta),
+                                         int(relu), tdesc(dz), _ptr(stats_ws), float(count), _stream()), "batchnorm_bwd_apply")
+    return dz
+
+
 # ---- resampling --------------------------------------------------------------------------
 def resize_extent(extent: int, scale: float) -> int:
     return int(lib().b200_resize_extent(int(extent), float(scale)))
@@ -306,13 +327,26 @@ def softmax_ce_loss(prob, labels, grad_scale, out, dlogits, ws):
 
 
 # ---- optimiser / utilities ------------------------------------------------------------------------
-def adam_advance(step):
-    check(lib().b200_adam_advance(_ptr(step), _stream()), "adam_advance")
+def adam_advance(step, loss_scale=None):
+    check(lib().b200_adam_advance(_ptr(step), _ptr(loss_scale), _stream()), "adam_advance")
 
 
-def adam_step(p, g, m, v, hyper, step, shadow=None):
+def adam_step(p, g, m, v, hyper, step, shadow=None, loss_scale=None):
     check(lib().b200_adam_step(_ptr(p), _ptr(g), _ptr(m), _ptr(v), p.numel(), _ptr(hyper), _ptr(step), _ptr(shadow),
-                               _stream()), "adam_step")
+                               _ptr(loss_scale), _stream()), "adam_step")
+
+
+def loss_scale_apply(t, loss_scale):
+    """t *= scale (device-resident loss scale; t: the contiguous loss-gradient tensor)."""
+    check(lib().b200_loss_scale_apply(_ptr(t), _DT[t.dtype], t.numel(), _ptr(loss_scale), _stream()), "loss_scale_apply")
+
+
+def loss_scale_check(g, loss_scale):
+    check(lib().b200_loss_scale_check(_ptr(g), g.numel(), _ptr(loss_scale), _stream()), "loss_scale_check")
+
+
+def loss_scale_update(loss_scale, growth_interval=2000):
+    check(lib().b200_loss_scale_update(_ptr(loss_scale), float(growth_interval), _stream()), "loss_scale_update")
 
 
 def cast(src, dst):

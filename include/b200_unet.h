@@ -172,6 +172,22 @@ int b200_batchnorm_bwd(const b200_tensor* dy, const b200_tensor* z, const float*
                        const float* save_rstd, const float* gamma, const float* beta, int relu,
                        const b200_tensor* dz, float* dgamma, float* dbeta, float* dbias, double* stats_ws,
                        void* stream);
+/* Synchronised BatchNorm under data parallelism (BatchNorm models are not sample-independent) -- the three
+ * calls above in phases, so the caller can sum the statistics over the ranks in between:
+ *   forward : b200_batchnorm_stats(z, NULL, ...)  -> all-reduce stats_ws (2*C doubles: sum z, sum z^2)
+ *             -> b200_batchnorm_fwd_apply(..., stats_ws, GLOBAL pixel count)
+ *   backward: b200_batchnorm_stats(z, dy, ...)    (also adds the LOCAL sums to dgamma / dbeta, which then join the
+ *             ordinary gradient exchange) -> all-reduce stats_ws (sum g, sum g*xhat) -> b200_batchnorm_bwd_apply(...,
+ *             GLOBAL pixel count).  With one rank the phases equal b200_batchnorm_fwd_train / b200_batchnorm_bwd. */
+int b200_batchnorm_stats(const b200_tensor* z, const b200_tensor* dy, const float* save_mean, const float* save_rstd,
+                         const float* gamma, const float* beta, int relu, double* stats_ws, float* dgamma, float* dbeta,
+                         void* stream);
+int b200_batchnorm_fwd_apply(const b200_tensor* z, const float* gamma, const float* beta, float eps, float momentum,
+                             int relu, const b200_tensor* y, float* save_mean, float* save_rstd, float* moving_mean,
+                             float* moving_var, const double* stats_ws, double count, void* stream);
+int b200_batchnorm_bwd_apply(const b200_tensor* dy, const b200_tensor* z, const float* save_mean, const float* save_rstd,
+                             const float* gamma, const float* beta, int relu, const b200_tensor* dz,
+                             const double* stats_ws, double count, void* stream);
 
 /* ---- separable linear resampling ----------------------------------------
  * tf.image.resize(bilinear, antialias) of ResizeByScale / ResizeToMatch
@@ -239,10 +255,21 @@ int b200_softmax_ce_loss(const b200_tensor* prob, const int32_t* labels, float g
  * hyper (device fp32[6]) = {lr, beta1, beta2, eps, 1-beta1, 1-beta2} (the last two evaluated in
  * double on the host and then rounded, as keras does); step (device int32[1]) is the
  * 1-based step count, incremented by b200_adam_advance.  Updates p/m/v in place and
- * writes the compute-dtype shadow copy of p (bf16 or NULL). */
-int b200_adam_advance(int32_t* step, void* stream);
+ * writes the compute-dtype shadow copy of p (bf16 or NULL).
+ * loss_scale (device fp32[4], or NULL) = {scale, finite steps in a row, found_inf flag, skipped steps}: the
+ * state of the keras LossScaleOptimizer (the wrapper `mixed_float16` puts around Adam, train_adaptive_unet.py:471-477).
+ * With it, g is divided by `scale`, and a step whose found_inf flag is set changes nothing (p, m, v, step). */
+int b200_adam_advance(int32_t* step, const float* loss_scale, void* stream);
 int b200_adam_step(float* p, const float* g, float* m, float* v, size_t count, const float* hyper,
-                   const int32_t* step, void* shadow_bf16, void* stream);
+                   const int32_t* step, void* shadow_bf16, const float* loss_scale, void* stream);
+/* Dynamic loss scaling around a training step, all state on the device (capturable in a CUDA graph):
+ *   b200_loss_scale_apply  : data *= scale (the loss gradient, right after the loss kernel)
+ *   b200_loss_scale_check  : found_inf |= any non-finite value in g (the flat gradient buffer, after backward)
+ *   b200_loss_scale_update : after the optimizer -- found_inf ? (scale = max(scale/2, 1), streak = 0, clear the flag)
+ *                            : (streak += 1; streak == growth_interval ? scale *= 2, streak = 0). */
+int b200_loss_scale_apply(void* data, int dtype, size_t count, const float* loss_scale, void* stream);
+int b200_loss_scale_check(const float* g, size_t count, float* loss_scale, void* stream);
+int b200_loss_scale_update(float* loss_scale, float growth_interval, void* stream);
 
 /* ---- patch pipeline on the device -- shared/pipeline.py:79-136, 177-246 -------------
  * random_patches / grid_patches + degrade_image (cv2 INTER_AREA shrink to round(P*scale), INTER_CUBIC

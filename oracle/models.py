@@ -369,6 +369,28 @@ def bf16_round(x):
     return x + (x.detach().to(torch.bfloat16).to(x.dtype) - x.detach())
 
 
+class _Bf16Storage(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        return x.to(torch.bfloat16).to(x.dtype)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g.to(torch.bfloat16).to(g.dtype)
+
+
+def bf16_storage(x):
+    """A tensor STORED in bf16 under the mixed policy: its value is rounded, and so is its gradient -- the gradient of a
+    bf16 tensor is carried in bf16 between ops (TensorFlow's Cast op back-propagates a Cast; the kernels here write
+    activation gradients to bf16 buffers).  ``bf16_round`` above is the straight-through form (fp32 gradients): enough
+    for LayerNorm nets, whose per-pixel statistics do not cancel across the batch.  BatchNorm backward subtracts
+    per-channel means over N*H*W, so sum(dz) == 0 holds exactly only before dz is rounded; the filter gradient
+    sum_p x[p] dz[p] then sees mean(x) * (rounding residue of sum dz), which is tens of percent of the true value on
+    post-ReLU inputs.  That residue is a deterministic function of the rounded values, so an oracle that rounds the
+    same tensors at the same points reproduces it."""
+    return _Bf16Storage.apply(x)
+
+
 def sr_flops_per_sample(scale, depth, input_size, base_channels=64, head=64) -> float:
     """Algorithmic forward FLOPs of every conv (2*H*W*Cin*Cout*k*k) for one sample."""
     sizes = resize_np.size_chain(input_size, scale, depth)

@@ -784,3 +784,39 @@ def test_adam():
         pr, mr, vr = K.adam_step(pr, f32(g), mr, vr, t, 1e-3)
     assert relerr(p, pr) < 1e-6 and relerr(m, mr) < 1e-6 and relerr(v, vr) < 1e-6
     assert relerr(shadow, pr) < 4e-3
+
+
+def test_dynamic_loss_scale_kernels():
+    """Device-resident LossScaleOptimizer state {scale, streak, found_inf, skipped}: the finite check, the skipped Adam step
+    and the scale dynamics (x2 after `growth` finite steps in a row, /2 floor 1 on inf / nan) -- keras semantics of the
+    reference's mixed_float16 policy (train_adaptive_unet.py:471-477)."""
+    ops, K = _ops(), _K()
+    n = 1003
+    p = rand((n,), 141); g = rand((n,), 142, scale=0.1); m = torch.zeros(n, device="cuda"); v = torch.zeros(n, device="cuda")
+    hyper = torch.tensor([1e-3, 0.9, 0.999, 1e-7, 1 - 0.9, 1 - 0.999], device="cuda"); step = torch.zeros(1, dtype=torch.int32, device="cuda")
+    ls = torch.tensor([4.0, 0.0, 0.0, 0.0], device="cuda")
+    gs = (g * 4.0).contiguous()                      # what backward produces from a loss gradient scaled by 4
+    ops.loss_scale_check(gs, ls)
+    assert ls.tolist() == [4.0, 0.0, 0.0, 0.0]
+    ops.adam_advance(step, ls); ops.adam_step(p, gs, m, v, hyper, step, None, ls); ops.loss_scale_update(ls, 3)
+    pr, mr, vr = K.adam_step(f32(rand((n,), 141)), f32(g), torch.zeros(n), torch.zeros(n), 1, 1e-3)
+    assert relerr(p, pr) < 1e-6 and relerr(m, mr) < 1e-6 and int(step) == 1 and ls.tolist() == [4.0, 1.0, 0.0, 0.0]
+    # a non-finite gradient: nothing moves, the scale halves, the streak restarts
+    bad = gs.clone(); bad[517] = float("inf")
+    p0, m0, v0 = p.clone(), m.clone(), v.clone()
+    ops.loss_scale_check(bad, ls)
+    assert ls[2].item() == 1.0
+    ops.adam_advance(step, ls); ops.adam_step(p, bad, m, v, hyper, step, None, ls); ops.loss_scale_update(ls, 3)
+    assert torch.equal(p, p0) and torch.equal(m, m0) and torch.equal(v, v0) and int(step) == 1
+    assert ls.tolist() == [2.0, 0.0, 0.0, 1.0]
+    bad[517] = float("nan"); bad[1002] = 1.0        # nan in the unaligned tail region too
+    ops.loss_scale_check(bad, ls); ops.loss_scale_update(ls, 3)
+    assert ls.tolist() == [1.0, 0.0, 0.0, 2.0]
+    ops.loss_scale_check(bad, ls); ops.loss_scale_update(ls, 3)
+    assert ls[0].item() == 1.0                       # floor
+    for k in range(3):                               # three finite steps in a row double the scale
+        ops.loss_scale_check(gs, ls); ops.loss_scale_update(ls, 3)
+    assert ls[0].item() == 2.0 and ls[1].item() == 0.0
+    x = rand((5, 7), 143, torch.bfloat16); x0 = x.clone()
+    ops.loss_scale_apply(x, ls)
+    assert torch.equal(x.float(), x0.float() * 2.0)

@@ -205,9 +205,10 @@ def test_seg_adaptive_step(policy):
     x = rng.random((batch, P, P, 3), dtype=np.float32)
     t = (rng.random((batch, P, P, 1)) > 0.5).astype(np.float32)
     bf = policy != "float32"
-    rnd = M.bf16_round if bf else (lambda v: v)
+    # bf16 policy: the oracle rounds every stored activation AND its gradient (M.bf16_storage), as the kernels do
+    rnd = M.bf16_storage if bf else (lambda v: v)
     new_stats = []
-    fwd = lambda ws, xx: M.seg_adaptive_forward(ws, xx, depth, True, rnd, new_stats)
+    fwd = lambda ws, xx: M.seg_adaptive_forward(ws, rnd(xx), depth, True, rnd, new_stats)   # (bf16: the input is cast too)
     y_ref, l_ref, g_ref = _oracle_step(ws_np, torch.from_numpy(x), torch.from_numpy(t), fwd,
                                        lambda tt, yy: K.bce_dice_loss(tt, yy, 0.4, 0.6), M.bf16_round if bf else None,
                                        dtype=torch.float32 if bf else torch.float64)
@@ -216,6 +217,16 @@ def test_seg_adaptive_step(policy):
                                  lambda tt, yy: K.bce_dice_loss(tt, yy, 0.4, 0.6), None)
         print("   fp32-oracle vs fp64-oracle worst grad relerr:",
               max(relerr(a, b) for a, b in zip(g32, g_ref) if b.abs().max() > 1e-7))
+    g_alt = None
+    if bf:
+        # the policy's own noise band: the SAME oracle, same bf16 storage points, evaluated in float64 instead of float32
+        # arithmetic.  Pre-rounding values then differ by ~1e-7, a few stored elements round the other way, and
+        # BatchNorm backward (d - mean(d) - xhat * mean(d * xhat): a small difference of nearly equal terms on this net;
+        # tools/bn_debug.py shows dy within 4e-3 and dz 8e-2 off at the LAST block) amplifies it.  How far the two oracle
+        # runs sit from each other is how far two faithful implementations of the policy sit from each other.
+        fwd_alt = lambda ws, xx: M.seg_adaptive_forward(ws, rnd(xx), depth, True, rnd, [])
+        _, _, g_alt = _oracle_step(ws_np, torch.from_numpy(x), torch.from_numpy(t), fwd_alt,
+                                   lambda tt, yy: K.bce_dice_loss(tt, yy, 0.4, 0.6), M.bf16_round, dtype=torch.float64)
     logs = model.train_on_batch(x, t)
     print(f"[{policy}] seg loss {logs['loss']:.6f} vs {l_ref:.6f}")
     assert abs(logs["loss"] - l_ref) < (2e-2 if bf else 1e-5)
@@ -228,14 +239,18 @@ def test_seg_adaptive_step(policy):
                 e = relerr(model._grad(ly, nm), g_ref[i])
                 is_pre_bn_bias = nm == "bias" and ly.name != "lesion_mask"
                 print(f"   {w['name']:<40s} grad relerr {e:.3e}")
-                # bf16 policy: activation gradients are STORED in bf16 (0.4% rounding); BatchNorm backward
-                # subtracts their per-channel mean, which amplifies that rounding (measured 0.12-0.31
-                # rel-L2 here).  That is policy noise, not kernel error (fp32 policy: 4e-6 vs fp64), so the
-                # bf16 BN model is only required to keep the gradient direction.
+                # bf16 policy: BatchNorm backward is ill-conditioned on this net (see g_alt above): bf16 rounding flips in
+                # the forward pass move the weight gradients by several percent in the ORACLE ITSELF (printed band).
+                # The 3e-2 tolerance of SURVEY 8c holds for this net under the fp32 policy (4e-6 vs fp64) and per
+                # kernel (test_batchnorm: 1e-2 on identical inputs); end to end the kernels must sit inside the band the
+                # policy itself spans: within 3e-2, or no further from the oracle than 2 x the distance between the two
+                # oracle evaluations and pointing the same way (cos > 0.95).
                 if bf:
+                    band = relerr(g_alt[i], g_ref[i])
                     a, b = model._grad(ly, nm).detach().double().cpu().flatten(), g_ref[i].double().flatten()
                     cos = float((a @ b) / (a.norm() * b.norm() + 1e-30))
-                    ok = cos > 0.9
+                    print(f"      policy band (oracle vs oracle) {band:.3e}, cos {cos:.4f}")
+                    ok = (e < 3e-2) or (e <= 2.0 * band + 1e-2 and cos > 0.95)
                 else:
                     # fp32 policy: ReLU masks / max-pool arg-max are discrete and BatchNorm backward is
                     # ill-conditioned, so ANY fp32 evaluation order moves these gradients: the fp32 torch oracle
@@ -512,4 +527,58 @@ def test_wgrad_side_stream_matches_single_stream():
             assert relerr(mm, m0) < 1e-5                              # the optimizer saw the COMPLETE gradients
     print("lockstep losses:", losses)
     assert losses[0][-1] < 0.6 * losses[0][0]                         # and it trains
+    _setup("float32")
+
+
+def test_sync_batchnorm_two_ranks_one_gpu():
+    """Synchronised BatchNorm (SURVEY 8e caveat): two data-parallel ranks (both on cuda:0, gloo) x 4 samples against one
+    process x 8 samples -- loss, every weight gradient, the moving statistics and the weights after Adam
+    (tools/syncbn_check.py; the driver's multi-GPU runs use NCCL on separate devices)."""
+    import os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, B200_DP_CHECK_ONE_GPU="1", B200_DP_SHARD="0", MASTER_ADDR="127.0.0.1")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29577", os.path.join(root, "tools", "syncbn_check.py")],
+                       env=env, capture_output=True, text=True, timeout=300)
+    print(r.stdout[-2000:], r.stderr[-2000:])
+    assert r.returncode == 0 and "SYNCBN_OK" in r.stdout
+
+
+def test_mixed_float16_policy_dynamic_loss_scaling():
+    """The reference's policy (`mixed_float16`, train_adaptive_unet.py:471-477): keras wraps Adam in a LossScaleOptimizer.
+    Here the kernels stay bf16 and the wrapper's semantics are reproduced on the device: the loss gradient is scaled by
+    2**15, Adam un-scales, so the trajectory equals the mixed_bfloat16 one; a batch that produces nan gradients is
+    skipped (weights, moments and Adam's step counter untouched) and halves the scale."""
+    from b200unet import builders as B
+    from b200unet.keras.optimizers import Adam
+    rng = np.random.default_rng(5)
+    hr = rng.random((4, 32, 32, 3), dtype=np.float32)
+    lr = np.clip(hr + 0.05 * rng.standard_normal(hr.shape).astype(np.float32), 0, 1)
+    out = {}
+    for policy in ("mixed_bfloat16", "mixed_float16"):
+        _setup(policy)
+        model, _ = B.build_super_resolution_unet(0.5, depth_override=2, input_size=32)
+        head = model.get_layer("residual_rgb")
+        head.weight_specs[0]["value"] = np.random.default_rng(3).uniform(-0.2, 0.2, (1, 1, 64, 3)).astype(np.float32)
+        loss, metrics = B.build_losses_and_metrics("charbonnier")
+        model.compile(optimizer=Adam(learning_rate=1e-4), loss=loss, metrics=metrics)
+        l0 = model.train_on_batch(lr, hr)["loss"]
+        out[policy] = (l0, model.G.clone(), model.P.clone(), model)
+    (lb, gb, pb, _), (lf, gf, pf, model) = out["mixed_bfloat16"], out["mixed_float16"]
+    opt = model.optimizer
+    assert opt.dynamic_loss_scale and opt.loss_scale == 2.0 ** 15
+    assert abs(lb - lf) <= 1e-6
+    assert relerr(gf / 2.0 ** 15, gb) < 2e-2          # scaled gradients (bf16 rounding of the scaled activations' gradients)
+    assert relerr(pf, pb) < 1e-5                       # Adam un-scales: same update
+    st = opt._state
+    assert st["loss_scale"].tolist()[:3] == [2.0 ** 15, 1.0, 0.0]
+    p_before, m_before, step_before = model.P.clone(), st["m"].clone(), int(st["step"])
+    bad = hr.copy(); bad[0] = np.nan                   # nan targets for one image: nan loss gradient wherever the output is not
+    # clipped (ClippedResidualAdd passes no gradient where input + residual leaves [0, 1]), hence nan weight gradients
+    model.train_on_batch(lr, bad)
+    torch.cuda.synchronize()
+    assert torch.equal(model.P, p_before) and torch.equal(st["m"], m_before) and int(st["step"]) == step_before
+    assert st["loss_scale"].tolist() == [2.0 ** 14, 0.0, 0.0, 1.0]
+    l2 = model.train_on_batch(lr, hr)["loss"]          # and training goes on
+    assert np.isfinite(l2) and not torch.equal(model.P, p_before)
     _setup("float32")
