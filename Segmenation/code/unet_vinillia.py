@@ -89,7 +89,7 @@ def train(args: argparse.Namespace):
     model = B.build_unet(args.image_size, num_classes=args.num_classes, base_channels=args.base_channels, depth=args.depth)
     binary = args.num_classes == 1
     model.compile(optimizer=Adam(learning_rate=args.learning_rate),
-                  loss=BinaryCrossentropy(global_dice=True) if binary else CategoricalCrossentropy(),
+                  loss=BinaryCrossentropy(global_dice=True, keras_metrics=True) if binary else CategoricalCrossentropy(),
                   metrics=[global_dice_metric] if binary else [])      # :94-99: Dice as one ratio over the batch
     args.model_dir.mkdir(parents=True, exist_ok=True)
     checkpoint_path = args.model_dir / f"{args.run_name}_best.keras"

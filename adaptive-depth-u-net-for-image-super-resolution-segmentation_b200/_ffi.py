@@ -94,6 +94,7 @@ SIGNATURES = {
     "b200_clipadd_bwd": (_i, [_TP, _TP, _TP, _TP, _vp]),
     "b200_sr_loss": (_i, [_TP, _TP, _i, _f, _f, _vp, _TP, _vp, _vp]),
     "b200_bce_dice_loss": (_i, [_TP, _TP, _f, _f, _f, _vp, _TP, _vp, _vp]),
+    "b200_binary_confusion": (_i, [_TP, _TP, _f, _vp, _vp]),
     "b200_softmax_fwd": (_i, [_TP, _TP, _vp]),
     "b200_softmax_ce_loss": (_i, [_TP, _vp, _f, _vp, _TP, _vp, _vp]),
     "b200_adam_advance": (_i, [_vp, _vp, _vp]),

@@ -89,6 +89,7 @@ int clipadd_bwd(const b200_tensor*, const b200_tensor*, const b200_tensor*, cons
 int sr_loss(const b200_tensor*, const b200_tensor*, int, float, float, float*, const b200_tensor*, float*, cudaStream_t);
 int bce_dice_loss(const b200_tensor*, const b200_tensor*, float, float, float, float*, const b200_tensor*, float*,
                   cudaStream_t);
+int binary_confusion(const b200_tensor*, const b200_tensor*, float, float*, cudaStream_t);
 int softmax_fwd(const b200_tensor*, const b200_tensor*, cudaStream_t);
 int softmax_ce_loss(const b200_tensor*, const int32_t*, float, float*, const b200_tensor*, float*, cudaStream_t);
 int adam_advance(int32_t*, const float*, cudaStream_t);
@@ -413,6 +414,11 @@ int b200_bce_dice_loss(const b200_tensor* pred, const b200_tensor* target, float
   REQ_T(pred, "pred"); REQ_T(target, "target");
   B200_REQUIRE(out && ws, B200_ERR_BAD_ARG, "bce_dice_loss: NULL out/ws");
   return bce_dice_loss(pred, target, bw, dw, gs, out, dpred, ws, ST(s));
+}
+int b200_binary_confusion(const b200_tensor* pred, const b200_tensor* target, float threshold, float* counts, void* s) {
+  REQ_T(pred, "pred"); REQ_T(target, "target");
+  B200_REQUIRE(counts, B200_ERR_BAD_ARG, "binary_confusion: NULL counts");
+  return binary_confusion(pred, target, threshold, counts, ST(s));
 }
 int b200_softmax_fwd(const b200_tensor* z, const b200_tensor* p, void* s) {
   REQ_T(z, "z"); REQ_T(p, "p");

@@ -190,6 +190,34 @@ bce_dice_grad_kernel(TView pred, TView tgt, const float* __restrict__ ws, float 
   }
 }
 
+// ---- BinaryAccuracy / Precision / Recall counters (keras metrics of the baseline trainer, unet_vinillia.py:266-270) ----
+// counts += {true positives, false positives, false negatives, correct}: prediction positive = pred > threshold,
+// label positive = target != 0 (keras casts y_true to bool); "correct" compares the thresholded prediction with the target.
+template <typename TP, typename TT>
+__global__ void __launch_bounds__(NT)
+binary_confusion_kernel(TView pred, TView tgt, float threshold, float* __restrict__ counts, long long total) {
+  const TP* pp = reinterpret_cast<const TP*>(pred.data);
+  const TT* tp = reinterpret_cast<const TT*>(tgt.data);
+  float c_tp = 0.f, c_fp = 0.f, c_fn = 0.f, c_ok = 0.f;
+  for (long long i = (long long)blockIdx.x * NT + threadIdx.x; i < total; i += (long long)gridDim.x * NT) {
+    int c = (int)(i % pred.c), n, h, w;
+    pix_decode(i / pred.c, pred.h, pred.w, n, h, w);
+    const float pv = ldf(pp + pix_offset(pred, n, h, w) + c);
+    const float y = ldf(tp + pix_offset(tgt, n, h, w) + c);
+    const bool pos = pv > threshold, lab = y != 0.f;
+    c_tp += (pos && lab) ? 1.f : 0.f;
+    c_fp += (pos && !lab) ? 1.f : 0.f;
+    c_fn += (!pos && lab) ? 1.f : 0.f;
+    c_ok += ((pos ? 1.f : 0.f) == y) ? 1.f : 0.f;
+  }
+  __shared__ float s[4];
+  if (threadIdx.x < 4) s[threadIdx.x] = 0.f;
+  __syncthreads();
+  block_atomic_add(c_tp, &s[0]); block_atomic_add(c_fp, &s[1]); block_atomic_add(c_fn, &s[2]); block_atomic_add(c_ok, &s[3]);
+  __syncthreads();
+  if (threadIdx.x < 4) atomicAdd(counts + threadIdx.x, s[threadIdx.x]);   // integer-valued sums: exact up to 2^24 per block
+}
+
 // ---- softmax / categorical cross-entropy -----------------------------------------------
 template <typename T>
 __global__ void __launch_bounds__(NT)
@@ -330,6 +358,17 @@ int bce_dice_loss(const b200_tensor* pred, const b200_tensor* target, float bw, 
   });
   count_launches((dpred && dpred->data) ? 2 : 1);
   return check_launch("bce_dice_loss");
+}
+
+int binary_confusion(const b200_tensor* pred, const b200_tensor* target, float threshold, float* counts, cudaStream_t st) {
+  B200_REQUIRE(same_shape(pred, target), B200_ERR_BAD_ARG, "binary_confusion: shape mismatch");
+  const long long total = (long long)pred->n * pred->h * pred->w * pred->c;
+  cudaMemsetAsync(counts, 0, sizeof(float) * 4, st);
+  TView pv = view_of(pred), tv = view_of(target);
+  B200_DISPATCH_2(pred->dtype, target->dtype, TP, TT, {
+    binary_confusion_kernel<TP, TT><<<grid_for(total), NT, 0, st>>>(pv, tv, threshold, counts, total);
+  });
+  return check_launch("binary_confusion_kernel");
 }
 
 int softmax_fwd(const b200_tensor* z, const b200_tensor* p, cudaStream_t st) {

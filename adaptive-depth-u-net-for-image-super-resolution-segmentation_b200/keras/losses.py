@@ -99,20 +99,44 @@ class BceDiceLoss(_PlanLoss):
     metric_names = ("dice", "iou")
     metric_slots = (2, 3)
 
-    def __init__(self, bce_weight=1.0, dice_weight=0.0, name="bce_dice", global_dice=False):
+    def __init__(self, bce_weight=1.0, dice_weight=0.0, name="bce_dice", global_dice=False, keras_metrics=False):
         self.bw, self.dw = float(bce_weight), float(dice_weight)
         self.__name__ = name
+        # the baseline trainer's extra keras metrics (unet_vinillia.py:266-270): BinaryAccuracy(name="accuracy"),
+        # Precision, Recall at threshold 0.5 -- one more pass over the (1-channel) prediction per step.  Precision and
+        # recall are STATEFUL in keras (tp / fp / fn accumulate over the epoch): next to the batch values the step logs
+        # the per-sample counter rates under "_tp" / "_fp" / "_fn", which Model combines at the end of an epoch.
+        self.keras_metrics = bool(keras_metrics)
         if global_dice:      # the baseline trainer's metric: one Dice ratio over the whole batch (unet_vinillia.py:94-99),
             # logged under the function's name as keras does ("dice_coefficient" / "val_dice_coefficient", :270-273)
             self.metric_names, self.metric_slots = ("dice_coefficient", "iou"), (4, 3)
+        self.extra_metric_names = ("accuracy", "precision", "recall") if self.keras_metrics else ()
 
     def _more_state(self, plan, st):
         st["ws"] = torch.zeros(1 + 3 * plan.batch, dtype=torch.float32, device=plan.dev)
+        if self.keras_metrics:
+            st["counts"] = torch.zeros(4, dtype=torch.float32, device=plan.dev)
 
     def launch(self, plan, st, grad_scale=1.0, with_grad=True):
         ov = plan.output_val
         ops.bce_dice_loss(ov.buf, st["target"], self.bw, self.dw, grad_scale, st["out"],
                           ov.grad if with_grad else None, st["ws"])
+        if self.keras_metrics:
+            ops.binary_confusion(ov.buf, st["target"], st["counts"])
+
+    def logs(self, st):
+        if not self.keras_metrics:
+            return super().logs(st)
+        d = {"loss": st["out"][0]}                    # keras' order: loss, then the metrics as listed at compile()
+        tp, fp, fn, ok = st["counts"].unbind(0)
+        n = float(st["target"].shape[0])
+        d["accuracy"] = ok / float(st["target"].numel())
+        d["precision"] = torch.where(tp + fp > 0, tp / (tp + fp).clamp_min(1.0), torch.zeros_like(tp))
+        d["recall"] = torch.where(tp + fn > 0, tp / (tp + fn).clamp_min(1.0), torch.zeros_like(tp))
+        for m, sl in zip(self.metric_names, self.metric_slots):
+            d[m] = st["out"][sl]
+        d["_tp"], d["_fp"], d["_fn"] = tp / n, fp / n, fn / n
+        return d
 
     def __call__(self, y_true, y_pred):
         out = torch.zeros(8, device=y_pred.device)
@@ -122,8 +146,8 @@ class BceDiceLoss(_PlanLoss):
         return out[0]
 
 
-def BinaryCrossentropy(global_dice=False):
-    return BceDiceLoss(1.0, 0.0, name="binary_crossentropy", global_dice=global_dice)
+def BinaryCrossentropy(global_dice=False, keras_metrics=False):
+    return BceDiceLoss(1.0, 0.0, name="binary_crossentropy", global_dice=global_dice, keras_metrics=keras_metrics)
 
 
 class CategoricalCrossentropy(_PlanLoss):

@@ -975,7 +975,8 @@ class Model:
         return res if return_dict else list(res.values())
 
     def _log_keys(self):
-        return ["loss"] + list(getattr(self.loss, "metric_names", ()))
+        keys = ["loss"] + list(getattr(self.loss, "extra_metric_names", ())) + list(getattr(self.loss, "metric_names", ()))
+        return keys + (["_tp", "_fp", "_fn"] if getattr(self.loss, "keras_metrics", False) else [])
 
     def _weighted_mean(self, sums: Dict[str, float], weight: float) -> Dict[str, float]:
         """Epoch-level logs as keras computes them: every batch weighted by its sample count (a ragged last batch counts
@@ -994,7 +995,12 @@ class Model:
             sums = {k: v for k, v in zip(keys, vals[:-1])}
         if weight <= 0:
             return {}
-        return {k: float(sums[k]) / weight for k in keys if k in sums}
+        res = {k: float(sums[k]) / weight for k in keys if k in sums}
+        if "_tp" in res:     # keras' stateful Precision / Recall: ratios of the counters accumulated over the epoch
+            tp, fp, fn = res.pop("_tp"), res.pop("_fp"), res.pop("_fn")
+            res["precision"] = tp / (tp + fp) if tp + fp > 0 else 0.0
+            res["recall"] = tp / (tp + fn) if tp + fn > 0 else 0.0
+        return res
 
     def fit(self, x=None, y=None, epochs=1, initial_epoch=0, steps_per_epoch=None, validation_data=None,
             validation_steps=None, validation_freq=1, callbacks=None, verbose=1, batch_size=None, **kwargs):

@@ -315,6 +315,12 @@ def bce_dice_loss(pred, target, bce_w, dice_w, grad_scale, out, dpred, ws):
     return out
 
 
+def binary_confusion(pred, target, counts, threshold=0.5):
+    """counts[4] = {tp, fp, fn, correct} of (pred > threshold) against (target != 0)."""
+    check(lib().b200_binary_confusion(tdesc(pred), tdesc(target), float(threshold), _ptr(counts), _stream()), "binary_confusion")
+    return counts
+
+
 def softmax_fwd(z, p):
     check(lib().b200_softmax_fwd(tdesc(z), tdesc(p), _stream()), "softmax_fwd")
     return p

@@ -247,6 +247,10 @@ int b200_bce_dice_loss(const b200_tensor* pred, const b200_tensor* target, float
 
 /* ---- softmax head + categorical cross-entropy (config C4; extrapolated) ----
  * unet_vinillia.py:89-90 softmax head; keras CategoricalCrossentropy semantics. */
+/* keras BinaryAccuracy / Precision / Recall (unet_vinillia.py:266-270) as counters: counts (device fp32[4]) =
+ * {true positives, false positives, false negatives, correct} over all elements, prediction positive = pred > threshold,
+ * label positive = target != 0.  accuracy = correct / elements, precision = tp / (tp + fp), recall = tp / (tp + fn). */
+int b200_binary_confusion(const b200_tensor* pred, const b200_tensor* target, float threshold, float* counts, void* stream);
 int b200_softmax_fwd(const b200_tensor* z, const b200_tensor* p, void* stream);
 int b200_softmax_ce_loss(const b200_tensor* prob, const int32_t* labels, float grad_scale, float* out,
                          const b200_tensor* dlogits, float* ws, void* stream);

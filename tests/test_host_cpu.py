@@ -284,3 +284,23 @@ def test_lowering_structure_on_cpu():
         assert all(op.act == ACT_RELU for op in plain), name
     assert {op.output.c for op in lower(nets["seg_base32"])[0] if op.kind == "conv"} == {32, 64, 128, 256, 512, 21}
     clear_session()
+
+
+def test_epoch_logs_are_sample_weighted_and_precision_recall_accumulate():
+    """keras weights every batch by its sample count (a ragged last batch counts for less) and its Precision / Recall are
+    stateful: ratios of the tp / fp / fn counters accumulated over the epoch, not means of per-batch ratios."""
+    from b200unet import builders as B
+    from b200unet.keras import clear_session
+    from b200unet.keras.losses import BinaryCrossentropy
+    clear_session()
+    model = B.build_unet(16, num_classes=1, base_channels=32, depth=1)
+    model.loss = BinaryCrossentropy(global_dice=True, keras_metrics=True)
+    assert model._log_keys() == ["loss", "accuracy", "precision", "recall", "dice_coefficient", "iou", "_tp", "_fp", "_fn"]
+    # two batches: 8 samples (loss 1.0, tp 10, fp 0, fn 10 per batch) and 2 samples (loss 3.0, tp 0, fp 6, fn 0)
+    sums = {"loss": 1.0 * 8 + 3.0 * 2, "accuracy": 0.5 * 8 + 1.0 * 2, "precision": 1.0 * 8 + 0.0 * 2, "recall": 0.5 * 8 + 0.0 * 2,
+            "dice_coefficient": 0.7 * 8 + 0.1 * 2, "iou": 0.5 * 10, "_tp": 10.0, "_fp": 6.0, "_fn": 10.0}
+    logs = model._weighted_mean(sums, 10.0)
+    assert abs(logs["loss"] - 1.4) < 1e-12 and abs(logs["accuracy"] - 0.6) < 1e-12
+    assert abs(logs["precision"] - 10 / 16) < 1e-12 and abs(logs["recall"] - 0.5) < 1e-12      # NOT 0.8 / 0.4 (batch means)
+    assert list(logs) == ["loss", "accuracy", "precision", "recall", "dice_coefficient", "iou"]
+    assert model._weighted_mean({}, 0.0) == {}

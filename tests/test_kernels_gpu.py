@@ -820,3 +820,17 @@ def test_dynamic_loss_scale_kernels():
     x = rand((5, 7), 143, torch.bfloat16); x0 = x.clone()
     ops.loss_scale_apply(x, ls)
     assert torch.equal(x.float(), x0.float() * 2.0)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_binary_confusion_counters(dtype):
+    """keras BinaryAccuracy / Precision / Recall (unet_vinillia.py:266-270) as tp / fp / fn / correct counters."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(9)
+    pred = torch.rand((3, 17, 13, 1), generator=g).to(dtype).cuda()
+    tgt = (torch.rand((3, 17, 13, 1), generator=g) > 0.6).float().cuda()
+    counts = torch.full((4,), 7.0, device="cuda")
+    ops.binary_confusion(pred, tgt, counts)
+    pos, lab = pred.float().cpu() > 0.5, tgt.cpu() != 0
+    want = [float((pos & lab).sum()), float((pos & ~lab).sum()), float((~pos & lab).sum()), float((pos.float() == tgt.cpu()).sum())]
+    assert counts.tolist() == want
