@@ -6,6 +6,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include "../../include/b200_unet.h"
 
@@ -135,6 +136,44 @@ inline bool first_use_on_device(int slot) {
   if (seen[dev] & bit) return false;
   seen[dev] |= bit;
   return true;
+}
+
+// ---- programmatic dependent launch (PDL) ---------------------------------------------------------------------
+// Every kernel of the library is launched with the programmatic-stream-serialisation attribute: its CTAs may be
+// scheduled while the previous kernel of the stream is still draining (its last CTAs, its memory flush), so launch
+// latency, block scheduling and -- in the tcgen05 kernels -- barrier init, TMEM allocation and tensor-map prefetch
+// overlap the predecessor's tail.  The contract each kernel keeps: NO global-memory access (read or write) before
+// pdl_sync().  griddepcontrol.wait returns once the preceding grid has completed and its writes are visible (so also
+// everything that grid waited for: the dependency chain is transitive); launch_dependents right after it lets the
+// NEXT kernel start its own prologue once all CTAs of this one are resident.  Cross-stream edges (events) and the
+// launches of other libraries stay full dependencies.  B200_PDL=0 launches everything the classic way.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_sync() { pdl_wait(); pdl_trigger(); }
+
+// Measured (C2 / C1, profiles/r02_pdl_sweep.json): early-resident CTAs of the big memory-bound kernels (8 x 148 blocks)
+// spin on SMs that the second stream's wgrad kernels would otherwise use -- C2 slows from 4.38 to 4.51-4.55 ms with PDL
+// on every launch, while the launch-bound C1 gains 7 % (1.089 -> 1.011 ms).  Restricting the early start to launches of
+// fewer than 2 x SM-count blocks (the persistent tcgen05 kernels, the deep levels, the small tensors) wins on both:
+// C2 4.38 -> 4.25 ms, C1 1.089 -> 1.004 ms (bounds 148 / 296 / 448 / 600 / 1200: 4.30 / 4.25 / 4.34 / 4.41 / 4.55 ms).
+// B200_PDL=0: never; B200_PDL_MAX_BLOCKS overrides the bound.
+inline bool pdl_enabled(unsigned long long blocks = 0) {
+  static const bool on = getenv("B200_PDL") ? atoi(getenv("B200_PDL")) != 0 : true;
+  static const long long bound = getenv("B200_PDL_MAX_BLOCKS") ? atoll(getenv("B200_PDL_MAX_BLOCKS")) : -1;
+  const unsigned long long lim = bound >= 0 ? (unsigned long long)bound : 2ull * (unsigned long long)sm_count();
+  return on && blocks < lim;
+}
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled((unsigned long long)grid.x * grid.y * grid.z) ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
 // dtype dispatch: DISPATCH_DTYPE(dt, T, { body using T })

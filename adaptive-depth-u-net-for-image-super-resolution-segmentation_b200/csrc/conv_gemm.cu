@@ -102,6 +102,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
   }
   if (warp == 0 && lane == 0) { prefetch_tmap(&tm_x); prefetch_tmap(&tm_b); }
   if (warp == 1) { tmem_alloc(smem_u32(&tmem_base_smem), (uint32_t)p.BN < 32u ? 32u : (uint32_t)p.BN); tmem_relinquish(); }
+  pdl_sync();      // (PDL) global memory only from here on
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -188,6 +189,7 @@ struct FinParams {
 // combined through shared memory in a fixed order (deterministic).
 __global__ void __launch_bounds__(256)
 conv_gemm_finalize_kernel(const FinParams p) {
+  pdl_sync();
   __shared__ float s_part[3][64][9];
   const int chunks = p.Cout / 8;
   const long long total = (long long)p.m_tiles * 128 * chunks;
@@ -299,6 +301,7 @@ wgrad_small_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
   }
   if (warp == 0 && lane == 0) { prefetch_tmap(&tm_x); prefetch_tmap(&tm_dz); }
   if (warp == 1) { tmem_alloc(smem_u32(&tmem_base_smem), 128); tmem_relinquish(); }
+  pdl_sync();      // (PDL) global memory only from here on
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -453,7 +456,7 @@ int conv_gemm_launch(const b200_tensor* x, const void* wmat, int cin, int cout, 
   if (first_use_on_device(0))
     cudaFuncSetAttribute(conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 1024 + MAX_STAGES * (A_BYTES + 128 * 128));
   const int grid = p.splits * p.m_tiles * p.n_tiles;
-  conv_gemm_kernel<<<grid, NTHREADS, smem, st>>>(tm_x, tm_b, p);
+  launch_pdl(conv_gemm_kernel, grid, NTHREADS, smem, st, tm_x, tm_b, p);
   rc = check_launch("conv_gemm_kernel");
   if (rc) return rc;
   FinParams f;
@@ -465,7 +468,7 @@ int conv_gemm_launch(const b200_tensor* x, const void* wmat, int cin, int cout, 
   const long long total = (long long)p.m_tiles * 128 * (cout / 8);
   long long blocks = (total + 63) / 64;
   if (blocks > 8LL * sm_count()) blocks = 8LL * sm_count();
-  conv_gemm_finalize_kernel<<<(int)blocks, 256, 0, st>>>(f);
+  launch_pdl(conv_gemm_finalize_kernel, (int)blocks, 256, 0, st, f);
   return check_launch("conv_gemm_finalize_kernel");
 }
 
@@ -520,7 +523,7 @@ int wgrad_small_launch(const b200_tensor* x, const b200_tensor* dy, float* out, 
   if (first_use_on_device(1))
     cudaFuncSetAttribute(wgrad_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   const int grid = p.splits * p.nlive * p.cblocks * p.oblocks;
-  wgrad_small_kernel<<<grid, NTHREADS, smem, st>>>(tm_x, tm_dz, p);
+  launch_pdl(wgrad_small_kernel, grid, NTHREADS, smem, st, tm_x, tm_dz, p);
   *splits_out = p.splits;
   *live_mask = mask;
   return check_launch("wgrad_small_kernel");

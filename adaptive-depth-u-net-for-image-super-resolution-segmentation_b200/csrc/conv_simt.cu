@@ -23,6 +23,7 @@ template <typename T, int KS, bool DGRAD>
 __global__ void __launch_bounds__(NTHREADS)
 conv_direct_kernel(TView x, const T* __restrict__ wgt, const float* __restrict__ bias, TView y, int act,
                    int accumulate, int tiles_w, int tiles_h) {
+  pdl_sync();
   constexpr int HALO = KS - 1;
   constexpr int PAD = KS / 2;
   constexpr int IW = TP + HALO;
@@ -113,6 +114,7 @@ conv_direct_kernel(TView x, const T* __restrict__ wgt, const float* __restrict__
 template <typename T, int KS, int CI_T>
 __global__ void __launch_bounds__(NTHREADS)
 wgrad_direct_kernel(TView x, TView dy, float* __restrict__ dw, int tiles_w, int tiles_h, int total_tiles) {
+  pdl_sync();
   constexpr int HALO = KS - 1;
   constexpr int PAD = KS / 2;
   constexpr int IW = TP + HALO;
@@ -190,6 +192,7 @@ wgrad_direct_kernel(TView x, TView dy, float* __restrict__ dw, int tiles_w, int 
 template <typename T>
 __global__ void __launch_bounds__(256)
 filter_pack_kernel(const T* __restrict__ hwio, T* __restrict__ ohwi, int cin, int cout) {
+  pdl_sync();
   __shared__ T tile[32][33];
   const int t = blockIdx.z;
   const int c0 = blockIdx.x * 32, o0 = blockIdx.y * 32;
@@ -221,11 +224,11 @@ int conv_simt_fprop(const b200_tensor* x, const b200_filter* f, const float* bia
   B200_DISPATCH_DTYPE(x->dtype, T, {
     const T* w = reinterpret_cast<const T*>(f->hwio);
     if (ks == 3) {
-      if (dgrad) conv_direct_kernel<T, 3, true><<<grid, NTHREADS, 0, st>>>(xv, w, bias, yv, act, accumulate, tiles_w, tiles_h);
-      else conv_direct_kernel<T, 3, false><<<grid, NTHREADS, 0, st>>>(xv, w, bias, yv, act, accumulate, tiles_w, tiles_h);
+      if (dgrad) launch_pdl(conv_direct_kernel<T, 3, true>, grid, NTHREADS, 0, st, xv, w, bias, yv, act, accumulate, tiles_w, tiles_h);
+      else launch_pdl(conv_direct_kernel<T, 3, false>, grid, NTHREADS, 0, st, xv, w, bias, yv, act, accumulate, tiles_w, tiles_h);
     } else {
-      if (dgrad) conv_direct_kernel<T, 1, true><<<grid, NTHREADS, 0, st>>>(xv, w, bias, yv, act, accumulate, tiles_w, tiles_h);
-      else conv_direct_kernel<T, 1, false><<<grid, NTHREADS, 0, st>>>(xv, w, bias, yv, act, accumulate, tiles_w, tiles_h);
+      if (dgrad) launch_pdl(conv_direct_kernel<T, 1, true>, grid, NTHREADS, 0, st, xv, w, bias, yv, act, accumulate, tiles_w, tiles_h);
+      else launch_pdl(conv_direct_kernel<T, 1, false>, grid, NTHREADS, 0, st, xv, w, bias, yv, act, accumulate, tiles_w, tiles_h);
     }
   });
   return check_launch("conv_direct_kernel");
@@ -247,11 +250,11 @@ int conv_simt_wgrad(const b200_tensor* x, const b200_tensor* dy, int ks, float* 
   TView xv = view_of(x), dv = view_of(dy);
   B200_DISPATCH_DTYPE(x->dtype, T, {
     if (ks == 3) {
-      if (narrow) wgrad_direct_kernel<T, 3, 4><<<grid, NTHREADS, 0, st>>>(xv, dv, dw, tiles_w, tiles_h, total);
-      else wgrad_direct_kernel<T, 3, 16><<<grid, NTHREADS, 0, st>>>(xv, dv, dw, tiles_w, tiles_h, total);
+      if (narrow) launch_pdl(wgrad_direct_kernel<T, 3, 4>, grid, NTHREADS, 0, st, xv, dv, dw, tiles_w, tiles_h, total);
+      else launch_pdl(wgrad_direct_kernel<T, 3, 16>, grid, NTHREADS, 0, st, xv, dv, dw, tiles_w, tiles_h, total);
     } else {
-      if (narrow) wgrad_direct_kernel<T, 1, 4><<<grid, NTHREADS, 0, st>>>(xv, dv, dw, tiles_w, tiles_h, total);
-      else wgrad_direct_kernel<T, 1, 16><<<grid, NTHREADS, 0, st>>>(xv, dv, dw, tiles_w, tiles_h, total);
+      if (narrow) launch_pdl(wgrad_direct_kernel<T, 1, 4>, grid, NTHREADS, 0, st, xv, dv, dw, tiles_w, tiles_h, total);
+      else launch_pdl(wgrad_direct_kernel<T, 1, 16>, grid, NTHREADS, 0, st, xv, dv, dw, tiles_w, tiles_h, total);
     }
   });
   return check_launch("wgrad_direct_kernel");
@@ -260,7 +263,7 @@ int conv_simt_wgrad(const b200_tensor* x, const b200_tensor* dy, int ks, float* 
 int filter_pack(const void* hwio, void* ohwi, int taps, int cin, int cout, int dtype, cudaStream_t st) {
   dim3 grid((cin + 31) / 32, (cout + 31) / 32, taps);
   B200_DISPATCH_DTYPE(dtype, T, {
-    filter_pack_kernel<T><<<grid, 256, 0, st>>>(reinterpret_cast<const T*>(hwio), reinterpret_cast<T*>(ohwi), cin, cout);
+    launch_pdl(filter_pack_kernel<T>, grid, 256, 0, st, reinterpret_cast<const T*>(hwio), reinterpret_cast<T*>(ohwi), cin, cout);
   });
   return check_launch("filter_pack_kernel");
 }

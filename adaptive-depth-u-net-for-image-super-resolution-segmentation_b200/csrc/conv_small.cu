@@ -21,6 +21,7 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 stem_fprop_kernel(TView x, const T* __restrict__ wgt, const float* __restrict__ bias, TView y, int act, int tiles_w,
                   int tiles_h) {
+  pdl_sync();
   __shared__ float s_x[3][ST_IW][ST_IW + 1];
   __shared__ __align__(16) float s_w[27][64];
   __shared__ float s_b[64];
@@ -104,6 +105,7 @@ constexpr int SW_TH = 8, SW_TW = 16;      // 128 pixels per tile
 template <typename T>
 __global__ void __launch_bounds__(256)
 stem_wgrad_kernel(TView x, TView dy, float* __restrict__ dw, int tiles_w, int tiles_h, int total_tiles) {
+  pdl_sync();
   __shared__ float s_x[3][SW_TH + 2][SW_TW + 3];
   __shared__ __align__(16) float s_dz[SW_TH * SW_TW][64];
   const int tid = threadIdx.x;
@@ -192,6 +194,7 @@ stem_wgrad_kernel(TView x, TView dy, float* __restrict__ dw, int tiles_w, int ti
 template <typename T, int COUT>
 __global__ void __launch_bounds__(256)
 head_fprop_kernel(TView x, const T* __restrict__ wgt, const float* __restrict__ bias, TView y, int act, long long npix) {
+  pdl_sync();
   const int Cin = x.c, chunks = Cin / 8;
   const int j = threadIdx.x % chunks, ppb = 256 / chunks;
   float w[8][COUT];
@@ -233,6 +236,7 @@ head_fprop_kernel(TView x, const T* __restrict__ wgt, const float* __restrict__ 
 template <typename T, int COUT>
 __global__ void __launch_bounds__(256)
 head_dgrad_kernel(TView dy, const T* __restrict__ wgt, TView dx, int accumulate, long long npix) {
+  pdl_sync();
   const int Cin = dx.c, chunks = Cin / 8;
   const int j = threadIdx.x % chunks, ppb = 256 / chunks;
   float w[8][COUT];
@@ -270,6 +274,7 @@ head_dgrad_kernel(TView dy, const T* __restrict__ wgt, TView dx, int accumulate,
 template <typename T, int COUT>
 __global__ void __launch_bounds__(256)
 head_wgrad_kernel(TView x, TView dy, float* __restrict__ dw, long long npix) {
+  pdl_sync();
   extern __shared__ float s_acc[];   // [Cin][COUT]
   const int Cin = x.c, chunks = Cin / 8;
   for (int i = threadIdx.x; i < Cin * COUT; i += 256) s_acc[i] = 0.f;
@@ -317,6 +322,7 @@ template <int COUT, int U>
 __global__ void __launch_bounds__(256)
 head_fprop_lean_kernel(const __nv_bfloat16* __restrict__ x, long long x_sw, const __nv_bfloat16* __restrict__ wgt,
                        const float* __restrict__ bias, __nv_bfloat16* __restrict__ y, long long y_sw, int act, int npix) {
+  pdl_sync();
   const int j = threadIdx.x & 7;
   float w[8][COUT];
 #pragma unroll
@@ -366,6 +372,7 @@ template <int COUT, int U>
 __global__ void __launch_bounds__(256)
 head_wgrad_lean_kernel(const __nv_bfloat16* __restrict__ x, long long x_sw, const __nv_bfloat16* __restrict__ d,
                        long long d_sw, float* __restrict__ dw, float* __restrict__ dbias, int npix) {
+  pdl_sync();
   __shared__ float s_red[256 * 8];
   const int j = threadIdx.x & 7;
   float acc[8][COUT], bacc[COUT];
@@ -426,6 +433,7 @@ head_wgrad_lean_kernel(const __nv_bfloat16* __restrict__ x, long long x_sw, cons
 // (8 pixels) per thread so that the channel of every element is a compile-time constant
 __global__ void __launch_bounds__(256)
 bias_sum_c3_kernel(const __nv_bfloat16* __restrict__ d, long long n_elem, float* __restrict__ dbias) {
+  pdl_sync();
   float a[3] = {0.f, 0.f, 0.f};
   const long long groups = n_elem / 24;
   for (long long g = (long long)blockIdx.x * 256 + threadIdx.x; g < groups; g += (long long)gridDim.x * 256) {
@@ -472,6 +480,7 @@ inline bool pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
 template <typename T, int CIN>
 __global__ void __launch_bounds__(256)
 im2col3x3_kernel(TView x, __nv_bfloat16* __restrict__ xcol, long long col_sw, int H, int W, int cin_rt) {
+  pdl_sync();
   constexpr int SEG = 32, MAXC = 7;
   __shared__ float s_rows[3][(SEG + 2) * MAXC];
   const int cin = CIN > 0 ? CIN : cin_rt;
@@ -518,7 +527,7 @@ int stem_fprop(const b200_tensor* x, const void* wgt, const float* bias, const b
   dim3 grid(tiles_w * tiles_h * y->n, (y->c + 63) / 64);
   TView xv = view_of(x), yv = view_of(y);
   B200_DISPATCH_DTYPE(x->dtype, T, {
-    stem_fprop_kernel<T><<<grid, 256, 0, st>>>(xv, reinterpret_cast<const T*>(wgt), bias, yv, act, tiles_w, tiles_h);
+    launch_pdl(stem_fprop_kernel<T>, grid, 256, 0, st, xv, reinterpret_cast<const T*>(wgt), bias, yv, act, tiles_w, tiles_h);
   });
   return check_launch("stem_fprop_kernel");
 }
@@ -531,7 +540,7 @@ int stem_wgrad(const b200_tensor* x, const b200_tensor* dy, float* dw, cudaStrea
   cudaMemsetAsync(dw, 0, sizeof(float) * 9 * x->c * dy->c, st);
   dim3 grid(gx, (dy->c + 63) / 64);
   TView xv = view_of(x), dv = view_of(dy);
-  B200_DISPATCH_DTYPE(x->dtype, T, { stem_wgrad_kernel<T><<<grid, 256, 0, st>>>(xv, dv, dw, tiles_w, tiles_h, total); });
+  B200_DISPATCH_DTYPE(x->dtype, T, { launch_pdl(stem_wgrad_kernel<T>, grid, 256, 0, st, xv, dv, dw, tiles_w, tiles_h, total); });
   return check_launch("stem_wgrad_kernel");
 }
 
@@ -548,8 +557,8 @@ int im2col3x3(const b200_tensor* x, const b200_tensor* xcol, cudaStream_t st) {
   dim3 grid((unsigned)((x->w + 31) / 32), (unsigned)x->h, (unsigned)x->n);
   __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(xcol->data);
   B200_DISPATCH_DTYPE(x->dtype, T, {
-    if (x->c == 3) im2col3x3_kernel<T, 3><<<grid, 256, 0, st>>>(xv, dst, xcol->stride_w, x->h, x->w, 3);
-    else im2col3x3_kernel<T, 0><<<grid, 256, 0, st>>>(xv, dst, xcol->stride_w, x->h, x->w, x->c);
+    if (x->c == 3) launch_pdl(im2col3x3_kernel<T, 3>, grid, 256, 0, st, xv, dst, xcol->stride_w, x->h, x->w, 3);
+    else launch_pdl(im2col3x3_kernel<T, 0>, grid, 256, 0, st, xv, dst, xcol->stride_w, x->h, x->w, x->c);
   });
   return check_launch("im2col3x3_kernel");
 }
@@ -582,7 +591,7 @@ int bias_sum_c3(const b200_tensor* dy, float* dbias, cudaStream_t st) {
   long long blocks = (n_elem / 24 + 255) / 256;
   if (blocks > 4LL * sm_count()) blocks = 4LL * sm_count();
   if (blocks < 1) blocks = 1;
-  bias_sum_c3_kernel<<<(int)blocks, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(dy->data), n_elem, dbias);
+  launch_pdl(bias_sum_c3_kernel, (int)blocks, 256, 0, st, reinterpret_cast<const __nv_bfloat16*>(dy->data), n_elem, dbias);
   return check_launch("bias_sum_c3_kernel");
 }
 
@@ -591,7 +600,7 @@ int head_fprop(const b200_tensor* x, const void* wgt, const float* bias, const b
     const int npix = x->n * x->h * x->w;
     long long blocks = (npix + 4 * 32 - 1) / (4 * 32);
     if (blocks > 8LL * sm_count()) blocks = 8LL * sm_count();
-    head_fprop_lean_kernel<3, 4><<<(int)blocks, 256, 0, st>>>(
+    launch_pdl(head_fprop_lean_kernel<3, 4>, (int)blocks, 256, 0, st, 
         reinterpret_cast<const __nv_bfloat16*>(x->data), x->stride_w, reinterpret_cast<const __nv_bfloat16*>(wgt), bias,
         reinterpret_cast<__nv_bfloat16*>(y->data), y->stride_w, act, npix);
     return check_launch("head_fprop_lean_kernel");
@@ -601,7 +610,7 @@ int head_fprop(const b200_tensor* x, const void* wgt, const float* bias, const b
   const size_t smem = sizeof(float) * x->c * y->c;
   B200_DISPATCH_DTYPE(x->dtype, T, {
     B200_HEAD_DISPATCH(y->c, {
-      head_fprop_kernel<T, COUT><<<head_grid(npix, 256 / (x->c / 8)), 256, 0, st>>>(xv, reinterpret_cast<const T*>(wgt), bias, yv, act, npix);
+      launch_pdl(head_fprop_kernel<T, COUT>, head_grid(npix, 256 / (x->c / 8)), 256, 0, st, xv, reinterpret_cast<const T*>(wgt), bias, yv, act, npix);
     });
   });
   return check_launch("head_fprop_kernel");
@@ -613,7 +622,7 @@ int head_dgrad(const b200_tensor* dy, const void* wgt, const b200_tensor* dx, in
   const size_t smem = sizeof(float) * dx->c * dy->c;
   B200_DISPATCH_DTYPE(dx->dtype, T, {
     B200_HEAD_DISPATCH(dy->c, {
-      head_dgrad_kernel<T, COUT><<<head_grid(npix, 256 / (dx->c / 8)), 256, 0, st>>>(dv, reinterpret_cast<const T*>(wgt), xv, accumulate, npix);
+      launch_pdl(head_dgrad_kernel<T, COUT>, head_grid(npix, 256 / (dx->c / 8)), 256, 0, st, dv, reinterpret_cast<const T*>(wgt), xv, accumulate, npix);
     });
   });
   return check_launch("head_dgrad_kernel");
@@ -625,7 +634,7 @@ int head_wgrad(const b200_tensor* x, const b200_tensor* dy, float* dw, cudaStrea
     cudaMemsetAsync(dw, 0, sizeof(float) * 64 * 3, st);
     long long blocks = (npix_i + 4 * 32 - 1) / (4 * 32);
     if (blocks > 4LL * sm_count()) blocks = 4LL * sm_count();
-    head_wgrad_lean_kernel<3, 4><<<(int)blocks, 256, 0, st>>>(
+    launch_pdl(head_wgrad_lean_kernel<3, 4>, (int)blocks, 256, 0, st, 
         reinterpret_cast<const __nv_bfloat16*>(x->data), x->stride_w, reinterpret_cast<const __nv_bfloat16*>(dy->data),
         dy->stride_w, dw, nullptr, npix_i);
     return check_launch("head_wgrad_lean_kernel");
@@ -638,7 +647,7 @@ int head_wgrad(const b200_tensor* x, const b200_tensor* dy, float* dw, cudaStrea
   long long blocks = (npix + ppb - 1) / ppb;
   if (blocks > 6LL * sm_count()) blocks = 6LL * sm_count();
   B200_DISPATCH_DTYPE(x->dtype, T, {
-    B200_HEAD_DISPATCH(dy->c, { head_wgrad_kernel<T, COUT><<<(int)blocks, 256, smem, st>>>(xv, dv, dw, npix); });
+    B200_HEAD_DISPATCH(dy->c, { launch_pdl(head_wgrad_kernel<T, COUT>, (int)blocks, 256, smem, st, xv, dv, dw, npix); });
   });
   return check_launch("head_wgrad_kernel");
 }

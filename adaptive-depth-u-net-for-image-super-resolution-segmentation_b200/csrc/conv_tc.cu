@@ -341,10 +341,6 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
     for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&bar_tmem_full[i]), 1); mbar_init(smem_u32(&bar_tmem_empty[i]), 4 * np); }
     fence_barrier_init();
   }
-  for (int i = threadIdx.x; i < p.Cout; i += blockDim.x) {
-    s_bias[i] = p.bias ? p.bias[i] : 0.f;
-    if (p.ln) { s_bias[p.Cout + i] = p.gamma[i]; s_bias[2 * p.Cout + i] = p.beta[i]; }
-  }
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tm_x); prefetch_tmap(&tm_b);
     if (p.tma_store) { prefetch_tmap(&tm_y); if (p.z) prefetch_tmap(&tm_z); }
@@ -354,6 +350,12 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
     cluster_sync_all();
     if (warp == 1) { tmem_alloc_cg2(smem_u32(&tmem_base_smem), tmem_cols); tmem_relinquish_cg2(); }
   } else if (warp == 1) { tmem_alloc(smem_u32(&tmem_base_smem), tmem_cols); tmem_relinquish(); }
+  // ---- everything above overlapped the previous kernel's tail (PDL); global memory is touched only from here on ----
+  pdl_sync();
+  for (int i = threadIdx.x; i < p.Cout; i += blockDim.x) {
+    s_bias[i] = p.bias ? p.bias[i] : 0.f;
+    if (p.ln) { s_bias[p.Cout + i] = p.gamma[i]; s_bias[2 * p.Cout + i] = p.beta[i]; }
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -968,10 +970,12 @@ int conv_tc_launch(const b200_tensor* x_in, const void* wmat, int cin, int cout,
     cfg.blockDim = dim3(p.ln && p.BN == 64 ? NTHREADS2 : NTHREADS);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl_enabled(2ull * clusters) ? 2 : 1;
     cudaError_t e;
     if (p.ln && p.BN == 64) e = cudaLaunchKernelEx(&cfg, conv3x3_tc_kernel<false, 1, true>, tm_x, tm_b, tm_y, tm_z, p);
     else if (p.ln) e = cudaLaunchKernelEx(&cfg, conv3x3_tc_kernel<false, 2, true>, tm_x, tm_b, tm_y, tm_z, p);
@@ -980,10 +984,10 @@ int conv_tc_launch(const b200_tensor* x_in, const void* wmat, int cin, int cout,
     return check_launch("conv3x3_tc_kernel");
   }
   int grid = p.total_items < sm_count() ? p.total_items : sm_count();
-  if (p.pair) conv3x3_tc_kernel<true, 0><<<grid, NTHREADS, smem, st>>>(tm_x, tm_b, tm_y, tm_z, p);
-  else if (p.ln && p.BN == 64) conv3x3_tc_kernel<false, 1><<<grid, NTHREADS2, smem, st>>>(tm_x, tm_b, tm_y, tm_z, p);
-  else if (p.ln) conv3x3_tc_kernel<false, 2><<<grid, NTHREADS, smem, st>>>(tm_x, tm_b, tm_y, tm_z, p);
-  else conv3x3_tc_kernel<false, 3><<<grid, NTHREADS, smem, st>>>(tm_x, tm_b, tm_y, tm_z, p);
+  if (p.pair) launch_pdl(conv3x3_tc_kernel<true, 0>, grid, NTHREADS, smem, st, tm_x, tm_b, tm_y, tm_z, p);
+  else if (p.ln && p.BN == 64) launch_pdl(conv3x3_tc_kernel<false, 1>, grid, NTHREADS2, smem, st, tm_x, tm_b, tm_y, tm_z, p);
+  else if (p.ln) launch_pdl(conv3x3_tc_kernel<false, 2>, grid, NTHREADS, smem, st, tm_x, tm_b, tm_y, tm_z, p);
+  else launch_pdl(conv3x3_tc_kernel<false, 3>, grid, NTHREADS, smem, st, tm_x, tm_b, tm_y, tm_z, p);
   return check_launch("conv3x3_tc_kernel");
 }
 

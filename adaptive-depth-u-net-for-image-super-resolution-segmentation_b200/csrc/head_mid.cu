@@ -34,6 +34,7 @@ template <int CIN, int CP>
 __global__ void __launch_bounds__(256)
 head_mid_fprop_kernel(const __nv_bfloat16* __restrict__ x, long long x_sw, const __nv_bfloat16* __restrict__ wgt,
                       const float* __restrict__ bias, __nv_bfloat16* __restrict__ y, int cout, int act, long long npix) {
+  pdl_sync();
   __shared__ __align__(16) float w_s[CIN][CP];
   __shared__ float b_s[CP];
   __shared__ __align__(16) __nv_bfloat16 out_s[8][32 * CP];
@@ -94,6 +95,7 @@ template <int CIN, int CP>
 __global__ void __launch_bounds__(256)
 head_mid_dgrad_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ wgt,
                       __nv_bfloat16* __restrict__ dx, long long dx_sw, int cout, int accumulate, long long npix) {
+  pdl_sync();
   __shared__ __align__(16) float w_s[CIN][CP];
   load_weights<CIN, CP>(wgt, cout, w_s);
   __syncthreads();
@@ -138,6 +140,7 @@ template <int CIN, int CP>
 __global__ void __launch_bounds__(256)
 head_mid_wgrad_kernel(const __nv_bfloat16* __restrict__ x, long long x_sw, const __nv_bfloat16* __restrict__ dy,
                       float* __restrict__ dw, int cout, long long npix) {
+  pdl_sync();
   __shared__ __align__(16) float x_s[WG_TP][CIN];
   __shared__ __align__(16) float d_s[WG_TP][CP];
   constexpr int OG = CP / 8;                       // output groups of 8
@@ -225,7 +228,7 @@ bool head_mid_supported(const b200_tensor* x, const b200_tensor* y, int ks) {
 int head_mid_fprop(const b200_tensor* x, const void* wgt, const float* bias, const b200_tensor* y, int act, cudaStream_t st) {
   const long long npix = (long long)x->n * x->h * x->w;
   B200_MID_DISPATCH(x->c, y->c, {
-    head_mid_fprop_kernel<CIN, CP><<<mid_grid(npix, 256, 8), 256, 0, st>>>(
+    launch_pdl(head_mid_fprop_kernel<CIN, CP>, mid_grid(npix, 256, 8), 256, 0, st, 
         reinterpret_cast<const __nv_bfloat16*>(x->data), x->stride_w, reinterpret_cast<const __nv_bfloat16*>(wgt), bias,
         reinterpret_cast<__nv_bfloat16*>(y->data), y->c, act, npix);
   });
@@ -236,7 +239,7 @@ int head_mid_fprop(const b200_tensor* x, const void* wgt, const float* bias, con
 int head_mid_dgrad(const b200_tensor* dy, const void* wgt, const b200_tensor* dx, int accumulate, cudaStream_t st) {
   const long long npix = (long long)dx->n * dx->h * dx->w;
   B200_MID_DISPATCH(dx->c, dy->c, {
-    head_mid_dgrad_kernel<CIN, CP><<<mid_grid(npix, 256, 8), 256, 0, st>>>(
+    launch_pdl(head_mid_dgrad_kernel<CIN, CP>, mid_grid(npix, 256, 8), 256, 0, st, 
         reinterpret_cast<const __nv_bfloat16*>(dy->data), reinterpret_cast<const __nv_bfloat16*>(wgt),
         reinterpret_cast<__nv_bfloat16*>(dx->data), dx->stride_w, dy->c, accumulate, npix);
   });
@@ -247,7 +250,7 @@ int head_mid_wgrad(const b200_tensor* x, const b200_tensor* dy, float* dw, cudaS
   const long long npix = (long long)x->n * x->h * x->w;
   cudaMemsetAsync(dw, 0, sizeof(float) * x->c * dy->c, st);
   B200_MID_DISPATCH(x->c, dy->c, {
-    head_mid_wgrad_kernel<CIN, CP><<<mid_grid(npix, WG_TP, 4), 256, 0, st>>>(
+    launch_pdl(head_mid_wgrad_kernel<CIN, CP>, mid_grid(npix, WG_TP, 4), 256, 0, st, 
         reinterpret_cast<const __nv_bfloat16*>(x->data), x->stride_w, reinterpret_cast<const __nv_bfloat16*>(dy->data), dw,
         dy->c, npix);
   });

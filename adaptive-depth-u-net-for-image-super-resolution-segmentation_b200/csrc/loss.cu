@@ -36,6 +36,7 @@ inline int grid_for(long long items) {
 template <typename TI, typename TR, typename TY>
 __global__ void __launch_bounds__(NT)
 clipadd_fwd_kernel(TView inp, TView res, TView y, long long total) {
+  pdl_sync();
   const TI* ip = reinterpret_cast<const TI*>(inp.data);
   const TR* rp = reinterpret_cast<const TR*>(res.data);
   TY* yp = reinterpret_cast<TY*>(y.data);
@@ -50,6 +51,7 @@ clipadd_fwd_kernel(TView inp, TView res, TView y, long long total) {
 template <typename TI, typename TR>
 __global__ void __launch_bounds__(NT)
 clipadd_bwd_kernel(TView inp, TView res, TView dy, TView dres, long long total) {
+  pdl_sync();
   const TI* ip = reinterpret_cast<const TI*>(inp.data);
   const TR* rp = reinterpret_cast<const TR*>(res.data);
   const TR* dp = reinterpret_cast<const TR*>(dy.data);
@@ -69,6 +71,7 @@ template <typename TP, typename TT>
 __global__ void __launch_bounds__(NT)
 sr_loss_kernel(TView pred, TView tgt, int kind, float eps, float gscale, float* __restrict__ ws, TView dpred,
                long long per_img) {
+  pdl_sync();
   const int n = blockIdx.y;
   const TP* pp = reinterpret_cast<const TP*>(pred.data);
   const TT* tp = reinterpret_cast<const TT*>(tgt.data);
@@ -107,6 +110,7 @@ sr_loss_kernel(TView pred, TView tgt, int kind, float eps, float gscale, float* 
 }
 
 __global__ void sr_loss_finalize_kernel(const float* __restrict__ ws, int n, float total, float per_img, float* out) {
+  pdl_sync();
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   out[0] = ws[0] / total;
   float acc = 0.f;
@@ -119,6 +123,7 @@ __global__ void sr_loss_finalize_kernel(const float* __restrict__ ws, int n, flo
 template <typename TP, typename TT>
 __global__ void __launch_bounds__(NT)
 bce_dice_reduce_kernel(TView pred, TView tgt, float* __restrict__ ws, long long per_img) {
+  pdl_sync();
   const int n = blockIdx.y;
   const TP* pp = reinterpret_cast<const TP*>(pred.data);
   const TT* tp = reinterpret_cast<const TT*>(tgt.data);
@@ -146,6 +151,7 @@ bce_dice_reduce_kernel(TView pred, TView tgt, float* __restrict__ ws, long long 
 
 __global__ void bce_dice_finalize_kernel(const float* __restrict__ ws, int n, float total, float bw, float dw,
                                          float* out) {
+  pdl_sync();
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   const float smooth = 1e-6f;
   float dice = 0.f, iou = 0.f, isum = 0.f, usum = 0.f;
@@ -166,6 +172,7 @@ template <typename TP, typename TT>
 __global__ void __launch_bounds__(NT)
 bce_dice_grad_kernel(TView pred, TView tgt, const float* __restrict__ ws, float bw, float dw, float gscale,
                      float total, TView dpred, long long per_img) {
+  pdl_sync();
   const int n = blockIdx.y;
   const TP* pp = reinterpret_cast<const TP*>(pred.data);
   const TT* tp = reinterpret_cast<const TT*>(tgt.data);
@@ -196,6 +203,7 @@ bce_dice_grad_kernel(TView pred, TView tgt, const float* __restrict__ ws, float 
 template <typename TP, typename TT>
 __global__ void __launch_bounds__(NT)
 binary_confusion_kernel(TView pred, TView tgt, float threshold, float* __restrict__ counts, long long total) {
+  pdl_sync();
   const TP* pp = reinterpret_cast<const TP*>(pred.data);
   const TT* tp = reinterpret_cast<const TT*>(tgt.data);
   float c_tp = 0.f, c_fp = 0.f, c_fn = 0.f, c_ok = 0.f;
@@ -222,6 +230,7 @@ binary_confusion_kernel(TView pred, TView tgt, float threshold, float* __restric
 template <typename T>
 __global__ void __launch_bounds__(NT)
 softmax_fwd_kernel(TView z, TView p, long long npix) {
+  pdl_sync();
   const T* zp = reinterpret_cast<const T*>(z.data);
   T* pp = reinterpret_cast<T*>(p.data);
   const int C = z.c;
@@ -244,6 +253,7 @@ template <typename T>
 __global__ void __launch_bounds__(NT)
 softmax_ce_kernel(TView prob, const int* __restrict__ labels, float gscale, float* __restrict__ ws, TView dz,
                   long long npix) {
+  pdl_sync();
   const T* pp = reinterpret_cast<const T*>(prob.data);
   T* gp = reinterpret_cast<T*>(dz.data);
   const int C = prob.c;
@@ -277,6 +287,7 @@ softmax_ce_kernel(TView prob, const int* __restrict__ labels, float gscale, floa
 }
 
 __global__ void mean_finalize_kernel(const float* ws, float total, float* out) {
+  pdl_sync();
   if (threadIdx.x == 0 && blockIdx.x == 0) out[0] = ws[0] / total;
 }
 
@@ -296,7 +307,7 @@ int clipadd_fwd(const b200_tensor* inp, const b200_tensor* res, const b200_tenso
   long long total = (long long)y->n * y->h * y->w * y->c;
   TView iv = view_of(inp), rv = view_of(res), yv = view_of(y);
   B200_DISPATCH_2(inp->dtype, res->dtype, TI, TR, {
-    clipadd_fwd_kernel<TI, TR, TR><<<grid_for(total), NT, 0, st>>>(iv, rv, yv, total);
+    launch_pdl(clipadd_fwd_kernel<TI, TR, TR>, grid_for(total), NT, 0, st, iv, rv, yv, total);
   });
   return check_launch("clipadd_fwd_kernel");
 }
@@ -309,7 +320,7 @@ int clipadd_bwd(const b200_tensor* inp, const b200_tensor* res, const b200_tenso
   long long total = (long long)dy->n * dy->h * dy->w * dy->c;
   TView iv = view_of(inp), rv = view_of(res), dv = view_of(dy), ov = view_of(dres);
   B200_DISPATCH_2(inp->dtype, res->dtype, TI, TR, {
-    clipadd_bwd_kernel<TI, TR><<<grid_for(total), NT, 0, st>>>(iv, rv, dv, ov, total);
+    launch_pdl(clipadd_bwd_kernel<TI, TR>, grid_for(total), NT, 0, st, iv, rv, dv, ov, total);
   });
   return check_launch("clipadd_bwd_kernel");
 }
@@ -331,9 +342,9 @@ int sr_loss(const b200_tensor* pred, const b200_tensor* target, int kind, float 
   if (bx > 64) bx = 64;
   dim3 grid((unsigned)bx, pred->n);
   B200_DISPATCH_2(pred->dtype, target->dtype, TP, TT, {
-    sr_loss_kernel<TP, TT><<<grid, NT, 0, st>>>(pv, tv, kind, eps, grad_scale / total, ws, gv, per_img);
+    launch_pdl(sr_loss_kernel<TP, TT>, grid, NT, 0, st, pv, tv, kind, eps, grad_scale / total, ws, gv, per_img);
   });
-  sr_loss_finalize_kernel<<<1, 32, 0, st>>>(ws, pred->n, total, (float)per_img, out);
+  launch_pdl(sr_loss_finalize_kernel, 1, 32, 0, st, ws, pred->n, total, (float)per_img, out);
   count_launches(1);
   return check_launch("sr_loss_kernel");
 }
@@ -349,11 +360,11 @@ int bce_dice_loss(const b200_tensor* pred, const b200_tensor* target, float bw, 
   if (bx > 64) bx = 64;
   dim3 grid((unsigned)bx, pred->n);
   B200_DISPATCH_2(pred->dtype, target->dtype, TP, TT, {
-    bce_dice_reduce_kernel<TP, TT><<<grid, NT, 0, st>>>(pv, tv, ws, per_img);
-    bce_dice_finalize_kernel<<<1, 32, 0, st>>>(ws, pred->n, total, bw, dw, out);
+    launch_pdl(bce_dice_reduce_kernel<TP, TT>, grid, NT, 0, st, pv, tv, ws, per_img);
+    launch_pdl(bce_dice_finalize_kernel, 1, 32, 0, st, ws, pred->n, total, bw, dw, out);
     if (dpred && dpred->data) {
       TView gv = view_of(dpred);
-      bce_dice_grad_kernel<TP, TT><<<grid, NT, 0, st>>>(pv, tv, ws, bw, dw, grad_scale, total, gv, per_img);
+      launch_pdl(bce_dice_grad_kernel<TP, TT>, grid, NT, 0, st, pv, tv, ws, bw, dw, grad_scale, total, gv, per_img);
     }
   });
   count_launches((dpred && dpred->data) ? 2 : 1);
@@ -366,7 +377,7 @@ int binary_confusion(const b200_tensor* pred, const b200_tensor* target, float t
   cudaMemsetAsync(counts, 0, sizeof(float) * 4, st);
   TView pv = view_of(pred), tv = view_of(target);
   B200_DISPATCH_2(pred->dtype, target->dtype, TP, TT, {
-    binary_confusion_kernel<TP, TT><<<grid_for(total), NT, 0, st>>>(pv, tv, threshold, counts, total);
+    launch_pdl(binary_confusion_kernel<TP, TT>, grid_for(total), NT, 0, st, pv, tv, threshold, counts, total);
   });
   return check_launch("binary_confusion_kernel");
 }
@@ -375,7 +386,7 @@ int softmax_fwd(const b200_tensor* z, const b200_tensor* p, cudaStream_t st) {
   B200_REQUIRE(same_shape(z, p) && z->dtype == p->dtype, B200_ERR_BAD_ARG, "softmax_fwd: shape/dtype mismatch");
   const long long npix = (long long)z->n * z->h * z->w;
   TView zv = view_of(z), pv = view_of(p);
-  B200_DISPATCH_DTYPE(z->dtype, T, { softmax_fwd_kernel<T><<<grid_for(npix), NT, 0, st>>>(zv, pv, npix); });
+  B200_DISPATCH_DTYPE(z->dtype, T, { launch_pdl(softmax_fwd_kernel<T>, grid_for(npix), NT, 0, st, zv, pv, npix); });
   return check_launch("softmax_fwd_kernel");
 }
 
@@ -391,9 +402,9 @@ int softmax_ce_loss(const b200_tensor* prob, const int32_t* labels, float grad_s
   }
   cudaMemsetAsync(ws, 0, sizeof(float), st);
   B200_DISPATCH_DTYPE(prob->dtype, T, {
-    softmax_ce_kernel<T><<<grid_for(npix), NT, 0, st>>>(pv, labels, grad_scale, ws, gv, npix);
+    launch_pdl(softmax_ce_kernel<T>, grid_for(npix), NT, 0, st, pv, labels, grad_scale, ws, gv, npix);
   });
-  mean_finalize_kernel<<<1, 32, 0, st>>>(ws, (float)npix, out);
+  launch_pdl(mean_finalize_kernel, 1, 32, 0, st, ws, (float)npix, out);
   count_launches(1);
   return check_launch("softmax_ce_kernel");
 }

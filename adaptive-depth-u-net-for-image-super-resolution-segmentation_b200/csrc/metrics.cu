@@ -15,6 +15,7 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 luma_pair_kernel(TView pred, TView hr, int shave, float* __restrict__ pred_y, float* __restrict__ hr_y,
                  float* __restrict__ sse) {
+  pdl_sync();
   const int oh = pred.h - 2 * shave, ow = pred.w - 2 * shave;
   const int n = blockIdx.y;
   const int plane = oh * ow;
@@ -57,7 +58,7 @@ int luma_pair(const b200_tensor* pred, const b200_tensor* hr, int shave, float* 
   if (bx > 64) bx = 64;
   dim3 grid(bx, pred->n);
   const TView pv = view_of(pred), hv = view_of(hr);
-  B200_DISPATCH_DTYPE(pred->dtype, T, { luma_pair_kernel<T><<<grid, 256, 0, st>>>(pv, hv, shave, pred_y, hr_y, sse); });
+  B200_DISPATCH_DTYPE(pred->dtype, T, { launch_pdl(luma_pair_kernel<T>, grid, 256, 0, st, pv, hv, shave, pred_y, hr_y, sse); });
   return check_launch("luma_pair_kernel");
 }
 
@@ -68,6 +69,7 @@ struct Gauss { float g[kWin]; };
 __global__ void __launch_bounds__(256)
 ssim_kernel(const float* __restrict__ a, const float* __restrict__ b, int h, int w, int ch, Gauss gw, float c1, float c2,
             float* __restrict__ out) {
+  pdl_sync();
   __shared__ float sa[kIn][kIn + 1], sb[kIn][kIn + 1];
   __shared__ float hz[5][kIn][kTile];      // horizontally filtered a, b, a*a, b*b, a*b
   __shared__ float red[2][8];
@@ -141,13 +143,14 @@ int ssim_planes(const float* a, const float* b, int n, int h, int w, int ch, flo
   cudaMemsetAsync(out, 0, sizeof(float) * 2 * n * ch, st);
   const int vh = h - kWin + 1, vw = w - kWin + 1;
   dim3 grid((vw + kTile - 1) / kTile, (vh + kTile - 1) / kTile, n * ch);
-  ssim_kernel<<<grid, 256, 0, st>>>(a, b, h, w, ch, gw, c1, c2, out);
+  launch_pdl(ssim_kernel, grid, 256, 0, st, a, b, h, w, ch, gw, c1, c2, out);
   return check_launch("ssim_kernel");
 }
 
 // ---- 2x2 average pooling between MS-SSIM scales ---------------------------------------------------
 __global__ void __launch_bounds__(256)
 avgpool2_planes_kernel(const float* __restrict__ x, int n, int h, int w, int ch, float* __restrict__ y) {
+  pdl_sync();
   const int oh = (h + 1) / 2, ow = (w + 1) / 2;
   const long long total = (long long)n * oh * ow * ch;      // channel-interleaved [n][h][w][ch] -> [n][oh][ow][ch]
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -166,7 +169,7 @@ int avgpool2_planes(const float* x, int n, int h, int w, int ch, float* y, cudaS
   const long long total = (long long)n * ((h + 1) / 2) * ((w + 1) / 2) * ch;
   long long want = (total + 255) / 256;
   const int grid = (int)(want < (long long)sm_count() * 16 ? want : (long long)sm_count() * 16);
-  avgpool2_planes_kernel<<<grid, 256, 0, st>>>(x, n, h, w, ch, y);
+  launch_pdl(avgpool2_planes_kernel, grid, 256, 0, st, x, n, h, w, ch, y);
   return check_launch("avgpool2_planes_kernel");
 }
 

@@ -52,6 +52,7 @@ template <typename T, int CPT>
 __global__ void __launch_bounds__(NT)
 ln_fwd_kernel(TView z, const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int relu,
               TView y, float* __restrict__ mean_out, float* __restrict__ rstd_out, int tpp, long long npix) {
+  pdl_sync();
   const int lane_g = threadIdx.x % tpp;
   const int ppb = NT / tpp;
   const int C = z.c, chunks = C / 8;
@@ -126,6 +127,7 @@ ln_bwd_kernel(TView dy, TView z, const float* __restrict__ mean, const float* __
               const float* __restrict__ gamma, const float* __restrict__ beta, int relu, TView dz,
               float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dbias, int tpp,
               long long npix) {
+  pdl_sync();
   __shared__ float s_acc[NT * 8];
   const int lane_g = threadIdx.x % tpp;
   const int ppb = NT / tpp;
@@ -230,6 +232,7 @@ ln_bwd_lean_kernel(const __nv_bfloat16* __restrict__ dy, long long dy_sw, const 
                    const float* __restrict__ gamma, const float* __restrict__ beta, int relu,
                    __nv_bfloat16* __restrict__ dz, long long dz_sw, float* __restrict__ dgamma,
                    float* __restrict__ dbeta, float* __restrict__ dbias, int npix) {
+  pdl_sync();
   constexpr int C = 8 * TPP, PPB = NT / TPP;
   __shared__ float s_acc[NT * 8];
   const int lane_g = threadIdx.x % TPP;
@@ -322,6 +325,7 @@ ln_bwd_lean_kernel(const __nv_bfloat16* __restrict__ dy, long long dy_sw, const 
 template <typename T>
 __global__ void __launch_bounds__(NT)
 bias_act_bwd_kernel(TView dy, TView y, int act, TView dz, float* __restrict__ dbias, long long total) {
+  pdl_sync();
   extern __shared__ float s_acc[];  // [C]
   const int C = y.c;
   for (int i = threadIdx.x; i < C; i += NT) s_acc[i] = 0.f;
@@ -349,6 +353,7 @@ bias_act_bwd_kernel(TView dy, TView y, int act, TView dz, float* __restrict__ db
 template <typename T, int C>
 __global__ void __launch_bounds__(NT)
 bias_act_bwd_narrow_kernel(TView dy, TView y, int act, TView dz, float* __restrict__ dbias, long long npix) {
+  pdl_sync();
   const T* dyp = reinterpret_cast<const T*>(dy.data);
   const T* yp = reinterpret_cast<const T*>(y.data);
   T* dzp = reinterpret_cast<T*>(dz.data);
@@ -380,6 +385,7 @@ bias_act_bwd_narrow_kernel(TView dy, TView y, int act, TView dz, float* __restri
 template <typename T>
 __global__ void __launch_bounds__(NT)
 bias_act_bwd_vec_kernel(TView dy, TView y, int act, TView dz, float* __restrict__ dbias, long long npix) {
+  pdl_sync();
   extern __shared__ float s_acc[];
   const int C = y.c, chunks = C / 8;
   for (int i = threadIdx.x; i < C; i += NT) s_acc[i] = 0.f;
@@ -421,6 +427,7 @@ __global__ void __launch_bounds__(NT)
 bn_stats_kernel(TView z, TView dy, const float* __restrict__ mean, const float* __restrict__ rstd,
                 const float* __restrict__ gamma, const float* __restrict__ beta, int relu,
                 double* __restrict__ stats, long long npix) {
+  pdl_sync();
   extern __shared__ float s_acc[];  // [2][C]
   const int C = z.c;
   for (int i = threadIdx.x; i < 2 * C; i += NT) s_acc[i] = 0.f;
@@ -457,6 +464,7 @@ bn_stats_kernel(TView z, TView dy, const float* __restrict__ mean, const float* 
 
 __global__ void bn_finalize_kernel(const double* __restrict__ stats, int C, double count, float eps, float momentum,
                                    float* save_mean, float* save_rstd, float* moving_mean, float* moving_var) {
+  pdl_sync();
   int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   double m = stats[c] / count;
@@ -473,6 +481,7 @@ __global__ void __launch_bounds__(NT)
 bn_apply_kernel(TView z, const float* __restrict__ mean, const float* __restrict__ rstd,
                 const float* __restrict__ gamma, const float* __restrict__ beta, int relu, TView y,
                 long long total, const float* __restrict__ mmean, const float* __restrict__ mvar, float eps) {
+  pdl_sync();
   const int C = z.c;
   const T* zp = reinterpret_cast<const T*>(z.data);
   T* yp = reinterpret_cast<T*>(y.data);
@@ -493,6 +502,7 @@ __global__ void __launch_bounds__(NT)
 bn_bwd_apply_kernel(TView dy, TView z, const float* __restrict__ mean, const float* __restrict__ rstd,
                     const float* __restrict__ gamma, const float* __restrict__ beta, int relu, TView dz,
                     const double* __restrict__ stats, double count, long long total) {
+  pdl_sync();
   const int C = z.c;
   const T* zp = reinterpret_cast<const T*>(z.data);
   const T* dyp = reinterpret_cast<const T*>(dy.data);
@@ -511,6 +521,7 @@ bn_bwd_apply_kernel(TView dy, TView z, const float* __restrict__ mean, const flo
 }
 
 __global__ void bn_bwd_params_kernel(const double* __restrict__ stats, int C, float* dgamma, float* dbeta) {
+  pdl_sync();
   int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   if (dbeta) dbeta[c] += (float)stats[c];
@@ -543,10 +554,10 @@ int layernorm_fwd(const b200_tensor* z, const float* gamma, const float* beta, f
   const int grid = grid_for(npix, NT / tpp);
   TView zv = view_of(z), yv = view_of(y);
   B200_DISPATCH_DTYPE(z->dtype, T, {
-    if (cpt == 1) ln_fwd_kernel<T, 1><<<grid, NT, 0, st>>>(zv, gamma, beta, eps, relu, yv, mean, rstd, tpp, npix);
-    else if (cpt == 2) ln_fwd_kernel<T, 2><<<grid, NT, 0, st>>>(zv, gamma, beta, eps, relu, yv, mean, rstd, tpp, npix);
-    else if (cpt <= 4) ln_fwd_kernel<T, 4><<<grid, NT, 0, st>>>(zv, gamma, beta, eps, relu, yv, mean, rstd, tpp, npix);
-    else ln_fwd_kernel<T, 8><<<grid, NT, 0, st>>>(zv, gamma, beta, eps, relu, yv, mean, rstd, tpp, npix);
+    if (cpt == 1) launch_pdl(ln_fwd_kernel<T, 1>, grid, NT, 0, st, zv, gamma, beta, eps, relu, yv, mean, rstd, tpp, npix);
+    else if (cpt == 2) launch_pdl(ln_fwd_kernel<T, 2>, grid, NT, 0, st, zv, gamma, beta, eps, relu, yv, mean, rstd, tpp, npix);
+    else if (cpt <= 4) launch_pdl(ln_fwd_kernel<T, 4>, grid, NT, 0, st, zv, gamma, beta, eps, relu, yv, mean, rstd, tpp, npix);
+    else launch_pdl(ln_fwd_kernel<T, 8>, grid, NT, 0, st, zv, gamma, beta, eps, relu, yv, mean, rstd, tpp, npix);
   });
   return check_launch("ln_fwd_kernel");
 }
@@ -581,16 +592,16 @@ int layernorm_bwd(const b200_tensor* dy, const b200_tensor* z, const float* mean
     const __nv_bfloat16* dyp = reinterpret_cast<const __nv_bfloat16*>(dy->data);
     const __nv_bfloat16* zp = reinterpret_cast<const __nv_bfloat16*>(z->data);
     __nv_bfloat16* dzp = reinterpret_cast<__nv_bfloat16*>(dz->data);
-    if (C == 64) ln_bwd_lean_kernel<8><<<gridl, NT, 0, st>>>(dyp, dy->stride_w, zp, z->stride_w, mean, rstd, gamma, beta, relu, dzp, dz->stride_w, dgamma, dbeta, dbias, (int)npix);
-    else if (C == 128) ln_bwd_lean_kernel<16><<<gridl, NT, 0, st>>>(dyp, dy->stride_w, zp, z->stride_w, mean, rstd, gamma, beta, relu, dzp, dz->stride_w, dgamma, dbeta, dbias, (int)npix);
-    else ln_bwd_lean_kernel<32><<<gridl, NT, 0, st>>>(dyp, dy->stride_w, zp, z->stride_w, mean, rstd, gamma, beta, relu, dzp, dz->stride_w, dgamma, dbeta, dbias, (int)npix);
+    if (C == 64) launch_pdl(ln_bwd_lean_kernel<8>, gridl, NT, 0, st, dyp, dy->stride_w, zp, z->stride_w, mean, rstd, gamma, beta, relu, dzp, dz->stride_w, dgamma, dbeta, dbias, (int)npix);
+    else if (C == 128) launch_pdl(ln_bwd_lean_kernel<16>, gridl, NT, 0, st, dyp, dy->stride_w, zp, z->stride_w, mean, rstd, gamma, beta, relu, dzp, dz->stride_w, dgamma, dbeta, dbias, (int)npix);
+    else launch_pdl(ln_bwd_lean_kernel<32>, gridl, NT, 0, st, dyp, dy->stride_w, zp, z->stride_w, mean, rstd, gamma, beta, relu, dzp, dz->stride_w, dgamma, dbeta, dbias, (int)npix);
     return check_launch("ln_bwd_lean_kernel");
   }
   B200_DISPATCH_DTYPE(z->dtype, T, {
-    if (cpt == 1) ln_bwd_kernel<T, 1><<<grid, NT, smem, st>>>(dyv, zv, mean, rstd, gamma, beta, relu, dzv, dgamma, dbeta, dbias, tpp, npix);
-    else if (cpt == 2) ln_bwd_kernel<T, 2><<<grid, NT, smem, st>>>(dyv, zv, mean, rstd, gamma, beta, relu, dzv, dgamma, dbeta, dbias, tpp, npix);
-    else if (cpt <= 4) ln_bwd_kernel<T, 4><<<grid, NT, smem, st>>>(dyv, zv, mean, rstd, gamma, beta, relu, dzv, dgamma, dbeta, dbias, tpp, npix);
-    else ln_bwd_kernel<T, 8><<<grid, NT, smem, st>>>(dyv, zv, mean, rstd, gamma, beta, relu, dzv, dgamma, dbeta, dbias, tpp, npix);
+    if (cpt == 1) launch_pdl(ln_bwd_kernel<T, 1>, grid, NT, smem, st, dyv, zv, mean, rstd, gamma, beta, relu, dzv, dgamma, dbeta, dbias, tpp, npix);
+    else if (cpt == 2) launch_pdl(ln_bwd_kernel<T, 2>, grid, NT, smem, st, dyv, zv, mean, rstd, gamma, beta, relu, dzv, dgamma, dbeta, dbias, tpp, npix);
+    else if (cpt <= 4) launch_pdl(ln_bwd_kernel<T, 4>, grid, NT, smem, st, dyv, zv, mean, rstd, gamma, beta, relu, dzv, dgamma, dbeta, dbias, tpp, npix);
+    else launch_pdl(ln_bwd_kernel<T, 8>, grid, NT, smem, st, dyv, zv, mean, rstd, gamma, beta, relu, dzv, dgamma, dbeta, dbias, tpp, npix);
   });
   return check_launch("ln_bwd_kernel");
 }
@@ -618,17 +629,17 @@ int bias_act_bwd(const b200_tensor* dy, const b200_tensor* y, int act, const b20
   B200_DISPATCH_DTYPE(y->dtype, T, {
     if (C == 1 || C == 3) {
       const int grid = grid_for(npix, NT);
-      if (C == 1) bias_act_bwd_narrow_kernel<T, 1><<<grid, NT, 0, st>>>(dyv, yv, act, dzv, dbias, npix);
-      else bias_act_bwd_narrow_kernel<T, 3><<<grid, NT, 0, st>>>(dyv, yv, act, dzv, dbias, npix);
+      if (C == 1) launch_pdl(bias_act_bwd_narrow_kernel<T, 1>, grid, NT, 0, st, dyv, yv, act, dzv, dbias, npix);
+      else launch_pdl(bias_act_bwd_narrow_kernel<T, 3>, grid, NT, 0, st, dyv, yv, act, dzv, dbias, npix);
     } else if (vec) {
       long long blocks = (npix + (NT / (C / 8)) - 1) / (NT / (C / 8));
       long long cap = 4LL * sm_count();
       int grid = (int)(blocks < cap ? (blocks < 1 ? 1 : blocks) : cap);
-      bias_act_bwd_vec_kernel<T><<<grid, NT, smem, st>>>(dyv, yv, act, dzv, dbias, npix);
+      launch_pdl(bias_act_bwd_vec_kernel<T>, grid, NT, smem, st, dyv, yv, act, dzv, dbias, npix);
     } else {
       long long total = npix * C;
       int grid = grid_for(total, NT);
-      bias_act_bwd_kernel<T><<<grid, NT, smem, st>>>(dyv, yv, act, dzv, dbias, total);
+      launch_pdl(bias_act_bwd_kernel<T>, grid, NT, smem, st, dyv, yv, act, dzv, dbias, total);
     }
   });
   return check_launch("bias_act_bwd_kernel");
@@ -644,9 +655,9 @@ int batchnorm_fwd_train(const b200_tensor* z, const float* gamma, const float* b
   TView zv = view_of(z), yv = view_of(y);
   const int sgrid = grid_for(npix, 64);
   B200_DISPATCH_DTYPE(z->dtype, T, {
-    bn_stats_kernel<T, 0><<<sgrid, NT, sizeof(float) * 2 * C, st>>>(zv, zv, nullptr, nullptr, nullptr, nullptr, 0, stats_ws, npix);
-    bn_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(stats_ws, C, (double)npix, eps, momentum, save_mean, save_rstd, moving_mean, moving_var);
-    bn_apply_kernel<T><<<grid_for(npix * C, NT), NT, 0, st>>>(zv, save_mean, save_rstd, gamma, beta, relu, yv, npix * C, nullptr, nullptr, eps);
+    launch_pdl(bn_stats_kernel<T, 0>, sgrid, NT, sizeof(float) * 2 * C, st, zv, zv, nullptr, nullptr, nullptr, nullptr, 0, stats_ws, npix);
+    launch_pdl(bn_finalize_kernel, (C + 127) / 128, 128, 0, st, stats_ws, C, (double)npix, eps, momentum, save_mean, save_rstd, moving_mean, moving_var);
+    launch_pdl(bn_apply_kernel<T>, grid_for(npix * C, NT), NT, 0, st, zv, save_mean, save_rstd, gamma, beta, relu, yv, npix * C, nullptr, nullptr, eps);
   });
   count_launches(2);
   return check_launch("batchnorm_fwd_train");
@@ -664,7 +675,7 @@ int batchnorm_stats(const b200_tensor* z, const b200_tensor* dy, const float* sa
   TView zv = view_of(z);
   if (!dy) {
     B200_DISPATCH_DTYPE(z->dtype, T, {
-      bn_stats_kernel<T, 0><<<grid_for(npix, 64), NT, sizeof(float) * 2 * C, st>>>(zv, zv, nullptr, nullptr, nullptr, nullptr, 0, stats_ws, npix);
+      launch_pdl(bn_stats_kernel<T, 0>, grid_for(npix, 64), NT, sizeof(float) * 2 * C, st, zv, zv, nullptr, nullptr, nullptr, nullptr, 0, stats_ws, npix);
     });
     return check_launch("bn_stats_kernel");
   }
@@ -672,9 +683,9 @@ int batchnorm_stats(const b200_tensor* z, const b200_tensor* dy, const float* sa
                "batchnorm_stats (backward): dy / statistics missing or mismatched");
   TView dyv = view_of(dy);
   B200_DISPATCH_DTYPE(z->dtype, T, {
-    bn_stats_kernel<T, 1><<<grid_for(npix, 64), NT, sizeof(float) * 2 * C, st>>>(zv, dyv, save_mean, save_rstd, gamma, beta, relu, stats_ws, npix);
+    launch_pdl(bn_stats_kernel<T, 1>, grid_for(npix, 64), NT, sizeof(float) * 2 * C, st, zv, dyv, save_mean, save_rstd, gamma, beta, relu, stats_ws, npix);
   });
-  bn_bwd_params_kernel<<<(C + 127) / 128, 128, 0, st>>>(stats_ws, C, dgamma, dbeta);
+  launch_pdl(bn_bwd_params_kernel, (C + 127) / 128, 128, 0, st, stats_ws, C, dgamma, dbeta);
   count_launches(1);
   return check_launch("bn_stats_kernel");
 }
@@ -686,9 +697,9 @@ int batchnorm_fwd_apply(const b200_tensor* z, const float* gamma, const float* b
   const int C = z->c;
   const long long npix = (long long)z->n * z->h * z->w;
   TView zv = view_of(z), yv = view_of(y);
-  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(stats_ws, C, count, eps, momentum, save_mean, save_rstd, moving_mean, moving_var);
+  launch_pdl(bn_finalize_kernel, (C + 127) / 128, 128, 0, st, stats_ws, C, count, eps, momentum, save_mean, save_rstd, moving_mean, moving_var);
   B200_DISPATCH_DTYPE(z->dtype, T, {
-    bn_apply_kernel<T><<<grid_for(npix * C, NT), NT, 0, st>>>(zv, save_mean, save_rstd, gamma, beta, relu, yv, npix * C, nullptr, nullptr, eps);
+    launch_pdl(bn_apply_kernel<T>, grid_for(npix * C, NT), NT, 0, st, zv, save_mean, save_rstd, gamma, beta, relu, yv, npix * C, nullptr, nullptr, eps);
   });
   count_launches(1);
   return check_launch("batchnorm_fwd_apply");
@@ -702,7 +713,7 @@ int batchnorm_bwd_apply(const b200_tensor* dy, const b200_tensor* z, const float
   const long long npix = (long long)z->n * z->h * z->w;
   TView zv = view_of(z), dyv = view_of(dy), dzv = view_of(dz);
   B200_DISPATCH_DTYPE(z->dtype, T, {
-    bn_bwd_apply_kernel<T><<<grid_for(npix * z->c, NT), NT, 0, st>>>(dyv, zv, save_mean, save_rstd, gamma, beta, relu, dzv, stats_ws, count, npix * z->c);
+    launch_pdl(bn_bwd_apply_kernel<T>, grid_for(npix * z->c, NT), NT, 0, st, dyv, zv, save_mean, save_rstd, gamma, beta, relu, dzv, stats_ws, count, npix * z->c);
   });
   return check_launch("batchnorm_bwd_apply");
 }
@@ -713,7 +724,7 @@ int batchnorm_fwd_infer(const b200_tensor* z, const float* gamma, const float* b
   const long long total = (long long)z->n * z->h * z->w * z->c;
   TView zv = view_of(z), yv = view_of(y);
   B200_DISPATCH_DTYPE(z->dtype, T, {
-    bn_apply_kernel<T><<<grid_for(total, NT), NT, 0, st>>>(zv, nullptr, nullptr, gamma, beta, relu, yv, total, moving_mean, moving_var, eps);
+    launch_pdl(bn_apply_kernel<T>, grid_for(total, NT), NT, 0, st, zv, nullptr, nullptr, gamma, beta, relu, yv, total, moving_mean, moving_var, eps);
   });
   return check_launch("batchnorm_fwd_infer");
 }
@@ -729,9 +740,9 @@ int batchnorm_bwd(const b200_tensor* dy, const b200_tensor* z, const float* save
   cudaMemsetAsync(stats_ws, 0, sizeof(double) * 2 * C, st);
   TView zv = view_of(z), dyv = view_of(dy), dzv = view_of(dz);
   B200_DISPATCH_DTYPE(z->dtype, T, {
-    bn_stats_kernel<T, 1><<<grid_for(npix, 64), NT, sizeof(float) * 2 * C, st>>>(zv, dyv, save_mean, save_rstd, gamma, beta, relu, stats_ws, npix);
-    bn_bwd_apply_kernel<T><<<grid_for(npix * C, NT), NT, 0, st>>>(dyv, zv, save_mean, save_rstd, gamma, beta, relu, dzv, stats_ws, (double)npix, npix * C);
-    bn_bwd_params_kernel<<<(C + 127) / 128, 128, 0, st>>>(stats_ws, C, dgamma, dbeta);
+    launch_pdl(bn_stats_kernel<T, 1>, grid_for(npix, 64), NT, sizeof(float) * 2 * C, st, zv, dyv, save_mean, save_rstd, gamma, beta, relu, stats_ws, npix);
+    launch_pdl(bn_bwd_apply_kernel<T>, grid_for(npix * C, NT), NT, 0, st, dyv, zv, save_mean, save_rstd, gamma, beta, relu, dzv, stats_ws, (double)npix, npix * C);
+    launch_pdl(bn_bwd_params_kernel, (C + 127) / 128, 128, 0, st, stats_ws, C, dgamma, dbeta);
   });
   count_launches(2);
   return check_launch("batchnorm_bwd");

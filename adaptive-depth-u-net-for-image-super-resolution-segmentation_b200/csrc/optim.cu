@@ -23,20 +23,24 @@ inline int grid_for(long long items, int per_thread = 1) {
 // The loss gradient is multiplied by `scale`; a step whose gradients hold an inf / nan is skipped (no moment, weight or
 // step-counter update) and halves the scale; `growth` finite steps in a row double it.
 __global__ void adam_advance_kernel(int* step, const float* __restrict__ ls) {
+  pdl_sync();
   if (threadIdx.x == 0 && blockIdx.x == 0 && !(ls && ls[2] != 0.f)) *step += 1;
 }
 
 __global__ void __launch_bounds__(NT) scale_by_device_kernel(float* p, size_t count, const float* __restrict__ ls) {
+  pdl_sync();
   const float s = ls[0];
   for (size_t i = (size_t)blockIdx.x * NT + threadIdx.x; i < count; i += (size_t)gridDim.x * NT) p[i] *= s;
 }
 __global__ void __launch_bounds__(NT) scale_by_device_bf16_kernel(__nv_bfloat16* p, size_t count, const float* __restrict__ ls) {
+  pdl_sync();
   const float s = ls[0];
   for (size_t i = (size_t)blockIdx.x * NT + threadIdx.x; i < count; i += (size_t)gridDim.x * NT)
     p[i] = __float2bfloat16_rn(__bfloat162float(p[i]) * s);
 }
 
 __global__ void __launch_bounds__(NT) finite_check_kernel(const float* __restrict__ g, size_t count, float* __restrict__ ls) {
+  pdl_sync();
   bool bad = false;
   const size_t n4 = count / 4;
   for (size_t i = (size_t)blockIdx.x * NT + threadIdx.x; i < n4; i += (size_t)gridDim.x * NT) {
@@ -48,6 +52,7 @@ __global__ void __launch_bounds__(NT) finite_check_kernel(const float* __restric
 }
 
 __global__ void loss_scale_update_kernel(float* ls, float growth) {
+  pdl_sync();
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   if (ls[2] != 0.f) {
     ls[0] = fmaxf(ls[0] * 0.5f, 1.f);
@@ -65,6 +70,7 @@ __global__ void __launch_bounds__(NT)
 adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
             size_t count, const float* __restrict__ hyper, const int* __restrict__ step,
             __nv_bfloat16* __restrict__ shadow, const float* __restrict__ ls) {
+  pdl_sync();
   if (ls && ls[2] != 0.f) return;                 // loss scaling: a non-finite gradient skips the whole step
   const float inv_scale = ls ? 1.f / ls[0] : 1.f;
   const float lr = hyper[0], b1 = hyper[1], b2 = hyper[2], eps = hyper[3];
@@ -109,11 +115,13 @@ adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restric
 
 template <typename TS, typename TD>
 __global__ void __launch_bounds__(NT) cast_kernel(const TS* __restrict__ s, TD* __restrict__ d, size_t count) {
+  pdl_sync();
   for (size_t i = (size_t)blockIdx.x * NT + threadIdx.x; i < count; i += (size_t)gridDim.x * NT) stf(d + i, ldf(s + i));
 }
 
 template <typename TS, typename TD>
 __global__ void __launch_bounds__(NT) copy_tensor_kernel(TView s, TView d, long long total) {
+  pdl_sync();
   const TS* sp = reinterpret_cast<const TS*>(s.data);
   TD* dp = reinterpret_cast<TD*>(d.data);
   for (long long i = (long long)blockIdx.x * NT + threadIdx.x; i < total; i += (long long)gridDim.x * NT) {
@@ -127,6 +135,7 @@ __global__ void __launch_bounds__(NT) copy_tensor_kernel(TView s, TView d, long 
 }
 
 __global__ void __launch_bounds__(NT) scale_kernel(float* p, size_t count, float s) {
+  pdl_sync();
   for (size_t i = (size_t)blockIdx.x * NT + threadIdx.x; i < count; i += (size_t)gridDim.x * NT) p[i] *= s;
 }
 
@@ -134,6 +143,7 @@ __global__ void __launch_bounds__(NT) scale_kernel(float* p, size_t count, float
 template <typename T>
 __global__ void __launch_bounds__(NT)
 convT2_fprop_kernel(TView x, const T* __restrict__ k, const float* __restrict__ bias, TView y, long long total) {
+  pdl_sync();
   const T* xp = reinterpret_cast<const T*>(x.data);
   T* yp = reinterpret_cast<T*>(y.data);
   const int Cin = x.c, Cout = y.c;
@@ -154,6 +164,7 @@ convT2_fprop_kernel(TView x, const T* __restrict__ k, const float* __restrict__ 
 template <typename T>
 __global__ void __launch_bounds__(NT)
 convT2_dgrad_kernel(TView dy, const T* __restrict__ k, TView dx, long long total) {
+  pdl_sync();
   const T* dyp = reinterpret_cast<const T*>(dy.data);
   T* dxp = reinterpret_cast<T*>(dx.data);
   const int Cin = dx.c, Cout = dy.c;
@@ -179,6 +190,7 @@ convT2_dgrad_kernel(TView dy, const T* __restrict__ k, TView dx, long long total
 template <typename T>
 __global__ void __launch_bounds__(NT)
 convT2_wgrad_kernel(TView x, TView dy, float* __restrict__ dk) {
+  pdl_sync();
   const T* xp = reinterpret_cast<const T*>(x.data);
   const T* dyp = reinterpret_cast<const T*>(dy.data);
   const int Cin = x.c, Cout = dy.c;
@@ -202,21 +214,21 @@ convT2_wgrad_kernel(TView x, TView dy, float* __restrict__ dk) {
 }  // namespace
 
 int adam_advance(int32_t* step, const float* ls, cudaStream_t st) {
-  adam_advance_kernel<<<1, 32, 0, st>>>(step, ls);
+  launch_pdl(adam_advance_kernel, 1, 32, 0, st, step, ls);
   return check_launch("adam_advance_kernel");
 }
 
 int loss_scale_apply(void* data, int dtype, size_t count, const float* ls, cudaStream_t st) {
-  if (dtype == B200_BF16) scale_by_device_bf16_kernel<<<grid_for((long long)count), NT, 0, st>>>(reinterpret_cast<__nv_bfloat16*>(data), count, ls);
-  else scale_by_device_kernel<<<grid_for((long long)count), NT, 0, st>>>(reinterpret_cast<float*>(data), count, ls);
+  if (dtype == B200_BF16) launch_pdl(scale_by_device_bf16_kernel, grid_for((long long)count), NT, 0, st, reinterpret_cast<__nv_bfloat16*>(data), count, ls);
+  else launch_pdl(scale_by_device_kernel, grid_for((long long)count), NT, 0, st, reinterpret_cast<float*>(data), count, ls);
   return check_launch("scale_by_device_kernel");
 }
 int loss_scale_check(const float* g, size_t count, float* ls, cudaStream_t st) {
-  finite_check_kernel<<<grid_for((long long)count, 8), NT, 0, st>>>(g, count, ls);
+  launch_pdl(finite_check_kernel, grid_for((long long)count, 8), NT, 0, st, g, count, ls);
   return check_launch("finite_check_kernel");
 }
 int loss_scale_update(float* ls, float growth, cudaStream_t st) {
-  loss_scale_update_kernel<<<1, 32, 0, st>>>(ls, growth);
+  launch_pdl(loss_scale_update_kernel, 1, 32, 0, st, ls, growth);
   return check_launch("loss_scale_update_kernel");
 }
 
@@ -225,7 +237,7 @@ int adam_step(float* p, const float* g, float* m, float* v, size_t count, const 
   B200_REQUIRE(((uintptr_t)p % 16 == 0) && ((uintptr_t)g % 16 == 0) && ((uintptr_t)m % 16 == 0) &&
                    ((uintptr_t)v % 16 == 0) && ((uintptr_t)shadow % 8 == 0),
                B200_ERR_BAD_ARG, "adam_step: buffers must be 16-byte aligned");
-  adam_kernel<<<grid_for((long long)count, 4), NT, 0, st>>>(p, g, m, v, count, hyper, step,
+  launch_pdl(adam_kernel, grid_for((long long)count, 4), NT, 0, st, p, g, m, v, count, hyper, step,
                                                             reinterpret_cast<__nv_bfloat16*>(shadow), ls);
   return check_launch("adam_kernel");
 }
@@ -233,13 +245,13 @@ int adam_step(float* p, const float* g, float* m, float* v, size_t count, const 
 int cast(const void* src, int sdt, void* dst, int ddt, size_t count, cudaStream_t st) {
   const int grid = grid_for((long long)count);
   if (sdt == B200_F32 && ddt == B200_BF16)
-    cast_kernel<float, __nv_bfloat16><<<grid, NT, 0, st>>>((const float*)src, (__nv_bfloat16*)dst, count);
+    launch_pdl(cast_kernel<float, __nv_bfloat16>, grid, NT, 0, st, (const float*)src, (__nv_bfloat16*)dst, count);
   else if (sdt == B200_BF16 && ddt == B200_F32)
-    cast_kernel<__nv_bfloat16, float><<<grid, NT, 0, st>>>((const __nv_bfloat16*)src, (float*)dst, count);
+    launch_pdl(cast_kernel<__nv_bfloat16, float>, grid, NT, 0, st, (const __nv_bfloat16*)src, (float*)dst, count);
   else if (sdt == B200_F32 && ddt == B200_F32)
-    cast_kernel<float, float><<<grid, NT, 0, st>>>((const float*)src, (float*)dst, count);
+    launch_pdl(cast_kernel<float, float>, grid, NT, 0, st, (const float*)src, (float*)dst, count);
   else
-    cast_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, NT, 0, st>>>((const __nv_bfloat16*)src, (__nv_bfloat16*)dst, count);
+    launch_pdl(cast_kernel<__nv_bfloat16, __nv_bfloat16>, grid, NT, 0, st, (const __nv_bfloat16*)src, (__nv_bfloat16*)dst, count);
   return check_launch("cast_kernel");
 }
 
@@ -248,15 +260,15 @@ int copy_tensor(const b200_tensor* s, const b200_tensor* d, cudaStream_t st) {
   long long total = (long long)d->n * d->h * d->w * d->c;
   TView sv = view_of(s), dv = view_of(d);
   const int grid = grid_for(total);
-  if (s->dtype == B200_F32 && d->dtype == B200_BF16) copy_tensor_kernel<float, __nv_bfloat16><<<grid, NT, 0, st>>>(sv, dv, total);
-  else if (s->dtype == B200_BF16 && d->dtype == B200_F32) copy_tensor_kernel<__nv_bfloat16, float><<<grid, NT, 0, st>>>(sv, dv, total);
-  else if (s->dtype == B200_F32) copy_tensor_kernel<float, float><<<grid, NT, 0, st>>>(sv, dv, total);
-  else copy_tensor_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, NT, 0, st>>>(sv, dv, total);
+  if (s->dtype == B200_F32 && d->dtype == B200_BF16) launch_pdl(copy_tensor_kernel<float, __nv_bfloat16>, grid, NT, 0, st, sv, dv, total);
+  else if (s->dtype == B200_BF16 && d->dtype == B200_F32) launch_pdl(copy_tensor_kernel<__nv_bfloat16, float>, grid, NT, 0, st, sv, dv, total);
+  else if (s->dtype == B200_F32) launch_pdl(copy_tensor_kernel<float, float>, grid, NT, 0, st, sv, dv, total);
+  else launch_pdl(copy_tensor_kernel<__nv_bfloat16, __nv_bfloat16>, grid, NT, 0, st, sv, dv, total);
   return check_launch("copy_tensor_kernel");
 }
 
 int scale_inplace(float* p, size_t count, float s, cudaStream_t st) {
-  scale_kernel<<<grid_for((long long)count), NT, 0, st>>>(p, count, s);
+  launch_pdl(scale_kernel, grid_for((long long)count), NT, 0, st, p, count, s);
   return check_launch("scale_kernel");
 }
 
@@ -308,7 +320,7 @@ int convT2_fprop(const b200_tensor* x, const void* kernel, const float* bias, in
   long long total = (long long)y->n * y->h * y->w * y->c;
   TView xv = view_of(x), yv = view_of(y);
   B200_DISPATCH_DTYPE(x->dtype, T, {
-    convT2_fprop_kernel<T><<<grid_for(total), NT, 0, st>>>(xv, (const T*)kernel, bias, yv, total);
+    launch_pdl(convT2_fprop_kernel<T>, grid_for(total), NT, 0, st, xv, (const T*)kernel, bias, yv, total);
   });
   return check_launch("convT2_fprop_kernel");
 }
@@ -332,7 +344,7 @@ int convT2_dgrad(const b200_tensor* dy, const void* kernel, int cout, const b200
   long long total = (long long)dx->n * dx->h * dx->w * dx->c;
   TView dv = view_of(dy), xv = view_of(dx);
   B200_DISPATCH_DTYPE(dx->dtype, T, {
-    convT2_dgrad_kernel<T><<<grid_for(total), NT, 0, st>>>(dv, (const T*)kernel, xv, total);
+    launch_pdl(convT2_dgrad_kernel<T>, grid_for(total), NT, 0, st, dv, (const T*)kernel, xv, total);
   });
   return check_launch("convT2_dgrad_kernel");
 }
@@ -356,7 +368,7 @@ int convT2_wgrad(const b200_tensor* x, const b200_tensor* dy, float* dk, float* 
     int splits = (int)((npix + 2047) / 2048);
     if (splits > 64) splits = 64;
     dim3 grid(4 * dy->c, splits);
-    B200_DISPATCH_DTYPE(x->dtype, T, { convT2_wgrad_kernel<T><<<grid, NT, 0, st>>>(xv, dv, dk); });
+    B200_DISPATCH_DTYPE(x->dtype, T, { launch_pdl(convT2_wgrad_kernel<T>, grid, NT, 0, st, xv, dv, dk); });
     int rc = check_launch("convT2_wgrad_kernel");
     if (rc) return rc;
   }

@@ -97,6 +97,7 @@ template <typename SrcT>
 __global__ void __launch_bounds__(256)
 patch_extract_kernel(const SrcT* __restrict__ img, int img_h, int img_w, const int32_t* __restrict__ origins,
                      float* __restrict__ hr, int n, int p, long long sn, long long sh) {
+  pdl_sync();
   const int row_elems = p * 3;
   const long long total = (long long)n * p * row_elems;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -120,11 +121,11 @@ int patch_extract(const void* image, int image_dtype, int img_h, int img_w, cons
   long long want = (total + block - 1) / block;
   const int grid = (int)(want < (long long)sm_count() * 16 ? want : (long long)sm_count() * 16);
   if (image_dtype == B200_U8)
-    patch_extract_kernel<unsigned char><<<grid, block, 0, st>>>(static_cast<const unsigned char*>(image), img_h, img_w,
+    launch_pdl(patch_extract_kernel<unsigned char>, grid, block, 0, st, static_cast<const unsigned char*>(image), img_h, img_w,
                                                                 origins, static_cast<float*>(hr->data), hr->n, p,
                                                                 hr->stride_n, hr->stride_h);
   else
-    patch_extract_kernel<float><<<grid, block, 0, st>>>(static_cast<const float*>(image), img_h, img_w, origins,
+    launch_pdl(patch_extract_kernel<float>, grid, block, 0, st, static_cast<const float*>(image), img_h, img_w, origins,
                                                         static_cast<float*>(hr->data), hr->n, p, hr->stride_n,
                                                         hr->stride_h);
   return check_launch("patch_extract_kernel");
@@ -136,6 +137,7 @@ template <int C, bool CLIP>
 __global__ void __launch_bounds__(256)
 gather2d_kernel(TView x, TView y, const int32_t* __restrict__ hi, const float* __restrict__ hw, int ht,
                 const int32_t* __restrict__ wi, const float* __restrict__ ww, int wt) {
+  pdl_sync();
   const long long total = (long long)y.n * y.h * y.w;
   const float* __restrict__ xp = static_cast<const float*>(x.data);
   float* __restrict__ yp = static_cast<float*>(y.data);
@@ -180,7 +182,7 @@ int gather2d(const b200_tensor* x, const b200_tensor* y, const int32_t* hi, cons
   const int block = 256;
   long long want = (total + block - 1) / block;
   const int grid = (int)(want < (long long)sm_count() * 32 ? want : (long long)sm_count() * 32);
-#define B200_G2D(CH, CL) gather2d_kernel<CH, CL><<<grid, block, 0, st>>>(xv, yv, hi, hw, ht, wi, ww, wt)
+#define B200_G2D(CH, CL) launch_pdl(gather2d_kernel<CH, CL>, grid, block, 0, st, xv, yv, hi, hw, ht, wi, ww, wt)
   if (x->c == 3) { if (clip01) B200_G2D(3, true); else B200_G2D(3, false); }
   else if (x->c == 1) { if (clip01) B200_G2D(1, true); else B200_G2D(1, false); }
   else return fail(B200_ERR_UNSUPPORTED, "gather2d: %d channels (1 or 3 supported)", x->c);
@@ -193,6 +195,7 @@ template <typename V>
 __global__ void __launch_bounds__(256)
 copy_rows_kernel(const V* __restrict__ src, const int32_t* __restrict__ src_rows, V* __restrict__ dst,
                  const int32_t* __restrict__ dst_rows, long long row_vecs) {
+  pdl_sync();
   const int r = blockIdx.y;
   const long long s = (src_rows ? (long long)src_rows[r] : (long long)r) * row_vecs;
   const long long d = (dst_rows ? (long long)dst_rows[r] : (long long)r) * row_vecs;
@@ -208,10 +211,10 @@ int copy_rows(const float* src, const int32_t* src_rows, float* dst, const int32
   if (bx > 64) bx = 64;
   dim3 grid((unsigned)bx, (unsigned)n_rows);
   if (vec)
-    copy_rows_kernel<float4><<<grid, 256, 0, st>>>(reinterpret_cast<const float4*>(src), src_rows,
+    launch_pdl(copy_rows_kernel<float4>, grid, 256, 0, st, reinterpret_cast<const float4*>(src), src_rows,
                                                    reinterpret_cast<float4*>(dst), dst_rows, units);
   else
-    copy_rows_kernel<float><<<grid, 256, 0, st>>>(src, src_rows, dst, dst_rows, units);
+    launch_pdl(copy_rows_kernel<float>, grid, 256, 0, st, src, src_rows, dst, dst_rows, units);
   return check_launch("copy_rows_kernel");
 }
 

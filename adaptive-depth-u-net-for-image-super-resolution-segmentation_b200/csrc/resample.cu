@@ -25,6 +25,7 @@ template <typename T, bool BATCHED>
 __global__ void __launch_bounds__(NT)
 resample_vec_kernel(TView x, TView y, const int* __restrict__ hs, const float* __restrict__ hw, int ht,
                     const int* __restrict__ ws, const float* __restrict__ ww, int wt, int accumulate) {
+  pdl_sync();
   const int chunks = y.c >> 3;
   const int item = blockIdx.x * NT + threadIdx.x;
   const int ow = item / chunks, j = item - ow * chunks;
@@ -153,6 +154,7 @@ __device__ __forceinline__ void rs_store(__nv_bfloat16* dst, const float2 (&v)[4
 template <int HT>
 __global__ void __launch_bounds__(NT)
 resample_up_kernel(const RsArgs a) {
+  pdl_sync();
   const int item = blockIdx.x * NT + threadIdx.x;
   const int ow = item / a.chunks, j = item - ow * a.chunks;
   if (ow >= a.yw) return;
@@ -205,6 +207,7 @@ resample_up_kernel(const RsArgs a) {
 template <int NSLOT, int NW>
 __global__ void __launch_bounds__(NT)
 resample_down_kernel(const RsArgs a) {
+  pdl_sync();
   const int item = blockIdx.x * NT + threadIdx.x;
   const int ow = item / a.chunks, j = item - ow * a.chunks;
   if (ow >= a.yw) return;
@@ -259,6 +262,7 @@ __global__ void __launch_bounds__(NT)
 resample_scalar_kernel(TView x, TView y, const int* __restrict__ hs, const float* __restrict__ hw, int ht,
                        const int* __restrict__ ws, const float* __restrict__ ww, int wt, int accumulate,
                        long long total) {
+  pdl_sync();
   const T* xp = reinterpret_cast<const T*>(x.data);
   T* yp = reinterpret_cast<T*>(y.data);
   for (long long i = (long long)blockIdx.x * NT + threadIdx.x; i < total; i += (long long)gridDim.x * NT) {
@@ -289,6 +293,7 @@ resample_scalar_kernel(TView x, TView y, const int* __restrict__ hs, const float
 template <typename T>
 __global__ void __launch_bounds__(NT)
 maxpool2_fwd_kernel(TView x, TView y, long long total) {
+  pdl_sync();
   const T* xp = reinterpret_cast<const T*>(x.data);
   T* yp = reinterpret_cast<T*>(y.data);
   for (long long i = (long long)blockIdx.x * NT + threadIdx.x; i < total; i += (long long)gridDim.x * NT) {
@@ -307,6 +312,7 @@ maxpool2_fwd_kernel(TView x, TView y, long long total) {
 template <typename T>
 __global__ void __launch_bounds__(NT)
 maxpool2_bwd_kernel(TView x, TView y, TView dy, TView dx, int accumulate, long long total) {
+  pdl_sync();
   const T* xp = reinterpret_cast<const T*>(x.data);
   const T* yp = reinterpret_cast<const T*>(y.data);
   const T* dyp = reinterpret_cast<const T*>(dy.data);
@@ -340,6 +346,7 @@ maxpool2_bwd_kernel(TView x, TView y, TView dy, TView dx, int accumulate, long l
 template <typename T>
 __global__ void __launch_bounds__(NT)
 maxpool2_fwd_vec_kernel(TView x, TView y, long long total) {
+  pdl_sync();
   const T* xp = reinterpret_cast<const T*>(x.data);
   T* yp = reinterpret_cast<T*>(y.data);
   const int chunks = y.c / 8;
@@ -361,6 +368,7 @@ maxpool2_fwd_vec_kernel(TView x, TView y, long long total) {
 template <typename T>
 __global__ void __launch_bounds__(NT)
 maxpool2_bwd_vec_kernel(TView x, TView y, TView dy, TView dx, int accumulate, long long total) {
+  pdl_sync();
   const T* xp = reinterpret_cast<const T*>(x.data);
   const T* yp = reinterpret_cast<const T*>(y.data);
   const T* dyp = reinterpret_cast<const T*>(dy.data);
@@ -565,26 +573,26 @@ int resample2d(const b200_tensor* x, const b200_tensor* y, const int32_t* hs, co
     nseg = (y->h + a.seg - 1) / a.seg;
     dim3 grid((unsigned)bx, (unsigned)nseg, (unsigned)y->n);
     if (mode == 1) {
-      if (ht == 1) resample_up_kernel<1><<<grid, NT, 0, st>>>(a);
-      else if (ht == 2) resample_up_kernel<2><<<grid, NT, 0, st>>>(a);
-      else resample_up_kernel<3><<<grid, NT, 0, st>>>(a);
+      if (ht == 1) launch_pdl(resample_up_kernel<1>, grid, NT, 0, st, a);
+      else if (ht == 2) launch_pdl(resample_up_kernel<2>, grid, NT, 0, st, a);
+      else launch_pdl(resample_up_kernel<3>, grid, NT, 0, st, a);
     } else if (mode == 2) {
-      if (wt <= 4) resample_down_kernel<4, 4><<<grid, NT, 0, st>>>(a);
-      else if (wt <= 8) resample_down_kernel<4, 8><<<grid, NT, 0, st>>>(a);
-      else resample_down_kernel<4, 0><<<grid, NT, 0, st>>>(a);
+      if (wt <= 4) launch_pdl(resample_down_kernel<4, 4>, grid, NT, 0, st, a);
+      else if (wt <= 8) launch_pdl(resample_down_kernel<4, 8>, grid, NT, 0, st, a);
+      else launch_pdl(resample_down_kernel<4, 0>, grid, NT, 0, st, a);
     } else {
-      if (wt <= 4) resample_down_kernel<6, 4><<<grid, NT, 0, st>>>(a);
-      else resample_down_kernel<6, 0><<<grid, NT, 0, st>>>(a);
+      if (wt <= 4) launch_pdl(resample_down_kernel<6, 4>, grid, NT, 0, st, a);
+      else launch_pdl(resample_down_kernel<6, 0>, grid, NT, 0, st, a);
     }
     return check_launch("resample_march_kernel");
   }
   B200_DISPATCH_DTYPE(x->dtype, T, {
     if (vec && y->h <= 65535 && y->n <= 65535) {
       dim3 grid((unsigned)(((long long)y->w * (y->c / 8) + NT - 1) / NT), (unsigned)y->h, (unsigned)y->n);
-      resample_vec_kernel<T, false><<<grid, NT, 0, st>>>(xv, yv, hs, hw, ht, ws, ww, wt, accumulate);
+      launch_pdl(resample_vec_kernel<T, false>, grid, NT, 0, st, xv, yv, hs, hw, ht, ws, ww, wt, accumulate);
     } else {
       long long total = (long long)y->n * y->h * y->w * y->c;
-      resample_scalar_kernel<T><<<grid_for(total), NT, 0, st>>>(xv, yv, hs, hw, ht, ws, ww, wt, accumulate, total);
+      launch_pdl(resample_scalar_kernel<T>, grid_for(total), NT, 0, st, xv, yv, hs, hw, ht, ws, ww, wt, accumulate, total);
     }
   });
   return check_launch("resample_kernel");
@@ -604,10 +612,10 @@ int maxpool2_fwd(const b200_tensor* x, const b200_tensor* y, cudaStream_t st) {
   TView xv = view_of(x), yv = view_of(y);
   if (pool_vec_ok(x) && pool_vec_ok(y)) {
     total /= 8;
-    B200_DISPATCH_DTYPE(x->dtype, T, { maxpool2_fwd_vec_kernel<T><<<grid_for(total), NT, 0, st>>>(xv, yv, total); });
+    B200_DISPATCH_DTYPE(x->dtype, T, { launch_pdl(maxpool2_fwd_vec_kernel<T>, grid_for(total), NT, 0, st, xv, yv, total); });
     return check_launch("maxpool2_fwd_vec_kernel");
   }
-  B200_DISPATCH_DTYPE(x->dtype, T, { maxpool2_fwd_kernel<T><<<grid_for(total), NT, 0, st>>>(xv, yv, total); });
+  B200_DISPATCH_DTYPE(x->dtype, T, { launch_pdl(maxpool2_fwd_kernel<T>, grid_for(total), NT, 0, st, xv, yv, total); });
   return check_launch("maxpool2_fwd_kernel");
 }
 
@@ -620,12 +628,12 @@ int maxpool2_bwd(const b200_tensor* x, const b200_tensor* y, const b200_tensor* 
   if (x->h % 2 == 0 && x->w % 2 == 0 && pool_vec_ok(x) && pool_vec_ok(y) && pool_vec_ok(dy) && pool_vec_ok(dx)) {
     const long long items = (long long)y->n * y->h * y->w * (y->c / 8);
     B200_DISPATCH_DTYPE(x->dtype, T, {
-      maxpool2_bwd_vec_kernel<T><<<grid_for(items), NT, 0, st>>>(xv, yv, dyv, dxv, accumulate, items);
+      launch_pdl(maxpool2_bwd_vec_kernel<T>, grid_for(items), NT, 0, st, xv, yv, dyv, dxv, accumulate, items);
     });
     return check_launch("maxpool2_bwd_vec_kernel");
   }
   B200_DISPATCH_DTYPE(x->dtype, T, {
-    maxpool2_bwd_kernel<T><<<grid_for(total), NT, 0, st>>>(xv, yv, dyv, dxv, accumulate, total);
+    launch_pdl(maxpool2_bwd_kernel<T>, grid_for(total), NT, 0, st, xv, yv, dyv, dxv, accumulate, total);
   });
   return check_launch("maxpool2_bwd_kernel");
 }

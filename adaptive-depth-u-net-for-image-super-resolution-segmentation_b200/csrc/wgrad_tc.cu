@@ -94,6 +94,7 @@ wgrad3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
   }
   if (warp == 0 && lane == 0) { prefetch_tmap(&tm_x); prefetch_tmap(&tm_dz); }
   if (warp == 1) { tmem_alloc(smem_u32(&tmem_base_smem), 512); tmem_relinquish(); }
+  pdl_sync();      // (PDL) the prologue above overlapped the previous kernel; global memory only from here on
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -200,6 +201,7 @@ wgrad3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
 __global__ void __launch_bounds__(256)
 wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw, long long count, int splits,
                     int live_mask, long long per_tap) {
+  pdl_sync();
   __shared__ float4 s_part[4][64];
   const long long n4 = count / 4;
   const int lane = threadIdx.x % 64, grp = threadIdx.x / 64;
@@ -331,7 +333,7 @@ int wgrad_tc_launch(const b200_tensor* x, const b200_tensor* dy, float* dw, void
     if (rcs || direct) return rcs;
     long long blocks_s = (count_s / 4 + 63) / 64;
     if (blocks_s > 8LL * sm_count()) blocks_s = 8LL * sm_count();
-    wgrad_reduce_kernel<<<(int)blocks_s, 256, 0, st>>>(reinterpret_cast<const float*>(ws), dw, count_s, splits_s, mask_s,
+    launch_pdl(wgrad_reduce_kernel, (int)blocks_s, 256, 0, st, reinterpret_cast<const float*>(ws), dw, count_s, splits_s, mask_s,
                                                        (long long)x->c * dy->c);
     return check_launch("wgrad_reduce_kernel");
   }
@@ -354,13 +356,13 @@ int wgrad_tc_launch(const b200_tensor* x, const b200_tensor* dy, float* dw, void
   if (first_use_on_device(2))
     cudaFuncSetAttribute(wgrad3x3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   const int grid = p.splits * p.cblocks * p.oblocks;
-  wgrad3x3_tc_kernel<<<grid, NTHREADS, smem, st>>>(tm_x, tm_dz, p);
+  launch_pdl(wgrad3x3_tc_kernel, grid, NTHREADS, smem, st, tm_x, tm_dz, p);
   int rc2 = check_launch("wgrad3x3_tc_kernel");
   if (rc2 || atomic) return rc2;
   const long long count = (long long)p.ntaps * p.Cin * p.Cout;
   long long blocks = (count / 4 + 63) / 64;
   if (blocks > 8LL * sm_count()) blocks = 8LL * sm_count();
-  wgrad_reduce_kernel<<<(int)blocks, 256, 0, st>>>(p.partial, dw, count, p.splits, g.live_mask, (long long)p.Cin * p.Cout);  // counted by check_launch
+  launch_pdl(wgrad_reduce_kernel, (int)blocks, 256, 0, st, p.partial, dw, count, p.splits, g.live_mask, (long long)p.Cin * p.Cout);  // counted by check_launch
   return check_launch("wgrad_reduce_kernel");
 }
 
