@@ -61,6 +61,8 @@ SIGNATURES = {
     "b200_conv2d_fprop": (_i, [_TP, _FP, _vp, _TP, _i, _i, _SP, _vp]),
     "b200_conv2d_ln_fprop": (_i, [_TP, _FP, _vp, _vp, _vp, _f, _i, _TP, _TP, _vp, _vp, _i, _SP, _vp]),
     "b200_conv2d_dgrad": (_i, [_TP, _FP, _TP, _i, _i, _SP, _vp]),
+    "b200_conv2d_dgrad_ln_bwd_supported": (_i, [_TP, _FP, _TP]),
+    "b200_conv2d_dgrad_ln_bwd": (_i, [_TP, _FP, _TP, _vp, _vp, _vp, _vp, _i, _TP, _vp, _vp, _vp, _vp]),
     "b200_conv2d_workspace": (_sz, [_TP, C.POINTER(Filter), _i]),
     "b200_conv2d_wgrad_workspace": (_sz, [_TP, _TP, _i, _i, _i]),
     "b200_conv2d_wgrad": (_i, [_TP, _TP, _i, _i, _vp, _vp, _sz, _i, _vp]),

@@ -41,10 +41,16 @@ struct ConvLnArgs {
   float* mean; float* rstd;
 };
 bool conv_tc_ln_supported(int cout);
+struct ConvLnBwdArgs {
+  const b200_tensor* z;
+  const float* mean; const float* rstd; const float* gamma; const float* beta; int relu;
+  float* dgamma; float* dbeta; float* dbias;
+};
+bool conv_tc_dgrad_lnbwd_supported(const b200_tensor* dy, int cout, int cin, const b200_tensor* dx, int ks);
 bool conv_gemm_wanted(const b200_tensor*, int, int, int);
 size_t conv_gemm_workspace(const b200_tensor*, int, int, int);
 int conv_tc_launch(const b200_tensor*, const void*, int, int, int, int, const float*, const b200_tensor*, int, int, cudaStream_t,
-                   const ConvLnArgs* ln, int ks, void* ws, size_t ws_bytes, const void* wmat_k = nullptr, int allow_pairs = 1);
+                   const ConvLnArgs* ln, int ks, void* ws, size_t ws_bytes, const void* wmat_k = nullptr, int allow_pairs = 1, const struct ConvLnBwdArgs* lnb = nullptr);
 int umma_probe(const void*, int, const void*, int, int, int, int, float*, cudaStream_t);
 int umma_rate(int, int, int, long long*, int, cudaStream_t);
 bool stem_supported(const b200_tensor*, const b200_tensor*, int);
@@ -230,6 +236,25 @@ size_t b200_conv2d_wgrad_workspace(const b200_tensor* x, const b200_tensor* dy, 
   if (algo == B200_ALGO_SIMT || kh != kw || (kh != 3 && kh != 1)) return 0;
   if (!wgrad_tc_supported(x, dy, kh)) return 0;
   return wgrad_tc_workspace(x, dy, kh);
+}
+
+int b200_conv2d_dgrad_ln_bwd_supported(const b200_tensor* dy, const b200_filter* f, const b200_tensor* dz) {
+  if (!valid_tensor(dy) || !valid_tensor(dz) || !f || !f->hwio || f->dtype != B200_BF16 || f->kh != 3 || f->kw != 3) return 0;
+  if (dy->c != f->cout || dz->c != f->cin || dy->n != dz->n || dy->h != dz->h || dy->w != dz->w) return 0;
+  return conv_tc_dgrad_lnbwd_supported(dy, f->cout, f->cin, dz, 3) ? 1 : 0;
+}
+
+int b200_conv2d_dgrad_ln_bwd(const b200_tensor* dy, const b200_filter* f, const b200_tensor* z, const float* mean,
+                             const float* rstd, const float* gamma, const float* beta, int relu, const b200_tensor* dz,
+                             float* dgamma, float* dbeta, float* dbias, void* stream) {
+  REQ_T(dy, "dy"); REQ_T(z, "z"); REQ_T(dz, "dz");
+  B200_REQUIRE(f && f->hwio && mean && rstd && gamma && beta, B200_ERR_BAD_ARG, "conv2d_dgrad_ln_bwd: NULL argument");
+  B200_REQUIRE(b200_conv2d_dgrad_ln_bwd_supported(dy, f, dz), B200_ERR_UNSUPPORTED,
+               "conv2d_dgrad_ln_bwd: only 3x3 bf16 filters with 64 input channels on plain 16x8 tiles (see "
+               "b200_conv2d_dgrad_ln_bwd_supported); run b200_conv2d_dgrad + b200_layernorm_bwd instead");
+  ConvLnBwdArgs a{z, mean, rstd, gamma, beta, relu, dgamma, dbeta, dbias};
+  return conv_tc_launch(dy, f->hwio, f->cout, f->cin, 1, 0, nullptr, dz, B200_ACT_NONE, 0, ST(stream), nullptr, 3, nullptr, 0,
+                        nullptr, 1, &a);
 }
 
 int b200_conv2d_wgrad(const b200_tensor* x, const b200_tensor* dy, int kh, int kw, float* dw, void* ws, size_t ws_bytes,

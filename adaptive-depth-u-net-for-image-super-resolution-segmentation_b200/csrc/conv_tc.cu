@@ -143,6 +143,13 @@ struct ConvTcParams {
   long long zsn, zsh, zsw;
   float* mean;
   float* rstd;
+  // fused LayerNormalization(+ReLU) BACKWARD epilogue of a dgrad launch (EPI == 4; CTA pairs, N = 64): the accumulator is
+  // dy of a LayerNorm output; with the saved z (p.z, read), mean / rstd (read), gamma / beta the epilogue writes dz instead
+  // and sums d(gamma), d(beta) and d(bias of the conv that produced z) over its pixels
+  int lnb;
+  float* dgamma;
+  float* dbeta;
+  float* dbias;
 };
 
 // D[tmem] (+)= A * B^T with the descriptors given as (lo, hi) words: the hi words are loop
@@ -304,7 +311,7 @@ __device__ __forceinline__ void ln_load(uint32_t taddr, const float* s_bias, uin
 // EPI selects which epilogues an instantiation contains (the LayerNorm epilogue's code generation is sensitive to
 // what else lives in the kernel): 0 = all, 1 = LayerNorm over 64 channels, 2 = LayerNorm over 128, 3 = no LayerNorm
 template <bool PAIR, int EPI, bool CG2 = false>
-__global__ void __launch_bounds__(EPI == 1 ? NTHREADS2 : NTHREADS, 1)
+__global__ void __launch_bounds__((EPI == 1 || EPI == 4) ? NTHREADS2 : NTHREADS, 1)
 conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_b,
                   const __grid_constant__ CUtensorMap tm_y, const __grid_constant__ CUtensorMap tm_z,
                   const ConvTcParams p) {
@@ -354,7 +361,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
   pdl_sync();
   for (int i = threadIdx.x; i < p.Cout; i += blockDim.x) {
     s_bias[i] = p.bias ? p.bias[i] : 0.f;
-    if (p.ln) { s_bias[p.Cout + i] = p.gamma[i]; s_bias[2 * p.Cout + i] = p.beta[i]; }
+    if (p.ln || p.lnb) { s_bias[p.Cout + i] = p.gamma[i]; s_bias[2 * p.Cout + i] = p.beta[i]; }
   }
   tc_fence_before();
   __syncthreads();
@@ -494,7 +501,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
     // stacked small images (srows huge otherwise) or pair tiles (rows of two images interleaved)
     const int sb_img = PAIR ? (ty & 1) : ty / p.srows, sb_row = PAIR ? (ty >> 1) : ty % p.srows;
     const int group = (warp - 2) >> 2;      // 0: warps 2..5, 1: warps 6..9 (EPI == 1 launches only)
-    const int egroups = EPI == 1 ? p.egroups : 1;
+    const int egroups = (EPI == 1 || EPI == 4) ? p.egroups : 1;
     StoreRing ring;
     ring.nslots = p.nslots / egroups; ring.slot = 0; ring.issuer = threadIdx.x == 64 + group * EPI_THREADS;
     ring.stg0 = stg0 + (uint32_t)(group * ring.nslots) * SLOT_BYTES;
@@ -502,6 +509,10 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
     ring.d_have = 0; ring.d_which = 0; ring.d_c = ring.d_w = ring.d_h = ring.d_n = 0; ring.d_slot = 0;
     ring.tm_y = &tm_y; ring.tm_z = &tm_z; ring.dbg = p.debug;
     int it = -1;
+    float lnb_acc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};     // (EPI == 4) column sums of dz, d, d*xhat for this thread's channel pair
+    uint4 zr[EPI == 4 ? 8 : 1], zn[EPI == 4 ? 8 : 1];       // (EPI == 4) saved pre-norm row of the current / the next own tile
+    float ln_mu = 0.f, ln_rs = 0.f, ln_mu_n = 0.f, ln_rs_n = 0.f;
+    bool lnb_primed = false;
     if (group < egroups)
     for (int q = q0; q < p.total_items; q += qstep) {
       const int item = item_of(q);
@@ -514,6 +525,35 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
       const int img = n + sb_img;
       const bool valid = oh < p.H && ow < p.W && sb_img < p.nb && img < p.N;
       const float* bias = s_bias + j * p.BN;
+      // fused LayerNorm backward: the operands that do not come from the MMAs (this pixel's 64 saved pre-norm values, its
+      // mean and rstd) are software-pipelined one tile ahead: the loads for the group's NEXT tile are issued here and
+      // consumed an epilogue later (the epilogue, not the MMA stream, paces this kernel, so a load issued at the top of
+      // its own tile would be waited for in full)
+      if (EPI == 4) {
+        auto load_z = [&](int qq, uint4* dst, float& mu, float& rs) {
+          bool ok = false;
+          if (qq < p.total_items) {
+            int j2, tw2, th2, n2;
+            decode_item(p, item_of(qq), j2, tw2, th2, n2);
+            const int oh2 = th2 * TILE_H + sb_row, ow2 = tw2 * TILE_W + tx;
+            if (oh2 < p.H && ow2 < p.W && n2 < p.N) {
+              ok = true;
+              const uint4* zp = reinterpret_cast<const uint4*>(p.z + (long long)n2 * p.zsn + (long long)oh2 * p.zsh + (long long)ow2 * p.zsw);
+#pragma unroll
+              for (int c = 0; c < 8; ++c) dst[c] = zp[c];
+              const long long pixb = ((long long)n2 * p.H + oh2) * p.W + ow2;
+              mu = p.mean[pixb]; rs = p.rstd[pixb];
+            }
+          }
+          if (!ok) {
+#pragma unroll
+            for (int c = 0; c < 8; ++c) dst[c] = make_uint4(0u, 0u, 0u, 0u);
+            mu = 0.f; rs = 0.f;
+          }
+        };
+        if (!lnb_primed) { load_z(q, zr, ln_mu, ln_rs); lnb_primed = true; }
+        load_z(q + egroups * qstep, zn, ln_mu_n, ln_rs_n);
+      }
       wait(smem_u32(&bar_tmem_full[as]), pa);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(as * p.BN);
@@ -529,7 +569,92 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
       const int cw = tw * TILE_W, ch = PAIR ? n : th * TILE_H, cn = PAIR ? 0 : n;
       if (p.debug == 1) {
         release_tmem();
-      } else if (EPI != 3 && p.ln) {
+      } else if (EPI == 4) {
+        // ---- dgrad + LayerNorm(+ReLU) backward: dy (accumulator) -> dz, plus the column sums of d, d*xhat and dz ----
+        // pass 1 consumes the accumulator 32 columns at a time and keeps d = masked dy as packed bf16 pairs (what the
+        // unfused path stores between the two kernels): 32 registers instead of 64 next to the two pipelined z rows
+        uint32_t dp[32];
+        const float* gam = s_bias + p.Cout;
+        const float* bet = s_bias + 2 * p.Cout;
+        const bool relu = p.ln_relu != 0;
+        const float nmr = -ln_mu * ln_rs;
+        float s1a = 0.f, s1b = 0.f, s2a = 0.f, s2b = 0.f;
+        const uint32_t* zw = reinterpret_cast<const uint32_t*>(zr);
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+          uint32_t v[32];
+          tmem_ld32(taddr + hf * 32, v);
+          tmem_ld_wait();
+          if (hf == 1) release_tmem();
+#pragma unroll
+          for (int k = 0; k < 16; ++k) {         // d = masked dy, sums of g = d*gamma and g*xhat
+            const int i = hf * 16 + k;
+            const float x0 = fmaf(bf16_lo(zw[i]), ln_rs, nmr), x1 = fmaf(bf16_hi(zw[i]), ln_rs, nmr);
+            const float g0 = gam[2 * i], g1 = gam[2 * i + 1];
+            float d0 = __uint_as_float(v[2 * k]), d1 = __uint_as_float(v[2 * k + 1]);
+            if (relu) {
+              d0 = fmaf(x0, g0, bet[2 * i]) > 0.f ? d0 : 0.f;
+              d1 = fmaf(x1, g1, bet[2 * i + 1]) > 0.f ? d1 : 0.f;
+            }
+            if (!valid) { d0 = 0.f; d1 = 0.f; }
+            dp[i] = pack_bf16(d0, d1);
+            d0 = bf16_lo(dp[i]); d1 = bf16_hi(dp[i]);
+            const float e0 = d0 * g0, e1 = d1 * g1;
+            s1a += e0; s1b += e1;                // (two independent chains per sum)
+            s2a = fmaf(e0, x0, s2a); s2b = fmaf(e1, x1, s2b);
+          }
+        }
+        const float c1 = -(s1a + s1b) * (1.f / 64.f) * ln_rs, c2 = -(s2a + s2b) * (1.f / 64.f) * ln_rs;
+        // slots of this group: [0] dz (also the TMA store's source), [1] d, [2] d*xhat -- all bf16, 128-byte swizzled rows
+        const uint32_t slotA = ring.stg0, slotB = slotA + SLOT_BYTES, slotC = slotB + SLOT_BYTES;
+        // barrier 1: everyone finished the column sums of the previous tile and the previous dz store has read its slot
+        if (ring.issuer) bulk_wait_read<0>();
+        __syncwarp();
+        named_bar_sync(ring.bar_id, EPI_THREADS);
+        {
+          const uint32_t rbase = (uint32_t)r * 128u, swz = (uint32_t)(r & 7);
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {          // pass 2: dz = rstd * (g - mean(g) - xhat * mean(g * xhat)), 8 channels per 16-byte chunk
+            uint32_t oa[4], ob[4], oc[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const int i = c * 4 + k;
+              const float x0 = fmaf(bf16_lo(zw[i]), ln_rs, nmr), x1 = fmaf(bf16_hi(zw[i]), ln_rs, nmr);
+              const float d0 = bf16_lo(dp[i]), d1 = bf16_hi(dp[i]);
+              const float z0 = fmaf(x0, c2, fmaf(d0 * gam[2 * i], ln_rs, c1));
+              const float z1 = fmaf(x1, c2, fmaf(d1 * gam[2 * i + 1], ln_rs, c1));
+              oa[k] = pack_bf16(valid ? z0 : 0.f, valid ? z1 : 0.f);
+              ob[k] = dp[i];
+              oc[k] = pack_bf16(d0 * x0, d1 * x1);
+            }
+            const uint32_t off = rbase + (((uint32_t)c ^ swz) << 4);
+            st_shared_v4(slotA + off, oa[0], oa[1], oa[2], oa[3]);
+            st_shared_v4(slotB + off, ob[0], ob[1], ob[2], ob[3]);
+            st_shared_v4(slotC + off, oc[0], oc[1], oc[2], oc[3]);
+          }
+        }
+        fence_proxy_async();
+        __syncwarp();
+        named_bar_sync(ring.bar_id, EPI_THREADS);      // barrier 2: the three tiles are complete
+        if (ring.issuer) { tma_store_4d(&tm_y, slotA, 0, cw, ch, cn); bulk_commit(); }
+        {
+          // column sums: this thread owns channels (2 cp, 2 cp + 1) over 32 of the tile's 128 pixel rows
+          const int tg = (int)threadIdx.x - 64 - group * EPI_THREADS;
+          const uint32_t cp = (uint32_t)(tg & 31), row0 = (uint32_t)(tg >> 5) * 32u;
+#pragma unroll 4
+          for (uint32_t rr = 0; rr < 32; ++rr) {
+            const uint32_t row = row0 + rr;
+            const uint32_t off = row * 128u + ((((cp >> 2) ^ (row & 7u))) << 4) + ((cp & 3u) << 2);
+            const uint32_t wa = ld_shared_u32(slotA + off), wb = ld_shared_u32(slotB + off), wc = ld_shared_u32(slotC + off);
+            lnb_acc[0] += bf16_lo(wa); lnb_acc[1] += bf16_hi(wa);
+            lnb_acc[2] += bf16_lo(wb); lnb_acc[3] += bf16_hi(wb);
+            lnb_acc[4] += bf16_lo(wc); lnb_acc[5] += bf16_hi(wc);
+          }
+        }
+#pragma unroll
+        for (int c = 0; c < 8; ++c) zr[c] = zn[c];        // rotate the pipeline: the next own tile's operands become current
+        ln_mu = ln_mu_n; ln_rs = ln_rs_n;
+      } else if (EPI != 3 && EPI != 4 && p.ln) {
         const long long pix = ((long long)img * p.H + oh) * p.W + ow;
         const float* gam = s_bias + p.Cout;
         const float* bet = s_bias + 2 * p.Cout;
@@ -623,7 +748,27 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
         release_tmem();
       }
     }
-    if (p.tma_store && group < egroups) ring.drain();
+    if (EPI == 4 && group < egroups) {
+      // per-group reduction of the column sums over the four 32-row quarters, then one atomic per (quantity, channel)
+      if (ring.issuer) bulk_wait_all();
+      __syncwarp();
+      named_bar_sync(ring.bar_id, EPI_THREADS);
+      float* red = reinterpret_cast<float*>(smem_raw + (ring.stg0 - smem_u32(smem_raw)));     // [4 quarters][3][64]
+      const int tg = (int)threadIdx.x - 64 - group * EPI_THREADS;
+      const int cp = tg & 31, qt = tg >> 5;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        red[(qt * 3 + k) * 64 + 2 * cp] = lnb_acc[2 * k];
+        red[(qt * 3 + k) * 64 + 2 * cp + 1] = lnb_acc[2 * k + 1];
+      }
+      named_bar_sync(ring.bar_id, EPI_THREADS);
+      for (int i = tg; i < 192; i += EPI_THREADS) {
+        const int k = i / 64, c = i % 64;
+        const float sum = red[(0 * 3 + k) * 64 + c] + red[(1 * 3 + k) * 64 + c] + red[(2 * 3 + k) * 64 + c] + red[(3 * 3 + k) * 64 + c];
+        float* dst = k == 0 ? p.dbias : (k == 1 ? p.dbeta : p.dgamma);
+        if (dst) atomicAdd(dst + c, sum);
+      }
+    } else if (p.tma_store && group < egroups) ring.drain();
   }
 
   tc_fence_before();
@@ -790,6 +935,21 @@ static bool flatten_1x1(const b200_tensor* t, b200_tensor* out) {
   return true;
 }
 
+bool conv_gemm_wanted(const b200_tensor* x, int cin, int cout, int ks);
+
+// shapes the fused dgrad + LayerNorm-backward epilogue takes (mirrors conv_tc_launch: the CTA-pair kernel on plain
+// 16x8 tiles, one 64-channel N tile, weights resident next to six staging slots: K = cout of the filter <= 128)
+bool conv_tc_dgrad_lnbwd_supported(const b200_tensor* dy, int k_channels, int n_channels, const b200_tensor* dx, int ks) {
+  static const int allow_cg2 = getenv("B200_CONV_CG2") ? atoi(getenv("B200_CONV_CG2")) : 1;
+  if (!allow_cg2 || ks != 3 || n_channels != 64 || k_channels % 64 != 0 || k_channels > 128) return false;
+  if (!conv_tc_supported(dy, k_channels, n_channels, dx, ks) || conv_gemm_wanted(dy, k_channels, n_channels, ks)) return false;
+  if (dx->h == 8 && dx->n > 1) return false;                 // pair tiles (two 8-row images per tile)
+  if (dx->h + 2 <= 9 && dx->n > 1) return false;             // stacked small images
+  if (dx->h == 1 && dx->w == 1) return false;                // flattened 1x1 batches
+  const long long tiles = (long long)dx->n * ((dx->h + TILE_H - 1) / TILE_H) * ((dx->w + TILE_W - 1) / TILE_W);
+  return tiles >= 2;
+}
+
 // x: input activations (C = K total); y: output (C = cout).
 //   b_mn = 1: wmat is the Keras HWIO kernel [9][cin][cout] (fprop, B read MN-major)
 //   b_mn = 0: wmat is [9][cout][cin] K-major (dgrad passes the HWIO kernel with cin/cout swapped + tap_rev)
@@ -801,6 +961,13 @@ struct ConvLnArgs {
 
 bool conv_tc_ln_supported(int cout) { return cout == 64 || cout == 128; }
 
+// dgrad with the LayerNorm(+ReLU) backward of the layer that PRODUCED the convolution's input fused into its epilogue
+struct ConvLnBwdArgs {
+  const b200_tensor* z;            // saved pre-norm activations of that layer (same shape as dx)
+  const float* mean; const float* rstd; const float* gamma; const float* beta; int relu;
+  float* dgamma; float* dbeta; float* dbias;   // accumulated into (atomics); any may be NULL
+};
+
 // small-spatial split-K path (conv_gemm.cu)
 bool conv_gemm_wanted(const b200_tensor* x, int cin, int cout, int ks);
 int conv_gemm_launch(const b200_tensor* x, const void* wmat, int cin, int cout, int tap_rev, int b_mn, const float* bias,
@@ -810,7 +977,7 @@ int conv_gemm_launch(const b200_tensor* x, const void* wmat, int cin, int cout, 
 // Cout = 64 layers run as CTA pairs, whose 32-column weight halves have no 128-byte-swizzled MN-major form.
 int conv_tc_launch(const b200_tensor* x_in, const void* wmat, int cin, int cout, int tap_rev, int b_mn, const float* bias,
                    const b200_tensor* y_in, int act, int accumulate, cudaStream_t st, const ConvLnArgs* ln, int ks,
-                   void* ws, size_t ws_bytes, const void* wmat_k, int allow_pairs) {
+                   void* ws, size_t ws_bytes, const void* wmat_k, int allow_pairs, const ConvLnBwdArgs* lnb) {
   B200_REQUIRE(conv_tc_supported(x_in, cin, cout, y_in, ks), B200_ERR_UNSUPPORTED,
                "conv3x3 tcgen05: unsupported shape cin=%d cout=%d (need bf16, multiples of 64, 16-byte aligned)", cin,
                cout);
@@ -873,6 +1040,14 @@ int conv_tc_launch(const b200_tensor* x_in, const void* wmat, int cin, int cout,
     if (b_mn && p.BN == 64) { wmat = wmat_k; b_mn = 0; tap_rev = 0; }   // [tap][cout][cin]: K-major, natural tap order
     p.total_items = ((spatial_tiles + 1) / 2) * p.n_tiles;              // work items of a cluster = tile pairs
   }
+  p.lnb = 0; p.dgamma = p.dbeta = p.dbias = nullptr;
+  if (lnb) {
+    B200_REQUIRE(p.cg2 && !ln && cout == 64 && p.n_tiles == 1 && ks == 3 && !accumulate && lnb->z && same_shape(lnb->z, y_in) &&
+                     lnb->z->dtype == B200_BF16 && (uintptr_t)lnb->z->data % 16 == 0 && lnb->z->stride_w % 8 == 0 &&
+                     lnb->z->stride_h % 8 == 0 && lnb->z->stride_n % 8 == 0,
+                 B200_ERR_UNSUPPORTED, "conv3x3 dgrad + LayerNorm backward: needs the CTA-pair kernel, 64 channels, bf16, aligned z");
+    p.lnb = 1;
+  }
   p.tap_rev = tap_rev;
   { const char* dbg = getenv("B200_CONV_DEBUG"); p.debug = dbg ? atoi(dbg) : 0; }
   p.b_mn = b_mn;
@@ -908,6 +1083,10 @@ int conv_tc_launch(const b200_tensor* x_in, const void* wmat, int cin, int cout,
   };
   if (!p.tma_store) {
     plan_smem(0, 2);
+  } else if (p.lnb) {
+    // three fixed slots (dz, d, d*xhat) for each of the two epilogue groups
+    B200_REQUIRE(plan_smem(6, 2) && p.resident, B200_ERR_UNSUPPORTED,
+                 "conv3x3 dgrad + LayerNorm backward: weights do not fit next to the six staging slots");
   } else {
     // prefer resident weights; within that, as many slots as one tile's jobs while keeping 3 window stages
     static const int max_slots = getenv("B200_CONV_SLOTS") ? atoi(getenv("B200_CONV_SLOTS")) : 4;
@@ -922,11 +1101,20 @@ int conv_tc_launch(const b200_tensor* x_in, const void* wmat, int cin, int cout,
   B200_REQUIRE(p.nsw >= 2, B200_ERR_UNSUPPORTED, "conv3x3 tcgen05: shared memory budget too small");
   static const int want_groups = getenv("B200_CONV_EGROUPS") ? atoi(getenv("B200_CONV_EGROUPS")) : 2;
   p.egroups = (ln && p.BN == 64 && !p.pair && p.tma_store && p.nslots >= 4 && want_groups == 2) ? 2 : 1;
+  if (p.lnb) p.egroups = 2;
   p.act = act; p.accumulate = accumulate; p.bias = bias;
   p.y = reinterpret_cast<__nv_bfloat16*>(y->data);
   p.ysn = y->stride_n; p.ysh = y->stride_h; p.ysw = y->stride_w;
   p.ln = ln ? 1 : 0;
   p.z = nullptr; p.zsn = p.zsh = p.zsw = 0;
+  if (lnb) {
+    p.ln_relu = lnb->relu; p.ln_eps = 0.f; p.gamma = lnb->gamma; p.beta = lnb->beta;
+    p.mean = const_cast<float*>(lnb->mean); p.rstd = const_cast<float*>(lnb->rstd);
+    p.z = reinterpret_cast<__nv_bfloat16*>(lnb->z->data);
+    p.zsn = lnb->z->stride_n; p.zsh = lnb->z->stride_h; p.zsw = lnb->z->stride_w;
+    p.dgamma = lnb->dgamma; p.dbeta = lnb->dbeta; p.dbias = lnb->dbias;
+    z = nullptr;
+  }
   if (ln) {
     B200_REQUIRE(p.n_tiles == 1 && conv_tc_ln_supported(cout), B200_ERR_UNSUPPORTED,
                  "conv3x3+LayerNorm tcgen05: Cout=%d needs a single N tile (64 or 128)", cout);
@@ -961,13 +1149,14 @@ int conv_tc_launch(const b200_tensor* x_in, const void* wmat, int cin, int cout,
     cudaFuncSetAttribute(conv3x3_tc_kernel<false, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT - 1024);
     cudaFuncSetAttribute(conv3x3_tc_kernel<false, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT - 1024);
     cudaFuncSetAttribute(conv3x3_tc_kernel<false, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT - 1024);
+    cudaFuncSetAttribute(conv3x3_tc_kernel<false, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT - 1024);
   }
   if (p.cg2) {
     // one cluster of two CTAs (the two SMs of a TPC) per tile pair; persistent over 74 clusters
     int clusters = p.total_items < sm_count() / 2 ? p.total_items : sm_count() / 2;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(2 * clusters);
-    cfg.blockDim = dim3(p.ln && p.BN == 64 ? NTHREADS2 : NTHREADS);
+    cfg.blockDim = dim3((p.ln && p.BN == 64) || p.lnb ? NTHREADS2 : NTHREADS);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
     cudaLaunchAttribute attr[2];
@@ -977,7 +1166,8 @@ int conv_tc_launch(const b200_tensor* x_in, const void* wmat, int cin, int cout,
     attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr; cfg.numAttrs = pdl_enabled(2ull * clusters) ? 2 : 1;
     cudaError_t e;
-    if (p.ln && p.BN == 64) e = cudaLaunchKernelEx(&cfg, conv3x3_tc_kernel<false, 1, true>, tm_x, tm_b, tm_y, tm_z, p);
+    if (p.lnb) e = cudaLaunchKernelEx(&cfg, conv3x3_tc_kernel<false, 4, true>, tm_x, tm_b, tm_y, tm_z, p);
+    else if (p.ln && p.BN == 64) e = cudaLaunchKernelEx(&cfg, conv3x3_tc_kernel<false, 1, true>, tm_x, tm_b, tm_y, tm_z, p);
     else if (p.ln) e = cudaLaunchKernelEx(&cfg, conv3x3_tc_kernel<false, 2, true>, tm_x, tm_b, tm_y, tm_z, p);
     else e = cudaLaunchKernelEx(&cfg, conv3x3_tc_kernel<false, 3, true>, tm_x, tm_b, tm_y, tm_z, p);
     if (e != cudaSuccess) { check_launch("conv3x3_tc_kernel (CTA pairs)"); return fail(B200_ERR_LAUNCH, "conv3x3_tc_kernel (CTA pairs): %s", cudaGetErrorString(e)); }

@@ -278,7 +278,7 @@ int scale_inplace(float* p, size_t count, float s, cudaStream_t st) {
 bool conv_tc_supported(const b200_tensor* x, int cin, int cout, const b200_tensor* y, int ks);
 int conv_tc_launch(const b200_tensor* x, const void* wmat, int cin, int cout, int tap_rev, int b_mn, const float* bias,
                    const b200_tensor* y, int act, int accumulate, cudaStream_t st, const struct ConvLnArgs* ln, int ks,
-                   void* ws, size_t ws_bytes, const void* wmat_k = nullptr, int allow_pairs = 1);
+                   void* ws, size_t ws_bytes, const void* wmat_k = nullptr, int allow_pairs = 1, const struct ConvLnBwdArgs* lnb = nullptr);
 bool conv_gemm_wanted(const b200_tensor* x, int cin, int cout, int ks);
 size_t conv_gemm_workspace(const b200_tensor* x, int cin, int cout, int ks);
 bool wgrad_tc_supported(const b200_tensor* x, const b200_tensor* dy, int ks);

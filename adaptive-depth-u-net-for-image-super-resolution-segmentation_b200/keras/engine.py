@@ -178,7 +178,8 @@ class Plan:
         self.output_val = self.vals[id(model.outputs[0])]
         self.steps: List[Callable[[], None]] = []       # forward launches
         self.bwd_steps: List[Callable[[], None]] = []   # backward launches (training only)
-        self.pre_steps: List[Callable[[], None]] = []   # weight repacks
+        self.pre_steps: List[Callable[[], None]] = []   # (unused: weight repacks sit in front of their layer's forward step)
+        self._repacked = set()
         self._resample_cache = {}
         # synchronised BatchNorm: training plans of a distributed model that has BatchNormalization layers
         self.sync_bn = bool(training and model._dist is not None and model._world() > 1 and model.sync_batchnorm
@@ -187,11 +188,7 @@ class Plan:
         self._build_forward()
         if training:
             self._build_backward()
-        # K-major packs of the filters that have one (see Model._filter): re-derived from the shadow at the start of a step
-        packed = {id(f): f for f in (model._filters.get(op.layer.name) for op in self.ops if op.kind == "conv")
-                  if f is not None and f.ohwi is not None}
-        for f in packed.values():
-            self.pre_steps.append(f.repack)
+
 
     # ------------------------------------------------------------------ buffers
     def _new(self, v: Val, grad=False):
@@ -247,10 +244,20 @@ class Plan:
         npix = lambda v: self.batch * v.h * v.w
         self.step_tags: List[str] = []
 
+        self.fwd_reads: List[list] = []   # flat kernel ranges (offset, count) of the compute-dtype shadow each forward step reads
+        self._cur_reads = []
+
         class _Tagged(list):
             def append(inner, fn, _tags=self.step_tags):
                 _tags.append(self._cur_tag)
+                self.fwd_reads.append(list(self._cur_reads))
+                self._cur_reads = []
                 list.append(inner, fn)
+
+        def reads(ly):
+            r = m._grad_range(ly, "kernel")
+            if r is not None:
+                self._cur_reads.append(r)
 
         S = self.steps = _Tagged()
         # split-K scratch of the small-spatial (deep-level) convolutions, fprop and dgrad: ONE buffer per plan, handed to
@@ -295,6 +302,8 @@ class Plan:
                     continue     # executed by the following LayerNormalization op (one fused kernel)
                 filt, bias = m._filter(op.layer), m._param(op.layer, "bias")
                 src = self._stem_source(op, S)
+                self._emit_repack(filt, S)
+                reads(op.layer)
                 if src is not None:
                     filt = m._stem_padded(op.layer)[0]
                     S.append(lambda xc=src, f=filt, b=bias, y=op.output, o=op:
@@ -313,6 +322,8 @@ class Plan:
                     src = self._stem_source(cs, S)
                     xin = src if src is not None else cs.inputs[0].buf
                     filt = m._stem_padded(cs.layer)[0] if src is not None else m._filter(cs.layer)
+                    self._emit_repack(filt, S)
+                    reads(cs.layer)
                     self._cur_tag = "conv+ln" + (":tc" if self.is_tc(cs) else ":simt")
                     S.append(lambda x=xin, f=filt, cb=m._param(cs.layer, "bias"),
                              z=op.inputs[0], y=op.output, o=op, g=g, b=b:
@@ -358,6 +369,7 @@ class Plan:
                 S.append(lambda x=op.inputs[0], y=op.output: ops.maxpool2_fwd(x.buf, y.buf))
             elif k == "convT":
                 kern, bias = m._shadow(op.layer, "kernel"), m._param(op.layer, "bias")
+                reads(op.layer)
                 S.append(lambda x=op.inputs[0], y=op.output, kk=kern, b=bias:
                          ops.convT2x2_fprop(x.buf, kk, b, y.buf, ws=self.conv_ws))
             elif k == "concat":
@@ -369,6 +381,17 @@ class Plan:
                 S.append(lambda z=op.inputs[0], p=op.output: ops.softmax_fwd(z.buf, p.buf))
             else:
                 raise AssertionError(k)
+
+    def _emit_repack(self, filt, S):
+        """The K-major pack of a filter that has one (Model._filter) is re-derived from the shadow right before the layer's
+        first forward use -- behind the all-gather of its bucket under the sharded optimizer."""
+        if filt is None or filt.ohwi is None or id(filt) in self._repacked:
+            return
+        self._repacked.add(id(filt))
+        tag, rd = self._cur_tag, self._cur_reads
+        self._cur_tag, self._cur_reads = "repack", []
+        S.append(filt.repack)
+        self._cur_tag, self._cur_reads = tag, rd
 
     def _stem_source(self, op, S):
         """Narrow-input 3x3 conv under the bf16 policy: emit the im2col launch and return the [B,H,W,64]
@@ -456,10 +479,32 @@ class Plan:
                     B.append(lambda x=x, o=out, dw=dw, kh=kh: ops.conv2d_wgrad(x.buf, o.grad, kh, kh, dw, self.wgrad_ws))
                 if x.needs_grad:
                     acc = write_flag(x)
-                    self._cur_tag = "dgrad" + sfx
-                    B.append(lambda x=x, o=out, f=filt, acc=acc: ops.conv2d_dgrad(o.grad, f, x.grad, acc, ws=self.conv_ws))
+                    # (measured, tools/lnb_probe.py: the fused epilogue is latency-bound -- 194 us against 75 + 85 us for
+                    # the two kernels at 64 x 128^2 x 64 -- so the engine keeps them apart unless B200_FUSE_LN_BWD=1)
+                    lnop = self._ln_producer(x) if (sfx == ":tc" and not acc and getattr(op, "xcol", None) is None
+                                                    and os.environ.get("B200_FUSE_LN_BWD", "0") == "1") else None
+                    if lnop is not None and ops.conv2d_dgrad_ln_bwd_supported(out.grad, filt, lnop.inputs[0].grad):
+                        # the input is a LayerNormalization(+ReLU) output read by this convolution only: its backward pass
+                        # runs in this dgrad's epilogue (dy of the LayerNorm output never reaches memory); the "ln" op
+                        # below then has nothing left to do
+                        z, lly = lnop.inputs[0], lnop.layer
+                        lnop.bwd_fused = True
+                        z.mark_grad_written()
+                        dbias = m._grad(lnop.conv_src.layer, "bias") if lnop.conv_src is not None else None
+                        writes(lly, "gamma", "beta")
+                        if lnop.conv_src is not None:
+                            writes(lnop.conv_src.layer, "bias")
+                        self._cur_tag = "dgrad+ln" + sfx
+                        B.append(lambda o=out, f=filt, z=z, lo=lnop, g=m._param(lly, "gamma"), b=m._param(lly, "beta"),
+                                 dg=m._grad(lly, "gamma"), db=m._grad(lly, "beta"), dbias=dbias:
+                                 ops.conv2d_dgrad_ln_bwd(o.grad, f, z.buf, lo.mean, lo.rstd, g, b, lo.relu, z.grad, dg, db, dbias))
+                    else:
+                        self._cur_tag = "dgrad" + sfx
+                        B.append(lambda x=x, o=out, f=filt, acc=acc: ops.conv2d_dgrad(o.grad, f, x.grad, acc, ws=self.conv_ws))
             elif k == "ln":
                 z, ly = op.inputs[0], op.layer
+                if getattr(op, "bwd_fused", False):
+                    continue                        # done in the epilogue of the consumer's dgrad (see "conv" above)
                 assert not z.grad_written, "LayerNormalization input must have a single consumer"
                 z.mark_grad_written()
                 dbias = m._grad(op.conv_src.layer, "bias") if op.conv_src is not None else None
@@ -533,6 +578,17 @@ class Plan:
                 op.inputs[0].mark_grad_written()
             else:
                 raise AssertionError(k)
+
+    def _ln_producer(self, v: Val):
+        """The LayerNormalization op whose output is `v`, when `v` is read by ONE op only (so that the gradient this
+        consumer produces is the whole gradient), is not part of a concat buffer and is 64 bf16 channels wide."""
+        if v.parent is not None or v.children or v.c != 64 or v.dtype != torch.bfloat16:
+            return None
+        prod = [o for o in self.ops if o.output is v]
+        cons = [o for o in self.ops if v in o.inputs]
+        if len(prod) != 1 or prod[0].kind != "ln" or len(cons) != 1 or v is self.output_val:
+            return None
+        return prod[0]
 
     @staticmethod
     def is_tc(op) -> bool:

@@ -563,7 +563,7 @@ class Model:
         if getattr(self, "_bucket_cache", None) is None:
             self._bucket_cache = {}
         if key not in self._bucket_cache:
-            elems = int(float(os.environ.get("B200_BUCKET_MB", "32")) * (1 << 20) / 4)
+            elems = int(float(os.environ.get("B200_BUCKET_MB", "64")) * (1 << 20) / 4)
             world = self._world()
             if self._sharded():
                 # kernel region: buckets that divide evenly over the ranks (reduce-scatter / sharded Adam / all-gather)
@@ -593,9 +593,38 @@ class Model:
 
     # ---- one training step, as launch sequences ------------------------------------------------
     def _seg_forward(self, plan: Plan, st):
-        self.G.zero_()
-        plan.run_pre()
-        plan.run_forward()
+        self._seg_forward_part(plan, 0, len(plan.steps))
+        self._seg_loss(plan, st)
+
+    def _seg_forward_part(self, plan: Plan, a: int, b: int):
+        if a == 0:
+            self.G.zero_()
+            plan.run_pre()
+        for f in plan.steps[a:b]:
+            f()
+
+    def _forward_segments(self, plan: Plan):
+        """Sharded optimizer: the forward pass cut where it first needs another bucket of the bf16 shadow, so that the
+        all-gathers issued behind Adam overlap the NEXT step's forward pass (first layers' bucket first) instead of
+        standing between two steps: [(first_step, last_step_exclusive, [indices of the buckets to wait for])]."""
+        n = len(plan.steps)
+        if not self._sharded():
+            return [(0, n, [])]
+        buckets = self._buckets(plan)
+        segs, seen, start, waits = [], set(), 0, []
+        for i, rd in enumerate(plan.fwd_reads):
+            need = [k for k, bk in enumerate(buckets) if bk["sharded"] and k not in seen
+                    and any(o < bk["hi"] and o + c > bk["lo"] for (o, c) in rd)]
+            if need:
+                if i > start:
+                    segs.append((start, i, waits))
+                    start, waits = i, []
+                waits = waits + need
+                seen.update(need)
+        segs.append((start, n, waits))
+        return segs
+
+    def _seg_loss(self, plan: Plan, st):
         self.loss.launch(plan, st, grad_scale=1.0 / self._world())
         ls = self.optimizer.loss_scale_state() if hasattr(self.optimizer, "loss_scale_state") else None
         if ls is not None:      # dynamic loss scaling: d(loss)/d(pred) *= scale (device-resident, so the graph stays valid)
@@ -713,17 +742,35 @@ class Model:
             return
         self.optimizer.apply(self, self._update_ranges(plan))
 
-    def _gather_updated(self, plan):
+    def _gather_updated(self, plan, order=None):
         """Sharded optimizer: publish the updated shards of the compute-dtype shadow (the fp32 master of the kernel
-        region stays sharded until someone reads the weights, see _sync_master)."""
+        region stays sharded until someone reads the weights, see _sync_master).  With `order` (bucket indices in the
+        order the next forward pass needs them) the all-gathers are only ISSUED, in that order, and their handles kept in
+        self._ag_works: the next step waits for each one right before the forward segment that reads its bucket."""
         if not self._sharded():
             return
         from ..parallel import all_gather_bucket
         dist, group = self._dist
-        works = [all_gather_bucket(dist, self.S, b, group=group, async_op=True) for b in self._buckets(plan) if b["sharded"]]
-        for w in works:
-            w.wait()
+        buckets = self._buckets(plan)
+        self._finish_gather()
+        if order is None:
+            works = [all_gather_bucket(dist, self.S, b, group=group, async_op=True) for b in buckets if b["sharded"]]
+            for w in works:
+                w.wait()
+        else:
+            rest = [k for k, b in enumerate(buckets) if b["sharded"] and k not in order]
+            self._ag_works = {k: all_gather_bucket(dist, self.S, buckets[k], group=group, async_op=True)
+                              for k in list(order) + rest}
         self._master_plan = plan if self.S is not self.P else None
+
+    def _finish_gather(self):
+        """Wait (stream-wise) for every shadow all-gather still in flight: before anything but the segmented training
+        step reads the shadow (evaluation, weight IO, another plan)."""
+        works = getattr(self, "_ag_works", None)
+        if works:
+            for w in works.values():
+                w.wait()
+            works.clear()
 
     def gathered_gradients(self, plan=None):
         """Collective (every rank): a copy of the flat gradient buffer with every bucket fully reduced -- under the
@@ -740,6 +787,7 @@ class Model:
 
     def _sync_master(self):
         """Collective (call on every rank): all-gather the fp32 master of the kernel region after sharded steps."""
+        self._finish_gather()
         plan = getattr(self, "_master_plan", None)
         if plan is None or self._dist is None:
             return
@@ -754,6 +802,7 @@ class Model:
         key = ("train", batch)
         if key in self._graphs:
             return self._graphs[key]
+        self._finish_gather()          # (the warm-up below reads the shadow outside the segmented step)
         plan = self._plan(batch, True)
         st = self.loss.make_state(plan)
         self.optimizer.ensure_state(self)
@@ -778,12 +827,20 @@ class Model:
                 # data parallel: the NCCL all-reduces stay OUTSIDE the graphs (launched eagerly, async, on
                 # NCCL's stream) and the backward pass is captured in segments that end where a gradient
                 # bucket becomes complete, so each bucket's exchange overlaps the following segment
+                fsegs = []
+                for (a, b, waits) in self._forward_segments(plan):
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g):
+                        self._seg_forward_part(plan, a, b)
+                    fsegs.append((g, waits))
+                entry["fsegs"] = fsegs
+                entry["ag_order"] = [k for _, waits in fsegs for k in waits]
                 segs = []
                 for k, (a, b, buckets) in enumerate(self._segments(plan)):
                     g = torch.cuda.CUDAGraph()
                     with torch.cuda.graph(g):
                         if k == 0:
-                            self._seg_forward(plan, st)
+                            self._seg_loss(plan, st)
                         self._run_bwd(plan, a, b)
                     segs.append((g, buckets))
                 ga = torch.cuda.CUDAGraph()
@@ -798,6 +855,14 @@ class Model:
         if entry["graph"] is not None:
             entry["graph"].replay()
         elif entry["segments"] is not None:
+            pend = getattr(self, "_ag_works", None) or {}
+            for g, waits in entry["fsegs"]:
+                for k in waits:                      # the previous step's all-gather of the bucket this segment reads first
+                    w = pend.pop(k, None)
+                    if w is not None:
+                        w.wait()
+                g.replay()
+            self._finish_gather()
             works = []
             for g, buckets in entry["segments"]:
                 g.replay()
@@ -806,13 +871,15 @@ class Model:
                 w.wait()
             self._check_finite()
             entry["adam_graph"].replay()
-            self._gather_updated(entry["plan"])
+            overlap = os.environ.get("B200_DP_OVERLAP_GATHER", "1") == "1"
+            self._gather_updated(entry["plan"], entry["ag_order"] if overlap else None)
             self._last_train_plan = entry["plan"]
         else:
             self._train_body(entry["plan"], entry["state"])
 
     def release_graphs(self):
         """Drop every captured graph (call before torch.distributed.destroy_process_group)."""
+        self._finish_gather()
         self._graphs = {}
         torch.cuda.synchronize()
 
@@ -936,6 +1003,7 @@ class Model:
         return PendingStep(res["done"][k], res["host"][k], names, slots)
 
     def test_on_batch(self, x, y):
+        self._finish_gather()
         batch = int(x.shape[0])
         e = self._eval_state(batch, True)
         plan, st = e["plan"], e["state"]
@@ -947,6 +1015,7 @@ class Model:
     def __call__(self, x, training=False):
         if training:
             raise NotImplementedError("Model(x, training=True): use train_on_batch / fit")
+        self._finish_gather()
         batch = int(x.shape[0])
         e = self._eval_state(batch, False)
         plan = e["plan"]

@@ -123,6 +123,19 @@ def conv2d_dgrad(dy, filt: ConvFilter, dx, accumulate=False, algo=ALGO_AUTO, ws=
     return dx
 
 
+def conv2d_dgrad_ln_bwd_supported(dy, filt: ConvFilter, dz) -> bool:
+    return bool(lib().b200_conv2d_dgrad_ln_bwd_supported(tdesc(dy), filt.struct(), tdesc(dz)))
+
+
+def conv2d_dgrad_ln_bwd(dy, filt: ConvFilter, z, mean, rstd, gamma, beta, relu, dz, dgamma, dbeta, dbias):
+    """dz = LayerNorm(+ReLU) backward of (conv dgrad of dy), the dgrad result never leaving the kernel; the parameter
+    gradients are ADDED to dgamma / dbeta / dbias."""
+    check(lib().b200_conv2d_dgrad_ln_bwd(tdesc(dy), filt.struct(), tdesc(z), _ptr(mean), _ptr(rstd), _ptr(gamma), _ptr(beta),
+                                         int(relu), tdesc(dz), _ptr(dgamma), _ptr(dbeta), _ptr(dbias), _stream()),
+          "conv2d_dgrad_ln_bwd")
+    return dz
+
+
 def conv2d_wgrad_workspace(x, dy, kh, kw, algo=ALGO_AUTO) -> int:
     return int(lib().b200_conv2d_wgrad_workspace(tdesc(x), tdesc(dy), kh, kw, algo))
 

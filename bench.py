@@ -219,10 +219,14 @@ def conv_flops(op, batch):
 
 def profile_step(model, plan, st):
     """One eager step with CUDA events around every launch closure: per-kernel-class time, and the
-    algorithmic FLOPs / time of the tcgen05 conv kernel (fprop + dgrad launches)."""
+    algorithmic FLOPs / time of the tcgen05 conv kernel (fprop + dgrad launches).  The stream is first held busy by a
+    ~10 ms spin kernel while the host enqueues the whole step, so that the events bracket DEVICE time only -- an eager
+    launch otherwise shows a ~10 us floor per launch that is the host's enqueue latency, not the kernel."""
     import torch
     from b200unet import ops
     rec = []
+    torch.cuda.synchronize()
+    torch.cuda._sleep(20_000_000)
 
     def timed(tag, fn):
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -429,7 +433,8 @@ def run_gpu(args):
     flops_fprop = sum(conv_flops(op, batch) for op in conv_ops)
     flops_dgrad = sum(conv_flops(op, batch) for op in conv_ops if op.inputs[0].needs_grad)
     # every launch of conv3x3_tc_kernel: plain fprop, fprop with the fused LayerNorm epilogue, dgrad
-    t_conv = prof.get("fwd:conv:tc", 0.0) + prof.get("fwd:conv+ln:tc", 0.0) + prof.get("bwd:dgrad:tc", 0.0)
+    t_conv = (prof.get("fwd:conv:tc", 0.0) + prof.get("fwd:conv+ln:tc", 0.0) + prof.get("bwd:dgrad:tc", 0.0)
+              + prof.get("bwd:dgrad+ln:tc", 0.0))      # (dgrad launches with the fused LayerNorm backward epilogue)
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))

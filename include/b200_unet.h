@@ -107,6 +107,19 @@ int b200_conv2d_ln_fprop(const b200_tensor* x, const b200_filter* f, const float
 /* dx (+)= conv_transpose(dy, f)  -- autodiff of the above w.r.t. its input. */
 int b200_conv2d_dgrad(const b200_tensor* dy, const b200_filter* f, const b200_tensor* dx,
                       int accumulate, int algo, const b200_scratch* ws, void* stream);
+/* dgrad with the backward pass of the LayerNormalization(+ReLU) that PRODUCED the convolution's input fused into its
+ * epilogue (autodiff of conv_block's Conv2D <- ReLU <- LayerNormalization chain, train_adaptive_unet.py:202-209): the
+ * accumulator tile is dy of the LayerNorm output; with that layer's saved pre-norm activations z, its per-pixel mean /
+ * rstd and gamma / beta the kernel writes
+ *     dz = rstd * (g - mean_c(g) - xhat * mean_c(g * xhat)),   g = dy * [relu: y > 0] * gamma,  xhat = (z - mean) * rstd
+ * and ADDS sum_pixels(dy_masked * xhat) to dgamma, sum_pixels(dy_masked) to dbeta and sum_pixels(dz) to dbias (the bias
+ * gradient of the convolution that produced z); any of the three may be NULL.  dy of the LayerNorm output is never
+ * written to memory.  b200_conv2d_dgrad_ln_bwd_supported tells whether the shapes take this kernel (3x3 bf16 filter, 64
+ * input channels, <= 128 output channels, plain 16x8 tiles); otherwise call b200_conv2d_dgrad + b200_layernorm_bwd. */
+int b200_conv2d_dgrad_ln_bwd_supported(const b200_tensor* dy, const b200_filter* f, const b200_tensor* dz);
+int b200_conv2d_dgrad_ln_bwd(const b200_tensor* dy, const b200_filter* f, const b200_tensor* z, const float* mean,
+                             const float* rstd, const float* gamma, const float* beta, int relu, const b200_tensor* dz,
+                             float* dgamma, float* dbeta, float* dbias, void* stream);
 /* Scratch of the split-K path that serves small-spatial layers (images <= 4x4 pixels, the deep U-Net
  * levels): b200_conv2d_workspace returns the bytes fprop (dgrad = 0, x = the input) or dgrad (dgrad = 1,
  * x = dy) of this layer needs in `ws` (0 = the layer does not take that path; `ws` may then be NULL).

@@ -834,3 +834,45 @@ def test_binary_confusion_counters(dtype):
     pos, lab = pred.float().cpu() > 0.5, tgt.cpu() != 0
     want = [float((pos & lab).sum()), float((pos & ~lab).sum()), float((~pos & lab).sum()), float((pos.float() == tgt.cpu()).sum())]
     assert counts.tolist() == want
+
+
+@pytest.mark.parametrize("shape", [(2, 32, 32, 64), (1, 20, 13, 128), (3, 16, 24, 64), (1, 33, 9, 128), (2, 128, 128, 64)])
+@pytest.mark.parametrize("relu", [True, False])
+def test_conv_dgrad_ln_bwd_fused(shape, relu):
+    """dgrad with the LayerNorm(+ReLU) backward of its input's producer fused into the epilogue (CTA-pair kernel, 64-channel
+    input): dz, d(gamma), d(beta) and d(bias) = sum(dz) against torch autograd through relu(LN(z)) -> conv, and against
+    the unfused pair of kernels (b200_conv2d_dgrad + b200_layernorm_bwd) on the same buffers."""
+    ops, K = _ops(), _K()
+    n, h, w, co = shape
+    ci, dt = 64, torch.bfloat16
+    z = rand((n, h, w, ci), 171, dt, 2.0)
+    wt = rand((3, 3, ci, co), 172, dt, 0.1)
+    dy = rand((n, h, w, co), 173, dt)
+    g = (1 + 0.3 * rand((ci,), 174)).contiguous(); be = rand((ci,), 175, scale=0.3)
+    filt = ops.ConvFilter(wt)
+    y = torch.empty_like(z); mean = torch.empty(n * h * w, device="cuda"); rstd = torch.empty_like(mean)
+    ops.layernorm_fwd(z, g, be, 1e-3, relu, y, mean, rstd)
+    dz = torch.full_like(z, 7.0)
+    assert ops.conv2d_dgrad_ln_bwd_supported(dy, filt, dz)
+    dg = torch.full((ci,), 0.5, device="cuda"); db = torch.full((ci,), -0.25, device="cuda"); dbias = torch.full((ci,), 2.0, device="cuda")
+    ops.conv2d_dgrad_ln_bwd(dy, filt, z, mean, rstd, g, be, relu, dz, dg, db, dbias)
+    torch.cuda.synchronize()
+    # oracle: autograd through relu(LN(z)) -> conv
+    zr, gr, br = f32(z).requires_grad_(), f32(g).requires_grad_(), f32(be).requires_grad_()
+    yr = K.layer_norm(zr, gr, br)
+    yr = torch.relu(yr) if relu else yr
+    (K.conv2d_same(yr, f32(wt)) * f32(dy)).sum().backward()
+    e = (relerr(dz, zr.grad), relerr(dg - 0.5, gr.grad), relerr(db + 0.25, br.grad), relerr(dbias - 2.0, zr.grad.sum(dim=(0, 1, 2))))
+    print(f"dgrad+LN bwd {shape} relu={relu}: dz {e[0]:.2e} dgamma {e[1]:.2e} dbeta {e[2]:.2e} dbias {e[3]:.2e}")
+    assert e[0] < 1e-2 and e[1] < 1e-2 and e[2] < 1e-2
+    assert e[3] < 2e-2 or float(zr.grad.sum(dim=(0, 1, 2)).abs().max()) < 1e-3      # sum(dz): a cancellation (about 0 per pixel)
+    # the unfused kernels on the same buffers: dz agrees to bf16 rounding of the intermediate dy they store
+    dx = torch.empty_like(z); dz2 = torch.empty_like(z)
+    dg2 = torch.zeros(ci, device="cuda"); db2 = torch.zeros(ci, device="cuda"); dbias2 = torch.zeros(ci, device="cuda")
+    ops.conv2d_dgrad(dy, filt, dx, False)
+    ops.layernorm_bwd(dx, z, mean, rstd, g, be, relu, dz2, dg2, db2, dbias2)
+    assert relerr(dz, dz2) < 1e-2 and relerr(dg - 0.5, dg2) < 1e-2 and relerr(db + 0.25, db2) < 1e-2
+    # shapes outside the fused kernel are refused, not mis-computed
+    z32 = rand((n, h, w, 128), 176, dt)
+    f2 = ops.ConvFilter(rand((3, 3, 128, 64), 177, dt, 0.1))
+    assert not ops.conv2d_dgrad_ln_bwd_supported(rand((n, h, w, 64), 178, dt), f2, z32)

@@ -55,7 +55,7 @@ def main():
     g_dp = m_dp.gathered_gradients()
     m_dp._sync_master()
     w_dp = m_dp.get_weights()
-    loss_dp = torch.tensor([logs["loss"]], dtype=torch.float64)
+    loss_dp = torch.tensor([logs["loss"]], dtype=torch.float64, device="cuda")
     dist.all_reduce(loss_dp)
 
     m_1 = make(False)
