@@ -466,7 +466,8 @@ class Plan:
                 writes(ly, "kernel")
                 # the step zeroes the flat gradient buffer first, so the tcgen05 wgrad kernels add their partial sums
                 # straight into it (vector atomics): no partial slabs, no reduce launch
-                atomic = sfx == ":tc" and os.environ.get("B200_WGRAD_ATOMIC", "1") == "1"
+                atomic = (sfx == ":tc" and os.environ.get("B200_WGRAD_ATOMIC", "1") == "1"
+                          and not getattr(m, "deterministic", False))
                 if getattr(op, "xcol", None) is not None:     # stem: 1x1 wgrad over the im2col tensor
                     if atomic:
                         B.append(lambda xc=op.xcol, o=out, dw=m._stem_padded(ly)[1]: ops.conv2d_wgrad_atomic(xc, o.grad, 1, 1, dw))

@@ -138,6 +138,13 @@ class Model:
         # forward and the backward pass), so N ranks x B/N samples train exactly like one rank x B samples
         # (B200_SYNC_BN=0 keeps per-replica statistics)
         self.sync_batchnorm = os.environ.get("B200_SYNC_BN", "1") == "1"
+        # deterministic=True (or B200_DETERMINISTIC=1; set before the first step): filter gradients through per-CTA
+        # partial slabs + a fixed-order reduce kernel instead of fp32 vector atomics into the gradient buffer (the
+        # default, ~3 % faster, sums in an order that varies run to run).  Activations and activation gradients are
+        # bit-reproducible either way (no atomics on those paths: tests/test_model_zz_determinism_gpu.py); the short
+        # per-channel reductions (gamma / beta / bias gradients, loss sums) still end in one fp32 atomic per block,
+        # reproducible to ~1e-7 relative, not bitwise.
+        self.deterministic = os.environ.get("B200_DETERMINISTIC", "0") == "1"
         self.input_shape = self.inputs[0].shape
         self.output_shape = self.outputs[0].shape
 
@@ -847,6 +854,26 @@ class Model:
                 with torch.cuda.graph(ga):
                     self._apply_optimizer(plan)
                 entry["segments"], entry["adam_graph"] = segs, ga
+                # Pipelined optimizer (sharded, no loss scaling -- whose finite check needs the complete gradient): a
+                # bucket's shard is updated and its shadow all-gathered one backward segment after its reduce-scatter was
+                # issued (the dgrad that still reads its first layer's weights sits at the head of that next segment), so
+                # at the end of the step only the LAST bucket's reduce-scatter -> Adam -> all-gather chain is exposed.
+                if (self._sharded() and not getattr(self.optimizer, "dynamic_loss_scale", False)
+                        and os.environ.get("B200_DP_PIPELINE_ADAM", "1") == "1"):
+                    from ..parallel import shard_of
+                    dist, group = self._dist
+                    rank, world = dist.get_rank(group), dist.get_world_size(group)
+                    adv = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(adv):
+                        self.optimizer.advance()
+                    per = {}
+                    for k, bk in enumerate(self._buckets(plan)):
+                        rng = shard_of(bk, rank, world) if bk["sharded"] else (bk["lo"], bk["hi"])
+                        gk = torch.cuda.CUDAGraph()
+                        with torch.cuda.graph(gk):
+                            self.optimizer.apply_ranges(self, [rng])
+                        per[k] = gk
+                    entry["adam_advance"], entry["adam_buckets"] = adv, per
         self._graphs[key] = entry
         return entry
 
@@ -863,6 +890,9 @@ class Model:
                         w.wait()
                 g.replay()
             self._finish_gather()
+            if "adam_buckets" in entry:
+                self._run_bwd_pipelined(entry)
+                return
             works = []
             for g, buckets in entry["segments"]:
                 g.replay()
@@ -876,6 +906,34 @@ class Model:
             self._last_train_plan = entry["plan"]
         else:
             self._train_body(entry["plan"], entry["state"])
+
+    def _run_bwd_pipelined(self, entry):
+        """Backward segments with the optimizer pipelined behind them (see _train_state): reduce-scatter of a bucket
+        right after the segment that completes it; its Adam shard update and the all-gather of its shadow one segment
+        later; the handles of the all-gathers are left for the next step's forward segments (self._ag_works)."""
+        from ..parallel import all_gather_bucket
+        dist, group = self._dist
+        plan = entry["plan"]
+        buckets = self._buckets(plan)
+        index = {id(b): k for k, b in enumerate(buckets)}
+        self._ag_works = {}
+
+        def finish(batch):
+            for k, w in batch:
+                w.wait()
+                entry["adam_buckets"][k].replay()
+                if buckets[k]["sharded"]:
+                    self._ag_works[k] = all_gather_bucket(dist, self.S, buckets[k], group=group, async_op=True)
+
+        entry["adam_advance"].replay()
+        prev = []
+        for g, ready in entry["segments"]:
+            g.replay()
+            finish(prev)
+            prev = list(zip([index[id(b)] for b in ready], self._reduce_async(ready)))
+        finish(prev)
+        self._master_plan = plan if self.S is not self.P else None
+        self._last_train_plan = plan
 
     def release_graphs(self):
         """Drop every captured graph (call before torch.distributed.destroy_process_group)."""

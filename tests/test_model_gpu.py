@@ -637,3 +637,32 @@ def test_sr_unet_step_at_baseline_topologies(cfg):
     print(f"[{name}] worst weight-gradient relerr {worst:.3e} over {i} tensors")
     assert not bad, bad
     _setup("float32")
+
+
+def test_deterministic_filter_gradients():
+    """Model.deterministic = True: the filter gradients (the slab + fixed-order reduce path) are BIT-identical between two
+    runs from the same state and between the single-stream and the two-stream schedule; they agree with the default
+    (atomic) path to summation-order noise."""
+    from b200unet import builders as B
+    from b200unet.keras.optimizers import Adam
+    rng = np.random.default_rng(2)
+    hr = rng.random((8, 64, 64, 3), dtype=np.float32)
+    lr = np.clip(hr + 0.05 * rng.standard_normal(hr.shape).astype(np.float32), 0, 1)
+    grads = []
+    for det, overlap in ((True, False), (True, True), (True, True), (False, True)):
+        _setup("mixed_bfloat16")
+        model, _ = B.build_super_resolution_unet(0.5, depth_override=3, input_size=64)
+        model.deterministic, model.overlap_wgrad = det, overlap
+        head = model.get_layer("residual_rgb")
+        head.weight_specs[0]["value"] = np.random.default_rng(3).uniform(-0.2, 0.2, (1, 1, 64, 3)).astype(np.float32)
+        loss, metrics = B.build_losses_and_metrics("charbonnier")
+        model.compile(optimizer=Adam(learning_rate=1e-4), loss=loss, metrics=metrics)
+        model.train_on_batch(lr, hr)
+        torch.cuda.synchronize()
+        kernels = torch.cat([model._grad(ly, "kernel").flatten() for ly in model.layers
+                             if type(ly).__name__ == "Conv2D" and ly.kernel_size == (3, 3) and ly.name != model.layers[1].name])
+        grads.append(kernels.clone())
+    assert torch.equal(grads[0].view(torch.int32), grads[1].view(torch.int32))     # single stream == two streams, bitwise
+    assert torch.equal(grads[1].view(torch.int32), grads[2].view(torch.int32))     # run to run, bitwise
+    assert relerr(grads[3], grads[0]) < 1e-5                                       # atomics: order noise only
+    _setup("float32")

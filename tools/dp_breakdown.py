@@ -46,8 +46,12 @@ def main():
     out["buckets"] = [{"mb_fp32": (b["hi"] - b["lo"]) * 4 / 2**20, "sharded": b["sharded"], "ready_after_step": b["ready_after"],
                        "of_steps": len(plan.bwd_steps)} for b in buckets]
     out["segments"] = len(e["segments"])
+    out["forward_segments"] = len(e["fsegs"])
+    out["pipelined_optimizer"] = "adam_buckets" in e
 
     def no_comm():
+        for g, _w in e["fsegs"]:
+            g.replay()
         for g, _b in e["segments"]:
             g.replay()
         e["adam_graph"].replay()
