@@ -104,6 +104,15 @@ SIGNATURES = {
     "b200_loss_scale_apply": (_i, [_vp, _i, _sz, _vp, _vp]),
     "b200_loss_scale_check": (_i, [_vp, _sz, _vp, _vp]),
     "b200_loss_scale_update": (_i, [_vp, _f, _vp]),
+    "b200_peer_alloc": (_i, [C.POINTER(C.c_void_p), _sz]),
+    "b200_peer_free": (_i, [_vp]),
+    "b200_peer_export": (_i, [_vp, _vp]),
+    "b200_peer_open": (_i, [_vp, C.POINTER(C.c_void_p)]),
+    "b200_peer_close": (_i, [_vp]),
+    "b200_peer_signal": (_i, [_vp, _vp]),
+    "b200_peer_wait": (_i, [_vp, _i, _vp, C.c_double, _vp]),
+    "b200_peer_pull": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp]),
+    "b200_peer_gather_sum": (_i, [_vp, _vp, _vp, _vp, _i, _sz, _i, _vp]),
     "b200_cast": (_i, [_vp, _i, _vp, _i, _sz, _vp]),
     "b200_copy_tensor": (_i, [_TP, _TP, _vp]),
     "b200_scale_inplace": (_i, [_vp, _sz, _f, _vp]),

@@ -11,7 +11,7 @@ HERE = Path(__file__).resolve().parent
 CSRC = HERE / "csrc"
 LIB_DIR = HERE / "lib"
 LIB_PATH = LIB_DIR / "libb200unet.so"
-SOURCES = ["api.cu", "conv_simt.cu", "conv_small.cu", "conv_tc.cu", "conv_gemm.cu", "wgrad_tc.cu", "norm.cu", "resample.cu", "loss.cu", "optim.cu", "pipeline.cu", "metrics.cu", "head_mid.cu"]
+SOURCES = ["api.cu", "conv_simt.cu", "conv_small.cu", "conv_tc.cu", "conv_gemm.cu", "wgrad_tc.cu", "norm.cu", "resample.cu", "loss.cu", "optim.cu", "pipeline.cu", "metrics.cu", "head_mid.cu", "peer.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr",

@@ -555,6 +555,34 @@ class Model:
         dist.broadcast(self.P, src=0, group=process_group)
         dist.broadcast(self.NT, src=0, group=process_group)
         self._refresh_shadow()
+        self._peer = None
+        if (os.environ.get("B200_DP_P2P", "0") == "1" and self._sharded() and self.S is not self.P
+                and dist.get_backend(process_group) == "nccl"):
+            self._enable_peer_exchange()
+
+    def _enable_peer_exchange(self):
+        """Move the gradient buffer and the weight shadow into memory every rank of the node can map, so that the
+        exchange of the sharded step runs on copy engines (peer.py / csrc/peer.cu) instead of NCCL kernels.  All ranks
+        agree on the outcome: if the mapping fails anywhere (no peer access, other node) everyone stays on NCCL."""
+        from ..peer import PeerExchange
+        dist, group = self._dist
+        px, err = None, ""
+        try:
+            px = PeerExchange(dist, group, self._device, self.P.numel(), self.S.dtype,
+                              float(os.environ.get("B200_DP_P2P_TIMEOUT", "30")))
+        except Exception as e:     # noqa: BLE001 -- any local failure: report, then agree below
+            err = f"{type(e).__name__}: {e}"
+        ok = torch.tensor([0 if px is None else 1], dtype=torch.int32, device=self._device)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+        if int(ok.item()) == 0:
+            if err:
+                print(f"[b200unet] rank {dist.get_rank(group)}: peer exchange unavailable ({err}); using NCCL", flush=True)
+            return
+        px.S.copy_(self.S)
+        self.G, self.S = px.G, px.S
+        self._filters, self._plans, self._graphs, self._bucket_cache = {}, {}, {}, None
+        self._peer = px
+        self._refresh_shadow()
 
     # ------------------------------------------------------------------ plans
     def _plan(self, batch, training) -> Plan:
@@ -574,9 +602,13 @@ class Model:
             world = self._world()
             if self._sharded():
                 # kernel region: buckets that divide evenly over the ranks (reduce-scatter / sharded Adam / all-gather)
-                bs = plan_buckets(self._kernel_region, plan.bwd_writes, elems, align=64 * world)
+                head = int(float(os.environ.get("B200_HEAD_BUCKET_MB", "1.5")) * (1 << 20) / 4)
+                bs = plan_buckets(self._kernel_region, plan.bwd_writes, elems, align=64 * world, head_elems=head)
+                # the head (first layers; complete only when backward ends, read first by the next forward pass) is
+                # replicated like the vector region: one all-reduce, Adam on every rank, no all-gather to wait for
+                replicate_head = os.environ.get("B200_HEAD_REPLICATED", "1") == "1"
                 for b in bs:
-                    b["sharded"] = True
+                    b["sharded"] = not (replicate_head and b.get("head", False))
                 # vector region (biases, gamma, beta): one small replicated bucket, complete when backward ends
                 bs.append({"lo": self._kernel_region, "hi": self.G.numel(), "ready_after": len(plan.bwd_steps) - 1,
                            "sharded": False})
@@ -716,17 +748,24 @@ class Model:
             dist, group = self._dist
             dist.all_reduce(ls[2:3], op=dist.ReduceOp.MAX, group=group)
 
-    def _reduce_async(self, buckets):
+    def _reduce_async(self, buckets, coalesce=True):
+        """Start the exchange of gradient buckets that just became complete -> handles to wait on (one per bucket, in
+        order, with coalesce=False)."""
         if not buckets:
             return []
         from ..parallel import reduce_scatter_bucket
         dist, group = self._dist
-        works = []
-        for b in buckets:
-            if b["sharded"]:
-                works.append(reduce_scatter_bucket(dist, self.G, b, group=group, async_op=True))
-            else:
-                works.append(dist.all_reduce(self.G[b["lo"]:b["hi"]], group=group, async_op=True))
+        whole = [b for b in buckets if not b["sharded"]]
+        if not (coalesce and len(whole) > 1 and dist.get_backend(group) == "nccl"):
+            return [reduce_scatter_bucket(dist, self.G, b, group=group, async_op=True) if b["sharded"] else
+                    dist.all_reduce(self.G[b["lo"]:b["hi"]], group=group, async_op=True) for b in buckets]
+        works = [reduce_scatter_bucket(dist, self.G, b, group=group, async_op=True) for b in buckets if b["sharded"]]
+        # replicated head + vector region complete together: one grouped NCCL launch instead of two latencies
+        from torch.distributed.distributed_c10d import _coalescing_manager
+        with _coalescing_manager(group, self.G.device, async_ops=True) as cm:
+            for b in whole:
+                dist.all_reduce(self.G[b["lo"]:b["hi"]], group=group)
+        works.append(cm)
         return works
 
     def _update_ranges(self, plan):
@@ -778,6 +817,8 @@ class Model:
             for w in works.values():
                 w.wait()
             works.clear()
+        if getattr(self, "_peer", None) is not None:
+            self._peer.wait_gathers()
 
     def gathered_gradients(self, plan=None):
         """Collective (every rank): a copy of the flat gradient buffer with every bucket fully reduced -- under the
@@ -885,6 +926,8 @@ class Model:
         """Launch one captured (or eager) training step on the data already in the input buffers."""
         if entry["graph"] is not None:
             entry["graph"].replay()
+        elif entry["segments"] is not None and getattr(self, "_peer", None) is not None:
+            self._run_step_p2p(entry)
         elif entry["segments"] is not None:
             pend = getattr(self, "_ag_works", None) or {}
             for g, waits in entry["fsegs"]:
@@ -911,6 +954,65 @@ class Model:
         else:
             self._train_body(entry["plan"], entry["state"])
 
+    def _run_step_p2p(self, entry):
+        """The segmented data-parallel step with the exchange on the copy engines (peer.py): per gradient bucket
+        signal -> wait for the peers -> pull my shard's slices -> sum, on the exchange stream behind the backward segment
+        that completes the bucket; after Adam, signal -> wait -> pull the peers' shards of the shadow in the order the
+        next forward pass reads them (it waits per bucket, on events).  The replicated buckets (head, vector region) still
+        go through one grouped NCCL all-reduce."""
+        from ..parallel import shard_of
+        from ..peer import ADAM_SLOT
+        px, plan = self._peer, entry["plan"]
+        buckets = self._buckets(plan)
+        index = {id(b): k for k, b in enumerate(buckets)}
+        main, cs = torch.cuda.current_stream(), px.stream
+        works = getattr(self, "_ag_works", None)
+        if works:                                     # left by an eager / NCCL step
+            for w in works.values():
+                w.wait()
+            works.clear()
+        if px.ag_plan is not plan:
+            px.wait_gathers()
+        if px.peers_past_adam is not None:
+            main.wait_event(px.peers_past_adam)       # nobody pulls last step's gradients out of my G any more: it may be zeroed
+        for g, waits in entry["fsegs"]:
+            for k in waits:
+                ev = px.ag_events.pop(k, None)
+                if ev is not None:
+                    main.wait_event(ev)
+            g.replay()
+        px.wait_gathers()
+        works = []
+        for g, ready in entry["segments"]:
+            g.replay()
+            mine = [b for b in ready if b["sharded"]]
+            if mine:
+                for b in mine:
+                    px.signal(index[id(b)])
+                cs.wait_event(main.record_event())
+                with torch.cuda.stream(cs):
+                    for b in mine:
+                        px.reduce_scatter(index[id(b)], *shard_of(b, px.rank, px.world))
+            works += self._reduce_async([b for b in ready if not b["sharded"]])
+        main.wait_stream(cs)
+        for w in works:
+            w.wait()
+        self._check_finite()
+        entry["adam_graph"].replay()
+        px.signal(ADAM_SLOT)
+        cs.wait_event(main.record_event())
+        order = list(entry["ag_order"])
+        order += [k for k, b in enumerate(buckets) if b["sharded"] and k not in order]
+        with torch.cuda.stream(cs):
+            px.wait_peers(ADAM_SLOT)
+            px.peers_past_adam = cs.record_event()
+            for k in order:
+                px.all_gather([shard_of(buckets[k], r, px.world) for r in range(px.world)])
+                px.ag_events[k] = cs.record_event()
+        px.ag_plan = plan
+        self._master_plan = plan if self.S is not self.P else None
+        self._last_train_plan = plan
+
     def _run_bwd_pipelined(self, entry):
         """Backward segments with the optimizer pipelined behind them (see _train_state): reduce-scatter of a bucket
         right after the segment that completes it; its Adam shard update and the all-gather of its shadow one segment
@@ -934,7 +1036,7 @@ class Model:
         for g, ready in entry["segments"]:
             g.replay()
             finish(prev)
-            prev = list(zip([index[id(b)] for b in ready], self._reduce_async(ready)))
+            prev = list(zip([index[id(b)] for b in ready], self._reduce_async(ready, coalesce=False)))
         finish(prev)
         self._master_plan = plan if self.S is not self.P else None
         self._last_train_plan = plan
@@ -944,6 +1046,9 @@ class Model:
         self._finish_gather()
         self._graphs = {}
         torch.cuda.synchronize()
+        if getattr(self, "_peer", None) is not None:      # collective: the ranks unmap each other's buffers together
+            self._peer.close()
+            self._peer = None
 
     def _eval_state(self, batch, with_loss):
         key = ("eval", batch, with_loss)

@@ -42,7 +42,8 @@ def complement_ranges(done: Sequence[Tuple[int, int]], total: int) -> List[Tuple
     return [(lo, hi) for lo, hi in rest if hi > lo]
 
 
-def plan_buckets(total: int, writes: Sequence[Sequence[Tuple[int, int]]], bucket_elems: int, align: int = 1) -> List[dict]:
+def plan_buckets(total: int, writes: Sequence[Sequence[Tuple[int, int]]], bucket_elems: int, align: int = 1,
+                 head_elems: int = 0) -> List[dict]:
     """Cut [0, total) into buckets of about `bucket_elems` elements, filled from the END of the buffer
     (backward writes the last layers first), and find for each bucket the index of the last backward
     step that writes into it.
@@ -52,7 +53,13 @@ def plan_buckets(total: int, writes: Sequence[Sequence[Tuple[int, int]]], bucket
     never splits a written range; with align > 1 (sharded optimizer: every bucket must divide evenly
     over the ranks) interior boundaries are snapped down to multiples of `align`, so a range may straddle
     two buckets and counts for the readiness of both.  `total` must be a multiple of `align`.
-    Returns [{"lo", "hi", "ready_after"}] ordered by readiness.
+
+    head_elems > 0 splits the bucket at offset 0 once more: the FIRST layers' gradients are the last ones backward
+    produces, so whatever bucket holds them is exchanged with nothing left to hide it behind, and the next forward
+    pass waits for it first.  Cutting a head of at most about `head_elems` elements off that bucket leaves only a
+    latency-sized exchange exposed; the remainder becomes ready as soon as its own last writer is done.  The head
+    boundary is snapped UP to `align`, so a straddling range delays the (late anyway) head, not the remainder.
+    Returns [{"lo", "hi", "ready_after"}] ordered by readiness (the head bucket, if one was cut, also has "head": True).
     """
     if total % align:
         raise ValueError(f"total {total} is not a multiple of align {align}")
@@ -62,17 +69,25 @@ def plan_buckets(total: int, writes: Sequence[Sequence[Tuple[int, int]]], bucket
         for rng in step:
             if rng[0] < total:
                 last_writer[rng] = max(last_writer.get(rng, -1), i)
-    cuts = [total]
+    cuts, head_cut = [total], None
     for (o, c) in reversed(ranges):
         lo = o // align * align
         if cuts[-1] - lo >= bucket_elems and lo < cuts[-1]:
             cuts.append(lo)
+    if head_elems > 0:
+        heads = [-(-o // align) * align for (o, c) in ranges]
+        heads = [h for h in heads if 0 < h <= head_elems and h < cuts[-1]]
+        if heads and cuts[-1] - max(heads) >= head_elems:      # not worth it when the last bucket is small already
+            cuts.append(max(heads))
+            head_cut = max(heads)
     if cuts[-1] != 0:
         cuts.append(0)
     buckets = []
     for hi, lo in zip(cuts, cuts[1:]):
         ready = max([last_writer[(o, c)] for (o, c) in ranges if o < hi and o + c > lo], default=-1)
         buckets.append({"lo": lo, "hi": hi, "ready_after": ready})
+        if hi == head_cut:
+            buckets[-1]["head"] = True
     if buckets and all(b["ready_after"] < 0 for b in buckets):
         buckets[-1]["ready_after"] = 0
     for b in buckets:

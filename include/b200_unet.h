@@ -347,6 +347,31 @@ int b200_debug_umma_probe(const void* a, int a_rows, const void* b, int start_by
  * operands; cycles[grid] (device int64) receives the elapsed SM cycles per CTA. */
 int b200_debug_umma_rate(int n, int iters, int a_stride_bytes, long long* cycles, int grid, void* stream);
 
+/* ---- data-parallel exchange over NVLink peer memory (one node) -----------------------
+ * The reference trains on one GPU (Super_resolution/code/train_adaptive_unet.py:622-632 is the step that is sharded);
+ * this is the exchange of the batch-sharded step: see csrc/peer.cu for the protocol.
+ *   b200_peer_alloc / _free     : zero-filled device memory that can be exported to the other ranks of the node
+ *   b200_peer_export / _open / _close : cudaIpc handle (B200_PEER_HANDLE_BYTES bytes) of such a buffer / a peer's mapping
+ *   b200_peer_signal            : counter += 1, visible to the peers once everything before it on `stream` is
+ *   b200_peer_wait              : stream waits until each of the n_peers (<= 32) counters has reached *own
+ *                                 (peer_counters = DEVICE array of pointers); traps after timeout_s (<= 0: 30 s)
+ *   b200_peer_pull              : n copy-engine copies peer -> local (host arrays of pointers / devices / sizes)
+ *   b200_peer_gather_sum        : staging[j] <- peer_src[j] (count floats each, copy engines), then
+ *                                 acc[i] += sum_j staging[j][i] in one kernel (reduce-scatter of my shard) */
+#define B200_PEER_HANDLE_BYTES 64
+int b200_peer_alloc(void** out, size_t bytes);
+int b200_peer_free(void* p);
+int b200_peer_export(const void* p, void* handle64);
+int b200_peer_open(const void* handle64, void** out);
+int b200_peer_close(void* p);
+int b200_peer_signal(unsigned long long* counter, void* stream);
+int b200_peer_wait(const unsigned long long* const* peer_counters, int n_peers, const unsigned long long* own,
+                   double timeout_s, void* stream);
+int b200_peer_pull(void* const* dst, const void* const* src, const int* src_device, const size_t* bytes, int n,
+                   int my_device, void* stream);
+int b200_peer_gather_sum(float* acc, float* staging, const void* const* peer_src, const int* peer_device, int n_peers,
+                         size_t count, int my_device, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

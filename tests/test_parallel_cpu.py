@@ -132,6 +132,13 @@ def test_shard_range_and_bucket_plan():
     assert all(x["lo"] % 128 == 0 and x["hi"] % 128 == 0 for x in a) and sum(x["hi"] - x["lo"] for x in a) == 1024
     lows = sorted(x["lo"] for x in a)
     assert lows[0] == 0 and {x["ready_after"] for x in a if x["lo"] <= 500 < x["hi"]} == {2}
+    # head bucket: the first layers (written last) get a small bucket of their own, boundary snapped UP so that the
+    # straddling range delays the head and not the remainder
+    wr = [[(900, 124)], [(300, 600)], [(100, 200)], [(0, 100)]]
+    h = plan_buckets(1024, wr, 2000, align=64, head_elems=150)
+    assert h == [{"lo": 128, "hi": 1024, "ready_after": 2}, {"lo": 0, "hi": 128, "ready_after": 3, "head": True}]
+    assert plan_buckets(1024, wr, 2000, align=64, head_elems=1000) == [{"lo": 0, "hi": 1024, "ready_after": 3}]
+    assert plan_buckets(1024, wr, 2000, align=64) == [{"lo": 0, "hi": 1024, "ready_after": 3}]
     # every element is covered exactly once whatever the bucket size
     for size in (1, 64, 10_000):
         bs = sorted(plan_buckets(1000, writes, size), key=lambda d: d["lo"])

@@ -48,6 +48,7 @@ def main():
     out["segments"] = len(e["segments"])
     out["forward_segments"] = len(e["fsegs"])
     out["pipelined_optimizer"] = "adam_buckets" in e
+    out["exchange"] = "peer memory (copy engines)" if getattr(model, "_peer", None) is not None else "NCCL"
 
     def no_comm():
         for g, _w in e["fsegs"]:

@@ -60,17 +60,33 @@ def main():
     p_ref = p_dp.clone()
     dist.broadcast(p_ref, src=0)
     same = bool((p_ref == p_dp).all().item())
+    # a few more steps (the exchange's cross-step ordering: gradient buffer reuse, shadow pulls overlapping the forward pass)
+    more = int(os.environ.get("B200_DP_CHECK_STEPS", "4"))
+    for _ in range(more):
+        m_dp.train_on_batch(lr[lo:hi], hr[lo:hi])
+    torch.cuda.synchronize()
+    m_dp._sync_master()
+    p_more = m_dp.P.clone()
+    p_ref = p_more.clone()
+    dist.broadcast(p_ref, src=0)
+    same_more = bool((p_ref == p_more).all().item())
+    peer = getattr(m_dp, "_peer", None) is not None
     if rank == 0:
         m_1 = make(False)
         m_1.train_on_batch(lr, hr)
         torch.cuda.synchronize()
         rel = ((g_dp - m_1.G).norm() / m_1.G.norm()).item()
         relp = ((p_dp - m_1.P).norm() / m_1.P.norm()).item()
-        print(f"DP check world={world}: grad rel-L2 vs single-GPU full batch {rel:.3e}; weights after Adam {relp:.3e}; "
-              f"ranks identical: {same}; loss(rank0 shard) {logs['loss']:.6f}", flush=True)
-        assert rel < 2e-2 and same
+        for _ in range(more):
+            m_1.train_on_batch(lr, hr)
+        torch.cuda.synchronize()
+        relm = ((p_more - m_1.P).norm() / m_1.P.norm()).item()
+        print(f"DP check world={world} (exchange: {'peer memory' if peer else 'NCCL'}): grad rel-L2 vs single-GPU full batch "
+              f"{rel:.3e}; weights after Adam {relp:.3e}; after {more} more steps {relm:.3e}; ranks identical: "
+              f"{same and same_more}; loss(rank0 shard) {logs['loss']:.6f}", flush=True)
+        assert rel < 2e-2 and same and same_more and relm < 2e-3
     else:
-        assert same
+        assert same and same_more
     m_dp.release_graphs()
     dist.barrier()
     dist.destroy_process_group()
