@@ -598,7 +598,11 @@ class Model:
         if getattr(self, "_bucket_cache", None) is None:
             self._bucket_cache = {}
         if key not in self._bucket_cache:
-            elems = int(float(os.environ.get("B200_BUCKET_MB", "64")) * (1 << 20) / 4)
+            # 64 MB buckets, or a quarter of the kernel region if that is more: measured on 8 GPUs, the 528 MB of C3's
+            # gradients in 7 buckets of 64 MB scale 0.925 of independent replicas, in 4 buckets of ~130 MB 0.947
+            # (profiles/r02_dp_breakdown_c3_n8_{head,b128}.json): every collective more is a launch + a tail on NCCL's stream
+            auto_mb = max(64.0, self._kernel_region * 4 / (1 << 20) / 4) if self._sharded() else 64.0
+            elems = int(float(os.environ.get("B200_BUCKET_MB", auto_mb)) * (1 << 20) / 4)
             world = self._world()
             if self._sharded():
                 # kernel region: buckets that divide evenly over the ranks (reduce-scatter / sharded Adam / all-gather)
@@ -1046,7 +1050,7 @@ class Model:
         self._finish_gather()
         self._graphs = {}
         torch.cuda.synchronize()
-        if getattr(self, "_peer", None) is not None:      # collective: the ranks unmap each other's buffers together
+        if getattr(self, "_peer", None) is not None:      # back to NCCL for whatever this model still trains
             self._peer.close()
             self._peer = None
 

@@ -126,14 +126,11 @@ class PeerExchange:
         self.ag_events.clear()
 
     def close(self):
-        """Collective: unmap the peers' buffers (every rank must be done with them)."""
+        """Stop using the peers' buffers.  The mappings are NOT unmapped here: cudaIpcCloseMemHandle needs the owning
+        device to quiesce, and a rank that is already past this point may be spinning in a NCCL kernel that waits for the
+        caller -- on 8 GPUs exactly that hung the teardown (profiles/r02_dp_check_n8_p2p.log: five correct steps, then the
+        collective close never returned).  The driver unmaps everything when the process exits."""
         if not self._mapped:
             return
         torch.cuda.synchronize(self.device)
-        self.dist.barrier(group=self.group)
-        lib = ops.lib()
-        for names in self._mapped.values():
-            for ptr in names.values():
-                lib.b200_peer_close(C.c_void_p(ptr))
         self._mapped = {}
-        self.dist.barrier(group=self.group)
