@@ -1,5 +1,6 @@
-"""The ordering protocol of the peer-memory exchange (``Model._run_step_p2p`` + ``peer.py`` + ``csrc/peer.cu``), checked
-on CPU by randomised interleaving.
+"""The ordering of the data-parallel step's exchange, checked on CPU by randomised interleaving: the peer-memory protocol
+(``Model._run_step_p2p`` + ``peer.py`` + ``csrc/peer.cu``) and, further down, the default NCCL schedule (``Model._run_step``:
+reduce-scatter per bucket behind its backward segment, shadow all-gathers overlapping the next forward pass).
 
 The REAL host code of the step (``Model._run_step_p2p``) is run for every rank against stand-ins for the CUDA streams,
 events, captured graphs and the PeerExchange; everything it issues lands in per-rank, per-stream FIFO queues.  A scheduler
@@ -254,6 +255,197 @@ def test_peer_exchange_checker_detects_a_missing_guard(monkeypatch):
     caught = 0
     for seed in range(60):
         sim = Sim(3, 2, steps=4, seed=seed, guard=False)
+        sim.enqueue_all(monkeypatch)
+        try:
+            sim.run()
+        except Violation:
+            caught += 1
+    assert caught > 0
+
+
+# ---- the same check for the default (NCCL) exchange: Model._run_step's segmented branch ---------------------------------
+class Work:
+    def __init__(self, sim, ev):
+        self.sim, self.ev = sim, ev
+
+    def wait(self):
+        self.sim.current().wait_event(self.ev)
+
+
+class Flat:
+    """Stands for the flat G / S tensor: slicing yields (buffer, lo, hi)."""
+
+    def __init__(self, name):
+        self.name = name
+
+    def __getitem__(self, sl):
+        return (self.name, sl.start, sl.stop)
+
+
+class FakeDist:
+    """torch.distributed stand-in with NCCL's stream semantics: the collective is ordered behind everything issued before
+    it on the calling stream, runs on the rank's communication stream, and completes only once every rank has joined it.
+    A rank's buffer is read between its join and its completion: it must not change in that window (lock)."""
+
+    class ReduceOp:
+        SUM, MAX = "sum", "max"
+
+    def __init__(self, ctx):
+        self.ctx = ctx
+
+    def get_rank(self, group=None):
+        return self.ctx.rank
+
+    def get_world_size(self, group=None):
+        return self.ctx.sim.world
+
+    def get_backend(self, group=None):
+        return "nccl"
+
+    def _collective(self, join, finish, what):
+        sim, ctx = self.ctx.sim, self.ctx
+        n = ctx.ncoll
+        ctx.ncoll += 1
+        state = sim.coll.setdefault(n, {"joined": set(), "data": {}})
+        ctx.nccl.wait_event(sim.current().record_event())
+        ctx.nccl.push(lambda: True, lambda: (join(state), state["joined"].add(ctx.rank)), f"join {what}")
+        ctx.nccl.push(lambda: len(state["joined"]) == sim.world, lambda: finish(state), f"finish {what}")
+        return Work(sim, ctx.nccl.record_event())
+
+    def _bucket(self, lo, hi):
+        return [k for k, b in enumerate(self.ctx.sim.buckets) if (b["lo"], b["hi"]) == (lo, hi)][0]
+
+    def reduce_scatter_tensor(self, out, inp, op=None, group=None, async_op=False):
+        sim, r, step = self.ctx.sim, self.ctx.rank, self.ctx.step
+        k = self._bucket(inp[1], inp[2])
+        assert inp[0] == "G" and (out[1], out[2]) == shard_of(sim.buckets[k], r, sim.world)
+
+        def join(state):
+            for s in range(sim.world):
+                if sim.G[r][k][s][0] != step:
+                    raise Violation(f"rank {r} step {step}: reduce-scatter of bucket {k} joins with tag {sim.G[r][k][s][0]}")
+            state["data"][r] = [v for _, v in sim.G[r][k]]
+            sim.locks.add(("G", r, k))
+
+        def finish(state):
+            sim.G[r][k][r] = (("sum", step), sum(state["data"][p][r] for p in range(sim.world)))
+            sim.locks.discard(("G", r, k))
+
+        return self._collective(join, finish, f"reduce_scatter {k}")
+
+    def all_gather_into_tensor(self, out, inp, group=None, async_op=False):
+        sim, r, step = self.ctx.sim, self.ctx.rank, self.ctx.step
+        k = self._bucket(out[1], out[2])
+        assert out[0] == "S" and (inp[1], inp[2]) == shard_of(sim.buckets[k], r, sim.world)
+
+        def join(state):
+            if sim.S[r][k][r] != step:
+                raise Violation(f"rank {r} step {step}: all-gather of bucket {k} joins with own version {sim.S[r][k][r]}")
+            state["data"][r] = step
+            sim.locks.add(("S", r, k))
+            for s in range(sim.world):
+                if s != r:
+                    sim.S[r][k][s] = "in flight"
+
+        def finish(state):
+            for s in range(sim.world):
+                sim.S[r][k][s] = state["data"][s]
+            sim.locks.discard(("S", r, k))
+
+        return self._collective(join, finish, f"all_gather {k}")
+
+    def all_reduce(self, t, op=None, group=None, async_op=False):
+        return self._collective(lambda state: None, lambda state: None, "all_reduce")
+
+
+class NcclSim(Sim):
+    def __init__(self, *a, forward_waits=True, **kw):
+        self.coll, self.locks, self.forward_waits = {}, set(), forward_waits
+        super().__init__(*a, **kw)
+
+    def _rank(self, r, guard):
+        sim, nb, world = self, len(self.buckets) - 1, self.world
+        ctx = types.SimpleNamespace(sim=self, rank=r, step=-1, ncoll=0)
+        ctx.main, ctx.cs, ctx.nccl = Stream(self, r, "main"), Stream(self, r, "unused"), Stream(self, r, "nccl")
+
+        def check_shadow(step, which, ks):
+            for k in ks:
+                for s in range(world):
+                    if sim.S[r][k][s] != step - 1:
+                        raise Violation(f"rank {r} step {step}: {which} reads shadow bucket {k} shard {s}: {sim.S[r][k][s]}")
+
+        def fwd(i, step):
+            if i == 0:
+                for k in range(nb):
+                    if ("G", r, k) in sim.locks:
+                        raise Violation(f"rank {r} step {step}: gradient bucket {k} zeroed under a running reduce-scatter")
+                    sim.G[r][k] = [(("z", step), 0.0)] * world
+            else:
+                check_shadow(step, f"forward segment {i}", [nb - i])
+
+        def bwd(j, step):
+            check_shadow(step, f"backward segment {j}", range(nb))
+            for s in range(world):
+                if sim.G[r][j][s][0] != ("z", step) or ("G", r, j) in sim.locks:
+                    raise Violation(f"rank {r} step {step}: bucket {j} not freshly zeroed / in use ({sim.G[r][j][s][0]})")
+                sim.G[r][j][s] = (step, sim.grad(r, j, s, step))
+
+        def adam(step):
+            for k in range(nb):
+                tag, val = sim.G[r][k][r]
+                want = sum(sim.grad(p, k, r, step) for p in range(world))
+                if tag != ("sum", step) or val != want or ("S", r, k) in sim.locks:
+                    raise Violation(f"rank {r} step {step}: Adam sees bucket {k} tag {tag} value {val}, wanted {want}")
+                sim.S[r][k][r] = step
+
+        plan = object()
+        entry = {"plan": plan, "graph": None,
+                 "fsegs": [(Graph(ctx, lambda step, i=i: fwd(i, step), f"fwd {i}"),
+                            [nb - i] if i and sim.forward_waits else []) for i in range(nb + 1)],
+                 "segments": [(Graph(ctx, lambda step, j=j: bwd(j, step), f"bwd {j}"),
+                               [self.buckets[j]] + ([self.buckets[nb]] if j == nb - 1 else [])) for j in range(nb)],
+                 "adam_graph": Graph(ctx, adam, "adam"),
+                 "ag_order": [nb - i for i in range(1, nb + 1)]}
+        model = types.SimpleNamespace(_peer=None, _ag_works=None, G=Flat("G"), S=Flat("S"), P=object(),
+                                      _dist=(FakeDist(ctx), None), _buckets=lambda _plan: sim.buckets,
+                                      _sharded=lambda: True, _check_finite=lambda: None)
+        for name in ("_run_step", "_finish_gather", "_gather_updated", "_reduce_async"):
+            setattr(model, name, types.MethodType(getattr(Model, name), model))
+        ctx.model, ctx.entry = model, entry
+        ctx.run_step = lambda: model._run_step(entry)
+        return ctx
+
+    def enqueue_all(self, monkeypatch):
+        monkeypatch.setattr(torch.cuda, "current_stream", lambda *a, **k: self._cur)
+        for ctx in self.ranks:
+            for step in range(self.steps):
+                ctx.step = step
+                self._cur = ctx.main
+                ctx.run_step()
+        self._cur = None
+
+    def run(self):
+        for ctx in self.ranks:
+            ctx.cs = ctx.nccl                        # the scheduler walks (main, cs): make the second one NCCL's stream
+        super().run()
+
+
+@pytest.mark.parametrize("world,n_buckets", [(2, 1), (2, 3), (4, 3), (8, 4)])
+def test_nccl_exchange_ordering_is_safe_under_random_interleavings(monkeypatch, world, n_buckets):
+    monkeypatch.delenv("B200_DP_OVERLAP_GATHER", raising=False)
+    for seed in range(30 if world < 8 else 8):
+        sim = NcclSim(world, n_buckets, steps=4, seed=seed)
+        sim.enqueue_all(monkeypatch)
+        sim.run()
+
+
+def test_nccl_exchange_checker_detects_a_forward_pass_that_does_not_wait(monkeypatch):
+    """If the forward segments did not wait for the all-gather of the bucket they read, some interleaving reads a shard
+    that is still in flight."""
+    monkeypatch.delenv("B200_DP_OVERLAP_GATHER", raising=False)
+    caught = 0
+    for seed in range(40):
+        sim = NcclSim(3, 2, steps=4, seed=seed, forward_waits=False)
         sim.enqueue_all(monkeypatch)
         try:
             sim.run()
